@@ -1,0 +1,130 @@
+"""Seeded synthetic weights and inputs for the decoder (no checkpoints ship with the reference).
+
+`decoder_param_shapes` lists every tensor of `Diffusion.state_dict()` in the reference's own
+order and naming (model/diffusion.py:128-172, 227-242); `make_decoder_state_dict` fills them
+from a CPU `torch.Generator`, so the same seed gives the same weights in the build container
+(where the golden fixtures are made with the real reference) and on the GPU box.
+"""
+import math
+
+import torch
+
+DIM = 64
+DIM_MULTS = (1, 2, 4)
+N_FEATS = 80
+SPK_EMB_DIM = 64
+
+
+def _resnet_shapes(p, cin, cout, tdim=DIM):
+    s = [(p + ".mlp.1.weight", (cout, tdim)), (p + ".mlp.1.bias", (cout,))]
+    for blk, ci in (("block1", cin), ("block2", cout)):
+        s += [(f"{p}.{blk}.block.0.weight", (cout, ci, 3, 3)), (f"{p}.{blk}.block.0.bias", (cout,)),
+              (f"{p}.{blk}.block.1.weight", (cout,)), (f"{p}.{blk}.block.1.bias", (cout,))]
+    if cin != cout:
+        s += [(p + ".res_conv.weight", (cout, cin, 1, 1)), (p + ".res_conv.bias", (cout,))]
+    return s
+
+
+def _attn_shapes(p, c):
+    return [(p + ".fn.g", (1,)), (p + ".fn.fn.to_qkv.weight", (384, c, 1, 1)),
+            (p + ".fn.fn.to_out.weight", (c, 128, 1, 1)), (p + ".fn.fn.to_out.bias", (c,))]
+
+
+def decoder_param_shapes(n_spks=1, pfx="estimator."):
+    """(name, shape) for every tensor in the reference `Diffusion.state_dict()`, in order."""
+    s = []
+    if n_spks > 1 or n_spks == -1:
+        s += [("spk_mlp.0.weight", (SPK_EMB_DIM * 4, SPK_EMB_DIM)), ("spk_mlp.0.bias", (SPK_EMB_DIM * 4,)),
+              ("spk_mlp.2.weight", (N_FEATS, SPK_EMB_DIM * 4)), ("spk_mlp.2.bias", (N_FEATS,))]
+    s += [("mlp.0.weight", (DIM * 4, DIM)), ("mlp.0.bias", (DIM * 4,)),
+          ("mlp.2.weight", (DIM, DIM * 4)), ("mlp.2.bias", (DIM,))]
+    dims = [2 + (1 if n_spks > 1 else 0)] + [DIM * m for m in DIM_MULTS]
+    in_out = list(zip(dims[:-1], dims[1:]))
+    for i, (ci, co) in enumerate(in_out):
+        s += _resnet_shapes(f"downs.{i}.0", ci, co)
+        s += _resnet_shapes(f"downs.{i}.1", co, co)
+        s += _attn_shapes(f"downs.{i}.2", co)
+        if i < len(in_out) - 1:
+            s += [(f"downs.{i}.3.conv.weight", (co, co, 3, 3)), (f"downs.{i}.3.conv.bias", (co,))]
+    ups = []
+    for i, (ci, co) in enumerate(reversed(in_out[1:])):
+        ups += _resnet_shapes(f"ups.{i}.0", co * 2, ci)
+        ups += _resnet_shapes(f"ups.{i}.1", ci, ci)
+        ups += _attn_shapes(f"ups.{i}.2", ci)
+        ups += [(f"ups.{i}.3.conv.weight", (ci, ci, 4, 4)), (f"ups.{i}.3.conv.bias", (ci,))]
+    s += ups
+    mid = dims[-1]
+    s += _resnet_shapes("mid_block1", mid, mid)
+    s += _attn_shapes("mid_attn", mid)
+    s += _resnet_shapes("mid_block2", mid, mid)
+    s += _resnet_shapes_block("final_block", DIM, DIM)
+    s += [("final_conv.weight", (1, DIM, 1, 1)), ("final_conv.bias", (1,))]
+    return [(pfx + n, sh) for n, sh in s]
+
+
+def _resnet_shapes_block(p, cin, cout):
+    return [(f"{p}.block.0.weight", (cout, cin, 3, 3)), (f"{p}.block.0.bias", (cout,)),
+            (f"{p}.block.1.weight", (cout,)), (f"{p}.block.1.bias", (cout,))]
+
+
+def make_decoder_state_dict(n_spks=1, seed=0, g=0.05, pfx="estimator."):
+    """Random weights at PyTorch-default-like scale; GroupNorm affine and Rezero `g` perturbed so
+    that every term of the maths is exercised (default init has g=0, gamma=1, beta=0)."""
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(seed)
+    sd = {}
+    for name, shape in decoder_param_shapes(n_spks, pfx):
+        if name.endswith(".fn.g"):
+            v = torch.full(shape, float(g))
+        elif ".block.1.weight" in name:                       # GroupNorm gamma
+            v = 1.0 + 0.1 * torch.randn(shape, generator=gen)
+        elif ".block.1.bias" in name:                         # GroupNorm beta
+            v = 0.1 * torch.randn(shape, generator=gen)
+        else:
+            if len(shape) == 1:
+                # bias of the layer just created: fan_in of the matching weight
+                fan_in = sd[name.replace(".bias", ".weight")][0].numel()
+                if ".3.conv." in name and name.startswith(pfx + "ups"):
+                    w = sd[name.replace(".bias", ".weight")]   # ConvTranspose2d: fan_in = Cout*kh*kw
+                    fan_in = w.shape[1] * w.shape[2] * w.shape[3]
+            else:
+                fan_in = math.prod(shape[1:])
+            bound = 1.0 / math.sqrt(fan_in)
+            v = (torch.rand(shape, generator=gen) * 2.0 - 1.0) * bound
+        sd[name] = v.float().contiguous()
+    return sd
+
+
+def make_inputs(B, T, n_spks=1, seed=1, ragged=True, temperature=1.5):
+    """mu ~ N(0,1), z = mu + N(0,1)/temperature, prefix mask with lengths U[0.6T, T] (item 0 full)."""
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(seed)
+    mu = torch.randn(B, N_FEATS, T, generator=gen)
+    z = mu + torch.randn(B, N_FEATS, T, generator=gen) / temperature
+    if ragged:
+        lengths = torch.randint(int(0.6 * T), T + 1, (B,), generator=gen)
+        lengths[0] = T
+    else:
+        lengths = torch.full((B,), T, dtype=torch.long)
+    mask = (torch.arange(T)[None, :] < lengths[:, None]).float().unsqueeze(1)   # (B,1,T)
+    spk = torch.randn(B, SPK_EMB_DIM, generator=gen) if (n_spks > 1) else None
+    return z.contiguous(), mask.contiguous(), mu.contiguous(), spk, lengths
+
+
+def make_mas_inputs(B, t_x, t_y, seed=1234, ragged=True):
+    """value = 5*N(0,1) - 40 (log-prior-like), prefix masks with t_x~U[t_x/2,t_x], t_y~U[0.6t_y,t_y]."""
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(seed)
+    value = 5.0 * torch.randn(B, t_x, t_y, generator=gen) - 40.0
+    if ragged:
+        tx = torch.randint(max(1, t_x // 2), t_x + 1, (B,), generator=gen)
+        ty = torch.randint(max(1, int(0.6 * t_y)), t_y + 1, (B,), generator=gen)
+        tx[0], ty[0] = t_x, t_y
+        tx = torch.minimum(tx, ty)
+    else:
+        tx = torch.full((B,), t_x, dtype=torch.long)
+        ty = torch.full((B,), t_y, dtype=torch.long)
+    xm = (torch.arange(t_x)[None, :] < tx[:, None]).float()
+    ym = (torch.arange(t_y)[None, :] < ty[:, None]).float()
+    mask = xm[:, :, None] * ym[:, None, :]
+    return value.contiguous(), mask.contiguous(), tx, ty

@@ -1,0 +1,88 @@
+"""CPU: the oracle restatements reproduce the golden fixtures made by the real reference."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import build_oracle, decoder_oracle, mas_oracle
+
+
+def _load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+DEC = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
+             if os.path.basename(p).startswith(("est_", "dec_")))
+MAS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "mas_*.npz")))
+
+
+def golden_path(g, B, tx, ty):
+    idx = g["idx"].astype(np.int64)
+    path = np.zeros((B, tx, ty), dtype=np.int32)
+    b, y = np.nonzero(idx >= 0)
+    path[b, idx[b, y], y] = 1
+    return path
+
+
+@pytest.mark.parametrize("name", DEC)
+def test_decoder_oracle_matches_reference(name, synth):
+    torch.set_num_threads(8)
+    g = _load(name)
+    n_spks, n_steps = int(g["n_spks"]), int(g["n_steps"])
+    sd = synth.make_decoder_state_dict(n_spks, seed=int(g["wseed"]), g=0.05)
+    z, mask, mu = (torch.from_numpy(g[k]) for k in ("z", "mask", "mu"))
+    spk = torch.from_numpy(g["spk"]) if "spk" in g else None
+    with torch.no_grad():
+        if n_steps == 0:
+            y = decoder_oracle.estimator_forward(sd, z * mask, mask, mu, torch.from_numpy(g["t"]), spk, n_spks)
+        else:
+            y = decoder_oracle.reverse_diffusion(sd, z, mask, mu, n_steps, True, spk, n_spks)
+    ref = torch.from_numpy(g["y"])
+    # same ATen kernels, same thread count: tolerance covers only op-order noise (|y|max up to ~140)
+    tol = 2e-5 * max(1.0, float(ref.abs().max()))
+    assert float((y - ref).abs().max()) <= tol
+
+
+def test_synth_weights_are_reproducible(synth):
+    import hashlib
+    g = _load("dec_spk1_b1_t64_n10")
+    sd = synth.make_decoder_state_dict(1, seed=int(g["wseed"]), g=0.05)
+    h = hashlib.sha256()
+    for k in sd:
+        h.update(k.encode())
+        h.update(sd[k].numpy().tobytes())
+    assert h.hexdigest() == str(g["sd_sha256"])
+
+
+@pytest.mark.parametrize("name", MAS)
+def test_mas_oracle_matches_reference_golden(name, synth):
+    g = _load(name)
+    B, tx, ty = (int(v) for v in g["shape"])
+    value, mask, txs, tys = synth.make_mas_inputs(B, tx, ty, seed=int(g["seed"]), ragged=bool(g["ragged"]))
+    assert abs(float(value.double().sum()) - float(g["value_sum"])) < 1e-6 * abs(float(g["value_sum"]))
+    path = mas_oracle.maximum_path(value, mask)
+    assert path.dtype == value.dtype
+    assert np.array_equal(path.numpy().astype(np.int32), golden_path(g, B, tx, ty))
+
+
+def test_mas_oracle_matches_compiled_reference(synth):
+    """oracle/_ref = the reference's own core.pyx compiled here; skipped where it is absent."""
+    build_oracle.build_ref()
+    ref = build_oracle.load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (no /root/reference on this box)")
+    rng = np.random.default_rng(0)
+    for B, tx, ty in [(3, 7, 7), (4, 1, 5), (6, 17, 40), (2, 50, 300)]:
+        value = (5 * rng.standard_normal((B, tx, ty)) - 40).astype(np.float32)
+        txs = rng.integers(1, tx + 1, B).astype(np.int32)
+        tys = np.maximum(rng.integers(1, ty + 1, B), txs).astype(np.int32)
+        v1, v2 = value.copy(), value.copy()
+        p1 = np.zeros_like(value, dtype=np.int32)
+        p2 = np.zeros_like(value, dtype=np.int32)
+        ref.maximum_path_c(p1, v1, txs, tys)
+        mas_oracle.maximum_path_c(p2, v2, txs, tys)
+        assert np.array_equal(p1, p2)
+        assert np.array_equal(v1, v2)          # the in-place DP table is bit-identical too
