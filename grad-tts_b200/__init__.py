@@ -1,0 +1,17 @@
+"""B200-native Grad-TTS hot path: reverse-diffusion mel decoder + Monotonic Alignment Search.
+
+Drop-in Python surface (same names and signatures as the reference's `model/` package):
+    GradTTS.forward(x, x_lengths, n_timesteps, temperature, stoc, spk, length_scale)
+    Diffusion.forward / reverse_diffusion(z, mask, mu, n_timesteps, stoc, spk)
+    GradLogPEstimator2d.forward(x, mask, mu, t, spk)
+    monotonic_align.maximum_path(value, mask)
+All arithmetic of those calls runs in hand-written sm_100a kernels behind the C ABI declared in
+include/gradtts_b200.h (libgradtts_b200.so); this package is only the host-side mirror.
+"""
+from . import _lib, synth  # noqa: F401
+from .model import GradTTS  # noqa: F401
+from .model.diffusion import Diffusion, GradLogPEstimator2d  # noqa: F401
+from .model.monotonic_align import maximum_path  # noqa: F401
+from . import dist  # noqa: F401
+
+__all__ = ["GradTTS", "Diffusion", "GradLogPEstimator2d", "maximum_path", "synth", "dist"]

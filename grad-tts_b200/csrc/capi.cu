@@ -1,0 +1,271 @@
+// extern "C" surface declared in include/gradtts_b200.h.
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/gradtts_b200.h"
+#include "common.cuh"
+#include "decoder_api.h"
+#include "ops.h"
+
+namespace gtts {
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace gtts
+
+using namespace gtts;
+
+struct gtts_decoder {
+    Decoder* impl;
+    // staging for the host-buffer entry point
+    float *z = nullptr, *mask = nullptr, *mu = nullptr, *spk = nullptr, *out = nullptr;
+    size_t cap_plane = 0, cap_mask = 0, cap_spk = 0;
+    cudaStream_t stream = nullptr;
+};
+
+extern "C" {
+
+int gtts_version(void) { return 100; }
+
+const char* gtts_last_error(void) { return g_last_error.c_str(); }
+
+int gtts_sm100_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int c = 0;
+    for (int i = 0; i < n; ++i) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ++c;
+    }
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------ MAS
+size_t gtts_mas_workspace_bytes(int B, int t_x, int t_y) { return mas_bits_workspace_bytes(B, t_x, t_y); }
+
+int gtts_mas_maximum_path(const float* value, const float* mask, float* path, int B, int t_x, int t_y, void* bits_ws,
+                          size_t bits_ws_bytes, int32_t* status, void* stream) {
+    GTTS_REQUIRE(value && mask && path && status, "maximum_path: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    GTTS_CHECK_CUDA(cudaMemsetAsync(path, 0, (size_t)B * t_x * t_y * sizeof(float), s));
+    GTTS_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
+    return mas_forward_f32(value, mask, nullptr, nullptr, path, B, t_x, t_y, -1e9f, (uint32_t*)bits_ws, bits_ws_bytes,
+                           status, s);
+}
+
+int gtts_mas_maximum_path_c(int32_t* paths, const float* values, const int32_t* t_xs, const int32_t* t_ys, int B,
+                            int t_x, int t_y, float max_neg_val, void* bits_ws, size_t bits_ws_bytes,
+                            int32_t* status, void* stream) {
+    GTTS_REQUIRE(paths && values && t_xs && t_ys && status, "maximum_path_c: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    GTTS_CHECK_CUDA(cudaMemsetAsync(paths, 0, (size_t)B * t_x * t_y * sizeof(int32_t), s));
+    GTTS_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
+    return mas_forward_i32(values, nullptr, t_xs, t_ys, paths, B, t_x, t_y, max_neg_val, (uint32_t*)bits_ws,
+                           bits_ws_bytes, status, s);
+}
+
+int gtts_mas_maximum_path_host(const float* value_host, const float* mask_host, float* path_host, int B, int t_x,
+                               int t_y, int32_t* status_host, int device) {
+    GTTS_REQUIRE(value_host && mask_host && path_host && status_host, "maximum_path_host: null pointer");
+    GTTS_CHECK_CUDA(cudaSetDevice(device));
+    const size_t n = (size_t)B * t_x * t_y;
+    float *dv = nullptr, *dm = nullptr, *dp = nullptr;
+    int32_t* ds = nullptr;
+    void* ws = nullptr;
+    const size_t wsb = mas_bits_workspace_bytes(B, t_x, t_y);
+    cudaStream_t s;
+    GTTS_CHECK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    int rc = 0;
+    auto cleanup = [&]() {
+        cudaFree(dv); cudaFree(dm); cudaFree(dp); cudaFree(ds); cudaFree(ws);
+        cudaStreamDestroy(s);
+    };
+#define GTTS_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); cleanup(); return 1; } } while (0)
+    GTTS_TRY(cudaMalloc(&dv, n * 4));
+    GTTS_TRY(cudaMalloc(&dm, n * 4));
+    GTTS_TRY(cudaMalloc(&dp, n * 4));
+    GTTS_TRY(cudaMalloc(&ds, 4));
+    if (wsb) GTTS_TRY(cudaMalloc(&ws, wsb));
+    GTTS_TRY(cudaMemcpyAsync(dv, value_host, n * 4, cudaMemcpyHostToDevice, s));
+    GTTS_TRY(cudaMemcpyAsync(dm, mask_host, n * 4, cudaMemcpyHostToDevice, s));
+    rc = gtts_mas_maximum_path(dv, dm, dp, B, t_x, t_y, ws, wsb, ds, s);
+    if (rc) { cleanup(); return rc; }
+    GTTS_TRY(cudaMemcpyAsync(path_host, dp, n * 4, cudaMemcpyDeviceToHost, s));
+    GTTS_TRY(cudaMemcpyAsync(status_host, ds, 4, cudaMemcpyDeviceToHost, s));
+    GTTS_TRY(cudaStreamSynchronize(s));
+#undef GTTS_TRY
+    cleanup();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ decoder
+int gtts_decoder_create(gtts_decoder** out, int n_spks, int n_feats, int dim, double beta_min, double beta_max,
+                        double pe_scale, int device) {
+    GTTS_REQUIRE(out != nullptr, "null out pointer");
+    Decoder* d = decoder_new(n_spks, n_feats, dim, beta_min, beta_max, pe_scale, device);
+    if (!d) return 1;
+    gtts_decoder* h = new gtts_decoder();
+    h->impl = d;
+    *out = h;
+    return 0;
+}
+
+void gtts_decoder_destroy(gtts_decoder* h) {
+    if (!h) return;
+    cudaSetDevice(decoder_device(h->impl));
+    cudaFree(h->z); cudaFree(h->mask); cudaFree(h->mu); cudaFree(h->spk); cudaFree(h->out);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    decoder_delete(h->impl);
+    delete h;
+}
+
+int gtts_decoder_set_param(gtts_decoder* h, const char* name, const float* data, size_t numel) {
+    GTTS_REQUIRE(h != nullptr, "null decoder handle");
+    return decoder_set_param(h->impl, name, data, numel);
+}
+
+int gtts_decoder_set_option(gtts_decoder* h, const char* key, int value) {
+    GTTS_REQUIRE(h != nullptr, "null decoder handle");
+    return decoder_set_option(h->impl, key, value);
+}
+
+int gtts_decoder_reverse_diffusion(gtts_decoder* h, const float* z, const float* mask, const float* mu,
+                                   const float* spk, float* out, int B, int T, int n_timesteps, int flags,
+                                   const float* noise, void* stream) {
+    GTTS_REQUIRE(h && z && mask && mu && out, "reverse_diffusion: null pointer");
+    return decoder_reverse_diffusion(h->impl, z, mask, mu, spk, out, B, T, n_timesteps, flags, noise,
+                                     (cudaStream_t)stream);
+}
+
+int gtts_decoder_estimator(gtts_decoder* h, const float* x, const float* mask, const float* mu, const float* t,
+                           const float* spk, float* out, int B, int T, int flags, void* stream) {
+    GTTS_REQUIRE(h && x && mask && mu && t && out, "estimator: null pointer");
+    return decoder_estimator(h->impl, x, mask, mu, t, spk, out, B, T, flags, (cudaStream_t)stream);
+}
+
+int gtts_decoder_reverse_diffusion_host(gtts_decoder* h, const float* z_host, const float* mask_host,
+                                        const float* mu_host, const float* spk_host, float* out_host, int B, int T,
+                                        int n_timesteps, int flags) {
+    GTTS_REQUIRE(h && z_host && mask_host && mu_host && out_host, "reverse_diffusion_host: null pointer");
+    GTTS_REQUIRE((flags & GTTS_FLAG_SDE) == 0, "reverse_diffusion_host: SDE noise is not supported on this entry");
+    GTTS_CHECK_CUDA(cudaSetDevice(decoder_device(h->impl)));
+    const size_t plane = (size_t)B * 80 * T, nmask = (size_t)B * T, nspk = (size_t)B * 64;
+    if (!h->stream) GTTS_CHECK_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if (plane > h->cap_plane) {
+        cudaFree(h->z); cudaFree(h->mu); cudaFree(h->out);
+        h->z = h->mu = h->out = nullptr; h->cap_plane = 0;
+        GTTS_CHECK_CUDA(cudaMalloc(&h->z, plane * 4));
+        GTTS_CHECK_CUDA(cudaMalloc(&h->mu, plane * 4));
+        GTTS_CHECK_CUDA(cudaMalloc(&h->out, plane * 4));
+        h->cap_plane = plane;
+    }
+    if (nmask > h->cap_mask) {
+        cudaFree(h->mask); h->mask = nullptr; h->cap_mask = 0;
+        GTTS_CHECK_CUDA(cudaMalloc(&h->mask, nmask * 4));
+        h->cap_mask = nmask;
+    }
+    if (spk_host && nspk > h->cap_spk) {
+        cudaFree(h->spk); h->spk = nullptr; h->cap_spk = 0;
+        GTTS_CHECK_CUDA(cudaMalloc(&h->spk, nspk * 4));
+        h->cap_spk = nspk;
+    }
+    cudaStream_t s = h->stream;
+    GTTS_CHECK_CUDA(cudaMemcpyAsync(h->z, z_host, plane * 4, cudaMemcpyHostToDevice, s));
+    GTTS_CHECK_CUDA(cudaMemcpyAsync(h->mu, mu_host, plane * 4, cudaMemcpyHostToDevice, s));
+    GTTS_CHECK_CUDA(cudaMemcpyAsync(h->mask, mask_host, nmask * 4, cudaMemcpyHostToDevice, s));
+    if (spk_host) GTTS_CHECK_CUDA(cudaMemcpyAsync(h->spk, spk_host, nspk * 4, cudaMemcpyHostToDevice, s));
+    if (int rc = decoder_reverse_diffusion(h->impl, h->z, h->mask, h->mu, spk_host ? h->spk : nullptr, h->out, B, T,
+                                           n_timesteps, flags, nullptr, s))
+        return rc;
+    GTTS_CHECK_CUDA(cudaMemcpyAsync(out_host, h->out, plane * 4, cudaMemcpyDeviceToHost, s));
+    GTTS_CHECK_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+long gtts_decoder_launches_last_call(const gtts_decoder* h) { return h ? decoder_launches_last_call(h->impl) : 0; }
+
+// ------------------------------------------------------------------------------------------------ test hooks
+int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, int Cin1, int Cout, const void* src0,
+                   const void* src1, const float* weight_pt, const float* bias, const void* residual,
+                   const float* mask, void* out, float* gn_stats, int per_sample_weights, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const ActKind ak = act ? ACT_BF16 : ACT_F32;
+    GTTS_REQUIRE(impl == 0 || ak == ACT_BF16, "tcgen05 conv needs bf16 activations");
+    const int Cin = Cin0 + Cin1;
+    ConvGeom g;
+    memset(&g, 0, sizeof(g));
+    g.B = B; g.Hin = H; g.Win = W; g.Hg = H; g.Wg = W; g.Hout = H; g.Wout = W;
+    g.Cin0 = Cin0; g.Cin1 = Cin1; g.Cout = Cout; g.ntaps = 1; g.nphase = 1; g.stride = 1; g.out_step = 1;
+    size_t wrows = Cout;
+    const size_t es = ak == ACT_F32 ? 4 : 2;
+    void* wpk = nullptr;
+    if (kind == 0 || kind == 2) {
+        g.ntaps = 9;
+        for (int t = 0; t < 9; ++t) { g.dy[0][t] = (int8_t)(t / 3 - 1); g.dx[0][t] = (int8_t)(t % 3 - 1); g.wrow[0][t] = t * Cout; }
+        if (kind == 2) { g.stride = 2; g.Hg = H / 2; g.Wg = W / 2; g.Hout = H / 2; g.Wout = W / 2; }
+        wrows = (size_t)9 * Cout;
+        GTTS_CHECK_CUDA(cudaMalloc(&wpk, wrows * Cin * es));
+        if (int rc = pack_conv_weight(ak, weight_pt, wpk, Cout, Cin, 3, 3, s)) return rc;
+    } else if (kind == 1) {
+        if (per_sample_weights) { g.w_batch_rows = Cout; wrows = (size_t)B * Cout; }
+        GTTS_CHECK_CUDA(cudaMalloc(&wpk, wrows * Cin * es));
+        // (rows, Cin, 1, 1) is already row-major [rows][Cin]
+        if (int rc = pack_conv_weight(ak, weight_pt, wpk, (int)wrows, Cin, 1, 1, s)) return rc;
+    } else if (kind == 3) {
+        GTTS_REQUIRE(Cin1 == 0 && Cin0 == Cout, "convT test: Cin must equal Cout");
+        g.ntaps = 4; g.nphase = 4; g.out_step = 2; g.Hout = 2 * H; g.Wout = 2 * W;
+        const int dd[2][2] = {{0, -1}, {0, 1}};
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+                const int ph = py * 2 + px;
+                g.oy[ph] = py; g.ox[ph] = px;
+                for (int ty = 0; ty < 2; ++ty)
+                    for (int tx = 0; tx < 2; ++tx) {
+                        const int t = ty * 2 + tx;
+                        g.dy[ph][t] = (int8_t)dd[py][ty]; g.dx[ph][t] = (int8_t)dd[px][tx];
+                        g.wrow[ph][t] = (ph * 4 + t) * Cout;
+                    }
+            }
+        wrows = (size_t)16 * Cout;
+        GTTS_CHECK_CUDA(cudaMalloc(&wpk, wrows * Cin * es));
+        if (int rc = pack_convT_weight(ak, weight_pt, wpk, Cout, s)) return rc;
+    } else {
+        set_error("gtts_test_conv: unknown kind");
+        return 2;
+    }
+    ConvEpilogue e;
+    memset(&e, 0, sizeof(e));
+    e.bias = bias; e.residual = residual; e.mask = mask; e.out = out;
+    float* partials = nullptr;
+    unsigned int* counters = nullptr;
+    if (gn_stats) {
+        const size_t slots = impl == 1 ? conv_tc_partials_slots(g) : conv_ffma_partials_slots(g);
+        GTTS_CHECK_CUDA(cudaMalloc(&partials, (size_t)B * slots * 16 * 4));
+        GTTS_CHECK_CUDA(cudaMalloc(&counters, (size_t)B * 4));
+        GTTS_CHECK_CUDA(cudaMemsetAsync(counters, 0, (size_t)B * 4, s));
+        e.gn_partials = partials; e.gn_stats = gn_stats; e.gn_counters = counters; e.gn_eps = 1e-5f;
+    }
+    int rc = 0;
+    if (impl == 1) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        TcConvPlan* tp = conv_tc_plan_create(g, src0, src1, wpk, (int)wrows, e, sms);
+        if (!tp) rc = 1;
+        else {
+            rc = conv_tc_launch(tp, s);
+            cudaStreamSynchronize(s);
+            conv_tc_plan_destroy(tp);
+        }
+    } else {
+        rc = conv_ffma(ak, g, src0, src1, wpk, e, s);
+    }
+    cudaError_t ce = cudaStreamSynchronize(s);
+    cudaFree(wpk); cudaFree(partials); cudaFree(counters);
+    if (rc) return rc;
+    GTTS_CHECK_CUDA(ce);
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

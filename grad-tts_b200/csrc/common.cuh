@@ -1,0 +1,256 @@
+// Shared device/host helpers for the sm_100a Grad-TTS decoder kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace gtts {
+
+// ---------------------------------------------------------------- host error plumbing
+void set_error(const std::string& msg);          // defined in capi.cu
+#define GTTS_CHECK_CUDA(expr)                                                                  \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            ::gtts::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) +      \
+                              " at " + __FILE__ + ":" + std::to_string(__LINE__));             \
+            return 1;                                                                          \
+        }                                                                                      \
+    } while (0)
+#define GTTS_REQUIRE(cond, msg)                                                                \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            ::gtts::set_error(std::string(msg) + " (" #cond ") at " + __FILE__ + ":" +         \
+                              std::to_string(__LINE__));                                       \
+            return 2;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+// ---------------------------------------------------------------- activation element types
+template <typename T> struct Act;
+template <> struct Act<float> {
+    static constexpr int kBytes = 4;
+    __device__ __forceinline__ static void load8(const float* p, float (&v)[8]) {
+        float4 a = *reinterpret_cast<const float4*>(p);
+        float4 b = *reinterpret_cast<const float4*>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    __device__ __forceinline__ static void store8(float* p, const float (&v)[8]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    __device__ __forceinline__ static float ld(const float* p) { return *p; }
+    __device__ __forceinline__ static void st(float* p, float v) { *p = v; }
+};
+template <> struct Act<__nv_bfloat16> {
+    static constexpr int kBytes = 2;
+    __device__ __forceinline__ static void load8(const __nv_bfloat16* p, float (&v)[8]) {
+        uint4 u = *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[2 * i]     = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    __device__ __forceinline__ static void store8(__nv_bfloat16* p, const float (&v)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    __device__ __forceinline__ static float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+    __device__ __forceinline__ static void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// ---------------------------------------------------------------- maths
+// Mish = x * tanh(softplus(x)), torch softplus(beta=1, threshold=20)  (reference model/diffusion.py:16-18)
+template <bool kStrict>
+__device__ __forceinline__ float mish(float x) {
+    if (kStrict) {
+        float sp = (x > 20.0f) ? x : log1pf(expf(x));
+        return x * tanhf(sp);
+    } else {
+        // tanh(log(1+e^x)) = n/(n+2) with n = e^x (e^x + 2); exact algebra, one ex2 + one rcp
+        if (x > 20.0f) return x;
+        float e = __expf(x);
+        float n = e * (e + 2.0f);
+        return x * __fdividef(n, n + 2.0f);
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------- GroupNorm statistics protocol
+// A conv kernel writes, for every (sample b, tile slot s), 16 floats: sum[8 groups], sumsq[8 groups]
+// into partials[(b*slots + s)*16 ...]; the last tile of a sample to finish (ticket on counters[b])
+// reduces all slots in a fixed order (deterministic, double accumulation) and writes
+// stats[b][g] = {mean, rstd}.  `nthreads` threads of the CTA (ids 0..nthreads-1, nthreads>=16,
+// multiple of 16, <=256) call this together; `sync` is a barrier over exactly those threads.
+struct GnStatsOut {
+    float* partials;        // [B][slots][16]
+    float* stats;           // [B][8][2]
+    unsigned int* counters; // [B], zero on entry, zero again on exit
+    int slots;              // tiles contributing per sample
+    float inv_count;        // 1 / ((C/8)*H*W)
+    float eps;
+};
+
+template <typename SyncFn>
+__device__ __forceinline__ void gn_stats_publish(const GnStatsOut& o, int b, int slot, int tid, int nthreads,
+                                                 const float* tile_vals16 /*smem, valid for tid<16*/,
+                                                 double* s_red /*smem [16][16]*/, int* s_flag, SyncFn sync) {
+    if (tid < 16) {
+        o.partials[((size_t)b * o.slots + slot) * 16 + tid] = tile_vals16[tid];
+        __threadfence();
+    }
+    sync();
+    if (tid == 0) {
+        __threadfence();
+        unsigned int old = atomicAdd(&o.counters[b], 1u);
+        *s_flag = (old == (unsigned int)(o.slots - 1));
+    }
+    sync();
+    if (*s_flag) {
+        __threadfence();
+        const int k = tid & 15, slice = tid >> 4, nslice = nthreads >> 4;
+        double acc = 0.0;
+        const float* p = o.partials + (size_t)b * o.slots * 16;
+        for (int s = slice; s < o.slots; s += nslice) acc += (double)__ldcg(p + (size_t)s * 16 + k);
+        s_red[slice * 16 + k] = acc;
+        sync();
+        if (tid < 8) {
+            double sum = 0.0, sq = 0.0;
+            for (int s = 0; s < nslice; ++s) { sum += s_red[s * 16 + tid]; sq += s_red[s * 16 + 8 + tid]; }
+            double mean = sum * (double)o.inv_count;
+            double var = sq * (double)o.inv_count - mean * mean;
+            if (var < 0.0) var = 0.0;
+            o.stats[((size_t)b * 8 + tid) * 2 + 0] = (float)mean;
+            o.stats[((size_t)b * 8 + tid) * 2 + 1] = (float)(1.0 / sqrt(var + (double)o.eps));
+        }
+        if (tid == 0) o.counters[b] = 0u;
+    }
+    sync();
+}
+
+// ---------------------------------------------------------------- sm_100a PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const void* desc, uint64_t* bar, void* smem, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const void* desc, uint64_t* bar, void* smem, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(const void* desc, uint64_t* bar, void* smem, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+
+// tcgen05 / TMEM
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 x bf16 -> f32)
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 columns of fp32: thread i of the warp gets row (lane base + i), 32 consecutive columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+}  // namespace gtts

@@ -1,0 +1,836 @@
+// Decoder scheduler: owns the weights (reference state_dict names), packs them per precision mode, builds a
+// per-(batch, T) plan = workspace + ordered kernel list for one GradLogPEstimator2d evaluation fused with the
+// Euler update, captures it in a CUDA graph and replays it n_timesteps times.
+//
+// Reference: Diffusion.reverse_diffusion (model/diffusion.py:254-268), GradLogPEstimator2d (:128-216).
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "decoder_api.h"
+#include "ops.h"
+
+namespace gtts {
+
+namespace {
+
+__global__ void schedule_kernel(float* t_tab, float* beta_tab, float* h_out, int n, double beta_min,
+                                double beta_max) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *h_out = (float)(1.0 / (double)n);          // dxt * noise_t * h: python float -> fp32 (:266)
+    if (i >= n) return;
+    // h = 1.0 / n ; t = float(1.0 - (i + 0.5) * h)                               (:256,259)
+    double h = 1.0 / (double)n;
+    float t = (float)(1.0 - ((double)i + 0.5) * h);
+    // noise_t = beta_min + (beta_max - beta_min) * t   (python scalars cast to fp32) (:219-224,262)
+    float bt = __fadd_rn((float)beta_min, __fmul_rn((float)(beta_max - beta_min), t));
+    t_tab[i] = t;
+    beta_tab[i] = bt;
+}
+
+__global__ void scale_vec_kernel(const float* src, float* dst, float s, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = s * src[i];
+}
+
+__global__ void copy_cols_kernel(const float* src, float* dst, int rows, int cols, int dst_ld, int dst_off) {
+    // dst[c][dst_off + r] = src[r][c]   (transpose a (rows, cols) Linear weight into a [cols][dst_ld] table)
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    int r = i / cols, c = i % cols;
+    dst[(size_t)c * dst_ld + dst_off + r] = src[i];
+}
+
+struct DevMem {
+    std::vector<void*> ptrs;
+    size_t total = 0;
+    void* alloc(size_t bytes, bool zero = false) {
+        void* p = nullptr;
+        if (bytes == 0) bytes = 16;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (zero) cudaMemset(p, 0, bytes);
+        ptrs.push_back(p);
+        total += bytes;
+        return p;
+    }
+    ~DevMem() { for (void* p : ptrs) cudaFree(p); }
+};
+
+const char* kResnetNames[12] = {"downs.0.0", "downs.0.1", "downs.1.0", "downs.1.1", "downs.2.0", "downs.2.1",
+                                "mid_block1", "mid_block2", "ups.0.0", "ups.0.1", "ups.1.0", "ups.1.1"};
+const int kResnetCout[12] = {64, 64, 128, 128, 256, 256, 256, 256, 128, 128, 64, 64};
+
+struct BlockW { void* w; const float* bias; const float* gamma; const float* beta; int cin, cout; };
+struct ResnetW { BlockW b1, b2; void* wres; const float* bres; int cin, cout, tb_off; };
+struct AttnW { void* wkv; const float* wq; const float* wout; float* gb; float g; int C; };
+struct SampW { void* w; const float* bias; int C; };
+
+struct Packed {
+    ActKind kind;
+    DevMem mem;
+    TembWeights temb;
+    const float *spk_w0t = nullptr, *spk_b0 = nullptr, *spk_w2t = nullptr, *spk_b2 = nullptr;
+    const float *first_wT = nullptr, *first_b = nullptr, *fr_w = nullptr, *fr_b = nullptr;
+    ResnetW res[12];
+    AttnW attn[6];          // downs.0.2, downs.1.2, downs.2.2, mid_attn, ups.0.2, ups.1.2
+    SampW down[2], up[2];
+    BlockW final_block;
+    const float* wf = nullptr;
+    float bf = 0.f;
+};
+
+}  // namespace
+
+struct Plan;
+
+struct Decoder {
+    int n_spks_mode = 0;      // 0: 2 input channels; 1: speaker channel (n_spks > 1); 2: n_spks == -1 (spk_mlp unused)
+    int cin_first = 2;
+    int n_feats = 80, dim = 64;
+    double beta_min = 0.05, beta_max = 20.0, pe_scale = 1000.0;
+    int device = 0, num_sms = 148;
+    int max_chunk = 8;
+    bool use_graph = true;
+    int conv_impl_bf16 = 1;   // 1: tcgen05, 0: FFMA (debug cross-check)
+    std::map<std::string, float*> params;
+    std::map<std::string, size_t> param_numel;
+    DevMem param_mem;
+    std::unique_ptr<Packed> packed[2];
+    std::map<std::string, Plan*> plans;
+    long launches_last_call = 0;
+    ~Decoder();
+};
+
+namespace {
+
+size_t esize(ActKind k) { return k == ACT_F32 ? 4 : 2; }
+
+int pack_weights(Decoder* d, ActKind kind) {
+    if (d->packed[kind]) return 0;
+    std::unique_ptr<Packed> P(new Packed());
+    P->kind = kind;
+    cudaStream_t s = 0;
+    auto get = [&](const std::string& n) -> const float* {
+        auto it = d->params.find("estimator." + n);
+        return it == d->params.end() ? nullptr : it->second;
+    };
+    auto numel = [&](const std::string& n) -> size_t {
+        auto it = d->param_numel.find("estimator." + n);
+        return it == d->param_numel.end() ? 0 : it->second;
+    };
+#define NEED(ptr, name)                                                                 \
+    do {                                                                                \
+        if ((ptr) == nullptr) { set_error(std::string("missing parameter estimator.") + (name)); return 3; } \
+    } while (0)
+    // ---- time MLP
+    {
+        const float *w0 = get("mlp.0.weight"), *b0 = get("mlp.0.bias"), *w2 = get("mlp.2.weight"), *b2 = get("mlp.2.bias");
+        NEED(w0, "mlp.0.weight"); NEED(b0, "mlp.0.bias"); NEED(w2, "mlp.2.weight"); NEED(b2, "mlp.2.bias");
+        float* w0t = (float*)P->mem.alloc(64 * 256 * 4);
+        float* w2t = (float*)P->mem.alloc(256 * 64 * 4);
+        float* wbt = (float*)P->mem.alloc(64 * 1792 * 4);
+        float* bb = (float*)P->mem.alloc(1792 * 4);
+        if (!w0t || !w2t || !wbt || !bb) { set_error("out of device memory packing weights"); return 4; }
+        if (transpose_2d(w0, w0t, 256, 64, s)) return 1;
+        if (transpose_2d(w2, w2t, 64, 256, s)) return 1;
+        int off = 0;
+        for (int r = 0; r < 12; ++r) {
+            std::string n = std::string(kResnetNames[r]) + ".mlp.1";
+            const float *w = get(n + ".weight"), *b = get(n + ".bias");
+            NEED(w, n + ".weight"); NEED(b, n + ".bias");
+            const int co = kResnetCout[r];
+            copy_cols_kernel<<<(co * 64 + 255) / 256, 256, 0, s>>>(w, wbt, co, 64, 1792, off);
+            GTTS_CHECK_CUDA(cudaMemcpyAsync(bb + off, b, co * 4, cudaMemcpyDeviceToDevice, s));
+            P->res[r].tb_off = off;
+            off += co;
+        }
+        P->temb = TembWeights{w0t, b0, w2t, b2, wbt, bb};
+    }
+    // ---- speaker MLP
+    if (d->n_spks_mode == 1) {
+        const float *w0 = get("spk_mlp.0.weight"), *b0 = get("spk_mlp.0.bias"), *w2 = get("spk_mlp.2.weight"),
+                    *b2 = get("spk_mlp.2.bias");
+        NEED(w0, "spk_mlp.0.weight"); NEED(b0, "spk_mlp.0.bias"); NEED(w2, "spk_mlp.2.weight"); NEED(b2, "spk_mlp.2.bias");
+        float* w0t = (float*)P->mem.alloc(64 * 256 * 4);
+        float* w2t = (float*)P->mem.alloc(256 * d->n_feats * 4);
+        if (transpose_2d(w0, w0t, 256, 64, s)) return 1;
+        if (transpose_2d(w2, w2t, d->n_feats, 256, s)) return 1;
+        P->spk_w0t = w0t; P->spk_b0 = b0; P->spk_w2t = w2t; P->spk_b2 = b2;
+    }
+    // ---- blocks
+    auto pack_block = [&](const std::string& n, int cin, int cout, BlockW* bw, bool first) -> int {
+        const float *w = get(n + ".block.0.weight"), *b = get(n + ".block.0.bias"), *ga = get(n + ".block.1.weight"),
+                    *be = get(n + ".block.1.bias");
+        NEED(w, n + ".block.0.weight"); NEED(b, n + ".block.0.bias"); NEED(ga, n + ".block.1.weight"); NEED(be, n + ".block.1.bias");
+        if (numel(n + ".block.0.weight") != (size_t)cout * cin * 9) { set_error("bad shape for estimator." + n + ".block.0.weight"); return 3; }
+        bw->bias = b; bw->gamma = ga; bw->beta = be; bw->cin = cin; bw->cout = cout;
+        if (first) {
+            float* wt = (float*)P->mem.alloc((size_t)cin * 9 * 64 * 4);
+            if (transpose_2d(w, wt, 64, cin * 9, s)) return 1;
+            bw->w = wt;
+        } else {
+            bw->w = P->mem.alloc((size_t)9 * cout * cin * esize(kind));
+            if (!bw->w) { set_error("out of device memory packing weights"); return 4; }
+            if (pack_conv_weight(kind, w, bw->w, cout, cin, 3, 3, s)) return 1;
+        }
+        return 0;
+    };
+    const int res_cin[12] = {d->cin_first, 64, 64, 128, 128, 256, 256, 256, 512, 128, 256, 64};
+    for (int r = 0; r < 12; ++r) {
+        ResnetW& R = P->res[r];
+        const std::string n = kResnetNames[r];
+        R.cin = res_cin[r]; R.cout = kResnetCout[r];
+        if (int rc = pack_block(n + ".block1", R.cin, R.cout, &R.b1, r == 0)) return rc;
+        if (int rc = pack_block(n + ".block2", R.cout, R.cout, &R.b2, false)) return rc;
+        R.wres = nullptr; R.bres = nullptr;
+        if (R.cin != R.cout) {
+            const float *w = get(n + ".res_conv.weight"), *b = get(n + ".res_conv.bias");
+            NEED(w, n + ".res_conv.weight"); NEED(b, n + ".res_conv.bias");
+            R.bres = b;
+            if (r == 0) {
+                P->fr_w = w; P->fr_b = b;            // (64, cin) row-major, used inline by gn_apply
+            } else {
+                R.wres = P->mem.alloc((size_t)R.cout * R.cin * esize(kind));
+                if (pack_conv_weight(kind, w, R.wres, R.cout, R.cin, 1, 1, s)) return 1;
+            }
+        }
+    }
+    P->first_wT = (const float*)P->res[0].b1.w;
+    P->first_b = P->res[0].b1.bias;
+    // ---- attention
+    const char* attn_names[6] = {"downs.0.2", "downs.1.2", "downs.2.2", "mid_attn", "ups.0.2", "ups.1.2"};
+    const int attn_c[6] = {64, 128, 256, 256, 128, 64};
+    for (int a = 0; a < 6; ++a) {
+        AttnW& A = P->attn[a];
+        const std::string n = attn_names[a];
+        const float *g = get(n + ".fn.g"), *wqkv = get(n + ".fn.fn.to_qkv.weight"), *wo = get(n + ".fn.fn.to_out.weight"),
+                    *bo = get(n + ".fn.fn.to_out.bias");
+        NEED(g, n + ".fn.g"); NEED(wqkv, n + ".fn.fn.to_qkv.weight"); NEED(wo, n + ".fn.fn.to_out.weight"); NEED(bo, n + ".fn.fn.to_out.bias");
+        A.C = attn_c[a];
+        if (numel(n + ".fn.fn.to_qkv.weight") != (size_t)384 * A.C) { set_error("bad shape for estimator." + n + ".fn.fn.to_qkv.weight"); return 3; }
+        GTTS_CHECK_CUDA(cudaMemcpy(&A.g, g, 4, cudaMemcpyDeviceToHost));
+        A.wq = wqkv;                                   // rows [0,128): q = 'b (qkv heads c) h w' (:91-92)
+        A.wout = wo;                                   // (C, 128)
+        A.wkv = P->mem.alloc((size_t)256 * A.C * esize(kind));
+        if (pack_conv_weight(kind, wqkv + (size_t)128 * A.C, A.wkv, 256, A.C, 1, 1, s)) return 1;
+        A.gb = (float*)P->mem.alloc(A.C * 4);
+        scale_vec_kernel<<<1, 256, 0, s>>>(bo, A.gb, A.g, A.C);
+    }
+    // ---- down / up sampling
+    for (int i = 0; i < 2; ++i) {
+        const int C = i == 0 ? 64 : 128;
+        std::string n = "downs." + std::to_string(i) + ".3.conv";
+        const float *w = get(n + ".weight"), *b = get(n + ".bias");
+        NEED(w, n + ".weight"); NEED(b, n + ".bias");
+        P->down[i].C = C; P->down[i].bias = b;
+        P->down[i].w = P->mem.alloc((size_t)9 * C * C * esize(kind));
+        if (pack_conv_weight(kind, w, P->down[i].w, C, C, 3, 3, s)) return 1;
+    }
+    for (int i = 0; i < 2; ++i) {
+        const int C = i == 0 ? 128 : 64;
+        std::string n = "ups." + std::to_string(i) + ".3.conv";
+        const float *w = get(n + ".weight"), *b = get(n + ".bias");
+        NEED(w, n + ".weight"); NEED(b, n + ".bias");
+        if (numel(n + ".weight") != (size_t)16 * C * C) { set_error("bad shape for estimator." + n + ".weight"); return 3; }
+        P->up[i].C = C; P->up[i].bias = b;
+        P->up[i].w = P->mem.alloc((size_t)16 * C * C * esize(kind));
+        if (pack_convT_weight(kind, w, P->up[i].w, C, s)) return 1;
+    }
+    // ---- final
+    if (int rc = pack_block("final_block", 64, 64, &P->final_block, false)) return rc;
+    {
+        const float *w = get("final_conv.weight"), *b = get("final_conv.bias");
+        NEED(w, "final_conv.weight"); NEED(b, "final_conv.bias");
+        P->wf = w;
+        GTTS_CHECK_CUDA(cudaMemcpy(&P->bf, b, 4, cudaMemcpyDeviceToHost));
+    }
+#undef NEED
+    GTTS_CHECK_CUDA(cudaStreamSynchronize(s));
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    d->packed[kind] = std::move(P);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ geometry helpers
+ConvGeom geom_base(int B, int Hin, int Win, int Cin0, int Cin1, int Cout) {
+    ConvGeom g;
+    memset(&g, 0, sizeof(g));
+    g.B = B; g.Hin = Hin; g.Win = Win; g.Hg = Hin; g.Wg = Win; g.Hout = Hin; g.Wout = Win;
+    g.Cin0 = Cin0; g.Cin1 = Cin1; g.Cout = Cout;
+    g.ntaps = 1; g.nphase = 1; g.stride = 1; g.out_step = 1;
+    return g;
+}
+ConvGeom geom_3x3(int B, int H, int W, int Cin0, int Cin1, int Cout, int stride) {
+    ConvGeom g = geom_base(B, H, W, Cin0, Cin1, Cout);
+    g.ntaps = 9; g.stride = stride;
+    for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+            g.dy[0][ky * 3 + kx] = (int8_t)(ky - 1);
+            g.dx[0][ky * 3 + kx] = (int8_t)(kx - 1);
+            g.wrow[0][ky * 3 + kx] = (ky * 3 + kx) * Cout;
+        }
+    if (stride == 2) { g.Hg = H / 2; g.Wg = W / 2; g.Hout = H / 2; g.Wout = W / 2; }
+    return g;
+}
+ConvGeom geom_1x1(int B, int H, int W, int Cin0, int Cin1, int Cout, int w_batch_rows) {
+    ConvGeom g = geom_base(B, H, W, Cin0, Cin1, Cout);
+    g.w_batch_rows = w_batch_rows;
+    return g;
+}
+ConvGeom geom_convT(int B, int H, int W, int C) {
+    ConvGeom g = geom_base(B, H, W, C, 0, C);
+    g.ntaps = 4; g.nphase = 4; g.out_step = 2; g.Hout = 2 * H; g.Wout = 2 * W;
+    const int dd[2][2] = {{0, -1}, {0, 1}};           // parity 0: in j, j-1 ; parity 1: in j, j+1
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+            const int ph = py * 2 + px;
+            g.oy[ph] = py; g.ox[ph] = px;
+            for (int ty = 0; ty < 2; ++ty)
+                for (int tx = 0; tx < 2; ++tx) {
+                    const int t = ty * 2 + tx;
+                    g.dy[ph][t] = (int8_t)dd[py][ty];
+                    g.dx[ph][t] = (int8_t)dd[px][tx];
+                    g.wrow[ph][t] = (ph * 4 + t) * C;
+                }
+        }
+    return g;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ plan
+struct Plan {
+    Decoder* d;
+    ActKind kind;
+    bool strict;
+    int B, T;
+    bool est_mode, sde;
+    DevMem mem;
+    std::vector<TcConvPlan*> tc_plans;
+    std::vector<std::function<int(cudaStream_t)>> ops;
+    // plan-owned I/O
+    float *xt = nullptr, *mu = nullptr, *m0 = nullptr, *m1 = nullptr, *m2 = nullptr, *splane = nullptr, *spk = nullptr;
+    float *tb = nullptr, *t_tab = nullptr, *beta_tab = nullptr, *t_per_sample = nullptr, *score = nullptr;
+    int* step = nullptr;
+    const float** noise_slot = nullptr;
+    float* h_dev = nullptr;
+    size_t noise_step_stride = 0;
+    int max_steps = 4096;
+    float* partials = nullptr;
+    unsigned int* counters = nullptr;
+    size_t partial_slots = 0;
+    cudaGraphExec_t graph_exec = nullptr;
+    bool warmed = false;
+    long kernels_per_step = 0;
+    ~Plan() {
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        for (auto* p : tc_plans) conv_tc_plan_destroy(p);
+    }
+};
+
+Decoder::~Decoder() {
+    for (auto& kv : plans) delete kv.second;
+}
+
+namespace {
+
+struct PlanBuilder {
+    Plan* pl;
+    Decoder* d;
+    Packed* P;
+    ActKind kind;
+    bool strict;
+    int B, T;
+    int H[3], W[3];
+    const float* lmask[3];
+    bool failed = false;
+
+    void* act(int lvl, int C) {
+        void* p = pl->mem.alloc((size_t)B * H[lvl] * W[lvl] * C * esize(kind));
+        if (!p) failed = true;
+        return p;
+    }
+    float* stats() {
+        float* p = (float*)pl->mem.alloc((size_t)B * 16 * 4, true);
+        if (!p) failed = true;
+        return p;
+    }
+    bool use_tc() const { return kind == ACT_BF16 && d->conv_impl_bf16 == 1; }
+    size_t slots_for(const ConvGeom& g) const { return use_tc() ? conv_tc_partials_slots(g) : conv_ffma_partials_slots(g); }
+
+    // Registers one convolution.  GN statistics are requested by passing a stats buffer.
+    void add_conv(const ConvGeom& g, const void* src0, const void* src1, const void* w, int wrows, const float* bias,
+                  const void* residual, const float* mask, void* out, float* gn_stats) {
+        ConvEpilogue e;
+        memset(&e, 0, sizeof(e));
+        e.bias = bias; e.residual = residual; e.mask = mask; e.out = out;
+        if (gn_stats) {
+            e.gn_partials = pl->partials; e.gn_stats = gn_stats; e.gn_counters = pl->counters; e.gn_eps = 1e-5f;
+            if (slots_for(g) > pl->partial_slots) { set_error("internal: GN partial buffer too small"); failed = true; return; }
+        }
+        pl->kernels_per_step++;
+        if (use_tc()) {
+            TcConvPlan* tp = conv_tc_plan_create(g, src0, src1, w, wrows, e, d->num_sms);
+            if (!tp) { failed = true; return; }
+            pl->tc_plans.push_back(tp);
+            pl->ops.push_back([tp](cudaStream_t s) { return conv_tc_launch(tp, s); });
+        } else {
+            ActKind k = kind;
+            pl->ops.push_back([k, g, src0, src1, w, e](cudaStream_t s) { return conv_ffma(k, g, src0, src1, w, e, s); });
+        }
+    }
+
+    void add_gn_apply(int lvl, int C, const void* raw, const float* st, const BlockW& bw, const float* tbias,
+                      const void* residual, bool first_res, void* out) {
+        GnApplyArgs a;
+        memset(&a, 0, sizeof(a));
+        a.raw = raw; a.stats = st; a.gamma = bw.gamma; a.beta = bw.beta; a.mask = lmask[lvl];
+        a.tbias = tbias; a.tbias_bstride = pl->est_mode ? 1792 : 0;
+        a.residual = residual;
+        if (first_res) {
+            a.fr_mu = pl->mu; a.fr_x = pl->xt; a.fr_s = pl->splane; a.fr_w = P->fr_w; a.fr_b = P->fr_b;
+            a.fr_cin = d->cin_first;
+        }
+        a.out = out; a.B = B; a.H = H[lvl]; a.W = W[lvl]; a.C = C;
+        ActKind k = kind;
+        bool st_ = strict;
+        pl->kernels_per_step++;
+        pl->ops.push_back([k, a, st_](cudaStream_t s) { return gn_apply(k, a, st_, s); });
+    }
+
+    // ResnetBlock (:61-79).  x0/x1 are the (masked) input sources; returns the masked output.
+    void* resnet(int r, int lvl, const void* x0, int c0, const void* x1, int c1) {
+        const ResnetW& R = P->res[r];
+        const int Co = R.cout;
+        const float* tb = pl->tb + R.tb_off;
+        void* raw1 = act(lvl, Co); void* a1 = act(lvl, Co); void* raw2 = act(lvl, Co); void* out = act(lvl, Co);
+        float* st1 = stats(); float* st2 = stats();
+        if (failed) return nullptr;
+        if (r == 0) {
+            FirstConvArgs f;
+            memset(&f, 0, sizeof(f));
+            f.mu = pl->mu; f.x = pl->xt; f.splane = pl->splane; f.mask = lmask[0];
+            f.w = P->first_wT; f.bias = P->first_b; f.B = B; f.H = H[0]; f.W = W[0]; f.cin = d->cin_first;
+            f.raw = raw1; f.gn_partials = pl->partials; f.gn_stats = st1; f.gn_counters = pl->counters; f.gn_eps = 1e-5f;
+            if (first_conv_partials_slots(H[0], W[0]) > pl->partial_slots) { set_error("internal: GN partial buffer too small"); failed = true; return nullptr; }
+            ActKind k = kind;
+            pl->kernels_per_step++;
+            pl->ops.push_back([k, f](cudaStream_t s) { return first_conv(k, f, s); });
+        } else {
+            add_conv(geom_3x3(B, H[lvl], W[lvl], c0, c1, Co, 1), x0, x1, R.b1.w, 9 * Co, R.b1.bias, nullptr, nullptr, raw1, st1);
+        }
+        add_gn_apply(lvl, Co, raw1, st1, R.b1, tb, nullptr, false, a1);
+        add_conv(geom_3x3(B, H[lvl], W[lvl], Co, 0, Co, 1), a1, nullptr, R.b2.w, 9 * Co, R.b2.bias, nullptr, nullptr, raw2, st2);
+        const void* resid = nullptr;
+        bool first_res = false;
+        if (r == 0) {
+            first_res = true;
+        } else if (R.wres) {
+            void* rb = act(lvl, Co);
+            add_conv(geom_1x1(B, H[lvl], W[lvl], c0, c1, Co, 0), x0, x1, R.wres, Co, R.bres, nullptr, nullptr, rb, nullptr);
+            resid = rb;
+        } else {
+            resid = x0;                                   // Identity(x * mask): x is stored masked
+        }
+        add_gn_apply(lvl, Co, raw2, st2, R.b2, nullptr, resid, first_res, out);
+        return out;
+    }
+
+    // Residual(Rezero(LinearAttention)) (:39-46, 82-110)
+    void* attention(int a, int lvl, const void* x) {
+        const AttnW& A = P->attn[a];
+        const int C = A.C, n = H[lvl] * W[lvl];
+        void* kv = act(lvl, 256);
+        void* out = act(lvl, C);
+        int chunks, chunk_len;
+        attn_ctx_plan(n, &chunks, &chunk_len);
+        float* partials = (float*)pl->mem.alloc((size_t)B * 4 * chunks * 1088 * 4);
+        unsigned int* counters = (unsigned int*)pl->mem.alloc((size_t)B * 4 * 4, true);
+        float* ctxn = (float*)pl->mem.alloc((size_t)B * 4096 * 4);
+        void* mb = pl->mem.alloc((size_t)B * C * C * esize(kind));
+        if (!kv || !out || !partials || !counters || !ctxn || !mb) { failed = true; return nullptr; }
+        add_conv(geom_1x1(B, H[lvl], W[lvl], C, 0, 256, 0), x, nullptr, A.wkv, 256, nullptr, nullptr, nullptr, kv, nullptr);
+        AttnCtxArgs ca{kv, B, n, partials, counters, ctxn, chunks, chunk_len};
+        ActKind k = kind;
+        bool st_ = strict;
+        pl->kernels_per_step += 2;
+        pl->ops.push_back([k, ca, st_](cudaStream_t s) { return attn_ctx(k, ca, st_, s); });
+        const float *wout = A.wout, *wq = A.wq;
+        float g = A.g;
+        int Bb = B;
+        pl->ops.push_back([k, ctxn, wout, wq, g, mb, Bb, C](cudaStream_t s) { return attn_fold(k, ctxn, wout, wq, g, mb, Bb, C, s); });
+        add_conv(geom_1x1(B, H[lvl], W[lvl], C, 0, C, C), x, nullptr, mb, B * C, A.gb, x, lmask[lvl], out, nullptr);
+        return out;
+    }
+
+    void* downsample(int i, int lvl, const void* x) {
+        const SampW& S = P->down[i];
+        void* out = act(lvl + 1, S.C);
+        if (failed) return nullptr;
+        add_conv(geom_3x3(B, H[lvl], W[lvl], S.C, 0, S.C, 2), x, nullptr, S.w, 9 * S.C, S.bias, nullptr, lmask[lvl + 1], out, nullptr);
+        return out;
+    }
+    void* upsample(int i, int lvl, const void* x) {
+        const SampW& S = P->up[i];
+        void* out = act(lvl - 1, S.C);
+        if (failed) return nullptr;
+        add_conv(geom_convT(B, H[lvl], W[lvl], S.C), x, nullptr, S.w, 16 * S.C, S.bias, nullptr, lmask[lvl - 1], out, nullptr);
+        return out;
+    }
+
+    int build() {
+        H[0] = d->n_feats; W[0] = T; H[1] = H[0] / 2; W[1] = T / 2; H[2] = H[0] / 4; W[2] = T / 4;
+        // plan-owned state
+        const size_t plane = (size_t)B * H[0] * T;
+        pl->xt = (float*)pl->mem.alloc(plane * 4);
+        pl->mu = (float*)pl->mem.alloc(plane * 4);
+        pl->score = (float*)pl->mem.alloc(plane * 4);
+        pl->m0 = (float*)pl->mem.alloc((size_t)B * T * 4);
+        pl->m1 = (float*)pl->mem.alloc((size_t)B * T / 2 * 4);
+        pl->m2 = (float*)pl->mem.alloc((size_t)B * T / 4 * 4);
+        pl->splane = (float*)pl->mem.alloc((size_t)B * H[0] * 4, true);
+        pl->spk = (float*)pl->mem.alloc((size_t)B * 64 * 4, true);
+        pl->tb = (float*)pl->mem.alloc((size_t)(pl->est_mode ? B : 1) * 1792 * 4);
+        pl->t_tab = (float*)pl->mem.alloc(pl->max_steps * 4, true);
+        pl->beta_tab = (float*)pl->mem.alloc(pl->max_steps * 4, true);
+        pl->t_per_sample = (float*)pl->mem.alloc((size_t)B * 4, true);
+        pl->step = (int*)pl->mem.alloc(16, true);
+        pl->noise_slot = (const float**)pl->mem.alloc(16, true);
+        pl->h_dev = (float*)pl->mem.alloc(16, true);
+        pl->counters = (unsigned int*)pl->mem.alloc((size_t)B * 4, true);
+        // GN partial buffer: the largest slot count of any conv (level 0, either tiling)
+        {
+            ConvGeom g0 = geom_3x3(B, H[0], W[0], 64, 0, 64, 1);
+            size_t s = conv_ffma_partials_slots(g0);
+            size_t s2 = conv_tc_partials_slots(g0);
+            size_t s3 = first_conv_partials_slots(H[0], W[0]);
+            for (int l = 1; l < 3; ++l)
+                for (int C = 64; C <= 256; C *= 2) {
+                    ConvGeom gl = geom_3x3(B, H[l], W[l], 64, 0, C, 1);
+                    s = std::max(s, conv_ffma_partials_slots(gl));
+                    s2 = std::max(s2, conv_tc_partials_slots(gl));
+                }
+            pl->partial_slots = std::max(s, std::max(s2, s3));
+            pl->partials = (float*)pl->mem.alloc((size_t)B * pl->partial_slots * 16 * 4);
+        }
+        if (!pl->xt || !pl->mu || !pl->score || !pl->m0 || !pl->m1 || !pl->m2 || !pl->partials) {
+            set_error("out of device memory building the decoder plan");
+            return 4;
+        }
+        lmask[0] = pl->m0; lmask[1] = pl->m1; lmask[2] = pl->m2;
+
+        // ---- time-embedding biases
+        {
+            TembWeights tw = P->temb;
+            const float* tsrc = pl->est_mode ? pl->t_per_sample : pl->t_tab;
+            const int* step = pl->step;
+            int is_table = pl->est_mode ? 0 : 1;
+            float pes = (float)d->pe_scale;
+            float* tb = pl->tb;
+            int nb = pl->est_mode ? B : 1;
+            bool st_ = strict;
+            pl->kernels_per_step++;
+            pl->ops.push_back([tw, tsrc, step, is_table, pes, tb, nb, st_](cudaStream_t s) {
+                return temb_bias(tw, tsrc, step, is_table, pes, tb, nb, st_, s);
+            });
+        }
+        // ---- U-Net (:189-211)
+        void* x = nullptr;
+        void* skip[3] = {nullptr, nullptr, nullptr};
+        x = resnet(0, 0, nullptr, 0, nullptr, 0);
+        x = failed ? nullptr : resnet(1, 0, x, 64, nullptr, 0);
+        x = failed ? nullptr : attention(0, 0, x);
+        skip[0] = x;
+        x = failed ? nullptr : downsample(0, 0, x);
+        x = failed ? nullptr : resnet(2, 1, x, 64, nullptr, 0);
+        x = failed ? nullptr : resnet(3, 1, x, 128, nullptr, 0);
+        x = failed ? nullptr : attention(1, 1, x);
+        skip[1] = x;
+        x = failed ? nullptr : downsample(1, 1, x);
+        x = failed ? nullptr : resnet(4, 2, x, 128, nullptr, 0);
+        x = failed ? nullptr : resnet(5, 2, x, 256, nullptr, 0);
+        x = failed ? nullptr : attention(2, 2, x);
+        skip[2] = x;                                         // downs.2.3 = Identity (:158)
+        x = failed ? nullptr : resnet(6, 2, x, 256, nullptr, 0);
+        x = failed ? nullptr : attention(3, 2, x);
+        x = failed ? nullptr : resnet(7, 2, x, 256, nullptr, 0);
+        x = failed ? nullptr : resnet(8, 2, x, 256, skip[2], 256);   // cat((x, hiddens.pop()), 1) (:207)
+        x = failed ? nullptr : resnet(9, 2, x, 128, nullptr, 0);
+        x = failed ? nullptr : attention(4, 2, x);
+        x = failed ? nullptr : upsample(0, 2, x);
+        x = failed ? nullptr : resnet(10, 1, x, 128, skip[1], 128);
+        x = failed ? nullptr : resnet(11, 1, x, 64, nullptr, 0);
+        x = failed ? nullptr : attention(5, 1, x);
+        x = failed ? nullptr : upsample(1, 1, x);
+        // ---- final block + final conv + Euler update (:212-216, 265-267)
+        void* rawf = failed ? nullptr : act(0, 64);
+        float* stf = failed ? nullptr : stats();
+        if (failed) return 5;
+        add_conv(geom_3x3(B, H[0], W[0], 64, 0, 64, 1), x, nullptr, P->final_block.w, 9 * 64, P->final_block.bias, nullptr, nullptr, rawf, stf);
+        if (failed) return 5;
+        {
+            EulerArgs e;
+            memset(&e, 0, sizeof(e));
+            e.raw = rawf; e.stats = stf; e.gamma = P->final_block.gamma; e.beta = P->final_block.beta;
+            e.wf = P->wf; e.bf = P->bf; e.mask = pl->m0; e.mu = pl->mu; e.xt = pl->xt;
+            e.score_out = pl->est_mode ? pl->score : nullptr;
+            e.beta_tab = pl->beta_tab; e.step = pl->step; e.h_ptr = pl->h_dev;
+            e.noise_slot = pl->noise_slot; e.noise_step_stride = 0; e.sde = pl->sde ? 1 : 0;
+            e.update = pl->est_mode ? 0 : 1;
+            e.B = B; e.H = H[0]; e.W = W[0];
+            Plan* plan = pl;
+            ActKind k = kind;
+            bool st_ = strict;
+            pl->kernels_per_step += 2;
+            pl->ops.push_back([k, e, st_, plan](cudaStream_t s) {
+                EulerArgs ee = e;
+                ee.noise_step_stride = plan->noise_step_stride;
+                return euler_step(k, ee, st_, s);
+            });
+            int* step = pl->step;
+            pl->ops.push_back([step](cudaStream_t s) { return advance_step(step, s); });
+        }
+        return 0;
+    }
+};
+
+
+int plan_create(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, Plan** out) {
+    if (int rc = pack_weights(d, kind)) return rc;
+    std::unique_ptr<Plan> pl(new Plan());
+    pl->d = d; pl->kind = kind; pl->strict = (kind == ACT_F32); pl->B = B; pl->T = T;
+    pl->est_mode = est_mode; pl->sde = sde;
+    PlanBuilder pb;
+    pb.pl = pl.get(); pb.d = d; pb.P = d->packed[kind].get(); pb.kind = kind; pb.strict = pl->strict;
+    pb.B = B; pb.T = T;
+    int rc = pb.build();
+    if (rc == 0 && pb.failed) rc = 5;
+    if (rc) {
+        if (pb.failed && cudaPeekAtLastError() == cudaSuccess) { /* error string already set */ }
+        return rc;
+    }
+    // ---- dry run on zeroed state (validates every launch), then capture the step as a CUDA graph
+    cudaStream_t cs;
+    GTTS_CHECK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    auto run_ops = [&](cudaStream_t s) -> int {
+        for (auto& op : pl->ops)
+            if (int r = op(s)) return r;
+        return 0;
+    };
+    GTTS_CHECK_CUDA(cudaMemsetAsync(pl->xt, 0, (size_t)B * d->n_feats * T * 4, cs));
+    GTTS_CHECK_CUDA(cudaMemsetAsync(pl->mu, 0, (size_t)B * d->n_feats * T * 4, cs));
+    GTTS_CHECK_CUDA(cudaMemsetAsync(pl->m0, 0, (size_t)B * T * 4, cs));
+    GTTS_CHECK_CUDA(cudaMemsetAsync(pl->m1, 0, (size_t)B * T / 2 * 4, cs));
+    GTTS_CHECK_CUDA(cudaMemsetAsync(pl->m2, 0, (size_t)B * T / 4 * 4, cs));
+    schedule_kernel<<<1, 32, 0, cs>>>(pl->t_tab, pl->beta_tab, pl->h_dev, 1, d->beta_min, d->beta_max);
+    {
+        // point the SDE noise slot at something readable for the dry run
+        const float* dummy = pl->score;
+        GTTS_CHECK_CUDA(cudaMemcpyAsync((void*)pl->noise_slot, &dummy, sizeof(dummy), cudaMemcpyHostToDevice, cs));
+    }
+    rc = run_ops(cs);
+    if (rc) { cudaStreamDestroy(cs); return rc; }
+    GTTS_CHECK_CUDA(cudaStreamSynchronize(cs));
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    if (d->use_graph) {
+        cudaGraph_t graph = nullptr;
+        GTTS_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        rc = run_ops(cs);
+        cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        if (rc || ce != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaStreamDestroy(cs);
+            if (!rc) { set_error(std::string("graph capture failed: ") + cudaGetErrorString(ce)); rc = 1; }
+            return rc;
+        }
+        ce = cudaGraphInstantiate(&pl->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) {
+            cudaStreamDestroy(cs);
+            set_error(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ce));
+            return 1;
+        }
+    }
+    GTTS_CHECK_CUDA(cudaStreamSynchronize(cs));
+    cudaStreamDestroy(cs);
+    *out = pl.release();
+    return 0;
+}
+
+int get_plan(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, Plan** out) {
+    std::string key = std::to_string((int)kind) + ":" + std::to_string(B) + ":" + std::to_string(T) + ":" +
+                      (est_mode ? "e" : "s") + (sde ? "n" : "o") + (d->use_graph ? "g" : "x") +
+                      std::to_string(d->conv_impl_bf16);
+    auto it = d->plans.find(key);
+    if (it != d->plans.end()) { *out = it->second; return 0; }
+    // keep at most a handful of plans alive (each owns its workspace)
+    if (d->plans.size() >= 6) {
+        for (auto& kv : d->plans) delete kv.second;
+        d->plans.clear();
+    }
+    Plan* pl = nullptr;
+    if (int rc = plan_create(d, kind, B, T, est_mode, sde, &pl)) return rc;
+    d->plans[key] = pl;
+    *out = pl;
+    return 0;
+}
+
+int plan_step(Plan* pl, cudaStream_t s) {
+    if (pl->graph_exec) {
+        GTTS_CHECK_CUDA(cudaGraphLaunch(pl->graph_exec, s));
+        return 0;
+    }
+    for (auto& op : pl->ops)
+        if (int r = op(s)) return r;
+    return 0;
+}
+
+int common_checks(Decoder* d, int B, int T, const float* spk) {
+    GTTS_REQUIRE(d != nullptr, "null decoder handle");
+    GTTS_REQUIRE(B >= 1 && T >= 4, "bad batch or length");
+    GTTS_REQUIRE(T % 4 == 0, "T must be a multiple of 4 (fix_len_compatibility, model/utils.py:13-17)");
+    GTTS_REQUIRE(d->n_spks_mode != 1 || spk != nullptr, "this decoder was built with n_spks > 1: spk is required");
+    return 0;
+}
+
+}  // namespace
+
+// flags: bit0 = fp32 (strict) precision, else bf16; bit1 = SDE update with injected noise
+int decoder_reverse_diffusion(Decoder* d, const float* z, const float* mask, const float* mu, const float* spk,
+                              float* out, int B, int T, int n_timesteps, int flags, const float* noise,
+                              cudaStream_t stream) {
+    if (int rc = common_checks(d, B, T, spk)) return rc;
+    GTTS_REQUIRE(n_timesteps >= 1 && n_timesteps <= 4096, "n_timesteps must be in [1, 4096]");
+    const bool sde = (flags & 2) != 0;
+    GTTS_REQUIRE(!sde || noise != nullptr, "SDE update requested without a noise tensor");
+    GTTS_CHECK_CUDA(cudaSetDevice(d->device));
+    const ActKind kind = (flags & 1) ? ACT_F32 : ACT_BF16;
+    const size_t plane = (size_t)d->n_feats * T;
+    d->launches_last_call = 0;
+    for (int b0 = 0; b0 < B; b0 += d->max_chunk) {
+        const int Bc = std::min(d->max_chunk, B - b0);
+        Plan* pl = nullptr;
+        if (int rc = get_plan(d, kind, Bc, T, false, sde, &pl)) return rc;
+        Packed* P = d->packed[kind].get();
+        if (int rc = build_level_masks(mask + (size_t)b0 * T, pl->m0, pl->m1, pl->m2, Bc, T, stream)) return rc;
+        GTTS_CHECK_CUDA(cudaMemcpyAsync(pl->mu, mu + b0 * plane, Bc * plane * 4, cudaMemcpyDeviceToDevice, stream));
+        if (int rc = init_xt(z + b0 * plane, pl->m0, pl->xt, Bc, d->n_feats, T, stream)) return rc;
+        if (d->n_spks_mode == 1)
+            if (int rc = spk_mlp(spk + (size_t)b0 * 64, P->spk_w0t, P->spk_b0, P->spk_w2t, P->spk_b2, pl->splane, Bc,
+                                 d->n_feats, pl->strict, stream)) return rc;
+        schedule_kernel<<<(n_timesteps + 255) / 256, 256, 0, stream>>>(pl->t_tab, pl->beta_tab, pl->h_dev, n_timesteps,
+                                                                      d->beta_min, d->beta_max);
+        GTTS_CHECK_CUDA(cudaMemsetAsync(pl->step, 0, 4, stream));
+        if (sde) {
+            const float* nb = noise + b0 * plane;
+            pl->noise_step_stride = (size_t)B * plane;
+            GTTS_CHECK_CUDA(cudaMemcpyAsync((void*)pl->noise_slot, &nb, sizeof(nb), cudaMemcpyHostToDevice, stream));
+            if (pl->graph_exec) {
+                // the stride is baked into the captured Euler node: SDE mode replays eagerly instead
+                for (int i = 0; i < n_timesteps; ++i)
+                    for (auto& op : pl->ops)
+                        if (int r = op(stream)) return r;
+            } else {
+                for (int i = 0; i < n_timesteps; ++i)
+                    if (int rc = plan_step(pl, stream)) return rc;
+            }
+        } else {
+            for (int i = 0; i < n_timesteps; ++i)
+                if (int rc = plan_step(pl, stream)) return rc;
+        }
+        GTTS_CHECK_CUDA(cudaMemcpyAsync(out + b0 * plane, pl->xt, Bc * plane * 4, cudaMemcpyDeviceToDevice, stream));
+        d->launches_last_call += pl->kernels_per_step * n_timesteps + 5;
+    }
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int decoder_estimator(Decoder* d, const float* x, const float* mask, const float* mu, const float* t, const float* spk,
+                      float* out, int B, int T, int flags, cudaStream_t stream) {
+    if (int rc = common_checks(d, B, T, spk)) return rc;
+    GTTS_CHECK_CUDA(cudaSetDevice(d->device));
+    const ActKind kind = (flags & 1) ? ACT_F32 : ACT_BF16;
+    const size_t plane = (size_t)d->n_feats * T;
+    d->launches_last_call = 0;
+    for (int b0 = 0; b0 < B; b0 += d->max_chunk) {
+        const int Bc = std::min(d->max_chunk, B - b0);
+        Plan* pl = nullptr;
+        if (int rc = get_plan(d, kind, Bc, T, true, false, &pl)) return rc;
+        Packed* P = d->packed[kind].get();
+        if (int rc = build_level_masks(mask + (size_t)b0 * T, pl->m0, pl->m1, pl->m2, Bc, T, stream)) return rc;
+        GTTS_CHECK_CUDA(cudaMemcpyAsync(pl->mu, mu + b0 * plane, Bc * plane * 4, cudaMemcpyDeviceToDevice, stream));
+        GTTS_CHECK_CUDA(cudaMemcpyAsync(pl->xt, x + b0 * plane, Bc * plane * 4, cudaMemcpyDeviceToDevice, stream));
+        GTTS_CHECK_CUDA(cudaMemcpyAsync(pl->t_per_sample, t + b0, Bc * 4, cudaMemcpyDeviceToDevice, stream));
+        if (d->n_spks_mode == 1)
+            if (int rc = spk_mlp(spk + (size_t)b0 * 64, P->spk_w0t, P->spk_b0, P->spk_w2t, P->spk_b2, pl->splane, Bc,
+                                 d->n_feats, pl->strict, stream)) return rc;
+        GTTS_CHECK_CUDA(cudaMemsetAsync(pl->step, 0, 4, stream));
+        if (int rc = plan_step(pl, stream)) return rc;
+        GTTS_CHECK_CUDA(cudaMemcpyAsync(out + b0 * plane, pl->score, Bc * plane * 4, cudaMemcpyDeviceToDevice, stream));
+        d->launches_last_call += pl->kernels_per_step + 3;
+    }
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+Decoder* decoder_new(int n_spks, int n_feats, int dim, double beta_min, double beta_max, double pe_scale, int device) {
+    if (n_feats != 80 || dim != 64) { set_error("only n_feats=80, dim=64 (the reference configuration) is supported"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); cudaGetLastError(); return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { set_error("cudaGetDeviceProperties failed"); return nullptr; }
+    if (prop.major != 10) { set_error("this library contains sm_100a code only; found compute capability " +
+                                      std::to_string(prop.major) + "." + std::to_string(prop.minor)); return nullptr; }
+    Decoder* d = new Decoder();
+    d->n_spks_mode = n_spks > 1 ? 1 : (n_spks == -1 ? 2 : 0);
+    d->cin_first = n_spks > 1 ? 3 : 2;
+    d->n_feats = n_feats; d->dim = dim;
+    d->beta_min = beta_min; d->beta_max = beta_max; d->pe_scale = pe_scale;
+    d->device = device; d->num_sms = prop.multiProcessorCount;
+    return d;
+}
+
+int decoder_set_param(Decoder* d, const char* name, const float* data, size_t numel) {
+    GTTS_REQUIRE(d != nullptr && name != nullptr && data != nullptr, "null argument");
+    GTTS_CHECK_CUDA(cudaSetDevice(d->device));
+    std::string n(name);
+    float* dst = nullptr;
+    auto it = d->params.find(n);
+    if (it != d->params.end() && d->param_numel[n] == numel) {
+        dst = it->second;
+    } else {
+        dst = (float*)d->param_mem.alloc(numel * 4);
+        GTTS_REQUIRE(dst != nullptr, "out of device memory for parameters");
+        d->params[n] = dst;
+        d->param_numel[n] = numel;
+    }
+    GTTS_CHECK_CUDA(cudaMemcpy(dst, data, numel * 4, cudaMemcpyDefault));
+    // any packed weights / plans built from the old values are stale
+    d->packed[0].reset();
+    d->packed[1].reset();
+    for (auto& kv : d->plans) delete kv.second;
+    d->plans.clear();
+    return 0;
+}
+
+void decoder_delete(Decoder* d) { delete d; }
+
+int decoder_set_option(Decoder* d, const char* key, int value) {
+    GTTS_REQUIRE(d != nullptr && key != nullptr, "null argument");
+    std::string k(key);
+    if (k == "max_chunk") { GTTS_REQUIRE(value >= 1, "max_chunk must be >= 1"); d->max_chunk = value; }
+    else if (k == "use_graph") d->use_graph = value != 0;
+    else if (k == "conv_impl_bf16") d->conv_impl_bf16 = value;
+    else { set_error("unknown option " + k); return 2; }
+    return 0;
+}
+
+long decoder_launches_last_call(const Decoder* d) { return d ? d->launches_last_call : 0; }
+int decoder_device(const Decoder* d) { return d ? d->device : -1; }
+
+}  // namespace gtts

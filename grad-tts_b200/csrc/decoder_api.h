@@ -1,0 +1,19 @@
+// Internal C++ interface of decoder.cu used by capi.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace gtts {
+struct Decoder;
+Decoder* decoder_new(int n_spks, int n_feats, int dim, double beta_min, double beta_max, double pe_scale, int device);
+void decoder_delete(Decoder* d);
+int decoder_set_param(Decoder* d, const char* name, const float* data, size_t numel);
+int decoder_set_option(Decoder* d, const char* key, int value);
+int decoder_reverse_diffusion(Decoder* d, const float* z, const float* mask, const float* mu, const float* spk,
+                              float* out, int B, int T, int n_timesteps, int flags, const float* noise,
+                              cudaStream_t stream);
+int decoder_estimator(Decoder* d, const float* x, const float* mask, const float* mu, const float* t, const float* spk,
+                      float* out, int B, int T, int flags, cudaStream_t stream);
+long decoder_launches_last_call(const Decoder* d);
+int decoder_device(const Decoder* d);
+}  // namespace gtts

@@ -1,0 +1,153 @@
+// Internal launcher interface between the decoder scheduler (decoder.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace gtts {
+
+enum ActKind { ACT_F32 = 0, ACT_BF16 = 1 };
+
+// ------------------------------------------------------------------------------------------------
+// Generic convolution descriptor (implicit GEMM view: M = output-grid pixels, N = Cout, K = taps*Cin)
+//
+// Activations are NHWC.  Output-grid position (j, i) of phase p reads, for tap t, input pixel
+// (j*stride + dy[p][t], i*stride + dx[p][t]) of each source (zero outside [0,Hin)x[0,Win)), multiplies
+// with weight rows  wrow[p][t] + b*w_batch_rows + co  of the packed K-major weight matrix
+// [rows][Cin0+Cin1], and writes output pixel (j*out_step + oy[p], i*out_step + ox[p]).
+//   3x3 s1 : stride 1, 9 taps dy,dx in {-1,0,1}, 1 phase
+//   3x3 s2 : stride 2, same taps                                   (Downsample, diffusion.py:30-36)
+//   1x1    : 1 tap
+//   convT  : 4 phases x 4 taps, out_step 2                         (Upsample, diffusion.py:21-27)
+// ------------------------------------------------------------------------------------------------
+struct ConvGeom {
+    int B, Hin, Win;          // input spatial size (both sources)
+    int Hg, Wg;               // output grid per phase
+    int Hout, Wout;           // output tensor spatial size
+    int Cin0, Cin1, Cout;
+    int ntaps, nphase, stride, out_step;
+    int8_t dy[4][9], dx[4][9];
+    int wrow[4][9];
+    int oy[4], ox[4];
+    int w_batch_rows;         // 0, or Cout for per-sample weights
+};
+
+struct ConvEpilogue {
+    const float* bias;        // [Cout] or null
+    const void* residual;     // NHWC at output resolution, activation type, or null
+    const float* mask;        // [B][Wout] or null (output multiplied by mask[b][w])
+    void* out;                // NHWC activation type
+    // GroupNorm statistics of (acc + bias) over the whole sample (null partials = off)
+    float* gn_partials;
+    float* gn_stats;          // [B][8][2] mean, rstd
+    unsigned int* gn_counters;
+    float gn_eps;
+};
+
+// CUDA-core implicit GEMM (fp32 accumulate, FFMA).  Strict-fp32 path and debugging cross-check.
+int conv_ffma(ActKind act, const ConvGeom& g, const void* src0, const void* src1, const void* weight,
+              const ConvEpilogue& e, cudaStream_t stream);
+size_t conv_ffma_partials_slots(const ConvGeom& g);
+
+// tcgen05 / TMEM / TMA implicit GEMM, bf16 operands, fp32 accumulate.
+struct TcConvPlan;   // opaque, owns the tensor maps for one (geometry, buffers) binding
+TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void* src1, const void* weight,
+                                int weight_rows, const ConvEpilogue& e, int num_sms);
+void conv_tc_plan_destroy(TcConvPlan* p);
+int conv_tc_launch(const TcConvPlan* p, cudaStream_t stream);
+size_t conv_tc_partials_slots(const ConvGeom& g);
+
+// ------------------------------------------------------------------------------------------------
+// Point-wise / small kernels
+// ------------------------------------------------------------------------------------------------
+// level masks: m0 = mask (B,T), m1 = m0[::2], m2 = m1[::2]   (diffusion.py:185-196)
+int build_level_masks(const float* mask, float* m0, float* m1, float* m2, int B, int T, cudaStream_t s);
+
+// speaker plane s[b][80] = Linear(Mish(Linear(spk)))            (diffusion.py:139-141,176)
+int spk_mlp(const float* spk, const float* w0t, const float* b0, const float* w2t, const float* b2, float* s_out,
+            int B, int n_feats, bool strict, cudaStream_t s);
+
+// time embedding + 12 per-block biases                           (diffusion.py:113-125,143-144,64-65)
+struct TembWeights {
+    const float* w0t; const float* b0;   // [64][256] transposed, [256]
+    const float* w2t; const float* b2;   // [256][64] transposed, [64]
+    const float* wbt; const float* bb;   // [64][1792] transposed (12 blocks concatenated), [1792]
+};
+// t: per-sample times (stride 1) or t_table indexed by *step (t_is_table): out tb[nb][1792]
+int temb_bias(const TembWeights& w, const float* t, const int* step, int t_is_table, float pe_scale, float* tb,
+              int nb, bool strict, cudaStream_t s);
+
+// first block: 3x3 conv from the fp32 planes [mu, x, (s)] * mask -> raw NHWC(64) + GN stats
+struct FirstConvArgs {
+    const float* mu; const float* x; const float* splane;   // (B,80,T), (B,80,T), (B,80) or null
+    const float* mask;                                      // (B,T)
+    const float* w;                                         // [27|18][64]  (k = (ci*3+ky)*3+kx, transposed)
+    const float* bias;                                      // [64]
+    int B, H, W, cin;
+    void* raw;                                              // NHWC act
+    float* gn_partials; float* gn_stats; unsigned int* gn_counters; float gn_eps;
+};
+int first_conv(ActKind act, const FirstConvArgs& a, cudaStream_t s);
+size_t first_conv_partials_slots(int H, int W);
+
+// GroupNorm apply + Mish + mask (+ time bias) (+ residual)       (diffusion.py:53-58,76-78)
+struct GnApplyArgs {
+    const void* raw; const float* stats;                    // NHWC act, [B][8][2]
+    const float* gamma; const float* beta;                  // [C]
+    const float* mask;                                      // [B][W]
+    const float* tbias; int tbias_bstride;                  // [.. + c] added after Mish (null = off)
+    const void* residual;                                   // NHWC act added after Mish (null = off)
+    // first-block residual computed inline: res = Wres[c][:] . [mu,x,s]*mask + bres[c]
+    const float* fr_mu; const float* fr_x; const float* fr_s; const float* fr_w; const float* fr_b; int fr_cin;
+    void* out;                                              // NHWC act
+    int B, H, W, C;
+};
+int gn_apply(ActKind act, const GnApplyArgs& a, bool strict, cudaStream_t s);
+
+// final Block's norm/act + final 1x1 conv + masks + Euler update  (diffusion.py:212-216, 259-267)
+struct EulerArgs {
+    const void* raw; const float* stats; const float* gamma; const float* beta;   // final_block conv output
+    const float* wf; float bf;                                                    // final_conv (64 -> 1)
+    const float* mask;                                                            // (B,T)
+    const float* mu; float* xt;                                                   // (B,80,T) fp32, xt updated
+    float* score_out;                                                             // (B,80,T) or null
+    const float* beta_tab; const int* step; const float* h_ptr;                   // beta_t per step, step index, h
+    const float* const* noise_slot; size_t noise_step_stride; int sde;            // SDE extension (noise base via slot)
+    int update;                                                                   // 0: only write score
+    int B, H, W;
+};
+int euler_step(ActKind act, const EulerArgs& a, bool strict, cudaStream_t s);
+int advance_step(int* step, cudaStream_t s);
+int init_xt(const float* z, const float* mask, float* xt, int B, int H, int W, cudaStream_t s);
+
+// LinearAttention core                                            (diffusion.py:93-99)
+struct AttnCtxArgs {
+    const void* kv;               // NHWC act, 256 channels: k = [0,128), v = [128,256), head-major
+    int B, n;                     // n = H*W positions
+    float* partials;              // [B][4][chunks][1088]
+    unsigned int* counters;       // [B*4]
+    float* ctxn;                  // [B][4][32][32]  ctx[d][e] / l[d]
+    int chunks, chunk_len;
+};
+int attn_ctx(ActKind act, const AttnCtxArgs& a, bool strict, cudaStream_t s);
+void attn_ctx_plan(int n, int* chunks, int* chunk_len);
+// per-sample folded weights M_b = g * Wout * blockdiag(ctxn^T) * Wq  -> [B*C][C] in weight type
+int attn_fold(ActKind wkind, const float* ctxn, const float* wout /*[C][128]*/, const float* wq /*[128][C]*/,
+              float g, void* mb_out, int B, int C, cudaStream_t s);
+
+// weight packing helpers (device side, fp32 source in PyTorch layout)
+int pack_conv_weight(ActKind wkind, const float* w_oihw, void* packed, int Cout, int Cin, int kh, int kw,
+                     cudaStream_t s);                       // -> [(ky*kw+kx)*Cout + co][ci]
+int pack_convT_weight(ActKind wkind, const float* w_iohw, void* packed, int C, cudaStream_t s);   // 4x4 s2 p1
+int transpose_2d(const float* src, float* dst, int rows, int cols, cudaStream_t s);               // dst[c][r]
+
+// MAS (mas.cu)
+size_t mas_bits_workspace_bytes(int B, int tx, int ty);
+int mas_forward_f32(const float* value, const float* mask, const int* t_xs, const int* t_ys, float* path, int B,
+                    int tx, int ty, float max_neg, uint32_t* bits_ws, size_t bits_ws_bytes, int* status,
+                    cudaStream_t stream);
+int mas_forward_i32(const float* value, const float* mask, const int* t_xs, const int* t_ys, int32_t* path, int B,
+                    int tx, int ty, float max_neg, uint32_t* bits_ws, size_t bits_ws_bytes, int* status,
+                    cudaStream_t stream);
+
+}  // namespace gtts

@@ -1,0 +1,434 @@
+// HBM-bound point-wise kernels of the decoder: masks, MLPs, first conv, GroupNorm-apply, Euler step,
+// weight packing.  Reference lines are cited per kernel (all in /root/reference/model/diffusion.py).
+#include "common.cuh"
+#include "ops.h"
+
+namespace gtts {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ masks
+__global__ void level_masks_kernel(const float* __restrict__ mask, float* m0, float* m1, float* m2, int B, int T) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * T) return;
+    int b = i / T, w = i % T;
+    float v = mask[i];
+    m0[i] = v;
+    if ((w & 1) == 0) m1[b * (T / 2) + (w >> 1)] = v;      // mask[..., ::2]      (:196)
+    if ((w & 3) == 0) m2[b * (T / 4) + (w >> 2)] = v;      // mask[..., ::2][::2]
+}
+
+__global__ void init_xt_kernel(const float* __restrict__ z, const float* __restrict__ mask, float* xt, int B, int H,
+                               int W) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t n = (size_t)B * H * W;
+    if (i >= n) return;
+    int w = (int)(i % W);
+    int b = (int)(i / ((size_t)H * W));
+    xt[i] = __fmul_rn(z[i], mask[(size_t)b * W + w]);       // xt = z * mask       (:257)
+}
+
+__global__ void advance_step_kernel(int* step) { *step += 1; }
+
+// ------------------------------------------------------------------------------------------------ spk MLP
+template <bool kStrict>
+__global__ void spk_mlp_kernel(const float* __restrict__ spk, const float* __restrict__ w0t,
+                               const float* __restrict__ b0, const float* __restrict__ w2t,
+                               const float* __restrict__ b2, float* __restrict__ s_out, int n_feats) {
+    __shared__ float sx[64], sh[256];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (tid < 64) sx[tid] = spk[b * 64 + tid];
+    __syncthreads();
+    float a = b0[tid];
+    for (int i = 0; i < 64; ++i) a += w0t[i * 256 + tid] * sx[i];
+    sh[tid] = mish<kStrict>(a);
+    __syncthreads();
+    if (tid < n_feats) {
+        float o = b2[tid];
+        for (int j = 0; j < 256; ++j) o += w2t[j * n_feats + tid] * sh[j];
+        s_out[b * n_feats + tid] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ time MLP
+// grid (14, nb), 256 threads; every CTA recomputes the 64-d embedding and writes 128 of the 1792 biases.
+template <bool kStrict>
+__global__ void temb_kernel(TembWeights w, const float* __restrict__ t, const int* __restrict__ step, int t_is_table,
+                            float pe_scale, float* __restrict__ tb) {
+    __shared__ float e[64], h1[256], part[256], h2[64];
+    const int tid = threadIdx.x, b = blockIdx.y;
+    const float tv = t_is_table ? t[*step] : t[b];
+    if (tid < 32) {
+        // emb = exp(arange(32).float() * -(log(1e4)/31)) ; arg = (scale * t) * emb          (:118-124)
+        const float c = (float)(-9.210340371976184 / 31.0);
+        float f = expf((float)tid * c);
+        float arg = __fmul_rn(__fmul_rn(pe_scale, tv), f);
+        e[tid] = sinf(arg);
+        e[tid + 32] = cosf(arg);
+    }
+    __syncthreads();
+    {
+        float a = w.b0[tid];
+        for (int i = 0; i < 64; ++i) a += w.w0t[i * 256 + tid] * e[i];
+        h1[tid] = mish<kStrict>(a);
+    }
+    __syncthreads();
+    {
+        const int o = tid & 63, p = tid >> 6;
+        float a = 0.f;
+        for (int j = p * 64; j < p * 64 + 64; ++j) a += w.w2t[j * 64 + o] * h1[j];
+        part[tid] = a;
+    }
+    __syncthreads();
+    if (tid < 64) {
+        float a = w.b2[tid] + ((part[tid] + part[64 + tid]) + (part[128 + tid] + part[192 + tid]));
+        h2[tid] = mish<kStrict>(a);                       // ResnetBlock.mlp = Mish -> Linear   (:64-65)
+    }
+    __syncthreads();
+    {
+        const int j = blockIdx.x * 128 + (tid & 127), p = tid >> 7;
+        float a = 0.f;
+        for (int i = p * 32; i < p * 32 + 32; ++i) a += w.wbt[i * 1792 + j] * h2[i];
+        part[tid] = a;
+    }
+    __syncthreads();
+    if (tid < 128) {
+        const int j = blockIdx.x * 128 + tid;
+        tb[(size_t)b * 1792 + j] = w.bb[j] + (part[tid] + part[128 + tid]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ first conv
+// Block.conv of downs.0.0.block1 on stack([mu, x, (s)]) * mask  (:181-184, 52-57).  One thread per pixel.
+template <typename T, int CIN>
+__global__ void __launch_bounds__(128)
+first_conv_kernel(FirstConvArgs a) {
+    __shared__ __align__(16) float wT[CIN * 9 * 64];
+    __shared__ float sb[64];
+    __shared__ float s_part[4][16];
+    __shared__ float s_tile[16];
+    __shared__ double s_red[8 * 16];
+    __shared__ int s_flag;
+    const int tid = threadIdx.x, b = blockIdx.y;
+    for (int i = tid; i < CIN * 9 * 64; i += 128) wT[i] = a.w[i];
+    if (tid < 64) sb[tid] = a.bias[tid];
+    __syncthreads();
+
+    const int H = a.H, W = a.W;
+    const int p = blockIdx.x * 128 + tid;                 // pixel within the sample
+    const bool valid = p < H * W;
+    const int h = valid ? p / W : 0, w = valid ? p % W : 0;
+    float acc[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) acc[c] = sb[c];
+    if (valid) {
+        const float* mrow = a.mask + (size_t)b * W;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int hh = h + ky - 1;
+            if (hh < 0 || hh >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ww = w + kx - 1;
+                if (ww < 0 || ww >= W) continue;
+                const float m = mrow[ww];
+                const size_t off = ((size_t)b * H + hh) * W + ww;
+                float in[CIN];
+                in[0] = a.mu[off] * m;
+                in[1] = a.x[off] * m;
+                if (CIN == 3) in[CIN - 1] = a.splane[b * H + hh] * m;
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) {
+                    const float4* wr = reinterpret_cast<const float4*>(&wT[((ci * 3 + ky) * 3 + kx) * 64]);
+#pragma unroll
+                    for (int c4 = 0; c4 < 16; ++c4) {
+                        float4 wv = wr[c4];
+                        acc[4 * c4 + 0] = fmaf(in[ci], wv.x, acc[4 * c4 + 0]);
+                        acc[4 * c4 + 1] = fmaf(in[ci], wv.y, acc[4 * c4 + 1]);
+                        acc[4 * c4 + 2] = fmaf(in[ci], wv.z, acc[4 * c4 + 2]);
+                        acc[4 * c4 + 3] = fmaf(in[ci], wv.w, acc[4 * c4 + 3]);
+                    }
+                }
+            }
+        }
+        T* o = reinterpret_cast<T*>(a.raw) + ((size_t)b * H * W + p) * 64;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = acc[g * 8 + j];
+            Act<T>::store8(o + g * 8, v);
+        }
+    }
+    // GroupNorm statistics (8 groups of 8 channels) over the unmasked conv output   (:53)
+    float st[16];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        float s = 0.f, q = 0.f;
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { float v = acc[g * 8 + j]; s += v; q += v * v; }
+        }
+        st[g] = warp_sum(s);
+        st[8 + g] = warp_sum(q);
+    }
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) s_part[tid >> 5][k] = st[k];
+    }
+    __syncthreads();
+    if (tid < 16) s_tile[tid] = (s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]);
+    __syncthreads();
+    GnStatsOut go{a.gn_partials, a.gn_stats, a.gn_counters, (int)gridDim.x, 1.0f / (8.0f * H * W), a.gn_eps};
+    gn_stats_publish(go, b, blockIdx.x, tid, 128, s_tile, s_red, &s_flag, [] { __syncthreads(); });
+}
+
+// ------------------------------------------------------------------------------------------------ GN apply
+template <typename T, bool kStrict>
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(GnApplyArgs a) {
+    const int C8 = a.C >> 3;
+    const size_t total = (size_t)a.B * a.H * a.W * C8;
+    const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= total) return;
+    const int c8 = (int)(idx % C8);
+    const size_t pix = idx / C8;
+    const int HW = a.H * a.W;
+    const int b = (int)(pix / HW);
+    const int w = (int)(pix % a.W);
+    const int c0 = c8 * 8;
+    const int g = (c0 * 8) / a.C;
+    const float mean = a.stats[(b * 8 + g) * 2], rstd = a.stats[(b * 8 + g) * 2 + 1];
+    const float m = a.mask[(size_t)b * a.W + w];
+    float v[8];
+    Act<T>::load8(reinterpret_cast<const T*>(a.raw) + pix * a.C + c0, v);
+    float r[8];
+    const bool has_res = a.residual != nullptr;
+    if (has_res) Act<T>::load8(reinterpret_cast<const T*>(a.residual) + pix * a.C + c0, r);
+    float fin[3] = {0.f, 0.f, 0.f};
+    if (a.fr_w) {
+        fin[0] = a.fr_mu[pix] * m;
+        fin[1] = a.fr_x[pix] * m;
+        if (a.fr_cin == 3) fin[2] = a.fr_s[pix / a.W] * m;           // s plane is (B,80): index b*H + h
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        float y = (v[j] - mean) * rstd * __ldg(a.gamma + c) + __ldg(a.beta + c);      // GroupNorm      (:53)
+        y = mish<kStrict>(y) * m;                                                     // Mish, * mask   (:54,58)
+        if (a.tbias) y += __ldg(a.tbias + (size_t)b * a.tbias_bstride + c);           // h += mlp(t)    (:76)
+        if (has_res) y += r[j];                                                       // + res_conv(x)  (:78)
+        if (a.fr_w) {
+            float rr = __ldg(a.fr_b + c);
+            for (int ci = 0; ci < a.fr_cin; ++ci) rr = fmaf(__ldg(a.fr_w + c * a.fr_cin + ci), fin[ci], rr);
+            y += rr;
+        }
+        v[j] = y * m;          // every consumer masks its input: store masked (binary masks)
+    }
+    Act<T>::store8(reinterpret_cast<T*>(a.out) + pix * a.C + c0, v);
+}
+
+// ------------------------------------------------------------------------------------------------ Euler step
+// final_block GN+Mish+mask -> final_conv(64->1)+bias -> *mask = score; then the sampler update.
+template <typename T, bool kStrict>
+__global__ void __launch_bounds__(256)
+euler_kernel(EulerArgs a) {
+    const size_t npix = (size_t)a.B * a.H * a.W;
+    const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const size_t pix = idx >> 3;
+    const int sub = (int)(idx & 7);
+    const bool valid = pix < npix;
+    const size_t pp = valid ? pix : 0;
+    const int HW = a.H * a.W;
+    const int b = (int)(pp / HW);
+    const int w = (int)(pp % a.W);
+    const float m = a.mask[(size_t)b * a.W + w];
+    const float mean = a.stats[(b * 8 + sub) * 2], rstd = a.stats[(b * 8 + sub) * 2 + 1];
+    float v[8];
+    Act<T>::load8(reinterpret_cast<const T*>(a.raw) + pp * 64 + sub * 8, v);
+    float part = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = sub * 8 + j;
+        float y = (v[j] - mean) * rstd * __ldg(a.gamma + c) + __ldg(a.beta + c);
+        y = mish<kStrict>(y) * m;                      // final_block(x, mask)              (:212)
+        part = fmaf(y * m, __ldg(a.wf + c), part);     // final_conv(x * mask)              (:213)
+    }
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    part += __shfl_xor_sync(0xffffffffu, part, 4);
+    if (!valid || sub != 0) return;
+    const float score = __fmul_rn(part + a.bf, m);     // (output * mask)                   (:216)
+    if (a.score_out) a.score_out[pix] = score;
+    if (!a.update) return;
+    const float beta_t = a.beta_tab[*a.step];
+    const float hh = *a.h_ptr;
+    const float xt = a.xt[pix], mu = a.mu[pix];
+    float nx;
+    if (!a.sde) {
+        // dxt = 0.5*(mu - xt - est); dxt = dxt*noise_t*h; xt = (xt - dxt)*mask          (:265-267)
+        float d = __fsub_rn(__fsub_rn(mu, xt), score);
+        d = __fmul_rn(0.5f, d);
+        d = __fmul_rn(__fmul_rn(d, beta_t), hh);
+        nx = __fmul_rn(__fsub_rn(xt, d), m);
+    } else {
+        // north-star SDE form (upstream Grad-TTS): x - (0.5*(mu-x) - score)*beta*h + sqrt(beta*h)*z
+        float d = __fsub_rn(__fmul_rn(0.5f, __fsub_rn(mu, xt)), score);
+        d = __fmul_rn(__fmul_rn(d, beta_t), hh);
+        const float* noise = *a.noise_slot;
+        float z = noise[(size_t)(*a.step) * a.noise_step_stride + pix];
+        d = __fsub_rn(d, __fmul_rn(sqrtf(__fmul_rn(beta_t, hh)), z));
+        nx = __fmul_rn(__fsub_rn(xt, d), m);
+    }
+    a.xt[pix] = nx;
+}
+
+// ------------------------------------------------------------------------------------------------ packing
+template <typename WT>
+__global__ void pack_conv_kernel(const float* __restrict__ w, WT* __restrict__ out, int Cout, int Cin, int kh,
+                                 int kw) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t n = (size_t)Cout * Cin * kh * kw;
+    if (i >= n) return;
+    int ci = (int)(i % Cin);
+    size_t r = i / Cin;
+    int co = (int)(r % Cout);
+    int tap = (int)(r / Cout);
+    int ky = tap / kw, kx = tap % kw;
+    Act<WT>::st(out + i, w[(((size_t)co * Cin + ci) * kh + ky) * kw + kx]);
+}
+
+// ConvTranspose2d(C, C, 4, 2, 1): weight (Cin, Cout, 4, 4); out[2j+py] taps: py=0 -> (dy=0,k=1),(dy=-1,k=3);
+// py=1 -> (dy=0,k=2),(dy=+1,k=0); same along x.  Row = ((phase*4 + tap)*C + co), phase = py*2+px, tap = ty*2+tx.
+template <typename WT>
+__global__ void pack_convT_kernel(const float* __restrict__ w, WT* __restrict__ out, int C) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t n = (size_t)16 * C * C;
+    if (i >= n) return;
+    int ci = (int)(i % C);
+    size_t r = i / C;
+    int co = (int)(r % C);
+    int pt = (int)(r / C);
+    int phase = pt >> 2, tap = pt & 3;
+    int py = phase >> 1, px = phase & 1, ty = tap >> 1, tx = tap & 1;
+    const int kk[2][2] = {{1, 3}, {2, 0}};
+    int ky = kk[py][ty], kx = kk[px][tx];
+    Act<WT>::st(out + i, w[(((size_t)ci * C + co) * 4 + ky) * 4 + kx]);
+}
+
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)rows * cols) return;
+    int r = (int)(i / cols), c = (int)(i % cols);
+    dst[(size_t)c * rows + r] = src[i];
+}
+
+inline unsigned int nblk(size_t n, int bs) { return (unsigned int)((n + bs - 1) / bs); }
+
+}  // namespace
+
+int build_level_masks(const float* mask, float* m0, float* m1, float* m2, int B, int T, cudaStream_t s) {
+    level_masks_kernel<<<nblk((size_t)B * T, 256), 256, 0, s>>>(mask, m0, m1, m2, B, T);
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int init_xt(const float* z, const float* mask, float* xt, int B, int H, int W, cudaStream_t s) {
+    init_xt_kernel<<<nblk((size_t)B * H * W, 256), 256, 0, s>>>(z, mask, xt, B, H, W);
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int advance_step(int* step, cudaStream_t s) {
+    advance_step_kernel<<<1, 1, 0, s>>>(step);
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int spk_mlp(const float* spk, const float* w0t, const float* b0, const float* w2t, const float* b2, float* s_out,
+            int B, int n_feats, bool strict, cudaStream_t s) {
+    GTTS_REQUIRE(n_feats <= 256, "spk_mlp: n_feats too large");
+    if (strict) spk_mlp_kernel<true><<<B, 256, 0, s>>>(spk, w0t, b0, w2t, b2, s_out, n_feats);
+    else        spk_mlp_kernel<false><<<B, 256, 0, s>>>(spk, w0t, b0, w2t, b2, s_out, n_feats);
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int temb_bias(const TembWeights& w, const float* t, const int* step, int t_is_table, float pe_scale, float* tb,
+              int nb, bool strict, cudaStream_t s) {
+    dim3 grid(14, nb);
+    if (strict) temb_kernel<true><<<grid, 256, 0, s>>>(w, t, step, t_is_table, pe_scale, tb);
+    else        temb_kernel<false><<<grid, 256, 0, s>>>(w, t, step, t_is_table, pe_scale, tb);
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+size_t first_conv_partials_slots(int H, int W) { return (size_t)(H * W + 127) / 128; }
+
+int first_conv(ActKind act, const FirstConvArgs& a, cudaStream_t s) {
+    GTTS_REQUIRE(a.cin == 2 || a.cin == 3, "first_conv: cin must be 2 or 3");
+    dim3 grid((unsigned int)first_conv_partials_slots(a.H, a.W), a.B);
+    if (act == ACT_F32) {
+        if (a.cin == 2) first_conv_kernel<float, 2><<<grid, 128, 0, s>>>(a);
+        else            first_conv_kernel<float, 3><<<grid, 128, 0, s>>>(a);
+    } else {
+        if (a.cin == 2) first_conv_kernel<__nv_bfloat16, 2><<<grid, 128, 0, s>>>(a);
+        else            first_conv_kernel<__nv_bfloat16, 3><<<grid, 128, 0, s>>>(a);
+    }
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int gn_apply(ActKind act, const GnApplyArgs& a, bool strict, cudaStream_t s) {
+    GTTS_REQUIRE(a.C % 64 == 0, "gn_apply: C must be a multiple of 64");
+    size_t total = (size_t)a.B * a.H * a.W * (a.C / 8);
+    unsigned int g = nblk(total, 256);
+    if (act == ACT_F32) {
+        if (strict) gn_apply_kernel<float, true><<<g, 256, 0, s>>>(a);
+        else        gn_apply_kernel<float, false><<<g, 256, 0, s>>>(a);
+    } else {
+        if (strict) gn_apply_kernel<__nv_bfloat16, true><<<g, 256, 0, s>>>(a);
+        else        gn_apply_kernel<__nv_bfloat16, false><<<g, 256, 0, s>>>(a);
+    }
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int euler_step(ActKind act, const EulerArgs& a, bool strict, cudaStream_t s) {
+    size_t total = (size_t)a.B * a.H * a.W * 8;
+    unsigned int g = nblk(total, 256);
+    if (act == ACT_F32) {
+        if (strict) euler_kernel<float, true><<<g, 256, 0, s>>>(a);
+        else        euler_kernel<float, false><<<g, 256, 0, s>>>(a);
+    } else {
+        if (strict) euler_kernel<__nv_bfloat16, true><<<g, 256, 0, s>>>(a);
+        else        euler_kernel<__nv_bfloat16, false><<<g, 256, 0, s>>>(a);
+    }
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int pack_conv_weight(ActKind wkind, const float* w, void* packed, int Cout, int Cin, int kh, int kw,
+                     cudaStream_t s) {
+    size_t n = (size_t)Cout * Cin * kh * kw;
+    if (wkind == ACT_F32) pack_conv_kernel<float><<<nblk(n, 256), 256, 0, s>>>(w, (float*)packed, Cout, Cin, kh, kw);
+    else pack_conv_kernel<__nv_bfloat16><<<nblk(n, 256), 256, 0, s>>>(w, (__nv_bfloat16*)packed, Cout, Cin, kh, kw);
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int pack_convT_weight(ActKind wkind, const float* w, void* packed, int C, cudaStream_t s) {
+    size_t n = (size_t)16 * C * C;
+    if (wkind == ACT_F32) pack_convT_kernel<float><<<nblk(n, 256), 256, 0, s>>>(w, (float*)packed, C);
+    else pack_convT_kernel<__nv_bfloat16><<<nblk(n, 256), 256, 0, s>>>(w, (__nv_bfloat16*)packed, C);
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int transpose_2d(const float* src, float* dst, int rows, int cols, cudaStream_t s) {
+    transpose_kernel<<<nblk((size_t)rows * cols, 256), 256, 0, s>>>(src, dst, rows, cols);
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace gtts

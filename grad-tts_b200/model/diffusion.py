@@ -1,0 +1,277 @@
+"""Drop-in `Diffusion` / `GradLogPEstimator2d` backed by the sm_100a kernels (reference model/diffusion.py).
+
+The modules keep the reference's constructor arguments, attribute names and `state_dict()` keys
+(e.g. `estimator.downs.0.0.block1.block.0.weight`), so a reference checkpoint loads unchanged; the forward
+passes hand raw device pointers to the C ABI (include/gradtts_b200.h).  Nothing here computes on the CPU
+or through ATen: if the parameters are not on an sm_100 CUDA device the call raises.
+"""
+import ctypes
+import math
+
+import torch
+
+from .. import _lib, synth
+from .base import BaseModule
+
+
+class _Node(torch.nn.Module):
+    """Anonymous container used to reproduce the reference's nested parameter names."""
+
+
+def _build_param_tree(root, names_shapes, init):
+    for name, shape in names_shapes:
+        parts = name.split(".")
+        node = root
+        for p in parts[:-1]:
+            if p not in node._modules:
+                node.add_module(p, _Node())
+            node = node._modules[p]
+        node.register_parameter(parts[-1], torch.nn.Parameter(init(name, shape)))
+
+
+def _default_init(name, shape):
+    """PyTorch-default-like init from the global RNG: U(+-1/sqrt(fan_in)); GroupNorm 1/0; Rezero g = 0."""
+    if name.endswith(".fn.g"):
+        return torch.zeros(shape)                                     # model/diffusion.py:43
+    if ".block.1.weight" in name:
+        return torch.ones(shape)
+    if ".block.1.bias" in name:
+        return torch.zeros(shape)
+    if len(shape) > 1:
+        fan_in = math.prod(shape[1:])
+        if ".3.conv.weight" in name and name.startswith("ups"):
+            fan_in = shape[1] * shape[2] * shape[3]
+    else:
+        fan_in = _default_init.last_fan_in
+    _default_init.last_fan_in = fan_in
+    bound = 1.0 / math.sqrt(fan_in)
+    return (torch.rand(shape) * 2.0 - 1.0) * bound
+
+
+_default_init.last_fan_in = 1
+
+
+class GradLogPEstimator2d(BaseModule):
+    """Score U-Net (reference model/diffusion.py:128-216). Parameters only; the maths lives in csrc/."""
+
+    def __init__(self, dim, dim_mults=(1, 2, 4), groups=8, n_spks=None, spk_emb_dim=64, n_feats=80, pe_scale=1000):
+        super().__init__()
+        if dim != 64 or tuple(dim_mults) != (1, 2, 4) or groups != 8 or spk_emb_dim != 64 or n_feats != 80:
+            raise NotImplementedError("the sm_100a kernels are specialised for the reference configuration "
+                                      "dim=64, dim_mults=(1,2,4), groups=8, spk_emb_dim=64, n_feats=80")
+        self.dim = dim
+        self.dim_mults = dim_mults
+        self.groups = groups
+        self.n_spks = n_spks if n_spks is not None else 1
+        self.spk_emb_dim = spk_emb_dim
+        self.n_feats = n_feats
+        self.pe_scale = pe_scale
+        self.beta_min, self.beta_max = 0.05, 20.0          # overwritten by the owning Diffusion
+        self.precision = "bf16"                            # "bf16" (tcgen05 convs) or "fp32" (true-fp32 arithmetic)
+        self.max_chunk = 8                                 # samples per workspace chunk
+        _build_param_tree(self, synth.decoder_param_shapes(self.n_spks, pfx=""), _default_init)
+        self._handle = None
+        self._handle_key = None
+        self._uploaded = None
+
+    # ---- handle management -------------------------------------------------------------------------
+    def _param_signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _get_handle(self):
+        lib = _lib.load()
+        p0 = next(self.parameters())
+        _lib.require_cuda_tensor(p0, "decoder parameters")
+        dev = p0.device.index if p0.device.index is not None else torch.cuda.current_device()
+        key = (dev, float(self.beta_min), float(self.beta_max), float(self.pe_scale))
+        if self._handle is None or self._handle_key != key:
+            self._release()
+            h = ctypes.c_void_p()
+            rc = lib.gtts_decoder_create(ctypes.byref(h), int(self.n_spks), int(self.n_feats), int(self.dim),
+                                         float(self.beta_min), float(self.beta_max), float(self.pe_scale), dev)
+            _lib.check(rc, "decoder_create")
+            self._handle, self._handle_key, self._uploaded = h, key, None
+        sig = self._param_signature()
+        if self._uploaded != sig:
+            for name, p in self.named_parameters():
+                t = p.detach()
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    t = t.to(torch.float32).contiguous()
+                rc = lib.gtts_decoder_set_param(self._handle, ("estimator." + name).encode(), t.data_ptr(), t.numel())
+                _lib.check(rc, f"decoder_set_param({name})")
+            self._uploaded = sig
+        _lib.check(lib.gtts_decoder_set_option(self._handle, b"max_chunk", int(self.max_chunk)), "set_option")
+        return self._handle
+
+    def _release(self):
+        if getattr(self, "_handle", None) is not None:
+            try:
+                _lib.load().gtts_decoder_destroy(self._handle)
+            except Exception:
+                pass
+            self._handle = None
+
+    def __del__(self):
+        self._release()
+
+    def __getstate__(self):
+        d = self.__dict__.copy()          # the native handle is per-process: never pickled / deep-copied
+        d["_handle"], d["_handle_key"], d["_uploaded"] = None, None, None
+        return d
+
+    def _flags(self):
+        if self.precision == "fp32":
+            return _lib.FLAG_FP32
+        if self.precision == "bf16":
+            return 0
+        raise ValueError(f"precision must be 'bf16' or 'fp32', got {self.precision!r}")
+
+    @staticmethod
+    def _prep(t, name, device):
+        _lib.require_cuda_tensor(t, name)
+        if t.device != device:
+            raise RuntimeError(f"{name} is on {t.device} but the decoder parameters are on {device}")
+        return t.detach().to(torch.float32).contiguous()
+
+    def _check_shapes(self, x, mask, mu, spk):
+        if x.dim() != 3 or x.shape[1] != self.n_feats or mu.shape != x.shape:
+            raise ValueError(f"expected x and mu of shape (B, {self.n_feats}, T), got {tuple(x.shape)}, {tuple(mu.shape)}")
+        B, _, T = x.shape
+        if tuple(mask.shape) != (B, 1, T):
+            raise ValueError(f"expected mask of shape (B, 1, T) = {(B, 1, T)}, got {tuple(mask.shape)}")
+        if T % 4 != 0:
+            raise ValueError("T must be a multiple of 4 (model/utils.py fix_len_compatibility)")
+        if self.n_spks > 1:
+            if spk is None or tuple(spk.shape) != (B, self.spk_emb_dim):
+                raise ValueError(f"n_spks > 1: spk of shape (B, {self.spk_emb_dim}) is required")
+        return B, T
+
+    # ---- reference API -----------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x, mask, mu, t, spk=None):
+        """Score estimate, reference model/diffusion.py:174-216. x, mu: (B,80,T); mask: (B,1,T); t: (B,)."""
+        h = self._get_handle()
+        dev = next(self.parameters()).device
+        x_, mask_, mu_ = (self._prep(v, n, dev) for v, n in ((x, "x"), (mask, "mask"), (mu, "mu")))
+        B, T = self._check_shapes(x_, mask_, mu_, spk)
+        t_ = self._prep(t, "t", dev).reshape(-1)
+        if t_.numel() != B:
+            raise ValueError("t must have one entry per sample")
+        spk_ = self._prep(spk, "spk", dev) if (spk is not None and self.n_spks > 1) else None
+        out = torch.empty_like(x_)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = _lib.load().gtts_decoder_estimator(h, x_.data_ptr(), mask_.data_ptr(), mu_.data_ptr(), t_.data_ptr(),
+                                                    spk_.data_ptr() if spk_ is not None else None, out.data_ptr(),
+                                                    B, T, self._flags(), ctypes.c_void_p(stream))
+        _lib.check(rc, "estimator")
+        return out.to(x.dtype)
+
+    def launches_last_call(self):
+        return int(_lib.load().gtts_decoder_launches_last_call(self._handle)) if self._handle is not None else 0
+
+
+def get_noise(t, beta_init, beta_term, cumulative=False):
+    # model/diffusion.py:219-224 (kept for callers that import it)
+    if cumulative:
+        return beta_init * t + 0.5 * (beta_term - beta_init) * (t ** 2)
+    return beta_init + (beta_term - beta_init) * t
+
+
+class Diffusion(BaseModule):
+    """Reverse-diffusion sampler (reference model/diffusion.py:227-272)."""
+
+    def __init__(self, n_feats, dim, n_spks=1, spk_emb_dim=64, beta_min=0.05, beta_max=20, pe_scale=1000):
+        super().__init__()
+        self.n_feats = n_feats
+        self.dim = dim
+        self.n_spks = n_spks
+        self.spk_emb_dim = spk_emb_dim
+        self.beta_min = beta_min
+        self.beta_max = beta_max
+        self.pe_scale = pe_scale
+        self.estimator = GradLogPEstimator2d(dim, n_spks=n_spks, spk_emb_dim=spk_emb_dim, n_feats=n_feats,
+                                             pe_scale=pe_scale)
+        self.estimator.beta_min, self.estimator.beta_max = beta_min, beta_max
+
+    @property
+    def precision(self):
+        return self.estimator.precision
+
+    @precision.setter
+    def precision(self, v):
+        self.estimator.precision = v
+
+    @torch.no_grad()
+    def reverse_diffusion(self, z, mask, mu, n_timesteps, stoc=False, spk=None, sde_noise=None):
+        """N Euler steps of the reverse ODE (model/diffusion.py:254-268).
+
+        `stoc` is accepted and ignored, exactly like the reference fork (it never reads the flag).
+        `sde_noise` (n_timesteps, B, 80, T) is an extension that switches on the upstream SDE update
+        x <- x - (0.5*(mu-x) - score)*beta*h + sqrt(beta*h)*noise with caller-supplied noise.
+        """
+        est = self.estimator
+        est.beta_min, est.beta_max, est.pe_scale = self.beta_min, self.beta_max, self.pe_scale
+        h = est._get_handle()
+        dev = next(self.parameters()).device
+        z_, mask_, mu_ = (est._prep(v, n, dev) for v, n in ((z, "z"), (mask, "mask"), (mu, "mu")))
+        B, T = est._check_shapes(z_, mask_, mu_, spk)
+        n_timesteps = int(n_timesteps)
+        spk_ = est._prep(spk, "spk", dev) if (spk is not None and self.n_spks > 1) else None
+        flags = est._flags()
+        noise_ = None
+        if sde_noise is not None:
+            noise_ = est._prep(sde_noise, "sde_noise", dev)
+            if tuple(noise_.shape) != (n_timesteps, B, self.n_feats, T):
+                raise ValueError("sde_noise must have shape (n_timesteps, B, 80, T)")
+            flags |= _lib.FLAG_SDE
+        out = torch.empty_like(z_)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = _lib.load().gtts_decoder_reverse_diffusion(
+                h, z_.data_ptr(), mask_.data_ptr(), mu_.data_ptr(), spk_.data_ptr() if spk_ is not None else None,
+                out.data_ptr(), B, T, n_timesteps, flags, noise_.data_ptr() if noise_ is not None else None,
+                ctypes.c_void_p(stream))
+        _lib.check(rc, "reverse_diffusion")
+        return out.to(z.dtype)
+
+    @torch.no_grad()
+    def forward(self, z, mask, mu, n_timesteps, stoc=False, spk=None):
+        # model/diffusion.py:270-272
+        return self.reverse_diffusion(z, mask, mu, n_timesteps, stoc, spk)
+
+    def reverse_diffusion_host(self, z, mask, mu, n_timesteps, spk=None, out=None):
+        """Same computation through the host-buffer C entry point: CPU (ideally pinned) tensors in, CPU tensor
+        out; the H2D/D2H copies happen inside the call (this is what bench.py's `e2e` leg times)."""
+        est = self.estimator
+        h = est._get_handle()
+        for t, n in ((z, "z"), (mask, "mask"), (mu, "mu")):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError(f"{n} must be a contiguous float32 CPU tensor")
+        B, _, T = z.shape
+        if out is None:
+            out = torch.empty_like(z)
+        rc = _lib.load().gtts_decoder_reverse_diffusion_host(
+            h, z.data_ptr(), mask.data_ptr(), mu.data_ptr(), spk.data_ptr() if spk is not None else None,
+            out.data_ptr(), B, T, int(n_timesteps), est._flags())
+        _lib.check(rc, "reverse_diffusion_host")
+        return out
+
+    # ---- training-side members of the reference class: outside this round's scope --------------------
+    def forward_diffusion(self, x0, mask, mu, t):
+        # model/diffusion.py:244-252; pure elementwise PyTorch, kept for callers
+        time = t.unsqueeze(-1).unsqueeze(-1)
+        cum_noise = get_noise(time, self.beta_min, self.beta_max, cumulative=True)
+        mean = x0 * torch.exp(-0.5 * cum_noise) + mu * (1.0 - torch.exp(-0.5 * cum_noise))
+        variance = 1.0 - torch.exp(-cum_noise)
+        z = torch.randn(x0.shape, dtype=x0.dtype, device=x0.device, requires_grad=False)
+        xt = mean + z * torch.sqrt(variance)
+        return xt * mask, z * mask
+
+    def loss_t(self, x0, mask, mu, t, spk=None):
+        raise NotImplementedError("training (estimator backward) is not part of the sm_100a hot path yet; "
+                                  "see DESIGN.md 'next' rows")
+
+    def compute_loss(self, x0, mask, mu, spk=None, offset=1e-5):
+        raise NotImplementedError("training (estimator backward) is not part of the sm_100a hot path yet; "
+                                  "see DESIGN.md 'next' rows")

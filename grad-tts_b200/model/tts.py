@@ -1,0 +1,131 @@
+"""GradTTS glue with the reference's signature (reference model/tts.py:21-108).
+
+Only the boundary is reproduced here: speaker embedding lookup, encoder call, duration -> length -> mask ->
+`generate_path` -> `mu_y`, the single RNG draw `z = mu_y + randn_like(mu_y) / temperature` (kept in PyTorch so
+the same seed gives the same z as the reference) and the decoder call, which runs on the sm_100a
+kernels.  The text encoder is NOT part of this hot path (out of scope); it is injected:
+pass `encoder=` (any module with the reference `TextEncoder.forward(x, x_lengths, spk) -> mu_x, logw, x_mask`
+contract), or leave it None inside the reference tree and `model.text_encoder.TextEncoder` is used.
+"""
+import math
+
+import torch
+
+from . import monotonic_align
+from .base import BaseModule
+from .diffusion import Diffusion
+from .utils import sequence_mask, generate_path, duration_loss, fix_len_compatibility  # noqa: F401
+
+
+def _reference_text_encoder(*args):
+    try:
+        from model.text_encoder import TextEncoder          # the reference's own module, if on sys.path
+    except Exception as e:                                  # pragma: no cover
+        raise RuntimeError(
+            "GradTTS needs a text encoder: pass `encoder=` or run inside the reference tree so that "
+            "`model.text_encoder.TextEncoder` is importable (the encoder is outside the B200 hot path)") from e
+    return TextEncoder(*args)
+
+
+class GradTTS(BaseModule):
+    def __init__(self, n_vocab, n_spks, spk_emb_dim, n_enc_channels, filter_channels, filter_channels_dp,
+                 n_heads, n_enc_layers, enc_kernel, enc_dropout, window_size,
+                 n_feats, dec_dim, beta_min, beta_max, pe_scale, encoder=None):
+        super().__init__()
+        self.n_vocab = n_vocab
+        self.n_spks = n_spks
+        self.spk_emb_dim = spk_emb_dim
+        self.n_enc_channels = n_enc_channels
+        self.filter_channels = filter_channels
+        self.filter_channels_dp = filter_channels_dp
+        self.n_heads = n_heads
+        self.n_enc_layers = n_enc_layers
+        self.enc_kernel = enc_kernel
+        self.enc_dropout = enc_dropout
+        self.window_size = window_size
+        self.n_feats = n_feats
+        self.dec_dim = dec_dim
+        self.beta_min = beta_min
+        self.beta_max = beta_max
+        self.pe_scale = pe_scale
+
+        if self.n_spks == -1:                                # model/tts.py:43-47
+            self.spk_emb = None
+        elif self.n_spks > 1:
+            self.spk_emb = torch.nn.Embedding(n_spks, spk_emb_dim)
+        if encoder is None:
+            encoder = _reference_text_encoder(n_vocab, n_feats, n_enc_channels, filter_channels, filter_channels_dp,
+                                              n_heads, n_enc_layers, enc_kernel, enc_dropout, window_size)
+        self.encoder = encoder
+        self.decoder = Diffusion(n_feats, dec_dim, n_spks, spk_emb_dim, beta_min, beta_max, pe_scale)
+
+    @torch.no_grad()
+    def forward(self, x, x_lengths, n_timesteps, temperature=1.0, stoc=False, spk=None, length_scale=1.0):
+        """Text -> (encoder_outputs, decoder_outputs, attn); reference model/tts.py:54-108."""
+        x, x_lengths = self.relocate_input([x, x_lengths])
+        if self.n_spks > 1:
+            spk = self.spk_emb(spk)                          # :77-79 (n_spks == -1 passes spk through)
+
+        mu_x, logw, x_mask = self.encoder(x, x_lengths, spk)               # :84
+
+        w = torch.exp(logw) * x_mask                                        # :86-90
+        w_ceil = torch.ceil(w) * length_scale
+        y_lengths = torch.clamp_min(torch.sum(w_ceil, [1, 2]), 1).long()
+        y_max_length = int(y_lengths.max())
+        y_max_length_ = fix_len_compatibility(y_max_length)
+
+        y_mask = sequence_mask(y_lengths, y_max_length_).unsqueeze(1).to(x_mask.dtype)    # :93-95
+        attn_mask = x_mask.unsqueeze(-1) * y_mask.unsqueeze(2)
+        attn = generate_path(w_ceil.squeeze(1), attn_mask.squeeze(1)).unsqueeze(1)
+
+        mu_y = torch.matmul(attn.squeeze(1).transpose(1, 2), mu_x.transpose(1, 2))        # :98-100
+        mu_y = mu_y.transpose(1, 2)
+        encoder_outputs = mu_y[:, :, :y_max_length]
+
+        z = mu_y + torch.randn_like(mu_y, device=mu_y.device) / temperature              # :103
+        decoder_outputs = self.decoder(z, y_mask, mu_y, n_timesteps, stoc, spk)           # :105  (sm_100a kernels)
+        decoder_outputs = decoder_outputs[:, :, :y_max_length]
+
+        return encoder_outputs, decoder_outputs, attn[:, :, :y_max_length]               # :108 (slices the text axis)
+
+    @torch.no_grad()
+    def align(self, mu_x, x_mask, y, y_mask):
+        """MAS between encoder outputs and a mel (reference model/tts.py:139-152, 224-231): builds the
+        log-prior with two device matmuls and runs `monotonic_align.maximum_path` on device."""
+        attn_mask = x_mask.unsqueeze(-1) * y_mask.unsqueeze(2)
+        const = -0.5 * math.log(2 * math.pi) * self.n_feats
+        factor = -0.5 * torch.ones(mu_x.shape, dtype=mu_x.dtype, device=mu_x.device)
+        y_square = torch.matmul(factor.transpose(1, 2), y ** 2)
+        y_mu_double = torch.matmul(2.0 * (factor * mu_x).transpose(1, 2), y)
+        mu_square = torch.sum(factor * (mu_x ** 2), 1).unsqueeze(-1)
+        log_prior = y_square - y_mu_double + mu_square + const
+        attn = monotonic_align.maximum_path(log_prior, attn_mask.squeeze(1))
+        return attn.detach()
+
+    def get_score_model(self, x, x_lengths, y, y_lengths, spk=None):
+        """Score model for a speech/text pair (reference model/tts.py:197-254): encoder + device MAS +
+        closure over the sm_100a estimator forward."""
+        x, x_lengths, y, y_lengths = self.relocate_input([x, x_lengths, y, y_lengths])
+        if self.n_spks > 1:
+            spk = self.spk_emb(spk)
+        mu_x, logw, x_mask = self.encoder(x, x_lengths, spk)
+        y_max_length = y.shape[-1]
+        y_mask = sequence_mask(y_lengths, y_max_length).unsqueeze(1).to(x_mask)
+        attn = self.align(mu_x, x_mask, y, y_mask)
+        mu_y = torch.matmul(attn.squeeze(1).transpose(1, 2), mu_x.transpose(1, 2)).transpose(1, 2)
+        estimator = self.decoder.estimator
+
+        class ScoreModel(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.y_mask, self.mu_y, self.spk = y_mask, mu_y, spk
+                self.estimator = estimator
+
+            def forward(self, x, t):
+                return self.estimator(x=x, mask=self.y_mask, mu=self.mu_y, t=t, spk=self.spk)
+
+        return ScoreModel(), mu_y, spk, y_mask
+
+    def compute_loss(self, x, x_lengths, y, y_lengths, spk=None, out_size=None):
+        raise NotImplementedError("training losses need the estimator backward, which is outside this round's "
+                                  "hot path; `align()` provides the on-device MAS used by compute_loss")

@@ -1,0 +1,95 @@
+/* gradtts_b200 -- C ABI of the B200-native Grad-TTS hot path (reverse-diffusion mel decoder + MAS).
+ *
+ * Plain pointers and sizes only; no torch types.  Every pointer is a DEVICE pointer on the handle's
+ * GPU unless the name says `_host`.  Every function that launches work takes the CUDA stream as a
+ * `void*` (cudaStream_t); nothing synchronises unless stated.  Return value 0 = success; non-zero =
+ * failure with a message available from gtts_last_error() (the Python host raises RuntimeError).
+ * There is no CPU fallback: on a machine without an sm_100 GPU gtts_decoder_create fails.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference):
+ *   gtts_mas_maximum_path          model/monotonic_align/__init__.py:8-23  maximum_path(value, mask)
+ *   gtts_mas_maximum_path_c        model/monotonic_align/core.pyx:40-45    maximum_path_c(paths, values, t_xs, t_ys, max_neg_val)
+ *   gtts_decoder_reverse_diffusion model/diffusion.py:254-272  Diffusion.forward / reverse_diffusion(z, mask, mu, n_timesteps, stoc, spk)
+ *   gtts_decoder_estimator         model/diffusion.py:174-216  GradLogPEstimator2d.forward(x, mask, mu, t, spk)
+ *   gtts_decoder_create/set_param  model/diffusion.py:128-172,227-242  module construction + load_state_dict
+ */
+#ifndef GRADTTS_B200_H
+#define GRADTTS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gtts_decoder gtts_decoder;
+
+#define GTTS_FLAG_FP32 1   /* true-fp32 arithmetic (FFMA convs, precise libm); default is bf16 tensor-core mode */
+#define GTTS_FLAG_SDE  2   /* north-star SDE update with caller-supplied noise (extension; the reference fork is ODE-only) */
+
+int gtts_version(void);
+const char* gtts_last_error(void);
+/* number of visible CUDA devices with compute capability 10.x (0 if none / no driver) */
+int gtts_sm100_device_count(void);
+
+/* ---- Monotonic Alignment Search ------------------------------------------------------------------
+ * value, mask: [B][t_x][t_y] fp32.  path: same shape, fp32, entries {0,1} (the reference returns
+ * value.dtype).  Lengths are taken from the mask exactly as the reference does:
+ * t_x = sum_x mask[b,x,0], t_y = sum_y mask[b,0,y]; the DP runs on value*mask.
+ * bits_ws: scratch for the direction bits when t_x*t_y is too large for shared memory
+ * (gtts_mas_workspace_bytes() bytes, may be NULL when that returns 0).
+ * status: one int32 on the device, set to 1 if any item had t_x > t_y (the reference's undefined case;
+ * that item's path is left all-zero).  The caller zero-initialises nothing: path and status are cleared here. */
+size_t gtts_mas_workspace_bytes(int B, int t_x, int t_y);
+int gtts_mas_maximum_path(const float* value, const float* mask, float* path, int B, int t_x, int t_y,
+                          void* bits_ws, size_t bits_ws_bytes, int32_t* status, void* stream);
+/* Same contract as the Cython entry point: int32 paths (cleared here), values already masked (NOT modified,
+ * unlike the reference which mutates its private copy), explicit lengths. */
+int gtts_mas_maximum_path_c(int32_t* paths, const float* values, const int32_t* t_xs, const int32_t* t_ys, int B,
+                            int t_x, int t_y, float max_neg_val, void* bits_ws, size_t bits_ws_bytes,
+                            int32_t* status, void* stream);
+/* Host-buffer convenience (pinned or pageable): H2D, kernel, D2H, stream sync. Returns status via *status_host. */
+int gtts_mas_maximum_path_host(const float* value_host, const float* mask_host, float* path_host, int B, int t_x,
+                               int t_y, int32_t* status_host, int device);
+
+/* ---- Decoder --------------------------------------------------------------------------------------
+ * n_spks follows the reference constructor: 1 (or <2) = two input channels; >1 = speaker channel, spk
+ * required; -1 = spk_mlp exists but is unused (params_tedlium.py). */
+int gtts_decoder_create(gtts_decoder** out, int n_spks, int n_feats, int dim, double beta_min, double beta_max,
+                        double pe_scale, int device);
+void gtts_decoder_destroy(gtts_decoder* d);
+/* Upload one tensor of Diffusion.state_dict() (key e.g. "estimator.downs.0.0.block1.block.0.weight"),
+ * fp32, contiguous, PyTorch layout; `data` may be a host or a device pointer.  Invalidates packed weights/plans. */
+int gtts_decoder_set_param(gtts_decoder* d, const char* name, const float* data, size_t numel);
+/* options: "max_chunk" (samples per workspace chunk), "use_graph" (0/1), "conv_impl_bf16" (1 tcgen05, 0 FFMA cross-check) */
+int gtts_decoder_set_option(gtts_decoder* d, const char* key, int value);
+
+/* z, mu, out: [B][80][T] fp32; mask: [B][1][T] fp32 with entries in {0,1}; spk: [B][64] or NULL;
+ * noise: [n_timesteps][B][80][T] (only with GTTS_FLAG_SDE).  T % 4 == 0.  out may alias z. */
+int gtts_decoder_reverse_diffusion(gtts_decoder* d, const float* z, const float* mask, const float* mu,
+                                   const float* spk, float* out, int B, int T, int n_timesteps, int flags,
+                                   const float* noise, void* stream);
+/* one score-network evaluation with per-sample times t[B] */
+int gtts_decoder_estimator(gtts_decoder* d, const float* x, const float* mask, const float* mu, const float* t,
+                           const float* spk, float* out, int B, int T, int flags, void* stream);
+/* Host-buffer variant of reverse_diffusion: copies inputs H2D, runs, copies the mel D2H, synchronises. */
+int gtts_decoder_reverse_diffusion_host(gtts_decoder* d, const float* z_host, const float* mask_host,
+                                        const float* mu_host, const float* spk_host, float* out_host, int B, int T,
+                                        int n_timesteps, int flags);
+/* kernels launched by the last reverse_diffusion / estimator call on this handle */
+long gtts_decoder_launches_last_call(const gtts_decoder* d);
+
+/* ---- Kernel-level test hooks (used by tests/ only) --------------------------------------------------
+ * conv: kind 0 = 3x3 s1, 1 = 1x1, 2 = 3x3 s2, 3 = convT 4x4 s2 p1.  impl 0 = FFMA, 1 = tcgen05 (bf16 only).
+ * act 0 = fp32, 1 = bf16 activations and packed weights.  weight_pt is the fp32 PyTorch-layout weight.
+ * Inputs/outputs are NHWC in the activation type.  gn_stats (B*16 floats, mean/rstd) may be NULL. */
+int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, int Cin1, int Cout,
+                   const void* src0, const void* src1, const float* weight_pt, const float* bias,
+                   const void* residual, const float* mask, void* out, float* gn_stats, int per_sample_weights,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRADTTS_B200_H */

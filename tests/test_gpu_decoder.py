@@ -1,0 +1,162 @@
+"""GPU: estimator / sampler / GradTTS through the drop-in modules, against golden fixtures and the oracle.
+
+Tolerances, all relative to the reference output's max-abs `s`:
+  fp32 mode : estimator 1e-5*max(1,s)  ... stated per test; 10-step decoder max-abs <= 1e-3 at |x|max ~ 140
+  bf16 mode : estimator max-abs <= 5e-2 on |score|max ~ 1.6; decoder rel-rms <= 2e-2
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import decoder_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+DEC = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
+             if os.path.basename(p).startswith(("est_", "dec_")))
+
+
+def _module(pkg, synth, n_spks, wseed, precision):
+    sd = synth.make_decoder_state_dict(n_spks, seed=wseed, g=0.05)
+    dec = pkg.Diffusion(80, 64, n_spks, 64, 0.05, 20.0, 1000)
+    missing = dec.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    dec = dec.to(DEV)
+    dec.precision = precision
+    return dec, sd
+
+
+def _run_golden(pkg, synth, name, precision):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    n_spks, n_steps = int(g["n_spks"]), int(g["n_steps"])
+    dec, _ = _module(pkg, synth, n_spks, int(g["wseed"]), precision)
+    z, mask, mu = (torch.from_numpy(g[k]).to(DEV) for k in ("z", "mask", "mu"))
+    spk = torch.from_numpy(g["spk"]).to(DEV) if "spk" in g else None
+    if n_steps == 0:
+        y = dec.estimator(z * mask, mask, mu, torch.from_numpy(g["t"]).to(DEV), spk)
+    else:
+        y = dec(z, mask, mu, n_steps, True, spk)            # stoc=True: ignored like the reference
+    return y.cpu(), torch.from_numpy(g["y"]), n_steps
+
+
+@pytest.mark.parametrize("name", DEC)
+def test_golden_fp32(name, pkg, synth):
+    y, ref, n_steps = _run_golden(pkg, synth, name, "fp32")
+    s = float(ref.abs().max())
+    err = float((y - ref).abs().max())
+    # single call: 1e-4 absolute on |score| ~ 1.6 ; sampler: the north-star bound max-abs 1e-3 (|x|max up to 141)
+    tol = 1e-4 if n_steps == 0 else 1e-3
+    assert err <= tol, f"{name}: max-abs {err} (|y|max {s})"
+
+
+@pytest.mark.parametrize("name", DEC)
+def test_golden_bf16(name, pkg, synth):
+    y, ref, n_steps = _run_golden(pkg, synth, name, "bf16")
+    s = float(ref.abs().max())
+    err = float((y - ref).abs().max())
+    relrms = float(((y - ref).pow(2).mean().sqrt()) / ref.pow(2).mean().sqrt())
+    if n_steps == 0:
+        assert err <= 5e-2, f"{name}: max-abs {err} (|y|max {s})"
+    else:
+        assert relrms <= 2e-2, f"{name}: rel-rms {relrms}, max-abs {err} (|y|max {s})"
+
+
+def test_masked_region_is_zero_and_inputs_untouched(pkg, synth):
+    dec, _ = _module(pkg, synth, 1, 0, "bf16")
+    z, mask, mu, _, lengths = synth.make_inputs(3, 48, 1, seed=3)
+    zc, mc, muc = z.to(DEV), mask.to(DEV), mu.to(DEV)
+    z0, mu0 = zc.clone(), muc.clone()
+    y = dec(zc, mc, muc, 3)
+    assert torch.equal(zc, z0) and torch.equal(muc, mu0)
+    assert float((y * (1 - mc)).abs().max()) == 0.0
+
+
+def test_batch_chunking_is_bitwise_invariant(pkg, synth):
+    """Per-sample maths: the same sample gives the same bits alone, in a batch, and across chunk sizes."""
+    dec, _ = _module(pkg, synth, 247, 3, "bf16")
+    z, mask, mu, spk, _ = synth.make_inputs(5, 40, 247, seed=4, ragged=False)
+    a = [t.to(DEV) for t in (z, mask, mu, spk)]
+    dec.estimator.max_chunk = 8
+    y_all = dec(a[0], a[1], a[2], 2, False, a[3])
+    dec.estimator.max_chunk = 2
+    y_chunk = dec(a[0], a[1], a[2], 2, False, a[3])
+    y_one = dec(a[0][3:4], a[1][3:4], a[2][3:4], 2, False, a[3][3:4])
+    assert torch.equal(y_all, y_chunk)
+    assert torch.equal(y_all[3:4], y_one)
+
+
+def test_sde_extension_matches_restatement(pkg, synth):
+    n_spks, B, T, n = 1, 2, 40, 3
+    dec, sd = _module(pkg, synth, n_spks, 0, "fp32")
+    z, mask, mu, _, _ = synth.make_inputs(B, T, n_spks, seed=12)
+    noise = torch.randn(n, B, 80, T, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        ref = decoder_oracle.reverse_diffusion(sd, z, mask, mu, n, True, None, n_spks, sde_noise=noise)
+    y = dec.reverse_diffusion(z.to(DEV), mask.to(DEV), mu.to(DEV), n, True, None, sde_noise=noise.to(DEV)).cpu()
+    assert float((y - ref).abs().max()) <= 1e-3
+
+
+def test_errors_are_loud(pkg, synth):
+    dec, _ = _module(pkg, synth, 1, 0, "bf16")
+    z, mask, mu, _, _ = synth.make_inputs(1, 40, 1, seed=3)
+    with pytest.raises(RuntimeError):
+        dec(z, mask, mu, 2)                                   # CPU inputs: no fallback
+    with pytest.raises(ValueError):
+        dec(z[:, :, :38].to(DEV), mask[:, :, :38].to(DEV), mu[:, :, :38].to(DEV), 2)      # T % 4 != 0
+    dec2 = pkg.Diffusion(80, 64, 1, 64, 0.05, 20.0, 1000)     # parameters on CPU
+    with pytest.raises(RuntimeError):
+        dec2(z.to(DEV), mask.to(DEV), mu.to(DEV), 2)
+
+
+class _StubEncoder(torch.nn.Module):
+    """Deterministic stand-in with the reference TextEncoder contract (mu_x, logw, x_mask)."""
+
+    def __init__(self, n_vocab, n_feats):
+        super().__init__()
+        self.emb = torch.nn.Embedding(n_vocab, n_feats)
+        self.dur = torch.nn.Embedding(n_vocab, 1)
+
+    def forward(self, x, x_lengths, spk=None):
+        x_mask = (torch.arange(x.shape[1], device=x.device)[None, :] < x_lengths[:, None]).unsqueeze(1).float()
+        mu_x = self.emb(x).transpose(1, 2) * x_mask
+        logw = (self.dur(x).transpose(1, 2).tanh() + 0.7) * x_mask
+        return mu_x, logw, x_mask
+
+
+def test_gradtts_forward_dropin(pkg, synth):
+    """Same seed => same z as the reference glue; return shapes incl. the attn slicing quirk (tts.py:108)."""
+    from oracle import decoder_oracle as do
+    torch.manual_seed(0)
+    enc = _StubEncoder(20, 80)
+    m = pkg.GradTTS(20, 1, 64, 192, 768, 256, 2, 6, 3, 0.1, 4, 80, 64, 0.05, 20.0, 1000, encoder=enc)
+    sd = synth.make_decoder_state_dict(1, seed=0, g=0.05)
+    m.decoder.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    m.decoder.precision = "fp32"
+    x = torch.randint(0, 20, (2, 13))
+    x_lengths = torch.tensor([13, 9])
+    torch.manual_seed(123)
+    enc_out, dec_out, attn = m(x, x_lengths, n_timesteps=3, temperature=1.5, stoc=False, length_scale=1.0)
+    # restate the glue on CPU with the same seed and compare against the oracle decoder
+    enc_cpu = _StubEncoder(20, 80)
+    enc_cpu.load_state_dict({k: v.cpu() for k, v in m.encoder.state_dict().items()})
+    mu_x, logw, x_mask = enc_cpu(x, x_lengths)
+    w_ceil = torch.ceil(torch.exp(logw) * x_mask)
+    y_lengths = torch.clamp_min(w_ceil.sum([1, 2]), 1).long()
+    y_max = int(y_lengths.max())
+    T = (y_max + 3) // 4 * 4
+    assert enc_out.shape == (2, 80, y_max) and dec_out.shape == (2, 80, y_max) and attn.shape == (2, 1, 13, T)
+    y_mask = (torch.arange(T)[None, :] < y_lengths[:, None]).unsqueeze(1).float()
+    utils = __import__("importlib").import_module("grad-tts_b200.model.utils")
+    attn_ref = utils.generate_path(w_ceil.squeeze(1), (x_mask.unsqueeze(-1) * y_mask.unsqueeze(2)).squeeze(1))
+    mu_y = torch.matmul(attn_ref.transpose(1, 2), mu_x.transpose(1, 2)).transpose(1, 2)
+    torch.manual_seed(123)
+    z = mu_y.to(DEV) + torch.randn_like(mu_y.to(DEV)) / 1.5          # the reference draws on the model device
+    with torch.no_grad():
+        ref = do.reverse_diffusion(sd, z.cpu(), y_mask, mu_y, 3)
+    assert float((enc_out.cpu() - mu_y[:, :, :y_max]).abs().max()) <= 1e-5
+    assert float((dec_out.cpu() - ref[:, :, :y_max]).abs().max()) <= 1e-3

@@ -1,0 +1,135 @@
+"""First-contact diagnostics on the GPU box: every stage prints numbers instead of asserting, so one run tells
+what works.  Usage: python tools/gpu_diag.py <stage>   (stages: mas conv_ffma conv_tc dec_fp32 dec_bf16_ffma dec_bf16_tc perf)"""
+import importlib
+import os
+import sys
+import time
+import traceback
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+
+pkg = importlib.import_module("grad-tts_b200")
+from oracle import decoder_oracle, mas_oracle  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def stage_mas():
+    for B, tx, ty in [(2, 7, 9), (4, 50, 120), (64, 200, 1000)]:
+        value, mask, _, _ = pkg.synth.make_mas_inputs(B, tx, ty, seed=5)
+        ref = mas_oracle.maximum_path(value, mask)
+        v, m = value.to(DEV), mask.to(DEV)
+        got = pkg.maximum_path(v, m).cpu()
+        print(f"mas {B}x{tx}x{ty}: equal={torch.equal(ref, got)} ones ref/got {int(ref.sum())}/{int(got.sum())}")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            pkg.maximum_path(v, m, check=False)
+        torch.cuda.synchronize()
+        print(f"   wrapper time {(time.perf_counter() - t0) / 10 * 1e3:.3f} ms")
+
+
+def stage_conv(impl, act):
+    import gpu_util as gu
+    for name, kw in gu.CONV_CASES:
+        try:
+            c = gu.conv_case(seed=hash(name) % 1000, **kw)
+            stats_ok = c["kind"] in (0, 1) and c["r"] is None and c["m"] is None and not c["per_sample"]
+            out, st = gu.run_conv(c, impl, act, want_stats=stats_ok)
+            ref, raw = gu.conv_reference(c, round_bf16=bool(act))
+            err = float((out - ref).abs().max())
+            nan = int(torch.isnan(out).sum())
+            serr = -1.0
+            if stats_ok:
+                sref = gu.gn_stats_reference(raw)
+                serr = float(((st - sref).abs() / (sref.abs() + 1.0)).max())
+            print(f"conv impl={impl} act={act} {name}: max-abs err {err:.3e} nan {nan} stats-err {serr:.3e} "
+                  f"|ref|max {float(ref.abs().max()):.2f}")
+            if err > 0.1 or nan:
+                d = (out - ref).abs()
+                d[torch.isnan(d)] = 1e9
+                bad = (d > 0.1)
+                idx = bad.nonzero()
+                print(f"     bad {int(bad.sum())} of {bad.numel()}; first {idx[:6].tolist()} last {idx[-3:].tolist()}")
+                print("     per-channel-bad", bad.sum((0, 2, 3))[:16].tolist(), "per-row-bad", bad.sum((0, 1, 3))[:24].tolist())
+                print("     per-col-bad", bad.sum((0, 1, 2))[:40].tolist())
+        except Exception:
+            print(f"conv impl={impl} act={act} {name}: EXCEPTION")
+            traceback.print_exc()
+
+
+def _decoder(n_spks, wseed, precision, conv_impl=None):
+    sd = pkg.synth.make_decoder_state_dict(n_spks, seed=wseed, g=0.05)
+    dec = pkg.Diffusion(80, 64, n_spks, 64, 0.05, 20.0, 1000)
+    dec.load_state_dict(sd)
+    dec = dec.to(DEV)
+    dec.precision = precision
+    if conv_impl is not None:
+        h = dec.estimator._get_handle()
+        pkg._lib.check(pkg._lib.load().gtts_decoder_set_option(h, b"conv_impl_bf16", conv_impl), "opt")
+    return dec, sd
+
+
+def stage_dec(precision, conv_impl=None):
+    torch.set_num_threads(os.cpu_count() or 8)
+    for n_spks, B, T, n in [(1, 2, 48, 0), (247, 2, 40, 0), (1, 1, 64, 10), (247, 2, 40, 3)]:
+        try:
+            dec, sd = _decoder(n_spks, 0, precision, conv_impl)
+            z, mask, mu, spk, _ = pkg.synth.make_inputs(B, T, n_spks, seed=7)
+            d = lambda t: None if t is None else t.to(DEV)
+            with torch.no_grad():
+                if n == 0:
+                    t = torch.tensor([0.3, 0.9][:B])
+                    ref = decoder_oracle.estimator_forward(sd, z * mask, mask, mu, t, spk, n_spks)
+                    got = dec.estimator(d(z * mask), d(mask), d(mu), d(t), d(spk)).cpu()
+                else:
+                    ref = decoder_oracle.reverse_diffusion(sd, z, mask, mu, n, False, spk, n_spks)
+                    got = dec(d(z), d(mask), d(mu), n, False, d(spk)).cpu()
+            err = float((got - ref).abs().max())
+            rr = float((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())
+            print(f"dec {precision} impl={conv_impl} n_spks={n_spks} B={B} T={T} steps={n}: max-abs {err:.3e} "
+                  f"rel-rms {rr:.3e} |ref|max {float(ref.abs().max()):.2f} nan {int(torch.isnan(got).sum())} "
+                  f"launches {dec.estimator.launches_last_call()}")
+        except Exception:
+            print(f"dec {precision} impl={conv_impl} n_spks={n_spks}: EXCEPTION")
+            traceback.print_exc()
+
+
+def stage_perf():
+    for (n_spks, B, T, n, chunk) in [(1, 1, 400, 10, 8), (1, 8, 800, 4, 8), (247, 32, 800, 2, 8), (1, 16, 1720, 2, 4),
+                                     (1, 16, 1720, 2, 8), (1, 16, 1720, 2, 16)]:
+        try:
+            dec, _ = _decoder(n_spks, 0, "bf16")
+            dec.estimator.max_chunk = chunk
+            z, mask, mu, spk, _ = pkg.synth.make_inputs(B, T, n_spks, seed=7, ragged=False)
+            d = lambda t: None if t is None else t.to(DEV)
+            a = (d(z), d(mask), d(mu))
+            s = d(spk)
+            dec(*a, n, False, s)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dec(*a, n, False, s)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            fs = B * T * n / (ms * 1e-3)
+            print(f"perf n_spks={n_spks} B={B} T={T} steps={n} chunk={chunk}: {ms:.2f} ms  {fs / 1e6:.3f} M frame-steps/s  "
+                  f"{fs * 134.154e6 / 1e12:.1f} TFLOP/s  mem {torch.cuda.memory_allocated() / 2**30:.1f} GiB torch")
+            del dec
+        except Exception:
+            print(f"perf {n_spks} {B} {T}: EXCEPTION")
+            traceback.print_exc()
+
+
+if __name__ == "__main__":
+    st = sys.argv[1]
+    print(f"===== stage {st} on {torch.cuda.get_device_name(0)}", flush=True)
+    {"mas": stage_mas, "conv_ffma": lambda: (stage_conv(0, 0), stage_conv(0, 1)), "conv_tc": lambda: stage_conv(1, 1),
+     "dec_fp32": lambda: stage_dec("fp32"), "dec_bf16_ffma": lambda: stage_dec("bf16", 0),
+     "dec_bf16_tc": lambda: stage_dec("bf16", 1), "perf": stage_perf}[st]()
+    torch.cuda.synchronize()
+    print(f"===== stage {st} done", flush=True)
