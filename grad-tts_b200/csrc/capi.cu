@@ -182,6 +182,11 @@ int gtts_decoder_reverse_diffusion_host(gtts_decoder* h, const float* z_host, co
     return 0;
 }
 
+int gtts_decoder_profile_step(gtts_decoder* h, int B, int T, int flags, int reps, char* buf, size_t buflen, void* stream) {
+    GTTS_REQUIRE(h != nullptr, "null decoder handle");
+    return decoder_profile_step(h->impl, B, T, flags, reps, buf, buflen, (cudaStream_t)stream);
+}
+
 long gtts_decoder_launches_last_call(const gtts_decoder* h) { return h ? decoder_launches_last_call(h->impl) : 0; }
 
 // ------------------------------------------------------------------------------------------------ test hooks

@@ -314,6 +314,13 @@ struct Plan {
     DevMem mem;
     std::vector<TcConvPlan*> tc_plans;
     std::vector<std::function<int(cudaStream_t)>> ops;
+    struct OpInfo { std::string name; int is_conv; double flops; double bytes; };
+    std::vector<OpInfo> info;
+    void push(const std::string& name, int is_conv, double flops, double bytes, std::function<int(cudaStream_t)> fn) {
+        ops.push_back(std::move(fn));
+        info.push_back(OpInfo{name, is_conv, flops, bytes});
+        kernels_per_step++;
+    }
     // plan-owned I/O
     float *xt = nullptr, *mu = nullptr, *m0 = nullptr, *m1 = nullptr, *m2 = nullptr, *splane = nullptr, *spk = nullptr;
     float *tb = nullptr, *t_tab = nullptr, *beta_tab = nullptr, *t_per_sample = nullptr, *score = nullptr;
@@ -374,15 +381,23 @@ struct PlanBuilder {
             e.gn_partials = pl->partials; e.gn_stats = gn_stats; e.gn_counters = pl->counters; e.gn_eps = 1e-5f;
             if (slots_for(g) > pl->partial_slots) { set_error("internal: GN partial buffer too small"); failed = true; return; }
         }
-        pl->kernels_per_step++;
+        const double cin = g.Cin0 + g.Cin1;
+        const double npx = (double)g.B * g.nphase * g.Hg * g.Wg;
+        const double flops = 2.0 * npx * g.Cout * g.ntaps * cin;
+        const double es = (double)esize(kind);
+        // algorithmic bytes: read every input once, write every output once, weights once
+        const double bytes = ((double)g.B * g.Hin * g.Win * cin + (double)g.B * g.Hout * g.Wout * g.Cout * (residual ? 2 : 1)) * es +
+                             (double)wrows * cin * es;
+        std::string name = std::string(g.nphase == 4 ? "convT4x4" : (g.ntaps == 9 ? (g.stride == 2 ? "conv3x3s2" : "conv3x3") : "conv1x1")) +
+                           "_" + std::to_string((int)cin) + "_" + std::to_string(g.Cout) + "_h" + std::to_string(g.Hin);
         if (use_tc()) {
             TcConvPlan* tp = conv_tc_plan_create(g, src0, src1, w, wrows, e, d->num_sms);
             if (!tp) { failed = true; return; }
             pl->tc_plans.push_back(tp);
-            pl->ops.push_back([tp](cudaStream_t s) { return conv_tc_launch(tp, s); });
+            pl->push(name, 1, flops, bytes, [tp](cudaStream_t s) { return conv_tc_launch(tp, s); });
         } else {
             ActKind k = kind;
-            pl->ops.push_back([k, g, src0, src1, w, e](cudaStream_t s) { return conv_ffma(k, g, src0, src1, w, e, s); });
+            pl->push(name, 1, flops, bytes, [k, g, src0, src1, w, e](cudaStream_t s) { return conv_ffma(k, g, src0, src1, w, e, s); });
         }
     }
 
@@ -400,8 +415,9 @@ struct PlanBuilder {
         a.out = out; a.B = B; a.H = H[lvl]; a.W = W[lvl]; a.C = C;
         ActKind k = kind;
         bool st_ = strict;
-        pl->kernels_per_step++;
-        pl->ops.push_back([k, a, st_](cudaStream_t s) { return gn_apply(k, a, st_, s); });
+        const double el = (double)B * H[lvl] * W[lvl] * C;
+        pl->push("gn_apply_" + std::to_string(C) + "_h" + std::to_string(H[lvl]), 0, 0.0,
+                 el * esize(kind) * (residual ? 3 : 2), [k, a, st_](cudaStream_t s) { return gn_apply(k, a, st_, s); });
     }
 
     // ResnetBlock (:61-79).  x0/x1 are the (masked) input sources; returns the masked output.
@@ -420,8 +436,9 @@ struct PlanBuilder {
             f.raw = raw1; f.gn_partials = pl->partials; f.gn_stats = st1; f.gn_counters = pl->counters; f.gn_eps = 1e-5f;
             if (first_conv_partials_slots(H[0], W[0]) > pl->partial_slots) { set_error("internal: GN partial buffer too small"); failed = true; return nullptr; }
             ActKind k = kind;
-            pl->kernels_per_step++;
-            pl->ops.push_back([k, f](cudaStream_t s) { return first_conv(k, f, s); });
+            const double px = (double)B * H[0] * W[0];
+            pl->push("first_conv", 0, 2.0 * px * 64 * 9 * d->cin_first, px * (8 + 64 * esize(kind)),
+                     [k, f](cudaStream_t s) { return first_conv(k, f, s); });
         } else {
             add_conv(geom_3x3(B, H[lvl], W[lvl], c0, c1, Co, 1), x0, x1, R.b1.w, 9 * Co, R.b1.bias, nullptr, nullptr, raw1, st1);
         }
@@ -459,12 +476,13 @@ struct PlanBuilder {
         AttnCtxArgs ca{kv, B, n, partials, counters, ctxn, chunks, chunk_len};
         ActKind k = kind;
         bool st_ = strict;
-        pl->kernels_per_step += 2;
-        pl->ops.push_back([k, ca, st_](cudaStream_t s) { return attn_ctx(k, ca, st_, s); });
+        pl->push("attn_ctx_h" + std::to_string(H[lvl]), 0, 2.0 * B * 4 * (double)n * 1024, (double)B * n * 256 * esize(kind),
+                 [k, ca, st_](cudaStream_t s) { return attn_ctx(k, ca, st_, s); });
         const float *wout = A.wout, *wq = A.wq;
         float g = A.g;
         int Bb = B;
-        pl->ops.push_back([k, ctxn, wout, wq, g, mb, Bb, C](cudaStream_t s) { return attn_fold(k, ctxn, wout, wq, g, mb, Bb, C, s); });
+        pl->push("attn_fold_" + std::to_string(C), 0, 2.0 * B * ((double)C * 128 * 32 + (double)C * C * 128), 0.0,
+                 [k, ctxn, wout, wq, g, mb, Bb, C](cudaStream_t s) { return attn_fold(k, ctxn, wout, wq, g, mb, Bb, C, s); });
         add_conv(geom_1x1(B, H[lvl], W[lvl], C, 0, C, C), x, nullptr, mb, B * C, A.gb, x, lmask[lvl], out, nullptr);
         return out;
     }
@@ -535,8 +553,7 @@ struct PlanBuilder {
             float* tb = pl->tb;
             int nb = pl->est_mode ? B : 1;
             bool st_ = strict;
-            pl->kernels_per_step++;
-            pl->ops.push_back([tw, tsrc, step, is_table, pes, tb, nb, st_](cudaStream_t s) {
+            pl->push("temb", 0, 0.0, 0.0, [tw, tsrc, step, is_table, pes, tb, nb, st_](cudaStream_t s) {
                 return temb_bias(tw, tsrc, step, is_table, pes, tb, nb, st_, s);
             });
         }
@@ -587,14 +604,14 @@ struct PlanBuilder {
             Plan* plan = pl;
             ActKind k = kind;
             bool st_ = strict;
-            pl->kernels_per_step += 2;
-            pl->ops.push_back([k, e, st_, plan](cudaStream_t s) {
+            const double px = (double)B * H[0] * W[0];
+            pl->push("euler_step", 0, 0.0, px * (64 * esize(kind) + 12), [k, e, st_, plan](cudaStream_t s) {
                 EulerArgs ee = e;
                 ee.noise_step_stride = plan->noise_step_stride;
                 return euler_step(k, ee, st_, s);
             });
             int* step = pl->step;
-            pl->ops.push_back([step](cudaStream_t s) { return advance_step(step, s); });
+            pl->push("advance_step", 0, 0.0, 0.0, [step](cudaStream_t s) { return advance_step(step, s); });
         }
         return 0;
     }
@@ -776,6 +793,46 @@ int decoder_estimator(Decoder* d, const float* x, const float* mask, const float
         d->launches_last_call += pl->kernels_per_step + 3;
     }
     GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Runs one step of the cached sampler plan for (B<=max_chunk, T) eagerly, `reps` times, with a CUDA event pair
+// around every launch; writes a JSON report {ops:[{name,is_conv,flops,bytes,ms}...]} into buf.
+int decoder_profile_step(Decoder* d, int B, int T, int flags, int reps, char* buf, size_t buflen, cudaStream_t stream) {
+    if (int rc = common_checks(d, B, T, (const float*)1)) return rc;
+    GTTS_REQUIRE(buf != nullptr && buflen > 64 && reps >= 1, "profile: bad arguments");
+    const ActKind kind = (flags & 1) ? ACT_F32 : ACT_BF16;
+    const int Bc = std::min(d->max_chunk, B);
+    Plan* pl = nullptr;
+    if (int rc = get_plan(d, kind, Bc, T, false, false, &pl)) return rc;
+    const size_t nops = pl->ops.size();
+    std::vector<cudaEvent_t> ev(2 * nops);
+    for (auto& e : ev) GTTS_CHECK_CUDA(cudaEventCreate(&e));
+    std::vector<double> ms(nops, 0.0);
+    for (int r = 0; r < reps; ++r) {
+        for (size_t i = 0; i < nops; ++i) {
+            GTTS_CHECK_CUDA(cudaEventRecord(ev[2 * i], stream));
+            if (int rc = pl->ops[i](stream)) return rc;
+            GTTS_CHECK_CUDA(cudaEventRecord(ev[2 * i + 1], stream));
+        }
+        GTTS_CHECK_CUDA(cudaStreamSynchronize(stream));
+        for (size_t i = 0; i < nops; ++i) {
+            float t = 0.f;
+            GTTS_CHECK_CUDA(cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]));
+            ms[i] += t / reps;
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    std::string js = "{\"B\":" + std::to_string(Bc) + ",\"T\":" + std::to_string(T) + ",\"ops\":[";
+    for (size_t i = 0; i < nops; ++i) {
+        char tmp[512];
+        snprintf(tmp, sizeof(tmp), "%s{\"name\":\"%s\",\"is_conv\":%d,\"flops\":%.6e,\"bytes\":%.6e,\"ms\":%.6f}",
+                 i ? "," : "", pl->info[i].name.c_str(), pl->info[i].is_conv, pl->info[i].flops, pl->info[i].bytes, ms[i]);
+        js += tmp;
+    }
+    js += "]}";
+    GTTS_REQUIRE(js.size() + 1 <= buflen, "profile: report buffer too small");
+    memcpy(buf, js.c_str(), js.size() + 1);
     return 0;
 }
 

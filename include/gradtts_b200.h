@@ -77,6 +77,10 @@ int gtts_decoder_estimator(gtts_decoder* d, const float* x, const float* mask, c
 int gtts_decoder_reverse_diffusion_host(gtts_decoder* d, const float* z_host, const float* mask_host,
                                         const float* mu_host, const float* spk_host, float* out_host, int B, int T,
                                         int n_timesteps, int flags);
+/* Measurement hook: replays one Euler step of the (min(B,max_chunk), T) sampler plan eagerly `reps` times with a CUDA
+ * event pair around every launch (on `stream`) and writes a JSON report
+ * {"B":..,"T":..,"ops":[{"name","is_conv","flops","bytes","ms"},...]} (algorithmic flops/bytes per launch) into buf. */
+int gtts_decoder_profile_step(gtts_decoder* d, int B, int T, int flags, int reps, char* buf, size_t buflen, void* stream);
 /* kernels launched by the last reverse_diffusion / estimator call on this handle */
 long gtts_decoder_launches_last_call(const gtts_decoder* d);
 
