@@ -25,8 +25,7 @@ attn_ctx_kernel(AttnCtxArgs a) {
     __shared__ __align__(16) float ks[kSub * kKPitch];
     __shared__ __align__(16) float vs[kSub * 32];
     __shared__ float s_m[32], s_scale[32];
-    __shared__ int s_flag;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int chunk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
     const int n0 = chunk * a.chunk_len;
     const int n1 = min(a.n, n0 + a.chunk_len);
@@ -127,27 +126,153 @@ attn_ctx_kernel(AttnCtxArgs a) {
         part[32 + i] = s;                                 // [32..64) = l, [64..1088) = ctx
     }
     if (tid < 32) part[tid] = s_m[tid];
-    __threadfence();
-    __syncthreads();
+}
 
-    // ---- ticket: the last chunk of this (b, head) merges all partials
-    if (tid == 0) {
-        __threadfence();
-        unsigned int old = atomicAdd(&a.counters[b * 4 + head], 1u);
-        s_flag = (old == (unsigned int)(a.chunks - 1));
+// ---------------------------------------------------------------------------------------------------------
+// bf16 path: the context contraction ctx[d][e] = sum_n p[n][d] v[n][e] on the (legacy-path) tensor cores.
+// One CTA = 4 warps = the 4 heads of one pixel chunk; per 64-pixel sub-tile the kv rows (512 B/pixel) are staged
+// once in shared memory, each warp turns its 32 k-columns into p = exp(k - running max) in place (bf16), and
+// runs P^T V as mma.sync.m16n8k16 (A and B both fetched with ldmatrix.trans from the [pixel][channel] rows).
+// HBM-bound by design: kv is read exactly once.
+constexpr int kTcSub = 64;
+constexpr int kTcPitch = 264;        // bf16 per smem pixel row: 256 + 8 pad (528 B, conflict-free ldmatrix)
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_ptr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(smem_ptr)));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(128)
+attn_ctx_tc_kernel(AttnCtxArgs a) {
+    __shared__ __align__(16) __nv_bfloat16 sm[kTcSub * kTcPitch];
+    const int tid = threadIdx.x, head = tid >> 5, lane = tid & 31;
+    const int chunk = blockIdx.x, b = blockIdx.y;
+    const int n0 = chunk * a.chunk_len, n1 = min(a.n, n0 + a.chunk_len);
+    const __nv_bfloat16* kv = reinterpret_cast<const __nv_bfloat16*>(a.kv) + (size_t)b * a.n * 256;
+
+    const int cp = lane & 15, par = lane >> 4;          // element-wise phase: columns 2cp, 2cp+1 ; pixel parity
+    const int g = lane >> 2, t = lane & 3;              // mma fragment coordinates
+    float acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    uint32_t* kw = reinterpret_cast<uint32_t*>(sm) + head * 16 + cp;      // word (2 bf16) of my k columns, pixel 0
+    constexpr int kWordPitch = kTcPitch / 2;
+
+    for (int p0 = n0; p0 < n1; p0 += kTcSub) {
+        __syncthreads();                                 // all warps are done with the previous sub-tile
+#pragma unroll 4
+        for (int it = 0; it < 16; ++it) {
+            const int idx = it * 128 + tid, px = idx >> 5, c16 = idx & 31, n = p0 + px;
+            uint4 val;
+            if (n < n1) val = __ldg(reinterpret_cast<const uint4*>(kv + (size_t)n * 256 + c16 * 8));
+            else if (c16 < 16) val = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);   // k = -inf
+            else val = make_uint4(0u, 0u, 0u, 0u);                                                      // v = 0
+            *reinterpret_cast<uint4*>(&sm[px * kTcPitch + c16 * 8]) = val;
+        }
+        __syncthreads();
+        // ---- running max of my two k columns
+        float x0 = -INFINITY, x1 = -INFINITY;
+#pragma unroll 8
+        for (int i = 0; i < kTcSub / 2; ++i) {
+            const uint32_t w = kw[(2 * i + par) * kWordPitch];
+            x0 = fmaxf(x0, __uint_as_float(w << 16));
+            x1 = fmaxf(x1, __uint_as_float(w & 0xffff0000u));
+        }
+        x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 16));
+        x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 16));
+        const float mn0 = fmaxf(m0, x0), mn1 = fmaxf(m1, x1);
+        const float sc0 = __expf(m0 - mn0), sc1 = __expf(m1 - mn1);       // exp(-inf) = 0 on the first sub-tile
+        m0 = mn0; m1 = mn1;
+        // ---- p = exp(k - m) in place (bf16); the row sums use the rounded values the MMA will see
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < kTcSub / 2; ++i) {
+            uint32_t* wp = kw + (2 * i + par) * kWordPitch;
+            const uint32_t w = *wp;
+            const float e0 = __expf(__uint_as_float(w << 16) - mn0), e1 = __expf(__uint_as_float(w & 0xffff0000u) - mn1);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
+            const uint32_t pw = *reinterpret_cast<uint32_t*>(&h2);
+            *wp = pw;
+            s0 += __uint_as_float(pw << 16);
+            s1 += __uint_as_float(pw & 0xffff0000u);
+        }
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+        l0 = fmaf(l0, sc0, s0);
+        l1 = fmaf(l1, sc1, s1);
+        __syncwarp();
+        // ---- rescale the accumulators: row d = mt*16 + hh*8 + g, its factor lives in lane d>>1, element d&1
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int d = mt * 16 + hh * 8 + g;
+                const float f0 = __shfl_sync(0xffffffffu, sc0, d >> 1), f1 = __shfl_sync(0xffffffffu, sc1, d >> 1);
+                const float f = (d & 1) ? f1 : f0;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) { acc[mt][nt][hh * 2] *= f; acc[mt][nt][hh * 2 + 1] *= f; }
+            }
+        // ---- ctx += P^T V over 4 k16 steps
+        const int j = lane >> 3, r = lane & 7;
+#pragma unroll
+        for (int ks = 0; ks < kTcSub / 16; ++ks) {
+            const int pxb = ks * 16;
+            uint32_t af[2][4], bf[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+                ldmatrix_x4_trans(af[mt], &sm[(pxb + (j >> 1) * 8 + r) * kTcPitch + head * 32 + mt * 16 + (j & 1) * 8]);
+#pragma unroll
+            for (int np = 0; np < 2; ++np)
+                ldmatrix_x4_trans(bf[np], &sm[(pxb + (j & 1) * 8 + r) * kTcPitch + 128 + head * 32 + (np * 2 + (j >> 1)) * 8]);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+                    mma_bf16_16816(acc[mt][nt], af[mt], bf[nt >> 1][(nt & 1) * 2], bf[nt >> 1][(nt & 1) * 2 + 1]);
+        }
     }
-    __syncthreads();
-    if (!s_flag) return;
-    __threadfence();
+    // ---- this chunk's partial (m[32], l[32], ctx[32][32]) for (b, head)
+    float* part = a.partials + (((size_t)b * 4 + head) * a.chunks + chunk) * 1088;
+    if (par == 0) {
+        part[2 * cp] = m0; part[2 * cp + 1] = m1;
+        part[32 + 2 * cp] = l0; part[32 + 2 * cp + 1] = l1;
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int d = mt * 16 + hh * 8 + g, e = nt * 8 + 2 * t;
+                *reinterpret_cast<float2*>(&part[64 + d * 32 + e]) = make_float2(acc[mt][nt][hh * 2], acc[mt][nt][hh * 2 + 1]);
+            }
+}
+
+// Deterministic merge of the per-chunk partials: grid (4 heads, B), 256 threads.
+template <bool kStrict>
+__global__ void __launch_bounds__(256)
+attn_merge_kernel(AttnCtxArgs a) {
+    __shared__ float s_m[32], s_scale[32];
+    const int tid = threadIdx.x, head = blockIdx.x, b = blockIdx.y;
     const float* pbase = a.partials + ((size_t)b * 4 + head) * a.chunks * 1088;
     if (tid < 32) {
         float M = -INFINITY;
-        for (int c = 0; c < a.chunks; ++c) M = fmaxf(M, __ldcg(pbase + (size_t)c * 1088 + tid));
+        for (int c = 0; c < a.chunks; ++c) M = fmaxf(M, pbase[(size_t)c * 1088 + tid]);
         float l = 0.f;
         for (int c = 0; c < a.chunks; ++c) {
-            const float mc = __ldcg(pbase + (size_t)c * 1088 + tid);
+            const float mc = pbase[(size_t)c * 1088 + tid];
             const float wgt = kStrict ? expf(mc - M) : __expf(mc - M);
-            l += wgt * __ldcg(pbase + (size_t)c * 1088 + 32 + tid);
+            l += wgt * pbase[(size_t)c * 1088 + 32 + tid];
         }
         s_m[tid] = M;
         s_scale[tid] = 1.0f / l;
@@ -158,25 +283,27 @@ attn_ctx_kernel(AttnCtxArgs a) {
         const float M = s_m[d];
         float s = 0.f;
         for (int c = 0; c < a.chunks; ++c) {
-            const float mc = __ldcg(pbase + (size_t)c * 1088 + d);
+            const float mc = pbase[(size_t)c * 1088 + d];
             const float wgt = kStrict ? expf(mc - M) : __expf(mc - M);
-            s += wgt * __ldcg(pbase + (size_t)c * 1088 + 64 + i);
+            s += wgt * pbase[(size_t)c * 1088 + 64 + i];
         }
         a.ctxn[((size_t)b * 4 + head) * 1024 + i] = s * s_scale[d];
     }
-    if (tid == 0) a.counters[b * 4 + head] = 0u;
-    (void)lane;
 }
 
-// grid (C/16, B), 256 threads
+// grid (C/16 output-row tiles, C/64 input-column tiles, B), 256 threads.  Each CTA builds 16 rows of
+// P = Wout * blockdiag(ctxn^T) (cheap, recomputed per column tile) and multiplies them with a 128 x 64 slice of
+// Wq staged in shared memory.
 template <typename WT>
 __global__ void __launch_bounds__(256)
 attn_fold_kernel(const float* __restrict__ ctxn, const float* __restrict__ wout, const float* __restrict__ wq,
                  float g, WT* __restrict__ mb, int C) {
-    __shared__ float cs[4 * 32 * 33];
-    __shared__ float ws[16 * 128];
-    __shared__ float P[16 * 128];
-    const int tid = threadIdx.x, b = blockIdx.y, co0 = blockIdx.x * 16;
+    __shared__ __align__(16) float buf[128 * 64];                    // phase 1: cs + ws ; phase 2: Wq slice
+    __shared__ float P[16 * 129];
+    float* cs = buf;                                                 // [4*32][33]
+    float* ws = buf + 4 * 32 * 33;                                   // [16][128]
+    float* qs = buf;                                                 // [128][64]
+    const int tid = threadIdx.x, b = blockIdx.z, co0 = blockIdx.x * 16, ci0 = blockIdx.y * 64;
     for (int i = tid; i < 4096; i += 256) {
         const int h = i >> 10, d = (i >> 5) & 31, e = i & 31;
         cs[(h * 32 + d) * 33 + e] = ctxn[(size_t)b * 4096 + i];
@@ -187,31 +314,31 @@ attn_fold_kernel(const float* __restrict__ ctxn, const float* __restrict__ wout,
         const int cl = tid >> 4, part = tid & 15;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int hd = part * 8 + k, h = hd >> 5;
+            const int hd = part + 16 * k, h = hd >> 5;
             float s = 0.f;
 #pragma unroll 8
             for (int e = 0; e < 32; ++e) s = fmaf(ws[cl * 128 + h * 32 + e], cs[hd * 33 + e], s);
-            P[cl * 128 + hd] = s;
+            P[cl * 129 + hd] = s;
         }
     }
     __syncthreads();
-    {   // M[co][ci] = g * sum_hd P[cl][hd] * Wq[hd][ci]
-        const int cl = tid >> 4, cg = tid & 15;
-        const int nk = C >> 4;
-        float acc[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+    for (int i = tid; i < 128 * 16; i += 256) {                      // 128 rows x 16 float4
+        const int r = i >> 4, c4 = i & 15;
+        *reinterpret_cast<float4*>(&qs[r * 64 + c4 * 4]) =
+            __ldg(reinterpret_cast<const float4*>(wq + (size_t)r * C + ci0 + c4 * 4));
+    }
+    __syncthreads();
+    {   // M[co][ci] = g * sum_hd P[cl][hd] * Wq[hd][ci]: thread -> (row cl, 4 consecutive columns)
+        const int cl = tid >> 4, cq = (tid & 15) * 4;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
         for (int hd = 0; hd < 128; ++hd) {
-            const float pv = P[cl * 128 + hd];
-            const float* wr = wq + (size_t)hd * C + cg;
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-                if (k < nk) acc[k] = fmaf(pv, __ldg(wr + 16 * k), acc[k]);
+            const float pv = P[cl * 129 + hd];
+            const float4 q4 = *reinterpret_cast<const float4*>(&qs[hd * 64 + cq]);
+            a0 = fmaf(pv, q4.x, a0); a1 = fmaf(pv, q4.y, a1); a2 = fmaf(pv, q4.z, a2); a3 = fmaf(pv, q4.w, a3);
         }
-        WT* o = mb + ((size_t)b * C + co0 + cl) * C + cg;
-#pragma unroll
-        for (int k = 0; k < 16; ++k)
-            if (k < nk) Act<WT>::st(o + 16 * k, g * acc[k]);
+        WT* o = mb + ((size_t)b * C + co0 + cl) * C + ci0 + cq;
+        Act<WT>::st(o + 0, g * a0); Act<WT>::st(o + 1, g * a1); Act<WT>::st(o + 2, g * a2); Act<WT>::st(o + 3, g * a3);
     }
 }
 
@@ -226,22 +353,30 @@ void attn_ctx_plan(int n, int* chunks, int* chunk_len) {
 
 int attn_ctx(ActKind act, const AttnCtxArgs& a, bool strict, cudaStream_t s) {
     GTTS_REQUIRE(a.chunk_len % kSub == 0 && a.chunks >= 1, "attn_ctx: bad chunk plan");
-    dim3 grid(a.chunks, 4, a.B);
     if (act == ACT_F32) {
+        dim3 grid(a.chunks, 4, a.B);
         if (strict) attn_ctx_kernel<float, true><<<grid, 256, 0, s>>>(a);
         else        attn_ctx_kernel<float, false><<<grid, 256, 0, s>>>(a);
     } else {
-        if (strict) attn_ctx_kernel<__nv_bfloat16, true><<<grid, 256, 0, s>>>(a);
-        else        attn_ctx_kernel<__nv_bfloat16, false><<<grid, 256, 0, s>>>(a);
+        dim3 grid(a.chunks, a.B);
+        attn_ctx_tc_kernel<<<grid, 128, 0, s>>>(a);
     }
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int attn_merge(const AttnCtxArgs& a, bool strict, cudaStream_t s) {
+    dim3 grid(4, a.B);
+    if (strict) attn_merge_kernel<true><<<grid, 256, 0, s>>>(a);
+    else        attn_merge_kernel<false><<<grid, 256, 0, s>>>(a);
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 int attn_fold(ActKind wkind, const float* ctxn, const float* wout, const float* wq, float g, void* mb_out, int B,
               int C, cudaStream_t s) {
-    GTTS_REQUIRE(C % 16 == 0 && C <= 256, "attn_fold: C must be a multiple of 16 and <= 256");
-    dim3 grid(C / 16, B);
+    GTTS_REQUIRE(C % 64 == 0 && C <= 256, "attn_fold: C must be a multiple of 64 and <= 256");
+    dim3 grid(C / 16, C / 64, B);
     if (wkind == ACT_F32) attn_fold_kernel<float><<<grid, 256, 0, s>>>(ctxn, wout, wq, g, (float*)mb_out, C);
     else attn_fold_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(ctxn, wout, wq, g, (__nv_bfloat16*)mb_out, C);
     GTTS_CHECK_CUDA(cudaGetLastError());

@@ -51,28 +51,58 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t saddr) {
     return d;
 }
 
-template <int N>
-__global__ void __launch_bounds__(256, 1)
+// Butterfly transpose-reduce of 8 per-thread values across the warp in 9 shuffles (instead of 40):
+// afterwards every lane holds the full 32-lane sum of value index ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1).
+__device__ __forceinline__ float warp_reduce8(const float (&v)[8], int lane) {
+    float w[4], u[2], t;
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float keep = b4 ? v[4 + i] : v[i], send = b4 ? v[i] : v[4 + i];
+        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float keep = b3 ? w[2 + i] : w[i], send = b3 ? w[i] : w[2 + i];
+        u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    {
+        const float keep = b2 ? u[1] : u[0], send = b2 ? u[0] : u[1];
+        t = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    return t;
+}
+
+constexpr int kStatSlots = 4;          // ring of per-tile GroupNorm partials between epilogue warps and the stats warp
+constexpr int kThreads = 384;          // warps 0-3: TMA, MMA, TMEM alloc, stats; warps 4-11: epilogue
+
+// kStats: GroupNorm partial statistics of (acc + bias); kRes: + residual; kMask: * mask[b][w]
+template <int N, bool kStats, bool kRes, bool kMask>
+__global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapW, const TcParams p) {
     constexpr int kBBytes = N * 128;
     constexpr int kStage = kABytes + kBBytes;
     constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
     constexpr uint32_t kTmemCols = 2 * N;          // 128 / 256 / 512: power of two
+    constexpr int kColsPerWarp = N / 2;            // two epilogue warps share each TMEM lane quarter
+    constexpr int kGsz = N / 8;                    // channels per GroupNorm group (4 groups per column half)
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
     uint8_t* misc = smem + (size_t)p.stages * kStage;
-    uint64_t* full = reinterpret_cast<uint64_t*>(misc);
-    uint64_t* empty = full + 8;
-    uint64_t* tfull = empty + 8;
-    uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    int* s_flag = reinterpret_cast<int*>(tmem_slot + 1);
-    float* s_part = reinterpret_cast<float*>(misc + 256);          // [4][16]
-    float* s_tile = s_part + 64;                                   // [16]
-    double* s_red = reinterpret_cast<double*>(misc + 1024);        // [8][16]
+    uint64_t* full = reinterpret_cast<uint64_t*>(misc);            // [8]
+    uint64_t* empty = full + 8;                                    // [8]
+    uint64_t* tfull = empty + 8;                                   // [2]
+    uint64_t* tempty = tfull + 2;                                  // [2]
+    uint64_t* sfull = tempty + 2;                                  // [kStatSlots]
+    uint64_t* sempty = sfull + kStatSlots;                         // [kStatSlots]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + kStatSlots);
+    float* s_bias = reinterpret_cast<float*>(misc + 512);          // [256]
+    float* s_ring = reinterpret_cast<float*>(misc + 1536);         // [kStatSlots][8 warps][8]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -81,12 +111,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tma_prefetch_desc(&mapA1);
         tma_prefetch_desc(&mapW);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 256); }
+        for (int i = 0; i < kStatSlots; ++i) { mbar_init(&sfull[i], 8); mbar_init(&sempty[i], 1); }
         mbar_fence_init();
     } else if (warp == 2) {
         tmem_alloc(tmem_slot, kTmemCols);
         tmem_relinquish();
     }
+    for (int i = tid; i < N; i += kThreads) s_bias[i] = p.e.bias ? p.e.bias[i] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -154,55 +186,105 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
             }
         }
+    } else if (warp == 3) {
+        // ================================================================ GroupNorm statistics warp
+        if (kStats) {
+            const ConvEpilogue& e = p.e;
+            const double inv_count = 1.0 / ((double)kGsz * (double)p.Hout * (double)p.Wout);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int slot = it % kStatSlots;
+                const int b = tile / tiles_per_phase, slot_in_sample = tile - b * tiles_per_phase;
+                mbar_wait(&sfull[slot], (uint32_t)(it / kStatSlots) & 1u);
+                // value k (0..7 sums, 8..15 sums of squares) of group g = k & 7 lives in column half g >> 2
+                float v = 0.f;
+                if (lane < 16) {
+                    const int g = lane & 7, which = lane >> 3, half = g >> 2, idx = which * 4 + (g & 3);
+                    const float* r = s_ring + (slot * 8 + half * 4) * 8 + idx;
+                    v = (r[0] + r[8]) + (r[16] + r[24]);
+                    e.gn_partials[((size_t)b * tiles_per_phase + slot_in_sample) * 16 + lane] = v;
+                    __threadfence();
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sempty[slot]);
+                unsigned int old = 0;
+                if (lane == 0) old = atomicAdd(&e.gn_counters[b], 1u);
+                old = __shfl_sync(0xffffffffu, old, 0);
+                if (old == (unsigned int)(tiles_per_phase - 1)) {
+                    // last tile of sample b: fixed-order reduction of all partials (deterministic)
+                    __threadfence();
+                    const int k = lane & 15, slice = lane >> 4;
+                    const float* pp = e.gn_partials + (size_t)b * tiles_per_phase * 16 + k;
+                    double acc = 0.0;
+                    for (int s = slice; s < tiles_per_phase; s += 2) acc += (double)__ldcg(pp + (size_t)s * 16);
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+                    const double sq = __shfl_down_sync(0xffffffffu, acc, 8);
+                    if (lane < 8) {
+                        const double mean = acc * inv_count;
+                        double var = sq * inv_count - mean * mean;
+                        if (var < 0.0) var = 0.0;
+                        e.gn_stats[((size_t)b * 8 + lane) * 2 + 0] = (float)mean;
+                        e.gn_stats[((size_t)b * 8 + lane) * 2 + 1] = (float)(1.0 / sqrt(var + (double)e.gn_eps));
+                    }
+                    if (lane == 0) e.gn_counters[b] = 0u;
+                }
+            }
+        }
     } else if (warp >= 4) {
-        // ================================================================ epilogue (128 threads)
-        const int et = tid - 128, wq = warp - 4;
+        // ================================================================ epilogue (8 warps, 256 threads)
+        const int ew = warp - 4, wq = ew & 3, half = ew >> 2;
+        const int row = wq * 32 + lane;                              // TMEM lane = pixel row of the tile
         const ConvEpilogue& e = p.e;
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.out);
         const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(e.residual);
-        constexpr int kGsz = N / 8;                                  // channels per GroupNorm group
+        const int cbase = half * kColsPerWarp;
         int it = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1;
             const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h;
             const int ph = (tile / tiles_per_phase) % p.nphase, b = tile / (tiles_per_phase * p.nphase);
-            const int hl = et / p.bw, wl = et - hl * p.bw;
+            const int hl = row / p.bw, wl = row - hl * p.bw;
             const int j = th * p.bh + hl, i = tw * p.bw + wl;
             const bool valid = (hl < p.bh) && (j < p.Hg) && (i < p.Wg);
             const int oh = j * p.out_step + p.oy[ph], ow = i * p.out_step + p.ox[ph];
             const size_t opix = valid ? ((size_t)b * p.Hout + oh) * p.Wout + ow : 0;
-            const float m = (e.mask && valid) ? e.mask[(size_t)b * p.Wout + ow] : 1.0f;
+            float m = 1.0f;
+            if (kMask) m = valid ? e.mask[(size_t)b * p.Wout + ow] : 0.f;
 
             mbar_wait(&tfull[buf], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * N);
+            const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * N + cbase);
 
-            float st_s[8], st_q[8];
+            float st[8];                                             // [0..3] sums, [4..7] sums of squares
 #pragma unroll
-            for (int g = 0; g < 8; ++g) { st_s[g] = 0.f; st_q[g] = 0.f; }
+            for (int g = 0; g < 8; ++g) st[g] = 0.f;
 
 #pragma unroll
-            for (int c0 = 0; c0 < N; c0 += 32) {
+            for (int c0 = 0; c0 < kColsPerWarp; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(taddr + (uint32_t)c0, r);
                 tmem_ld_wait();
                 float f[32];
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    f[q] = __uint_as_float(r[q]);
-                    if (e.bias) f[q] += __ldg(e.bias + c0 + q);
+                for (int q4 = 0; q4 < 8; ++q4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[cbase + c0 + q4 * 4]);
+                    f[q4 * 4 + 0] = __uint_as_float(r[q4 * 4 + 0]) + b4.x;
+                    f[q4 * 4 + 1] = __uint_as_float(r[q4 * 4 + 1]) + b4.y;
+                    f[q4 * 4 + 2] = __uint_as_float(r[q4 * 4 + 2]) + b4.z;
+                    f[q4 * 4 + 3] = __uint_as_float(r[q4 * 4 + 3]) + b4.w;
                 }
-                if (e.gn_partials && valid) {
+                if (kStats) {
 #pragma unroll
                     for (int q = 0; q < 32; ++q) {
-                        const int g = (c0 + q) / kGsz;
-                        st_s[g] += f[q];
-                        st_q[g] += f[q] * f[q];
+                        const int g = (c0 + q) / kGsz;               // local group 0..3 (compile time)
+                        const float x = valid ? f[q] : 0.f;
+                        st[g] += x;
+                        st[4 + g] = fmaf(x, x, st[4 + g]);
                     }
                 }
                 if (valid) {
-                    if (res) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(res + opix * N + c0);
+                    if (kRes) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(res + opix * N + cbase + c0);
 #pragma unroll
                         for (int v4 = 0; v4 < 4; ++v4) {
                             const uint4 u = __ldg(rp + v4);
@@ -214,11 +296,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             }
                         }
                     }
-                    if (e.mask) {
+                    if (kMask) {
 #pragma unroll
                         for (int q = 0; q < 32; ++q) f[q] *= m;
                     }
-                    uint4* op = reinterpret_cast<uint4*>(out + opix * N + c0);
+                    uint4* op = reinterpret_cast<uint4*>(out + opix * N + cbase + c0);
 #pragma unroll
                     for (int v4 = 0; v4 < 4; ++v4) {
                         uint32_t w[4];
@@ -235,20 +317,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             tc_fence_before();
             mbar_arrive(&tempty[buf]);
 
-            if (e.gn_partials) {
-#pragma unroll
-                for (int g = 0; g < 8; ++g) { st_s[g] = warp_sum(st_s[g]); st_q[g] = warp_sum(st_q[g]); }
-                if (lane == 0) {
-#pragma unroll
-                    for (int g = 0; g < 8; ++g) { s_part[wq * 16 + g] = st_s[g]; s_part[wq * 16 + 8 + g] = st_q[g]; }
-                }
-                named_bar_sync(1, 128);
-                if (et < 16) s_tile[et] = (s_part[et] + s_part[16 + et]) + (s_part[32 + et] + s_part[48 + et]);
-                named_bar_sync(1, 128);
-                GnStatsOut go{e.gn_partials, e.gn_stats, e.gn_counters, tiles_per_phase,
-                              1.0f / ((float)kGsz * (float)p.Hout * (float)p.Wout), e.gn_eps};
-                gn_stats_publish(go, b, th * p.tiles_w + tw, et, 128, s_tile, s_red, s_flag,
-                                 [] { named_bar_sync(1, 128); });
+            if (kStats) {
+                const float t = warp_reduce8(st, lane);
+                const int slot = it % kStatSlots;
+                mbar_wait(&sempty[slot], ((uint32_t)(it / kStatSlots) & 1u) ^ 1u);
+                if ((lane & 3) == 0) s_ring[(slot * 8 + ew) * 8 + (lane >> 2)] = t;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sfull[slot]);            // release: orders the ring writes of this warp
             }
         }
     }
@@ -388,22 +463,36 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
 
 void conv_tc_plan_destroy(TcConvPlan* p) { delete p; }
 
-int conv_tc_launch(const TcConvPlan* pl, cudaStream_t stream) {
-    static bool attr_set[3] = {false, false, false};
-    const int idx = pl->N == 64 ? 0 : (pl->N == 128 ? 1 : 2);
-    if (!attr_set[idx]) {
-        const int maxsmem = 227 * 1024;
-        if (idx == 0) GTTS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsmem));
-        if (idx == 1) GTTS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsmem));
-        if (idx == 2) GTTS_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsmem));
-        attr_set[idx] = true;
+namespace {
+template <int N, bool kStats, bool kRes, bool kMask>
+int launch_variant(const TcConvPlan* pl, cudaStream_t stream) {
+    static bool attr_set = false;
+    auto k = conv_tc_kernel<N, kStats, kRes, kMask>;
+    if (!attr_set) {
+        GTTS_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
     }
-    if (pl->p.num_tiles == 0) return 0;
-    if (idx == 0) conv_tc_kernel<64><<<pl->grid, 256, pl->smem, stream>>>(pl->mapA0, pl->mapA1, pl->mapW, pl->p);
-    if (idx == 1) conv_tc_kernel<128><<<pl->grid, 256, pl->smem, stream>>>(pl->mapA0, pl->mapA1, pl->mapW, pl->p);
-    if (idx == 2) conv_tc_kernel<256><<<pl->grid, 256, pl->smem, stream>>>(pl->mapA0, pl->mapA1, pl->mapW, pl->p);
+    k<<<pl->grid, kThreads, pl->smem, stream>>>(pl->mapA0, pl->mapA1, pl->mapW, pl->p);
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+template <int N>
+int launch_n(const TcConvPlan* pl, cudaStream_t stream) {
+    const ConvEpilogue& e = pl->p.e;
+    const bool st = e.gn_partials != nullptr, rs = e.residual != nullptr, mk = e.mask != nullptr;
+    if (st) return launch_variant<N, true, false, false>(pl, stream);
+    if (rs && mk) return launch_variant<N, false, true, true>(pl, stream);
+    if (rs) return launch_variant<N, false, true, false>(pl, stream);
+    if (mk) return launch_variant<N, false, false, true>(pl, stream);
+    return launch_variant<N, false, false, false>(pl, stream);
+}
+}  // namespace
+
+int conv_tc_launch(const TcConvPlan* pl, cudaStream_t stream) {
+    if (pl->p.num_tiles == 0) return 0;
+    if (pl->N == 64) return launch_n<64>(pl, stream);
+    if (pl->N == 128) return launch_n<128>(pl, stream);
+    return launch_n<256>(pl, stream);
 }
 
 }  // namespace gtts

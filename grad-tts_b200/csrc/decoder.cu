@@ -468,16 +468,16 @@ struct PlanBuilder {
         int chunks, chunk_len;
         attn_ctx_plan(n, &chunks, &chunk_len);
         float* partials = (float*)pl->mem.alloc((size_t)B * 4 * chunks * 1088 * 4);
-        unsigned int* counters = (unsigned int*)pl->mem.alloc((size_t)B * 4 * 4, true);
         float* ctxn = (float*)pl->mem.alloc((size_t)B * 4096 * 4);
         void* mb = pl->mem.alloc((size_t)B * C * C * esize(kind));
-        if (!kv || !out || !partials || !counters || !ctxn || !mb) { failed = true; return nullptr; }
+        if (!kv || !out || !partials || !ctxn || !mb) { failed = true; return nullptr; }
         add_conv(geom_1x1(B, H[lvl], W[lvl], C, 0, 256, 0), x, nullptr, A.wkv, 256, nullptr, nullptr, nullptr, kv, nullptr);
-        AttnCtxArgs ca{kv, B, n, partials, counters, ctxn, chunks, chunk_len};
+        AttnCtxArgs ca{kv, B, n, partials, ctxn, chunks, chunk_len};
         ActKind k = kind;
         bool st_ = strict;
         pl->push("attn_ctx_h" + std::to_string(H[lvl]), 0, 2.0 * B * 4 * (double)n * 1024, (double)B * n * 256 * esize(kind),
                  [k, ca, st_](cudaStream_t s) { return attn_ctx(k, ca, st_, s); });
+        pl->push("attn_merge", 0, 0.0, 0.0, [ca, st_](cudaStream_t s) { return attn_merge(ca, st_, s); });
         const float *wout = A.wout, *wq = A.wq;
         float g = A.g;
         int Bb = B;

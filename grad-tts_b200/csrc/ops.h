@@ -125,11 +125,11 @@ struct AttnCtxArgs {
     const void* kv;               // NHWC act, 256 channels: k = [0,128), v = [128,256), head-major
     int B, n;                     // n = H*W positions
     float* partials;              // [B][4][chunks][1088]
-    unsigned int* counters;       // [B*4]
     float* ctxn;                  // [B][4][32][32]  ctx[d][e] / l[d]
     int chunks, chunk_len;
 };
-int attn_ctx(ActKind act, const AttnCtxArgs& a, bool strict, cudaStream_t s);
+int attn_ctx(ActKind act, const AttnCtxArgs& a, bool strict, cudaStream_t s);      // per-chunk partials
+int attn_merge(const AttnCtxArgs& a, bool strict, cudaStream_t s);                   // partials -> ctxn
 void attn_ctx_plan(int n, int* chunks, int* chunk_len);
 // per-sample folded weights M_b = g * Wout * blockdiag(ctxn^T) * Wq  -> [B*C][C] in weight type
 int attn_fold(ActKind wkind, const float* ctxn, const float* wout /*[C][128]*/, const float* wq /*[128][C]*/,

@@ -184,103 +184,146 @@ first_conv_kernel(FirstConvArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ GN apply
-template <typename T, bool kStrict>
+// grid (blocks per sample, B); each thread owns one 8-channel vector position (fixed channels, so the affine
+// constants stay in registers) and streams kVecPerThread vectors of it with all loads issued up front.
+constexpr int kGnVec = 4;
+
+template <typename T, bool kStrict, bool kHasRes, bool kHasTb, bool kFirstRes>
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(GnApplyArgs a) {
     const int C8 = a.C >> 3;
-    const size_t total = (size_t)a.B * a.H * a.W * C8;
-    const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= total) return;
-    const int c8 = (int)(idx % C8);
-    const size_t pix = idx / C8;
-    const int HW = a.H * a.W;
-    const int b = (int)(pix / HW);
-    const int w = (int)(pix % a.W);
+    const int b = blockIdx.y;
+    const size_t per_sample = (size_t)a.H * a.W * C8;                  // vectors per sample
+    const size_t v0 = (size_t)blockIdx.x * (256 * kGnVec) + threadIdx.x;
+    const int c8 = (int)(threadIdx.x % C8);                            // 256 % C8 == 0: same channels for all my vectors
     const int c0 = c8 * 8;
     const int g = (c0 * 8) / a.C;
     const float mean = a.stats[(b * 8 + g) * 2], rstd = a.stats[(b * 8 + g) * 2 + 1];
-    const float m = a.mask[(size_t)b * a.W + w];
-    float v[8];
-    Act<T>::load8(reinterpret_cast<const T*>(a.raw) + pix * a.C + c0, v);
-    float r[8];
-    const bool has_res = a.residual != nullptr;
-    if (has_res) Act<T>::load8(reinterpret_cast<const T*>(a.residual) + pix * a.C + c0, r);
-    float fin[3] = {0.f, 0.f, 0.f};
-    if (a.fr_w) {
-        fin[0] = a.fr_mu[pix] * m;
-        fin[1] = a.fr_x[pix] * m;
-        if (a.fr_cin == 3) fin[2] = a.fr_s[pix / a.W] * m;           // s plane is (B,80): index b*H + h
-    }
+    float sc[8], sh[8], tb[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int c = c0 + j;
-        float y = (v[j] - mean) * rstd * __ldg(a.gamma + c) + __ldg(a.beta + c);      // GroupNorm      (:53)
-        y = mish<kStrict>(y) * m;                                                     // Mish, * mask   (:54,58)
-        if (a.tbias) y += __ldg(a.tbias + (size_t)b * a.tbias_bstride + c);           // h += mlp(t)    (:76)
-        if (has_res) y += r[j];                                                       // + res_conv(x)  (:78)
-        if (a.fr_w) {
-            float rr = __ldg(a.fr_b + c);
-            for (int ci = 0; ci < a.fr_cin; ++ci) rr = fmaf(__ldg(a.fr_w + c * a.fr_cin + ci), fin[ci], rr);
-            y += rr;
-        }
-        v[j] = y * m;          // every consumer masks its input: store masked (binary masks)
+        // GroupNorm (:53) as y = x*scale + shift with scale = rstd*gamma, shift = beta - mean*scale (ATen's form)
+        sc[j] = rstd * __ldg(a.gamma + c0 + j);
+        sh[j] = __ldg(a.beta + c0 + j) - mean * sc[j];
+        tb[j] = kHasTb ? __ldg(a.tbias + (size_t)b * a.tbias_bstride + c0 + j) : 0.f;
     }
-    Act<T>::store8(reinterpret_cast<T*>(a.out) + pix * a.C + c0, v);
+    const T* raw = reinterpret_cast<const T*>(a.raw) + (size_t)b * per_sample * 8;
+    const T* res = kHasRes ? reinterpret_cast<const T*>(a.residual) + (size_t)b * per_sample * 8 : nullptr;
+    T* out = reinterpret_cast<T*>(a.out) + (size_t)b * per_sample * 8;
+    const float* mrow = a.mask + (size_t)b * a.W;
+
+    float v[kGnVec][8], r[kGnVec][8], m[kGnVec];
+    bool ok[kGnVec];
+#pragma unroll
+    for (int k = 0; k < kGnVec; ++k) {
+        const size_t vi = v0 + (size_t)k * 256;
+        ok[k] = vi < per_sample;
+        if (ok[k]) {
+            Act<T>::load8(raw + vi * 8, v[k]);
+            if (kHasRes) Act<T>::load8(res + vi * 8, r[k]);
+            m[k] = mrow[(int)((vi / C8) % a.W)];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kGnVec; ++k) {
+        if (!ok[k]) continue;
+        const size_t vi = v0 + (size_t)k * 256;
+        float fin[3] = {0.f, 0.f, 0.f};
+        if (kFirstRes) {
+            const size_t pix = (size_t)b * a.H * a.W + vi / C8;
+            fin[0] = a.fr_mu[pix] * m[k];
+            fin[1] = a.fr_x[pix] * m[k];
+            if (a.fr_cin == 3) fin[2] = a.fr_s[pix / a.W] * m[k];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float y = fmaf(v[k][j], sc[j], sh[j]);
+            y = mish<kStrict>(y) * m[k];                                 // Mish, * mask   (:54,58)
+            if (kHasTb) y += tb[j];                                      // h += mlp(t)    (:76)
+            if (kHasRes) y += r[k][j];                                   // + res_conv(x)  (:78)
+            if (kFirstRes) {
+                const int c = c0 + j;
+                float rr = __ldg(a.fr_b + c);
+                for (int ci = 0; ci < a.fr_cin; ++ci) rr = fmaf(__ldg(a.fr_w + c * a.fr_cin + ci), fin[ci], rr);
+                y += rr;
+            }
+            v[k][j] = y * m[k];        // every consumer masks its input: store masked (binary masks)
+        }
+        Act<T>::store8(out + vi * 8, v[k]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ Euler step
 // final_block GN+Mish+mask -> final_conv(64->1)+bias -> *mask = score; then the sampler update.
+// 8 lanes per pixel (one 8-channel vector each), kEuPix pixels per lane group with the loads issued up front.
+constexpr int kEuPix = 4;
+
 template <typename T, bool kStrict>
 __global__ void __launch_bounds__(256)
 euler_kernel(EulerArgs a) {
     const size_t npix = (size_t)a.B * a.H * a.W;
-    const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
-    const size_t pix = idx >> 3;
-    const int sub = (int)(idx & 7);
-    const bool valid = pix < npix;
-    const size_t pp = valid ? pix : 0;
+    const int sub = threadIdx.x & 7;
+    const size_t pbase = ((size_t)blockIdx.x * 32 + (threadIdx.x >> 3)) * kEuPix;   // 32 lane groups per CTA
     const int HW = a.H * a.W;
-    const int b = (int)(pp / HW);
-    const int w = (int)(pp % a.W);
-    const float m = a.mask[(size_t)b * a.W + w];
-    const float mean = a.stats[(b * 8 + sub) * 2], rstd = a.stats[(b * 8 + sub) * 2 + 1];
-    float v[8];
-    Act<T>::load8(reinterpret_cast<const T*>(a.raw) + pp * 64 + sub * 8, v);
-    float part = 0.f;
+    float sc[8], sh_[8], wf[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int c = sub * 8 + j;
-        float y = (v[j] - mean) * rstd * __ldg(a.gamma + c) + __ldg(a.beta + c);
-        y = mish<kStrict>(y) * m;                      // final_block(x, mask)              (:212)
-        part = fmaf(y * m, __ldg(a.wf + c), part);     // final_conv(x * mask)              (:213)
+        sc[j] = __ldg(a.gamma + sub * 8 + j);
+        sh_[j] = __ldg(a.beta + sub * 8 + j);
+        wf[j] = __ldg(a.wf + sub * 8 + j);
     }
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    part += __shfl_xor_sync(0xffffffffu, part, 4);
-    if (!valid || sub != 0) return;
-    const float score = __fmul_rn(part + a.bf, m);     // (output * mask)                   (:216)
-    if (a.score_out) a.score_out[pix] = score;
-    if (!a.update) return;
-    const float beta_t = a.beta_tab[*a.step];
-    const float hh = *a.h_ptr;
-    const float xt = a.xt[pix], mu = a.mu[pix];
-    float nx;
-    if (!a.sde) {
-        // dxt = 0.5*(mu - xt - est); dxt = dxt*noise_t*h; xt = (xt - dxt)*mask          (:265-267)
-        float d = __fsub_rn(__fsub_rn(mu, xt), score);
-        d = __fmul_rn(0.5f, d);
-        d = __fmul_rn(__fmul_rn(d, beta_t), hh);
-        nx = __fmul_rn(__fsub_rn(xt, d), m);
-    } else {
-        // north-star SDE form (upstream Grad-TTS): x - (0.5*(mu-x) - score)*beta*h + sqrt(beta*h)*z
-        float d = __fsub_rn(__fmul_rn(0.5f, __fsub_rn(mu, xt)), score);
-        d = __fmul_rn(__fmul_rn(d, beta_t), hh);
-        const float* noise = *a.noise_slot;
-        float z = noise[(size_t)(*a.step) * a.noise_step_stride + pix];
-        d = __fsub_rn(d, __fmul_rn(sqrtf(__fmul_rn(beta_t, hh)), z));
-        nx = __fmul_rn(__fsub_rn(xt, d), m);
+    float v[kEuPix][8];
+#pragma unroll
+    for (int k = 0; k < kEuPix; ++k) {
+        const size_t pix = pbase + k;
+        if (pix < npix) Act<T>::load8(reinterpret_cast<const T*>(a.raw) + pix * 64 + sub * 8, v[k]);
     }
-    a.xt[pix] = nx;
+    const float beta_t = a.update ? a.beta_tab[*a.step] : 0.f;
+    const float hh = a.update ? *a.h_ptr : 0.f;
+#pragma unroll
+    for (int k = 0; k < kEuPix; ++k) {
+        const size_t pix = pbase + k;
+        const bool valid = pix < npix;
+        const size_t pp = valid ? pix : 0;
+        const int b = (int)(pp / HW);
+        const int w = (int)(pp % a.W);
+        const float m = a.mask[(size_t)b * a.W + w];
+        const float mean = a.stats[(b * 8 + sub) * 2], rstd = a.stats[(b * 8 + sub) * 2 + 1];
+        float part = 0.f;
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float y = (v[k][j] - mean) * rstd * sc[j] + sh_[j];
+                y = mish<kStrict>(y) * m;                      // final_block(x, mask)              (:212)
+                part = fmaf(y * m, wf[j], part);               // final_conv(x * mask)              (:213)
+            }
+        }
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        part += __shfl_xor_sync(0xffffffffu, part, 4);
+        if (!valid || sub != 0) continue;
+        const float score = __fmul_rn(part + a.bf, m);         // (output * mask)                   (:216)
+        if (a.score_out) a.score_out[pix] = score;
+        if (!a.update) continue;
+        const float xt = a.xt[pix], mu = a.mu[pix];
+        float nx;
+        if (!a.sde) {
+            // dxt = 0.5*(mu - xt - est); dxt = dxt*noise_t*h; xt = (xt - dxt)*mask          (:265-267)
+            float d = __fsub_rn(__fsub_rn(mu, xt), score);
+            d = __fmul_rn(0.5f, d);
+            d = __fmul_rn(__fmul_rn(d, beta_t), hh);
+            nx = __fmul_rn(__fsub_rn(xt, d), m);
+        } else {
+            // north-star SDE form (upstream Grad-TTS): x - (0.5*(mu-x) - score)*beta*h + sqrt(beta*h)*z
+            float d = __fsub_rn(__fmul_rn(0.5f, __fsub_rn(mu, xt)), score);
+            d = __fmul_rn(__fmul_rn(d, beta_t), hh);
+            const float* noise = *a.noise_slot;
+            float z = noise[(size_t)(*a.step) * a.noise_step_stride + pix];
+            d = __fsub_rn(d, __fmul_rn(sqrtf(__fmul_rn(beta_t, hh)), z));
+            nx = __fmul_rn(__fsub_rn(xt, d), m);
+        }
+        a.xt[pix] = nx;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ packing
@@ -379,24 +422,38 @@ int first_conv(ActKind act, const FirstConvArgs& a, cudaStream_t s) {
     return 0;
 }
 
+namespace {
+template <typename T, bool kStrict>
+int gn_apply_dispatch(const GnApplyArgs& a, cudaStream_t s) {
+    const size_t per_sample = (size_t)a.H * a.W * (a.C / 8);
+    dim3 grid((unsigned int)((per_sample + 256 * kGnVec - 1) / (256 * kGnVec)), a.B);
+    const bool res = a.residual != nullptr, tb = a.tbias != nullptr, fr = a.fr_w != nullptr;
+    if (fr)             gn_apply_kernel<T, kStrict, false, false, true><<<grid, 256, 0, s>>>(a);
+    else if (res && tb) gn_apply_kernel<T, kStrict, true, true, false><<<grid, 256, 0, s>>>(a);
+    else if (res)       gn_apply_kernel<T, kStrict, true, false, false><<<grid, 256, 0, s>>>(a);
+    else if (tb)        gn_apply_kernel<T, kStrict, false, true, false><<<grid, 256, 0, s>>>(a);
+    else                gn_apply_kernel<T, kStrict, false, false, false><<<grid, 256, 0, s>>>(a);
+    return 0;
+}
+}  // namespace
+
 int gn_apply(ActKind act, const GnApplyArgs& a, bool strict, cudaStream_t s) {
-    GTTS_REQUIRE(a.C % 64 == 0, "gn_apply: C must be a multiple of 64");
-    size_t total = (size_t)a.B * a.H * a.W * (a.C / 8);
-    unsigned int g = nblk(total, 256);
+    GTTS_REQUIRE(a.C % 64 == 0 && a.C <= 256, "gn_apply: C must be 64, 128 or 256");
+    GTTS_REQUIRE(!(a.fr_w && (a.residual || a.tbias)), "gn_apply: first-block residual excludes the others");
     if (act == ACT_F32) {
-        if (strict) gn_apply_kernel<float, true><<<g, 256, 0, s>>>(a);
-        else        gn_apply_kernel<float, false><<<g, 256, 0, s>>>(a);
+        if (strict) gn_apply_dispatch<float, true>(a, s);
+        else        gn_apply_dispatch<float, false>(a, s);
     } else {
-        if (strict) gn_apply_kernel<__nv_bfloat16, true><<<g, 256, 0, s>>>(a);
-        else        gn_apply_kernel<__nv_bfloat16, false><<<g, 256, 0, s>>>(a);
+        if (strict) gn_apply_dispatch<__nv_bfloat16, true>(a, s);
+        else        gn_apply_dispatch<__nv_bfloat16, false>(a, s);
     }
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 int euler_step(ActKind act, const EulerArgs& a, bool strict, cudaStream_t s) {
-    size_t total = (size_t)a.B * a.H * a.W * 8;
-    unsigned int g = nblk(total, 256);
+    const size_t npix = (size_t)a.B * a.H * a.W;
+    unsigned int g = nblk(npix, 32 * kEuPix);
     if (act == ACT_F32) {
         if (strict) euler_kernel<float, true><<<g, 256, 0, s>>>(a);
         else        euler_kernel<float, false><<<g, 256, 0, s>>>(a);

@@ -125,11 +125,33 @@ def stage_perf():
             traceback.print_exc()
 
 
+def stage_profile():
+    import ctypes, json
+    for (n_spks, B, T) in [(1, 16, 1720), (1, 1, 400)]:
+        dec, _ = _decoder(n_spks, 0, "bf16")
+        dec.estimator.max_chunk = B
+        z, mask, mu, spk, _ = pkg.synth.make_inputs(B, T, n_spks, seed=7, ragged=False)
+        dec(z.to(DEV), mask.to(DEV), mu.to(DEV), 2)
+        torch.cuda.synchronize()
+        buf = ctypes.create_string_buffer(1 << 17)
+        h = dec.estimator._get_handle()
+        rc = pkg._lib.load().gtts_decoder_profile_step(h, B, T, 0, 5, buf, len(buf),
+                                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        pkg._lib.check(rc, "profile")
+        rep = json.loads(buf.value.decode())
+        tot = sum(o["ms"] for o in rep["ops"])
+        print(f"--- profile B={B} T={T}: total {tot:.3f} ms over {len(rep['ops'])} launches")
+        for o in rep["ops"]:
+            tf = o["flops"] / (o["ms"] * 1e-3) / 1e12 if o["ms"] > 0 else 0
+            gb = o["bytes"] / (o["ms"] * 1e-3) / 1e9 if o["ms"] > 0 else 0
+            print(f"   {o['name']:28s} {o['ms'] * 1e3:9.1f} us  {tf:8.1f} TFLOP/s  {gb:8.0f} GB/s(alg)")
+
+
 if __name__ == "__main__":
     st = sys.argv[1]
     print(f"===== stage {st} on {torch.cuda.get_device_name(0)}", flush=True)
     {"mas": stage_mas, "conv_ffma": lambda: (stage_conv(0, 0), stage_conv(0, 1)), "conv_tc": lambda: stage_conv(1, 1),
      "dec_fp32": lambda: stage_dec("fp32"), "dec_bf16_ffma": lambda: stage_dec("bf16", 0),
-     "dec_bf16_tc": lambda: stage_dec("bf16", 1), "perf": stage_perf}[st]()
+     "dec_bf16_tc": lambda: stage_dec("bf16", 1), "perf": stage_perf, "profile": stage_profile}[st]()
     torch.cuda.synchronize()
     print(f"===== stage {st} done", flush=True)
