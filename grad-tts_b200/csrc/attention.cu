@@ -262,32 +262,42 @@ attn_ctx_tc_kernel(AttnCtxArgs a) {
 template <bool kStrict>
 __global__ void __launch_bounds__(256)
 attn_merge_kernel(AttnCtxArgs a) {
-    __shared__ float s_m[32], s_scale[32];
+    __shared__ float s_m[32], s_scale[32], s_part[8][32], s_w[64][32];
     const int tid = threadIdx.x, head = blockIdx.x, b = blockIdx.y;
-    const float* pbase = a.partials + ((size_t)b * 4 + head) * a.chunks * 1088;
-    if (tid < 32) {
+    const int d = tid & 31, cg = tid >> 5;
+    const int nch = a.chunks;                                       // <= 64 by construction (attn_ctx_plan: ~32)
+    const float* pbase = a.partials + ((size_t)b * 4 + head) * nch * 1088;
+    {   // global max per d: 8 chunk groups in parallel, then a fixed-order combine
         float M = -INFINITY;
-        for (int c = 0; c < a.chunks; ++c) M = fmaxf(M, pbase[(size_t)c * 1088 + tid]);
-        float l = 0.f;
-        for (int c = 0; c < a.chunks; ++c) {
-            const float mc = pbase[(size_t)c * 1088 + tid];
-            const float wgt = kStrict ? expf(mc - M) : __expf(mc - M);
-            l += wgt * pbase[(size_t)c * 1088 + 32 + tid];
-        }
+        for (int c = cg; c < nch; c += 8) M = fmaxf(M, pbase[(size_t)c * 1088 + d]);
+        s_part[cg][d] = M;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        float M = s_part[0][tid];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) M = fmaxf(M, s_part[k][tid]);
         s_m[tid] = M;
+    }
+    __syncthreads();
+    for (int c = cg; c < nch; c += 8) {                             // per-chunk weights exp(m_c - M)
+        const float mc = pbase[(size_t)c * 1088 + d];
+        s_w[c][d] = kStrict ? expf(mc - s_m[d]) : __expf(mc - s_m[d]);
+    }
+    __syncthreads();
+    if (tid < 32) {
+        float l = 0.f;
+        for (int c = 0; c < nch; ++c) l += s_w[c][tid] * pbase[(size_t)c * 1088 + 32 + tid];
         s_scale[tid] = 1.0f / l;
     }
     __syncthreads();
-    for (int i = tid; i < 1024; i += 256) {
-        const int d = i >> 5;
-        const float M = s_m[d];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = tid + 256 * k, dd = i >> 5;
         float s = 0.f;
-        for (int c = 0; c < a.chunks; ++c) {
-            const float mc = pbase[(size_t)c * 1088 + d];
-            const float wgt = kStrict ? expf(mc - M) : __expf(mc - M);
-            s += wgt * pbase[(size_t)c * 1088 + 64 + i];
-        }
-        a.ctxn[((size_t)b * 4 + head) * 1024 + i] = s * s_scale[d];
+#pragma unroll 8
+        for (int c = 0; c < nch; ++c) s += s_w[c][dd] * pbase[(size_t)c * 1088 + 64 + i];
+        a.ctxn[((size_t)b * 4 + head) * 1024 + i] = s * s_scale[dd];
     }
 }
 
@@ -366,6 +376,7 @@ int attn_ctx(ActKind act, const AttnCtxArgs& a, bool strict, cudaStream_t s) {
 }
 
 int attn_merge(const AttnCtxArgs& a, bool strict, cudaStream_t s) {
+    GTTS_REQUIRE(a.chunks <= 64, "attn_merge: too many chunks");
     dim3 grid(4, a.B);
     if (strict) attn_merge_kernel<true><<<grid, 256, 0, s>>>(a);
     else        attn_merge_kernel<false><<<grid, 256, 0, s>>>(a);

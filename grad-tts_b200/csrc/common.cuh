@@ -43,6 +43,16 @@ template <> struct Act<float> {
     }
     __device__ __forceinline__ static float ld(const float* p) { return *p; }
     __device__ __forceinline__ static void st(float* p, float v) { *p = v; }
+    struct Packed { float4 a, b; };
+    __device__ __forceinline__ static Packed load_packed(const float* p) {
+        Packed r;
+        r.a = __ldg(reinterpret_cast<const float4*>(p));
+        r.b = __ldg(reinterpret_cast<const float4*>(p + 4));
+        return r;
+    }
+    __device__ __forceinline__ static void unpack(const Packed& k, float (&v)[8]) {
+        v[0] = k.a.x; v[1] = k.a.y; v[2] = k.a.z; v[3] = k.a.w; v[4] = k.b.x; v[5] = k.b.y; v[6] = k.b.z; v[7] = k.b.w;
+    }
 };
 template <> struct Act<__nv_bfloat16> {
     static constexpr int kBytes = 2;
@@ -66,6 +76,18 @@ template <> struct Act<__nv_bfloat16> {
     }
     __device__ __forceinline__ static float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
     __device__ __forceinline__ static void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+    typedef uint4 Packed;                                  // 8 bf16 stay packed in 4 registers until used
+    __device__ __forceinline__ static Packed load_packed(const __nv_bfloat16* p) {
+        return __ldg(reinterpret_cast<const uint4*>(p));
+    }
+    __device__ __forceinline__ static void unpack(const Packed& u, float (&v)[8]) {
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[2 * i]     = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
 };
 
 // ---------------------------------------------------------------- maths

@@ -190,7 +190,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         // ================================================================ GroupNorm statistics warp
         if (kStats) {
             const ConvEpilogue& e = p.e;
-            const double inv_count = 1.0 / ((double)kGsz * (double)p.Hout * (double)p.Wout);
             int it = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
                 const int slot = it % kStatSlots;
@@ -203,31 +202,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     const float* r = s_ring + (slot * 8 + half * 4) * 8 + idx;
                     v = (r[0] + r[8]) + (r[16] + r[24]);
                     e.gn_partials[((size_t)b * tiles_per_phase + slot_in_sample) * 16 + lane] = v;
-                    __threadfence();
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sempty[slot]);
-                unsigned int old = 0;
-                if (lane == 0) old = atomicAdd(&e.gn_counters[b], 1u);
-                old = __shfl_sync(0xffffffffu, old, 0);
-                if (old == (unsigned int)(tiles_per_phase - 1)) {
-                    // last tile of sample b: fixed-order reduction of all partials (deterministic)
-                    __threadfence();
-                    const int k = lane & 15, slice = lane >> 4;
-                    const float* pp = e.gn_partials + (size_t)b * tiles_per_phase * 16 + k;
-                    double acc = 0.0;
-                    for (int s = slice; s < tiles_per_phase; s += 2) acc += (double)__ldcg(pp + (size_t)s * 16);
-                    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-                    const double sq = __shfl_down_sync(0xffffffffu, acc, 8);
-                    if (lane < 8) {
-                        const double mean = acc * inv_count;
-                        double var = sq * inv_count - mean * mean;
-                        if (var < 0.0) var = 0.0;
-                        e.gn_stats[((size_t)b * 8 + lane) * 2 + 0] = (float)mean;
-                        e.gn_stats[((size_t)b * 8 + lane) * 2 + 1] = (float)(1.0 / sqrt(var + (double)e.gn_eps));
-                    }
-                    if (lane == 0) e.gn_counters[b] = 0u;
-                }
             }
         }
     } else if (warp >= 4) {
@@ -328,11 +305,61 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
     }
 
+    // ---- GroupNorm statistics: ONE fence + ticket per CTA (not per tile).  Every CTA publishes how many tiles of each
+    // sample it contributed; whoever completes a sample's count reduces that sample's partials in a fixed order.
+    if (kStats) __threadfence();
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
+    }
+    if (kStats) {
+        const ConvEpilogue& e = p.e;
+        int* s_nfin = reinterpret_cast<int*>(misc + 2560);
+        int* s_fin = s_nfin + 1;
+        double* s_red = reinterpret_cast<double*>(smem);             // pipeline buffers are idle now: [24][16]
+        if (tid == 0) *s_nfin = 0;
+        __syncthreads();
+        if (warp == 0) {
+            const int G = (int)gridDim.x, bx = (int)blockIdx.x, tps = tiles_per_phase;
+            for (int b = lane; b < p.B; b += 32) {
+                const int lo = b * tps, hi = lo + tps - 1;           // tiles of sample b: lo..hi; mine: bx + i*G
+                const int i_min = lo > bx ? (lo - bx + G - 1) / G : 0;
+                const int i_max = hi >= bx ? (hi - bx) / G : -1;
+                const int cnt = i_max - i_min + 1;
+                if (cnt > 0) {
+                    const unsigned int old = atomicAdd(&e.gn_counters[b], (unsigned int)cnt);
+                    if (old + (unsigned int)cnt == (unsigned int)tps) s_fin[atomicAdd(s_nfin, 1)] = b;
+                }
+            }
+        }
+        __syncthreads();
+        const int nfin = *s_nfin;
+        if (nfin > 0) {
+            __threadfence();
+            const double inv_count = 1.0 / ((double)kGsz * (double)p.Hout * (double)p.Wout);
+            for (int f = 0; f < nfin; ++f) {
+                const int b = s_fin[f];
+                const int k = tid & 15, slice = tid >> 4;            // 24 slices of 16 components
+                const float* pp = e.gn_partials + (size_t)b * tiles_per_phase * 16 + k;
+                double acc = 0.0;
+                for (int sl = slice; sl < tiles_per_phase; sl += kThreads / 16) acc += (double)__ldcg(pp + (size_t)sl * 16);
+                s_red[slice * 16 + k] = acc;
+                __syncthreads();
+                if (tid < 8) {
+                    double sum = 0.0, sq = 0.0;
+                    for (int sl = 0; sl < kThreads / 16; ++sl) { sum += s_red[sl * 16 + tid]; sq += s_red[sl * 16 + 8 + tid]; }
+                    const double mean = sum * inv_count;
+                    double var = sq * inv_count - mean * mean;
+                    if (var < 0.0) var = 0.0;
+                    e.gn_stats[((size_t)b * 8 + tid) * 2 + 0] = (float)mean;
+                    e.gn_stats[((size_t)b * 8 + tid) * 2 + 1] = (float)(1.0 / sqrt(var + (double)e.gn_eps));
+                }
+                if (tid == 0) e.gn_counters[b] = 0u;
+                __syncthreads();
+            }
+        }
     }
 }
 

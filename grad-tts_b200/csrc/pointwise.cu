@@ -189,7 +189,7 @@ first_conv_kernel(FirstConvArgs a) {
 constexpr int kGnVec = 4;
 
 template <typename T, bool kStrict, bool kHasRes, bool kHasTb, bool kFirstRes>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 gn_apply_kernel(GnApplyArgs a) {
     const int C8 = a.C >> 3;
     const int b = blockIdx.y;
@@ -212,22 +212,35 @@ gn_apply_kernel(GnApplyArgs a) {
     T* out = reinterpret_cast<T*>(a.out) + (size_t)b * per_sample * 8;
     const float* mrow = a.mask + (size_t)b * a.W;
 
-    float v[kGnVec][8], r[kGnVec][8], m[kGnVec];
+    typename Act<T>::Packed pv[kGnVec], pr[kGnVec];
+    float m[kGnVec];
     bool ok[kGnVec];
 #pragma unroll
     for (int k = 0; k < kGnVec; ++k) {
         const size_t vi = v0 + (size_t)k * 256;
         ok[k] = vi < per_sample;
         if (ok[k]) {
-            Act<T>::load8(raw + vi * 8, v[k]);
-            if (kHasRes) Act<T>::load8(res + vi * 8, r[k]);
+            pv[k] = Act<T>::load_packed(raw + vi * 8);
+            if (kHasRes) pr[k] = Act<T>::load_packed(res + vi * 8);
             m[k] = mrow[(int)((vi / C8) % a.W)];
+        }
+    }
+    float frw[kFirstRes ? 8 : 1][3], frb[kFirstRes ? 8 : 1];
+    if (kFirstRes) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            frb[j] = __ldg(a.fr_b + c0 + j);
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) frw[j][ci] = ci < a.fr_cin ? __ldg(a.fr_w + (c0 + j) * a.fr_cin + ci) : 0.f;
         }
     }
 #pragma unroll
     for (int k = 0; k < kGnVec; ++k) {
         if (!ok[k]) continue;
         const size_t vi = v0 + (size_t)k * 256;
+        float v[8], r[8];
+        Act<T>::unpack(pv[k], v);
+        if (kHasRes) Act<T>::unpack(pr[k], r);
         float fin[3] = {0.f, 0.f, 0.f};
         if (kFirstRes) {
             const size_t pix = (size_t)b * a.H * a.W + vi / C8;
@@ -237,19 +250,19 @@ gn_apply_kernel(GnApplyArgs a) {
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            float y = fmaf(v[k][j], sc[j], sh[j]);
+            float y = fmaf(v[j], sc[j], sh[j]);
             y = mish<kStrict>(y) * m[k];                                 // Mish, * mask   (:54,58)
             if (kHasTb) y += tb[j];                                      // h += mlp(t)    (:76)
-            if (kHasRes) y += r[k][j];                                   // + res_conv(x)  (:78)
+            if (kHasRes) y += r[j];                                      // + res_conv(x)  (:78)
             if (kFirstRes) {
-                const int c = c0 + j;
-                float rr = __ldg(a.fr_b + c);
-                for (int ci = 0; ci < a.fr_cin; ++ci) rr = fmaf(__ldg(a.fr_w + c * a.fr_cin + ci), fin[ci], rr);
+                float rr = frb[j];
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) rr = fmaf(frw[j][ci], fin[ci], rr);
                 y += rr;
             }
-            v[k][j] = y * m[k];        // every consumer masks its input: store masked (binary masks)
+            v[j] = y * m[k];           // every consumer masks its input: store masked (binary masks)
         }
-        Act<T>::store8(out + vi * 8, v[k]);
+        Act<T>::store8(out + vi * 8, v);
     }
 }
 
@@ -259,7 +272,7 @@ gn_apply_kernel(GnApplyArgs a) {
 constexpr int kEuPix = 4;
 
 template <typename T, bool kStrict>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 euler_kernel(EulerArgs a) {
     const size_t npix = (size_t)a.B * a.H * a.W;
     const int sub = threadIdx.x & 7;
@@ -272,11 +285,11 @@ euler_kernel(EulerArgs a) {
         sh_[j] = __ldg(a.beta + sub * 8 + j);
         wf[j] = __ldg(a.wf + sub * 8 + j);
     }
-    float v[kEuPix][8];
+    typename Act<T>::Packed pv[kEuPix];
 #pragma unroll
     for (int k = 0; k < kEuPix; ++k) {
         const size_t pix = pbase + k;
-        if (pix < npix) Act<T>::load8(reinterpret_cast<const T*>(a.raw) + pix * 64 + sub * 8, v[k]);
+        if (pix < npix) pv[k] = Act<T>::load_packed(reinterpret_cast<const T*>(a.raw) + pix * 64 + sub * 8);
     }
     const float beta_t = a.update ? a.beta_tab[*a.step] : 0.f;
     const float hh = a.update ? *a.h_ptr : 0.f;
@@ -291,9 +304,11 @@ euler_kernel(EulerArgs a) {
         const float mean = a.stats[(b * 8 + sub) * 2], rstd = a.stats[(b * 8 + sub) * 2 + 1];
         float part = 0.f;
         if (valid) {
+            float v[8];
+            Act<T>::unpack(pv[k], v);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                float y = (v[k][j] - mean) * rstd * sc[j] + sh_[j];
+                float y = (v[j] - mean) * rstd * sc[j] + sh_[j];
                 y = mish<kStrict>(y) * m;                      // final_block(x, mask)              (:212)
                 part = fmaf(y * m, wf[j], part);               // final_conv(x * mask)              (:213)
             }
