@@ -196,6 +196,7 @@ int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, i
     cudaStream_t s = (cudaStream_t)stream;
     const ActKind ak = act ? ACT_BF16 : ACT_F32;
     GTTS_REQUIRE(impl == 0 || ak == ACT_BF16, "tcgen05 conv needs bf16 activations");
+    const int halo_mode = impl >= 2 ? impl - 1 : 0;            // impl 2 -> halo (base_offset = phase), 3 -> halo (base_offset 0)
     const int Cin = Cin0 + Cin1;
     ConvGeom g;
     memset(&g, 0, sizeof(g));
@@ -244,18 +245,20 @@ int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, i
     float* partials = nullptr;
     unsigned int* counters = nullptr;
     if (gn_stats) {
-        const size_t slots = impl == 1 ? conv_tc_partials_slots(g) : conv_ffma_partials_slots(g);
+        size_t slots = impl >= 1 ? conv_tc_partials_slots(g) : conv_ffma_partials_slots(g);
+        if (halo_mode && conv_tc_halo_eligible(g)) slots = conv_tc_halo_partials_slots(g);
         GTTS_CHECK_CUDA(cudaMalloc(&partials, (size_t)B * slots * 16 * 4));
         GTTS_CHECK_CUDA(cudaMalloc(&counters, (size_t)B * 4));
         GTTS_CHECK_CUDA(cudaMemsetAsync(counters, 0, (size_t)B * 4, s));
         e.gn_partials = partials; e.gn_stats = gn_stats; e.gn_counters = counters; e.gn_eps = 1e-5f;
     }
     int rc = 0;
-    if (impl == 1) {
+    if (impl >= 1) {
+        GTTS_REQUIRE(!halo_mode || (conv_tc_halo_eligible(g) && !residual && !mask), "halo test: geometry not eligible");
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        TcConvPlan* tp = conv_tc_plan_create(g, src0, src1, wpk, (int)wrows, e, sms);
+        TcConvPlan* tp = conv_tc_plan_create(g, src0, src1, wpk, (int)wrows, e, sms, halo_mode);
         if (!tp) rc = 1;
         else {
             rc = conv_tc_launch(tp, s);

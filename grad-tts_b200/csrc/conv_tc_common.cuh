@@ -1,0 +1,367 @@
+// Shared device/host pieces of the tcgen05 convolution kernels (conv_tc.cu: one TMA box per tap;
+// conv_tc_halo.cu: one halo box per tile, taps as shifted descriptor views).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ops.h"
+
+namespace gtts {
+namespace tc {
+
+constexpr int kABytes = 128 * 128;                 // 128 pixel rows x 64 bf16
+constexpr int kMiscBytes = 4096;                   // barriers + epilogue scratch
+constexpr int kHaloABytes = 18 * 16 * 128;         // halo box: 18 rows x 16 pixels x 64 bf16
+constexpr int kStatSlots = 4;                      // ring of per-tile GroupNorm partials (epilogue warps -> stats warp)
+constexpr int kThreads = 384;                      // warps 0-3: TMA, MMA, TMEM alloc, stats; warps 4-11: epilogue
+
+struct TcParams {
+    int bh, bw, tiles_h, tiles_w, nphase, B;
+    int Hg, Wg, Hout, Wout, out_step;
+    int ntaps, nchunk0, nchunk1, Cin0;
+    int stride2, w_batch_rows, num_tiles, a_bytes, stages;
+    int halo_mode, b_slots, b_resident;            // conv_tc_halo.cu only
+    int8_t dy[4][9], dx[4][9];
+    int wrow[4][9];
+    int oy[4], ox[4];
+    ConvEpilogue e;
+};
+
+// misc shared-memory block layout (relative to `misc`)
+//   [0,   512)  mbarriers        [512, 1536) bias[256]      [1536, 2560) stats ring      [2560, 4096) finalize list
+struct TcShared {
+    uint64_t *full, *empty, *tfull, *tempty, *sfull, *sempty, *fullb, *emptyb;
+    uint32_t* tmem_slot;
+    float* s_bias;
+    float* s_ring;
+    uint8_t* misc;
+};
+__device__ __forceinline__ TcShared tc_shared(uint8_t* misc) {
+    TcShared s;
+    s.misc = misc;
+    s.full = reinterpret_cast<uint64_t*>(misc);        // [8]
+    s.empty = s.full + 8;                              // [8]
+    s.tfull = s.empty + 8;                             // [2]
+    s.tempty = s.tfull + 2;                            // [2]
+    s.sfull = s.tempty + 2;                            // [kStatSlots]
+    s.sempty = s.sfull + kStatSlots;                   // [kStatSlots]
+    s.fullb = s.sempty + kStatSlots;                   // [16]
+    s.emptyb = s.fullb + 16;                           // [16]
+    s.tmem_slot = reinterpret_cast<uint32_t*>(s.emptyb + 16);
+    s.s_bias = reinterpret_cast<float*>(misc + 512);
+    s.s_ring = reinterpret_cast<float*>(misc + 1536);
+    return s;
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor.  sbo = byte distance between 8-row groups,
+// base_offset = swizzle phase of the start row (bits 7..9 of the start address within the 1024-byte pattern).
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t saddr, uint32_t sbo = 1024, uint32_t base_offset = 0) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);      // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(sbo >> 4) << 32;               // stride byte offset
+    d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+    d |= (uint64_t)(base_offset & 7u) << 49;       // matrix base offset
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+
+template <int N>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+    // kind::f16: D=f32 (bit 4), A=bf16 (bit 7), B=bf16 (bit 10), K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// Butterfly transpose-reduce of 8 per-thread values across the warp in 9 shuffles (instead of 40):
+// afterwards every lane holds the full 32-lane sum of value index ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1).
+__device__ __forceinline__ float warp_reduce8(const float (&v)[8], int lane) {
+    float w[4], u[2], t;
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float keep = b4 ? v[4 + i] : v[i], send = b4 ? v[i] : v[4 + i];
+        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float keep = b3 ? w[2 + i] : w[i], send = b3 ? w[i] : w[2 + i];
+        u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    {
+        const float keep = b2 ? u[1] : u[0], send = b2 ? u[0] : u[1];
+        t = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    return t;
+}
+
+// Common prologue: barrier init, TMEM allocation, bias staging.  `stages` A/B ring slots, `b_slots` extra B ring slots.
+template <int N>
+__device__ __forceinline__ uint32_t tc_prologue(const TcParams& p, const TcShared& sh, int nfull, int nfullb, int tid,
+                                                int warp, int lane) {
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < nfull; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }
+        for (int s = 0; s < nfullb; ++s) { mbar_init(&sh.fullb[s], 1); mbar_init(&sh.emptyb[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&sh.tfull[i], 1); mbar_init(&sh.tempty[i], 256); }
+        for (int i = 0; i < kStatSlots; ++i) { mbar_init(&sh.sfull[i], 8); mbar_init(&sh.sempty[i], 1); }
+        mbar_fence_init();
+    } else if (warp == 2) {
+        tmem_alloc(sh.tmem_slot, 2 * N);
+        tmem_relinquish();
+    }
+    for (int i = tid; i < N; i += kThreads) sh.s_bias[i] = p.e.bias ? p.e.bias[i] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    return *sh.tmem_slot;
+}
+
+// GroupNorm statistics warp (warp 3): sums the 8 epilogue warps' per-tile values and writes the tile's 16 partials.
+template <bool kStats>
+__device__ __forceinline__ void tc_stats_loop(const TcParams& p, const TcShared& sh, int lane) {
+    uint64_t* sfull = sh.sfull;
+    uint64_t* sempty = sh.sempty;
+    float* s_ring = sh.s_ring;
+    const int tiles_per_phase = p.tiles_h * p.tiles_w;
+    if (kStats) {
+        const ConvEpilogue& e = p.e;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int slot = it % kStatSlots;
+            const int b = tile / tiles_per_phase, slot_in_sample = tile - b * tiles_per_phase;
+            mbar_wait(&sfull[slot], (uint32_t)(it / kStatSlots) & 1u);
+            // value k (0..7 sums, 8..15 sums of squares) of group g = k & 7 lives in column half g >> 2
+            float v = 0.f;
+            if (lane < 16) {
+                const int g = lane & 7, which = lane >> 3, half = g >> 2, idx = which * 4 + (g & 3);
+                const float* r = s_ring + (slot * 8 + half * 4) * 8 + idx;
+                v = (r[0] + r[8]) + (r[16] + r[24]);
+                e.gn_partials[((size_t)b * tiles_per_phase + slot_in_sample) * 16 + lane] = v;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sempty[slot]);
+        }
+    }
+}
+
+// Epilogue warps (warps 4..11): TMEM -> registers -> (+bias, stats, +residual, *mask) -> bf16 NHWC stores.
+template <int N, bool kStats, bool kRes, bool kMask>
+__device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShared& sh, uint32_t tmem_base, int warp,
+                                                 int lane) {
+    constexpr int kColsPerWarp = N / 2;            // two epilogue warps share each TMEM lane quarter
+    constexpr int kGsz = N / 8;                    // channels per GroupNorm group (4 groups per column half)
+    uint64_t* tfull = sh.tfull;
+    uint64_t* tempty = sh.tempty;
+    uint64_t* sfull = sh.sfull;
+    uint64_t* sempty = sh.sempty;
+    float* s_bias = sh.s_bias;
+    float* s_ring = sh.s_ring;
+    const int tiles_per_phase = p.tiles_h * p.tiles_w;
+    const int ew = warp - 4, wq = ew & 3, half = ew >> 2;
+    const int row = wq * 32 + lane;                              // TMEM lane = pixel row of the tile
+    const ConvEpilogue& e = p.e;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.out);
+    const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(e.residual);
+    const int cbase = half * kColsPerWarp;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h;
+        const int ph = (tile / tiles_per_phase) % p.nphase, b = tile / (tiles_per_phase * p.nphase);
+        const int hl = row / p.bw, wl = row - hl * p.bw;
+        const int j = th * p.bh + hl, i = tw * p.bw + wl;
+        const bool valid = (hl < p.bh) && (j < p.Hg) && (i < p.Wg);
+        const int oh = j * p.out_step + p.oy[ph], ow = i * p.out_step + p.ox[ph];
+        const size_t opix = valid ? ((size_t)b * p.Hout + oh) * p.Wout + ow : 0;
+        float m = 1.0f;
+        if (kMask) m = valid ? e.mask[(size_t)b * p.Wout + ow] : 0.f;
+
+        mbar_wait(&tfull[buf], (uint32_t)(it >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * N + cbase);
+
+        float st[8];                                             // [0..3] sums, [4..7] sums of squares
+#pragma unroll
+        for (int g = 0; g < 8; ++g) st[g] = 0.f;
+
+#pragma unroll
+        for (int c0 = 0; c0 < kColsPerWarp; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(taddr + (uint32_t)c0, r);
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[cbase + c0 + q4 * 4]);
+                f[q4 * 4 + 0] = __uint_as_float(r[q4 * 4 + 0]) + b4.x;
+                f[q4 * 4 + 1] = __uint_as_float(r[q4 * 4 + 1]) + b4.y;
+                f[q4 * 4 + 2] = __uint_as_float(r[q4 * 4 + 2]) + b4.z;
+                f[q4 * 4 + 3] = __uint_as_float(r[q4 * 4 + 3]) + b4.w;
+            }
+            if (kStats) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const int g = (c0 + q) / kGsz;               // local group 0..3 (compile time)
+                    const float x = valid ? f[q] : 0.f;
+                    st[g] += x;
+                    st[4 + g] = fmaf(x, x, st[4 + g]);
+                }
+            }
+            if (valid) {
+                if (kRes) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(res + opix * N + cbase + c0);
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4) {
+                        const uint4 u = __ldg(rp + v4);
+                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            f[v4 * 8 + 2 * k] += __uint_as_float(w[k] << 16);
+                            f[v4 * 8 + 2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
+                        }
+                    }
+                }
+                if (kMask) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) f[q] *= m;
+                }
+                uint4* op = reinterpret_cast<uint4*>(out + opix * N + cbase + c0);
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[v4 * 8 + 2 * k], f[v4 * 8 + 2 * k + 1]);
+                        w[k] = *reinterpret_cast<uint32_t*>(&h2);
+                    }
+                    op[v4] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+        }
+        // all TMEM reads of this buffer are complete: hand it back to the MMA warp
+        tc_fence_before();
+        mbar_arrive(&tempty[buf]);
+
+        if (kStats) {
+            const float t = warp_reduce8(st, lane);
+            const int slot = it % kStatSlots;
+            mbar_wait(&sempty[slot], ((uint32_t)(it / kStatSlots) & 1u) ^ 1u);
+            if ((lane & 3) == 0) s_ring[(slot * 8 + ew) * 8 + (lane >> 2)] = t;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sfull[slot]);            // release: orders the ring writes of this warp
+        }
+    }
+}
+
+// Kernel tail: one fence + ticket per CTA; whoever completes a sample's tile count reduces its partials (fixed order).
+template <int N, bool kStats>
+__device__ __forceinline__ void tc_teardown(const TcParams& p, const TcShared& sh, uint8_t* smem, uint32_t tmem_base,
+                                            int tid, int warp, int lane) {
+    constexpr int kGsz = N / 8;
+    uint8_t* misc = sh.misc;
+    const int tiles_per_phase = p.tiles_h * p.tiles_w;
+    if (kStats) __threadfence();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * N);
+    }
+    if (kStats) {
+        const ConvEpilogue& e = p.e;
+        int* s_nfin = reinterpret_cast<int*>(misc + 2560);
+        int* s_fin = s_nfin + 1;
+        double* s_red = reinterpret_cast<double*>(smem);             // pipeline buffers are idle now: [24][16]
+        if (tid == 0) *s_nfin = 0;
+        __syncthreads();
+        if (warp == 0) {
+            const int G = (int)gridDim.x, bx = (int)blockIdx.x, tps = tiles_per_phase;
+            for (int b = lane; b < p.B; b += 32) {
+                const int lo = b * tps, hi = lo + tps - 1;           // tiles of sample b: lo..hi; mine: bx + i*G
+                const int i_min = lo > bx ? (lo - bx + G - 1) / G : 0;
+                const int i_max = hi >= bx ? (hi - bx) / G : -1;
+                const int cnt = i_max - i_min + 1;
+                if (cnt > 0) {
+                    const unsigned int old = atomicAdd(&e.gn_counters[b], (unsigned int)cnt);
+                    if (old + (unsigned int)cnt == (unsigned int)tps) s_fin[atomicAdd(s_nfin, 1)] = b;
+                }
+            }
+        }
+        __syncthreads();
+        const int nfin = *s_nfin;
+        if (nfin > 0) {
+            __threadfence();
+            const double inv_count = 1.0 / ((double)kGsz * (double)p.Hout * (double)p.Wout);
+            for (int f = 0; f < nfin; ++f) {
+                const int b = s_fin[f];
+                const int k = tid & 15, slice = tid >> 4;            // 24 slices of 16 components
+                const float* pp = e.gn_partials + (size_t)b * tiles_per_phase * 16 + k;
+                double acc = 0.0;
+                for (int sl = slice; sl < tiles_per_phase; sl += kThreads / 16) acc += (double)__ldcg(pp + (size_t)sl * 16);
+                s_red[slice * 16 + k] = acc;
+                __syncthreads();
+                if (tid < 8) {
+                    double sum = 0.0, sq = 0.0;
+                    for (int sl = 0; sl < kThreads / 16; ++sl) { sum += s_red[sl * 16 + tid]; sq += s_red[sl * 16 + 8 + tid]; }
+                    const double mean = sum * inv_count;
+                    double var = sq * inv_count - mean * mean;
+                    if (var < 0.0) var = 0.0;
+                    e.gn_stats[((size_t)b * 8 + tid) * 2 + 0] = (float)mean;
+                    e.gn_stats[((size_t)b * 8 + tid) * 2 + 1] = (float)(1.0 / sqrt(var + (double)e.gn_eps));
+                }
+                if (tid == 0) e.gn_counters[b] = 0u;
+                __syncthreads();
+            }
+        }
+    }
+}
+
+}  // namespace tc
+
+struct TcConvPlan {
+    CUtensorMap mapA0, mapA1, mapW;
+    tc::TcParams p;
+    int N, grid;
+    size_t smem;
+};
+int conv_tc_halo_launch(const TcConvPlan* pl, cudaStream_t stream);      // conv_tc_halo.cu
+
+namespace tc {
+// ------------------------------------------------------------------------------------------------ host helpers
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+inline bool encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not found"); return false; }
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        return false;
+    }
+    return true;
+}
+
+}  // namespace tc
+}  // namespace gtts

@@ -1,0 +1,156 @@
+// 3x3 stride-1 convolution on tcgen05 with ONE halo load per (tile, 64-channel chunk).
+//
+// conv_tc.cu fetches a separate TMA box for each of the 9 taps, so the same activations cross the L2 -> SMEM
+// path nine times; measured on B200 that path (~14.5 TB/s chip-wide) is what bounds the 64- and 128-channel
+// layers.  Here the tile is 16 rows x 8 pixels (M = 128) and the producer loads one 18 x 16-pixel box
+// (64 channels, 128-byte swizzled, 36 KB).  Pixel (hh, ww) of the box sits in shared-memory row hh*16 + ww, so
+// for tap (dy, dx) the A operand "row m = hl*8 + wl -> box row (hl+dy)*16 + (wl+dx)" is an ordinary K-major
+// SWIZZLE_128B matrix whose 8-row groups are 2048 bytes apart (SBO) and whose start is shifted by
+// (dy*16 + dx) rows: nine descriptor views of one buffer.  Because 16 rows = 2 swizzle patterns, every group
+// starts at the same swizzle phase (dx), which the descriptor's base-offset field carries.
+// Weights are loaded once per CTA when all 9*Cin/64 tiles fit in shared memory (64->64, 64->128), otherwise they
+// stream through their own ring.
+#include <cstring>
+
+#include "conv_tc_common.cuh"
+
+namespace gtts {
+
+using namespace tc;
+
+namespace {
+
+template <int N, bool kStats>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                    const __grid_constant__ CUtensorMap mapW, const TcParams p) {
+    constexpr int kBBytes = N * 128;
+    constexpr uint32_t kIdesc = make_idesc<N>();
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+    uint8_t* smem_b = smem + (size_t)p.stages * kHaloABytes;
+    const TcShared sh = tc_shared(smem_b + (size_t)p.b_slots * kBBytes);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA0);
+        tma_prefetch_desc(&mapA1);
+        tma_prefetch_desc(&mapW);
+    }
+    const uint32_t tmem_base = tc_prologue<N>(p, sh, p.stages, p.b_slots, tid, warp, lane);
+
+    const int nck = p.nchunk0 + p.nchunk1;
+    const int tiles_per_phase = p.tiles_h * p.tiles_w;
+
+    if (warp == 0) {
+        // ================================================================ TMA producer
+        if (lane == 0) {
+            int sa = 0, sb = 0;
+            uint32_t pha = 0, phb = 0;
+            bool first = true;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, b = tile / tiles_per_phase;
+                const int h0 = th * 16, w0 = tw * 8;
+                for (int ck = 0; ck < nck; ++ck) {
+                    mbar_wait(&sh.empty[sa], pha ^ 1u);
+                    mbar_expect_tx(&sh.full[sa], (uint32_t)kHaloABytes);
+                    if (ck < p.nchunk0) tma_load_4d(&mapA0, &sh.full[sa], smem + (size_t)sa * kHaloABytes, ck * 64, w0 - 1, h0 - 1, b);
+                    else tma_load_4d(&mapA1, &sh.full[sa], smem + (size_t)sa * kHaloABytes, (ck - p.nchunk0) * 64, w0 - 1, h0 - 1, b);
+                    if (++sa == p.stages) { sa = 0; pha ^= 1u; }
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (p.b_resident) {
+                            if (first) {
+                                const int slot = ck * 9 + tap;
+                                mbar_expect_tx(&sh.fullb[slot], (uint32_t)kBBytes);
+                                tma_load_2d(&mapW, &sh.fullb[slot], smem_b + (size_t)slot * kBBytes, ck * 64, p.wrow[0][tap]);
+                            }
+                        } else {
+                            mbar_wait(&sh.emptyb[sb], phb ^ 1u);
+                            mbar_expect_tx(&sh.fullb[sb], (uint32_t)kBBytes);
+                            tma_load_2d(&mapW, &sh.fullb[sb], smem_b + (size_t)sb * kBBytes, ck * 64, p.wrow[0][tap]);
+                            if (++sb == p.b_slots) { sb = 0; phb ^= 1u; }
+                        }
+                    }
+                }
+                first = false;
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================ MMA issuer
+        int sa = 0, sb = 0, it = 0;
+        uint32_t pha = 0, phb = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            mbar_wait(&sh.tempty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
+            for (int ck = 0; ck < nck; ++ck) {
+                mbar_wait(&sh.full[sa], pha);
+                const uint32_t a_base = smem_u32(smem + (size_t)sa * kHaloABytes);
+                for (int tap = 0; tap < 9; ++tap) {
+                    int slot;
+                    if (p.b_resident) {
+                        slot = ck * 9 + tap;
+                        if (it == 0) mbar_wait(&sh.fullb[slot], 0u);
+                    } else {
+                        slot = sb;
+                        mbar_wait(&sh.fullb[sb], phb);
+                    }
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const int dy = tap / 3, dx = tap - dy * 3;
+                        const uint32_t a_addr = a_base + (uint32_t)((dy * 16 + dx) * 128);
+                        const uint64_t adesc = make_sw128_kmajor_desc(a_addr, 2048u, p.halo_mode == 1 ? (uint32_t)dx : 0u);
+                        const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smem_b + (size_t)slot * kBBytes));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
+                                       (uint32_t)((ck | tap | k) != 0));
+                        if (!p.b_resident) tc_commit(&sh.emptyb[sb]);
+                        if (tap == 8) {
+                            tc_commit(&sh.empty[sa]);
+                            if (ck == nck - 1) tc_commit(&sh.tfull[buf]);
+                        }
+                    }
+                    __syncwarp();
+                    if (!p.b_resident) { if (++sb == p.b_slots) { sb = 0; phb ^= 1u; } }
+                }
+                if (++sa == p.stages) { sa = 0; pha ^= 1u; }
+            }
+        }
+    } else if (warp == 3) {
+        tc_stats_loop<kStats>(p, sh, lane);
+    } else if (warp >= 4) {
+        tc_epilogue_loop<N, kStats, false, false>(p, sh, tmem_base, warp, lane);
+    }
+    tc_teardown<N, kStats>(p, sh, smem, tmem_base, tid, warp, lane);
+}
+
+template <int N, bool kStats>
+int launch_halo(const TcConvPlan* pl, cudaStream_t stream) {
+    static bool attr_set = false;
+    auto k = conv_tc_halo_kernel<N, kStats>;
+    if (!attr_set) {
+        GTTS_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    k<<<pl->grid, kThreads, pl->smem, stream>>>(pl->mapA0, pl->mapA1, pl->mapW, pl->p);
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+int conv_tc_halo_launch(const TcConvPlan* pl, cudaStream_t stream) {
+    const ConvEpilogue& e = pl->p.e;
+    GTTS_REQUIRE(e.residual == nullptr && e.mask == nullptr, "conv_tc_halo: plain or GN-statistics epilogue only");
+    const bool st = e.gn_partials != nullptr;
+    if (pl->N == 64) return st ? launch_halo<64, true>(pl, stream) : launch_halo<64, false>(pl, stream);
+    if (pl->N == 128) return st ? launch_halo<128, true>(pl, stream) : launch_halo<128, false>(pl, stream);
+    set_error("conv_tc_halo: unsupported Cout");
+    return 2;
+}
+
+}  // namespace gtts

@@ -98,6 +98,7 @@ struct Decoder {
     int max_chunk = 8;
     bool use_graph = true;
     int conv_impl_bf16 = 1;   // 1: tcgen05, 0: FFMA (debug cross-check)
+    int halo_mode = 0;        // 3x3 convs: 0 = per-tap boxes, 1/2 = halo box + shifted descriptor views
     std::map<std::string, float*> params;
     std::map<std::string, size_t> param_numel;
     DevMem param_mem;
@@ -369,7 +370,11 @@ struct PlanBuilder {
         return p;
     }
     bool use_tc() const { return kind == ACT_BF16 && d->conv_impl_bf16 == 1; }
-    size_t slots_for(const ConvGeom& g) const { return use_tc() ? conv_tc_partials_slots(g) : conv_ffma_partials_slots(g); }
+    size_t slots_for(const ConvGeom& g) const {
+        if (!use_tc()) return conv_ffma_partials_slots(g);
+        if (d->halo_mode && conv_tc_halo_eligible(g)) return conv_tc_halo_partials_slots(g);
+        return conv_tc_partials_slots(g);
+    }
 
     // Registers one convolution.  GN statistics are requested by passing a stats buffer.
     void add_conv(const ConvGeom& g, const void* src0, const void* src1, const void* w, int wrows, const float* bias,
@@ -391,7 +396,7 @@ struct PlanBuilder {
         std::string name = std::string(g.nphase == 4 ? "convT4x4" : (g.ntaps == 9 ? (g.stride == 2 ? "conv3x3s2" : "conv3x3") : "conv1x1")) +
                            "_" + std::to_string((int)cin) + "_" + std::to_string(g.Cout) + "_h" + std::to_string(g.Hin);
         if (use_tc()) {
-            TcConvPlan* tp = conv_tc_plan_create(g, src0, src1, w, wrows, e, d->num_sms);
+            TcConvPlan* tp = conv_tc_plan_create(g, src0, src1, w, wrows, e, d->num_sms, (residual || mask) ? 0 : d->halo_mode);
             if (!tp) { failed = true; return; }
             pl->tc_plans.push_back(tp);
             pl->push(name, 1, flops, bytes, [tp](cudaStream_t s) { return conv_tc_launch(tp, s); });
@@ -526,13 +531,13 @@ struct PlanBuilder {
         {
             ConvGeom g0 = geom_3x3(B, H[0], W[0], 64, 0, 64, 1);
             size_t s = conv_ffma_partials_slots(g0);
-            size_t s2 = conv_tc_partials_slots(g0);
+            size_t s2 = std::max(conv_tc_partials_slots(g0), conv_tc_halo_partials_slots(g0));
             size_t s3 = first_conv_partials_slots(H[0], W[0]);
             for (int l = 1; l < 3; ++l)
                 for (int C = 64; C <= 256; C *= 2) {
                     ConvGeom gl = geom_3x3(B, H[l], W[l], 64, 0, C, 1);
                     s = std::max(s, conv_ffma_partials_slots(gl));
-                    s2 = std::max(s2, conv_tc_partials_slots(gl));
+                    s2 = std::max(s2, std::max(conv_tc_partials_slots(gl), conv_tc_halo_partials_slots(gl)));
                 }
             pl->partial_slots = std::max(s, std::max(s2, s3));
             pl->partials = (float*)pl->mem.alloc((size_t)B * pl->partial_slots * 16 * 4);
@@ -683,7 +688,7 @@ int plan_create(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde,
 int get_plan(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, Plan** out) {
     std::string key = std::to_string((int)kind) + ":" + std::to_string(B) + ":" + std::to_string(T) + ":" +
                       (est_mode ? "e" : "s") + (sde ? "n" : "o") + (d->use_graph ? "g" : "x") +
-                      std::to_string(d->conv_impl_bf16);
+                      std::to_string(d->conv_impl_bf16) + std::to_string(d->halo_mode);
     auto it = d->plans.find(key);
     if (it != d->plans.end()) { *out = it->second; return 0; }
     // keep at most a handful of plans alive (each owns its workspace)
@@ -883,6 +888,7 @@ int decoder_set_option(Decoder* d, const char* key, int value) {
     if (k == "max_chunk") { GTTS_REQUIRE(value >= 1, "max_chunk must be >= 1"); d->max_chunk = value; }
     else if (k == "use_graph") d->use_graph = value != 0;
     else if (k == "conv_impl_bf16") d->conv_impl_bf16 = value;
+    else if (k == "halo_mode") d->halo_mode = value;
     else { set_error("unknown option " + k); return 2; }
     return 0;
 }

@@ -125,11 +125,40 @@ def stage_perf():
             traceback.print_exc()
 
 
+def stage_halo():
+    import gpu_util as gu
+    cases = [("3x3_64_64_l0", dict(kind=0, B=2, H=80, W=24, Cin0=64, Cin1=0, Cout=64)),
+             ("3x3_64_128_odd", dict(kind=0, B=1, H=40, W=22, Cin0=64, Cin1=0, Cout=128)),
+             ("3x3_128_128", dict(kind=0, B=2, H=40, W=36, Cin0=128, Cin1=0, Cout=128)),
+             ("3x3_cat_256_64", dict(kind=0, B=1, H=40, W=20, Cin0=128, Cin1=128, Cout=64)),
+             ("3x3_cat_512_128", dict(kind=0, B=1, H=20, W=12, Cin0=256, Cin1=256, Cout=128))]
+    for impl in (2, 3):
+        for name, kw in cases:
+            try:
+                c = gu.conv_case(seed=hash(name) % 1000, **kw)
+                out, st = gu.run_conv(c, impl, 1, want_stats=True)
+                ref, raw = gu.conv_reference(c, round_bf16=True)
+                err = float((out - ref).abs().max())
+                sref = gu.gn_stats_reference(raw)
+                serr = float(((st - sref).abs() / (sref.abs() + 1.0)).max())
+                d = (out - ref).abs()
+                bad = d > 0.1
+                print(f"halo impl={impl} {name}: max-abs err {err:.3e} nan {int(torch.isnan(out).sum())} stats-err {serr:.3e} "
+                      f"bad {int(bad.sum())}/{bad.numel()}")
+                if int(bad.sum()):
+                    print("     per-col-bad", bad.sum((0, 1, 2))[:24].tolist(), "per-row-bad", bad.sum((0, 1, 3))[:40].tolist())
+            except Exception:
+                print(f"halo impl={impl} {name}: EXCEPTION")
+                traceback.print_exc()
+
+
 def stage_profile():
     import ctypes, json
     for (n_spks, B, T) in [(1, 16, 1720), (1, 1, 400)]:
         dec, _ = _decoder(n_spks, 0, "bf16")
         dec.estimator.max_chunk = B
+        hm = int(os.environ.get("GTTS_HALO", "0"))
+        pkg._lib.check(pkg._lib.load().gtts_decoder_set_option(dec.estimator._get_handle(), b"halo_mode", hm), "opt")
         z, mask, mu, spk, _ = pkg.synth.make_inputs(B, T, n_spks, seed=7, ragged=False)
         dec(z.to(DEV), mask.to(DEV), mu.to(DEV), 2)
         torch.cuda.synchronize()
@@ -152,6 +181,6 @@ if __name__ == "__main__":
     print(f"===== stage {st} on {torch.cuda.get_device_name(0)}", flush=True)
     {"mas": stage_mas, "conv_ffma": lambda: (stage_conv(0, 0), stage_conv(0, 1)), "conv_tc": lambda: stage_conv(1, 1),
      "dec_fp32": lambda: stage_dec("fp32"), "dec_bf16_ffma": lambda: stage_dec("bf16", 0),
-     "dec_bf16_tc": lambda: stage_dec("bf16", 1), "perf": stage_perf, "profile": stage_profile}[st]()
+     "dec_bf16_tc": lambda: stage_dec("bf16", 1), "perf": stage_perf, "profile": stage_profile, "halo": stage_halo}[st]()
     torch.cuda.synchronize()
     print(f"===== stage {st} done", flush=True)
