@@ -196,7 +196,7 @@ int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, i
     cudaStream_t s = (cudaStream_t)stream;
     const ActKind ak = act ? ACT_BF16 : ACT_F32;
     GTTS_REQUIRE(impl == 0 || ak == ACT_BF16, "tcgen05 conv needs bf16 activations");
-    const int halo_mode = impl >= 2 ? impl - 1 : 0;            // impl 2 -> halo (base_offset = phase), 3 -> halo (base_offset 0)
+    const int halo_mode = impl >= 2 ? impl - 1 : 0;            // impl 2 -> halo box 18x16, 3 -> halo box 18x10
     const int Cin = Cin0 + Cin1;
     ConvGeom g;
     memset(&g, 0, sizeof(g));

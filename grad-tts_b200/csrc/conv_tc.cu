@@ -183,15 +183,18 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
     if (halo_mode) {
         // A ring: halo boxes of 18 x 16 pixels x 64 ch (36 KB); B: resident (all 9*nck tiles) if it fits, else a ring
         const int nck = p.nchunk0 + p.nchunk1, btile = g.Cout * 128, ntiles_b = 9 * nck;
-        p.a_bytes = kHaloABytes;
-        if (ntiles_b <= 16 && ntiles_b * btile + 3 * kHaloABytes <= budget) { p.stages = 3; p.b_resident = 1; p.b_slots = ntiles_b; }
-        else if (ntiles_b <= 16 && ntiles_b * btile + 2 * kHaloABytes <= budget) { p.stages = 2; p.b_resident = 1; p.b_slots = ntiles_b; }
+        const int pw = halo_mode == 2 ? 10 : 16;
+        const int abytes = (18 * pw * 128 + 1023) / 1024 * 1024;     // stage stride keeps every stage 1024-aligned
+        p.a_bytes = abytes;
+        if (ntiles_b <= 16 && ntiles_b * btile + 4 * abytes <= budget) { p.stages = 4; p.b_resident = 1; p.b_slots = ntiles_b; }
+        else if (ntiles_b <= 16 && ntiles_b * btile + 3 * abytes <= budget) { p.stages = 3; p.b_resident = 1; p.b_slots = ntiles_b; }
+        else if (ntiles_b <= 16 && ntiles_b * btile + 2 * abytes <= budget) { p.stages = 2; p.b_resident = 1; p.b_slots = ntiles_b; }
         else {
             p.stages = 3; p.b_resident = 0;
-            p.b_slots = (budget - 3 * kHaloABytes) / btile;
+            p.b_slots = (budget - 3 * abytes) / btile;
             if (p.b_slots > 16) p.b_slots = 16;
         }
-        pl->smem = (size_t)p.stages * kHaloABytes + (size_t)p.b_slots * btile + kMiscBytes + 1024;
+        pl->smem = (size_t)p.stages * abytes + (size_t)p.b_slots * btile + kMiscBytes + 1024;
     } else {
         const int stage_bytes = kABytes + g.Cout * 128;
         int stages = budget / stage_bytes;
@@ -208,7 +211,7 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
             uint64_t dims[4] = {(uint64_t)C, W, H, (uint64_t)g.B};
             uint64_t str[3] = {(uint64_t)C * 2, W * C * 2, H * W * C * 2};
             uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, 1};
-            if (halo_mode) { box[1] = 16; box[2] = 18; }
+            if (halo_mode) { box[1] = halo_mode == 2 ? 10 : 16; box[2] = 18; }
             return encode_map(m, src, 4, dims, str, box);
         } else {
             uint64_t dims[5] = {(uint64_t)2 * C, W / 2, 2, H / 2, (uint64_t)g.B};

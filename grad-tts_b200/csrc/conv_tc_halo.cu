@@ -5,9 +5,11 @@
 // layers.  Here the tile is 16 rows x 8 pixels (M = 128) and the producer loads one 18 x 16-pixel box
 // (64 channels, 128-byte swizzled, 36 KB).  Pixel (hh, ww) of the box sits in shared-memory row hh*16 + ww, so
 // for tap (dy, dx) the A operand "row m = hl*8 + wl -> box row (hl+dy)*16 + (wl+dx)" is an ordinary K-major
-// SWIZZLE_128B matrix whose 8-row groups are 2048 bytes apart (SBO) and whose start is shifted by
-// (dy*16 + dx) rows: nine descriptor views of one buffer.  Because 16 rows = 2 swizzle patterns, every group
-// starts at the same swizzle phase (dx), which the descriptor's base-offset field carries.
+// SWIZZLE_128B matrix whose 8-row groups are pitch*128 bytes apart (SBO) and whose start is shifted by
+// (dy*pitch + dx) rows: nine descriptor views of one buffer.  Measured on B200: the tcgen05 swizzle XOR is a
+// function of the absolute shared-memory address bits (descriptor base_offset = 0), so row-shifted starts and
+// group strides that are not multiples of the 1024-byte pattern read exactly what TMA wrote
+// (tests/test_gpu_kernels.py::test_halo_conv).  halo_mode 1: box 18 x 16 pixels; halo_mode 2: box 18 x 10.
 // Weights are loaded once per CTA when all 9*Cin/64 tiles fit in shared memory (64->64, 64->128), otherwise they
 // stream through their own ring.
 #include <cstring>
@@ -30,7 +32,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-    uint8_t* smem_b = smem + (size_t)p.stages * kHaloABytes;
+    const int pw = p.halo_mode == 2 ? 10 : 16;                     // box width in pixels = row pitch of the halo tile
+    const int a_stage = p.a_bytes;                                  // 18 * pw * 128, rounded up to 1024
+    uint8_t* smem_b = smem + (size_t)p.stages * a_stage;
     const TcShared sh = tc_shared(smem_b + (size_t)p.b_slots * kBBytes);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -55,9 +59,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                 const int h0 = th * 16, w0 = tw * 8;
                 for (int ck = 0; ck < nck; ++ck) {
                     mbar_wait(&sh.empty[sa], pha ^ 1u);
-                    mbar_expect_tx(&sh.full[sa], (uint32_t)kHaloABytes);
-                    if (ck < p.nchunk0) tma_load_4d(&mapA0, &sh.full[sa], smem + (size_t)sa * kHaloABytes, ck * 64, w0 - 1, h0 - 1, b);
-                    else tma_load_4d(&mapA1, &sh.full[sa], smem + (size_t)sa * kHaloABytes, (ck - p.nchunk0) * 64, w0 - 1, h0 - 1, b);
+                    mbar_expect_tx(&sh.full[sa], (uint32_t)(18 * pw * 128));
+                    if (ck < p.nchunk0) tma_load_4d(&mapA0, &sh.full[sa], smem + (size_t)sa * a_stage, ck * 64, w0 - 1, h0 - 1, b);
+                    else tma_load_4d(&mapA1, &sh.full[sa], smem + (size_t)sa * a_stage, (ck - p.nchunk0) * 64, w0 - 1, h0 - 1, b);
                     if (++sa == p.stages) { sa = 0; pha ^= 1u; }
                     for (int tap = 0; tap < 9; ++tap) {
                         if (p.b_resident) {
@@ -88,7 +92,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
             for (int ck = 0; ck < nck; ++ck) {
                 mbar_wait(&sh.full[sa], pha);
-                const uint32_t a_base = smem_u32(smem + (size_t)sa * kHaloABytes);
+                const uint32_t a_base = smem_u32(smem + (size_t)sa * a_stage);
                 for (int tap = 0; tap < 9; ++tap) {
                     int slot;
                     if (p.b_resident) {
@@ -101,8 +105,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                     tc_fence_after();
                     if (elect_one()) {
                         const int dy = tap / 3, dx = tap - dy * 3;
-                        const uint32_t a_addr = a_base + (uint32_t)((dy * 16 + dx) * 128);
-                        const uint64_t adesc = make_sw128_kmajor_desc(a_addr, 2048u, p.halo_mode == 1 ? (uint32_t)dx : 0u);
+                        const uint32_t a_addr = a_base + (uint32_t)((dy * pw + dx) * 128);
+                        const uint64_t adesc = make_sw128_kmajor_desc(a_addr, (uint32_t)(pw * 128), 0u);
                         const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smem_b + (size_t)slot * kBBytes));
 #pragma unroll
                         for (int k = 0; k < 4; ++k)

@@ -51,8 +51,8 @@ size_t conv_ffma_partials_slots(const ConvGeom& g);
 
 // tcgen05 / TMEM / TMA implicit GEMM, bf16 operands, fp32 accumulate.
 struct TcConvPlan;   // opaque, owns the tensor maps for one (geometry, buffers) binding
-// halo_mode: 0 = one TMA box per tap; 1/2 = one halo box per tile, taps as shifted descriptor views
-// (1: descriptor base_offset = swizzle phase of the start row, 2: base_offset = 0); falls back to 0 when not eligible.
+// halo_mode: 0 = one TMA box per tap; 1/2 = one halo box per tile (18 x 16 / 18 x 10 pixels), the nine taps as
+// shifted shared-memory descriptor views of it; falls back to 0 when the geometry is not eligible.
 TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void* src1, const void* weight,
                                 int weight_rows, const ConvEpilogue& e, int num_sms, int halo_mode);
 bool conv_tc_halo_eligible(const ConvGeom& g);

@@ -63,7 +63,7 @@ void gtts_decoder_destroy(gtts_decoder* d);
  * fp32, contiguous, PyTorch layout; `data` may be a host or a device pointer.  Invalidates packed weights/plans. */
 int gtts_decoder_set_param(gtts_decoder* d, const char* name, const float* data, size_t numel);
 /* options: "max_chunk" (samples per workspace chunk), "use_graph" (0/1), "conv_impl_bf16" (1 tcgen05, 0 FFMA cross-check),
- * "halo_mode" (3x3 convs: 0 per-tap TMA boxes, 1 halo box + shifted descriptor views) */
+ * "halo_mode" (3x3 convs: 0 per-tap TMA boxes, 1 / 2 halo box 18x16 / 18x10 + shifted descriptor views) */
 int gtts_decoder_set_option(gtts_decoder* d, const char* key, int value);
 
 /* z, mu, out: [B][80][T] fp32; mask: [B][1][T] fp32 with entries in {0,1}; spk: [B][64] or NULL;
@@ -87,7 +87,7 @@ long gtts_decoder_launches_last_call(const gtts_decoder* d);
 
 /* ---- Kernel-level test hooks (used by tests/ only) --------------------------------------------------
  * conv: kind 0 = 3x3 s1, 1 = 1x1, 2 = 3x3 s2, 3 = convT 4x4 s2 p1.  impl 0 = FFMA, 1 = tcgen05 per-tap boxes,
- * 2 / 3 = tcgen05 halo box with descriptor base_offset = swizzle phase / 0 (3x3 s1 only; bf16 only).
+ * 2 / 3 = tcgen05 halo box 18x16 / 18x10 pixels with shifted descriptor views (3x3 s1 only; bf16 only).
  * act 0 = fp32, 1 = bf16 activations and packed weights.  weight_pt is the fp32 PyTorch-layout weight.
  * Inputs/outputs are NHWC in the activation type.  gn_stats (B*16 floats, mean/rstd) may be NULL. */
 int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, int Cin1, int Cout,
