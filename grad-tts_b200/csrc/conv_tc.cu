@@ -92,8 +92,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         int stage = 0, it = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1;
-            mbar_wait(&sh.tempty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+            const int buf = it % acc_bufs<N>();
+            mbar_wait(&sh.tempty[buf], ((uint32_t)(it / acc_bufs<N>()) & 1u) ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
             for (int kb = 0; kb < nkb; ++kb) {

@@ -13,7 +13,8 @@ constexpr int kABytes = 128 * 128;                 // 128 pixel rows x 64 bf16
 constexpr int kMiscBytes = 4096;                   // barriers + epilogue scratch
 constexpr int kHaloABytes = 18 * 16 * 128;         // halo box: 18 rows x 16 pixels x 64 bf16
 constexpr int kStatSlots = 4;                      // ring of per-tile GroupNorm partials (epilogue warps -> stats warp)
-constexpr int kThreads = 384;                      // warps 0-3: TMA, MMA, TMEM alloc, stats; warps 4-11: epilogue
+constexpr int kThreads = 640;                      // warps 0-3: TMA, MMA, TMEM alloc, stats; warps 4-19: two epilogue groups
+template <int N> __host__ __device__ constexpr int acc_bufs() { return N <= 128 ? 4 : 2; }   // TMEM accumulator buffers (N cols each)
 
 struct TcParams {
     int bh, bw, tiles_h, tiles_w, nphase, B;
@@ -41,9 +42,9 @@ __device__ __forceinline__ TcShared tc_shared(uint8_t* misc) {
     s.misc = misc;
     s.full = reinterpret_cast<uint64_t*>(misc);        // [8]
     s.empty = s.full + 8;                              // [8]
-    s.tfull = s.empty + 8;                             // [2]
-    s.tempty = s.tfull + 2;                            // [2]
-    s.sfull = s.tempty + 2;                            // [kStatSlots]
+    s.tfull = s.empty + 8;                             // [4]
+    s.tempty = s.tfull + 4;                            // [4]
+    s.sfull = s.tempty + 4;                            // [kStatSlots]
     s.sempty = s.sfull + kStatSlots;                   // [kStatSlots]
     s.fullb = s.sempty + kStatSlots;                   // [16]
     s.emptyb = s.fullb + 16;                           // [16]
@@ -71,6 +72,49 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
     // kind::f16: D=f32 (bit 4), A=bf16 (bit 7), B=bf16 (bit 10), K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
 }
+
+// Packed fp32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100): halves the issue slots of the epilogue arithmetic.
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    float2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<uint64_t*>(&r))
+        : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
+    return r;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    float2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<uint64_t*>(&r))
+        : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
+    return r;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(*reinterpret_cast<uint64_t*>(&r))
+        : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)), "l"(*reinterpret_cast<uint64_t*>(&c)));
+    return r;
+}
+
+// Tile walker: decodes tile = blockIdx.x + it*gridDim.x into (tw, th, ph, b) incrementally (no per-tile divisions).
+struct TileWalk {
+    int tile, tw, th, ph, b;
+    int d_tw, d_th, d_ph, d_b, tiles_w, tiles_h, nphase;
+    __device__ __forceinline__ void init(const TcParams& p, int start, int step) {
+        tiles_w = p.tiles_w; tiles_h = p.tiles_h; nphase = p.nphase;
+        tile = start;
+        tw = start % tiles_w; int r = start / tiles_w;
+        th = r % tiles_h; r /= tiles_h;
+        ph = r % nphase; b = r / nphase;
+        d_tw = step % tiles_w; r = step / tiles_w;
+        d_th = r % tiles_h; r /= tiles_h;
+        d_ph = r % nphase; d_b = r / nphase;
+    }
+    __device__ __forceinline__ void advance(int step) {
+        tile += step;
+        tw += d_tw; if (tw >= tiles_w) { tw -= tiles_w; ++th; }
+        th += d_th; if (th >= tiles_h) { th -= tiles_h; ++ph; }
+        ph += d_ph; if (ph >= nphase) { ph -= nphase; ++b; }
+        b += d_b;
+    }
+};
 
 // Butterfly transpose-reduce of 8 per-thread values across the warp in 9 shuffles (instead of 40):
 // afterwards every lane holds the full 32-lane sum of value index ((lane>>4)&1)*4 + ((lane>>3)&1)*2 + ((lane>>2)&1).
@@ -103,11 +147,11 @@ __device__ __forceinline__ uint32_t tc_prologue(const TcParams& p, const TcShare
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < nfull; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }
         for (int s = 0; s < nfullb; ++s) { mbar_init(&sh.fullb[s], 1); mbar_init(&sh.emptyb[s], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&sh.tfull[i], 1); mbar_init(&sh.tempty[i], 256); }
+        for (int i = 0; i < acc_bufs<N>(); ++i) { mbar_init(&sh.tfull[i], 1); mbar_init(&sh.tempty[i], 256); }
         for (int i = 0; i < kStatSlots; ++i) { mbar_init(&sh.sfull[i], 8); mbar_init(&sh.sempty[i], 1); }
         mbar_fence_init();
     } else if (warp == 2) {
-        tmem_alloc(sh.tmem_slot, 2 * N);
+        tmem_alloc(sh.tmem_slot, acc_bufs<N>() * N);
         tmem_relinquish();
     }
     for (int i = tid; i < N; i += kThreads) sh.s_bias[i] = p.e.bias ? p.e.bias[i] : 0.f;
@@ -145,67 +189,83 @@ __device__ __forceinline__ void tc_stats_loop(const TcParams& p, const TcShared&
     }
 }
 
-// Epilogue warps (warps 4..11): TMEM -> registers -> (+bias, stats, +residual, *mask) -> bf16 NHWC stores.
+// Epilogue warps (warps 4..19): TMEM -> registers -> (+bias, stats, +residual, *mask) -> bf16 NHWC stores.
+// Two groups of 8 warps take alternate tiles (group = tile iteration parity), so one group's TMEM reads, arithmetic
+// and stores overlap the other's; within a group two warps share each TMEM lane quarter and split the columns.
 template <int N, bool kStats, bool kRes, bool kMask>
 __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShared& sh, uint32_t tmem_base, int warp,
                                                  int lane) {
     constexpr int kColsPerWarp = N / 2;            // two epilogue warps share each TMEM lane quarter
     constexpr int kGsz = N / 8;                    // channels per GroupNorm group (4 groups per column half)
-    uint64_t* tfull = sh.tfull;
-    uint64_t* tempty = sh.tempty;
-    uint64_t* sfull = sh.sfull;
-    uint64_t* sempty = sh.sempty;
-    float* s_bias = sh.s_bias;
-    float* s_ring = sh.s_ring;
-    const int tiles_per_phase = p.tiles_h * p.tiles_w;
-    const int ew = warp - 4, wq = ew & 3, half = ew >> 2;
-    const int row = wq * 32 + lane;                              // TMEM lane = pixel row of the tile
+    constexpr int kBufs = acc_bufs<N>();
+    const int ew16 = warp - 4, grp = ew16 >> 3, ew = ew16 & 7, wq = ew & 3, half = ew >> 2;
+    const int row = wq * 32 + lane;                                  // TMEM lane = pixel row of the tile
     const ConvEpilogue& e = p.e;
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.out);
     const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(e.residual);
     const int cbase = half * kColsPerWarp;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h;
-        const int ph = (tile / tiles_per_phase) % p.nphase, b = tile / (tiles_per_phase * p.nphase);
-        const int hl = row / p.bw, wl = row - hl * p.bw;
-        const int j = th * p.bh + hl, i = tw * p.bw + wl;
-        const bool valid = (hl < p.bh) && (j < p.Hg) && (i < p.Wg);
+    const int hl = row / p.bw, wl = row - hl * p.bw;                 // fixed for the whole kernel
+    const bool row_in_tile = hl < p.bh;
+    const float* s_bias = sh.s_bias;
+    TileWalk tw;
+    const int G = (int)gridDim.x;
+    tw.init(p, (int)blockIdx.x + grp * G, 2 * G);
+    for (int it = grp; tw.tile < p.num_tiles; it += 2, tw.advance(2 * G)) {
+        const int buf = it % kBufs;
+        const int b = tw.b, ph = tw.ph;
+        const int j = tw.th * p.bh + hl, i = tw.tw * p.bw + wl;
+        const bool valid = row_in_tile && (j < p.Hg) && (i < p.Wg);
+        const bool all_valid = __all_sync(0xffffffffu, valid);
         const int oh = j * p.out_step + p.oy[ph], ow = i * p.out_step + p.ox[ph];
         const size_t opix = valid ? ((size_t)b * p.Hout + oh) * p.Wout + ow : 0;
         float m = 1.0f;
         if (kMask) m = valid ? e.mask[(size_t)b * p.Wout + ow] : 0.f;
+        const float2 m2 = make_float2(m, m);
 
-        mbar_wait(&tfull[buf], (uint32_t)(it >> 1) & 1u);
+        mbar_wait(&sh.tfull[buf], (uint32_t)(it / kBufs) & 1u);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * N + cbase);
 
-        float st[8];                                             // [0..3] sums, [4..7] sums of squares
+        float2 ssum[4], ssq[4];                                      // per local group: packed (even, odd) columns
 #pragma unroll
-        for (int g = 0; g < 8; ++g) st[g] = 0.f;
+        for (int g = 0; g < 4; ++g) { ssum[g] = make_float2(0.f, 0.f); ssq[g] = make_float2(0.f, 0.f); }
 
 #pragma unroll
         for (int c0 = 0; c0 < kColsPerWarp; c0 += 32) {
             uint32_t r[32];
             tmem_ld32(taddr + (uint32_t)c0, r);
             tmem_ld_wait();
-            float f[32];
+            if (c0 + 32 >= kColsPerWarp) {
+                // last TMEM read of this buffer: hand it back to the MMA warp before the arithmetic and stores
+                tc_fence_before();
+                mbar_arrive(&sh.tempty[buf]);
+            }
+            float2 f[16];
 #pragma unroll
             for (int q4 = 0; q4 < 8; ++q4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[cbase + c0 + q4 * 4]);
-                f[q4 * 4 + 0] = __uint_as_float(r[q4 * 4 + 0]) + b4.x;
-                f[q4 * 4 + 1] = __uint_as_float(r[q4 * 4 + 1]) + b4.y;
-                f[q4 * 4 + 2] = __uint_as_float(r[q4 * 4 + 2]) + b4.z;
-                f[q4 * 4 + 3] = __uint_as_float(r[q4 * 4 + 3]) + b4.w;
+                f[q4 * 2 + 0] = fadd2(make_float2(__uint_as_float(r[q4 * 4 + 0]), __uint_as_float(r[q4 * 4 + 1])),
+                                      make_float2(b4.x, b4.y));
+                f[q4 * 2 + 1] = fadd2(make_float2(__uint_as_float(r[q4 * 4 + 2]), __uint_as_float(r[q4 * 4 + 3])),
+                                      make_float2(b4.z, b4.w));
             }
             if (kStats) {
+                if (all_valid) {
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const int g = (c0 + q) / kGsz;               // local group 0..3 (compile time)
-                    const float x = valid ? f[q] : 0.f;
-                    st[g] += x;
-                    st[4 + g] = fmaf(x, x, st[4 + g]);
+                    for (int q = 0; q < 16; ++q) {
+                        const int g = (c0 + 2 * q) / kGsz;           // local group 0..3 (compile time; kGsz is even)
+                        ssum[g] = fadd2(ssum[g], f[q]);
+                        ssq[g] = ffma2(f[q], f[q], ssq[g]);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const int g = (c0 + 2 * q) / kGsz;
+                        // select, not multiply: rows outside the tile hold whatever was in shared memory (maybe NaN)
+                        const float2 x = valid ? f[q] : make_float2(0.f, 0.f);
+                        ssum[g] = fadd2(ssum[g], x);
+                        ssq[g] = ffma2(x, x, ssq[g]);
+                    }
                 }
             }
             if (valid) {
@@ -216,15 +276,14 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
                         const uint4 u = __ldg(rp + v4);
                         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            f[v4 * 8 + 2 * k] += __uint_as_float(w[k] << 16);
-                            f[v4 * 8 + 2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
-                        }
+                        for (int k = 0; k < 4; ++k)
+                            f[v4 * 4 + k] = fadd2(f[v4 * 4 + k], make_float2(__uint_as_float(w[k] << 16),
+                                                                             __uint_as_float(w[k] & 0xffff0000u)));
                     }
                 }
                 if (kMask) {
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) f[q] *= m;
+                    for (int q = 0; q < 16; ++q) f[q] = fmul2(f[q], m2);
                 }
                 uint4* op = reinterpret_cast<uint4*>(out + opix * N + cbase + c0);
 #pragma unroll
@@ -232,24 +291,24 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
                     uint32_t w[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[v4 * 8 + 2 * k], f[v4 * 8 + 2 * k + 1]);
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[v4 * 4 + k].x, f[v4 * 4 + k].y);
                         w[k] = *reinterpret_cast<uint32_t*>(&h2);
                     }
                     op[v4] = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
         }
-        // all TMEM reads of this buffer are complete: hand it back to the MMA warp
-        tc_fence_before();
-        mbar_arrive(&tempty[buf]);
 
         if (kStats) {
+            float st[8];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) { st[g] = ssum[g].x + ssum[g].y; st[4 + g] = ssq[g].x + ssq[g].y; }
             const float t = warp_reduce8(st, lane);
             const int slot = it % kStatSlots;
-            mbar_wait(&sempty[slot], ((uint32_t)(it / kStatSlots) & 1u) ^ 1u);
-            if ((lane & 3) == 0) s_ring[(slot * 8 + ew) * 8 + (lane >> 2)] = t;
+            mbar_wait(&sh.sempty[slot], ((uint32_t)(it / kStatSlots) & 1u) ^ 1u);
+            if ((lane & 3) == 0) sh.s_ring[(slot * 8 + ew) * 8 + (lane >> 2)] = t;
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sfull[slot]);            // release: orders the ring writes of this warp
+            if (lane == 0) mbar_arrive(&sh.sfull[slot]);             // release: orders the ring writes of this warp
         }
     }
 }
@@ -266,7 +325,7 @@ __device__ __forceinline__ void tc_teardown(const TcParams& p, const TcShared& s
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * N);
+        tmem_dealloc(tmem_base, acc_bufs<N>() * N);
     }
     if (kStats) {
         const ConvEpilogue& e = p.e;

@@ -86,8 +86,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         int sa = 0, sb = 0, it = 0;
         uint32_t pha = 0, phb = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1;
-            mbar_wait(&sh.tempty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+            const int buf = it % acc_bufs<N>();
+            mbar_wait(&sh.tempty[buf], ((uint32_t)(it / acc_bufs<N>()) & 1u) ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
             for (int ck = 0; ck < nck; ++ck) {
