@@ -29,7 +29,7 @@ struct TcParams {
 };
 
 // misc shared-memory block layout (relative to `misc`)
-//   [0,   512)  mbarriers        [512, 1536) bias[256]      [1536, 2560) stats ring      [2560, 4096) finalize list
+//   [0,   640)  mbarriers + TMEM slot   [640, 1664) bias[256]   [1664, 2688) stats ring   [2688, 4096) finalize list
 struct TcShared {
     uint64_t *full, *empty, *tfull, *tempty, *sfull, *sempty, *fullb, *emptyb;
     uint32_t* tmem_slot;
@@ -49,8 +49,8 @@ __device__ __forceinline__ TcShared tc_shared(uint8_t* misc) {
     s.fullb = s.sempty + kStatSlots;                   // [16]
     s.emptyb = s.fullb + 16;                           // [16]
     s.tmem_slot = reinterpret_cast<uint32_t*>(s.emptyb + 16);
-    s.s_bias = reinterpret_cast<float*>(misc + 512);
-    s.s_ring = reinterpret_cast<float*>(misc + 1536);
+    s.s_bias = reinterpret_cast<float*>(misc + 640);
+    s.s_ring = reinterpret_cast<float*>(misc + 1664);
     return s;
 }
 
@@ -329,7 +329,7 @@ __device__ __forceinline__ void tc_teardown(const TcParams& p, const TcShared& s
     }
     if (kStats) {
         const ConvEpilogue& e = p.e;
-        int* s_nfin = reinterpret_cast<int*>(misc + 2560);
+        int* s_nfin = reinterpret_cast<int*>(misc + 2688);
         int* s_fin = s_nfin + 1;
         double* s_red = reinterpret_cast<double*>(smem);             // pipeline buffers are idle now: [24][16]
         if (tid == 0) *s_nfin = 0;
