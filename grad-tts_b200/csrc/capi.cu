@@ -1,4 +1,5 @@
 // extern "C" surface declared in include/gradtts_b200.h.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -263,6 +264,20 @@ int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, i
         else {
             rc = conv_tc_launch(tp, s);
             cudaStreamSynchronize(s);
+            if (const char* reps_env = getenv("GTTS_CONV_REPS")) {
+                const int reps = atoi(reps_env);
+                cudaEvent_t e0, e1;
+                cudaEventCreate(&e0); cudaEventCreate(&e1);
+                cudaEventRecord(e0, s);
+                for (int i = 0; i < reps && rc == 0; ++i) rc = conv_tc_launch(tp, s);
+                cudaEventRecord(e1, s);
+                cudaEventSynchronize(e1);
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, e0, e1);
+                fprintf(stderr, "[gtts_test_conv] impl=%d kind=%d B=%d H=%d W=%d Cin=%d Cout=%d: %.1f us/launch\n", impl, kind, B, H, W,
+                        Cin, Cout, 1e3f * ms / (reps > 0 ? reps : 1));
+                cudaEventDestroy(e0); cudaEventDestroy(e1);
+            }
             conv_tc_plan_destroy(tp);
         }
     } else {

@@ -218,6 +218,11 @@ __device__ __forceinline__ void tma_load_4d(const void* desc, uint64_t* bar, voi
         "r"(c2), "r"(c3)
         : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_4d(const void* desc, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
+                 ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_load_5d(const void* desc, uint64_t* bar, void* smem, int c0, int c1, int c2,
                                             int c3, int c4) {
     asm volatile(

@@ -18,6 +18,7 @@
 // * Persistent CTAs (one per SM) walk the tile list round-robin.
 //
 // Reference ops covered: Conv2d 3x3 (diffusion.py:52), 1x1 (:70,87,88), 3x3 s2 (:33), ConvTranspose2d 4x4 s2 (:24).
+#include <cstdlib>
 #include <cstring>
 
 #include "conv_tc_common.cuh"
@@ -89,6 +90,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
     } else if (warp == 1) {
         // ================================================================ MMA issuer
+        // One elected lane issues everything; the other lanes only shadow the barrier waits.
+        const bool leader = elect_one();
+        const int nstage = p.stages;
+        const uint64_t a_desc0 = make_sw128_kmajor_desc(smem_u32(smem));
+        const uint64_t b_desc0 = make_sw128_kmajor_desc(smem_u32(smem) + kABytes);
+        const uint64_t stage_step = (uint64_t)(kStage >> 4);
         int stage = 0, it = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -99,10 +106,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t a_addr = smem_u32(smem + (size_t)stage * kStage);
-                    const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
-                    const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + kABytes);
+                if (leader) {
+                    const uint64_t adesc = a_desc0 + (uint64_t)stage * stage_step;
+                    const uint64_t bdesc = b_desc0 + (uint64_t)stage * stage_step;
 #pragma unroll
                     for (int k = 0; k < 4; ++k)                     // 4 x (K = 16 bf16 = 32 bytes)
                         tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
@@ -110,10 +116,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     tc_commit(&empty[stage]);                       // smem slot free when these MMAs retire
                     if (kb == nkb - 1) tc_commit(&sh.tfull[buf]);   // accumulator complete
                 }
-                __syncwarp();
-                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                if (++stage == nstage) { stage = 0; phase ^= 1u; }
             }
         }
+        __syncwarp();
     } else if (warp == 3) {
         tc_stats_loop<kStats>(p, sh, lane);
     } else if (warp >= 4) {
@@ -178,6 +184,7 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
     memcpy(p.dy, g.dy, sizeof(p.dy)); memcpy(p.dx, g.dx, sizeof(p.dx));
     memcpy(p.wrow, g.wrow, sizeof(p.wrow)); memcpy(p.oy, g.oy, sizeof(p.oy)); memcpy(p.ox, g.ox, sizeof(p.ox));
     p.e = e;
+    { const char* dbg = getenv("GTTS_CONV_DBG"); p.dbg = dbg ? atoi(dbg) : 0; }
     pl->N = g.Cout;
     const int budget = 227 * 1024 - kMiscBytes - 1024;
     if (halo_mode) {
@@ -186,7 +193,11 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
         const int pw = halo_mode == 2 ? 10 : 16;
         const int abytes = (18 * pw * 128 + 1023) / 1024 * 1024;     // stage stride keeps every stage 1024-aligned
         p.a_bytes = abytes;
-        if (ntiles_b <= 16 && ntiles_b * btile + 4 * abytes <= budget) { p.stages = 4; p.b_resident = 1; p.b_slots = ntiles_b; }
+        { const char* pf = getenv("GTTS_HALO_PREFETCH"); p.halo_prefetch = pf ? atoi(pf) : 6; }
+        int max_st = 6;
+        if (const char* ms = getenv("GTTS_HALO_STAGES")) max_st = atoi(ms);
+        if (ntiles_b <= 16 && max_st >= 6 && ntiles_b * btile + 6 * abytes <= budget) { p.stages = 6; p.b_resident = 1; p.b_slots = ntiles_b; }
+        else if (ntiles_b <= 16 && ntiles_b * btile + 4 * abytes <= budget) { p.stages = 4; p.b_resident = 1; p.b_slots = ntiles_b; }
         else if (ntiles_b <= 16 && ntiles_b * btile + 3 * abytes <= budget) { p.stages = 3; p.b_resident = 1; p.b_slots = ntiles_b; }
         else if (ntiles_b <= 16 && ntiles_b * btile + 2 * abytes <= budget) { p.stages = 2; p.b_resident = 1; p.b_slots = ntiles_b; }
         else {

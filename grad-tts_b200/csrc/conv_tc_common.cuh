@@ -21,7 +21,8 @@ struct TcParams {
     int Hg, Wg, Hout, Wout, out_step;
     int ntaps, nchunk0, nchunk1, Cin0;
     int stride2, w_batch_rows, num_tiles, a_bytes, stages;
-    int halo_mode, b_slots, b_resident;            // conv_tc_halo.cu only
+    int halo_mode, b_slots, b_resident, halo_prefetch;   // conv_tc_halo.cu only
+    int dbg;                                       // experiment switches (GTTS_CONV_DBG): 1 no MMA issue, 2 no epilogue work
     int8_t dy[4][9], dx[4][9];
     int wrow[4][9];
     int oy[4], ox[4];
@@ -224,6 +225,7 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
 
         mbar_wait(&sh.tfull[buf], (uint32_t)(it / kBufs) & 1u);
         tc_fence_after();
+        if (p.dbg & 2) { tc_fence_before(); mbar_arrive(&sh.tempty[buf]); if (kStats) { const int slot = it % kStatSlots; mbar_wait(&sh.sempty[slot], ((uint32_t)(it / kStatSlots) & 1u) ^ 1u); __syncwarp(); if (lane == 0) mbar_arrive(&sh.sfull[slot]); } continue; }
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * N + cbase);
 
         float2 ssum[4], ssq[4];                                      // per local group: packed (even, odd) columns

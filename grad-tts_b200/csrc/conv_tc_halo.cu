@@ -54,9 +54,20 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             int sa = 0, sb = 0;
             uint32_t pha = 0, phb = 0;
             bool first = true;
+            const int pf_dist = p.halo_prefetch;                     // tiles of look-ahead for the L2 prefetch
+            auto prefetch_tile = [&](int t) {
+                if (t >= p.num_tiles) return;
+                const int ptw = t % p.tiles_w, pth = (t / p.tiles_w) % p.tiles_h, pb = t / tiles_per_phase;
+                for (int ck = 0; ck < nck; ++ck) {
+                    if (ck < p.nchunk0) tma_prefetch_4d(&mapA0, ck * 64, ptw * 8 - 1, pth * 16 - 1, pb);
+                    else tma_prefetch_4d(&mapA1, (ck - p.nchunk0) * 64, ptw * 8 - 1, pth * 16 - 1, pb);
+                }
+            };
+            for (int i = 1; i <= pf_dist; ++i) prefetch_tile((int)blockIdx.x + i * (int)gridDim.x);
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, b = tile / tiles_per_phase;
                 const int h0 = th * 16, w0 = tw * 8;
+                if (pf_dist > 0) prefetch_tile(tile + (pf_dist + 1) * (int)gridDim.x);
                 for (int ck = 0; ck < nck; ++ck) {
                     mbar_wait(&sh.empty[sa], pha ^ 1u);
                     mbar_expect_tx(&sh.full[sa], (uint32_t)(18 * pw * 128));
@@ -83,6 +94,16 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         }
     } else if (warp == 1) {
         // ================================================================ MMA issuer
+        // One elected lane issues everything; the other lanes only shadow the barrier waits.  All descriptors are
+        // precomputed: per MMA the issue path is a couple of 64-bit adds.
+        const bool leader = elect_one();
+        const int nstage = p.stages, nslot = p.b_slots, resident = p.b_resident, dbg = p.dbg;
+        const uint64_t a_desc0 = make_sw128_kmajor_desc(smem_u32(smem), (uint32_t)(pw * 128), 0u);
+        const uint64_t b_desc0 = make_sw128_kmajor_desc(smem_u32(smem_b));
+        const uint64_t a_stage_step = (uint64_t)(a_stage >> 4), b_slot_step = (uint64_t)(kBBytes >> 4);
+        uint64_t tap_off[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) tap_off[t] = (uint64_t)((((t / 3) * pw + (t % 3)) * 128) >> 4);
         int sa = 0, sb = 0, it = 0;
         uint32_t pha = 0, phb = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -92,38 +113,53 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
             for (int ck = 0; ck < nck; ++ck) {
                 mbar_wait(&sh.full[sa], pha);
-                const uint32_t a_base = smem_u32(smem + (size_t)sa * a_stage);
-                for (int tap = 0; tap < 9; ++tap) {
-                    int slot;
-                    if (p.b_resident) {
-                        slot = ck * 9 + tap;
-                        if (it == 0) mbar_wait(&sh.fullb[slot], 0u);
-                    } else {
-                        slot = sb;
-                        mbar_wait(&sh.fullb[sb], phb);
+                const uint64_t adesc = a_desc0 + (uint64_t)sa * a_stage_step;
+                if (resident) {
+                    if (it == 0) {
+#pragma unroll 1
+                        for (int tap = 0; tap < 9; ++tap) mbar_wait(&sh.fullb[ck * 9 + tap], 0u);
                     }
                     tc_fence_after();
-                    if (elect_one()) {
-                        const int dy = tap / 3, dx = tap - dy * 3;
-                        const uint32_t a_addr = a_base + (uint32_t)((dy * pw + dx) * 128);
-                        const uint64_t adesc = make_sw128_kmajor_desc(a_addr, (uint32_t)(pw * 128), 0u);
-                        const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(smem_b + (size_t)slot * kBBytes));
+                    if (leader) {
+                        const uint64_t bdesc = b_desc0 + (uint64_t)(ck * 9) * b_slot_step;
+                        if (!(dbg & 1)) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
-                                       (uint32_t)((ck | tap | k) != 0));
-                        if (!p.b_resident) tc_commit(&sh.emptyb[sb]);
-                        if (tap == 8) {
-                            tc_commit(&sh.empty[sa]);
-                            if (ck == nck - 1) tc_commit(&sh.tfull[buf]);
+                            for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    tc_mma_f16(d_tmem, adesc + tap_off[tap] + (uint64_t)(2 * k),
+                                               bdesc + (uint64_t)tap * b_slot_step + (uint64_t)(2 * k), kIdesc,
+                                               (uint32_t)((ck | tap | k) != 0));
                         }
+                        tc_commit(&sh.empty[sa]);
+                        if (ck == nck - 1) tc_commit(&sh.tfull[buf]);
                     }
-                    __syncwarp();
-                    if (!p.b_resident) { if (++sb == p.b_slots) { sb = 0; phb ^= 1u; } }
+                } else {
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&sh.fullb[sb], phb);
+                        tc_fence_after();
+                        if (leader) {
+                            const uint64_t bdesc = b_desc0 + (uint64_t)sb * b_slot_step;
+                            if (!(dbg & 1)) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    tc_mma_f16(d_tmem, adesc + tap_off[tap] + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
+                                               kIdesc, (uint32_t)((ck | tap | k) != 0));
+                            }
+                            tc_commit(&sh.emptyb[sb]);
+                            if (tap == 8) {
+                                tc_commit(&sh.empty[sa]);
+                                if (ck == nck - 1) tc_commit(&sh.tfull[buf]);
+                            }
+                        }
+                        if (++sb == nslot) { sb = 0; phb ^= 1u; }
+                    }
                 }
-                if (++sa == p.stages) { sa = 0; pha ^= 1u; }
+                if (++sa == nstage) { sa = 0; pha ^= 1u; }
             }
         }
+        __syncwarp();
     } else if (warp == 3) {
         tc_stats_loop<kStats>(p, sh, lane);
     } else if (warp >= 4) {

@@ -152,6 +152,25 @@ def stage_halo():
                 traceback.print_exc()
 
 
+def stage_convdbg():
+    """Times one large conv through the test hook (GTTS_CONV_REPS) under the experiment switches GTTS_CONV_DBG."""
+    import gpu_util as gu
+    cin, cout, H, W, B = [int(v) for v in os.environ.get("GTTS_SHAPE", "64,64,80,1720,8").split(",")]
+    c = gu.conv_case(0, B, H, W, cin, 0, cout, seed=1)
+    os.environ["GTTS_CONV_REPS"] = "5"
+    for impl in (1, 3):
+        for dbg in (0, 1, 2, 3):
+            if impl == 1 and dbg:
+                continue
+            os.environ["GTTS_CONV_DBG"] = str(dbg)
+            for pf, st in ((0, 4), (0, 6), (4, 6), (8, 6), (16, 6)) if impl == 3 else ((0, 4),):
+                os.environ["GTTS_HALO_PREFETCH"] = str(pf)
+                os.environ["GTTS_HALO_STAGES"] = str(st)
+                print(f"impl={impl} dbg={dbg} prefetch={pf} stages={st}", flush=True)
+                gu.run_conv(c, impl, 1, want_stats=True)
+    os.environ["GTTS_CONV_DBG"] = "0"
+
+
 def stage_profile():
     import ctypes, json
     for (n_spks, B, T) in [(1, 16, 1720), (1, 1, 400)]:
@@ -181,6 +200,6 @@ if __name__ == "__main__":
     print(f"===== stage {st} on {torch.cuda.get_device_name(0)}", flush=True)
     {"mas": stage_mas, "conv_ffma": lambda: (stage_conv(0, 0), stage_conv(0, 1)), "conv_tc": lambda: stage_conv(1, 1),
      "dec_fp32": lambda: stage_dec("fp32"), "dec_bf16_ffma": lambda: stage_dec("bf16", 0),
-     "dec_bf16_tc": lambda: stage_dec("bf16", 1), "perf": stage_perf, "profile": stage_profile, "halo": stage_halo}[st]()
+     "dec_bf16_tc": lambda: stage_dec("bf16", 1), "perf": stage_perf, "profile": stage_profile, "halo": stage_halo, "convdbg": stage_convdbg}[st]()
     torch.cuda.synchronize()
     print(f"===== stage {st} done", flush=True)
