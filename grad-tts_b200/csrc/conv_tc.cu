@@ -147,18 +147,14 @@ void pick_tile(int Hg, int Wg, int* bh_out, int* bw_out) {
 
 }  // namespace
 
-size_t conv_tc_partials_slots(const ConvGeom& g) {
-    int bh, bw;
-    pick_tile(g.Hg, g.Wg, &bh, &bw);
-    return (size_t)((g.Hg + bh - 1) / bh) * ((g.Wg + bw - 1) / bw);
-}
+size_t conv_tc_partials_slots(const ConvGeom&) { return 256; }         // one partial per (sample, CTA); grid <= #SMs
 
 bool conv_tc_halo_eligible(const ConvGeom& g) {
     return g.ntaps == 9 && g.stride == 1 && g.nphase == 1 && g.w_batch_rows == 0 && (g.Cout == 64 || g.Cout == 128) &&
            g.Hg >= 16 && g.Wg >= 8;
 }
 
-size_t conv_tc_halo_partials_slots(const ConvGeom& g) { return (size_t)((g.Hg + 15) / 16) * ((g.Wg + 7) / 8); }
+size_t conv_tc_halo_partials_slots(const ConvGeom&) { return 256; }    // one partial per (sample, CTA); grid <= #SMs
 
 TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void* src1, const void* weight,
                                 int weight_rows, const ConvEpilogue& e, int num_sms, int halo_mode) {
@@ -214,6 +210,7 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
         pl->smem = (size_t)stages * stage_bytes + kMiscBytes + 1024;
     }
     pl->grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    if (pl->grid > 256) pl->grid = 256;                    // GN partial buffers hold 256 CTA slots per sample
 
     bool ok = true;
     const uint64_t H = g.Hin, W = g.Win;

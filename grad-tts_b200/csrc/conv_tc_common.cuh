@@ -22,7 +22,7 @@ struct TcParams {
     int ntaps, nchunk0, nchunk1, Cin0;
     int stride2, w_batch_rows, num_tiles, a_bytes, stages;
     int halo_mode, b_slots, b_resident, halo_prefetch;   // conv_tc_halo.cu only
-    int dbg;                                       // experiment switches (GTTS_CONV_DBG): 1 no MMA issue, 2 no epilogue work
+    int dbg;                                       // experiment switches (GTTS_CONV_DBG): 1 no MMA issue, 2 no epilogue work, 4 no A loads (halo), 8 no stats ring
     int8_t dy[4][9], dx[4][9];
     int wrow[4][9];
     int oy[4], ox[4];
@@ -162,31 +162,39 @@ __device__ __forceinline__ uint32_t tc_prologue(const TcParams& p, const TcShare
     return *sh.tmem_slot;
 }
 
-// GroupNorm statistics warp (warp 3): sums the 8 epilogue warps' per-tile values and writes the tile's 16 partials.
+// GroupNorm statistics warp (warp 3): sums the 8 epilogue warps' per-tile values, accumulates them per sample in
+// registers (a CTA's tiles of one sample are consecutive in its walk) and writes ONE 16-float partial per
+// (sample, CTA): partials[(b * gridDim.x + blockIdx.x) * 16 + k].  Fixed tile->CTA assignment and order: deterministic.
 template <bool kStats>
 __device__ __forceinline__ void tc_stats_loop(const TcParams& p, const TcShared& sh, int lane) {
     uint64_t* sfull = sh.sfull;
     uint64_t* sempty = sh.sempty;
     float* s_ring = sh.s_ring;
     const int tiles_per_phase = p.tiles_h * p.tiles_w;
-    if (kStats) {
+    if (kStats && !(p.dbg & 8)) {
         const ConvEpilogue& e = p.e;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int G = (int)gridDim.x;
+        int it = 0, cur_b = -1;
+        float acc = 0.f;
+        // value k (0..7 sums, 8..15 sums of squares) of group g = k & 7 lives in column half g >> 2
+        const int g = lane & 7, which = (lane >> 3) & 1, half = g >> 2, idx = which * 4 + (g & 3);
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += G, ++it) {
             const int slot = it % kStatSlots;
-            const int b = tile / tiles_per_phase, slot_in_sample = tile - b * tiles_per_phase;
+            const int b = tile / tiles_per_phase;
+            if (b != cur_b) {
+                if (cur_b >= 0 && lane < 16) e.gn_partials[((size_t)cur_b * G + blockIdx.x) * 16 + lane] = acc;
+                cur_b = b;
+                acc = 0.f;
+            }
             mbar_wait(&sfull[slot], (uint32_t)(it / kStatSlots) & 1u);
-            // value k (0..7 sums, 8..15 sums of squares) of group g = k & 7 lives in column half g >> 2
-            float v = 0.f;
             if (lane < 16) {
-                const int g = lane & 7, which = lane >> 3, half = g >> 2, idx = which * 4 + (g & 3);
                 const float* r = s_ring + (slot * 8 + half * 4) * 8 + idx;
-                v = (r[0] + r[8]) + (r[16] + r[24]);
-                e.gn_partials[((size_t)b * tiles_per_phase + slot_in_sample) * 16 + lane] = v;
+                acc += (r[0] + r[8]) + (r[16] + r[24]);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sempty[slot]);
         }
+        if (cur_b >= 0 && lane < 16) e.gn_partials[((size_t)cur_b * G + blockIdx.x) * 16 + lane] = acc;
     }
 }
 
@@ -225,7 +233,7 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
 
         mbar_wait(&sh.tfull[buf], (uint32_t)(it / kBufs) & 1u);
         tc_fence_after();
-        if (p.dbg & 2) { tc_fence_before(); mbar_arrive(&sh.tempty[buf]); if (kStats) { const int slot = it % kStatSlots; mbar_wait(&sh.sempty[slot], ((uint32_t)(it / kStatSlots) & 1u) ^ 1u); __syncwarp(); if (lane == 0) mbar_arrive(&sh.sfull[slot]); } continue; }
+        if (p.dbg & 2) { tc_fence_before(); mbar_arrive(&sh.tempty[buf]); if (kStats && !(p.dbg & 8)) { const int slot = it % kStatSlots; mbar_wait(&sh.sempty[slot], ((uint32_t)(it / kStatSlots) & 1u) ^ 1u); __syncwarp(); if (lane == 0) mbar_arrive(&sh.sfull[slot]); } continue; }
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * N + cbase);
 
         float2 ssum[4], ssq[4];                                      // per local group: packed (even, odd) columns
@@ -301,7 +309,7 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
             }
         }
 
-        if (kStats) {
+        if (kStats && !(p.dbg & 8)) {
             float st[8];
 #pragma unroll
             for (int g = 0; g < 4; ++g) { st[g] = ssum[g].x + ssum[g].y; st[4 + g] = ssq[g].x + ssq[g].y; }
@@ -356,10 +364,17 @@ __device__ __forceinline__ void tc_teardown(const TcParams& p, const TcShared& s
             const double inv_count = 1.0 / ((double)kGsz * (double)p.Hout * (double)p.Wout);
             for (int f = 0; f < nfin; ++f) {
                 const int b = s_fin[f];
-                const int k = tid & 15, slice = tid >> 4;            // 24 slices of 16 components
-                const float* pp = e.gn_partials + (size_t)b * tiles_per_phase * 16 + k;
+                const int G = (int)gridDim.x, tps = tiles_per_phase;
+                const int lo = b * tps, hi = lo + tps - 1;
+                const int k = tid & 15, slice = tid >> 4;            // kThreads/16 slices of 16 components
+                const float* pp = e.gn_partials + (size_t)b * G * 16 + k;
                 double acc = 0.0;
-                for (int sl = slice; sl < tiles_per_phase; sl += kThreads / 16) acc += (double)__ldcg(pp + (size_t)sl * 16);
+                for (int c = slice; c < G; c += kThreads / 16) {
+                    // CTA c contributed to sample b iff it owns a tile in [lo, hi]
+                    const int i_min = lo > c ? (lo - c + G - 1) / G : 0;
+                    const int i_max = hi >= c ? (hi - c) / G : -1;
+                    if (i_max >= i_min) acc += (double)__ldcg(pp + (size_t)c * 16);
+                }
                 s_red[slice * 16 + k] = acc;
                 __syncthreads();
                 if (tid < 8) {

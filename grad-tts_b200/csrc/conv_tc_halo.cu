@@ -54,38 +54,55 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             int sa = 0, sb = 0;
             uint32_t pha = 0, phb = 0;
             bool first = true;
-            const int pf_dist = p.halo_prefetch;                     // tiles of look-ahead for the L2 prefetch
-            auto prefetch_tile = [&](int t) {
-                if (t >= p.num_tiles) return;
-                const int ptw = t % p.tiles_w, pth = (t / p.tiles_w) % p.tiles_h, pb = t / tiles_per_phase;
-                for (int ck = 0; ck < nck; ++ck) {
-                    if (ck < p.nchunk0) tma_prefetch_4d(&mapA0, ck * 64, ptw * 8 - 1, pth * 16 - 1, pb);
-                    else tma_prefetch_4d(&mapA1, (ck - p.nchunk0) * 64, ptw * 8 - 1, pth * 16 - 1, pb);
+            const int G = (int)gridDim.x, nstage = p.stages, nslot = p.b_slots, resident = p.b_resident, dbg = p.dbg;
+            const int nck0 = p.nchunk0;
+            const uint32_t a_tx = (uint32_t)(18 * pw * 128);
+            TileWalk tw, pf;
+            tw.init(p, (int)blockIdx.x, G);
+            const int pf_dist = p.halo_prefetch;                     // tiles of look-ahead for the L2 prefetch (0 = off)
+            if (pf_dist > 0) {
+                pf.init(p, (int)blockIdx.x, G);
+                for (int i = 0; i < pf_dist && pf.tile < p.num_tiles; ++i) {
+                    pf.advance(G);
+                    if (pf.tile < p.num_tiles)
+                        for (int ck = 0; ck < nck; ++ck)
+                            tma_prefetch_4d(ck < nck0 ? &mapA0 : &mapA1, (ck < nck0 ? ck : ck - nck0) * 64, pf.tw * 8 - 1,
+                                            pf.th * 16 - 1, pf.b);
                 }
-            };
-            for (int i = 1; i <= pf_dist; ++i) prefetch_tile((int)blockIdx.x + i * (int)gridDim.x);
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, b = tile / tiles_per_phase;
-                const int h0 = th * 16, w0 = tw * 8;
-                if (pf_dist > 0) prefetch_tile(tile + (pf_dist + 1) * (int)gridDim.x);
+            }
+            for (; tw.tile < p.num_tiles; tw.advance(G)) {
+                const int b = tw.b, h0 = tw.th * 16, w0 = tw.tw * 8;
+                if (pf_dist > 0 && pf.tile < p.num_tiles) {
+                    pf.advance(G);
+                    if (pf.tile < p.num_tiles)
+                        for (int ck = 0; ck < nck; ++ck)
+                            tma_prefetch_4d(ck < nck0 ? &mapA0 : &mapA1, (ck < nck0 ? ck : ck - nck0) * 64, pf.tw * 8 - 1,
+                                            pf.th * 16 - 1, pf.b);
+                }
                 for (int ck = 0; ck < nck; ++ck) {
                     mbar_wait(&sh.empty[sa], pha ^ 1u);
-                    mbar_expect_tx(&sh.full[sa], (uint32_t)(18 * pw * 128));
-                    if (ck < p.nchunk0) tma_load_4d(&mapA0, &sh.full[sa], smem + (size_t)sa * a_stage, ck * 64, w0 - 1, h0 - 1, b);
-                    else tma_load_4d(&mapA1, &sh.full[sa], smem + (size_t)sa * a_stage, (ck - p.nchunk0) * 64, w0 - 1, h0 - 1, b);
-                    if (++sa == p.stages) { sa = 0; pha ^= 1u; }
-                    for (int tap = 0; tap < 9; ++tap) {
-                        if (p.b_resident) {
-                            if (first) {
+                    if (dbg & 4) {
+                        mbar_arrive(&sh.full[sa]);                   // experiment: no A traffic at all
+                    } else {
+                        mbar_expect_tx(&sh.full[sa], a_tx);
+                        tma_load_4d(ck < nck0 ? &mapA0 : &mapA1, &sh.full[sa], smem + (size_t)sa * a_stage,
+                                    (ck < nck0 ? ck : ck - nck0) * 64, w0 - 1, h0 - 1, b);
+                    }
+                    if (++sa == nstage) { sa = 0; pha ^= 1u; }
+                    if (resident) {
+                        if (first) {
+                            for (int tap = 0; tap < 9; ++tap) {
                                 const int slot = ck * 9 + tap;
                                 mbar_expect_tx(&sh.fullb[slot], (uint32_t)kBBytes);
                                 tma_load_2d(&mapW, &sh.fullb[slot], smem_b + (size_t)slot * kBBytes, ck * 64, p.wrow[0][tap]);
                             }
-                        } else {
+                        }
+                    } else {
+                        for (int tap = 0; tap < 9; ++tap) {
                             mbar_wait(&sh.emptyb[sb], phb ^ 1u);
                             mbar_expect_tx(&sh.fullb[sb], (uint32_t)kBBytes);
                             tma_load_2d(&mapW, &sh.fullb[sb], smem_b + (size_t)sb * kBBytes, ck * 64, p.wrow[0][tap]);
-                            if (++sb == p.b_slots) { sb = 0; phb ^= 1u; }
+                            if (++sb == nslot) { sb = 0; phb ^= 1u; }
                         }
                     }
                 }
