@@ -189,7 +189,7 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
         const int pw = halo_mode == 2 ? 10 : 16;
         const int abytes = (18 * pw * 128 + 1023) / 1024 * 1024;     // stage stride keeps every stage 1024-aligned
         p.a_bytes = abytes;
-        { const char* pf = getenv("GTTS_HALO_PREFETCH"); p.halo_prefetch = pf ? atoi(pf) : 6; }
+        { const char* pf = getenv("GTTS_HALO_PREFETCH"); p.halo_prefetch = pf ? atoi(pf) : 0; }
         int max_st = 6;
         if (const char* ms = getenv("GTTS_HALO_STAGES")) max_st = atoi(ms);
         if (ntiles_b <= 16 && max_st >= 6 && ntiles_b * btile + 6 * abytes <= budget) { p.stages = 6; p.b_resident = 1; p.b_slots = ntiles_b; }

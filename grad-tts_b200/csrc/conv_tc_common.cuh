@@ -12,9 +12,9 @@ namespace tc {
 constexpr int kABytes = 128 * 128;                 // 128 pixel rows x 64 bf16
 constexpr int kMiscBytes = 4096;                   // barriers + epilogue scratch
 constexpr int kHaloABytes = 18 * 16 * 128;         // halo box: 18 rows x 16 pixels x 64 bf16
-constexpr int kStatSlots = 4;                      // ring of per-tile GroupNorm partials (epilogue warps -> stats warp)
+constexpr int kStatSlots = 8;                      // ring of per-tile GroupNorm partials (epilogue warps -> stats warp)
 constexpr int kThreads = 640;                      // warps 0-3: TMA, MMA, TMEM alloc, stats; warps 4-19: two epilogue groups
-template <int N> __host__ __device__ constexpr int acc_bufs() { return N <= 128 ? 4 : 2; }   // TMEM accumulator buffers (N cols each)
+template <int N> __host__ __device__ constexpr int acc_bufs() { return N <= 64 ? 8 : (N <= 128 ? 4 : 2); }   // TMEM accumulator buffers (N cols each)
 
 struct TcParams {
     int bh, bw, tiles_h, tiles_w, nphase, B;
@@ -30,7 +30,7 @@ struct TcParams {
 };
 
 // misc shared-memory block layout (relative to `misc`)
-//   [0,   640)  mbarriers + TMEM slot   [640, 1664) bias[256]   [1664, 2688) stats ring   [2688, 4096) finalize list
+//   [0,   768)  mbarriers + TMEM slot   [768, 1792) bias[256]   [1792, 3840) stats ring   [3840, 4096) finalize list
 struct TcShared {
     uint64_t *full, *empty, *tfull, *tempty, *sfull, *sempty, *fullb, *emptyb;
     uint32_t* tmem_slot;
@@ -43,15 +43,15 @@ __device__ __forceinline__ TcShared tc_shared(uint8_t* misc) {
     s.misc = misc;
     s.full = reinterpret_cast<uint64_t*>(misc);        // [8]
     s.empty = s.full + 8;                              // [8]
-    s.tfull = s.empty + 8;                             // [4]
-    s.tempty = s.tfull + 4;                            // [4]
-    s.sfull = s.tempty + 4;                            // [kStatSlots]
+    s.tfull = s.empty + 8;                             // [8]
+    s.tempty = s.tfull + 8;                            // [8]
+    s.sfull = s.tempty + 8;                            // [kStatSlots]
     s.sempty = s.sfull + kStatSlots;                   // [kStatSlots]
     s.fullb = s.sempty + kStatSlots;                   // [16]
     s.emptyb = s.fullb + 16;                           // [16]
     s.tmem_slot = reinterpret_cast<uint32_t*>(s.emptyb + 16);
-    s.s_bias = reinterpret_cast<float*>(misc + 640);
-    s.s_ring = reinterpret_cast<float*>(misc + 1664);
+    s.s_bias = reinterpret_cast<float*>(misc + 768);
+    s.s_ring = reinterpret_cast<float*>(misc + 1792);
     return s;
 }
 
@@ -339,7 +339,7 @@ __device__ __forceinline__ void tc_teardown(const TcParams& p, const TcShared& s
     }
     if (kStats) {
         const ConvEpilogue& e = p.e;
-        int* s_nfin = reinterpret_cast<int*>(misc + 2688);
+        int* s_nfin = reinterpret_cast<int*>(misc + 3840);
         int* s_fin = s_nfin + 1;
         double* s_red = reinterpret_cast<double*>(smem);             // pipeline buffers are idle now: [24][16]
         if (tid == 0) *s_nfin = 0;

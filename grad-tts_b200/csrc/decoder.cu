@@ -98,7 +98,7 @@ struct Decoder {
     int max_chunk = 8;
     bool use_graph = true;
     int conv_impl_bf16 = 1;   // 1: tcgen05, 0: FFMA (debug cross-check)
-    int halo_mode = 0;        // 3x3 convs: 0 = per-tap boxes, 1/2 = halo box + shifted descriptor views
+    int halo_mode = 2;        // 3x3 convs: 0 = per-tap boxes, 1/2 = halo box (18x16 / 18x10) + shifted descriptor views
     std::map<std::string, float*> params;
     std::map<std::string, size_t> param_numel;
     DevMem param_mem;
@@ -885,7 +885,7 @@ void decoder_delete(Decoder* d) { delete d; }
 int decoder_set_option(Decoder* d, const char* key, int value) {
     GTTS_REQUIRE(d != nullptr && key != nullptr, "null argument");
     std::string k(key);
-    if (k == "max_chunk") { GTTS_REQUIRE(value >= 1, "max_chunk must be >= 1"); d->max_chunk = value; }
+    if (k == "max_chunk") { GTTS_REQUIRE(value >= 1 && value <= 32, "max_chunk must be in [1, 32]"); d->max_chunk = value; }
     else if (k == "use_graph") d->use_graph = value != 0;
     else if (k == "conv_impl_bf16") d->conv_impl_bf16 = value;
     else if (k == "halo_mode") d->halo_mode = value;
