@@ -147,9 +147,16 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kN>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kN) : "memory"); }
+
 __global__ void __launch_bounds__(128)
 attn_ctx_tc_kernel(AttnCtxArgs a) {
-    __shared__ __align__(16) __nv_bfloat16 sm[kTcSub * kTcPitch];
+    extern __shared__ __align__(16) __nv_bfloat16 sm_all[];          // two sub-tile buffers (cp.async double buffering)
     const int tid = threadIdx.x, head = tid >> 5, lane = tid & 31;
     const int chunk = blockIdx.x, b = blockIdx.y;
     const int n0 = chunk * a.chunk_len, n1 = min(a.n, n0 + a.chunk_len);
@@ -165,21 +172,26 @@ attn_ctx_tc_kernel(AttnCtxArgs a) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-    uint32_t* kw = reinterpret_cast<uint32_t*>(sm) + head * 16 + cp;      // word (2 bf16) of my k columns, pixel 0
     constexpr int kWordPitch = kTcPitch / 2;
-
-    for (int p0 = n0; p0 < n1; p0 += kTcSub) {
-        __syncthreads();                                 // all warps are done with the previous sub-tile
+    auto fetch = [&](int p0, __nv_bfloat16* dst) {
 #pragma unroll 4
         for (int it = 0; it < 16; ++it) {
             const int idx = it * 128 + tid, px = idx >> 5, c16 = idx & 31, n = p0 + px;
-            uint4 val;
-            if (n < n1) val = __ldg(reinterpret_cast<const uint4*>(kv + (size_t)n * 256 + c16 * 8));
-            else if (c16 < 16) val = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);   // k = -inf
-            else val = make_uint4(0u, 0u, 0u, 0u);                                                      // v = 0
-            *reinterpret_cast<uint4*>(&sm[px * kTcPitch + c16 * 8]) = val;
+            __nv_bfloat16* d = &dst[px * kTcPitch + c16 * 8];
+            if (n < n1) cp_async16(d, kv + (size_t)n * 256 + c16 * 8);
+            else if (c16 < 16) *reinterpret_cast<uint4*>(d) = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);  // k = -inf
+            else *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);                                                   // v = 0
         }
-        __syncthreads();
+        cp_async_commit();
+    };
+    fetch(n0, sm_all);
+    int ib = 0;
+    for (int p0 = n0; p0 < n1; p0 += kTcSub, ib ^= 1) {
+        __nv_bfloat16* sm = sm_all + ib * (kTcSub * kTcPitch);
+        if (p0 + kTcSub < n1) { fetch(p0 + kTcSub, sm_all + (ib ^ 1) * (kTcSub * kTcPitch)); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();                                 // this sub-tile has landed for every thread
+        uint32_t* kw = reinterpret_cast<uint32_t*>(sm) + head * 16 + cp;   // word (2 bf16) of my k columns, pixel 0
         // ---- running max of my two k columns
         float x0 = -INFINITY, x1 = -INFINITY;
 #pragma unroll 8
@@ -240,6 +252,7 @@ attn_ctx_tc_kernel(AttnCtxArgs a) {
                 for (int nt = 0; nt < 4; ++nt)
                     mma_bf16_16816(acc[mt][nt], af[mt], bf[nt >> 1][(nt & 1) * 2], bf[nt >> 1][(nt & 1) * 2 + 1]);
         }
+        __syncthreads();                                 // everyone is done with this buffer before it is refilled
     }
     // ---- this chunk's partial (m[32], l[32], ctx[32][32]) for (b, head)
     float* part = a.partials + (((size_t)b * 4 + head) * a.chunks + chunk) * 1088;
@@ -369,7 +382,13 @@ int attn_ctx(ActKind act, const AttnCtxArgs& a, bool strict, cudaStream_t s) {
         else        attn_ctx_kernel<float, false><<<grid, 256, 0, s>>>(a);
     } else {
         dim3 grid(a.chunks, a.B);
-        attn_ctx_tc_kernel<<<grid, 128, 0, s>>>(a);
+        const int smem = 2 * kTcSub * kTcPitch * 2;
+        static bool attr_set = false;
+        if (!attr_set) {
+            GTTS_CHECK_CUDA(cudaFuncSetAttribute(attn_ctx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_set = true;
+        }
+        attn_ctx_tc_kernel<<<grid, 128, smem, s>>>(a);
     }
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -184,17 +184,20 @@ first_conv_kernel(FirstConvArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ GN apply
-// grid (blocks per sample, B); each thread owns one 8-channel vector position (fixed channels, so the affine
-// constants stay in registers) and streams kVecPerThread vectors of it with all loads issued up front.
+// grid (blocks per sample, B).  Each thread owns one 8-channel vector position (fixed channels, so the affine
+// constants stay in registers) and walks kGnIter groups of kGnVec vectors; the loads of group i+1 are issued before
+// the arithmetic of group i (software pipeline), so every SM keeps ~48 KB of reads in flight all the time.
 constexpr int kGnVec = 4;
+constexpr int kGnIter = 4;
 
 template <typename T, bool kStrict, bool kHasRes, bool kHasTb, bool kFirstRes>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 gn_apply_kernel(GnApplyArgs a) {
+    typedef typename Act<T>::Packed Packed;
     const int C8 = a.C >> 3;
     const int b = blockIdx.y;
     const size_t per_sample = (size_t)a.H * a.W * C8;                  // vectors per sample
-    const size_t v0 = (size_t)blockIdx.x * (256 * kGnVec) + threadIdx.x;
+    const size_t v00 = (size_t)blockIdx.x * (256 * kGnVec * kGnIter) + threadIdx.x;
     const int c8 = (int)(threadIdx.x % C8);                            // 256 % C8 == 0: same channels for all my vectors
     const int c0 = c8 * 8;
     const int g = (c0 * 8) / a.C;
@@ -211,20 +214,6 @@ gn_apply_kernel(GnApplyArgs a) {
     const T* res = kHasRes ? reinterpret_cast<const T*>(a.residual) + (size_t)b * per_sample * 8 : nullptr;
     T* out = reinterpret_cast<T*>(a.out) + (size_t)b * per_sample * 8;
     const float* mrow = a.mask + (size_t)b * a.W;
-
-    typename Act<T>::Packed pv[kGnVec], pr[kGnVec];
-    float m[kGnVec];
-    bool ok[kGnVec];
-#pragma unroll
-    for (int k = 0; k < kGnVec; ++k) {
-        const size_t vi = v0 + (size_t)k * 256;
-        ok[k] = vi < per_sample;
-        if (ok[k]) {
-            pv[k] = Act<T>::load_packed(raw + vi * 8);
-            if (kHasRes) pr[k] = Act<T>::load_packed(res + vi * 8);
-            m[k] = mrow[(int)((vi / C8) % a.W)];
-        }
-    }
     float frw[kFirstRes ? 8 : 1][3], frb[kFirstRes ? 8 : 1];
     if (kFirstRes) {
 #pragma unroll
@@ -234,35 +223,56 @@ gn_apply_kernel(GnApplyArgs a) {
             for (int ci = 0; ci < 3; ++ci) frw[j][ci] = ci < a.fr_cin ? __ldg(a.fr_w + (c0 + j) * a.fr_cin + ci) : 0.f;
         }
     }
+
+    Packed pv[2][kGnVec], pr[2][kGnVec];
+    float m[2][kGnVec], fin[2][kGnVec][3];
+    auto issue = [&](int stage, int it) {
 #pragma unroll
-    for (int k = 0; k < kGnVec; ++k) {
-        if (!ok[k]) continue;
-        const size_t vi = v0 + (size_t)k * 256;
-        float v[8], r[8];
-        Act<T>::unpack(pv[k], v);
-        if (kHasRes) Act<T>::unpack(pr[k], r);
-        float fin[3] = {0.f, 0.f, 0.f};
-        if (kFirstRes) {
-            const size_t pix = (size_t)b * a.H * a.W + vi / C8;
-            fin[0] = a.fr_mu[pix] * m[k];
-            fin[1] = a.fr_x[pix] * m[k];
-            if (a.fr_cin == 3) fin[2] = a.fr_s[pix / a.W] * m[k];
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float y = fmaf(v[j], sc[j], sh[j]);
-            y = mish<kStrict>(y) * m[k];                                 // Mish, * mask   (:54,58)
-            if (kHasTb) y += tb[j];                                      // h += mlp(t)    (:76)
-            if (kHasRes) y += r[j];                                      // + res_conv(x)  (:78)
-            if (kFirstRes) {
-                float rr = frb[j];
-#pragma unroll
-                for (int ci = 0; ci < 3; ++ci) rr = fmaf(frw[j][ci], fin[ci], rr);
-                y += rr;
+        for (int k = 0; k < kGnVec; ++k) {
+            const size_t vi = v00 + (size_t)(it * kGnVec + k) * 256;
+            if (vi < per_sample) {
+                pv[stage][k] = Act<T>::load_packed(raw + vi * 8);
+                if (kHasRes) pr[stage][k] = Act<T>::load_packed(res + vi * 8);
+                const size_t pin = vi / C8;                            // pixel within the sample
+                m[stage][k] = mrow[(int)(pin % a.W)];
+                if (kFirstRes) {
+                    const size_t pix = (size_t)b * a.H * a.W + pin;
+                    fin[stage][k][0] = a.fr_mu[pix];
+                    fin[stage][k][1] = a.fr_x[pix];
+                    fin[stage][k][2] = a.fr_cin == 3 ? a.fr_s[pix / a.W] : 0.f;
+                }
             }
-            v[j] = y * m[k];           // every consumer masks its input: store masked (binary masks)
         }
-        Act<T>::store8(out + vi * 8, v);
+    };
+    issue(0, 0);
+#pragma unroll
+    for (int it = 0; it < kGnIter; ++it) {
+        const int cur = it & 1;
+        if (it + 1 < kGnIter) issue(cur ^ 1, it + 1);
+#pragma unroll
+        for (int k = 0; k < kGnVec; ++k) {
+            const size_t vi = v00 + (size_t)(it * kGnVec + k) * 256;
+            if (vi >= per_sample) continue;
+            float v[8], r[8];
+            Act<T>::unpack(pv[cur][k], v);
+            if (kHasRes) Act<T>::unpack(pr[cur][k], r);
+            const float mk = m[cur][k];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float y = fmaf(v[j], sc[j], sh[j]);
+                y = mish<kStrict>(y) * mk;                               // Mish, * mask   (:54,58)
+                if (kHasTb) y += tb[j];                                  // h += mlp(t)    (:76)
+                if (kHasRes) y += r[j];                                  // + res_conv(x)  (:78)
+                if (kFirstRes) {                                         // res_conv(x*mask) of the first block, inline
+                    float rr = frb[j];
+#pragma unroll
+                    for (int ci = 0; ci < 3; ++ci) rr = fmaf(frw[j][ci], fin[cur][k][ci] * mk, rr);
+                    y += rr;
+                }
+                v[j] = y * mk;         // every consumer masks its input: store masked (binary masks)
+            }
+            Act<T>::store8(out + vi * 8, v);
+        }
     }
 }
 
@@ -278,6 +288,26 @@ euler_kernel(EulerArgs a) {
     const int sub = threadIdx.x & 7;
     const size_t pbase = ((size_t)blockIdx.x * 32 + (threadIdx.x >> 3)) * kEuPix;   // 32 lane groups per CTA
     const int HW = a.H * a.W;
+    // ---- everything this thread will need from memory is requested up front
+    typename Act<T>::Packed pv[kEuPix];
+#pragma unroll
+    for (int k = 0; k < kEuPix; ++k) {
+        const size_t pix = pbase + k;
+        if (pix < npix) pv[k] = Act<T>::load_packed(reinterpret_cast<const T*>(a.raw) + pix * 64 + sub * 8);
+    }
+    // lane 2k holds xt of pixel k, lane 2k+1 holds mu of pixel k (kEuPix = 4 pixels, 8 lanes)
+    const size_t mypix = pbase + (sub >> 1);
+    float pre = 0.f;
+    if (a.update && mypix < npix) pre = (sub & 1) ? a.mu[mypix] : a.xt[mypix];
+    float mk[kEuPix], mean[kEuPix], rstd[kEuPix];
+#pragma unroll
+    for (int k = 0; k < kEuPix; ++k) {
+        const size_t pp = (pbase + k < npix) ? pbase + k : 0;
+        const int b = (int)(pp / HW), w = (int)(pp % a.W);
+        mk[k] = a.mask[(size_t)b * a.W + w];
+        mean[k] = a.stats[(b * 8 + sub) * 2];
+        rstd[k] = a.stats[(b * 8 + sub) * 2 + 1];
+    }
     float sc[8], sh_[8], wf[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -285,30 +315,23 @@ euler_kernel(EulerArgs a) {
         sh_[j] = __ldg(a.beta + sub * 8 + j);
         wf[j] = __ldg(a.wf + sub * 8 + j);
     }
-    typename Act<T>::Packed pv[kEuPix];
-#pragma unroll
-    for (int k = 0; k < kEuPix; ++k) {
-        const size_t pix = pbase + k;
-        if (pix < npix) pv[k] = Act<T>::load_packed(reinterpret_cast<const T*>(a.raw) + pix * 64 + sub * 8);
-    }
     const float beta_t = a.update ? a.beta_tab[*a.step] : 0.f;
     const float hh = a.update ? *a.h_ptr : 0.f;
+    float noise_v = 0.f;
+    if (a.update && a.sde && !(sub & 1) && mypix < npix)
+        noise_v = (*a.noise_slot)[(size_t)(*a.step) * a.noise_step_stride + mypix];
+    const unsigned gbase = (threadIdx.x & 31) & ~7u;                  // first lane of my 8-lane group
 #pragma unroll
     for (int k = 0; k < kEuPix; ++k) {
-        const size_t pix = pbase + k;
-        const bool valid = pix < npix;
-        const size_t pp = valid ? pix : 0;
-        const int b = (int)(pp / HW);
-        const int w = (int)(pp % a.W);
-        const float m = a.mask[(size_t)b * a.W + w];
-        const float mean = a.stats[(b * 8 + sub) * 2], rstd = a.stats[(b * 8 + sub) * 2 + 1];
+        const bool valid = pbase + k < npix;
+        const float m = mk[k];
         float part = 0.f;
         if (valid) {
             float v[8];
             Act<T>::unpack(pv[k], v);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                float y = (v[j] - mean) * rstd * sc[j] + sh_[j];
+                float y = (v[j] - mean[k]) * rstd[k] * sc[j] + sh_[j];
                 y = mish<kStrict>(y) * m;                      // final_block(x, mask)              (:212)
                 part = fmaf(y * m, wf[j], part);               // final_conv(x * mask)              (:213)
             }
@@ -316,11 +339,13 @@ euler_kernel(EulerArgs a) {
         part += __shfl_xor_sync(0xffffffffu, part, 1);
         part += __shfl_xor_sync(0xffffffffu, part, 2);
         part += __shfl_xor_sync(0xffffffffu, part, 4);
-        if (!valid || sub != 0) continue;
+        const float mu = __shfl_sync(0xffffffffu, pre, gbase + 2 * k + 1);
+        if (!valid || sub != 2 * k) continue;                  // lane 2k finishes pixel k
+        const size_t pix = pbase + k;
         const float score = __fmul_rn(part + a.bf, m);         // (output * mask)                   (:216)
         if (a.score_out) a.score_out[pix] = score;
         if (!a.update) continue;
-        const float xt = a.xt[pix], mu = a.mu[pix];
+        const float xt = pre;
         float nx;
         if (!a.sde) {
             // dxt = 0.5*(mu - xt - est); dxt = dxt*noise_t*h; xt = (xt - dxt)*mask          (:265-267)
@@ -332,9 +357,7 @@ euler_kernel(EulerArgs a) {
             // north-star SDE form (upstream Grad-TTS): x - (0.5*(mu-x) - score)*beta*h + sqrt(beta*h)*z
             float d = __fsub_rn(__fmul_rn(0.5f, __fsub_rn(mu, xt)), score);
             d = __fmul_rn(__fmul_rn(d, beta_t), hh);
-            const float* noise = *a.noise_slot;
-            float z = noise[(size_t)(*a.step) * a.noise_step_stride + pix];
-            d = __fsub_rn(d, __fmul_rn(sqrtf(__fmul_rn(beta_t, hh)), z));
+            d = __fsub_rn(d, __fmul_rn(sqrtf(__fmul_rn(beta_t, hh)), noise_v));
             nx = __fmul_rn(__fsub_rn(xt, d), m);
         }
         a.xt[pix] = nx;
@@ -441,7 +464,7 @@ namespace {
 template <typename T, bool kStrict>
 int gn_apply_dispatch(const GnApplyArgs& a, cudaStream_t s) {
     const size_t per_sample = (size_t)a.H * a.W * (a.C / 8);
-    dim3 grid((unsigned int)((per_sample + 256 * kGnVec - 1) / (256 * kGnVec)), a.B);
+    dim3 grid((unsigned int)((per_sample + 256 * kGnVec * kGnIter - 1) / (256 * kGnVec * kGnIter)), a.B);
     const bool res = a.residual != nullptr, tb = a.tbias != nullptr, fr = a.fr_w != nullptr;
     if (fr)             gn_apply_kernel<T, kStrict, false, false, true><<<grid, 256, 0, s>>>(a);
     else if (res && tb) gn_apply_kernel<T, kStrict, true, true, false><<<grid, 256, 0, s>>>(a);
