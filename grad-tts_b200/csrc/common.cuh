@@ -218,6 +218,12 @@ __device__ __forceinline__ void tma_load_4d(const void* desc, uint64_t* bar, voi
         "r"(c2), "r"(c3)
         : "memory");
 }
+// 1-D bulk copy global -> shared (no tensor map), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_4d(const void* desc, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
                  ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)

@@ -276,6 +276,140 @@ gn_apply_kernel(GnApplyArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ GN apply (bulk)
+// bf16 streaming version: one persistent CTA per SM, a producer warp feeds a deep shared-memory ring with 1-D bulk
+// copies (cp.async.bulk, 16 KB of `raw` (+16 KB of residual) per stage, up to ~190 KB in flight per SM), eight
+// consumer warps read 16 bytes per thread from the ring, apply GroupNorm+Mish+mask(+bias)(+residual) and store
+// the result straight to global memory (fully coalesced).
+constexpr int kBkVec = 1024;                       // 8-channel vectors per chunk (16 KB of bf16)
+constexpr int kBkThreads = 288;                    // 8 consumer warps + 1 producer warp
+
+template <bool kHasRes, bool kHasTb, bool kFirstRes>
+__global__ void __launch_bounds__(kBkThreads, 1)
+gn_apply_bulk_kernel(GnApplyArgs a, int chunks_per_sample, int total_chunks, int stages) {
+    typedef __nv_bfloat16 T;
+    extern __shared__ __align__(128) uint8_t bsm[];
+    constexpr int kStageBytes = kBkVec * 16 * (kHasRes ? 2 : 1);
+    uint64_t* full = reinterpret_cast<uint64_t*>(bsm + (size_t)stages * kStageBytes);
+    uint64_t* empty = full + stages;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int C8 = a.C >> 3;
+    const size_t per_sample = (size_t)a.H * a.W * C8;
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp == 8) {
+        // ================================================================ producer
+        if (lane == 0) {
+            int st = 0;
+            uint32_t ph = 0;
+            for (int c = blockIdx.x; c < total_chunks; c += gridDim.x) {
+                const int b = c / chunks_per_sample, ci = c - b * chunks_per_sample;
+                const size_t off = (size_t)ci * kBkVec;
+                const uint32_t nvec = (uint32_t)min((size_t)kBkVec, per_sample - off);
+                const uint32_t bytes = nvec * 16u;
+                mbar_wait(&empty[st], ph ^ 1u);
+                mbar_expect_tx(&full[st], bytes * (kHasRes ? 2u : 1u));
+                uint8_t* dst = bsm + (size_t)st * kStageBytes;
+                bulk_load(dst, reinterpret_cast<const T*>(a.raw) + ((size_t)b * per_sample + off) * 8, bytes, &full[st]);
+                if (kHasRes)
+                    bulk_load(dst + kBkVec * 16, reinterpret_cast<const T*>(a.residual) + ((size_t)b * per_sample + off) * 8,
+                              bytes, &full[st]);
+                if (++st == stages) { st = 0; ph ^= 1u; }
+            }
+        }
+        return;
+    }
+    // ================================================================ consumers (256 threads)
+    const int c8 = tid % C8, c0 = c8 * 8;                              // 256 % C8 == 0: fixed channels per thread
+    const int g = (c0 * 8) / a.C;
+    float ga[8], be[8], frw[kFirstRes ? 8 : 1][3], frb[kFirstRes ? 8 : 1];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ga[j] = __ldg(a.gamma + c0 + j); be[j] = __ldg(a.beta + c0 + j); }
+    if (kFirstRes) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            frb[j] = __ldg(a.fr_b + c0 + j);
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) frw[j][ci] = ci < a.fr_cin ? __ldg(a.fr_w + (c0 + j) * a.fr_cin + ci) : 0.f;
+        }
+    }
+    int st = 0, cur_b = -1;
+    uint32_t ph = 0;
+    float sc[8], sh[8], tb[8];
+    for (int c = blockIdx.x; c < total_chunks; c += gridDim.x) {
+        const int b = c / chunks_per_sample, ci = c - b * chunks_per_sample;
+        const size_t off = (size_t)ci * kBkVec;
+        const int nvec = (int)min((size_t)kBkVec, per_sample - off);
+        if (b != cur_b) {
+            cur_b = b;
+            const float mean = a.stats[(b * 8 + g) * 2], rstd = a.stats[(b * 8 + g) * 2 + 1];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                sc[j] = rstd * ga[j];                                    // GroupNorm (:53): y = x*scale + shift
+                sh[j] = be[j] - mean * sc[j];
+                tb[j] = kHasTb ? __ldg(a.tbias + (size_t)b * a.tbias_bstride + c0 + j) : 0.f;
+            }
+        }
+        // per-vector side inputs are requested before waiting for the bulk data
+        float mk[4], fin[4][3];
+        const float* mrow = a.mask + (size_t)b * a.W;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int vl = tid + k * 256;
+            mk[k] = 0.f;
+            if (vl < nvec) {
+                const size_t pin = (off + vl) / C8;
+                mk[k] = mrow[(int)(pin % a.W)];
+                if (kFirstRes) {
+                    const size_t pix = (size_t)b * a.H * a.W + pin;
+                    fin[k][0] = a.fr_mu[pix] * mk[k];
+                    fin[k][1] = a.fr_x[pix] * mk[k];
+                    fin[k][2] = a.fr_cin == 3 ? a.fr_s[pix / a.W] * mk[k] : 0.f;
+                }
+            }
+        }
+        mbar_wait(&full[st], ph);
+        const uint8_t* src = bsm + (size_t)st * kStageBytes;
+        uint4 pv[4], pr[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int vl = tid + k * 256;
+            pv[k] = *reinterpret_cast<const uint4*>(src + (size_t)vl * 16);
+            if (kHasRes) pr[k] = *reinterpret_cast<const uint4*>(src + kBkVec * 16 + (size_t)vl * 16);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);                          // slot can be refilled
+        if (++st == stages) { st = 0; ph ^= 1u; }
+        T* out = reinterpret_cast<T*>(a.out) + ((size_t)b * per_sample + off) * 8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int vl = tid + k * 256;
+            if (vl >= nvec) continue;
+            float v[8], r[8];
+            Act<T>::unpack(pv[k], v);
+            if (kHasRes) Act<T>::unpack(pr[k], r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float y = fmaf(v[j], sc[j], sh[j]);
+                y = mish<false>(y) * mk[k];                              // Mish, * mask   (:54,58)
+                if (kHasTb) y += tb[j];                                  // h += mlp(t)    (:76)
+                if (kHasRes) y += r[j];                                  // + res_conv(x)  (:78)
+                if (kFirstRes) {
+                    float rr = frb[j];
+#pragma unroll
+                    for (int ci = 0; ci < 3; ++ci) rr = fmaf(frw[j][ci], fin[k][ci], rr);
+                    y += rr;
+                }
+                v[j] = y * mk[k];
+            }
+            Act<T>::store8(out + (size_t)vl * 8, v);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ Euler step
 // final_block GN+Mish+mask -> final_conv(64->1)+bias -> *mask = score; then the sampler update.
 // 8 lanes per pixel (one 8-channel vector each), kEuPix pixels per lane group with the loads issued up front.
@@ -475,9 +609,46 @@ int gn_apply_dispatch(const GnApplyArgs& a, cudaStream_t s) {
 }
 }  // namespace
 
+namespace {
+template <bool kHasRes, bool kHasTb, bool kFirstRes>
+int gn_apply_bulk_launch(const GnApplyArgs& a, cudaStream_t s) {
+    static int num_sms = 0;
+    static bool attr_set = false;
+    auto k = gn_apply_bulk_kernel<kHasRes, kHasTb, kFirstRes>;
+    if (!attr_set) {
+        int dev = 0;
+        GTTS_CHECK_CUDA(cudaGetDevice(&dev));
+        GTTS_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+        GTTS_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    const size_t per_sample = (size_t)a.H * a.W * (a.C / 8);
+    const int cps = (int)((per_sample + kBkVec - 1) / kBkVec), total = cps * a.B;
+    const int stage_bytes = kBkVec * 16 * (kHasRes ? 2 : 1);
+    int stages = (192 * 1024) / stage_bytes;
+    if (stages > 10) stages = 10;
+    const size_t smem = (size_t)stages * stage_bytes + 2 * stages * sizeof(uint64_t);
+    const int grid = total < num_sms ? total : num_sms;
+    k<<<grid, kBkThreads, smem, s>>>(a, cps, total, stages);
+    return 0;
+}
+}  // namespace
+
 int gn_apply(ActKind act, const GnApplyArgs& a, bool strict, cudaStream_t s) {
     GTTS_REQUIRE(a.C % 64 == 0 && a.C <= 256, "gn_apply: C must be 64, 128 or 256");
     GTTS_REQUIRE(!(a.fr_w && (a.residual || a.tbias)), "gn_apply: first-block residual excludes the others");
+    if (act == ACT_BF16 && !strict) {
+        const bool res = a.residual != nullptr, tb = a.tbias != nullptr, fr = a.fr_w != nullptr;
+        int rc;
+        if (fr)             rc = gn_apply_bulk_launch<false, false, true>(a, s);
+        else if (res && tb) rc = gn_apply_bulk_launch<true, true, false>(a, s);
+        else if (res)       rc = gn_apply_bulk_launch<true, false, false>(a, s);
+        else if (tb)        rc = gn_apply_bulk_launch<false, true, false>(a, s);
+        else                rc = gn_apply_bulk_launch<false, false, false>(a, s);
+        if (rc) return rc;
+        GTTS_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     if (act == ACT_F32) {
         if (strict) gn_apply_dispatch<float, true>(a, s);
         else        gn_apply_dispatch<float, false>(a, s);

@@ -176,7 +176,7 @@ def stage_profile():
     for (n_spks, B, T) in [(1, 16, 1720), (1, 1, 400)]:
         dec, _ = _decoder(n_spks, 0, "bf16")
         dec.estimator.max_chunk = B
-        hm = int(os.environ.get("GTTS_HALO", "0"))
+        hm = int(os.environ.get("GTTS_HALO", "2"))
         pkg._lib.check(pkg._lib.load().gtts_decoder_set_option(dec.estimator._get_handle(), b"halo_mode", hm), "opt")
         z, mask, mu, spk, _ = pkg.synth.make_inputs(B, T, n_spks, seed=7, ragged=False)
         dec(z.to(DEV), mask.to(DEV), mu.to(DEV), 2)
