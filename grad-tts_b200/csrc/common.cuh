@@ -106,6 +106,40 @@ __device__ __forceinline__ float mish(float x) {
     }
 }
 
+// Packed fp32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100): halves the issue slots of the epilogue arithmetic.
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    float2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<uint64_t*>(&r))
+        : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
+    return r;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    float2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<uint64_t*>(&r))
+        : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
+    return r;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(*reinterpret_cast<uint64_t*>(&r))
+        : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)), "l"(*reinterpret_cast<uint64_t*>(&c)));
+    return r;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// Branch-free fast Mish on a pair: y * n/(n+2), n = e(e+2), e = 2^min(ylog2, 43) where ylog2 = y*log2(e) is supplied
+// by the caller (folded into the preceding affine).  For y > 30 the factor rounds to 1 (torch's softplus threshold
+// path returns y there as well); for y << 0 it underflows to 0.
+__device__ __forceinline__ float2 mish2_fast(float2 y, float2 ylog2) {
+    float2 e = make_float2(ex2_approx(fminf(ylog2.x, 43.0f)), ex2_approx(fminf(ylog2.y, 43.0f)));
+    const float2 n = ffma2(e, e, fadd2(e, e));
+    const float2 d = fadd2(n, make_float2(2.0f, 2.0f));
+    const float2 t = fmul2(n, make_float2(rcp_approx(d.x), rcp_approx(d.y)));
+    return fmul2(y, t);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

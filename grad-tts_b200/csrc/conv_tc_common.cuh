@@ -74,26 +74,6 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
 }
 
-// Packed fp32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100): halves the issue slots of the epilogue arithmetic.
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-    float2 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<uint64_t*>(&r))
-        : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
-    return r;
-}
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-    float2 r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<uint64_t*>(&r))
-        : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
-    return r;
-}
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-    float2 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(*reinterpret_cast<uint64_t*>(&r))
-        : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)), "l"(*reinterpret_cast<uint64_t*>(&c)));
-    return r;
-}
-
 // Tile walker: decodes tile = blockIdx.x + it*gridDim.x into (tw, th, ph, b) incrementally (no per-tile divisions).
 struct TileWalk {
     int tile, tw, th, ph, b;

@@ -276,137 +276,97 @@ gn_apply_kernel(GnApplyArgs a) {
     }
 }
 
-// ------------------------------------------------------------------------------------------------ GN apply (bulk)
-// bf16 streaming version: one persistent CTA per SM, a producer warp feeds a deep shared-memory ring with 1-D bulk
-// copies (cp.async.bulk, 16 KB of `raw` (+16 KB of residual) per stage, up to ~190 KB in flight per SM), eight
-// consumer warps read 16 bytes per thread from the ring, apply GroupNorm+Mish+mask(+bias)(+residual) and store
-// the result straight to global memory (fully coalesced).
-constexpr int kBkVec = 1024;                       // 8-channel vectors per chunk (16 KB of bf16)
-constexpr int kBkThreads = 288;                    // 8 consumer warps + 1 producer warp
+// ------------------------------------------------------------------------------------------------ GN apply (bf16 fast)
+// The pass is issue-bound, not bandwidth-bound (measured: a 190 KB-deep bulk-copy ring fed by 8 math warps was
+// slower).  This version spends ~10 issue slots per element: packed f32x2 affine / Mish / mask / bias arithmetic,
+// a branch-free Mish (two MUFU per element), bf16 data kept packed in registers until used.
+constexpr int kGfVec = 4;
 
 template <bool kHasRes, bool kHasTb, bool kFirstRes>
-__global__ void __launch_bounds__(kBkThreads, 1)
-gn_apply_bulk_kernel(GnApplyArgs a, int chunks_per_sample, int total_chunks, int stages) {
+__global__ void __launch_bounds__(256, 3)
+gn_apply_fast_kernel(GnApplyArgs a) {
     typedef __nv_bfloat16 T;
-    extern __shared__ __align__(128) uint8_t bsm[];
-    constexpr int kStageBytes = kBkVec * 16 * (kHasRes ? 2 : 1);
-    uint64_t* full = reinterpret_cast<uint64_t*>(bsm + (size_t)stages * kStageBytes);
-    uint64_t* empty = full + stages;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int C8 = a.C >> 3;
+    const int b = blockIdx.y;
     const size_t per_sample = (size_t)a.H * a.W * C8;
-    if (tid == 0) {
-        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
-        mbar_fence_init();
+    const size_t v0 = (size_t)blockIdx.x * (256 * kGfVec) + threadIdx.x;
+    const int c0 = (int)(threadIdx.x % C8) * 8;
+    const int g = (c0 * 8) / a.C;
+    const float mean = a.stats[(b * 8 + g) * 2], rstd = a.stats[(b * 8 + g) * 2 + 1];
+    constexpr float kLog2e = 1.4426950408889634f;
+    float2 sc[4], sh[4], scl[4], shl[4], tb[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float s0 = rstd * __ldg(a.gamma + c0 + 2 * q), s1 = rstd * __ldg(a.gamma + c0 + 2 * q + 1);
+        const float h0 = __ldg(a.beta + c0 + 2 * q) - mean * s0, h1 = __ldg(a.beta + c0 + 2 * q + 1) - mean * s1;
+        sc[q] = make_float2(s0, s1);                   sh[q] = make_float2(h0, h1);
+        scl[q] = make_float2(s0 * kLog2e, s1 * kLog2e); shl[q] = make_float2(h0 * kLog2e, h1 * kLog2e);
+        tb[q] = kHasTb ? make_float2(__ldg(a.tbias + (size_t)b * a.tbias_bstride + c0 + 2 * q),
+                                     __ldg(a.tbias + (size_t)b * a.tbias_bstride + c0 + 2 * q + 1))
+                       : make_float2(0.f, 0.f);
     }
-    __syncthreads();
-    if (warp == 8) {
-        // ================================================================ producer
-        if (lane == 0) {
-            int st = 0;
-            uint32_t ph = 0;
-            for (int c = blockIdx.x; c < total_chunks; c += gridDim.x) {
-                const int b = c / chunks_per_sample, ci = c - b * chunks_per_sample;
-                const size_t off = (size_t)ci * kBkVec;
-                const uint32_t nvec = (uint32_t)min((size_t)kBkVec, per_sample - off);
-                const uint32_t bytes = nvec * 16u;
-                mbar_wait(&empty[st], ph ^ 1u);
-                mbar_expect_tx(&full[st], bytes * (kHasRes ? 2u : 1u));
-                uint8_t* dst = bsm + (size_t)st * kStageBytes;
-                bulk_load(dst, reinterpret_cast<const T*>(a.raw) + ((size_t)b * per_sample + off) * 8, bytes, &full[st]);
-                if (kHasRes)
-                    bulk_load(dst + kBkVec * 16, reinterpret_cast<const T*>(a.residual) + ((size_t)b * per_sample + off) * 8,
-                              bytes, &full[st]);
-                if (++st == stages) { st = 0; ph ^= 1u; }
+    const T* raw = reinterpret_cast<const T*>(a.raw) + (size_t)b * per_sample * 8;
+    const T* res = kHasRes ? reinterpret_cast<const T*>(a.residual) + (size_t)b * per_sample * 8 : nullptr;
+    T* out = reinterpret_cast<T*>(a.out) + (size_t)b * per_sample * 8;
+    const float* mrow = a.mask + (size_t)b * a.W;
+
+    uint4 pv[kGfVec], pr[kGfVec];
+    float m[kGfVec], fin[kFirstRes ? kGfVec : 1][3];
+    bool ok[kGfVec];
+#pragma unroll
+    for (int k = 0; k < kGfVec; ++k) {
+        const size_t vi = v0 + (size_t)k * 256;
+        ok[k] = vi < per_sample;
+        if (ok[k]) {
+            pv[k] = __ldg(reinterpret_cast<const uint4*>(raw + vi * 8));
+            if (kHasRes) pr[k] = __ldg(reinterpret_cast<const uint4*>(res + vi * 8));
+            const size_t pin = vi / C8;
+            m[k] = mrow[(int)(pin % a.W)];
+            if (kFirstRes) {
+                const size_t pix = (size_t)b * a.H * a.W + pin;
+                fin[k][0] = a.fr_mu[pix] * m[k];
+                fin[k][1] = a.fr_x[pix] * m[k];
+                fin[k][2] = a.fr_cin == 3 ? a.fr_s[pix / a.W] * m[k] : 0.f;
             }
         }
-        return;
     }
-    // ================================================================ consumers (256 threads)
-    const int c8 = tid % C8, c0 = c8 * 8;                              // 256 % C8 == 0: fixed channels per thread
-    const int g = (c0 * 8) / a.C;
-    float ga[8], be[8], frw[kFirstRes ? 8 : 1][3], frb[kFirstRes ? 8 : 1];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { ga[j] = __ldg(a.gamma + c0 + j); be[j] = __ldg(a.beta + c0 + j); }
+    float2 frw[kFirstRes ? 4 : 1][3], frb[kFirstRes ? 4 : 1];
     if (kFirstRes) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            frb[j] = __ldg(a.fr_b + c0 + j);
+        for (int q = 0; q < 4; ++q) {
+            frb[q] = make_float2(__ldg(a.fr_b + c0 + 2 * q), __ldg(a.fr_b + c0 + 2 * q + 1));
 #pragma unroll
-            for (int ci = 0; ci < 3; ++ci) frw[j][ci] = ci < a.fr_cin ? __ldg(a.fr_w + (c0 + j) * a.fr_cin + ci) : 0.f;
+            for (int ci = 0; ci < 3; ++ci)
+                frw[q][ci] = ci < a.fr_cin ? make_float2(__ldg(a.fr_w + (c0 + 2 * q) * a.fr_cin + ci),
+                                                         __ldg(a.fr_w + (c0 + 2 * q + 1) * a.fr_cin + ci))
+                                           : make_float2(0.f, 0.f);
         }
     }
-    int st = 0, cur_b = -1;
-    uint32_t ph = 0;
-    float sc[8], sh[8], tb[8];
-    for (int c = blockIdx.x; c < total_chunks; c += gridDim.x) {
-        const int b = c / chunks_per_sample, ci = c - b * chunks_per_sample;
-        const size_t off = (size_t)ci * kBkVec;
-        const int nvec = (int)min((size_t)kBkVec, per_sample - off);
-        if (b != cur_b) {
-            cur_b = b;
-            const float mean = a.stats[(b * 8 + g) * 2], rstd = a.stats[(b * 8 + g) * 2 + 1];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                sc[j] = rstd * ga[j];                                    // GroupNorm (:53): y = x*scale + shift
-                sh[j] = be[j] - mean * sc[j];
-                tb[j] = kHasTb ? __ldg(a.tbias + (size_t)b * a.tbias_bstride + c0 + j) : 0.f;
+    for (int k = 0; k < kGfVec; ++k) {
+        if (!ok[k]) continue;
+        const uint32_t w[4] = {pv[k].x, pv[k].y, pv[k].z, pv[k].w};
+        const uint32_t rw[4] = {pr[k].x, pr[k].y, pr[k].z, pr[k].w};
+        const float2 m2 = make_float2(m[k], m[k]);
+        uint32_t ow[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 x = make_float2(__uint_as_float(w[q] << 16), __uint_as_float(w[q] & 0xffff0000u));
+            const float2 y = ffma2(x, sc[q], sh[q]);                    // GroupNorm affine          (:53)
+            float2 o = mish2_fast(y, ffma2(x, scl[q], shl[q]));         // Mish                      (:54)
+            if (kHasTb) o = fadd2(o, tb[q]);                            // (mish*m + tb)*m == (mish + tb)*m, m in {0,1}
+            if (kHasRes) o = fadd2(o, make_float2(__uint_as_float(rw[q] << 16), __uint_as_float(rw[q] & 0xffff0000u)));
+            if (kFirstRes) {
+                float2 rr = frb[q];
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) rr = ffma2(frw[q][ci], make_float2(fin[k][ci], fin[k][ci]), rr);
+                o = fadd2(o, rr);
             }
+            o = fmul2(o, m2);                                           // * mask (stored masked)
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(o.x, o.y);
+            ow[q] = *reinterpret_cast<uint32_t*>(&h2);
         }
-        // per-vector side inputs are requested before waiting for the bulk data
-        float mk[4], fin[4][3];
-        const float* mrow = a.mask + (size_t)b * a.W;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int vl = tid + k * 256;
-            mk[k] = 0.f;
-            if (vl < nvec) {
-                const size_t pin = (off + vl) / C8;
-                mk[k] = mrow[(int)(pin % a.W)];
-                if (kFirstRes) {
-                    const size_t pix = (size_t)b * a.H * a.W + pin;
-                    fin[k][0] = a.fr_mu[pix] * mk[k];
-                    fin[k][1] = a.fr_x[pix] * mk[k];
-                    fin[k][2] = a.fr_cin == 3 ? a.fr_s[pix / a.W] * mk[k] : 0.f;
-                }
-            }
-        }
-        mbar_wait(&full[st], ph);
-        const uint8_t* src = bsm + (size_t)st * kStageBytes;
-        uint4 pv[4], pr[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int vl = tid + k * 256;
-            pv[k] = *reinterpret_cast<const uint4*>(src + (size_t)vl * 16);
-            if (kHasRes) pr[k] = *reinterpret_cast<const uint4*>(src + kBkVec * 16 + (size_t)vl * 16);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);                          // slot can be refilled
-        if (++st == stages) { st = 0; ph ^= 1u; }
-        T* out = reinterpret_cast<T*>(a.out) + ((size_t)b * per_sample + off) * 8;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int vl = tid + k * 256;
-            if (vl >= nvec) continue;
-            float v[8], r[8];
-            Act<T>::unpack(pv[k], v);
-            if (kHasRes) Act<T>::unpack(pr[k], r);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float y = fmaf(v[j], sc[j], sh[j]);
-                y = mish<false>(y) * mk[k];                              // Mish, * mask   (:54,58)
-                if (kHasTb) y += tb[j];                                  // h += mlp(t)    (:76)
-                if (kHasRes) y += r[j];                                  // + res_conv(x)  (:78)
-                if (kFirstRes) {
-                    float rr = frb[j];
-#pragma unroll
-                    for (int ci = 0; ci < 3; ++ci) rr = fmaf(frw[j][ci], fin[k][ci], rr);
-                    y += rr;
-                }
-                v[j] = y * mk[k];
-            }
-            Act<T>::store8(out + (size_t)vl * 8, v);
-        }
+        *reinterpret_cast<uint4*>(out + (v0 + (size_t)k * 256) * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
 }
 
@@ -463,11 +423,25 @@ euler_kernel(EulerArgs a) {
         if (valid) {
             float v[8];
             Act<T>::unpack(pv[k], v);
+            if (kStrict) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float y = (v[j] - mean[k]) * rstd[k] * sc[j] + sh_[j];
-                y = mish<kStrict>(y) * m;                      // final_block(x, mask)              (:212)
-                part = fmaf(y * m, wf[j], part);               // final_conv(x * mask)              (:213)
+                for (int j = 0; j < 8; ++j) {
+                    float y = (v[j] - mean[k]) * rstd[k] * sc[j] + sh_[j];
+                    y = mish<true>(y) * m;                     // final_block(x, mask)              (:212)
+                    part = fmaf(y * m, wf[j], part);           // final_conv(x * mask)              (:213)
+                }
+            } else {
+                const float2 r2 = make_float2(rstd[k], rstd[k]), nm2 = make_float2(-mean[k] * rstd[k], -mean[k] * rstd[k]);
+                const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f);
+                float2 p2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 xn = ffma2(make_float2(v[2 * q], v[2 * q + 1]), r2, nm2);
+                    const float2 y = ffma2(xn, make_float2(sc[2 * q], sc[2 * q + 1]), make_float2(sh_[2 * q], sh_[2 * q + 1]));
+                    const float2 o = mish2_fast(y, fmul2(y, l2e));
+                    p2 = ffma2(o, make_float2(wf[2 * q], wf[2 * q + 1]), p2);
+                }
+                part = (p2.x + p2.y) * m;                      // binary mask: (mish*m)*m*w summed == m * sum(mish*w)
             }
         }
         part += __shfl_xor_sync(0xffffffffu, part, 1);
@@ -611,25 +585,10 @@ int gn_apply_dispatch(const GnApplyArgs& a, cudaStream_t s) {
 
 namespace {
 template <bool kHasRes, bool kHasTb, bool kFirstRes>
-int gn_apply_bulk_launch(const GnApplyArgs& a, cudaStream_t s) {
-    static int num_sms = 0;
-    static bool attr_set = false;
-    auto k = gn_apply_bulk_kernel<kHasRes, kHasTb, kFirstRes>;
-    if (!attr_set) {
-        int dev = 0;
-        GTTS_CHECK_CUDA(cudaGetDevice(&dev));
-        GTTS_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        GTTS_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
+int gn_apply_fast_launch(const GnApplyArgs& a, cudaStream_t s) {
     const size_t per_sample = (size_t)a.H * a.W * (a.C / 8);
-    const int cps = (int)((per_sample + kBkVec - 1) / kBkVec), total = cps * a.B;
-    const int stage_bytes = kBkVec * 16 * (kHasRes ? 2 : 1);
-    int stages = (192 * 1024) / stage_bytes;
-    if (stages > 10) stages = 10;
-    const size_t smem = (size_t)stages * stage_bytes + 2 * stages * sizeof(uint64_t);
-    const int grid = total < num_sms ? total : num_sms;
-    k<<<grid, kBkThreads, smem, s>>>(a, cps, total, stages);
+    dim3 grid((unsigned int)((per_sample + 256 * kGfVec - 1) / (256 * kGfVec)), a.B);
+    gn_apply_fast_kernel<kHasRes, kHasTb, kFirstRes><<<grid, 256, 0, s>>>(a);
     return 0;
 }
 }  // namespace
@@ -640,11 +599,11 @@ int gn_apply(ActKind act, const GnApplyArgs& a, bool strict, cudaStream_t s) {
     if (act == ACT_BF16 && !strict) {
         const bool res = a.residual != nullptr, tb = a.tbias != nullptr, fr = a.fr_w != nullptr;
         int rc;
-        if (fr)             rc = gn_apply_bulk_launch<false, false, true>(a, s);
-        else if (res && tb) rc = gn_apply_bulk_launch<true, true, false>(a, s);
-        else if (res)       rc = gn_apply_bulk_launch<true, false, false>(a, s);
-        else if (tb)        rc = gn_apply_bulk_launch<false, true, false>(a, s);
-        else                rc = gn_apply_bulk_launch<false, false, false>(a, s);
+        if (fr)             rc = gn_apply_fast_launch<false, false, true>(a, s);
+        else if (res && tb) rc = gn_apply_fast_launch<true, true, false>(a, s);
+        else if (res)       rc = gn_apply_fast_launch<true, false, false>(a, s);
+        else if (tb)        rc = gn_apply_fast_launch<false, true, false>(a, s);
+        else                rc = gn_apply_fast_launch<false, false, false>(a, s);
         if (rc) return rc;
         GTTS_CHECK_CUDA(cudaGetLastError());
         return 0;
