@@ -33,7 +33,7 @@ namespace {
 template <int N, bool kStats, bool kRes, bool kMask>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-               const __grid_constant__ CUtensorMap mapW, const TcParams p) {
+               const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapWh, const TcParams p) {
     constexpr int kBBytes = N * 128;
     constexpr int kStage = kABytes + kBBytes;
     constexpr uint32_t kIdesc = make_idesc<N>();
@@ -50,8 +50,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tma_prefetch_desc(&mapA0);
         tma_prefetch_desc(&mapA1);
         tma_prefetch_desc(&mapW);
+        tma_prefetch_desc(&mapWh);
     }
     const uint32_t tmem_base = tc_prologue<N>(p, sh, p.stages, 0, tid, warp, lane);
+    const int n_it = tc_num_iters(p);
+    const int G = (int)gridDim.x;
 
     const int nkb = p.ntaps * (p.nchunk0 + p.nchunk1);
     const int tiles_per_phase = p.tiles_h * p.tiles_w;
@@ -61,7 +64,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const uint32_t rank = p.mc ? cluster_ctarank() : 0u;
+            for (int it = 0; it < n_it; ++it) {
+                const int tile = (int)blockIdx.x + it * G;
+                const bool dummy = tile >= p.num_tiles;              // only with multicast: keeps the pair in lockstep
                 const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h;
                 const int ph = (tile / tiles_per_phase) % p.nphase, b = tile / (tiles_per_phase * p.nphase);
                 const int h0 = th * p.bh, w0 = tw * p.bw;
@@ -71,8 +77,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     for (int ck = 0; ck < p.nchunk0 + p.nchunk1; ++ck) {
                         mbar_wait(&empty[stage], phase ^ 1u);
                         uint8_t* sa = smem + (size_t)stage * kStage;
-                        mbar_expect_tx(&full[stage], (uint32_t)(p.a_bytes + kBBytes));
-                        if (p.stride2) {
+                        mbar_expect_tx(&full[stage], (uint32_t)((dummy ? 0 : p.a_bytes) + kBBytes));
+                        if (dummy) {
+                        } else if (p.stride2) {
                             // 5-D view (2C, W/2, 2, H/2, B): input pixel 2*o + d, d in {-1,0,1}
                             const int px = dx & 1, py = dy & 1;
                             tma_load_5d(&mapA0, &full[stage], sa, px * p.Cin0 + ck * 64, w0 + (dx < 0 ? -1 : 0), py,
@@ -82,7 +89,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         } else {
                             tma_load_4d(&mapA1, &full[stage], sa, (ck - p.nchunk0) * 64, w0 + dx, h0 + dy, b);
                         }
-                        tma_load_2d(&mapW, &full[stage], sa + kABytes, ck * 64, wr);
+                        if (p.mc) {
+                            // my half of the weight tile goes to both CTAs of the pair (same smem offset, same barrier)
+                            // (multicast is only used with one phase and shared weights: the row is p.wrow[0][tap])
+                            tma_load_2d_mc(&mapWh, &full[stage], sa + kABytes + rank * (kBBytes / 2), ck * 64,
+                                           p.wrow[0][tap] + (int)rank * (N / 2), (uint16_t)3);
+                        } else {
+                            tma_load_2d(&mapW, &full[stage], sa + kABytes, ck * 64, wr);
+                        }
                         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -98,7 +112,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const uint64_t stage_step = (uint64_t)(kStage >> 4);
         int stage = 0, it = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int mc = p.mc;
+        for (it = 0; it < n_it; ++it) {
             const int buf = it % acc_bufs<N>();
             mbar_wait(&sh.tempty[buf], ((uint32_t)(it / acc_bufs<N>()) & 1u) ^ 1u);
             tc_fence_after();
@@ -113,7 +128,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     for (int k = 0; k < 4; ++k)                     // 4 x (K = 16 bf16 = 32 bytes)
                         tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
                                    (uint32_t)((kb | k) != 0));
-                    tc_commit(&empty[stage]);                       // smem slot free when these MMAs retire
+                    if (mc) tc_commit_mc(&empty[stage], (uint16_t)3);   // frees the slot in both CTAs of the pair
+                    else tc_commit(&empty[stage]);                  // smem slot free when these MMAs retire
                     if (kb == nkb - 1) tc_commit(&sh.tfull[buf]);   // accumulator complete
                 }
                 if (++stage == nstage) { stage = 0; phase ^= 1u; }
@@ -211,6 +227,19 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
     }
     pl->grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
     if (pl->grid > 256) pl->grid = 256;                    // GN partial buffers hold 256 CTA slots per sample
+    {
+        // 2-CTA clusters with weight-tile multicast: the N=256 layers are bound by L2->SMEM fill, 2/3 of it weights
+        const char* mce = getenv("GTTS_MC");
+        const int want = mce ? atoi(mce) : 1;
+        p.mc = (want && !halo_mode && g.Cout == 256 && g.nphase == 1 && g.w_batch_rows == 0 && p.num_tiles >= 2 &&
+                num_sms >= 2) ? 1 : 0;
+        if (p.mc) {
+            int gmax = num_sms & ~1;
+            if (gmax > 256) gmax = 256;
+            const int need = (p.num_tiles + 1) & ~1;
+            pl->grid = need < gmax ? need : gmax;
+        }
+    }
 
     bool ok = true;
     const uint64_t H = g.Hin, W = g.Win;
@@ -237,6 +266,8 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
         uint64_t str[1] = {K * 2};
         uint32_t box[2] = {64, (uint32_t)g.Cout};
         ok = ok && encode_map(&pl->mapW, weight, 2, dims, str, box);
+        uint32_t boxh[2] = {64, (uint32_t)g.Cout / 2};
+        ok = ok && encode_map(&pl->mapWh, weight, 2, dims, str, boxh);
     }
     if (!ok) { delete pl; return nullptr; }
     return pl;
@@ -253,7 +284,20 @@ int launch_variant(const TcConvPlan* pl, cudaStream_t stream) {
         GTTS_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    k<<<pl->grid, kThreads, pl->smem, stream>>>(pl->mapA0, pl->mapA1, pl->mapW, pl->p);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(pl->grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = pl->smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pl->p.mc ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GTTS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, pl->mapA0, pl->mapA1, pl->mapW, pl->mapWh, pl->p));
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

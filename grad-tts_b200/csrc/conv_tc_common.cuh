@@ -22,6 +22,7 @@ struct TcParams {
     int ntaps, nchunk0, nchunk1, Cin0;
     int stride2, w_batch_rows, num_tiles, a_bytes, stages;
     int halo_mode, b_slots, b_resident, halo_prefetch;   // conv_tc_halo.cu only
+    int mc;                                        // 1: 2-CTA cluster, weight tiles multicast (conv_tc.cu)
     int dbg;                                       // experiment switches (GTTS_CONV_DBG): 1 no MMA issue, 2 no epilogue work, 4 no A loads (halo), 8 no stats ring
     int8_t dy[4][9], dx[4][9];
     int wrow[4][9];
@@ -72,6 +73,13 @@ template <int N>
 __device__ __forceinline__ constexpr uint32_t make_idesc() {
     // kind::f16: D=f32 (bit 4), A=bf16 (bit 7), B=bf16 (bit 10), K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// Number of tile iterations of this CTA.  With weight multicast both CTAs of a pair must run the same count, so the
+// count is taken from the pair's first CTA; the odd one may then get a dummy tile (tile >= num_tiles).
+__device__ __forceinline__ int tc_num_iters(const TcParams& p) {
+    const int G = (int)gridDim.x, bx = p.mc ? ((int)blockIdx.x & ~1) : (int)blockIdx.x;
+    return p.num_tiles > bx ? (p.num_tiles - bx + G - 1) / G : 0;
 }
 
 // Tile walker: decodes tile = blockIdx.x + it*gridDim.x into (tw, th, ph, b) incrementally (no per-tile divisions).
@@ -126,7 +134,7 @@ template <int N>
 __device__ __forceinline__ uint32_t tc_prologue(const TcParams& p, const TcShared& sh, int nfull, int nfullb, int tid,
                                                 int warp, int lane) {
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < nfull; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }
+        for (int s = 0; s < nfull; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], p.mc ? 2 : 1); }
         for (int s = 0; s < nfullb; ++s) { mbar_init(&sh.fullb[s], 1); mbar_init(&sh.emptyb[s], 1); }
         for (int i = 0; i < acc_bufs<N>(); ++i) { mbar_init(&sh.tfull[i], 1); mbar_init(&sh.tempty[i], 256); }
         for (int i = 0; i < kStatSlots; ++i) { mbar_init(&sh.sfull[i], 8); mbar_init(&sh.sempty[i], 1); }
@@ -138,6 +146,7 @@ __device__ __forceinline__ uint32_t tc_prologue(const TcParams& p, const TcShare
     for (int i = tid; i < N; i += kThreads) sh.s_bias[i] = p.e.bias ? p.e.bias[i] : 0.f;
     tc_fence_before();
     __syncthreads();
+    if (p.mc) cluster_sync();                      // the peer's barriers are initialised before anything targets them
     tc_fence_after();
     return *sh.tmem_slot;
 }
@@ -154,20 +163,23 @@ __device__ __forceinline__ void tc_stats_loop(const TcParams& p, const TcShared&
     if (kStats && !(p.dbg & 8)) {
         const ConvEpilogue& e = p.e;
         const int G = (int)gridDim.x;
-        int it = 0, cur_b = -1;
+        int cur_b = -1;
         float acc = 0.f;
         // value k (0..7 sums, 8..15 sums of squares) of group g = k & 7 lives in column half g >> 2
         const int g = lane & 7, which = (lane >> 3) & 1, half = g >> 2, idx = which * 4 + (g & 3);
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += G, ++it) {
+        const int n_it = tc_num_iters(p);
+        for (int it = 0; it < n_it; ++it) {
+            const int tile = (int)blockIdx.x + it * G;
             const int slot = it % kStatSlots;
-            const int b = tile / tiles_per_phase;
+            const bool dummy = tile >= p.num_tiles;
+            const int b = dummy ? cur_b : tile / tiles_per_phase;
             if (b != cur_b) {
                 if (cur_b >= 0 && lane < 16) e.gn_partials[((size_t)cur_b * G + blockIdx.x) * 16 + lane] = acc;
                 cur_b = b;
                 acc = 0.f;
             }
             mbar_wait(&sfull[slot], (uint32_t)(it / kStatSlots) & 1u);
-            if (lane < 16) {
+            if (lane < 16 && !dummy) {
                 const float* r = s_ring + (slot * 8 + half * 4) * 8 + idx;
                 acc += (r[0] + r[8]) + (r[16] + r[24]);
             }
@@ -199,11 +211,12 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
     TileWalk tw;
     const int G = (int)gridDim.x;
     tw.init(p, (int)blockIdx.x + grp * G, 2 * G);
-    for (int it = grp; tw.tile < p.num_tiles; it += 2, tw.advance(2 * G)) {
+    const int n_it = tc_num_iters(p);
+    for (int it = grp; it < n_it; it += 2, tw.advance(2 * G)) {
         const int buf = it % kBufs;
         const int b = tw.b, ph = tw.ph;
         const int j = tw.th * p.bh + hl, i = tw.tw * p.bw + wl;
-        const bool valid = row_in_tile && (j < p.Hg) && (i < p.Wg);
+        const bool valid = row_in_tile && (j < p.Hg) && (i < p.Wg) && (tw.tile < p.num_tiles);
         const bool all_valid = __all_sync(0xffffffffu, valid);
         const int oh = j * p.out_step + p.oy[ph], ow = i * p.out_step + p.ox[ph];
         const size_t opix = valid ? ((size_t)b * p.Hout + oh) * p.Wout + ow : 0;
@@ -313,6 +326,7 @@ __device__ __forceinline__ void tc_teardown(const TcParams& p, const TcShared& s
     if (kStats) __threadfence();
     tc_fence_before();
     __syncthreads();
+    if (p.mc) cluster_sync();                      // nobody leaves while the peer may still multicast into it
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, acc_bufs<N>() * N);
@@ -376,7 +390,7 @@ __device__ __forceinline__ void tc_teardown(const TcParams& p, const TcShared& s
 }  // namespace tc
 
 struct TcConvPlan {
-    CUtensorMap mapA0, mapA1, mapW;
+    CUtensorMap mapA0, mapA1, mapW, mapWh;
     tc::TcParams p;
     int N, grid;
     size_t smem;

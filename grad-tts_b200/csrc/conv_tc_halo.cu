@@ -123,7 +123,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         for (int t = 0; t < 9; ++t) tap_off[t] = (uint64_t)((((t / 3) * pw + (t % 3)) * 128) >> 4);
         int sa = 0, sb = 0, it = 0;
         uint32_t pha = 0, phb = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int n_it = tc_num_iters(p);
+        for (it = 0; it < n_it; ++it) {
             const int buf = it % acc_bufs<N>();
             mbar_wait(&sh.tempty[buf], ((uint32_t)(it / acc_bufs<N>()) & 1u) ^ 1u);
             tc_fence_after();

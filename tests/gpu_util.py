@@ -103,6 +103,8 @@ CONV_CASES = [
     ("3x3_64_128_odd", dict(kind=0, B=1, H=40, W=22, Cin0=64, Cin1=0, Cout=128)),
     ("3x3_256_256_l2", dict(kind=0, B=2, H=20, W=10, Cin0=256, Cin1=0, Cout=256)),
     ("3x3_cat_512_128", dict(kind=0, B=1, H=20, W=12, Cin0=256, Cin1=256, Cout=128)),
+    ("3x3_128_256_oddtiles", dict(kind=0, B=1, H=20, W=30, Cin0=128, Cin1=0, Cout=256)),
+    ("3x3_256_256_big", dict(kind=0, B=3, H=20, W=108, Cin0=256, Cin1=0, Cout=256)),
     ("1x1_kv_64_256", dict(kind=1, B=2, H=80, W=16, Cin0=64, Cin1=0, Cout=256, bias=False)),
     ("1x1_cat_256_64", dict(kind=1, B=1, H=40, W=12, Cin0=128, Cin1=128, Cout=64)),
     ("1x1_persample_res_mask", dict(kind=1, B=3, H=20, W=12, Cin0=128, Cin1=0, Cout=128, residual=True, mask=True,
