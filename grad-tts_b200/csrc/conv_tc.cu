@@ -124,10 +124,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 if (leader) {
                     const uint64_t adesc = a_desc0 + (uint64_t)stage * stage_step;
                     const uint64_t bdesc = b_desc0 + (uint64_t)stage * stage_step;
+                    if (!(p.dbg & 1)) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)                     // 4 x (K = 16 bf16 = 32 bytes)
-                        tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
-                                   (uint32_t)((kb | k) != 0));
+                        for (int k = 0; k < 4; ++k)                 // 4 x (K = 16 bf16 = 32 bytes)
+                            tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
+                                       (uint32_t)((kb | k) != 0));
+                    }
                     if (mc) tc_commit_mc(&empty[stage], (uint16_t)3);   // frees the slot in both CTAs of the pair
                     else tc_commit(&empty[stage]);                  // smem slot free when these MMAs retire
                     if (kb == nkb - 1) tc_commit(&sh.tfull[buf]);   // accumulator complete
@@ -230,7 +232,7 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
     {
         // 2-CTA clusters with weight-tile multicast: the N=256 layers are bound by L2->SMEM fill, 2/3 of it weights
         const char* mce = getenv("GTTS_MC");
-        const int want = mce ? atoi(mce) : 1;
+        const int want = mce ? atoi(mce) : 0;      // measured: no gain on B200 (these layers are MMA-, not fill-bound)
         p.mc = (want && !halo_mode && g.Cout == 256 && g.nphase == 1 && g.w_batch_rows == 0 && p.num_tiles >= 2 &&
                 num_sms >= 2) ? 1 : 0;
         if (p.mc) {
