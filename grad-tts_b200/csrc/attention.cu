@@ -22,6 +22,8 @@ constexpr int kKPitch = 36;      // floats per k row in smem (16-byte aligned ro
 template <typename T, bool kStrict>
 __global__ void __launch_bounds__(256)
 attn_ctx_kernel(AttnCtxArgs a) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) float ks[kSub * kKPitch];
     __shared__ __align__(16) float vs[kSub * 32];
     __shared__ float s_m[32], s_scale[32];
@@ -156,6 +158,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 __global__ void __launch_bounds__(128)
 attn_ctx_tc_kernel(AttnCtxArgs a) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) __nv_bfloat16 sm_all[];          // two sub-tile buffers (cp.async double buffering)
     const int tid = threadIdx.x, head = tid >> 5, lane = tid & 31;
     const int chunk = blockIdx.x, b = blockIdx.y;
@@ -275,6 +279,8 @@ attn_ctx_tc_kernel(AttnCtxArgs a) {
 template <bool kStrict>
 __global__ void __launch_bounds__(256)
 attn_merge_kernel(AttnCtxArgs a) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_m[32], s_scale[32], s_part[8][32], s_w[64][32];
     const int tid = threadIdx.x, head = blockIdx.x, b = blockIdx.y;
     const int d = tid & 31, cg = tid >> 5;
@@ -321,6 +327,8 @@ template <typename WT>
 __global__ void __launch_bounds__(256)
 attn_fold_kernel(const float* __restrict__ ctxn, const float* __restrict__ wout, const float* __restrict__ wq,
                  float g, WT* __restrict__ mb, int C) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) float buf[128 * 64];                    // phase 1: cs + ws ; phase 2: Wq slice
     __shared__ float P[16 * 129];
     float* cs = buf;                                                 // [4*32][33]
@@ -378,8 +386,8 @@ int attn_ctx(ActKind act, const AttnCtxArgs& a, bool strict, cudaStream_t s) {
     GTTS_REQUIRE(a.chunk_len % kSub == 0 && a.chunks >= 1, "attn_ctx: bad chunk plan");
     if (act == ACT_F32) {
         dim3 grid(a.chunks, 4, a.B);
-        if (strict) attn_ctx_kernel<float, true><<<grid, 256, 0, s>>>(a);
-        else        attn_ctx_kernel<float, false><<<grid, 256, 0, s>>>(a);
+        if (strict) GTTS_CHECK_CUDA(launch_pdl(attn_ctx_kernel<float, true>, grid, dim3(256), 0, s, 1, a));
+        else        GTTS_CHECK_CUDA(launch_pdl(attn_ctx_kernel<float, false>, grid, dim3(256), 0, s, 1, a));
     } else {
         dim3 grid(a.chunks, a.B);
         const int smem = 2 * kTcSub * kTcPitch * 2;
@@ -388,7 +396,7 @@ int attn_ctx(ActKind act, const AttnCtxArgs& a, bool strict, cudaStream_t s) {
             GTTS_CHECK_CUDA(cudaFuncSetAttribute(attn_ctx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             attr_set = true;
         }
-        attn_ctx_tc_kernel<<<grid, 128, smem, s>>>(a);
+        GTTS_CHECK_CUDA(launch_pdl(attn_ctx_tc_kernel, grid, dim3(128), (size_t)smem, s, 1, a));
     }
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -397,8 +405,8 @@ int attn_ctx(ActKind act, const AttnCtxArgs& a, bool strict, cudaStream_t s) {
 int attn_merge(const AttnCtxArgs& a, bool strict, cudaStream_t s) {
     GTTS_REQUIRE(a.chunks <= 64, "attn_merge: too many chunks");
     dim3 grid(4, a.B);
-    if (strict) attn_merge_kernel<true><<<grid, 256, 0, s>>>(a);
-    else        attn_merge_kernel<false><<<grid, 256, 0, s>>>(a);
+    if (strict) GTTS_CHECK_CUDA(launch_pdl(attn_merge_kernel<true>, grid, dim3(256), 0, s, 1, a));
+    else        GTTS_CHECK_CUDA(launch_pdl(attn_merge_kernel<false>, grid, dim3(256), 0, s, 1, a));
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -407,8 +415,8 @@ int attn_fold(ActKind wkind, const float* ctxn, const float* wout, const float* 
               int C, cudaStream_t s) {
     GTTS_REQUIRE(C % 64 == 0 && C <= 256, "attn_fold: C must be a multiple of 64 and <= 256");
     dim3 grid(C / 16, C / 64, B);
-    if (wkind == ACT_F32) attn_fold_kernel<float><<<grid, 256, 0, s>>>(ctxn, wout, wq, g, (float*)mb_out, C);
-    else attn_fold_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(ctxn, wout, wq, g, (__nv_bfloat16*)mb_out, C);
+    if (wkind == ACT_F32) GTTS_CHECK_CUDA(launch_pdl(attn_fold_kernel<float>, grid, dim3(256), 0, s, 1, ctxn, wout, wq, g, (float*)mb_out, C));
+    else GTTS_CHECK_CUDA(launch_pdl(attn_fold_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, 1, ctxn, wout, wq, g, (__nv_bfloat16*)mb_out, C));
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <string.h>
 
 namespace gtts {
 
@@ -27,6 +28,40 @@ void set_error(const std::string& msg);          // defined in capi.cu
             return 2;                                                                          \
         }                                                                                      \
     } while (0)
+
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel of the Euler step is launched with programmaticStreamSerialization: it may start while its
+// predecessor drains, runs its prologue, and blocks in pdl_wait() until the predecessor grid has completed and its
+// memory is visible.  pdl_trigger() at kernel entry lets the successor be scheduled as soon as resources free up.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();                               // capi.cu (env GTTS_PDL, default on)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              int cluster_x, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    ++n;
+    if (cluster_x > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster_x;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---------------------------------------------------------------- activation element types
 template <typename T> struct Act;

@@ -286,20 +286,8 @@ int launch_variant(const TcConvPlan* pl, cudaStream_t stream) {
         GTTS_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(pl->grid);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = pl->smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = pl->p.mc ? 2 : 1;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    GTTS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, pl->mapA0, pl->mapA1, pl->mapW, pl->mapWh, pl->p));
+    GTTS_CHECK_CUDA(launch_pdl(k, dim3(pl->grid), dim3(kThreads), pl->smem, stream, pl->p.mc ? 2 : 1, pl->mapA0, pl->mapA1,
+                               pl->mapW, pl->mapWh, pl->p));
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -133,6 +133,7 @@ __device__ __forceinline__ float warp_reduce8(const float (&v)[8], int lane) {
 template <int N>
 __device__ __forceinline__ uint32_t tc_prologue(const TcParams& p, const TcShared& sh, int nfull, int nfullb, int tid,
                                                 int warp, int lane) {
+    pdl_trigger();
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < nfull; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], p.mc ? 2 : 1); }
         for (int s = 0; s < nfullb; ++s) { mbar_init(&sh.fullb[s], 1); mbar_init(&sh.emptyb[s], 1); }
@@ -148,6 +149,7 @@ __device__ __forceinline__ uint32_t tc_prologue(const TcParams& p, const TcShare
     __syncthreads();
     if (p.mc) cluster_sync();                      // the peer's barriers are initialised before anything targets them
     tc_fence_after();
+    pdl_wait();                                    // everything above overlapped the predecessor's tail
     return *sh.tmem_slot;
 }
 

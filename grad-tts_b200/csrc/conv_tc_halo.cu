@@ -194,7 +194,7 @@ int launch_halo(const TcConvPlan* pl, cudaStream_t stream) {
         GTTS_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    k<<<pl->grid, kThreads, pl->smem, stream>>>(pl->mapA0, pl->mapA1, pl->mapW, pl->p);
+    GTTS_CHECK_CUDA(launch_pdl(k, dim3(pl->grid), dim3(kThreads), pl->smem, stream, 1, pl->mapA0, pl->mapA1, pl->mapW, pl->p));
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -28,7 +28,9 @@ __global__ void init_xt_kernel(const float* __restrict__ z, const float* __restr
     xt[i] = __fmul_rn(z[i], mask[(size_t)b * W + w]);       // xt = z * mask       (:257)
 }
 
-__global__ void advance_step_kernel(int* step) { *step += 1; }
+__global__ void advance_step_kernel(int* step) {
+    pdl_trigger();
+    pdl_wait(); *step += 1; }
 
 // ------------------------------------------------------------------------------------------------ spk MLP
 template <bool kStrict>
@@ -55,6 +57,8 @@ __global__ void spk_mlp_kernel(const float* __restrict__ spk, const float* __res
 template <bool kStrict>
 __global__ void temb_kernel(TembWeights w, const float* __restrict__ t, const int* __restrict__ step, int t_is_table,
                             float pe_scale, float* __restrict__ tb) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float e[64], h1[256], part[256], h2[64];
     const int tid = threadIdx.x, b = blockIdx.y;
     const float tv = t_is_table ? t[*step] : t[b];
@@ -99,82 +103,109 @@ __global__ void temb_kernel(TembWeights w, const float* __restrict__ t, const in
 }
 
 // ------------------------------------------------------------------------------------------------ first conv
-// Block.conv of downs.0.0.block1 on stack([mu, x, (s)]) * mask  (:181-184, 52-57).  One thread per pixel.
+// Block.conv of downs.0.0.block1 on stack([mu, x, (s)]) * mask  (:181-184, 52-57), straight from the fp32 planes.
+// Thread = 4 consecutive pixels x 16 output channels (4 threads cover the 64 channels of a pixel quad), so every
+// 16-byte weight read from shared memory feeds 16 FMAs.  A CTA walks kFcTiles tiles of 128 pixels of one sample and
+// publishes ONE GroupNorm partial (one fence + ticket per CTA).
+constexpr int kFcTiles = 8;
+
 template <typename T, int CIN>
 __global__ void __launch_bounds__(128)
 first_conv_kernel(FirstConvArgs a) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __align__(16) float wT[CIN * 9 * 64];
     __shared__ float sb[64];
     __shared__ float s_part[4][16];
     __shared__ float s_tile[16];
     __shared__ double s_red[8 * 16];
     __shared__ int s_flag;
-    const int tid = threadIdx.x, b = blockIdx.y;
+    const int tid = threadIdx.x, b = blockIdx.y, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < CIN * 9 * 64; i += 128) wT[i] = a.w[i];
     if (tid < 64) sb[tid] = a.bias[tid];
     __syncthreads();
 
-    const int H = a.H, W = a.W;
-    const int p = blockIdx.x * 128 + tid;                 // pixel within the sample
-    const bool valid = p < H * W;
-    const int h = valid ? p / W : 0, w = valid ? p % W : 0;
-    float acc[64];
+    const int H = a.H, W = a.W, HW = H * W;
+    const int q = tid & 3, quad = tid >> 2;               // channels q*16..q*16+15 ; pixel quad within the tile
+    const float* mrow = a.mask + (size_t)b * W;
+    float st[4] = {0.f, 0.f, 0.f, 0.f};                   // sums of my two groups, then their sums of squares
+
+    for (int t = 0; t < kFcTiles; ++t) {
+        const int p0 = (blockIdx.x * kFcTiles + t) * 128 + quad * 4;      // first pixel of my quad (W % 4 == 0)
+        if (p0 >= HW) break;                               // uniform per quad; later tiles are out of range too
+        const int h = p0 / W, w0 = p0 - h * W;
+        float acc[4][16];
 #pragma unroll
-    for (int c = 0; c < 64; ++c) acc[c] = sb[c];
-    if (valid) {
-        const float* mrow = a.mask + (size_t)b * W;
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[j][c] = sb[q * 16 + c];
+        float mk[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int ww = w0 - 1 + i;
+            mk[i] = (ww >= 0 && ww < W) ? mrow[ww] : 0.f;
+        }
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int hh = h + ky - 1;
             if (hh < 0 || hh >= H) continue;
+            float in[CIN][6];
+            const size_t rowoff = ((size_t)b * H + hh) * W;
+            const float sv = CIN == 3 ? a.splane[b * H + hh] : 0.f;
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int ww = w + kx - 1;
-                if (ww < 0 || ww >= W) continue;
-                const float m = mrow[ww];
-                const size_t off = ((size_t)b * H + hh) * W + ww;
-                float in[CIN];
-                in[0] = a.mu[off] * m;
-                in[1] = a.x[off] * m;
-                if (CIN == 3) in[CIN - 1] = a.splane[b * H + hh] * m;
+            for (int i = 0; i < 6; ++i) {
+                const int ww = w0 - 1 + i;
+                const bool inb = ww >= 0 && ww < W;
+                in[0][i] = inb ? a.mu[rowoff + ww] * mk[i] : 0.f;
+                in[1][i] = inb ? a.x[rowoff + ww] * mk[i] : 0.f;
+                if (CIN == 3) in[CIN - 1][i] = sv * mk[i];
+            }
 #pragma unroll
-                for (int ci = 0; ci < CIN; ++ci) {
-                    const float4* wr = reinterpret_cast<const float4*>(&wT[((ci * 3 + ky) * 3 + kx) * 64]);
+            for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
-                    for (int c4 = 0; c4 < 16; ++c4) {
-                        float4 wv = wr[c4];
-                        acc[4 * c4 + 0] = fmaf(in[ci], wv.x, acc[4 * c4 + 0]);
-                        acc[4 * c4 + 1] = fmaf(in[ci], wv.y, acc[4 * c4 + 1]);
-                        acc[4 * c4 + 2] = fmaf(in[ci], wv.z, acc[4 * c4 + 2]);
-                        acc[4 * c4 + 3] = fmaf(in[ci], wv.w, acc[4 * c4 + 3]);
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4* wr = reinterpret_cast<const float4*>(&wT[((ci * 3 + ky) * 3 + kx) * 64 + q * 16]);
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 wv = wr[c4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float xin = in[ci][j + kx];
+                            acc[j][4 * c4 + 0] = fmaf(xin, wv.x, acc[j][4 * c4 + 0]);
+                            acc[j][4 * c4 + 1] = fmaf(xin, wv.y, acc[j][4 * c4 + 1]);
+                            acc[j][4 * c4 + 2] = fmaf(xin, wv.z, acc[j][4 * c4 + 2]);
+                            acc[j][4 * c4 + 3] = fmaf(xin, wv.w, acc[j][4 * c4 + 3]);
+                        }
                     }
                 }
-            }
         }
-        T* o = reinterpret_cast<T*>(a.raw) + ((size_t)b * H * W + p) * 64;
+        T* o = reinterpret_cast<T*>(a.raw) + ((size_t)b * HW + p0) * 64 + q * 16;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            float v[8];
+        for (int j = 0; j < 4; ++j) {
+            float v0[8], v1[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = acc[g * 8 + j];
-            Act<T>::store8(o + g * 8, v);
+            for (int c = 0; c < 8; ++c) { v0[c] = acc[j][c]; v1[c] = acc[j][8 + c]; }
+            Act<T>::store8(o + (size_t)j * 64, v0);
+            Act<T>::store8(o + (size_t)j * 64 + 8, v1);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                st[0] += v0[c]; st[2] = fmaf(v0[c], v0[c], st[2]);
+                st[1] += v1[c]; st[3] = fmaf(v1[c], v1[c], st[3]);
+            }
         }
     }
     // GroupNorm statistics (8 groups of 8 channels) over the unmasked conv output   (:53)
-    float st[16];
+    // reduce over the 8 quads of the warp that share q (lanes q, q+4, ...), fixed order
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-        float s = 0.f, q = 0.f;
-        if (valid) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { float v = acc[g * 8 + j]; s += v; q += v * v; }
-        }
-        st[g] = warp_sum(s);
-        st[8 + g] = warp_sum(q);
+    for (int k = 0; k < 4; ++k) {
+        st[k] += __shfl_xor_sync(0xffffffffu, st[k], 4);
+        st[k] += __shfl_xor_sync(0xffffffffu, st[k], 8);
+        st[k] += __shfl_xor_sync(0xffffffffu, st[k], 16);
     }
-    if ((tid & 31) == 0) {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) s_part[tid >> 5][k] = st[k];
+    if (lane < 4) {
+        // lane = q: groups 2q, 2q+1 -> slots [g] (sum) and [8+g] (sum of squares)
+        s_part[warp][2 * lane] = st[0];     s_part[warp][2 * lane + 1] = st[1];
+        s_part[warp][8 + 2 * lane] = st[2]; s_part[warp][8 + 2 * lane + 1] = st[3];
     }
     __syncthreads();
     if (tid < 16) s_tile[tid] = (s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]);
@@ -193,6 +224,8 @@ constexpr int kGnIter = 4;
 template <typename T, bool kStrict, bool kHasRes, bool kHasTb, bool kFirstRes>
 __global__ void __launch_bounds__(256, 2)
 gn_apply_kernel(GnApplyArgs a) {
+    pdl_trigger();
+    pdl_wait();
     typedef typename Act<T>::Packed Packed;
     const int C8 = a.C >> 3;
     const int b = blockIdx.y;
@@ -285,6 +318,8 @@ constexpr int kGfVec = 4;
 template <bool kHasRes, bool kHasTb, bool kFirstRes>
 __global__ void __launch_bounds__(256, 3)
 gn_apply_fast_kernel(GnApplyArgs a) {
+    pdl_trigger();
+    pdl_wait();
     typedef __nv_bfloat16 T;
     const int C8 = a.C >> 3;
     const int b = blockIdx.y;
@@ -378,6 +413,8 @@ constexpr int kEuPix = 4;
 template <typename T, bool kStrict>
 __global__ void __launch_bounds__(256, 3)
 euler_kernel(EulerArgs a) {
+    pdl_trigger();
+    pdl_wait();
     const size_t npix = (size_t)a.B * a.H * a.W;
     const int sub = threadIdx.x & 7;
     const size_t pbase = ((size_t)blockIdx.x * 32 + (threadIdx.x >> 3)) * kEuPix;   // 32 lane groups per CTA
@@ -529,7 +566,7 @@ int init_xt(const float* z, const float* mask, float* xt, int B, int H, int W, c
 }
 
 int advance_step(int* step, cudaStream_t s) {
-    advance_step_kernel<<<1, 1, 0, s>>>(step);
+    GTTS_CHECK_CUDA(launch_pdl(advance_step_kernel, dim3(1), dim3(1), 0, s, 1, step));
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -546,23 +583,24 @@ int spk_mlp(const float* spk, const float* w0t, const float* b0, const float* w2
 int temb_bias(const TembWeights& w, const float* t, const int* step, int t_is_table, float pe_scale, float* tb,
               int nb, bool strict, cudaStream_t s) {
     dim3 grid(14, nb);
-    if (strict) temb_kernel<true><<<grid, 256, 0, s>>>(w, t, step, t_is_table, pe_scale, tb);
-    else        temb_kernel<false><<<grid, 256, 0, s>>>(w, t, step, t_is_table, pe_scale, tb);
+    if (strict) GTTS_CHECK_CUDA(launch_pdl(temb_kernel<true>, grid, dim3(256), 0, s, 1, w, t, step, t_is_table, pe_scale, tb));
+    else        GTTS_CHECK_CUDA(launch_pdl(temb_kernel<false>, grid, dim3(256), 0, s, 1, w, t, step, t_is_table, pe_scale, tb));
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-size_t first_conv_partials_slots(int H, int W) { return (size_t)(H * W + 127) / 128; }
+size_t first_conv_partials_slots(int H, int W) { return (size_t)((H * W + 127) / 128 + kFcTiles - 1) / kFcTiles; }
 
 int first_conv(ActKind act, const FirstConvArgs& a, cudaStream_t s) {
     GTTS_REQUIRE(a.cin == 2 || a.cin == 3, "first_conv: cin must be 2 or 3");
+    GTTS_REQUIRE(a.W % 4 == 0, "first_conv: W must be a multiple of 4");
     dim3 grid((unsigned int)first_conv_partials_slots(a.H, a.W), a.B);
     if (act == ACT_F32) {
-        if (a.cin == 2) first_conv_kernel<float, 2><<<grid, 128, 0, s>>>(a);
-        else            first_conv_kernel<float, 3><<<grid, 128, 0, s>>>(a);
+        if (a.cin == 2) GTTS_CHECK_CUDA(launch_pdl(first_conv_kernel<float, 2>, grid, dim3(128), 0, s, 1, a));
+        else            GTTS_CHECK_CUDA(launch_pdl(first_conv_kernel<float, 3>, grid, dim3(128), 0, s, 1, a));
     } else {
-        if (a.cin == 2) first_conv_kernel<__nv_bfloat16, 2><<<grid, 128, 0, s>>>(a);
-        else            first_conv_kernel<__nv_bfloat16, 3><<<grid, 128, 0, s>>>(a);
+        if (a.cin == 2) GTTS_CHECK_CUDA(launch_pdl(first_conv_kernel<__nv_bfloat16, 2>, grid, dim3(128), 0, s, 1, a));
+        else            GTTS_CHECK_CUDA(launch_pdl(first_conv_kernel<__nv_bfloat16, 3>, grid, dim3(128), 0, s, 1, a));
     }
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -574,11 +612,11 @@ int gn_apply_dispatch(const GnApplyArgs& a, cudaStream_t s) {
     const size_t per_sample = (size_t)a.H * a.W * (a.C / 8);
     dim3 grid((unsigned int)((per_sample + 256 * kGnVec * kGnIter - 1) / (256 * kGnVec * kGnIter)), a.B);
     const bool res = a.residual != nullptr, tb = a.tbias != nullptr, fr = a.fr_w != nullptr;
-    if (fr)             gn_apply_kernel<T, kStrict, false, false, true><<<grid, 256, 0, s>>>(a);
-    else if (res && tb) gn_apply_kernel<T, kStrict, true, true, false><<<grid, 256, 0, s>>>(a);
-    else if (res)       gn_apply_kernel<T, kStrict, true, false, false><<<grid, 256, 0, s>>>(a);
-    else if (tb)        gn_apply_kernel<T, kStrict, false, true, false><<<grid, 256, 0, s>>>(a);
-    else                gn_apply_kernel<T, kStrict, false, false, false><<<grid, 256, 0, s>>>(a);
+    if (fr)             GTTS_CHECK_CUDA(launch_pdl(gn_apply_kernel<T, kStrict, false, false, true>, grid, dim3(256), 0, s, 1, a));
+    else if (res && tb) GTTS_CHECK_CUDA(launch_pdl(gn_apply_kernel<T, kStrict, true, true, false>, grid, dim3(256), 0, s, 1, a));
+    else if (res)       GTTS_CHECK_CUDA(launch_pdl(gn_apply_kernel<T, kStrict, true, false, false>, grid, dim3(256), 0, s, 1, a));
+    else if (tb)        GTTS_CHECK_CUDA(launch_pdl(gn_apply_kernel<T, kStrict, false, true, false>, grid, dim3(256), 0, s, 1, a));
+    else                GTTS_CHECK_CUDA(launch_pdl(gn_apply_kernel<T, kStrict, false, false, false>, grid, dim3(256), 0, s, 1, a));
     return 0;
 }
 }  // namespace
@@ -588,7 +626,7 @@ template <bool kHasRes, bool kHasTb, bool kFirstRes>
 int gn_apply_fast_launch(const GnApplyArgs& a, cudaStream_t s) {
     const size_t per_sample = (size_t)a.H * a.W * (a.C / 8);
     dim3 grid((unsigned int)((per_sample + 256 * kGfVec - 1) / (256 * kGfVec)), a.B);
-    gn_apply_fast_kernel<kHasRes, kHasTb, kFirstRes><<<grid, 256, 0, s>>>(a);
+    GTTS_CHECK_CUDA(launch_pdl(gn_apply_fast_kernel<kHasRes, kHasTb, kFirstRes>, grid, dim3(256), 0, s, 1, a));
     return 0;
 }
 }  // namespace
@@ -623,11 +661,11 @@ int euler_step(ActKind act, const EulerArgs& a, bool strict, cudaStream_t s) {
     const size_t npix = (size_t)a.B * a.H * a.W;
     unsigned int g = nblk(npix, 32 * kEuPix);
     if (act == ACT_F32) {
-        if (strict) euler_kernel<float, true><<<g, 256, 0, s>>>(a);
-        else        euler_kernel<float, false><<<g, 256, 0, s>>>(a);
+        if (strict) GTTS_CHECK_CUDA(launch_pdl(euler_kernel<float, true>, dim3(g), dim3(256), 0, s, 1, a));
+        else        GTTS_CHECK_CUDA(launch_pdl(euler_kernel<float, false>, dim3(g), dim3(256), 0, s, 1, a));
     } else {
-        if (strict) euler_kernel<__nv_bfloat16, true><<<g, 256, 0, s>>>(a);
-        else        euler_kernel<__nv_bfloat16, false><<<g, 256, 0, s>>>(a);
+        if (strict) GTTS_CHECK_CUDA(launch_pdl(euler_kernel<__nv_bfloat16, true>, dim3(g), dim3(256), 0, s, 1, a));
+        else        GTTS_CHECK_CUDA(launch_pdl(euler_kernel<__nv_bfloat16, false>, dim3(g), dim3(256), 0, s, 1, a));
     }
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
