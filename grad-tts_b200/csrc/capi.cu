@@ -14,7 +14,8 @@ static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
 bool pdl_enabled() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("GTTS_PDL"); v = e ? (atoi(e) != 0) : 0;      // measured on B200: no gain (-2 %), so off unless GTTS_PDL=1 }
+    // measured on B200: no gain (-2 %), so off unless GTTS_PDL=1
+    if (v < 0) { const char* e = getenv("GTTS_PDL"); v = e ? (atoi(e) != 0) : 0; }
     return v != 0;
 }
 }  // namespace gtts
