@@ -267,7 +267,7 @@ def main():
                 "avg_launch_ms": 1e3 * t_conv / len(conv), "conv_share_of_step": t_conv / t_all,
                 "chunk_batch": rep["B"],
                 "non_conv_ms": {k: sum(o["ms"] for o in rep["ops"] if o["name"].startswith(k))
-                                for k in ("gn_apply", "attn_ctx", "attn_merge", "attn_fold", "first_conv", "euler", "temb")}}
+                                for k in ("gn_apply", "attn_xk", "attn_ctx", "attn_merge", "attn_fold", "first_conv", "euler", "temb")}}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

@@ -275,6 +275,230 @@ attn_ctx_tc_kernel(AttnCtxArgs a) {
             }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fused k-projection + context (C = 64 or 128): reads only x.
+//   k = Wk x is computed per 64-pixel sub-tile on the fly (never stored to HBM); v is never formed at all because
+//   ctx[d,e] = sum_n p[d,n] (Wv x_n)[e] = (S Wv^T)[d,e]  with  S[d,c] = sum_n p[d,n] x[n,c]   (128 x C per sample).
+// The kernel accumulates S with an online softmax over the pixels of its chunk and writes (m, l, S) partials;
+// attn_merge_s finishes ctx = (S / l) Wv^T per head.  Replaces the 1x1 kv conv (write-bound: 512 B/pixel) and the
+// kv read of attn_ctx_tc: HBM traffic per pixel drops from 128+512+512 bytes to 2C bytes.
+constexpr int kXkSub = 64;
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_ptr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(smem_ptr)));
+}
+
+template <int C>
+__global__ void __launch_bounds__(256)
+attn_xk_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ wk, float* __restrict__ partials,
+               int n, int chunks, int chunk_len) {
+    pdl_trigger();
+    pdl_wait();
+    constexpr int kXP = C + 8;                    // bf16 pitch of x / Wk rows (16-byte pad: conflict-free ldmatrix)
+    constexpr int kKP = 128 + 8;                  // bf16 pitch of the k/p tile
+    constexpr int kPart = 256 + 128 * C;          // floats per partial: m[128], l[128], S[128][C]
+    extern __shared__ __align__(16) __nv_bfloat16 xs_all[];
+    __nv_bfloat16* wks = xs_all;                                   // [128][kXP]
+    __nv_bfloat16* xs = wks + 128 * kXP;                           // [2][64][kXP]
+    __nv_bfloat16* kt = xs + 2 * kXkSub * kXP;                     // [64][kKP]
+    float* s_m = reinterpret_cast<float*>(kt + kXkSub * kKP);      // [128] running max
+    float* s_scale = s_m + 128;                                    // [128]
+    float* s_l = s_scale + 128;                                    // [128]
+    float* s_pmax = s_l + 128;                                     // [4][128] partial maxima / sums
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int chunk = blockIdx.x, b = blockIdx.y;
+    const int n0 = chunk * chunk_len, n1 = min(n, n0 + chunk_len);
+    const __nv_bfloat16* xb = x + (size_t)b * n * C;
+    const int g = lane >> 2, t = lane & 3, j = lane >> 3, r = lane & 7;
+
+    for (int i = tid; i < 128 * (C / 8); i += 256) {               // Wk -> smem (16-byte pieces)
+        const int row = i / (C / 8), c8 = i % (C / 8);
+        *reinterpret_cast<uint4*>(&wks[row * kXP + c8 * 8]) = __ldg(reinterpret_cast<const uint4*>(wk + (size_t)row * C + c8 * 8));
+    }
+    if (tid < 128) { s_m[tid] = -INFINITY; s_l[tid] = 0.f; }
+    auto fetch = [&](int p0, __nv_bfloat16* dst) {
+        for (int i = tid; i < kXkSub * (C / 8); i += 256) {
+            const int px = i / (C / 8), c8 = i % (C / 8), nn = p0 + px;
+            __nv_bfloat16* d = &dst[px * kXP + c8 * 8];
+            if (nn < n1) cp_async16(d, xb + (size_t)nn * C + c8 * 8);
+            else *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);      // x = 0 beyond the chunk
+        }
+        cp_async_commit();
+    };
+    float acc[C / 8][4];                                            // S rows 16*warp + {g, g+8}, all C columns
+#pragma unroll
+    for (int i = 0; i < C / 8; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
+
+    fetch(n0, xs);
+    int ib = 0;
+    for (int p0 = n0; p0 < n1; p0 += kXkSub, ib ^= 1) {
+        __nv_bfloat16* xt = xs + ib * (kXkSub * kXP);
+        if (p0 + kXkSub < n1) { fetch(p0 + kXkSub, xs + (ib ^ 1) * (kXkSub * kXP)); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();                                            // x tile (and, first time, Wk) visible to all
+        // ---- GEMM1: k[64 px][128] = x[64][C] . Wk^T ; warp -> 16 pixel rows x 64 k-channels
+        {
+            const int px0 = (warp & 3) * 16, nc0 = (warp >> 2) * 64;
+            float kc[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) kc[i][q] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < C / 16; ++ks) {
+                uint32_t af[4];
+                ldmatrix_x4(af, &xt[(px0 + (j & 1) * 8 + r) * kXP + ks * 16 + (j >> 1) * 8]);
+#pragma unroll
+                for (int np = 0; np < 4; ++np) {
+                    uint32_t bf[4];                                 // two n-tiles: (b0,b1) of n-tile 2np, then of 2np+1
+                    ldmatrix_x4(bf, &wks[(nc0 + np * 16 + (j >> 1) * 8 + r) * kXP + ks * 16 + (j & 1) * 8]);
+                    mma_bf16_16816(kc[2 * np], af, bf[0], bf[1]);
+                    mma_bf16_16816(kc[2 * np + 1], af, bf[2], bf[3]);
+                }
+            }
+            const int nvalid = n1 - p0;                             // pixels beyond the chunk get k = -inf
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int col = nc0 + i * 8 + 2 * t;
+                float v0 = kc[i][0], v1 = kc[i][1], v2 = kc[i][2], v3 = kc[i][3];
+                if (px0 + g >= nvalid) { v0 = -INFINITY; v1 = -INFINITY; }
+                if (px0 + g + 8 >= nvalid) { v2 = -INFINITY; v3 = -INFINITY; }
+                *reinterpret_cast<__nv_bfloat162*>(&kt[(px0 + g) * kKP + col]) = __floats2bfloat162_rn(v0, v1);
+                *reinterpret_cast<__nv_bfloat162*>(&kt[(px0 + g + 8) * kKP + col]) = __floats2bfloat162_rn(v2, v3);
+            }
+        }
+        __syncthreads();
+        // ---- column maxima: thread -> column pair cp, pixel quarter pq
+        const int cp = tid & 63, pq = tid >> 6;
+        uint32_t* kw = reinterpret_cast<uint32_t*>(kt) + cp;        // word of columns 2cp, 2cp+1, pixel 0
+        constexpr int kWP = kKP / 2;
+        {
+            float x0 = -INFINITY, x1 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint32_t w = kw[(pq * 16 + i) * kWP];
+                x0 = fmaxf(x0, __uint_as_float(w << 16));
+                x1 = fmaxf(x1, __uint_as_float(w & 0xffff0000u));
+            }
+            s_pmax[pq * 128 + 2 * cp] = x0;
+            s_pmax[pq * 128 + 2 * cp + 1] = x1;
+        }
+        __syncthreads();
+        if (tid < 128) {
+            const float mx = fmaxf(fmaxf(s_pmax[tid], s_pmax[128 + tid]), fmaxf(s_pmax[256 + tid], s_pmax[384 + tid]));
+            const float mo = s_m[tid], mn = fmaxf(mo, mx);
+            s_scale[tid] = __expf(mo - mn);                         // exp(-inf) = 0 on the first sub-tile
+            s_m[tid] = mn;
+        }
+        __syncthreads();
+        // ---- p = exp(k - m) in place (bf16), partial row sums of the rounded values
+        {
+            const float m0 = s_m[2 * cp], m1 = s_m[2 * cp + 1];
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                uint32_t* wp = kw + (pq * 16 + i) * kWP;
+                const uint32_t w = *wp;
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(__expf(__uint_as_float(w << 16) - m0),
+                                                          __expf(__uint_as_float(w & 0xffff0000u) - m1));
+                const uint32_t pw = *reinterpret_cast<uint32_t*>(&h2);
+                *wp = pw;
+                s0 += __uint_as_float(pw << 16);
+                s1 += __uint_as_float(pw & 0xffff0000u);
+            }
+            s_pmax[pq * 128 + 2 * cp] = s0;
+            s_pmax[pq * 128 + 2 * cp + 1] = s1;
+        }
+        __syncthreads();
+        if (tid < 128)
+            s_l[tid] = fmaf(s_l[tid], s_scale[tid], (s_pmax[tid] + s_pmax[128 + tid]) + (s_pmax[256 + tid] + s_pmax[384 + tid]));
+        // ---- GEMM2: S[128 d][C] += P^T[128][64 px] . x[64 px][C] ; warp -> d rows 16*warp .. +15
+        {
+            const float f0 = s_scale[warp * 16 + g], f1 = s_scale[warp * 16 + g + 8];
+#pragma unroll
+            for (int i = 0; i < C / 8; ++i) { acc[i][0] *= f0; acc[i][1] *= f0; acc[i][2] *= f1; acc[i][3] *= f1; }
+#pragma unroll
+            for (int ks = 0; ks < kXkSub / 16; ++ks) {
+                const int pxb = ks * 16;
+                uint32_t af[4];
+                ldmatrix_x4_trans(af, &kt[(pxb + (j >> 1) * 8 + r) * kKP + warp * 16 + (j & 1) * 8]);
+#pragma unroll
+                for (int np = 0; np < C / 16; ++np) {
+                    uint32_t bf[4];
+                    ldmatrix_x4_trans(bf, &xt[(pxb + (j & 1) * 8 + r) * kXP + (np * 2 + (j >> 1)) * 8]);
+                    mma_bf16_16816(acc[2 * np], af, bf[0], bf[1]);
+                    mma_bf16_16816(acc[2 * np + 1], af, bf[2], bf[3]);
+                }
+            }
+        }
+        __syncthreads();                                            // k tile and this x buffer are free again
+    }
+    // ---- partial (m[128], l[128], S[128][C]) of this chunk
+    float* part = partials + ((size_t)b * chunks + chunk) * kPart;
+    if (tid < 128) { part[tid] = s_m[tid]; part[128 + tid] = s_l[tid]; }
+#pragma unroll
+    for (int i = 0; i < C / 8; ++i) {
+        const int d = warp * 16 + g, c = i * 8 + 2 * t;
+        *reinterpret_cast<float2*>(&part[256 + d * C + c]) = make_float2(acc[i][0], acc[i][1]);
+        *reinterpret_cast<float2*>(&part[256 + (d + 8) * C + c]) = make_float2(acc[i][2], acc[i][3]);
+    }
+}
+
+// Merge of the (m, l, S) partials and ctx = (S / l) Wv^T: grid (4 heads, B), 256 threads.
+template <int C>
+__global__ void __launch_bounds__(256)
+attn_merge_s_kernel(const float* __restrict__ partials, const float* __restrict__ wv /*[128][C] fp32 rows h*32+e*/,
+                    float* __restrict__ ctxn, int chunks) {
+    pdl_trigger();
+    pdl_wait();
+    constexpr int kPart = 256 + 128 * C;
+    __shared__ float s_w[64][32], s_M[32], s_il[32], s_part[8][32];
+    __shared__ float s_S[32][C + 1];
+    const int tid = threadIdx.x, head = blockIdx.x, b = blockIdx.y;
+    const int d = tid & 31, cg = tid >> 5;
+    const float* pb = partials + (size_t)b * chunks * kPart;
+    {
+        float M = -INFINITY;
+        for (int c = cg; c < chunks; c += 8) M = fmaxf(M, pb[(size_t)c * kPart + head * 32 + d]);
+        s_part[cg][d] = M;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        float M = s_part[0][tid];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) M = fmaxf(M, s_part[k][tid]);
+        s_M[tid] = M;
+    }
+    __syncthreads();
+    for (int c = cg; c < chunks; c += 8) s_w[c][d] = __expf(pb[(size_t)c * kPart + head * 32 + d] - s_M[d]);
+    __syncthreads();
+    if (tid < 32) {
+        float l = 0.f;
+        for (int c = 0; c < chunks; ++c) l += s_w[c][tid] * pb[(size_t)c * kPart + 128 + head * 32 + tid];
+        s_il[tid] = 1.0f / l;
+    }
+    for (int i = tid; i < 32 * C; i += 256) {                       // merged, normalised S of this head
+        const int dd = i / C, cc = i % C;
+        float sacc = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < chunks; ++c) sacc += s_w[c][dd] * pb[(size_t)c * kPart + 256 + (size_t)(head * 32 + dd) * C + cc];
+        s_S[dd][cc] = sacc;
+    }
+    __syncthreads();
+    for (int i = tid; i < 1024; i += 256) {                         // ctx[d][e] = sum_c S[d][c] Wv[h*32+e][c] / l[d]
+        const int dd = i >> 5, e = i & 31;
+        const float* wr = wv + (size_t)(head * 32 + e) * C;
+        float a = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < C; ++c) a = fmaf(s_S[dd][c], __ldg(wr + c), a);
+        ctxn[((size_t)b * 4 + head) * 1024 + i] = a * s_il[dd];
+    }
+}
+
 // Deterministic merge of the per-chunk partials: grid (4 heads, B), 256 threads.
 template <bool kStrict>
 __global__ void __launch_bounds__(256)
@@ -397,6 +621,33 @@ int attn_ctx(ActKind act, const AttnCtxArgs& a, bool strict, cudaStream_t s) {
             attr_set = true;
         }
         GTTS_CHECK_CUDA(launch_pdl(attn_ctx_tc_kernel, grid, dim3(128), (size_t)smem, s, 1, a));
+    }
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+size_t attn_xk_partial_floats(int C) { return (size_t)256 + 128 * C; }
+
+// Fused path (bf16, C = 64 / 128): x -> (m, l, S) partials -> ctxn
+int attn_xk(const void* x, const void* wk_bf16, const float* wv_f32, float* partials, float* ctxn, int B, int n, int C,
+            int chunks, int chunk_len, cudaStream_t s) {
+    GTTS_REQUIRE(C == 64 || C == 128, "attn_xk: C must be 64 or 128");
+    GTTS_REQUIRE(chunks >= 1 && chunks <= 64 && chunk_len % kXkSub == 0, "attn_xk: bad chunk plan");
+    const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
+    const __nv_bfloat16* wk = reinterpret_cast<const __nv_bfloat16*>(wk_bf16);
+    dim3 grid(chunks, B), gm(4, B);
+    if (C == 64) {
+        const size_t smem = (size_t)(128 * 72 + 2 * kXkSub * 72 + kXkSub * 136) * 2 + (3 * 128 + 512) * 4;
+        static bool set64 = false;
+        if (!set64) { GTTS_CHECK_CUDA(cudaFuncSetAttribute(attn_xk_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set64 = true; }
+        GTTS_CHECK_CUDA(launch_pdl(attn_xk_kernel<64>, grid, dim3(256), smem, s, 1, xb, wk, partials, n, chunks, chunk_len));
+        GTTS_CHECK_CUDA(launch_pdl(attn_merge_s_kernel<64>, gm, dim3(256), 0, s, 1, (const float*)partials, wv_f32, ctxn, chunks));
+    } else {
+        const size_t smem = (size_t)(128 * 136 + 2 * kXkSub * 136 + kXkSub * 136) * 2 + (3 * 128 + 512) * 4;
+        static bool set128 = false;
+        if (!set128) { GTTS_CHECK_CUDA(cudaFuncSetAttribute(attn_xk_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set128 = true; }
+        GTTS_CHECK_CUDA(launch_pdl(attn_xk_kernel<128>, grid, dim3(256), smem, s, 1, xb, wk, partials, n, chunks, chunk_len));
+        GTTS_CHECK_CUDA(launch_pdl(attn_merge_s_kernel<128>, gm, dim3(256), 0, s, 1, (const float*)partials, wv_f32, ctxn, chunks));
     }
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -98,6 +98,7 @@ struct Decoder {
     int max_chunk = 8;
     bool use_graph = true;
     int conv_impl_bf16 = 1;   // 1: tcgen05, 0: FFMA (debug cross-check)
+    int fused_attn = 1;       // bf16, C <= 128: fused k-projection + context kernel (no kv tensor)
     int halo_mode = 2;        // 3x3 convs: 0 = per-tap boxes, 1/2 = halo box (18x16 / 18x10) + shifted descriptor views
     std::map<std::string, float*> params;
     std::map<std::string, size_t> param_numel;
@@ -468,24 +469,39 @@ struct PlanBuilder {
     void* attention(int a, int lvl, const void* x) {
         const AttnW& A = P->attn[a];
         const int C = A.C, n = H[lvl] * W[lvl];
-        void* kv = act(lvl, 256);
         void* out = act(lvl, C);
         int chunks, chunk_len;
         attn_ctx_plan(n, &chunks, &chunk_len);
-        float* partials = (float*)pl->mem.alloc((size_t)B * 4 * chunks * 1088 * 4);
         float* ctxn = (float*)pl->mem.alloc((size_t)B * 4096 * 4);
         void* mb = pl->mem.alloc((size_t)B * C * C * esize(kind));
-        if (!kv || !out || !partials || !ctxn || !mb) { failed = true; return nullptr; }
-        add_conv(geom_1x1(B, H[lvl], W[lvl], C, 0, 256, 0), x, nullptr, A.wkv, 256, nullptr, nullptr, nullptr, kv, nullptr);
-        AttnCtxArgs ca{kv, B, n, partials, ctxn, chunks, chunk_len};
+        if (!out || !ctxn || !mb) { failed = true; return nullptr; }
         ActKind k = kind;
         bool st_ = strict;
-        pl->push("attn_ctx_h" + std::to_string(H[lvl]), 0, 2.0 * B * 4 * (double)n * 1024, (double)B * n * 256 * esize(kind),
-                 [k, ca, st_](cudaStream_t s) { return attn_ctx(k, ca, st_, s); });
-        pl->push("attn_merge", 0, 0.0, 0.0, [ca, st_](cudaStream_t s) { return attn_merge(ca, st_, s); });
+        int Bb = B;
+        if (kind == ACT_BF16 && C <= 128 && d->fused_attn) {
+            // fused k-projection + context: reads x only, k and v are never written to HBM
+            float* partials = (float*)pl->mem.alloc((size_t)B * chunks * attn_xk_partial_floats(C) * 4);
+            if (!partials) { failed = true; return nullptr; }
+            const void* wk = A.wkv;                                  // rows [0,128) of the packed kv weight = k
+            const float* wv = A.wq + (size_t)256 * C;                // rows [256,384) of to_qkv.weight = v (fp32)
+            pl->push("attn_xk_" + std::to_string(C) + "_h" + std::to_string(H[lvl]), 0,
+                     2.0 * B * (double)n * 128 * C * 2, (double)B * n * C * 2,
+                     [x, wk, wv, partials, ctxn, Bb, n, C, chunks, chunk_len](cudaStream_t s) {
+                         return attn_xk(x, wk, wv, partials, ctxn, Bb, n, C, chunks, chunk_len, s);
+                     });
+            pl->kernels_per_step++;                                  // attn_xk launches two kernels
+        } else {
+            void* kv = act(lvl, 256);
+            float* partials = (float*)pl->mem.alloc((size_t)B * 4 * chunks * 1088 * 4);
+            if (!kv || !partials) { failed = true; return nullptr; }
+            add_conv(geom_1x1(B, H[lvl], W[lvl], C, 0, 256, 0), x, nullptr, A.wkv, 256, nullptr, nullptr, nullptr, kv, nullptr);
+            AttnCtxArgs ca{kv, B, n, partials, ctxn, chunks, chunk_len};
+            pl->push("attn_ctx_h" + std::to_string(H[lvl]), 0, 2.0 * B * 4 * (double)n * 1024, (double)B * n * 256 * esize(kind),
+                     [k, ca, st_](cudaStream_t s) { return attn_ctx(k, ca, st_, s); });
+            pl->push("attn_merge", 0, 0.0, 0.0, [ca, st_](cudaStream_t s) { return attn_merge(ca, st_, s); });
+        }
         const float *wout = A.wout, *wq = A.wq;
         float g = A.g;
-        int Bb = B;
         pl->push("attn_fold_" + std::to_string(C), 0, 2.0 * B * ((double)C * 128 * 32 + (double)C * C * 128), 0.0,
                  [k, ctxn, wout, wq, g, mb, Bb, C](cudaStream_t s) { return attn_fold(k, ctxn, wout, wq, g, mb, Bb, C, s); });
         add_conv(geom_1x1(B, H[lvl], W[lvl], C, 0, C, C), x, nullptr, mb, B * C, A.gb, x, lmask[lvl], out, nullptr);
@@ -688,7 +704,7 @@ int plan_create(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde,
 int get_plan(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, Plan** out) {
     std::string key = std::to_string((int)kind) + ":" + std::to_string(B) + ":" + std::to_string(T) + ":" +
                       (est_mode ? "e" : "s") + (sde ? "n" : "o") + (d->use_graph ? "g" : "x") +
-                      std::to_string(d->conv_impl_bf16) + std::to_string(d->halo_mode);
+                      std::to_string(d->conv_impl_bf16) + std::to_string(d->halo_mode) + std::to_string(d->fused_attn);
     auto it = d->plans.find(key);
     if (it != d->plans.end()) { *out = it->second; return 0; }
     // keep at most a handful of plans alive (each owns its workspace)
@@ -889,6 +905,7 @@ int decoder_set_option(Decoder* d, const char* key, int value) {
     else if (k == "use_graph") d->use_graph = value != 0;
     else if (k == "conv_impl_bf16") d->conv_impl_bf16 = value;
     else if (k == "halo_mode") d->halo_mode = value;
+    else if (k == "fused_attn") d->fused_attn = value;
     else { set_error("unknown option " + k); return 2; }
     return 0;
 }

@@ -63,7 +63,8 @@ void gtts_decoder_destroy(gtts_decoder* d);
  * fp32, contiguous, PyTorch layout; `data` may be a host or a device pointer.  Invalidates packed weights/plans. */
 int gtts_decoder_set_param(gtts_decoder* d, const char* name, const float* data, size_t numel);
 /* options: "max_chunk" (samples per workspace chunk), "use_graph" (0/1), "conv_impl_bf16" (1 tcgen05, 0 FFMA cross-check),
- * "halo_mode" (3x3 convs: 0 per-tap TMA boxes, 1 / 2 halo box 18x16 / 18x10 + shifted descriptor views) */
+ * "halo_mode" (3x3 convs: 0 per-tap TMA boxes, 1 / 2 halo box 18x16 / 18x10 + shifted descriptor views),
+ * "fused_attn" (1: fused k-projection + context kernel for C <= 128, 0: 1x1 kv conv + context kernel) */
 int gtts_decoder_set_option(gtts_decoder* d, const char* key, int value);
 
 /* z, mu, out: [B][80][T] fp32; mask: [B][1][T] fp32 with entries in {0,1}; spk: [B][64] or NULL;

@@ -99,8 +99,11 @@ def stage_dec(precision, conv_impl=None):
 
 
 def stage_perf():
-    for (n_spks, B, T, n, chunk) in [(1, 1, 400, 10, 8), (1, 8, 800, 4, 8), (247, 32, 800, 2, 8), (1, 16, 1720, 2, 4),
-                                     (1, 16, 1720, 2, 8), (1, 16, 1720, 2, 16)]:
+    cfgs = [(1, 1, 400, 10, 8), (1, 8, 800, 4, 8), (247, 32, 800, 2, 8), (1, 16, 1720, 2, 4), (1, 16, 1720, 2, 8),
+            (1, 16, 1720, 2, 16)]
+    if os.environ.get("GTTS_PERF") == "chunks":
+        cfgs = [(1, 64, 1720, 2, 16), (1, 64, 1720, 2, 32), (1, 100, 400, 10, 25), (1, 100, 400, 10, 32), (247, 32, 800, 4, 16), (247, 32, 800, 4, 32)]
+    for (n_spks, B, T, n, chunk) in cfgs:
         try:
             dec, _ = _decoder(n_spks, 0, "bf16")
             dec.estimator.max_chunk = chunk
@@ -177,6 +180,8 @@ def stage_profile():
         dec.estimator.max_chunk = B
         hm = int(os.environ.get("GTTS_HALO", "2"))
         pkg._lib.check(pkg._lib.load().gtts_decoder_set_option(dec.estimator._get_handle(), b"halo_mode", hm), "opt")
+        pkg._lib.check(pkg._lib.load().gtts_decoder_set_option(dec.estimator._get_handle(), b"fused_attn",
+                                                               int(os.environ.get("GTTS_FUSED_ATTN", "1"))), "opt")
         z, mask, mu, spk, _ = pkg.synth.make_inputs(B, T, n_spks, seed=7, ragged=False)
         dec(z.to(DEV), mask.to(DEV), mu.to(DEV), 2)
         torch.cuda.synchronize()
