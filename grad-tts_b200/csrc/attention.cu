@@ -291,8 +291,8 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_p
 
 template <int C>
 __global__ void __launch_bounds__(256)
-attn_xk_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ wk, float* __restrict__ partials,
-               int n, int chunks, int chunk_len) {
+attn_xk_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ wk, const float* __restrict__ wv,
+               float* __restrict__ partials, int n, int chunks, int chunk_len) {
     pdl_trigger();
     pdl_wait();
     constexpr int kXP = C + 8;                    // bf16 pitch of x / Wk rows (16-byte pad: conflict-free ldmatrix)
@@ -437,65 +437,32 @@ attn_xk_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
         }
         __syncthreads();                                            // k tile and this x buffer are free again
     }
-    // ---- partial (m[128], l[128], S[128][C]) of this chunk
-    float* part = partials + ((size_t)b * chunks + chunk) * kPart;
-    if (tid < 128) { part[tid] = s_m[tid]; part[128 + tid] = s_l[tid]; }
+    // ---- this chunk's partial in the compact format of attn_merge: per head (m[32], l[32], ctx[32][32]) with
+    //      ctx[d][e] = sum_c S[d][c] Wv[h*32+e][c]   (linear in S, so it can be applied per chunk)
+    float* sS = reinterpret_cast<float*>(xs_all);                   // [128][C + 1] fp32, aliases the tile buffers
+    constexpr int kSP = C + 1;
 #pragma unroll
     for (int i = 0; i < C / 8; ++i) {
         const int d = warp * 16 + g, c = i * 8 + 2 * t;
-        *reinterpret_cast<float2*>(&part[256 + d * C + c]) = make_float2(acc[i][0], acc[i][1]);
-        *reinterpret_cast<float2*>(&part[256 + (d + 8) * C + c]) = make_float2(acc[i][2], acc[i][3]);
-    }
-}
-
-// Merge of the (m, l, S) partials and ctx = (S / l) Wv^T: grid (4 heads, B), 256 threads.
-template <int C>
-__global__ void __launch_bounds__(256)
-attn_merge_s_kernel(const float* __restrict__ partials, const float* __restrict__ wv /*[128][C] fp32 rows h*32+e*/,
-                    float* __restrict__ ctxn, int chunks) {
-    pdl_trigger();
-    pdl_wait();
-    constexpr int kPart = 256 + 128 * C;
-    __shared__ float s_w[64][32], s_M[32], s_il[32], s_part[8][32];
-    __shared__ float s_S[32][C + 1];
-    const int tid = threadIdx.x, head = blockIdx.x, b = blockIdx.y;
-    const int d = tid & 31, cg = tid >> 5;
-    const float* pb = partials + (size_t)b * chunks * kPart;
-    {
-        float M = -INFINITY;
-        for (int c = cg; c < chunks; c += 8) M = fmaxf(M, pb[(size_t)c * kPart + head * 32 + d]);
-        s_part[cg][d] = M;
+        sS[d * kSP + c] = acc[i][0];       sS[d * kSP + c + 1] = acc[i][1];
+        sS[(d + 8) * kSP + c] = acc[i][2]; sS[(d + 8) * kSP + c + 1] = acc[i][3];
     }
     __syncthreads();
-    if (tid < 32) {
-        float M = s_part[0][tid];
-#pragma unroll
-        for (int k = 1; k < 8; ++k) M = fmaxf(M, s_part[k][tid]);
-        s_M[tid] = M;
-    }
-    __syncthreads();
-    for (int c = cg; c < chunks; c += 8) s_w[c][d] = __expf(pb[(size_t)c * kPart + head * 32 + d] - s_M[d]);
-    __syncthreads();
-    if (tid < 32) {
-        float l = 0.f;
-        for (int c = 0; c < chunks; ++c) l += s_w[c][tid] * pb[(size_t)c * kPart + 128 + head * 32 + tid];
-        s_il[tid] = 1.0f / l;
-    }
-    for (int i = tid; i < 32 * C; i += 256) {                       // merged, normalised S of this head
-        const int dd = i / C, cc = i % C;
-        float sacc = 0.f;
-#pragma unroll 8
-        for (int c = 0; c < chunks; ++c) sacc += s_w[c][dd] * pb[(size_t)c * kPart + 256 + (size_t)(head * 32 + dd) * C + cc];
-        s_S[dd][cc] = sacc;
-    }
-    __syncthreads();
-    for (int i = tid; i < 1024; i += 256) {                         // ctx[d][e] = sum_c S[d][c] Wv[h*32+e][c] / l[d]
-        const int dd = i >> 5, e = i & 31;
+    float* part0 = partials + ((size_t)b * 4 * chunks + chunk) * 1088;       // head h at + h*chunks*1088
+#pragma unroll 1
+    for (int k = 0; k < 16; ++k) {
+        const int i = tid + 256 * k, head = i >> 10, dd = (i >> 5) & 31, e = i & 31;
         const float* wr = wv + (size_t)(head * 32 + e) * C;
+        const float* sr = &sS[(head * 32 + dd) * kSP];
         float a = 0.f;
 #pragma unroll 8
-        for (int c = 0; c < C; ++c) a = fmaf(s_S[dd][c], __ldg(wr + c), a);
-        ctxn[((size_t)b * 4 + head) * 1024 + i] = a * s_il[dd];
+        for (int c = 0; c < C; ++c) a = fmaf(sr[c], __ldg(wr + c), a);
+        part0[(size_t)head * chunks * 1088 + 64 + (i & 1023)] = a;
+    }
+    if (tid < 128) {
+        const int head = tid >> 5, dd = tid & 31;
+        part0[(size_t)head * chunks * 1088 + dd] = s_m[tid];
+        part0[(size_t)head * chunks * 1088 + 32 + dd] = s_l[tid];
     }
 }
 
@@ -626,28 +593,26 @@ int attn_ctx(ActKind act, const AttnCtxArgs& a, bool strict, cudaStream_t s) {
     return 0;
 }
 
-size_t attn_xk_partial_floats(int C) { return (size_t)256 + 128 * C; }
-
-// Fused path (bf16, C = 64 / 128): x -> (m, l, S) partials -> ctxn
-int attn_xk(const void* x, const void* wk_bf16, const float* wv_f32, float* partials, float* ctxn, int B, int n, int C,
-            int chunks, int chunk_len, cudaStream_t s) {
+// Fused path (bf16, C = 64 / 128): x -> per-chunk (m, l, ctx) partials in the layout attn_merge expects
+int attn_xk(const void* x, const void* wk_bf16, const float* wv_f32, float* partials, int B, int n, int C, int chunks,
+            int chunk_len, cudaStream_t s) {
     GTTS_REQUIRE(C == 64 || C == 128, "attn_xk: C must be 64 or 128");
     GTTS_REQUIRE(chunks >= 1 && chunks <= 64 && chunk_len % kXkSub == 0, "attn_xk: bad chunk plan");
     const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
     const __nv_bfloat16* wk = reinterpret_cast<const __nv_bfloat16*>(wk_bf16);
-    dim3 grid(chunks, B), gm(4, B);
+    dim3 grid(chunks, B);
     if (C == 64) {
-        const size_t smem = (size_t)(128 * 72 + 2 * kXkSub * 72 + kXkSub * 136) * 2 + (3 * 128 + 512) * 4;
+        size_t smem = (size_t)(128 * 72 + 2 * kXkSub * 72 + kXkSub * 136) * 2 + (3 * 128 + 512) * 4;
+        if (smem < (size_t)128 * 65 * 4 + 4096) smem = (size_t)128 * 65 * 4 + 4096;
         static bool set64 = false;
         if (!set64) { GTTS_CHECK_CUDA(cudaFuncSetAttribute(attn_xk_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set64 = true; }
-        GTTS_CHECK_CUDA(launch_pdl(attn_xk_kernel<64>, grid, dim3(256), smem, s, 1, xb, wk, partials, n, chunks, chunk_len));
-        GTTS_CHECK_CUDA(launch_pdl(attn_merge_s_kernel<64>, gm, dim3(256), 0, s, 1, (const float*)partials, wv_f32, ctxn, chunks));
+        GTTS_CHECK_CUDA(launch_pdl(attn_xk_kernel<64>, grid, dim3(256), smem, s, 1, xb, wk, wv_f32, partials, n, chunks, chunk_len));
     } else {
-        const size_t smem = (size_t)(128 * 136 + 2 * kXkSub * 136 + kXkSub * 136) * 2 + (3 * 128 + 512) * 4;
+        size_t smem = (size_t)(128 * 136 + 2 * kXkSub * 136 + kXkSub * 136) * 2 + (3 * 128 + 512) * 4;
+        if (smem < (size_t)128 * 129 * 4 + 4096) smem = (size_t)128 * 129 * 4 + 4096;
         static bool set128 = false;
         if (!set128) { GTTS_CHECK_CUDA(cudaFuncSetAttribute(attn_xk_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set128 = true; }
-        GTTS_CHECK_CUDA(launch_pdl(attn_xk_kernel<128>, grid, dim3(256), smem, s, 1, xb, wk, partials, n, chunks, chunk_len));
-        GTTS_CHECK_CUDA(launch_pdl(attn_merge_s_kernel<128>, gm, dim3(256), 0, s, 1, (const float*)partials, wv_f32, ctxn, chunks));
+        GTTS_CHECK_CUDA(launch_pdl(attn_xk_kernel<128>, grid, dim3(256), smem, s, 1, xb, wk, wv_f32, partials, n, chunks, chunk_len));
     }
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -478,28 +478,27 @@ struct PlanBuilder {
         ActKind k = kind;
         bool st_ = strict;
         int Bb = B;
+        float* partials = (float*)pl->mem.alloc((size_t)B * 4 * chunks * 1088 * 4);
+        if (!partials) { failed = true; return nullptr; }
+        AttnCtxArgs ca{nullptr, B, n, partials, ctxn, chunks, chunk_len};
         if (kind == ACT_BF16 && C <= 128 && d->fused_attn) {
             // fused k-projection + context: reads x only, k and v are never written to HBM
-            float* partials = (float*)pl->mem.alloc((size_t)B * chunks * attn_xk_partial_floats(C) * 4);
-            if (!partials) { failed = true; return nullptr; }
             const void* wk = A.wkv;                                  // rows [0,128) of the packed kv weight = k
             const float* wv = A.wq + (size_t)256 * C;                // rows [256,384) of to_qkv.weight = v (fp32)
             pl->push("attn_xk_" + std::to_string(C) + "_h" + std::to_string(H[lvl]), 0,
                      2.0 * B * (double)n * 128 * C * 2, (double)B * n * C * 2,
-                     [x, wk, wv, partials, ctxn, Bb, n, C, chunks, chunk_len](cudaStream_t s) {
-                         return attn_xk(x, wk, wv, partials, ctxn, Bb, n, C, chunks, chunk_len, s);
+                     [x, wk, wv, partials, Bb, n, C, chunks, chunk_len](cudaStream_t s) {
+                         return attn_xk(x, wk, wv, partials, Bb, n, C, chunks, chunk_len, s);
                      });
-            pl->kernels_per_step++;                                  // attn_xk launches two kernels
         } else {
             void* kv = act(lvl, 256);
-            float* partials = (float*)pl->mem.alloc((size_t)B * 4 * chunks * 1088 * 4);
-            if (!kv || !partials) { failed = true; return nullptr; }
+            if (!kv) { failed = true; return nullptr; }
             add_conv(geom_1x1(B, H[lvl], W[lvl], C, 0, 256, 0), x, nullptr, A.wkv, 256, nullptr, nullptr, nullptr, kv, nullptr);
-            AttnCtxArgs ca{kv, B, n, partials, ctxn, chunks, chunk_len};
+            ca.kv = kv;
             pl->push("attn_ctx_h" + std::to_string(H[lvl]), 0, 2.0 * B * 4 * (double)n * 1024, (double)B * n * 256 * esize(kind),
                      [k, ca, st_](cudaStream_t s) { return attn_ctx(k, ca, st_, s); });
-            pl->push("attn_merge", 0, 0.0, 0.0, [ca, st_](cudaStream_t s) { return attn_merge(ca, st_, s); });
         }
+        pl->push("attn_merge", 0, 0.0, 0.0, [ca, st_](cudaStream_t s) { return attn_merge(ca, st_, s); });
         const float *wout = A.wout, *wq = A.wq;
         float g = A.g;
         pl->push("attn_fold_" + std::to_string(C), 0, 2.0 * B * ((double)C * 128 * 32 + (double)C * C * 128), 0.0,
