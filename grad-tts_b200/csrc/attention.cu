@@ -291,7 +291,7 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_p
 
 template <int C>
 __global__ void __launch_bounds__(256)
-attn_xk_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ wk, const float* __restrict__ wv,
+attn_xk_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ wk /*[256][C]: k rows, then v rows*/,
                float* __restrict__ partials, int n, int chunks, int chunk_len) {
     pdl_trigger();
     pdl_wait();
@@ -438,31 +438,52 @@ attn_xk_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
         __syncthreads();                                            // k tile and this x buffer are free again
     }
     // ---- this chunk's partial in the compact format of attn_merge: per head (m[32], l[32], ctx[32][32]) with
-    //      ctx[d][e] = sum_c S[d][c] Wv[h*32+e][c]   (linear in S, so it can be applied per chunk)
-    float* sS = reinterpret_cast<float*>(xs_all);                   // [128][C + 1] fp32, aliases the tile buffers
-    constexpr int kSP = C + 1;
-#pragma unroll
-    for (int i = 0; i < C / 8; ++i) {
-        const int d = warp * 16 + g, c = i * 8 + 2 * t;
-        sS[d * kSP + c] = acc[i][0];       sS[d * kSP + c + 1] = acc[i][1];
-        sS[(d + 8) * kSP + c] = acc[i][2]; sS[(d + 8) * kSP + c + 1] = acc[i][3];
+    //      ctx[d][e] = sum_c S[d][c] Wv[h*32+e][c]   (linear in S, so it can be applied per chunk).
+    // S stays in registers: the fp32 accumulator fragments are repacked as bf16 A fragments (two adjacent n8 tiles
+    // = one k16 slice) and multiplied with the bf16 Wv rows staged where Wk was.
+    for (int i = tid; i < 128 * (C / 8); i += 256) {
+        const int row = i / (C / 8), c8 = i % (C / 8);
+        *reinterpret_cast<uint4*>(&wks[row * kXP + c8 * 8]) =
+            __ldg(reinterpret_cast<const uint4*>(wk + (size_t)(128 + row) * C + c8 * 8));      // rows [128,256) = v
     }
     __syncthreads();
-    float* part0 = partials + ((size_t)b * 4 * chunks + chunk) * 1088;       // head h at + h*chunks*1088
-#pragma unroll 1
-    for (int k = 0; k < 16; ++k) {
-        const int i = tid + 256 * k, head = i >> 10, dd = (i >> 5) & 31, e = i & 31;
-        const float* wr = wv + (size_t)(head * 32 + e) * C;
-        const float* sr = &sS[(head * 32 + dd) * kSP];
-        float a = 0.f;
-#pragma unroll 8
-        for (int c = 0; c < C; ++c) a = fmaf(sr[c], __ldg(wr + c), a);
-        part0[(size_t)head * chunks * 1088 + 64 + (i & 1023)] = a;
+    const int head = warp >> 1;
+    float out[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) out[i][q] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < C / 16; ++ks) {
+        uint32_t af[4];
+        {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[2 * ks][0], acc[2 * ks][1]);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(acc[2 * ks][2], acc[2 * ks][3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[2 * ks + 1][0], acc[2 * ks + 1][1]);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(acc[2 * ks + 1][2], acc[2 * ks + 1][3]);
+            af[0] = *reinterpret_cast<uint32_t*>(&h0); af[1] = *reinterpret_cast<uint32_t*>(&h1);
+            af[2] = *reinterpret_cast<uint32_t*>(&h2); af[3] = *reinterpret_cast<uint32_t*>(&h3);
+        }
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+            uint32_t bf[4];
+            ldmatrix_x4(bf, &wks[(head * 32 + np * 16 + (j >> 1) * 8 + r) * kXP + ks * 16 + (j & 1) * 8]);
+            mma_bf16_16816(out[2 * np], af, bf[0], bf[1]);
+            mma_bf16_16816(out[2 * np + 1], af, bf[2], bf[3]);
+        }
+    }
+    float* part = partials + (((size_t)b * 4 + head) * chunks + chunk) * 1088;
+    const int dl = (warp & 1) * 16 + g;                              // row within the head
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const int e = nt * 8 + 2 * t;
+        *reinterpret_cast<float2*>(&part[64 + dl * 32 + e]) = make_float2(out[nt][0], out[nt][1]);
+        *reinterpret_cast<float2*>(&part[64 + (dl + 8) * 32 + e]) = make_float2(out[nt][2], out[nt][3]);
     }
     if (tid < 128) {
-        const int head = tid >> 5, dd = tid & 31;
-        part0[(size_t)head * chunks * 1088 + dd] = s_m[tid];
-        part0[(size_t)head * chunks * 1088 + 32 + dd] = s_l[tid];
+        float* ph = partials + (((size_t)b * 4 + (tid >> 5)) * chunks + chunk) * 1088;
+        ph[tid & 31] = s_m[tid];
+        ph[32 + (tid & 31)] = s_l[tid];
     }
 }
 
@@ -594,25 +615,23 @@ int attn_ctx(ActKind act, const AttnCtxArgs& a, bool strict, cudaStream_t s) {
 }
 
 // Fused path (bf16, C = 64 / 128): x -> per-chunk (m, l, ctx) partials in the layout attn_merge expects
-int attn_xk(const void* x, const void* wk_bf16, const float* wv_f32, float* partials, int B, int n, int C, int chunks,
-            int chunk_len, cudaStream_t s) {
+int attn_xk(const void* x, const void* wkv_bf16, float* partials, int B, int n, int C, int chunks, int chunk_len,
+            cudaStream_t s) {
     GTTS_REQUIRE(C == 64 || C == 128, "attn_xk: C must be 64 or 128");
     GTTS_REQUIRE(chunks >= 1 && chunks <= 64 && chunk_len % kXkSub == 0, "attn_xk: bad chunk plan");
     const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
-    const __nv_bfloat16* wk = reinterpret_cast<const __nv_bfloat16*>(wk_bf16);
+    const __nv_bfloat16* wk = reinterpret_cast<const __nv_bfloat16*>(wkv_bf16);
     dim3 grid(chunks, B);
     if (C == 64) {
         size_t smem = (size_t)(128 * 72 + 2 * kXkSub * 72 + kXkSub * 136) * 2 + (3 * 128 + 512) * 4;
-        if (smem < (size_t)128 * 65 * 4 + 4096) smem = (size_t)128 * 65 * 4 + 4096;
         static bool set64 = false;
         if (!set64) { GTTS_CHECK_CUDA(cudaFuncSetAttribute(attn_xk_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set64 = true; }
-        GTTS_CHECK_CUDA(launch_pdl(attn_xk_kernel<64>, grid, dim3(256), smem, s, 1, xb, wk, wv_f32, partials, n, chunks, chunk_len));
+        GTTS_CHECK_CUDA(launch_pdl(attn_xk_kernel<64>, grid, dim3(256), smem, s, 1, xb, wk, partials, n, chunks, chunk_len));
     } else {
         size_t smem = (size_t)(128 * 136 + 2 * kXkSub * 136 + kXkSub * 136) * 2 + (3 * 128 + 512) * 4;
-        if (smem < (size_t)128 * 129 * 4 + 4096) smem = (size_t)128 * 129 * 4 + 4096;
         static bool set128 = false;
         if (!set128) { GTTS_CHECK_CUDA(cudaFuncSetAttribute(attn_xk_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set128 = true; }
-        GTTS_CHECK_CUDA(launch_pdl(attn_xk_kernel<128>, grid, dim3(256), smem, s, 1, xb, wk, wv_f32, partials, n, chunks, chunk_len));
+        GTTS_CHECK_CUDA(launch_pdl(attn_xk_kernel<128>, grid, dim3(256), smem, s, 1, xb, wk, partials, n, chunks, chunk_len));
     }
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -483,12 +483,11 @@ struct PlanBuilder {
         AttnCtxArgs ca{nullptr, B, n, partials, ctxn, chunks, chunk_len};
         if (kind == ACT_BF16 && C <= 128 && d->fused_attn) {
             // fused k-projection + context: reads x only, k and v are never written to HBM
-            const void* wk = A.wkv;                                  // rows [0,128) of the packed kv weight = k
-            const float* wv = A.wq + (size_t)256 * C;                // rows [256,384) of to_qkv.weight = v (fp32)
+            const void* wk = A.wkv;                                  // packed bf16 [256][C]: k rows, then v rows
             pl->push("attn_xk_" + std::to_string(C) + "_h" + std::to_string(H[lvl]), 0,
                      2.0 * B * (double)n * 128 * C * 2, (double)B * n * C * 2,
-                     [x, wk, wv, partials, Bb, n, C, chunks, chunk_len](cudaStream_t s) {
-                         return attn_xk(x, wk, wv, partials, Bb, n, C, chunks, chunk_len, s);
+                     [x, wk, partials, Bb, n, C, chunks, chunk_len](cudaStream_t s) {
+                         return attn_xk(x, wk, partials, Bb, n, C, chunks, chunk_len, s);
                      });
         } else {
             void* kv = act(lvl, 256);

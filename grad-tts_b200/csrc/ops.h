@@ -136,7 +136,7 @@ int attn_ctx(ActKind act, const AttnCtxArgs& a, bool strict, cudaStream_t s);   
 int attn_merge(const AttnCtxArgs& a, bool strict, cudaStream_t s);                   // partials -> ctxn
 void attn_ctx_plan(int n, int* chunks, int* chunk_len);
 // fused k-projection + context for bf16 activations with C = 64 / 128 (attention.cu): reads x only
-int attn_xk(const void* x, const void* wk_bf16, const float* wv_f32, float* partials, int B, int n, int C, int chunks,
+int attn_xk(const void* x, const void* wkv_bf16 /*[256][C]*/, float* partials, int B, int n, int C, int chunks,
             int chunk_len, cudaStream_t s);                  // writes attn_merge-format partials
 // per-sample folded weights M_b = g * Wout * blockdiag(ctxn^T) * Wq  -> [B*C][C] in weight type
 int attn_fold(ActKind wkind, const float* ctxn, const float* wout /*[C][128]*/, const float* wq /*[128][C]*/,
