@@ -522,9 +522,8 @@ attn_merge_kernel(AttnCtxArgs a) {
         s_scale[tid] = 1.0f / l;
     }
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int i = tid + 256 * k, dd = i >> 5;
+    {   // blockIdx.z selects a quarter of the 32x32 outputs: one output per thread
+        const int i = tid + 256 * (int)blockIdx.z, dd = i >> 5;
         float s = 0.f;
 #pragma unroll 8
         for (int c = 0; c < nch; ++c) s += s_w[c][dd] * pbase[(size_t)c * 1088 + 64 + i];
@@ -639,7 +638,7 @@ int attn_xk(const void* x, const void* wkv_bf16, float* partials, int B, int n, 
 
 int attn_merge(const AttnCtxArgs& a, bool strict, cudaStream_t s) {
     GTTS_REQUIRE(a.chunks <= 64, "attn_merge: too many chunks");
-    dim3 grid(4, a.B);
+    dim3 grid(4, a.B, 4);
     if (strict) GTTS_CHECK_CUDA(launch_pdl(attn_merge_kernel<true>, grid, dim3(256), 0, s, 1, a));
     else        GTTS_CHECK_CUDA(launch_pdl(attn_merge_kernel<false>, grid, dim3(256), 0, s, 1, a));
     GTTS_CHECK_CUDA(cudaGetLastError());

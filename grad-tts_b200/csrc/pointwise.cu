@@ -316,7 +316,7 @@ gn_apply_kernel(GnApplyArgs a) {
 constexpr int kGfVec = 4;
 
 template <bool kHasRes, bool kHasTb, bool kFirstRes>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, kFirstRes ? 3 : 4)
 gn_apply_fast_kernel(GnApplyArgs a) {
     pdl_trigger();
     pdl_wait();
@@ -329,13 +329,13 @@ gn_apply_fast_kernel(GnApplyArgs a) {
     const int g = (c0 * 8) / a.C;
     const float mean = a.stats[(b * 8 + g) * 2], rstd = a.stats[(b * 8 + g) * 2 + 1];
     constexpr float kLog2e = 1.4426950408889634f;
-    float2 sc[4], sh[4], scl[4], shl[4], tb[4];
+    float2 sc[4], sh[4], tb[4];
+    const float2 l2e = make_float2(kLog2e, kLog2e);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const float s0 = rstd * __ldg(a.gamma + c0 + 2 * q), s1 = rstd * __ldg(a.gamma + c0 + 2 * q + 1);
         const float h0 = __ldg(a.beta + c0 + 2 * q) - mean * s0, h1 = __ldg(a.beta + c0 + 2 * q + 1) - mean * s1;
         sc[q] = make_float2(s0, s1);                   sh[q] = make_float2(h0, h1);
-        scl[q] = make_float2(s0 * kLog2e, s1 * kLog2e); shl[q] = make_float2(h0 * kLog2e, h1 * kLog2e);
         tb[q] = kHasTb ? make_float2(__ldg(a.tbias + (size_t)b * a.tbias_bstride + c0 + 2 * q),
                                      __ldg(a.tbias + (size_t)b * a.tbias_bstride + c0 + 2 * q + 1))
                        : make_float2(0.f, 0.f);
@@ -388,7 +388,7 @@ gn_apply_fast_kernel(GnApplyArgs a) {
         for (int q = 0; q < 4; ++q) {
             const float2 x = make_float2(__uint_as_float(w[q] << 16), __uint_as_float(w[q] & 0xffff0000u));
             const float2 y = ffma2(x, sc[q], sh[q]);                    // GroupNorm affine          (:53)
-            float2 o = mish2_fast(y, ffma2(x, scl[q], shl[q]));         // Mish                      (:54)
+            float2 o = mish2_fast(y, fmul2(y, l2e));                    // Mish                      (:54)
             if (kHasTb) o = fadd2(o, tb[q]);                            // (mish*m + tb)*m == (mish + tb)*m, m in {0,1}
             if (kHasRes) o = fadd2(o, make_float2(__uint_as_float(rw[q] << 16), __uint_as_float(rw[q] & 0xffff0000u)));
             if (kFirstRes) {
