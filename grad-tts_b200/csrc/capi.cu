@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "decoder_api.h"
 #include "ops.h"
+#include <vector>
 
 namespace gtts {
 static thread_local std::string g_last_error;
@@ -197,6 +198,26 @@ int gtts_decoder_profile_step(gtts_decoder* h, int B, int T, int flags, int reps
 long gtts_decoder_launches_last_call(const gtts_decoder* h) { return h ? decoder_launches_last_call(h->impl) : 0; }
 
 // ------------------------------------------------------------------------------------------------ test hooks
+int gtts_test_issue_microbench(int N, int n_mma, int n_commit, int iters, int wait_each, int grid, double* issue_cycles,
+                               double* total_cycles) {
+    GTTS_REQUIRE((N == 64 || N == 128 || N == 256) && grid >= 1 && grid <= 1024 && iters >= 1,
+                 "gtts_test_issue_microbench: bad arguments");
+    unsigned long long* d = nullptr;
+    GTTS_CHECK_CUDA(cudaMalloc(&d, sizeof(unsigned long long) * 2 * grid));
+    int rc = microbench_issue(N, n_mma, n_commit, iters, wait_each, grid, d, nullptr);
+    if (rc == 0) rc = microbench_issue(N, n_mma, n_commit, iters, wait_each, grid, d, nullptr);   // second run is the warm one
+    std::vector<unsigned long long> h(2 * grid);
+    cudaError_t e = cudaMemcpy(h.data(), d, sizeof(unsigned long long) * 2 * grid, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (rc) return rc;
+    GTTS_CHECK_CUDA(e);
+    double a = 0, b = 0;
+    for (int i = 0; i < grid; ++i) { a += (double)h[2 * i]; b += (double)h[2 * i + 1]; }
+    *issue_cycles = a / grid;
+    *total_cycles = b / grid;
+    return 0;
+}
+
 int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, int Cin1, int Cout, const void* src0,
                    const void* src1, const float* weight_pt, const float* bias, const void* residual,
                    const float* mask, void* out, float* gn_stats, int per_sample_weights, void* stream) {
@@ -255,8 +276,8 @@ int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, i
         size_t slots = impl >= 1 ? conv_tc_partials_slots(g) : conv_ffma_partials_slots(g);
         if (halo_mode && conv_tc_halo_eligible(g)) slots = conv_tc_halo_partials_slots(g);
         GTTS_CHECK_CUDA(cudaMalloc(&partials, (size_t)B * slots * 16 * 4));
-        GTTS_CHECK_CUDA(cudaMalloc(&counters, (size_t)B * 4));
-        GTTS_CHECK_CUDA(cudaMemsetAsync(counters, 0, (size_t)B * 4, s));
+        GTTS_CHECK_CUDA(cudaMalloc(&counters, (size_t)(B + 32) * 4));
+        GTTS_CHECK_CUDA(cudaMemsetAsync(counters, 0, (size_t)(B + 32) * 4, s));
         e.gn_partials = partials; e.gn_stats = gn_stats; e.gn_counters = counters; e.gn_eps = 1e-5f;
     }
     int rc = 0;
@@ -270,6 +291,67 @@ int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, i
         else {
             rc = conv_tc_launch(tp, s);
             cudaStreamSynchronize(s);
+            if (getenv("GTTS_CONV_TIMING")) {
+                const int L = 4, G = conv_tc_plan_grid(tp);                       // L back-to-back instrumented launches
+                unsigned long long* dbg = nullptr;
+                cudaMalloc(&dbg, (size_t)L * 256 * 32 * 8);
+                cudaMemset(dbg, 0, (size_t)L * 256 * 32 * 8);
+                cudaStreamSynchronize(s);
+                for (int l = 0; l < L && rc == 0; ++l) {
+                    conv_tc_plan_set_debug(tp, dbg + (size_t)l * 256 * 32);
+                    rc = conv_tc_launch(tp, s);
+                }
+                cudaStreamSynchronize(s);
+                std::vector<unsigned long long> hv((size_t)L * 256 * 32);
+                cudaMemcpy(hv.data(), dbg, hv.size() * 8, cudaMemcpyDeviceToHost);
+                unsigned long long base = ~0ull;
+                for (int c = 0; c < G; ++c) if (hv[c * 32 + 7] < base) base = hv[c * 32 + 7];
+                for (int l = 0; l < L; ++l) {
+                    unsigned long long s0 = ~0ull, s1 = 0, e0 = ~0ull, e1 = 0;
+                    for (int c = 0; c < G; ++c) {
+                        const unsigned long long* o = hv.data() + ((size_t)l * 256 + c) * 32;
+                        if (o[7] < s0) s0 = o[7]; if (o[7] > s1) s1 = o[7];
+                        if (o[15] < e0) e0 = o[15]; if (o[15] > e1) e1 = o[15];
+                    }
+                    fprintf(stderr, "[conv timing] launch %d: CTA start %.1f..%.1f us, CTA end %.1f..%.1f us (globaltimer, rel.)\n", l,
+                            (s0 - base) * 1e-3, (s1 - base) * 1e-3, (e0 - base) * 1e-3, (e1 - base) * 1e-3);
+                }
+                const unsigned long long* h = hv.data() + (size_t)(L - 1) * 256 * 32;
+                {
+                    double mean = 0;
+                    for (int c = 0; c < G; ++c) mean += (double)(h[c * 32 + 15] - h[c * 32 + 7]);
+                    fprintf(stderr, "[conv timing] mean CTA lifetime %.1f us; per CTA (cta:smid:us:tiles:issue_cyc:full_wait_cyc):", mean / G * 1e-3);
+                    for (int c = 0; c < G; ++c)
+                        fprintf(stderr, " %d:%llu:%.0f:%llu:%llu:%llu", c, h[c * 32 + 4] >> 32, (h[c * 32 + 15] - h[c * 32 + 7]) * 1e-3,
+                                h[c * 32 + 4] & 0xffffffffull, h[c * 32 + 2], h[c * 32 + 1]);
+                    fprintf(stderr, "\n");
+                    {
+                        unsigned long long mn = ~0ull, mx = 0, sm = 0, fmn = ~0ull, fmx = 0;
+                        for (int c = 0; c < G; ++c) {
+                            const unsigned long long v = h[c * 32 + 17], f = h[c * 32 + 16];
+                            if (v < mn) mn = v; if (v > mx) mx = v; sm += v;
+                            if (f < fmn) fmn = f; if (f > fmx) fmx = f;
+                        }
+                        fprintf(stderr, "[conv timing] per-CTA ticket phase: min %llu mean %llu max %llu cycles; fence+sync min %llu max %llu\n",
+                                mn, sm / G, mx, fmn, fmx);
+                    }
+                    fprintf(stderr, "[conv timing] CTA 0 arrival at 2nd barrier (cycles after 1st), warps 0..7: %llu %llu %llu %llu %llu %llu %llu %llu\n",
+                            h[24], h[25], h[26], h[27], h[28], h[29], h[30], h[31]);
+                    int slow = 0;
+                    for (int c = 0; c < G; ++c) if (h[c * 32 + 15] > h[slow * 32 + 15]) slow = c;
+                    fprintf(stderr, "[conv timing] last CTA %d: teardown cycles: fence+sync %llu, tickets %llu, fence2 %llu, finalize %llu (nfin %llu) atomic %llu dealloc %llu\n",
+                            slow, h[slow * 32 + 16], h[slow * 32 + 17], h[slow * 32 + 18], h[slow * 32 + 19], h[slow * 32 + 20], h[slow * 32 + 21], h[slow * 32 + 22]);
+                }
+                for (int c : {0, 73, 147})
+                    fprintf(stderr, "[conv timing] cta %d: mma{tempty %llu full %llu issue %llu commit %llu n %llu loop %llu} "
+                            "producer{wait_empty %llu} epi{wait_tfull %llu tmem_ld %llu stats_ring %llu loop %llu} "
+                            "prologue %llu main %llu total %llu cycles = %llu ns\n", c,
+                            h[c * 32 + 0], h[c * 32 + 1], h[c * 32 + 2], h[c * 32 + 3], h[c * 32 + 4] & 0xffffffffull, h[c * 32 + 5], h[c * 32 + 6],
+                            h[c * 32 + 8], h[c * 32 + 9], h[c * 32 + 13], h[c * 32 + 14], h[c * 32 + 10], h[c * 32 + 11], h[c * 32 + 12],
+                            h[c * 32 + 15] - h[c * 32 + 7]);
+                conv_tc_plan_set_debug(tp, nullptr);
+                cudaFree(dbg);
+            }
             if (const char* reps_env = getenv("GTTS_CONV_REPS")) {
                 const int reps = atoi(reps_env);
                 cudaEvent_t e0, e1;

@@ -66,6 +66,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             uint32_t phase = 0;
             const uint32_t rank = p.mc ? cluster_ctarank() : 0u;
             for (int it = 0; it < n_it; ++it) {
+                if (kStats && (it == n_it - 8 || it == n_it - 1)) prefetch_l2(p.e.gn_counters);   // see conv_tc_halo.cu
                 const int tile = (int)blockIdx.x + it * G;
                 const bool dummy = tile >= p.num_tiles;              // only with multicast: keeps the pair in lockstep
                 const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h;
@@ -104,8 +105,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         }
     } else if (warp == 1) {
         // ================================================================ MMA issuer
-        // One elected lane issues everything; the other lanes only shadow the barrier waits.
-        const bool leader = elect_one();
+        // Converged warp, elect.sync directly on the tcgen05 branch (bare UTCHMMA in SASS; see conv_tc_halo.cu).
         const int nstage = p.stages;
         const uint64_t a_desc0 = make_sw128_kmajor_desc(smem_u32(smem));
         const uint64_t b_desc0 = make_sw128_kmajor_desc(smem_u32(smem) + kABytes);
@@ -121,7 +121,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                if (leader) {
+                if (elect_one()) {
                     const uint64_t adesc = a_desc0 + (uint64_t)stage * stage_step;
                     const uint64_t bdesc = b_desc0 + (uint64_t)stage * stage_step;
                     if (!(p.dbg & 1)) {
@@ -134,10 +134,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     else tc_commit(&empty[stage]);                  // smem slot free when these MMAs retire
                     if (kb == nkb - 1) tc_commit(&sh.tfull[buf]);   // accumulator complete
                 }
+                __syncwarp();
                 if (++stage == nstage) { stage = 0; phase ^= 1u; }
             }
         }
-        __syncwarp();
     } else if (warp == 3) {
         tc_stats_loop<kStats>(p, sh, lane);
     } else if (warp >= 4) {
@@ -276,6 +276,8 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
 }
 
 void conv_tc_plan_destroy(TcConvPlan* p) { delete p; }
+int conv_tc_plan_grid(const TcConvPlan* p) { return p->grid; }
+void conv_tc_plan_set_debug(TcConvPlan* p, unsigned long long* dbg_out) { p->p.dbg_out = dbg_out; }
 
 namespace {
 template <int N, bool kStats, bool kRes, bool kMask>

@@ -10,7 +10,7 @@ namespace gtts {
 namespace tc {
 
 constexpr int kABytes = 128 * 128;                 // 128 pixel rows x 64 bf16
-constexpr int kMiscBytes = 4096;                   // barriers + epilogue scratch
+constexpr int kMiscBytes = 6144;                   // barriers + epilogue scratch
 constexpr int kHaloABytes = 18 * 16 * 128;         // halo box: 18 rows x 16 pixels x 64 bf16
 constexpr int kStatSlots = 8;                      // ring of per-tile GroupNorm partials (epilogue warps -> stats warp)
 constexpr int kThreads = 640;                      // warps 0-3: TMA, MMA, TMEM alloc, stats; warps 4-19: two epilogue groups
@@ -23,6 +23,7 @@ struct TcParams {
     int stride2, w_batch_rows, num_tiles, a_bytes, stages;
     int halo_mode, b_slots, b_resident, halo_prefetch;   // conv_tc_halo.cu only
     int mc;                                        // 1: 2-CTA cluster, weight tiles multicast (conv_tc.cu)
+    unsigned long long* dbg_out;                   // optional per-CTA cycle counters (GTTS_CONV_TIMING), 16 per CTA
     int dbg;                                       // experiment switches (GTTS_CONV_DBG): 1 no MMA issue, 2 no epilogue work, 4 no A loads (halo), 8 no stats ring
     int8_t dy[4][9], dx[4][9];
     int wrow[4][9];
@@ -31,7 +32,7 @@ struct TcParams {
 };
 
 // misc shared-memory block layout (relative to `misc`)
-//   [0,   768)  mbarriers + TMEM slot   [768, 1792) bias[256]   [1792, 3840) stats ring   [3840, 4096) finalize list
+//   [0,   768)  mbarriers + TMEM slot   [768, 1792) bias[256]   [1792, 3840) stats ring   [3840, 4096) tail flags   [4096, 6144) per-sample statistics rows
 struct TcShared {
     uint64_t *full, *empty, *tfull, *tempty, *sfull, *sempty, *fullb, *emptyb;
     uint32_t* tmem_slot;
@@ -137,7 +138,7 @@ __device__ __forceinline__ uint32_t tc_prologue(const TcParams& p, const TcShare
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < nfull; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], p.mc ? 2 : 1); }
         for (int s = 0; s < nfullb; ++s) { mbar_init(&sh.fullb[s], 1); mbar_init(&sh.emptyb[s], 1); }
-        for (int i = 0; i < acc_bufs<N>(); ++i) { mbar_init(&sh.tfull[i], 1); mbar_init(&sh.tempty[i], 256); }
+        for (int i = 0; i < acc_bufs<N>(); ++i) { mbar_init(&sh.tfull[i], 1); mbar_init(&sh.tempty[i], 8); }   // one arrive per epilogue warp
         for (int i = 0; i < kStatSlots; ++i) { mbar_init(&sh.sfull[i], 8); mbar_init(&sh.sempty[i], 1); }
         mbar_fence_init();
     } else if (warp == 2) {
@@ -170,13 +171,19 @@ __device__ __forceinline__ void tc_stats_loop(const TcParams& p, const TcShared&
         // value k (0..7 sums, 8..15 sums of squares) of group g = k & 7 lives in column half g >> 2
         const int g = lane & 7, which = (lane >> 3) & 1, half = g >> 2, idx = which * 4 + (g & 3);
         const int n_it = tc_num_iters(p);
+        // Per-sample rows are staged in shared memory and written to global memory only at the very end, all samples at
+        // once: the finalising CTA then finds every row in L2 (rows written 100+ us earlier had been evicted to DRAM by
+        // the kernel's own output stream, and reading them back cost ~5 us of tail).  Untouched samples read as zero.
+        float* s_rows = reinterpret_cast<float*>(sh.misc + 4096);    // [B <= 32][16]
+        for (int i = lane; i < p.B * 16; i += 32) s_rows[i] = 0.f;
+        __syncwarp();
         for (int it = 0; it < n_it; ++it) {
             const int tile = (int)blockIdx.x + it * G;
             const int slot = it % kStatSlots;
             const bool dummy = tile >= p.num_tiles;
             const int b = dummy ? cur_b : tile / tiles_per_phase;
             if (b != cur_b) {
-                if (cur_b >= 0 && lane < 16) e.gn_partials[((size_t)cur_b * G + blockIdx.x) * 16 + lane] = acc;
+                if (cur_b >= 0 && lane < 16) s_rows[cur_b * 16 + lane] = acc;
                 cur_b = b;
                 acc = 0.f;
             }
@@ -188,7 +195,10 @@ __device__ __forceinline__ void tc_stats_loop(const TcParams& p, const TcShared&
             __syncwarp();
             if (lane == 0) mbar_arrive(&sempty[slot]);
         }
-        if (cur_b >= 0 && lane < 16) e.gn_partials[((size_t)cur_b * G + blockIdx.x) * 16 + lane] = acc;
+        if (cur_b >= 0 && lane < 16) s_rows[cur_b * 16 + lane] = acc;
+        __syncwarp();
+        for (int i = lane; i < p.B * 16; i += 32)                    // two 64-byte rows per warp-wide store
+            e.gn_partials[((size_t)(i >> 4) * G + blockIdx.x) * 16 + (i & 15)] = s_rows[i];
     }
 }
 
@@ -214,6 +224,8 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
     const int G = (int)gridDim.x;
     tw.init(p, (int)blockIdx.x + grp * G, 2 * G);
     const int n_it = tc_num_iters(p);
+    long long c_wait = 0, c_ld = 0, c_sring = 0;
+    const long long te0 = clock64();
     for (int it = grp; it < n_it; it += 2, tw.advance(2 * G)) {
         const int buf = it % kBufs;
         const int b = tw.b, ph = tw.ph;
@@ -226,9 +238,11 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
         if (kMask) m = valid ? e.mask[(size_t)b * p.Wout + ow] : 0.f;
         const float2 m2 = make_float2(m, m);
 
+        const long long tq0 = clock64();
         mbar_wait(&sh.tfull[buf], (uint32_t)(it / kBufs) & 1u);
         tc_fence_after();
-        if (p.dbg & 2) { tc_fence_before(); mbar_arrive(&sh.tempty[buf]); if (kStats && !(p.dbg & 8)) { const int slot = it % kStatSlots; mbar_wait(&sh.sempty[slot], ((uint32_t)(it / kStatSlots) & 1u) ^ 1u); __syncwarp(); if (lane == 0) mbar_arrive(&sh.sfull[slot]); } continue; }
+        c_wait += clock64() - tq0;
+        if (p.dbg & 2) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&sh.tempty[buf]); if (kStats && !(p.dbg & 8)) { const int slot = it % kStatSlots; mbar_wait(&sh.sempty[slot], ((uint32_t)(it / kStatSlots) & 1u) ^ 1u); __syncwarp(); if (lane == 0) mbar_arrive(&sh.sfull[slot]); } continue; }
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * N + cbase);
 
         float2 ssum[4], ssq[4];                                      // per local group: packed (even, odd) columns
@@ -238,12 +252,16 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
 #pragma unroll
         for (int c0 = 0; c0 < kColsPerWarp; c0 += 32) {
             uint32_t r[32];
+            const long long tl = clock64();
             tmem_ld32(taddr + (uint32_t)c0, r);
             tmem_ld_wait();
+            c_ld += clock64() - tl;
             if (c0 + 32 >= kColsPerWarp) {
                 // last TMEM read of this buffer: hand it back to the MMA warp before the arithmetic and stores
+                // (one arrive per warp: 256 threads hammering one mbarrier word cost ~0.5 us per tile)
                 tc_fence_before();
-                mbar_arrive(&sh.tempty[buf]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh.tempty[buf]);
             }
             float2 f[16];
 #pragma unroll
@@ -310,11 +328,18 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
             for (int g = 0; g < 4; ++g) { st[g] = ssum[g].x + ssum[g].y; st[4 + g] = ssq[g].x + ssq[g].y; }
             const float t = warp_reduce8(st, lane);
             const int slot = it % kStatSlots;
+            const long long ts = clock64();
             mbar_wait(&sh.sempty[slot], ((uint32_t)(it / kStatSlots) & 1u) ^ 1u);
+            c_sring += clock64() - ts;
             if ((lane & 3) == 0) sh.s_ring[(slot * 8 + ew) * 8 + (lane >> 2)] = t;
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh.sfull[slot]);             // release: orders the ring writes of this warp
         }
+    }
+    if (p.dbg_out && ew16 == 0 && lane == 0) {
+        unsigned long long* o = p.dbg_out + blockIdx.x * 32;
+        o[8] = (unsigned long long)c_wait; o[9] = (unsigned long long)c_ld; o[13] = (unsigned long long)c_sring;
+        o[14] = (unsigned long long)(clock64() - te0);
     }
 }
 
@@ -324,66 +349,101 @@ __device__ __forceinline__ void tc_teardown(const TcParams& p, const TcShared& s
                                             int tid, int warp, int lane) {
     constexpr int kGsz = N / 8;
     uint8_t* misc = sh.misc;
-    const int tiles_per_phase = p.tiles_h * p.tiles_w;
-    if (kStats) __threadfence();
+    const long long td0 = clock64();
+    // only the statistics warp has written anything the finalising CTA will read (the partial rows); fencing the
+    // epilogue warps too would make every CTA wait ~8 us for its streaming output stores to be acknowledged
+    if (kStats && warp == 3) __threadfence();
     tc_fence_before();
     __syncthreads();
+    const long long td1 = clock64();
     if (p.mc) cluster_sync();                      // nobody leaves while the peer may still multicast into it
     if (warp == 2) {
+        const long long tq = clock64();
         tc_fence_after();
         tmem_dealloc(tmem_base, acc_bufs<N>() * N);
+        if (p.dbg_out && lane == 0) p.dbg_out[blockIdx.x * 32 + 22] = (unsigned long long)(clock64() - tq);
     }
     if (kStats) {
+        // ONE ticket per CTA (not one per sample).  The CTA that draws the last ticket reduces every sample: one warp per sample,
+        // all partial rows of a sample requested before the first add (one L2 round trip), double accumulation in a
+        // fixed order -> deterministic.  (The previous tail -- per-sample tickets, samples reduced one after another --
+        // cost 55 us at 16 samples because the last CTA is last for every sample.)
         const ConvEpilogue& e = p.e;
-        int* s_nfin = reinterpret_cast<int*>(misc + 3840);
-        int* s_fin = s_nfin + 1;
-        double* s_red = reinterpret_cast<double*>(smem);             // pipeline buffers are idle now: [24][16]
-        if (tid == 0) *s_nfin = 0;
+        int* s_last = reinterpret_cast<int*>(misc + 3840);
+        if (tid == 0) {
+            // two-level ticket: same-address atomics serialise at ~100 cycles each in L2, and all CTAs arrive together
+            // (148 on one word measured 14k cycles); 16 group counters then one root counter cost ~(10 + 16) x 100.
+            const unsigned int grp = blockIdx.x & 15u;
+            const unsigned int gsize = (gridDim.x - grp + 15u) >> 4;             // CTAs with this residue
+            const unsigned int ngroups = gridDim.x < 16u ? gridDim.x : 16u;
+            int last = 0;
+            if (p.dbg & 16) {
+            } else if (atomicAdd(&e.gn_counters[1 + grp], 1u) == gsize - 1u) {
+                e.gn_counters[1 + grp] = 0u;                                     // whole group has arrived: reset for the next launch
+                __threadfence();
+                last = atomicAdd(&e.gn_counters[0], 1u) == ngroups - 1u;
+            }
+            *s_last = last;
+        }
+        if (p.dbg_out && lane == 0 && warp < 8) p.dbg_out[blockIdx.x * 32 + 24 + warp] = (unsigned long long)(clock64() - td1);
         __syncthreads();
-        if (warp == 0) {
-            const int G = (int)gridDim.x, bx = (int)blockIdx.x, tps = tiles_per_phase;
-            for (int b = lane; b < p.B; b += 32) {
-                const int lo = b * tps, hi = lo + tps - 1;           // tiles of sample b: lo..hi; mine: bx + i*G
-                const int i_min = lo > bx ? (lo - bx + G - 1) / G : 0;
-                const int i_max = hi >= bx ? (hi - bx) / G : -1;
-                const int cnt = i_max - i_min + 1;
-                if (cnt > 0) {
-                    const unsigned int old = atomicAdd(&e.gn_counters[b], (unsigned int)cnt);
-                    if (old + (unsigned int)cnt == (unsigned int)tps) s_fin[atomicAdd(s_nfin, 1)] = b;
+        const long long td2 = clock64();
+        if (p.dbg_out && tid == 0) {
+            p.dbg_out[blockIdx.x * 32 + 16] = (unsigned long long)(td1 - td0);
+            p.dbg_out[blockIdx.x * 32 + 17] = (unsigned long long)(td2 - td1);
+        }
+        if (*s_last) {
+            __threadfence();
+            const long long td3 = clock64();
+            const double inv_count = 1.0 / ((double)kGsz * (double)p.Hout * (double)p.Wout);
+            const int G = (int)gridDim.x;
+            const int q = lane & 3, r0 = lane >> 2;                  // float4 column q of partial rows r0, r0 + 8, ...
+            for (int b = warp; b < p.B; b += kThreads / 32) {
+                const float4* pp = reinterpret_cast<const float4*>(e.gn_partials + (size_t)b * G * 16) + q;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                for (int base = 0; base < G; base += 64) {
+                    float4 v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int c = base + r0 + 8 * i;
+                        v[i] = c < G ? __ldcg(pp + (size_t)c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        a0 += (double)v[i].x; a1 += (double)v[i].y; a2 += (double)v[i].z; a3 += (double)v[i].w;
+                    }
+                }
+#pragma unroll
+                for (int off = 4; off < 32; off <<= 1) {
+                    a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+                    a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+                    a3 += __shfl_xor_sync(0xffffffffu, a3, off);
+                }
+                // lanes 0,1 hold the sums of groups 4q..4q+3; lanes 2,3 the matching sums of squares
+                const double q0 = __shfl_sync(0xffffffffu, a0, (lane + 2) & 31), q1 = __shfl_sync(0xffffffffu, a1, (lane + 2) & 31);
+                const double q2 = __shfl_sync(0xffffffffu, a2, (lane + 2) & 31), q3 = __shfl_sync(0xffffffffu, a3, (lane + 2) & 31);
+                if (lane < 2) {
+                    const double su[4] = {a0, a1, a2, a3}, sq[4] = {q0, q1, q2, q3};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double mean = su[j] * inv_count;
+                        double var = sq[j] * inv_count - mean * mean;
+                        if (var < 0.0) var = 0.0;
+                        const int g = lane * 4 + j;
+                        e.gn_stats[((size_t)b * 8 + g) * 2 + 0] = (float)mean;
+                        e.gn_stats[((size_t)b * 8 + g) * 2 + 1] = (float)rsqrt(var + (double)e.gn_eps);
+                    }
                 }
             }
-        }
-        __syncthreads();
-        const int nfin = *s_nfin;
-        if (nfin > 0) {
-            __threadfence();
-            const double inv_count = 1.0 / ((double)kGsz * (double)p.Hout * (double)p.Wout);
-            for (int f = 0; f < nfin; ++f) {
-                const int b = s_fin[f];
-                const int G = (int)gridDim.x, tps = tiles_per_phase;
-                const int lo = b * tps, hi = lo + tps - 1;
-                const int k = tid & 15, slice = tid >> 4;            // kThreads/16 slices of 16 components
-                const float* pp = e.gn_partials + (size_t)b * G * 16 + k;
-                double acc = 0.0;
-                for (int c = slice; c < G; c += kThreads / 16) {
-                    // CTA c contributed to sample b iff it owns a tile in [lo, hi]
-                    const int i_min = lo > c ? (lo - c + G - 1) / G : 0;
-                    const int i_max = hi >= c ? (hi - c) / G : -1;
-                    if (i_max >= i_min) acc += (double)__ldcg(pp + (size_t)c * 16);
-                }
-                s_red[slice * 16 + k] = acc;
+            if (tid == 0) e.gn_counters[0] = 0u;                     // ready for the next launch
+            if (p.dbg_out) {
                 __syncthreads();
-                if (tid < 8) {
-                    double sum = 0.0, sq = 0.0;
-                    for (int sl = 0; sl < kThreads / 16; ++sl) { sum += s_red[sl * 16 + tid]; sq += s_red[sl * 16 + 8 + tid]; }
-                    const double mean = sum * inv_count;
-                    double var = sq * inv_count - mean * mean;
-                    if (var < 0.0) var = 0.0;
-                    e.gn_stats[((size_t)b * 8 + tid) * 2 + 0] = (float)mean;
-                    e.gn_stats[((size_t)b * 8 + tid) * 2 + 1] = (float)(1.0 / sqrt(var + (double)e.gn_eps));
+                if (tid == 0) {
+                    unsigned long long* o = p.dbg_out + blockIdx.x * 32;
+                    o[18] = (unsigned long long)(td3 - td2); o[19] = (unsigned long long)(clock64() - td3);
+                    o[20] = (unsigned long long)p.B;
                 }
-                if (tid == 0) e.gn_counters[b] = 0u;
-                __syncthreads();
             }
         }
     }

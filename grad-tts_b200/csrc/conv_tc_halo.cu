@@ -43,7 +43,11 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         tma_prefetch_desc(&mapA1);
         tma_prefetch_desc(&mapW);
     }
+    const long long tk0 = clock64();
+    unsigned long long gt0 = 0;
+    if (p.dbg_out && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
     const uint32_t tmem_base = tc_prologue<N>(p, sh, p.stages, p.b_slots, tid, warp, lane);
+    if (p.dbg_out && tid == 0) p.dbg_out[blockIdx.x * 32 + 10] = (unsigned long long)(clock64() - tk0);
 
     const int nck = p.nchunk0 + p.nchunk1;
     const int tiles_per_phase = p.tiles_h * p.tiles_w;
@@ -58,6 +62,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             const int nck0 = p.nchunk0;
             const uint32_t a_tx = (uint32_t)(18 * pw * 128);
             TileWalk tw, pf;
+            long long c_pwait = 0;
             tw.init(p, (int)blockIdx.x, G);
             const int pf_dist = p.halo_prefetch;                     // tiles of look-ahead for the L2 prefetch (0 = off)
             if (pf_dist > 0) {
@@ -70,8 +75,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                                             pf.th * 16 - 1, pf.b);
                 }
             }
-            for (; tw.tile < p.num_tiles; tw.advance(G)) {
+            const int n_it = tc_num_iters(p);
+            int it = 0;
+            for (; tw.tile < p.num_tiles; tw.advance(G), ++it) {
                 const int b = tw.b, h0 = tw.th * 16, w0 = tw.tw * 8;
+                // the tail's ticket counters were last touched a launch ago and have been evicted by this kernel's own
+                // traffic; an L2 miss under full load costs ~8 us on the critical tail, so fetch the line ahead of time
+                if (kStats && (it == n_it - 8 || it == n_it - 1)) prefetch_l2(p.e.gn_counters);
                 if (pf_dist > 0 && pf.tile < p.num_tiles) {
                     pf.advance(G);
                     if (pf.tile < p.num_tiles)
@@ -80,7 +90,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                                             pf.th * 16 - 1, pf.b);
                 }
                 for (int ck = 0; ck < nck; ++ck) {
+                    const long long tp0 = clock64();
                     mbar_wait(&sh.empty[sa], pha ^ 1u);
+                    c_pwait += clock64() - tp0;
                     if (dbg & 4) {
                         mbar_arrive(&sh.full[sa]);                   // experiment: no A traffic at all
                     } else {
@@ -108,12 +120,16 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                 }
                 first = false;
             }
+            if (p.dbg_out) p.dbg_out[blockIdx.x * 32 + 6] = (unsigned long long)c_pwait;
         }
     } else if (warp == 1) {
         // ================================================================ MMA issuer
-        // One elected lane issues everything; the other lanes only shadow the barrier waits.  All descriptors are
-        // precomputed: per MMA the issue path is a couple of 64-bit adds.
-        const bool leader = elect_one();
+        // The whole warp runs the loop converged and `elect.sync` sits directly on the branch around the tcgen05
+        // instructions: ptxas then knows exactly one thread is active and emits bare UTCHMMA instead of wrapping each one
+        // in an ELECT/BRA.U.ANY "for each active lane" loop (which it must do under a data-dependent `if (leader)`).
+        // (A second issuing warp on alternate tiles was tried: no gain -- with both feeding the pipe an N=64 MMA still
+        // takes ~65 cycles in this kernel vs 52 in isolation: the tensor pipe's operand reads, 6 KB per MMA, share the
+        // shared-memory port with the TMA fill of the next halo boxes.  The kernel is SMEM-bandwidth bound.)
         const int nstage = p.stages, nslot = p.b_slots, resident = p.b_resident, dbg = p.dbg;
         const uint64_t a_desc0 = make_sw128_kmajor_desc(smem_u32(smem), (uint32_t)(pw * 128), 0u);
         const uint64_t b_desc0 = make_sw128_kmajor_desc(smem_u32(smem_b));
@@ -124,13 +140,21 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         int sa = 0, sb = 0, it = 0;
         uint32_t pha = 0, phb = 0;
         const int n_it = tc_num_iters(p);
+        long long c_tempty = 0, c_full = 0, c_issue = 0, c_commit = 0, c_n = 0;
+        const long long tl0 = clock64();
         for (it = 0; it < n_it; ++it) {
             const int buf = it % acc_bufs<N>();
+            const long long t0 = clock64();
             mbar_wait(&sh.tempty[buf], ((uint32_t)(it / acc_bufs<N>()) & 1u) ^ 1u);
             tc_fence_after();
+            const long long t1 = clock64();
+            c_tempty += t1 - t0;
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
             for (int ck = 0; ck < nck; ++ck) {
+                const long long t2 = clock64();
                 mbar_wait(&sh.full[sa], pha);
+                const long long t2b = clock64();
+                c_full += t2b - t2;
                 const uint64_t adesc = a_desc0 + (uint64_t)sa * a_stage_step;
                 if (resident) {
                     if (it == 0) {
@@ -138,7 +162,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                         for (int tap = 0; tap < 9; ++tap) mbar_wait(&sh.fullb[ck * 9 + tap], 0u);
                     }
                     tc_fence_after();
-                    if (leader) {
+                    if (elect_one()) {
                         const uint64_t bdesc = b_desc0 + (uint64_t)(ck * 9) * b_slot_step;
                         if (!(dbg & 1)) {
 #pragma unroll
@@ -149,15 +173,20 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                                                bdesc + (uint64_t)tap * b_slot_step + (uint64_t)(2 * k), kIdesc,
                                                (uint32_t)((ck | tap | k) != 0));
                         }
+                        const long long t3 = clock64();
                         tc_commit(&sh.empty[sa]);
                         if (ck == nck - 1) tc_commit(&sh.tfull[buf]);
+                        c_issue += t3 - t2b;
+                        c_commit += clock64() - t3;
+                        c_n += 1;
                     }
+                    __syncwarp();
                 } else {
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         mbar_wait(&sh.fullb[sb], phb);
                         tc_fence_after();
-                        if (leader) {
+                        if (elect_one()) {
                             const uint64_t bdesc = b_desc0 + (uint64_t)sb * b_slot_step;
                             if (!(dbg & 1)) {
 #pragma unroll
@@ -171,19 +200,33 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                                 if (ck == nck - 1) tc_commit(&sh.tfull[buf]);
                             }
                         }
+                        __syncwarp();
                         if (++sb == nslot) { sb = 0; phb ^= 1u; }
                     }
                 }
                 if (++sa == nstage) { sa = 0; pha ^= 1u; }
             }
         }
-        __syncwarp();
+        if (p.dbg_out && lane == 0) {                    // lane 0 is the elected lane of a converged warp
+            unsigned long long* o = p.dbg_out + blockIdx.x * 32;
+            o[0] = (unsigned long long)c_tempty; o[1] = (unsigned long long)c_full; o[2] = (unsigned long long)c_issue;
+            unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            o[3] = (unsigned long long)c_commit; o[4] = (unsigned long long)c_n | ((unsigned long long)smid << 32); o[5] = (unsigned long long)(clock64() - tl0);
+        }
     } else if (warp == 3) {
         tc_stats_loop<kStats>(p, sh, lane);
     } else if (warp >= 4) {
         tc_epilogue_loop<N, kStats, false, false>(p, sh, tmem_base, warp, lane);
     }
+    if (p.dbg_out && tid == 0) p.dbg_out[blockIdx.x * 32 + 11] = (unsigned long long)(clock64() - tk0);
     tc_teardown<N, kStats>(p, sh, smem, tmem_base, tid, warp, lane);
+    if (p.dbg_out && tid == 0) {
+        unsigned long long gt1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+        p.dbg_out[blockIdx.x * 32 + 12] = (unsigned long long)(clock64() - tk0);
+        p.dbg_out[blockIdx.x * 32 + 15] = gt1;
+        p.dbg_out[blockIdx.x * 32 + 7] = gt0;
+    }
 }
 
 template <int N, bool kStats>

@@ -540,7 +540,7 @@ struct PlanBuilder {
         pl->step = (int*)pl->mem.alloc(16, true);
         pl->noise_slot = (const float**)pl->mem.alloc(16, true);
         pl->h_dev = (float*)pl->mem.alloc(16, true);
-        pl->counters = (unsigned int*)pl->mem.alloc((size_t)B * 4, true);
+        pl->counters = (unsigned int*)pl->mem.alloc((size_t)(B + 32) * 4, true);   // per-sample tickets or 1 + 16 group tickets
         // GN partial buffer: the largest slot count of any conv (level 0, either tiling)
         {
             ConvGeom g0 = geom_3x3(B, H[0], W[0], 64, 0, 64, 1);

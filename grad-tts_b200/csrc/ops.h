@@ -58,6 +58,10 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
 bool conv_tc_halo_eligible(const ConvGeom& g);
 size_t conv_tc_halo_partials_slots(const ConvGeom& g);
 void conv_tc_plan_destroy(TcConvPlan* p);
+void conv_tc_plan_set_debug(TcConvPlan* p, unsigned long long* dbg_out);   // per-CTA cycle counters (experiments)
+int conv_tc_plan_grid(const TcConvPlan* p);
+int microbench_issue(int N, int n_mma, int n_commit, int iters, int wait_each, int grid, unsigned long long* out_dev,
+                     cudaStream_t stream);                                  // tcgen05 issue-path micro-benchmark
 int conv_tc_launch(const TcConvPlan* p, cudaStream_t stream);
 size_t conv_tc_partials_slots(const ConvGeom& g);
 

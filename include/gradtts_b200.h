@@ -96,6 +96,11 @@ int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, i
                    const void* residual, const float* mask, void* out, float* gn_stats, int per_sample_weights,
                    void* stream);
 
+/* Test hook: tcgen05 issue-path micro-benchmark (cycles per CTA, averaged over `grid` CTAs): `iters` rounds of
+ * {n_mma tcgen05.mma M128xNx16, n_commit tcgen05.commit}, optionally waiting on the last commit every round. */
+int gtts_test_issue_microbench(int N, int n_mma, int n_commit, int iters, int wait_each, int grid, double* issue_cycles,
+                               double* total_cycles);
+
 #ifdef __cplusplus
 }
 #endif

@@ -161,6 +161,10 @@ def stage_convdbg():
     cin, cout, H, W, B = [int(v) for v in os.environ.get("GTTS_SHAPE", "64,64,80,1720,8").split(",")]
     c = gu.conv_case(0, B, H, W, cin, 0, cout, seed=1)
     os.environ["GTTS_CONV_REPS"] = "5"
+    if os.environ.get("GTTS_CONV_TIMING"):
+        os.environ["GTTS_CONV_DBG"] = os.environ.get("GTTS_CONV_DBG_T", "0")
+        gu.run_conv(c, 3, 1, want_stats=True)
+        return
     for impl in (1, 3):
         if impl == 3 and cout > 128:
             continue
@@ -171,6 +175,20 @@ def stage_convdbg():
                 print(f"impl={impl} dbg={dbg} mc={mc}", flush=True)
                 gu.run_conv(c, impl, 1, want_stats=True)
     os.environ["GTTS_CONV_DBG"] = "0"
+
+
+def stage_mbench():
+    """tcgen05 issue-path micro-benchmark: what do commits cost relative to MMAs?"""
+    import ctypes
+    lib = pkg._lib.load()
+    a, b = ctypes.c_double(), ctypes.c_double()
+    iters = 200
+    for N in (64, 128, 256):
+        for (nm, nc, we) in [(0, 1, 0), (0, 2, 0), (0, 1, 1), (36, 0, 0), (36, 1, 0), (36, 2, 0), (36, 4, 0), (36, 1, 1), (36, 2, 1),
+                             (4, 0, 0), (4, 1, 0), (4, 1, 1), (8, 1, 0), (16, 1, 0), (72, 2, 0)]:
+            pkg._lib.check(lib.gtts_test_issue_microbench(N, nm, nc, iters, we, 148, ctypes.byref(a), ctypes.byref(b)), "mb")
+            print(f"N={N:3d} mma={nm:2d} commit={nc} wait_each={we}: issue {a.value / iters:8.1f}  total {b.value / iters:8.1f} cycles/round"
+                  + (f"  ({b.value / iters / nm:6.1f}/mma)" if nm else ""), flush=True)
 
 
 def stage_profile():
@@ -204,6 +222,6 @@ if __name__ == "__main__":
     print(f"===== stage {st} on {torch.cuda.get_device_name(0)}", flush=True)
     {"mas": stage_mas, "conv_ffma": lambda: (stage_conv(0, 0), stage_conv(0, 1)), "conv_tc": lambda: stage_conv(1, 1),
      "dec_fp32": lambda: stage_dec("fp32"), "dec_bf16_ffma": lambda: stage_dec("bf16", 0),
-     "dec_bf16_tc": lambda: stage_dec("bf16", 1), "perf": stage_perf, "profile": stage_profile, "halo": stage_halo, "convdbg": stage_convdbg}[st]()
+     "dec_bf16_tc": lambda: stage_dec("bf16", 1), "perf": stage_perf, "profile": stage_profile, "halo": stage_halo, "convdbg": stage_convdbg, "mbench": stage_mbench}[st]()
     torch.cuda.synchronize()
     print(f"===== stage {st} done", flush=True)
