@@ -289,23 +289,24 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_p
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(smem_ptr)));
 }
 
+// Structure (FlashAttention-2 style, everything between two x tiles is warp-local): warp w owns the 16 k-channels
+// d = 16w..16w+15 for ALL pixels of a 64-pixel tile:  k^T[16 d][64 px] = Wk[16 d][C] . x^T  (Wk fragments live in
+// registers for the whole kernel), so the running max / sum of a row never leave the warp (two shuffles), the fp32
+// accumulator fragments of k^T are exactly the bf16 A fragments of P for  S[16 d][C] += P[16 d][64 px] . x[64 px][C],
+// and the only CTA-wide synchronisation is the hand-over of the cp.async x-tile ring (one __syncthreads per tile).
+constexpr int kXkStages = 3;
+
 template <int C>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, C == 64 ? 2 : 1)
 attn_xk_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ wk /*[256][C]: k rows, then v rows*/,
                float* __restrict__ partials, int n, int chunks, int chunk_len) {
     pdl_trigger();
     pdl_wait();
     constexpr int kXP = C + 8;                    // bf16 pitch of x / Wk rows (16-byte pad: conflict-free ldmatrix)
-    constexpr int kKP = 128 + 8;                  // bf16 pitch of the k/p tile
-    constexpr int kPart = 256 + 128 * C;          // floats per partial: m[128], l[128], S[128][C]
+    constexpr int kTile = kXkSub * kXP;
     extern __shared__ __align__(16) __nv_bfloat16 xs_all[];
-    __nv_bfloat16* wks = xs_all;                                   // [128][kXP]
-    __nv_bfloat16* xs = wks + 128 * kXP;                           // [2][64][kXP]
-    __nv_bfloat16* kt = xs + 2 * kXkSub * kXP;                     // [64][kKP]
-    float* s_m = reinterpret_cast<float*>(kt + kXkSub * kKP);      // [128] running max
-    float* s_scale = s_m + 128;                                    // [128]
-    float* s_l = s_scale + 128;                                    // [128]
-    float* s_pmax = s_l + 128;                                     // [4][128] partial maxima / sums
+    __nv_bfloat16* wks = xs_all;                                   // [128][kXP]  Wk, later Wv
+    __nv_bfloat16* xs = wks + 128 * kXP;                           // [kXkStages][64][kXP]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int chunk = blockIdx.x, b = blockIdx.y;
@@ -317,126 +318,112 @@ attn_xk_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
         const int row = i / (C / 8), c8 = i % (C / 8);
         *reinterpret_cast<uint4*>(&wks[row * kXP + c8 * 8]) = __ldg(reinterpret_cast<const uint4*>(wk + (size_t)row * C + c8 * 8));
     }
-    if (tid < 128) { s_m[tid] = -INFINITY; s_l[tid] = 0.f; }
-    auto fetch = [&](int p0, __nv_bfloat16* dst) {
-        for (int i = tid; i < kXkSub * (C / 8); i += 256) {
-            const int px = i / (C / 8), c8 = i % (C / 8), nn = p0 + px;
-            __nv_bfloat16* d = &dst[px * kXP + c8 * 8];
-            if (nn < n1) cp_async16(d, xb + (size_t)nn * C + c8 * 8);
-            else *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);      // x = 0 beyond the chunk
+    auto fetch = [&](int p0, __nv_bfloat16* dst) {                  // always commits a group (possibly empty)
+        if (p0 < n1) {
+            for (int i = tid; i < kXkSub * (C / 8); i += 256) {
+                const int px = i / (C / 8), c8 = i % (C / 8), nn = p0 + px;
+                __nv_bfloat16* d = &dst[px * kXP + c8 * 8];
+                if (nn < n1) cp_async16(d, xb + (size_t)nn * C + c8 * 8);
+                else *reinterpret_cast<uint4*>(d) = make_uint4(0u, 0u, 0u, 0u);  // x = 0 beyond the chunk
+            }
         }
         cp_async_commit();
     };
+    fetch(n0, xs);
+    fetch(n0 + kXkSub, xs + kTile);
+
     float acc[C / 8][4];                                            // S rows 16*warp + {g, g+8}, all C columns
 #pragma unroll
     for (int i = 0; i < C / 8; ++i)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;       // rows g and g+8 (replicated over the 4 t-lanes)
+    uint32_t afw[C / 16][4];                                        // this warp's 16 Wk rows as A fragments
 
-    fetch(n0, xs);
-    int ib = 0;
-    for (int p0 = n0; p0 < n1; p0 += kXkSub, ib ^= 1) {
-        __nv_bfloat16* xt = xs + ib * (kXkSub * kXP);
-        if (p0 + kXkSub < n1) { fetch(p0 + kXkSub, xs + (ib ^ 1) * (kXkSub * kXP)); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        __syncthreads();                                            // x tile (and, first time, Wk) visible to all
-        // ---- GEMM1: k[64 px][128] = x[64][C] . Wk^T ; warp -> 16 pixel rows x 64 k-channels
+    int ib = 0, it = 0;
+    for (int p0 = n0; p0 < n1; p0 += kXkSub, ++it) {
+        const __nv_bfloat16* xt = xs + ib * kTile;
+        cp_async_wait<1>();                                         // tile `it` has landed (tile it+1 may be in flight)
+        __syncthreads();                                            // ... for everyone; tile it-1's buffer is free
         {
-            const int px0 = (warp & 3) * 16, nc0 = (warp >> 2) * 64;
-            float kc[8][4];
+            int nb = ib + 2; if (nb >= kXkStages) nb -= kXkStages;
+            fetch(p0 + 2 * kXkSub, xs + nb * kTile);
+        }
+        if (it == 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int ks = 0; ks < C / 16; ++ks)
+                ldmatrix_x4(afw[ks], &wks[(warp * 16 + (j & 1) * 8 + r) * kXP + ks * 16 + (j >> 1) * 8]);
+        }
+        // ---- GEMM1: k^T[16 d][64 px]; n-tile nt = pixels 8nt..8nt+7
+        float kc[8][4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) kc[i][q] = 0.f;
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int ks = 0; ks < C / 16; ++ks) {
-                uint32_t af[4];
-                ldmatrix_x4(af, &xt[(px0 + (j & 1) * 8 + r) * kXP + ks * 16 + (j >> 1) * 8]);
+            for (int q = 0; q < 4; ++q) kc[i][q] = 0.f;
 #pragma unroll
-                for (int np = 0; np < 4; ++np) {
-                    uint32_t bf[4];                                 // two n-tiles: (b0,b1) of n-tile 2np, then of 2np+1
-                    ldmatrix_x4(bf, &wks[(nc0 + np * 16 + (j >> 1) * 8 + r) * kXP + ks * 16 + (j & 1) * 8]);
-                    mma_bf16_16816(kc[2 * np], af, bf[0], bf[1]);
-                    mma_bf16_16816(kc[2 * np + 1], af, bf[2], bf[3]);
-                }
+        for (int ks = 0; ks < C / 16; ++ks) {
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {
+                uint32_t bf[4];                                     // (b0,b1) of n-tile 2np, then of 2np+1
+                ldmatrix_x4(bf, &xt[(np * 16 + (j >> 1) * 8 + r) * kXP + ks * 16 + (j & 1) * 8]);
+                mma_bf16_16816(kc[2 * np], afw[ks], bf[0], bf[1]);
+                mma_bf16_16816(kc[2 * np + 1], afw[ks], bf[2], bf[3]);
             }
-            const int nvalid = n1 - p0;                             // pixels beyond the chunk get k = -inf
+        }
+        const int nvalid = n1 - p0;
+        if (nvalid < kXkSub) {                                      // pixels beyond the chunk: k = -inf -> p = 0
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int col = nc0 + i * 8 + 2 * t;
-                float v0 = kc[i][0], v1 = kc[i][1], v2 = kc[i][2], v3 = kc[i][3];
-                if (px0 + g >= nvalid) { v0 = -INFINITY; v1 = -INFINITY; }
-                if (px0 + g + 8 >= nvalid) { v2 = -INFINITY; v3 = -INFINITY; }
-                *reinterpret_cast<__nv_bfloat162*>(&kt[(px0 + g) * kKP + col]) = __floats2bfloat162_rn(v0, v1);
-                *reinterpret_cast<__nv_bfloat162*>(&kt[(px0 + g + 8) * kKP + col]) = __floats2bfloat162_rn(v2, v3);
+                const int col = i * 8 + 2 * t;
+                if (col >= nvalid) { kc[i][0] = -INFINITY; kc[i][2] = -INFINITY; }
+                if (col + 1 >= nvalid) { kc[i][1] = -INFINITY; kc[i][3] = -INFINITY; }
             }
         }
-        __syncthreads();
-        // ---- column maxima: thread -> column pair cp, pixel quarter pq
-        const int cp = tid & 63, pq = tid >> 6;
-        uint32_t* kw = reinterpret_cast<uint32_t*>(kt) + cp;        // word of columns 2cp, 2cp+1, pixel 0
-        constexpr int kWP = kKP / 2;
-        {
-            float x0 = -INFINITY, x1 = -INFINITY;
+        // ---- online softmax over the pixels (rows of k^T), warp-local
+        float x0 = -INFINITY, x1 = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const uint32_t w = kw[(pq * 16 + i) * kWP];
-                x0 = fmaxf(x0, __uint_as_float(w << 16));
-                x1 = fmaxf(x1, __uint_as_float(w & 0xffff0000u));
-            }
-            s_pmax[pq * 128 + 2 * cp] = x0;
-            s_pmax[pq * 128 + 2 * cp + 1] = x1;
+        for (int i = 0; i < 8; ++i) {
+            x0 = fmaxf(x0, fmaxf(kc[i][0], kc[i][1]));
+            x1 = fmaxf(x1, fmaxf(kc[i][2], kc[i][3]));
         }
-        __syncthreads();
-        if (tid < 128) {
-            const float mx = fmaxf(fmaxf(s_pmax[tid], s_pmax[128 + tid]), fmaxf(s_pmax[256 + tid], s_pmax[384 + tid]));
-            const float mo = s_m[tid], mn = fmaxf(mo, mx);
-            s_scale[tid] = __expf(mo - mn);                         // exp(-inf) = 0 on the first sub-tile
-            s_m[tid] = mn;
+        x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1)); x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 2));
+        x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
+        const float mn0 = fmaxf(m0, x0), mn1 = fmaxf(m1, x1);
+        const float f0 = __expf(m0 - mn0), f1 = __expf(m1 - mn1);   // exp(-inf) = 0 on the first tile
+        m0 = mn0; m1 = mn1;
+        uint32_t pa[4][4];                                          // P as A fragments: k16 slice ks2 = pixels 16ks2..
+        float s0 = 0.f, s1 = 0.f;                                   // row sums of the ROUNDED values (what GEMM2 sees)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(__expf(kc[i][0] - mn0), __expf(kc[i][1] - mn0));
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(__expf(kc[i][2] - mn1), __expf(kc[i][3] - mn1));
+            const uint32_t w0 = *reinterpret_cast<uint32_t*>(&h0), w1 = *reinterpret_cast<uint32_t*>(&h1);
+            s0 += __uint_as_float(w0 << 16) + __uint_as_float(w0 & 0xffff0000u);
+            s1 += __uint_as_float(w1 << 16) + __uint_as_float(w1 & 0xffff0000u);
+            pa[i >> 1][(i & 1) * 2 + 0] = w0;                       // a0/a2: row g,   k 2t.. (+8 for the odd n-tile)
+            pa[i >> 1][(i & 1) * 2 + 1] = w1;                       // a1/a3: row g+8
         }
-        __syncthreads();
-        // ---- p = exp(k - m) in place (bf16), partial row sums of the rounded values
-        {
-            const float m0 = s_m[2 * cp], m1 = s_m[2 * cp + 1];
-            float s0 = 0.f, s1 = 0.f;
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        l0 = fmaf(l0, f0, s0);
+        l1 = fmaf(l1, f1, s1);
+        // ---- GEMM2: S[16 d][C] = S * f + P[16 d][64 px] . x[64 px][C]
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                uint32_t* wp = kw + (pq * 16 + i) * kWP;
-                const uint32_t w = *wp;
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(__expf(__uint_as_float(w << 16) - m0),
-                                                          __expf(__uint_as_float(w & 0xffff0000u) - m1));
-                const uint32_t pw = *reinterpret_cast<uint32_t*>(&h2);
-                *wp = pw;
-                s0 += __uint_as_float(pw << 16);
-                s1 += __uint_as_float(pw & 0xffff0000u);
-            }
-            s_pmax[pq * 128 + 2 * cp] = s0;
-            s_pmax[pq * 128 + 2 * cp + 1] = s1;
-        }
-        __syncthreads();
-        if (tid < 128)
-            s_l[tid] = fmaf(s_l[tid], s_scale[tid], (s_pmax[tid] + s_pmax[128 + tid]) + (s_pmax[256 + tid] + s_pmax[384 + tid]));
-        // ---- GEMM2: S[128 d][C] += P^T[128][64 px] . x[64 px][C] ; warp -> d rows 16*warp .. +15
-        {
-            const float f0 = s_scale[warp * 16 + g], f1 = s_scale[warp * 16 + g + 8];
+        for (int i = 0; i < C / 8; ++i) { acc[i][0] *= f0; acc[i][1] *= f0; acc[i][2] *= f1; acc[i][3] *= f1; }
 #pragma unroll
-            for (int i = 0; i < C / 8; ++i) { acc[i][0] *= f0; acc[i][1] *= f0; acc[i][2] *= f1; acc[i][3] *= f1; }
+        for (int ks = 0; ks < kXkSub / 16; ++ks) {
 #pragma unroll
-            for (int ks = 0; ks < kXkSub / 16; ++ks) {
-                const int pxb = ks * 16;
-                uint32_t af[4];
-                ldmatrix_x4_trans(af, &kt[(pxb + (j >> 1) * 8 + r) * kKP + warp * 16 + (j & 1) * 8]);
-#pragma unroll
-                for (int np = 0; np < C / 16; ++np) {
-                    uint32_t bf[4];
-                    ldmatrix_x4_trans(bf, &xt[(pxb + (j & 1) * 8 + r) * kXP + (np * 2 + (j >> 1)) * 8]);
-                    mma_bf16_16816(acc[2 * np], af, bf[0], bf[1]);
-                    mma_bf16_16816(acc[2 * np + 1], af, bf[2], bf[3]);
-                }
+            for (int np = 0; np < C / 16; ++np) {
+                uint32_t bf[4];
+                ldmatrix_x4_trans(bf, &xt[(ks * 16 + (j & 1) * 8 + r) * kXP + (np * 2 + (j >> 1)) * 8]);
+                mma_bf16_16816(acc[2 * np], pa[ks], bf[0], bf[1]);
+                mma_bf16_16816(acc[2 * np + 1], pa[ks], bf[2], bf[3]);
             }
         }
-        __syncthreads();                                            // k tile and this x buffer are free again
+        if (++ib == kXkStages) ib = 0;
     }
+    cp_async_wait<0>();
+    __syncthreads();                                                // every warp has its Wk fragments: reuse wks for Wv
     // ---- this chunk's partial in the compact format of attn_merge: per head (m[32], l[32], ctx[32][32]) with
     //      ctx[d][e] = sum_c S[d][c] Wv[h*32+e][c]   (linear in S, so it can be applied per chunk).
     // S stays in registers: the fp32 accumulator fragments are repacked as bf16 A fragments (two adjacent n8 tiles
@@ -480,10 +467,9 @@ attn_xk_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
         *reinterpret_cast<float2*>(&part[64 + dl * 32 + e]) = make_float2(out[nt][0], out[nt][1]);
         *reinterpret_cast<float2*>(&part[64 + (dl + 8) * 32 + e]) = make_float2(out[nt][2], out[nt][3]);
     }
-    if (tid < 128) {
-        float* ph = partials + (((size_t)b * 4 + (tid >> 5)) * chunks + chunk) * 1088;
-        ph[tid & 31] = s_m[tid];
-        ph[32 + (tid & 31)] = s_l[tid];
+    if (t == 0) {
+        part[dl] = m0;       part[dl + 8] = m1;
+        part[32 + dl] = l0;  part[32 + dl + 8] = l1;
     }
 }
 
@@ -622,12 +608,12 @@ int attn_xk(const void* x, const void* wkv_bf16, float* partials, int B, int n, 
     const __nv_bfloat16* wk = reinterpret_cast<const __nv_bfloat16*>(wkv_bf16);
     dim3 grid(chunks, B);
     if (C == 64) {
-        size_t smem = (size_t)(128 * 72 + 2 * kXkSub * 72 + kXkSub * 136) * 2 + (3 * 128 + 512) * 4;
+        size_t smem = (size_t)(128 * 72 + kXkStages * kXkSub * 72) * 2;
         static bool set64 = false;
         if (!set64) { GTTS_CHECK_CUDA(cudaFuncSetAttribute(attn_xk_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set64 = true; }
         GTTS_CHECK_CUDA(launch_pdl(attn_xk_kernel<64>, grid, dim3(256), smem, s, 1, xb, wk, partials, n, chunks, chunk_len));
     } else {
-        size_t smem = (size_t)(128 * 136 + 2 * kXkSub * 136 + kXkSub * 136) * 2 + (3 * 128 + 512) * 4;
+        size_t smem = (size_t)(128 * 136 + kXkStages * kXkSub * 136) * 2;
         static bool set128 = false;
         if (!set128) { GTTS_CHECK_CUDA(cudaFuncSetAttribute(attn_xk_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set128 = true; }
         GTTS_CHECK_CUDA(launch_pdl(attn_xk_kernel<128>, grid, dim3(256), smem, s, 1, xb, wk, partials, n, chunks, chunk_len));

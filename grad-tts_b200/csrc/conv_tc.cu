@@ -168,7 +168,12 @@ void pick_tile(int Hg, int Wg, int* bh_out, int* bw_out) {
 size_t conv_tc_partials_slots(const ConvGeom&) { return 256; }         // one partial per (sample, CTA); grid <= #SMs
 
 bool conv_tc_halo_eligible(const ConvGeom& g) {
-    return g.ntaps == 9 && g.stride == 1 && g.nphase == 1 && g.w_batch_rows == 0 && (g.Cout == 64 || g.Cout == 128) &&
+    // Cout = 256 also runs (tests cover it; GTTS_HALO256=1) but loses to the per-tap kernel: two 256-column accumulators
+    // fill TMEM, so the epilogue no longer overlaps the next tile's MMAs, and the fixed 128-pixel halo tile wastes rows
+    // at H = 20.
+    const bool halo256 = getenv("GTTS_HALO256") != nullptr;
+    return g.ntaps == 9 && g.stride == 1 && g.nphase == 1 && g.w_batch_rows == 0 &&
+           (g.Cout == 64 || g.Cout == 128 || (g.Cout == 256 && halo256)) &&
            g.Hg >= 16 && g.Wg >= 8;
 }
 
@@ -185,7 +190,16 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
     TcParams& p = pl->p;
     if (halo_mode && !conv_tc_halo_eligible(g)) halo_mode = 0;
     p.halo_mode = halo_mode;
-    if (halo_mode) { p.bh = 16; p.bw = 8; }
+    if (halo_mode) {
+        // 128-pixel halo tile: 16 rows x 8 pixels (8-row UMMA groups run along W), or transposed 8 rows x 16 pixels with
+        // H as the fast box dimension (groups run along H) when that covers the image with fewer tiles (H = 40: 270 vs
+        // 324 tiles per sample, H = 20: 81 vs 108).
+        p.bh = 16; p.bw = 8; p.halo_t = 0;
+        if (halo_mode == 2 && g.Hg >= 10 && g.Wg >= 18 && !getenv("GTTS_HALO_NO_T")) {
+            const long t0 = (long)((g.Hg + 15) / 16) * ((g.Wg + 7) / 8), t1 = (long)((g.Hg + 7) / 8) * ((g.Wg + 15) / 16);
+            if (t1 < t0) { p.halo_t = 1; p.bh = 8; p.bw = 16; }
+        }
+    }
     else pick_tile(g.Hg, g.Wg, &p.bh, &p.bw);
     p.tiles_h = (g.Hg + p.bh - 1) / p.bh;
     p.tiles_w = (g.Wg + p.bw - 1) / p.bw;
@@ -207,6 +221,7 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
         const int pw = halo_mode == 2 ? 10 : 16;
         const int abytes = (18 * pw * 128 + 1023) / 1024 * 1024;     // stage stride keeps every stage 1024-aligned
         p.a_bytes = abytes;
+        p.pass_tiles = 1;
         { const char* pf = getenv("GTTS_HALO_PREFETCH"); p.halo_prefetch = pf ? atoi(pf) : 0; }
         int max_st = 6;
         if (const char* ms = getenv("GTTS_HALO_STAGES")) max_st = atoi(ms);
@@ -215,8 +230,11 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
         else if (ntiles_b <= 16 && ntiles_b * btile + 3 * abytes <= budget) { p.stages = 3; p.b_resident = 1; p.b_slots = ntiles_b; }
         else if (ntiles_b <= 16 && ntiles_b * btile + 2 * abytes <= budget) { p.stages = 2; p.b_resident = 1; p.b_slots = ntiles_b; }
         else {
-            p.stages = 3; p.b_resident = 0;
-            p.b_slots = (budget - 3 * abytes) / btile;
+            // streamed weights: two A tiles per pass of the weight ring, A ring double-buffered across chunks
+            p.pass_tiles = 2;
+            if (const char* pt = getenv("GTTS_PASS_TILES")) p.pass_tiles = atoi(pt) == 1 ? 1 : 2;
+            p.stages = p.pass_tiles == 2 ? 4 : 3; p.b_resident = 0;
+            p.b_slots = (budget - p.stages * abytes) / btile;
             if (p.b_slots > 16) p.b_slots = 16;
         }
         pl->smem = (size_t)p.stages * abytes + (size_t)p.b_slots * btile + kMiscBytes + 1024;
@@ -251,6 +269,11 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
             uint64_t str[3] = {(uint64_t)C * 2, W * C * 2, H * W * C * 2};
             uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, 1};
             if (halo_mode) { box[1] = halo_mode == 2 ? 10 : 16; box[2] = 18; }
+            if (p.halo_t) {                                          // dims (C, H, W, B): H is the fast box dimension
+                uint64_t dims_t[4] = {(uint64_t)C, H, W, (uint64_t)g.B};
+                uint64_t str_t[3] = {W * C * 2, (uint64_t)C * 2, H * W * C * 2};
+                return encode_map(m, src, 4, dims_t, str_t, box);
+            }
             return encode_map(m, src, 4, dims, str, box);
         } else {
             uint64_t dims[5] = {(uint64_t)2 * C, W / 2, 2, H / 2, (uint64_t)g.B};

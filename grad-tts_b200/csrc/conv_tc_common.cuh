@@ -22,6 +22,8 @@ struct TcParams {
     int ntaps, nchunk0, nchunk1, Cin0;
     int stride2, w_batch_rows, num_tiles, a_bytes, stages;
     int halo_mode, b_slots, b_resident, halo_prefetch;   // conv_tc_halo.cu only
+    int halo_t;                                    // 1: halo tile is 8 rows x 16 pixels with H as the fast box dimension
+    int pass_tiles;                                // streamed weights: A tiles that share one pass of the weight ring (1 or 2)
     int mc;                                        // 1: 2-CTA cluster, weight tiles multicast (conv_tc.cu)
     unsigned long long* dbg_out;                   // optional per-CTA cycle counters (GTTS_CONV_TIMING), 16 per CTA
     int dbg;                                       // experiment switches (GTTS_CONV_DBG): 1 no MMA issue, 2 no epilogue work, 4 no A loads (halo), 8 no stats ring
@@ -217,7 +219,8 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.out);
     const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(e.residual);
     const int cbase = half * kColsPerWarp;
-    const int hl = row / p.bw, wl = row - hl * p.bw;                 // fixed for the whole kernel
+    int hl = row / p.bw, wl = row - hl * p.bw;                       // fixed for the whole kernel
+    if (p.halo_t) { wl = row >> 3; hl = row & 7; }                   // transposed halo tile: 8-row groups run along H
     const bool row_in_tile = hl < p.bh;
     const float* s_bias = sh.s_bias;
     TileWalk tw;

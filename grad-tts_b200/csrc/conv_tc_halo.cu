@@ -59,7 +59,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             uint32_t pha = 0, phb = 0;
             bool first = true;
             const int G = (int)gridDim.x, nstage = p.stages, nslot = p.b_slots, resident = p.b_resident, dbg = p.dbg;
-            const int nck0 = p.nchunk0;
+            const int nck0 = p.nchunk0, ht = p.halo_t;
             const uint32_t a_tx = (uint32_t)(18 * pw * 128);
             TileWalk tw, pf;
             long long c_pwait = 0;
@@ -71,14 +71,46 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                     pf.advance(G);
                     if (pf.tile < p.num_tiles)
                         for (int ck = 0; ck < nck; ++ck)
-                            tma_prefetch_4d(ck < nck0 ? &mapA0 : &mapA1, (ck < nck0 ? ck : ck - nck0) * 64, pf.tw * 8 - 1,
-                                            pf.th * 16 - 1, pf.b);
+                            tma_prefetch_4d(ck < nck0 ? &mapA0 : &mapA1, (ck < nck0 ? ck : ck - nck0) * 64,
+                                            ht ? pf.th * p.bh - 1 : pf.tw * p.bw - 1, ht ? pf.tw * p.bw - 1 : pf.th * p.bh - 1, pf.b);
                 }
             }
             const int n_it = tc_num_iters(p);
             int it = 0;
+            if (!resident) {
+                // ---- streamed weights: `pass_tiles` A tiles share every weight slot (fill per tile: A + B / pass_tiles)
+                const int TP = p.pass_tiles;
+                for (; tw.tile < p.num_tiles; it += TP) {
+                    if (kStats && (it >= n_it - 8)) prefetch_l2(p.e.gn_counters);
+                    int tb[2], th0[2], tw0[2];
+                    int nt = 0;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        if (k < TP && tw.tile < p.num_tiles) { tb[k] = tw.b; th0[k] = tw.th * p.bh; tw0[k] = tw.tw * p.bw; tw.advance(G); nt = k + 1; }
+                    for (int ck = 0; ck < nck; ++ck) {
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            if (k >= nt) continue;
+                            const long long tp0 = clock64();
+                            mbar_wait(&sh.empty[sa], pha ^ 1u);
+                            c_pwait += clock64() - tp0;
+                            mbar_expect_tx(&sh.full[sa], a_tx);
+                            tma_load_4d(ck < nck0 ? &mapA0 : &mapA1, &sh.full[sa], smem + (size_t)sa * a_stage,
+                                        (ck < nck0 ? ck : ck - nck0) * 64, ht ? th0[k] - 1 : tw0[k] - 1,
+                                        ht ? tw0[k] - 1 : th0[k] - 1, tb[k]);
+                            if (++sa == nstage) { sa = 0; pha ^= 1u; }
+                        }
+                        for (int tap = 0; tap < 9; ++tap) {
+                            mbar_wait(&sh.emptyb[sb], phb ^ 1u);
+                            mbar_expect_tx(&sh.fullb[sb], (uint32_t)kBBytes);
+                            tma_load_2d(&mapW, &sh.fullb[sb], smem_b + (size_t)sb * kBBytes, ck * 64, p.wrow[0][tap]);
+                            if (++sb == nslot) { sb = 0; phb ^= 1u; }
+                        }
+                    }
+                }
+            } else
             for (; tw.tile < p.num_tiles; tw.advance(G), ++it) {
-                const int b = tw.b, h0 = tw.th * 16, w0 = tw.tw * 8;
+                const int b = tw.b, h0 = tw.th * p.bh, w0 = tw.tw * p.bw;
                 // the tail's ticket counters were last touched a launch ago and have been evicted by this kernel's own
                 // traffic; an L2 miss under full load costs ~8 us on the critical tail, so fetch the line ahead of time
                 if (kStats && (it == n_it - 8 || it == n_it - 1)) prefetch_l2(p.e.gn_counters);
@@ -86,8 +118,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                     pf.advance(G);
                     if (pf.tile < p.num_tiles)
                         for (int ck = 0; ck < nck; ++ck)
-                            tma_prefetch_4d(ck < nck0 ? &mapA0 : &mapA1, (ck < nck0 ? ck : ck - nck0) * 64, pf.tw * 8 - 1,
-                                            pf.th * 16 - 1, pf.b);
+                            tma_prefetch_4d(ck < nck0 ? &mapA0 : &mapA1, (ck < nck0 ? ck : ck - nck0) * 64,
+                                            ht ? pf.th * p.bh - 1 : pf.tw * p.bw - 1, ht ? pf.tw * p.bw - 1 : pf.th * p.bh - 1, pf.b);
                 }
                 for (int ck = 0; ck < nck; ++ck) {
                     const long long tp0 = clock64();
@@ -98,23 +130,14 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                     } else {
                         mbar_expect_tx(&sh.full[sa], a_tx);
                         tma_load_4d(ck < nck0 ? &mapA0 : &mapA1, &sh.full[sa], smem + (size_t)sa * a_stage,
-                                    (ck < nck0 ? ck : ck - nck0) * 64, w0 - 1, h0 - 1, b);
+                                    (ck < nck0 ? ck : ck - nck0) * 64, ht ? h0 - 1 : w0 - 1, ht ? w0 - 1 : h0 - 1, b);
                     }
                     if (++sa == nstage) { sa = 0; pha ^= 1u; }
-                    if (resident) {
-                        if (first) {
-                            for (int tap = 0; tap < 9; ++tap) {
-                                const int slot = ck * 9 + tap;
-                                mbar_expect_tx(&sh.fullb[slot], (uint32_t)kBBytes);
-                                tma_load_2d(&mapW, &sh.fullb[slot], smem_b + (size_t)slot * kBBytes, ck * 64, p.wrow[0][tap]);
-                            }
-                        }
-                    } else {
+                    if (first) {
                         for (int tap = 0; tap < 9; ++tap) {
-                            mbar_wait(&sh.emptyb[sb], phb ^ 1u);
-                            mbar_expect_tx(&sh.fullb[sb], (uint32_t)kBBytes);
-                            tma_load_2d(&mapW, &sh.fullb[sb], smem_b + (size_t)sb * kBBytes, ck * 64, p.wrow[0][tap]);
-                            if (++sb == nslot) { sb = 0; phb ^= 1u; }
+                            const int slot = ck * 9 + tap;
+                            mbar_expect_tx(&sh.fullb[slot], (uint32_t)kBBytes);
+                            tma_load_2d(&mapW, &sh.fullb[slot], smem_b + (size_t)slot * kBBytes, ck * 64, p.wrow[0][tap]);
                         }
                     }
                 }
@@ -136,12 +159,72 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         const uint64_t a_stage_step = (uint64_t)(a_stage >> 4), b_slot_step = (uint64_t)(kBBytes >> 4);
         uint64_t tap_off[9];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) tap_off[t] = (uint64_t)((((t / 3) * pw + (t % 3)) * 128) >> 4);
+        for (int t = 0; t < 9; ++t)                                  // box row of tap (dy, dx): dy*pw + dx, transposed: dx*pw + dy
+            tap_off[t] = (uint64_t)(((p.halo_t ? (t % 3) * pw + (t / 3) : (t / 3) * pw + (t % 3)) * 128) >> 4);
         int sa = 0, sb = 0, it = 0;
         uint32_t pha = 0, phb = 0;
         const int n_it = tc_num_iters(p);
         long long c_tempty = 0, c_full = 0, c_issue = 0, c_commit = 0, c_n = 0;
         const long long tl0 = clock64();
+        if (!resident) {
+            // ---- streamed weights: every weight slot (one tap of one 64-channel chunk) feeds `pass_tiles` accumulators
+            // before it is released, so a tile costs A + B / pass_tiles bytes of L2 -> SMEM fill.  (With one tile per
+            // pass the 128->128, 256->256, 512->128 layers stream 0.3 - 1.2 MB of weights per 128-pixel tile and are
+            // fill-bound at ~45 B/clk/SM; with two they are tensor/SMEM-bound.)
+            const int TP = p.pass_tiles;
+            constexpr int kBufs = acc_bufs<N>();
+            for (it = 0; it < n_it; it += TP) {
+                const int nt = n_it - it < TP ? n_it - it : TP;
+                uint32_t d_tmem[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (k >= nt) continue;
+                    const int buf = (it + k) % kBufs;
+                    mbar_wait(&sh.tempty[buf], ((uint32_t)((it + k) / kBufs) & 1u) ^ 1u);
+                    d_tmem[k] = tmem_base + (uint32_t)(buf * N);
+                }
+                tc_fence_after();
+                for (int ck = 0; ck < nck; ++ck) {
+                    uint64_t adesc[2];
+                    int sa_k[2];
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        if (k >= nt) continue;
+                        mbar_wait(&sh.full[sa], pha);
+                        sa_k[k] = sa;
+                        adesc[k] = a_desc0 + (uint64_t)sa * a_stage_step;
+                        if (++sa == nstage) { sa = 0; pha ^= 1u; }
+                    }
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&sh.fullb[sb], phb);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t bdesc = b_desc0 + (uint64_t)sb * b_slot_step;
+                            if (!(dbg & 1)) {
+#pragma unroll
+                                for (int k = 0; k < 2; ++k)
+#pragma unroll
+                                    for (int kk = 0; kk < 4; ++kk)
+                                        if (k < nt) tc_mma_f16(d_tmem[k], adesc[k] + tap_off[tap] + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk),
+                                                   kIdesc, (uint32_t)((ck | tap | kk) != 0));
+                            }
+                            tc_commit(&sh.emptyb[sb]);
+                            if (tap == 8) {
+#pragma unroll
+                                for (int k = 0; k < 2; ++k) if (k < nt) tc_commit(&sh.empty[sa_k[k]]);
+                                if (ck == nck - 1) {
+#pragma unroll
+                                    for (int k = 0; k < 2; ++k) if (k < nt) tc_commit(&sh.tfull[(it + k) % kBufs]);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        if (++sb == nslot) { sb = 0; phb ^= 1u; }
+                    }
+                }
+            }
+        } else
         for (it = 0; it < n_it; ++it) {
             const int buf = it % acc_bufs<N>();
             const long long t0 = clock64();
@@ -156,54 +239,30 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                 const long long t2b = clock64();
                 c_full += t2b - t2;
                 const uint64_t adesc = a_desc0 + (uint64_t)sa * a_stage_step;
-                if (resident) {
-                    if (it == 0) {
+                if (it == 0) {
 #pragma unroll 1
-                        for (int tap = 0; tap < 9; ++tap) mbar_wait(&sh.fullb[ck * 9 + tap], 0u);
-                    }
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint64_t bdesc = b_desc0 + (uint64_t)(ck * 9) * b_slot_step;
-                        if (!(dbg & 1)) {
-#pragma unroll
-                            for (int tap = 0; tap < 9; ++tap)
-#pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    tc_mma_f16(d_tmem, adesc + tap_off[tap] + (uint64_t)(2 * k),
-                                               bdesc + (uint64_t)tap * b_slot_step + (uint64_t)(2 * k), kIdesc,
-                                               (uint32_t)((ck | tap | k) != 0));
-                        }
-                        const long long t3 = clock64();
-                        tc_commit(&sh.empty[sa]);
-                        if (ck == nck - 1) tc_commit(&sh.tfull[buf]);
-                        c_issue += t3 - t2b;
-                        c_commit += clock64() - t3;
-                        c_n += 1;
-                    }
-                    __syncwarp();
-                } else {
-#pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        mbar_wait(&sh.fullb[sb], phb);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const uint64_t bdesc = b_desc0 + (uint64_t)sb * b_slot_step;
-                            if (!(dbg & 1)) {
-#pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    tc_mma_f16(d_tmem, adesc + tap_off[tap] + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
-                                               kIdesc, (uint32_t)((ck | tap | k) != 0));
-                            }
-                            tc_commit(&sh.emptyb[sb]);
-                            if (tap == 8) {
-                                tc_commit(&sh.empty[sa]);
-                                if (ck == nck - 1) tc_commit(&sh.tfull[buf]);
-                            }
-                        }
-                        __syncwarp();
-                        if (++sb == nslot) { sb = 0; phb ^= 1u; }
-                    }
+                    for (int tap = 0; tap < 9; ++tap) mbar_wait(&sh.fullb[ck * 9 + tap], 0u);
                 }
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t bdesc = b_desc0 + (uint64_t)(ck * 9) * b_slot_step;
+                    if (!(dbg & 1)) {
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                tc_mma_f16(d_tmem, adesc + tap_off[tap] + (uint64_t)(2 * k),
+                                           bdesc + (uint64_t)tap * b_slot_step + (uint64_t)(2 * k), kIdesc,
+                                           (uint32_t)((ck | tap | k) != 0));
+                    }
+                    const long long t3 = clock64();
+                    tc_commit(&sh.empty[sa]);
+                    if (ck == nck - 1) tc_commit(&sh.tfull[buf]);
+                    c_issue += t3 - t2b;
+                    c_commit += clock64() - t3;
+                    c_n += 1;
+                }
+                __syncwarp();
                 if (++sa == nstage) { sa = 0; pha ^= 1u; }
             }
         }
@@ -250,6 +309,7 @@ int conv_tc_halo_launch(const TcConvPlan* pl, cudaStream_t stream) {
     const bool st = e.gn_partials != nullptr;
     if (pl->N == 64) return st ? launch_halo<64, true>(pl, stream) : launch_halo<64, false>(pl, stream);
     if (pl->N == 128) return st ? launch_halo<128, true>(pl, stream) : launch_halo<128, false>(pl, stream);
+    if (pl->N == 256) return st ? launch_halo<256, true>(pl, stream) : launch_halo<256, false>(pl, stream);
     set_error("conv_tc_halo: unsupported Cout");
     return 2;
 }

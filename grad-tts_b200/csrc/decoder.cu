@@ -95,7 +95,7 @@ struct Decoder {
     int n_feats = 80, dim = 64;
     double beta_min = 0.05, beta_max = 20.0, pe_scale = 1000.0;
     int device = 0, num_sms = 148;
-    int max_chunk = 8;
+    int max_chunk = 32;
     bool use_graph = true;
     int conv_impl_bf16 = 1;   // 1: tcgen05, 0: FFMA (debug cross-check)
     int fused_attn = 1;       // bf16, C <= 128: fused k-projection + context kernel (no kv tensor)

@@ -166,8 +166,6 @@ def stage_convdbg():
         gu.run_conv(c, 3, 1, want_stats=True)
         return
     for impl in (1, 3):
-        if impl == 3 and cout > 128:
-            continue
         for dbg in (0, 1, 2, 3):
             os.environ["GTTS_CONV_DBG"] = str(dbg)
             for mc in ((0, 1) if impl == 1 else (0,)):
