@@ -167,11 +167,17 @@ void pick_tile(int Hg, int Wg, int* bh_out, int* bw_out) {
 
 size_t conv_tc_partials_slots(const ConvGeom&) { return 256; }         // one partial per (sample, CTA); grid <= #SMs
 
+// CTA-pair (cta_group::2) halo kernel, conv_tc_halo2.cu.  GTTS_CTA2=0 falls back to the single-CTA kernels.
+bool conv_tc_cta2_enabled() {
+    const char* e = getenv("GTTS_CTA2");
+    return e ? atoi(e) != 0 : true;
+}
+
 bool conv_tc_halo_eligible(const ConvGeom& g) {
     // Cout = 256 also runs (tests cover it; GTTS_HALO256=1) but loses to the per-tap kernel: two 256-column accumulators
     // fill TMEM, so the epilogue no longer overlaps the next tile's MMAs, and the fixed 128-pixel halo tile wastes rows
     // at H = 20.
-    const bool halo256 = getenv("GTTS_HALO256") != nullptr;
+    const bool halo256 = getenv("GTTS_HALO256") != nullptr || conv_tc_cta2_enabled();
     return g.ntaps == 9 && g.stride == 1 && g.nphase == 1 && g.w_batch_rows == 0 &&
            (g.Cout == 64 || g.Cout == 128 || (g.Cout == 256 && halo256)) &&
            g.Hg >= 16 && g.Wg >= 8;
@@ -225,6 +231,22 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
         { const char* pf = getenv("GTTS_HALO_PREFETCH"); p.halo_prefetch = pf ? atoi(pf) : 0; }
         int max_st = 6;
         if (const char* ms = getenv("GTTS_HALO_STAGES")) max_st = atoi(ms);
+        const bool cta2 = halo_mode == 2 && conv_tc_cta2_enabled() && p.num_tiles >= 2 && num_sms >= 2;
+        if (cta2) {
+            // CTA pair: every CTA holds half of each weight tile (Cout/2 rows)
+            const int bhalf = g.Cout * 64;
+            p.mc = 2;
+            if (ntiles_b * bhalf + 3 * abytes <= budget) {
+                p.b_resident = 1; p.b_slots = ntiles_b;
+                p.stages = (budget - ntiles_b * bhalf) / abytes;
+                if (p.stages > max_st) p.stages = max_st;
+            } else {
+                p.b_resident = 0; p.stages = 3;
+                p.b_slots = (budget - 3 * abytes) / bhalf;
+                if (p.b_slots > 16) p.b_slots = 16;
+            }
+            pl->smem = (size_t)p.stages * abytes + (size_t)p.b_slots * bhalf + kMiscBytes + 1024;
+        } else {
         if (ntiles_b <= 16 && max_st >= 6 && ntiles_b * btile + 6 * abytes <= budget) { p.stages = 6; p.b_resident = 1; p.b_slots = ntiles_b; }
         else if (ntiles_b <= 16 && ntiles_b * btile + 4 * abytes <= budget) { p.stages = 4; p.b_resident = 1; p.b_slots = ntiles_b; }
         else if (ntiles_b <= 16 && ntiles_b * btile + 3 * abytes <= budget) { p.stages = 3; p.b_resident = 1; p.b_slots = ntiles_b; }
@@ -238,6 +260,7 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
             if (p.b_slots > 16) p.b_slots = 16;
         }
         pl->smem = (size_t)p.stages * abytes + (size_t)p.b_slots * btile + kMiscBytes + 1024;
+        }
     } else {
         const int stage_bytes = kABytes + g.Cout * 128;
         int stages = budget / stage_bytes;
@@ -251,8 +274,9 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
         // 2-CTA clusters with weight-tile multicast: the N=256 layers are bound by L2->SMEM fill, 2/3 of it weights
         const char* mce = getenv("GTTS_MC");
         const int want = mce ? atoi(mce) : 0;      // measured: no gain on B200 (these layers are MMA-, not fill-bound)
-        p.mc = (want && !halo_mode && g.Cout == 256 && g.nphase == 1 && g.w_batch_rows == 0 && p.num_tiles >= 2 &&
-                num_sms >= 2) ? 1 : 0;
+        if (p.mc != 2)
+            p.mc = (want && !halo_mode && g.Cout == 256 && g.nphase == 1 && g.w_batch_rows == 0 && p.num_tiles >= 2 &&
+                    num_sms >= 2) ? 1 : 0;
         if (p.mc) {
             int gmax = num_sms & ~1;
             if (gmax > 256) gmax = 256;
@@ -330,7 +354,7 @@ int launch_n(const TcConvPlan* pl, cudaStream_t stream) {
 
 int conv_tc_launch(const TcConvPlan* pl, cudaStream_t stream) {
     if (pl->p.num_tiles == 0) return 0;
-    if (pl->p.halo_mode) return conv_tc_halo_launch(pl, stream);
+    if (pl->p.halo_mode) return pl->p.mc == 2 ? conv_tc_halo2_launch(pl, stream) : conv_tc_halo_launch(pl, stream);
     if (pl->N == 64) return launch_n<64>(pl, stream);
     if (pl->N == 128) return launch_n<128>(pl, stream);
     return launch_n<256>(pl, stream);

@@ -24,7 +24,7 @@ struct TcParams {
     int halo_mode, b_slots, b_resident, halo_prefetch;   // conv_tc_halo.cu only
     int halo_t;                                    // 1: halo tile is 8 rows x 16 pixels with H as the fast box dimension
     int pass_tiles;                                // streamed weights: A tiles that share one pass of the weight ring (1 or 2)
-    int mc;                                        // 1: 2-CTA cluster, weight tiles multicast (conv_tc.cu)
+    int mc;                                        // 1: 2-CTA cluster, weight tiles multicast (conv_tc.cu); 2: CTA pair, cta_group::2 MMAs (conv_tc_halo2.cu)
     unsigned long long* dbg_out;                   // optional per-CTA cycle counters (GTTS_CONV_TIMING), 16 per CTA
     int dbg;                                       // experiment switches (GTTS_CONV_DBG): 1 no MMA issue, 2 no epilogue work, 4 no A loads (halo), 8 no stats ring
     int8_t dy[4][9], dx[4][9];
@@ -245,7 +245,7 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
         mbar_wait(&sh.tfull[buf], (uint32_t)(it / kBufs) & 1u);
         tc_fence_after();
         c_wait += clock64() - tq0;
-        if (p.dbg & 2) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&sh.tempty[buf]); if (kStats && !(p.dbg & 8)) { const int slot = it % kStatSlots; mbar_wait(&sh.sempty[slot], ((uint32_t)(it / kStatSlots) & 1u) ^ 1u); __syncwarp(); if (lane == 0) mbar_arrive(&sh.sfull[slot]); } continue; }
+        if (p.dbg & 2) { tc_fence_before(); __syncwarp(); if (lane == 0) { if (p.mc == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&sh.tempty[buf]), 0u)); else mbar_arrive(&sh.tempty[buf]); } if (kStats && !(p.dbg & 8)) { const int slot = it % kStatSlots; mbar_wait(&sh.sempty[slot], ((uint32_t)(it / kStatSlots) & 1u) ^ 1u); __syncwarp(); if (lane == 0) mbar_arrive(&sh.sfull[slot]); } continue; }
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * N + cbase);
 
         float2 ssum[4], ssq[4];                                      // per local group: packed (even, odd) columns
@@ -264,7 +264,10 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
                 // (one arrive per warp: 256 threads hammering one mbarrier word cost ~0.5 us per tile)
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sh.tempty[buf]);
+                if (lane == 0) {
+                    if (p.mc == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&sh.tempty[buf]), 0u));   // CTA pair: the leader issues the MMAs
+                    else mbar_arrive(&sh.tempty[buf]);
+                }
             }
             float2 f[16];
 #pragma unroll
@@ -347,7 +350,8 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
 }
 
 // Kernel tail: one fence + ticket per CTA; whoever completes a sample's tile count reduces its partials (fixed order).
-template <int N, bool kStats>
+// kCta2 is a compile-time switch: a kernel that merely CONTAINS a cta_group::2 instruction must be launched as a cluster.
+template <int N, bool kStats, bool kCta2 = false>
 __device__ __forceinline__ void tc_teardown(const TcParams& p, const TcShared& sh, uint8_t* smem, uint32_t tmem_base,
                                             int tid, int warp, int lane) {
     constexpr int kGsz = N / 8;
@@ -363,7 +367,8 @@ __device__ __forceinline__ void tc_teardown(const TcParams& p, const TcShared& s
     if (warp == 2) {
         const long long tq = clock64();
         tc_fence_after();
-        tmem_dealloc(tmem_base, acc_bufs<N>() * N);
+        if (kCta2) tmem_dealloc2(tmem_base, acc_bufs<N>() * N);
+        else tmem_dealloc(tmem_base, acc_bufs<N>() * N);
         if (p.dbg_out && lane == 0) p.dbg_out[blockIdx.x * 32 + 22] = (unsigned long long)(clock64() - tq);
     }
     if (kStats) {
@@ -461,6 +466,7 @@ struct TcConvPlan {
     size_t smem;
 };
 int conv_tc_halo_launch(const TcConvPlan* pl, cudaStream_t stream);      // conv_tc_halo.cu
+int conv_tc_halo2_launch(const TcConvPlan* pl, cudaStream_t stream);     // conv_tc_halo2.cu
 
 namespace tc {
 // ------------------------------------------------------------------------------------------------ host helpers

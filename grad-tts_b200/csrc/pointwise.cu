@@ -134,11 +134,11 @@ first_conv_kernel(FirstConvArgs a) {
         const int p0 = (blockIdx.x * kFcTiles + t) * 128 + quad * 4;      // first pixel of my quad (W % 4 == 0)
         if (p0 >= HW) break;                               // uniform per quad; later tiles are out of range too
         const int h = p0 / W, w0 = p0 - h * W;
-        float acc[4][16];
+        float2 acc[4][8];                                  // packed channel pairs: FFMA2 halves the issue slots
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int c = 0; c < 16; ++c) acc[j][c] = sb[q * 16 + c];
+            for (int c = 0; c < 8; ++c) acc[j][c] = make_float2(sb[q * 16 + 2 * c], sb[q * 16 + 2 * c + 1]);
         float mk[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
@@ -168,13 +168,12 @@ first_conv_kernel(FirstConvArgs a) {
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
                         const float4 wv = wr[c4];
+                        const float2 w01 = make_float2(wv.x, wv.y), w23 = make_float2(wv.z, wv.w);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float xin = in[ci][j + kx];
-                            acc[j][4 * c4 + 0] = fmaf(xin, wv.x, acc[j][4 * c4 + 0]);
-                            acc[j][4 * c4 + 1] = fmaf(xin, wv.y, acc[j][4 * c4 + 1]);
-                            acc[j][4 * c4 + 2] = fmaf(xin, wv.z, acc[j][4 * c4 + 2]);
-                            acc[j][4 * c4 + 3] = fmaf(xin, wv.w, acc[j][4 * c4 + 3]);
+                            const float2 xin = make_float2(in[ci][j + kx], in[ci][j + kx]);
+                            acc[j][2 * c4 + 0] = ffma2(xin, w01, acc[j][2 * c4 + 0]);
+                            acc[j][2 * c4 + 1] = ffma2(xin, w23, acc[j][2 * c4 + 1]);
                         }
                     }
                 }
@@ -184,7 +183,10 @@ first_conv_kernel(FirstConvArgs a) {
         for (int j = 0; j < 4; ++j) {
             float v0[8], v1[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) { v0[c] = acc[j][c]; v1[c] = acc[j][8 + c]; }
+            for (int c = 0; c < 4; ++c) {
+                v0[2 * c] = acc[j][c].x;     v0[2 * c + 1] = acc[j][c].y;
+                v1[2 * c] = acc[j][4 + c].x; v1[2 * c + 1] = acc[j][4 + c].y;
+            }
             Act<T>::store8(o + (size_t)j * 64, v0);
             Act<T>::store8(o + (size_t)j * 64 + 8, v1);
 #pragma unroll
