@@ -3,7 +3,8 @@ import collections
 import re
 import sys
 
-path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/diag.log"
+args = [a for a in sys.argv[1:] if not a.startswith("-")]
+path = args[0] if args else "gpurun_out/diag.log"
 rows, seen, on = [], 0, False
 for line in open(path):
     if "profile B=" in line:
