@@ -261,8 +261,18 @@ def main():
         f_conv = sum(o["flops"] for o in conv)
         tf_peak, hbm_peak, which = peaks()
         ach = f_conv / t_conv / 1e12
-        roof = {"bound": "tensor", "kernel": "conv_tc_kernel (all 46 tcgen05 implicit-GEMM convs of one Euler step)",
-                "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None,
+        # DRAM bytes per launch from the committed ncu capture of this command (profiles/r01_conv_dram_v6.json: 40 conv
+        # launches of one Euler step at chunk 32 x 1720); only quoted when this run uses the same chunk shape
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_conv_dram_v6.json")))
+            if rep["B"] == 32 and T == 1720 and tj["launches"] == len(conv):
+                traffic, traffic_src = tj["traffic_bytes_per_launch"], "profiles/r01_conv_dram_v6.json (ncu dram__bytes_read+write)"
+        except (OSError, KeyError, ValueError):
+            pass
+        roof = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convolutions (conv_tc / conv_tc_halo / conv_tc_halo2, all launches of one Euler step)",
+                "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": traffic,
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": sum(o.get("bytes", 0) for o in conv) / len(conv),
                 "peak_source": f"{which} (bf16_tflops_sustained)", "launches_per_step": len(conv),
                 "avg_launch_ms": 1e3 * t_conv / len(conv), "conv_share_of_step": t_conv / t_all,
                 "chunk_batch": rep["B"],
