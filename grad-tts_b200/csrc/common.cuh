@@ -164,14 +164,14 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 __device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-// Branch-free fast Mish on a pair: y * n/(n+2), n = e(e+2), e = 2^min(ylog2, 43) where ylog2 = y*log2(e) is supplied
-// by the caller (folded into the preceding affine).  For y > 30 the factor rounds to 1 (torch's softplus threshold
-// path returns y there as well); for y << 0 it underflows to 0.
+// Branch-free fast Mish on a pair: y * tanh(softplus(y)) = y * n/(n+2) with n = e(e+2), e = exp(y).  Written as
+// y * (1 - 2/d), d = n + 2 = (e+1)^2 + 1: no clamp is needed (e = inf gives d = inf, 1/d = 0, factor 1 -- torch's softplus
+// threshold path returns y there as well; y << 0 gives d -> 2, factor -> 0 with absolute error ~1e-7), and d comes from one
+// add and one FMA.  ylog2 = y*log2(e) is supplied by the caller.  Two MUFU + four packed instructions per pair.
 __device__ __forceinline__ float2 mish2_fast(float2 y, float2 ylog2) {
-    float2 e = make_float2(ex2_approx(fminf(ylog2.x, 43.0f)), ex2_approx(fminf(ylog2.y, 43.0f)));
-    const float2 n = ffma2(e, e, fadd2(e, e));
-    const float2 d = fadd2(n, make_float2(2.0f, 2.0f));
-    const float2 t = fmul2(n, make_float2(rcp_approx(d.x), rcp_approx(d.y)));
+    const float2 e1 = fadd2(make_float2(ex2_approx(ylog2.x), ex2_approx(ylog2.y)), make_float2(1.0f, 1.0f));
+    const float2 d = ffma2(e1, e1, make_float2(1.0f, 1.0f));
+    const float2 t = ffma2(make_float2(rcp_approx(d.x), rcp_approx(d.y)), make_float2(-2.0f, -2.0f), make_float2(1.0f, 1.0f));
     return fmul2(y, t);
 }
 
