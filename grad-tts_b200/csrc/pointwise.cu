@@ -419,7 +419,7 @@ gn_apply_fast_kernel(GnApplyArgs a) {
 // ------------------------------------------------------------------------------------------------ Euler step
 // final_block GN+Mish+mask -> final_conv(64->1)+bias -> *mask = score; then the sampler update.
 // 8 lanes per pixel (one 8-channel vector each), kEuPix pixels per lane group with the loads issued up front.
-constexpr int kEuPix = 4;
+constexpr int kEuPix = 8;
 
 template <typename T, bool kStrict>
 __global__ void __launch_bounds__(256, 3)
@@ -437,22 +437,23 @@ euler_kernel(EulerArgs a) {
         const size_t pix = pbase + k;
         if (pix < npix) pv[k] = Act<T>::load_packed(reinterpret_cast<const T*>(a.raw) + pix * 64 + sub * 8);
     }
-    // lane 2k holds xt of pixel k, lane 2k+1 holds mu of pixel k (kEuPix = 4 pixels, 8 lanes)
-    const size_t mypix = pbase + (sub >> 1);
-    float pre = 0.f;
-    if (a.update && mypix < npix) pre = (sub & 1) ? a.mu[mypix] : a.xt[mypix];
+    // lane k of the 8-lane group holds xt and mu of pixel k and finishes that pixel
+    const size_t mypix = pbase + sub;
+    float pre_xt = 0.f, pre_mu = 0.f;
+    if (a.update && mypix < npix) { pre_xt = a.xt[mypix]; pre_mu = a.mu[mypix]; }
     float mk[kEuPix], mean[kEuPix], rstd[kEuPix];
-    {
-        // pbase is a multiple of kEuPix = 4 and so are W and H*W (T % 4 == 0): the 4 pixels share sample and row.
-        // 32-bit arithmetic, one division pair per thread (the first version did eight 64-bit divisions).
-        const uint32_t pp = pbase < npix ? (uint32_t)pbase : 0u;
+#pragma unroll
+    for (int q4 = 0; q4 < kEuPix / 4; ++q4) {
+        // pbase + 4*q4 is a multiple of 4 and so are W and H*W (T % 4 == 0): each quad of pixels shares sample and row.
+        // 32-bit arithmetic, one division pair per quad (the first version did eight 64-bit divisions per thread).
+        const uint32_t pp = pbase + 4 * q4 < npix ? (uint32_t)pbase + 4u * q4 : 0u;
         const uint32_t b = pp / (uint32_t)HW, rem = pp - b * (uint32_t)HW, w0 = rem % (uint32_t)a.W;
         const float mean_b = a.stats[(b * 8 + sub) * 2], rstd_b = a.stats[(b * 8 + sub) * 2 + 1];
 #pragma unroll
-        for (int k = 0; k < kEuPix; ++k) {
-            mk[k] = a.mask[(size_t)b * a.W + w0 + k];
-            mean[k] = mean_b;
-            rstd[k] = rstd_b;
+        for (int k = 0; k < 4; ++k) {
+            mk[4 * q4 + k] = a.mask[(size_t)b * a.W + w0 + k];
+            mean[4 * q4 + k] = mean_b;
+            rstd[4 * q4 + k] = rstd_b;
         }
     }
     float sc[8], sh_[8], wf[8];
@@ -465,9 +466,8 @@ euler_kernel(EulerArgs a) {
     const float beta_t = a.update ? a.beta_tab[*a.step] : 0.f;
     const float hh = a.update ? *a.h_ptr : 0.f;
     float noise_v = 0.f;
-    if (a.update && a.sde && !(sub & 1) && mypix < npix)
+    if (a.update && a.sde && mypix < npix)
         noise_v = (*a.noise_slot)[(size_t)(*a.step) * a.noise_step_stride + mypix];
-    const unsigned gbase = (threadIdx.x & 31) & ~7u;                  // first lane of my 8-lane group
 #pragma unroll
     for (int k = 0; k < kEuPix; ++k) {
         const bool valid = pbase + k < npix;
@@ -500,13 +500,13 @@ euler_kernel(EulerArgs a) {
         part += __shfl_xor_sync(0xffffffffu, part, 1);
         part += __shfl_xor_sync(0xffffffffu, part, 2);
         part += __shfl_xor_sync(0xffffffffu, part, 4);
-        const float mu = __shfl_sync(0xffffffffu, pre, gbase + 2 * k + 1);
-        if (!valid || sub != 2 * k) continue;                  // lane 2k finishes pixel k
+        if (!valid || sub != k) continue;                      // lane k finishes pixel k
+        const float mu = pre_mu;
         const size_t pix = pbase + k;
         const float score = __fmul_rn(part + a.bf, m);         // (output * mask)                   (:216)
         if (a.score_out) a.score_out[pix] = score;
         if (!a.update) continue;
-        const float xt = pre;
+        const float xt = pre_xt;
         float nx;
         if (!a.sde) {
             // dxt = 0.5*(mu - xt - est); dxt = dxt*noise_t*h; xt = (xt - dxt)*mask          (:265-267)
