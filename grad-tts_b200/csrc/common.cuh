@@ -125,6 +125,20 @@ template <> struct Act<__nv_bfloat16> {
     }
 };
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256).  A thread that owns 32 contiguous bytes of an NHWC pixel row writes
+// one full 32-byte sector per instruction instead of two half sectors -- the epilogues' stores are scattered across
+// pixels (lane = pixel), so the LSU cost is per sector, not per byte.  Address must be 32-byte aligned.
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&w)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                 "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_256(const void* p, uint32_t (&w)[8]) {
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(p));
+}
+
 // ---------------------------------------------------------------- maths
 // Mish = x * tanh(softplus(x)), torch softplus(beta=1, threshold=20)  (reference model/diffusion.py:16-18)
 template <bool kStrict>

@@ -299,14 +299,14 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
             }
             if (valid) {
                 if (kRes) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(res + opix * N + cbase + c0);
+                    const __nv_bfloat16* rp = res + opix * N + cbase + c0;
 #pragma unroll
-                    for (int v4 = 0; v4 < 4; ++v4) {
-                        const uint4 u = __ldg(rp + v4);
-                        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+                    for (int v8 = 0; v8 < 2; ++v8) {                 // 2 x 32 bytes = 32 bf16 residual values
+                        uint32_t w[8];
+                        ld_global_nc_256(rp + v8 * 16, w);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            f[v4 * 4 + k] = fadd2(f[v4 * 4 + k], make_float2(__uint_as_float(w[k] << 16),
+                        for (int k = 0; k < 8; ++k)
+                            f[v8 * 8 + k] = fadd2(f[v8 * 8 + k], make_float2(__uint_as_float(w[k] << 16),
                                                                              __uint_as_float(w[k] & 0xffff0000u)));
                     }
                 }
@@ -314,16 +314,16 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
 #pragma unroll
                     for (int q = 0; q < 16; ++q) f[q] = fmul2(f[q], m2);
                 }
-                uint4* op = reinterpret_cast<uint4*>(out + opix * N + cbase + c0);
+                __nv_bfloat16* op = out + opix * N + cbase + c0;
 #pragma unroll
-                for (int v4 = 0; v4 < 4; ++v4) {
-                    uint32_t w[4];
+                for (int v8 = 0; v8 < 2; ++v8) {                     // one full 32-byte sector per store instruction
+                    uint32_t w[8];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[v4 * 4 + k].x, f[v4 * 4 + k].y);
+                    for (int k = 0; k < 8; ++k) {
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[v8 * 8 + k].x, f[v8 * 8 + k].y);
                         w[k] = *reinterpret_cast<uint32_t*>(&h2);
                     }
-                    op[v4] = make_uint4(w[0], w[1], w[2], w[3]);
+                    st_global_256(op + v8 * 16, w);
                 }
             }
         }

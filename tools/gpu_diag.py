@@ -159,6 +159,17 @@ def stage_convdbg():
     """Times one large conv through the test hook (GTTS_CONV_REPS) under the experiment switches GTTS_CONV_DBG."""
     import gpu_util as gu
     cin, cout, H, W, B = [int(v) for v in os.environ.get("GTTS_SHAPE", "64,64,80,1720,8").split(",")]
+    kind = int(os.environ.get("GTTS_KIND", "0"))
+    if kind != 0:       # 1x1 (optionally per-sample weights + residual + mask: GTTS_KIND=1 GTTS_RES=1), stride-2, ConvT
+        res = bool(int(os.environ.get("GTTS_RES", "0")))
+        c = gu.conv_case(kind, B, H, W, cin, 0, cout, seed=1, residual=res, mask=res or kind in (2, 3), per_sample=res)
+        os.environ["GTTS_CONV_REPS"] = "5"
+        for dbg in (0, 1, 2, 3):
+            os.environ["GTTS_CONV_DBG"] = str(dbg)
+            print(f"impl=1 kind={kind} dbg={dbg}", flush=True)
+            gu.run_conv(c, 1, 1)
+        os.environ["GTTS_CONV_DBG"] = "0"
+        return
     c = gu.conv_case(0, B, H, W, cin, 0, cout, seed=1)
     os.environ["GTTS_CONV_REPS"] = "5"
     if os.environ.get("GTTS_CONV_TIMING"):
