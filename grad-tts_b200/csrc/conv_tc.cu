@@ -41,7 +41,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-    const TcShared sh = tc_shared(smem + (size_t)p.stages * kStage);
+    // Weights either travel with every A tile (stage = A | B) or, when all nphase*ntaps*nchunks tiles fit next to a few A
+    // stages, are loaded once per CTA into their own region (1x1, stride-2 and transposed 64-channel convs: the kernel is
+    // L2->SMEM-fill bound and a weight tile is a third to two thirds of every stage).
+    const int resident = p.b_resident;
+    const int stage_bytes = resident ? kABytes : kStage;
+    uint8_t* smem_b = smem + (size_t)p.stages * stage_bytes;        // resident weights (b_slots tiles)
+    const TcShared sh = tc_shared(smem_b + (size_t)(resident ? p.b_slots : 0) * kBBytes);
     uint64_t* full = sh.full;
     uint64_t* empty = sh.empty;
 
@@ -52,7 +58,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tma_prefetch_desc(&mapW);
         tma_prefetch_desc(&mapWh);
     }
-    const uint32_t tmem_base = tc_prologue<N>(p, sh, p.stages, 0, tid, warp, lane);
+    const uint32_t tmem_base = tc_prologue<N>(p, sh, p.stages, 1, tid, warp, lane);
     const int n_it = tc_num_iters(p);
     const int G = (int)gridDim.x;
 
@@ -65,6 +71,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t rank = p.mc ? cluster_ctarank() : 0u;
+            if (resident && n_it > 0) {
+                const int nck = p.nchunk0 + p.nchunk1;
+                mbar_expect_tx(&sh.fullb[0], (uint32_t)(p.b_slots * kBBytes));
+                for (int ph = 0; ph < p.nphase; ++ph)
+                    for (int tap = 0; tap < p.ntaps; ++tap)
+                        for (int ck = 0; ck < nck; ++ck)
+                            tma_load_2d(&mapW, &sh.fullb[0], smem_b + (size_t)((ph * p.ntaps + tap) * nck + ck) * kBBytes, ck * 64,
+                                        p.wrow[ph][tap]);
+            }
             for (int it = 0; it < n_it; ++it) {
                 if (kStats && (it == n_it - 8 || it == n_it - 1)) prefetch_l2(p.e.gn_counters);   // see conv_tc_halo.cu
                 const int tile = (int)blockIdx.x + it * G;
@@ -77,8 +92,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     const int wr = p.wrow[ph][tap] + b * p.w_batch_rows;
                     for (int ck = 0; ck < p.nchunk0 + p.nchunk1; ++ck) {
                         mbar_wait(&empty[stage], phase ^ 1u);
-                        uint8_t* sa = smem + (size_t)stage * kStage;
-                        mbar_expect_tx(&full[stage], (uint32_t)((dummy ? 0 : p.a_bytes) + kBBytes));
+                        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                        mbar_expect_tx(&full[stage], (uint32_t)((dummy ? 0 : p.a_bytes) + (resident ? 0 : kBBytes)));
                         if (dummy) {
                         } else if (p.stride2) {
                             // 5-D view (2C, W/2, 2, H/2, B): input pixel 2*o + d, d in {-1,0,1}
@@ -90,7 +105,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         } else {
                             tma_load_4d(&mapA1, &full[stage], sa, (ck - p.nchunk0) * 64, w0 + dx, h0 + dy, b);
                         }
-                        if (p.mc) {
+                        if (resident) {
+                        } else if (p.mc) {
                             // my half of the weight tile goes to both CTAs of the pair (same smem offset, same barrier)
                             // (multicast is only used with one phase and shared weights: the row is p.wrow[0][tap])
                             tma_load_2d_mc(&mapWh, &full[stage], sa + kABytes + rank * (kBBytes / 2), ck * 64,
@@ -109,12 +125,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int nstage = p.stages;
         const uint64_t a_desc0 = make_sw128_kmajor_desc(smem_u32(smem));
         const uint64_t b_desc0 = make_sw128_kmajor_desc(smem_u32(smem) + kABytes);
-        const uint64_t stage_step = (uint64_t)(kStage >> 4);
+        const uint64_t stage_step = (uint64_t)(stage_bytes >> 4);
+        const uint64_t b_res0 = make_sw128_kmajor_desc(smem_u32(smem_b));
         int stage = 0, it = 0;
         uint32_t phase = 0;
         const int mc = p.mc;
+        if (resident && n_it > 0) mbar_wait(&sh.fullb[0], 0u);
         for (it = 0; it < n_it; ++it) {
             const int buf = it % acc_bufs<N>();
+            const int ph_tile = resident ? (((int)blockIdx.x + it * G) / tiles_per_phase) % p.nphase : 0;
             mbar_wait(&sh.tempty[buf], ((uint32_t)(it / acc_bufs<N>()) & 1u) ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
@@ -123,7 +142,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t adesc = a_desc0 + (uint64_t)stage * stage_step;
-                    const uint64_t bdesc = b_desc0 + (uint64_t)stage * stage_step;
+                    const uint64_t bdesc = resident ? b_res0 + (uint64_t)(ph_tile * nkb + kb) * (uint64_t)(kBBytes >> 4)
+                                                    : b_desc0 + (uint64_t)stage * stage_step;
                     if (!(p.dbg & 1)) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k)                 // 4 x (K = 16 bf16 = 32 bytes)
@@ -269,11 +289,21 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
         pl->smem = (size_t)p.stages * abytes + (size_t)p.b_slots * btile + kMiscBytes + 1024;
         }
     } else {
-        const int stage_bytes = kABytes + g.Cout * 128;
-        int stages = budget / stage_bytes;
-        if (stages > 8) stages = 8;
-        p.stages = stages;
-        pl->smem = (size_t)stages * stage_bytes + kMiscBytes + 1024;
+        const int btile = g.Cout * 128, nwt = g.nphase * g.ntaps * (p.nchunk0 + p.nchunk1);
+        const bool want_res = getenv("GTTS_TAP_RESIDENT") ? atoi(getenv("GTTS_TAP_RESIDENT")) != 0 : true;
+        if (want_res && g.w_batch_rows == 0 && nwt * btile + 4 * kABytes <= budget && nwt * btile < (1 << 20)) {
+            p.b_resident = 1; p.b_slots = nwt;
+            int stages = (budget - nwt * btile) / kABytes;
+            if (stages > 8) stages = 8;
+            p.stages = stages;
+            pl->smem = (size_t)stages * kABytes + (size_t)nwt * btile + kMiscBytes + 1024;
+        } else {
+            const int stage_bytes = kABytes + btile;
+            int stages = budget / stage_bytes;
+            if (stages > 8) stages = 8;
+            p.stages = stages;
+            pl->smem = (size_t)stages * stage_bytes + kMiscBytes + 1024;
+        }
     }
     pl->grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
     if (pl->grid > 256) pl->grid = 256;                    // GN partial buffers hold 256 CTA slots per sample
@@ -282,7 +312,7 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
         const char* mce = getenv("GTTS_MC");
         const int want = mce ? atoi(mce) : 0;      // measured: no gain on B200 (these layers are MMA-, not fill-bound)
         if (p.mc != 2)
-            p.mc = (want && !halo_mode && g.Cout == 256 && g.nphase == 1 && g.w_batch_rows == 0 && p.num_tiles >= 2 &&
+            p.mc = (want && !halo_mode && !p.b_resident && g.Cout == 256 && g.nphase == 1 && g.w_batch_rows == 0 && p.num_tiles >= 2 &&
                     num_sms >= 2) ? 1 : 0;
         if (p.mc) {
             int gmax = num_sms & ~1;

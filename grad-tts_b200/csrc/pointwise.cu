@@ -187,8 +187,20 @@ first_conv_kernel(FirstConvArgs a) {
                 v0[2 * c] = acc[j][c].x;     v0[2 * c + 1] = acc[j][c].y;
                 v1[2 * c] = acc[j][4 + c].x; v1[2 * c + 1] = acc[j][4 + c].y;
             }
-            Act<T>::store8(o + (size_t)j * 64, v0);
-            Act<T>::store8(o + (size_t)j * 64 + 8, v1);
+            if (sizeof(T) == 2) {                          // 16 bf16 = one full 32-byte sector in one store
+                uint32_t w[8];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(v0[2 * c], v0[2 * c + 1]);
+                    __nv_bfloat162 h1 = __floats2bfloat162_rn(v1[2 * c], v1[2 * c + 1]);
+                    w[c] = *reinterpret_cast<uint32_t*>(&h0);
+                    w[4 + c] = *reinterpret_cast<uint32_t*>(&h1);
+                }
+                st_global_256(o + (size_t)j * 64, w);
+            } else {
+                Act<T>::store8(o + (size_t)j * 64, v0);
+                Act<T>::store8(o + (size_t)j * 64 + 8, v1);
+            }
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 st[0] += v0[c]; st[2] = fmaf(v0[c], v0[c], st[2]);
