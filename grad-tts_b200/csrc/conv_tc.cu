@@ -251,14 +251,9 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
         { const char* pf = getenv("GTTS_HALO_PREFETCH"); p.halo_prefetch = pf ? atoi(pf) : 0; }
         int max_st = 6;
         if (const char* ms = getenv("GTTS_HALO_STAGES")) max_st = atoi(ms);
-        // CTA pairs pay off where a single CTA cannot keep the weights resident (measured, chunk 16x1720: 128->128
-        // 134 -> 111 us, 256->64 192 -> 133 us, 512->128 144 -> 127 us, 256->256 134 -> 125 us); with resident weights
-        // and short tiles (64->64, 64->128: 36 MMAs per tile) the pair's cross-CTA handshakes cost more than the halved
-        // weight reads save (175 -> 207 us), so those stay on one CTA.  GTTS_CTA2=2 forces pairs everywhere.
-        const bool single_resident = ntiles_b <= 16 && ntiles_b * btile + 3 * abytes <= budget;
-        const char* c2 = getenv("GTTS_CTA2");
-        const bool cta2 = halo_mode == 2 && conv_tc_cta2_enabled() && p.num_tiles >= 2 && num_sms >= 2 &&
-                          (!single_resident || (c2 && atoi(c2) == 2));
+        // CTA pairs for every halo conv (measured, chunk 16x1720: 64->64 174 -> 136 us, 128->128 134 -> 108 us,
+        // 256->64 192 -> 131 us, 512->128 144 -> 125 us, 256->256 134 -> 123 us).  GTTS_CTA2=0: single-CTA kernels.
+        const bool cta2 = halo_mode == 2 && conv_tc_cta2_enabled() && p.num_tiles >= 2 && num_sms >= 2;
         if (cta2) {
             // CTA pair: every CTA holds half of each weight tile (Cout/2 rows)
             const int bhalf = g.Cout * 64;

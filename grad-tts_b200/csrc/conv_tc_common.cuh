@@ -245,7 +245,7 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
         mbar_wait(&sh.tfull[buf], (uint32_t)(it / kBufs) & 1u);
         tc_fence_after();
         c_wait += clock64() - tq0;
-        if (p.dbg & 2) { tc_fence_before(); __syncwarp(); if (lane == 0) { if (p.mc == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&sh.tempty[buf]), 0u)); else mbar_arrive(&sh.tempty[buf]); } if (kStats && !(p.dbg & 8)) { const int slot = it % kStatSlots; mbar_wait(&sh.sempty[slot], ((uint32_t)(it / kStatSlots) & 1u) ^ 1u); __syncwarp(); if (lane == 0) mbar_arrive(&sh.sfull[slot]); } continue; }
+        if (p.dbg & 2) { tc_fence_before(); __syncwarp(); if (lane == 0) { if (p.mc == 2) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&sh.tempty[buf]), 0u)); else mbar_arrive(&sh.tempty[buf]); } if (kStats && !(p.dbg & 8)) { const int slot = it % kStatSlots; mbar_wait(&sh.sempty[slot], ((uint32_t)(it / kStatSlots) & 1u) ^ 1u); __syncwarp(); if (lane == 0) mbar_arrive(&sh.sfull[slot]); } continue; }
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * N + cbase);
 
         float2 ssum[4], ssq[4];                                      // per local group: packed (even, odd) columns
@@ -265,7 +265,7 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    if (p.mc == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&sh.tempty[buf]), 0u));   // CTA pair: the leader issues the MMAs
+                    if (p.mc == 2) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&sh.tempty[buf]), 0u));   // CTA pair: the leader issues the MMAs
                     else mbar_arrive(&sh.tempty[buf]);
                 }
             }
