@@ -375,6 +375,9 @@ gn_apply_fast_kernel(GnApplyArgs a) {
                                            : make_float2(0.f, 0.f);
         }
     }
+    // pixel column of my vector: one division for the first vector, then += 256/C8 pixels per vector with wrap-around
+    const uint32_t pstep = 256u >> c8shift;
+    uint32_t hrow_n = (vbase >> c8shift) / W, wcol_n = (vbase >> c8shift) - hrow_n * W;
 #pragma unroll 1
     for (int itg = 0; itg < kGfIter; ++itg) {
     const uint32_t v0 = vbase + (uint32_t)itg * (256u * kGfVec);
@@ -388,7 +391,7 @@ gn_apply_fast_kernel(GnApplyArgs a) {
         if (ok[k]) {
             pv[k] = __ldg(reinterpret_cast<const uint4*>(raw + (size_t)vi * 8));
             if (kHasRes) pr[k] = __ldg(reinterpret_cast<const uint4*>(res + (size_t)vi * 8));
-            const uint32_t pin = vi >> c8shift, hrow = pin / W, wcol = pin - hrow * W;
+            const uint32_t pin = vi >> c8shift, hrow = hrow_n, wcol = wcol_n;
             m[k] = mrow[wcol];
             if (kFirstRes) {
                 const size_t pix = (size_t)b * a.H * W + pin;
@@ -397,6 +400,8 @@ gn_apply_fast_kernel(GnApplyArgs a) {
                 fin[k][2] = a.fr_cin == 3 ? a.fr_s[(size_t)b * a.H + hrow] * m[k] : 0.f;
             }
         }
+        wcol_n += pstep;
+        while (wcol_n >= W) { wcol_n -= W; ++hrow_n; }
     }
 #pragma unroll
     for (int k = 0; k < kGfVec; ++k) {
