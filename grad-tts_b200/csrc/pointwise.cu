@@ -334,6 +334,9 @@ constexpr int kGfVec = 4;
 template <bool kHasRes, bool kHasTb, bool kFirstRes, int kGfIter>
 __global__ void __launch_bounds__(256, kFirstRes ? 3 : 4)
 gn_apply_fast_kernel(GnApplyArgs a) {
+    // first-block variant: the kHasTb flag is reused as "the input has a third (speaker) channel" (the two exclude each other)
+    constexpr bool kTb = kHasTb && !kFirstRes, kCin3 = kFirstRes && kHasTb;
+    constexpr int kCin = kCin3 ? 3 : 2;
     pdl_trigger();
     pdl_wait();
     typedef __nv_bfloat16 T;
@@ -354,7 +357,7 @@ gn_apply_fast_kernel(GnApplyArgs a) {
         const float s0 = rstd * __ldg(a.gamma + c0 + 2 * q), s1 = rstd * __ldg(a.gamma + c0 + 2 * q + 1);
         const float h0 = __ldg(a.beta + c0 + 2 * q) - mean * s0, h1 = __ldg(a.beta + c0 + 2 * q + 1) - mean * s1;
         sc[q] = make_float2(s0, s1);                   sh[q] = make_float2(h0, h1);
-        tb[q] = kHasTb ? make_float2(__ldg(a.tbias + (size_t)b * a.tbias_bstride + c0 + 2 * q),
+        tb[q] = kTb ? make_float2(__ldg(a.tbias + (size_t)b * a.tbias_bstride + c0 + 2 * q),
                                      __ldg(a.tbias + (size_t)b * a.tbias_bstride + c0 + 2 * q + 1))
                        : make_float2(0.f, 0.f);
     }
@@ -363,16 +366,14 @@ gn_apply_fast_kernel(GnApplyArgs a) {
     T* out = reinterpret_cast<T*>(a.out) + (size_t)b * per_sample * 8;
     const float* mrow = a.mask + (size_t)b * W;
 
-    float2 frw[kFirstRes ? 4 : 1][3], frb[kFirstRes ? 4 : 1];
+    float2 frw[kFirstRes ? 4 : 1][kCin], frb[kFirstRes ? 4 : 1];
     if (kFirstRes) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             frb[q] = make_float2(__ldg(a.fr_b + c0 + 2 * q), __ldg(a.fr_b + c0 + 2 * q + 1));
 #pragma unroll
-            for (int ci = 0; ci < 3; ++ci)
-                frw[q][ci] = ci < a.fr_cin ? make_float2(__ldg(a.fr_w + (c0 + 2 * q) * a.fr_cin + ci),
-                                                         __ldg(a.fr_w + (c0 + 2 * q + 1) * a.fr_cin + ci))
-                                           : make_float2(0.f, 0.f);
+            for (int ci = 0; ci < kCin; ++ci)
+                frw[q][ci] = make_float2(__ldg(a.fr_w + (c0 + 2 * q) * kCin + ci), __ldg(a.fr_w + (c0 + 2 * q + 1) * kCin + ci));
         }
     }
     // pixel column of my vector: one division for the first vector, then += 256/C8 pixels per vector with wrap-around
@@ -382,7 +383,7 @@ gn_apply_fast_kernel(GnApplyArgs a) {
     for (int itg = 0; itg < kGfIter; ++itg) {
     const uint32_t v0 = vbase + (uint32_t)itg * (256u * kGfVec);
     uint4 pv[kGfVec], pr[kGfVec];
-    float m[kGfVec], fin[kFirstRes ? kGfVec : 1][3];
+    float m[kGfVec], fin[kFirstRes ? kGfVec : 1][kCin];
     bool ok[kGfVec];
 #pragma unroll
     for (int k = 0; k < kGfVec; ++k) {
@@ -397,7 +398,7 @@ gn_apply_fast_kernel(GnApplyArgs a) {
                 const size_t pix = (size_t)b * a.H * W + pin;
                 fin[k][0] = a.fr_mu[pix] * m[k];
                 fin[k][1] = a.fr_x[pix] * m[k];
-                fin[k][2] = a.fr_cin == 3 ? a.fr_s[(size_t)b * a.H + hrow] * m[k] : 0.f;
+                if (kCin3) fin[k][kCin - 1] = a.fr_s[(size_t)b * a.H + hrow] * m[k];
             }
         }
         wcol_n += pstep;
@@ -415,13 +416,12 @@ gn_apply_fast_kernel(GnApplyArgs a) {
             const float2 x = make_float2(__uint_as_float(w[q] << 16), __uint_as_float(w[q] & 0xffff0000u));
             const float2 y = ffma2(x, sc[q], sh[q]);                    // GroupNorm affine          (:53)
             float2 o = mish2_fast(y, fmul2(y, l2e));                    // Mish                      (:54)
-            if (kHasTb) o = fadd2(o, tb[q]);                            // (mish*m + tb)*m == (mish + tb)*m, m in {0,1}
+            if (kTb) o = fadd2(o, tb[q]);                            // (mish*m + tb)*m == (mish + tb)*m, m in {0,1}
             if (kHasRes) o = fadd2(o, make_float2(__uint_as_float(rw[q] << 16), __uint_as_float(rw[q] & 0xffff0000u)));
             if (kFirstRes) {
                 float2 rr = frb[q];
 #pragma unroll
-                for (int ci = 0; ci < 3; ++ci)
-                    if (ci < 2 || a.fr_cin == 3) rr = ffma2(frw[q][ci], make_float2(fin[k][ci], fin[k][ci]), rr);
+                for (int ci = 0; ci < kCin; ++ci) rr = ffma2(frw[q][ci], make_float2(fin[k][ci], fin[k][ci]), rr);
                 o = fadd2(o, rr);
             }
             o = fmul2(o, m2);                                           // * mask (stored masked)
@@ -671,7 +671,7 @@ int gn_apply(ActKind act, const GnApplyArgs& a, bool strict, cudaStream_t s) {
     if (act == ACT_BF16 && !strict) {
         const bool res = a.residual != nullptr, tb = a.tbias != nullptr, fr = a.fr_w != nullptr;
         int rc;
-        if (fr)             rc = gn_apply_fast_launch<false, false, true>(a, s);
+        if (fr)             rc = a.fr_cin == 3 ? gn_apply_fast_launch<false, true, true>(a, s) : gn_apply_fast_launch<false, false, true>(a, s);
         else if (res && tb) rc = gn_apply_fast_launch<true, true, false>(a, s);
         else if (res)       rc = gn_apply_fast_launch<true, false, false>(a, s);
         else if (tb)        rc = gn_apply_fast_launch<false, true, false>(a, s);
