@@ -337,6 +337,7 @@ int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, i
                     }
                     fprintf(stderr, "[conv timing] CTA 0 arrival at 2nd barrier (cycles after 1st), warps 0..7: %llu %llu %llu %llu %llu %llu %llu %llu\n",
                             h[24], h[25], h[26], h[27], h[28], h[29], h[30], h[31]);
+                    fprintf(stderr, "[conv timing] CTA 0 epilogue group 0 warp 0: math %llu store %llu stats-reduce %llu cycles\n", h[23], h[24], h[25]);
                     int slow = 0;
                     for (int c = 0; c < G; ++c) if (h[c * 32 + 15] > h[slow * 32 + 15]) slow = c;
                     fprintf(stderr, "[conv timing] last CTA %d: teardown cycles: fence+sync %llu, tickets %llu, fence2 %llu, finalize %llu (nfin %llu) atomic %llu dealloc %llu\n",

@@ -6,6 +6,17 @@
 #include "common.cuh"
 #include "ops.h"
 
+// Per-phase cycle counters of the epilogue loop (GTTS_CONV_TIMING=1): compiled in only with -DGTTS_EPI_TIMING=1, because
+// six clock reads per tile cost ~8 % of a 64->64 conv.
+#ifndef GTTS_EPI_TIMING
+#define GTTS_EPI_TIMING 0
+#endif
+#if GTTS_EPI_TIMING
+#define GTTS_EPI_CLK() clock64()
+#else
+#define GTTS_EPI_CLK() 0ll
+#endif
+
 namespace gtts {
 namespace tc {
 
@@ -227,8 +238,8 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
     const int G = (int)gridDim.x;
     tw.init(p, (int)blockIdx.x + grp * G, 2 * G);
     const int n_it = tc_num_iters(p);
-    long long c_wait = 0, c_ld = 0, c_sring = 0;
-    const long long te0 = clock64();
+    long long c_wait = 0, c_ld = 0, c_sring = 0, c_math = 0, c_store = 0, c_red = 0;
+    const long long te0 = GTTS_EPI_CLK();
     for (int it = grp; it < n_it; it += 2, tw.advance(2 * G)) {
         const int buf = it % kBufs;
         const int b = tw.b, ph = tw.ph;
@@ -241,10 +252,10 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
         if (kMask) m = valid ? e.mask[(size_t)b * p.Wout + ow] : 0.f;
         const float2 m2 = make_float2(m, m);
 
-        const long long tq0 = clock64();
+        const long long tq0 = GTTS_EPI_CLK();
         mbar_wait(&sh.tfull[buf], (uint32_t)(it / kBufs) & 1u);
         tc_fence_after();
-        c_wait += clock64() - tq0;
+        c_wait += GTTS_EPI_CLK() - tq0;
         if (p.dbg & 2) { tc_fence_before(); __syncwarp(); if (lane == 0) { if (p.mc == 2) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&sh.tempty[buf]), 0u)); else mbar_arrive(&sh.tempty[buf]); } if (kStats && !(p.dbg & 8)) { const int slot = it % kStatSlots; mbar_wait(&sh.sempty[slot], ((uint32_t)(it / kStatSlots) & 1u) ^ 1u); __syncwarp(); if (lane == 0) mbar_arrive(&sh.sfull[slot]); } continue; }
         const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * N + cbase);
 
@@ -255,10 +266,11 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
 #pragma unroll
         for (int c0 = 0; c0 < kColsPerWarp; c0 += 32) {
             uint32_t r[32];
-            const long long tl = clock64();
+            const long long tl = GTTS_EPI_CLK();
             tmem_ld32(taddr + (uint32_t)c0, r);
             tmem_ld_wait();
-            c_ld += clock64() - tl;
+            const long long tm0 = GTTS_EPI_CLK();
+            c_ld += tm0 - tl;
             if (c0 + 32 >= kColsPerWarp) {
                 // last TMEM read of this buffer: hand it back to the MMA warp before the arithmetic and stores
                 // (one arrive per warp: 256 threads hammering one mbarrier word cost ~0.5 us per tile)
@@ -297,6 +309,8 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
                     }
                 }
             }
+            const long long tm1 = GTTS_EPI_CLK();
+            c_math += tm1 - tm0;
             if (valid) {
                 if (kRes) {
                     const __nv_bfloat16* rp = res + opix * N + cbase + c0;
@@ -323,20 +337,23 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
                         __nv_bfloat162 h2 = __floats2bfloat162_rn(f[v8 * 8 + k].x, f[v8 * 8 + k].y);
                         w[k] = *reinterpret_cast<uint32_t*>(&h2);
                     }
-                    st_global_256(op + v8 * 16, w);
+                    if (!(p.dbg & 64)) st_global_256(op + v8 * 16, w);
                 }
             }
+            c_store += GTTS_EPI_CLK() - tm1;
         }
 
         if (kStats && !(p.dbg & 8)) {
             float st[8];
 #pragma unroll
             for (int g = 0; g < 4; ++g) { st[g] = ssum[g].x + ssum[g].y; st[4 + g] = ssq[g].x + ssq[g].y; }
+            const long long tr0 = GTTS_EPI_CLK();
             const float t = warp_reduce8(st, lane);
             const int slot = it % kStatSlots;
-            const long long ts = clock64();
+            const long long ts = GTTS_EPI_CLK();
+            c_red += ts - tr0;
             mbar_wait(&sh.sempty[slot], ((uint32_t)(it / kStatSlots) & 1u) ^ 1u);
-            c_sring += clock64() - ts;
+            c_sring += GTTS_EPI_CLK() - ts;
             if ((lane & 3) == 0) sh.s_ring[(slot * 8 + ew) * 8 + (lane >> 2)] = t;
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh.sfull[slot]);             // release: orders the ring writes of this warp
@@ -345,7 +362,8 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
     if (p.dbg_out && ew16 == 0 && lane == 0) {
         unsigned long long* o = p.dbg_out + blockIdx.x * 32;
         o[8] = (unsigned long long)c_wait; o[9] = (unsigned long long)c_ld; o[13] = (unsigned long long)c_sring;
-        o[14] = (unsigned long long)(clock64() - te0);
+        o[14] = (unsigned long long)(GTTS_EPI_CLK() - te0);
+        o[23] = (unsigned long long)c_math; o[24] = (unsigned long long)c_store; o[25] = (unsigned long long)c_red;
     }
 }
 

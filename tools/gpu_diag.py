@@ -177,7 +177,7 @@ def stage_convdbg():
         gu.run_conv(c, 3, 1, want_stats=True)
         return
     for impl in (1, 3):
-        for dbg in (0, 1, 2, 3):
+        for dbg in [int(v) for v in os.environ.get("GTTS_DBG_LIST", "0,1,2,3").split(",")]:
             os.environ["GTTS_CONV_DBG"] = str(dbg)
             for mc in ((0, 1) if impl == 1 else (0,)):
                 os.environ["GTTS_MC"] = str(mc)
