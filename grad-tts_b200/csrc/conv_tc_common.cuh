@@ -21,7 +21,7 @@ namespace gtts {
 namespace tc {
 
 constexpr int kABytes = 128 * 128;                 // 128 pixel rows x 64 bf16
-constexpr int kMiscBytes = 6144;                   // barriers + epilogue scratch
+constexpr int kMiscBytes = 8192;                   // barriers + epilogue scratch
 constexpr int kHaloABytes = 18 * 16 * 128;         // halo box: 18 rows x 16 pixels x 64 bf16
 constexpr int kStatSlots = 8;                      // ring of per-tile GroupNorm partials (epilogue warps -> stats warp)
 constexpr int kThreads = 640;                      // warps 0-3: TMA, MMA, TMEM alloc, stats; warps 4-19: two epilogue groups
@@ -45,7 +45,7 @@ struct TcParams {
 };
 
 // misc shared-memory block layout (relative to `misc`)
-//   [0,   768)  mbarriers + TMEM slot   [768, 1792) bias[256]   [1792, 3840) stats ring   [3840, 4096) tail flags   [4096, 6144) per-sample statistics rows
+//   [0,   768)  mbarriers + TMEM slot   [768, 1792) bias[256]   [1792, 3840) stats ring   [3840, 4096) tail flags   [4096, 8192) per-sample statistics rows (<= 64 samples)
 struct TcShared {
     uint64_t *full, *empty, *tfull, *tempty, *sfull, *sempty, *fullb, *emptyb;
     uint32_t* tmem_slot;
@@ -187,7 +187,7 @@ __device__ __forceinline__ void tc_stats_loop(const TcParams& p, const TcShared&
         // Per-sample rows are staged in shared memory and written to global memory only at the very end, all samples at
         // once: the finalising CTA then finds every row in L2 (rows written 100+ us earlier had been evicted to DRAM by
         // the kernel's own output stream, and reading them back cost ~5 us of tail).  Untouched samples read as zero.
-        float* s_rows = reinterpret_cast<float*>(sh.misc + 4096);    // [B <= 32][16]
+        float* s_rows = reinterpret_cast<float*>(sh.misc + 4096);    // [B <= 64][16]
         for (int i = lane; i < p.B * 16; i += 32) s_rows[i] = 0.f;
         __syncwarp();
         for (int it = 0; it < n_it; ++it) {

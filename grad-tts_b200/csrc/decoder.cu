@@ -95,7 +95,7 @@ struct Decoder {
     int n_feats = 80, dim = 64;
     double beta_min = 0.05, beta_max = 20.0, pe_scale = 1000.0;
     int device = 0, num_sms = 148;
-    int max_chunk = 32;
+    int max_chunk = 64;
     bool use_graph = true;
     int conv_impl_bf16 = 1;   // 1: tcgen05, 0: FFMA (debug cross-check)
     int fused_attn = 1;       // bf16, C <= 128: fused k-projection + context kernel (no kv tensor)
@@ -899,7 +899,7 @@ void decoder_delete(Decoder* d) { delete d; }
 int decoder_set_option(Decoder* d, const char* key, int value) {
     GTTS_REQUIRE(d != nullptr && key != nullptr, "null argument");
     std::string k(key);
-    if (k == "max_chunk") { GTTS_REQUIRE(value >= 1 && value <= 32, "max_chunk must be in [1, 32]"); d->max_chunk = value; }
+    if (k == "max_chunk") { GTTS_REQUIRE(value >= 1 && value <= 64, "max_chunk must be in [1, 64]"); d->max_chunk = value; }
     else if (k == "use_graph") d->use_graph = value != 0;
     else if (k == "conv_impl_bf16") d->conv_impl_bf16 = value;
     else if (k == "halo_mode") d->halo_mode = value;

@@ -68,7 +68,7 @@ class GradLogPEstimator2d(BaseModule):
         self.pe_scale = pe_scale
         self.beta_min, self.beta_max = 0.05, 20.0          # overwritten by the owning Diffusion
         self.precision = "bf16"                            # "bf16" (tcgen05 convs) or "fp32" (true-fp32 arithmetic)
-        self.max_chunk = 32                                # samples per workspace chunk
+        self.max_chunk = 64                                # samples per workspace chunk
         _build_param_tree(self, synth.decoder_param_shapes(self.n_spks, pfx=""), _default_init)
         self._handle = None
         self._handle_key = None
