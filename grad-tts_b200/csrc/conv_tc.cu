@@ -351,6 +351,11 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
         ok = ok && encode_map(&pl->mapWh, weight, 2, dims, str, boxh);
     }
     if (!ok) { delete pl; return nullptr; }
+    if (e.in_stats && p.mc != 2) {
+        set_error("conv_tc: the fused input transform needs the CTA-pair halo kernel (geometry not eligible)");
+        delete pl;
+        return nullptr;
+    }
     return pl;
 }
 

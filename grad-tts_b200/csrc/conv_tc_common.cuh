@@ -424,7 +424,7 @@ __device__ __forceinline__ void tc_teardown(const TcParams& p, const TcShared& s
             const double inv_count = 1.0 / ((double)kGsz * (double)p.Hout * (double)p.Wout);
             const int G = (int)gridDim.x;
             const int q = lane & 3, r0 = lane >> 2;                  // float4 column q of partial rows r0, r0 + 8, ...
-            for (int b = warp; b < p.B; b += kThreads / 32) {
+            for (int b = warp; b < p.B && warp < kThreads / 32; b += kThreads / 32) {
                 const float4* pp = reinterpret_cast<const float4*>(e.gn_partials + (size_t)b * G * 16) + q;
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
                 for (int base = 0; base < G; base += 64) {

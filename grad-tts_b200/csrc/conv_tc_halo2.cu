@@ -26,8 +26,16 @@ __device__ __forceinline__ constexpr uint32_t make_idesc2() {      // as make_id
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((256u >> 4) << 24);
 }
 
-template <int N, bool kStats>
-__global__ void __launch_bounds__(kThreads, 1)
+constexpr int kFuseWarps = 4;                       // transform warps of the fused-input variant (warps 20..23, one per SMSP)
+
+// kFuse: the A tiles are the RAW output of the previous conv; four extra warps apply (Mish(GroupNorm(raw)) + tbias) * mask
+// in place in shared memory between the TMA arrival (local barrier rawfull) and the MMA (the leader's `full`, which then
+// counts warp arrivals of both CTAs instead of TMA bytes).  Saves the separate gn_apply pass (one write + one read of the
+// activation through HBM) and is bitwise identical to it -- but it is OFF by default (decoder option fuse_gn): measured
+// 435 us vs 134 (conv) + 103 (gn_apply) us for 64->64 at 80x1720x16.  GN+Mish at 5 TB/s already needs a whole SM's issue and
+// MUFU capacity (32 warps); four latency-bound transform warps, which also redo the 41 % halo overlap, cannot supply it.
+template <int N, bool kStats, bool kFuse>
+__global__ void __launch_bounds__(kThreads + (kFuse ? kFuseWarps * 32 : 0), 1)
 conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                      const __grid_constant__ CUtensorMap mapWh, const TcParams p) {
     constexpr int kBHalf = N * 64;                                  // bytes of this CTA's half of one weight tile
@@ -44,6 +52,7 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
+    uint64_t* rawfull = reinterpret_cast<uint64_t*>(sh.misc + 3904);   // [8] local "raw tile landed" barriers (kFuse)
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA0);
         tma_prefetch_desc(&mapA1);
@@ -53,8 +62,9 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
     pdl_trigger();
     const int nslot = p.b_slots, resident = p.b_resident, nstage = p.stages;
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < nstage; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], 1); }
+        for (int s = 0; s < nstage; ++s) { mbar_init(&sh.full[s], kFuse ? 2 * kFuseWarps : 1); mbar_init(&sh.empty[s], 1); }
         for (int s = 0; s < 16; ++s) { mbar_init(&sh.fullb[s], 1); mbar_init(&sh.emptyb[s], 1); }
+        if (kFuse) for (int s = 0; s < nstage; ++s) mbar_init(&rawfull[s], 1);
         for (int i = 0; i < kBufs; ++i) { mbar_init(&sh.tfull[i], 1); mbar_init(&sh.tempty[i], 16); }   // 8 warps x 2 CTAs
         for (int i = 0; i < kStatSlots; ++i) { mbar_init(&sh.sfull[i], 8); mbar_init(&sh.sempty[i], 1); }
         mbar_fence_init();
@@ -95,9 +105,15 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
                 const int b = tw.b, h0 = tw.th * p.bh, w0 = tw.tw * p.bw;
                 for (int ck = 0; ck < nck; ++ck) {
                     mbar_wait(&sh.empty[sa], pha ^ 1u);
-                    if (rank == 0) mbar_expect_tx(&sh.full[sa], 2u * a_tx);
-                    tma_load_4d_2sm(ck < nck0 ? &mapA0 : &mapA1, mapa_u32(smem_u32(&sh.full[sa]), 0u), smem + (size_t)sa * a_stage,
+                    if (kFuse) {
+                        mbar_expect_tx(&rawfull[sa], a_tx);          // my own tile only; the transform warps pass it on
+                        tma_load_4d(ck < nck0 ? &mapA0 : &mapA1, &rawfull[sa], smem + (size_t)sa * a_stage,
                                     (ck < nck0 ? ck : ck - nck0) * 64, ht ? h0 - 1 : w0 - 1, ht ? w0 - 1 : h0 - 1, b);
+                    } else {
+                        if (rank == 0) mbar_expect_tx(&sh.full[sa], 2u * a_tx);
+                        tma_load_4d_2sm(ck < nck0 ? &mapA0 : &mapA1, mapa_u32(smem_u32(&sh.full[sa]), 0u), smem + (size_t)sa * a_stage,
+                                        (ck < nck0 ? ck : ck - nck0) * 64, ht ? h0 - 1 : w0 - 1, ht ? w0 - 1 : h0 - 1, b);
+                    }
                     if (++sa == nstage) { sa = 0; pha ^= 1u; }
                     if (!resident) {
                         for (int tap = 0; tap < 9; ++tap) {
@@ -179,21 +195,91 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
         }
     } else if (warp == 3) {
         tc_stats_loop<kStats>(p, sh, lane);
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < kThreads / 32) {
         tc_epilogue_loop<N, kStats, false, false>(p, sh, tmem_base, warp, lane);
+    } else if (kFuse && warp >= kThreads / 32) {
+        // ================================================================ input transform (both CTAs)
+        // thread -> 16-byte chunk j (8 channels) of rows r0, r0+16, ...; the 128-byte swizzle puts chunk j of row r at
+        // chunk position j ^ (r & 7) (stages are 1024-byte aligned).
+        const ConvEpilogue& e = p.e;
+        const int t = tid - kThreads, j = t & 7, r0 = t >> 3;       // 128 threads: 8 chunks x 16 rows per pass
+        const int G = (int)gridDim.x, ht = p.halo_t;
+        const uint32_t full_leader = mapa_u32(smem_u32(&sh.full[0]), 0u);
+        TileWalk tw;
+        tw.init(p, (int)blockIdx.x, G);
+        int sa = 0;
+        uint32_t pha = 0;
+        int cur_b = -1, cur_ck = -1;
+        float2 sc[4], sh2[4], tb[4];
+        const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f);
+        for (int it = 0; it < n_it; ++it, tw.advance(G)) {
+            const int b = tw.b, h0 = tw.th * p.bh - 1, w0 = tw.tw * p.bw - 1;     // image coordinates of box row 0
+            const bool live = b < p.B;                                              // dummy tile of an odd tail: zeros
+            for (int ck = 0; ck < nck; ++ck) {
+                if (live && (b != cur_b || ck != cur_ck)) {                         // per-(sample, chunk) affine constants
+                    cur_b = b; cur_ck = ck;
+                    const int c0 = ck * 64 + j * 8, Cin = nck * 64;
+                    const int g = (c0 * 8) / Cin;
+                    const float mean = e.in_stats[(b * 8 + g) * 2], rstd = e.in_stats[(b * 8 + g) * 2 + 1];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float s0 = rstd * __ldg(e.in_gamma + c0 + 2 * q), s1 = rstd * __ldg(e.in_gamma + c0 + 2 * q + 1);
+                        const float h0f = __ldg(e.in_beta + c0 + 2 * q) - mean * s0, h1f = __ldg(e.in_beta + c0 + 2 * q + 1) - mean * s1;
+                        sc[q] = make_float2(s0, s1);
+                        sh2[q] = make_float2(h0f, h1f);
+                        tb[q] = e.in_tbias ? make_float2(__ldg(e.in_tbias + (size_t)b * e.in_tb_bstride + c0 + 2 * q),
+                                                         __ldg(e.in_tbias + (size_t)b * e.in_tb_bstride + c0 + 2 * q + 1))
+                                           : make_float2(0.f, 0.f);
+                    }
+                }
+                mbar_wait(&rawfull[sa], pha);
+                uint8_t* st = smem + (size_t)sa * a_stage;
+#pragma unroll 2
+                for (int r = r0; r < 18 * pw; r += 16) {
+                    const int a0 = r / pw, a1 = r - a0 * pw;                         // (slow, fast) box coordinates
+                    const int h = h0 + (ht ? a1 : a0), w = w0 + (ht ? a0 : a1);
+                    uint4* cp = reinterpret_cast<uint4*>(st + r * 128 + ((j ^ (r & 7)) << 4));
+                    const bool inb = live && h >= 0 && h < p.Hg && w >= 0 && w < p.Wg;
+                    uint4 o4 = make_uint4(0u, 0u, 0u, 0u);
+                    if (inb) {
+                        const float m = __ldg(e.in_mask + (size_t)b * p.Wg + w);
+                        const float2 m2 = make_float2(m, m);
+                        const uint4 v = *cp;
+                        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+                        uint32_t ow[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 x = make_float2(__uint_as_float(wv[q] << 16), __uint_as_float(wv[q] & 0xffff0000u));
+                            const float2 y = ffma2(x, sc[q], sh2[q]);
+                            float2 o = mish2_fast(y, fmul2(y, l2e));
+                            o = fmul2(fadd2(o, tb[q]), m2);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(o.x, o.y);
+                            ow[q] = *reinterpret_cast<uint32_t*>(&h2);
+                        }
+                        o4 = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    }
+                    *cp = o4;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy writes -> tensor-core reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(full_leader + (uint32_t)(sa * 8));
+                if (++sa == nstage) { sa = 0; pha ^= 1u; }
+            }
+        }
     }
     tc_teardown<N, kStats, true>(p, sh, smem, tmem_base, tid, warp, lane);
 }
 
-template <int N, bool kStats>
+template <int N, bool kStats, bool kFuse>
 int launch_halo2(const TcConvPlan* pl, cudaStream_t stream) {
     static bool attr_set = false;
-    auto k = conv_tc_halo2_kernel<N, kStats>;
+    auto k = conv_tc_halo2_kernel<N, kStats, kFuse>;
     if (!attr_set) {
         GTTS_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    GTTS_CHECK_CUDA(launch_pdl(k, dim3(pl->grid), dim3(kThreads), pl->smem, stream, 2, pl->mapA0, pl->mapA1, pl->mapWh, pl->p));
+    GTTS_CHECK_CUDA(launch_pdl(k, dim3(pl->grid), dim3(kThreads + (kFuse ? kFuseWarps * 32 : 0)), pl->smem, stream, 2, pl->mapA0,
+                               pl->mapA1, pl->mapWh, pl->p));
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -204,9 +290,16 @@ int conv_tc_halo2_launch(const TcConvPlan* pl, cudaStream_t stream) {
     const ConvEpilogue& e = pl->p.e;
     GTTS_REQUIRE(e.residual == nullptr && e.mask == nullptr, "conv_tc_halo2: plain or GN-statistics epilogue only");
     const bool st = e.gn_partials != nullptr;
-    if (pl->N == 64) return st ? launch_halo2<64, true>(pl, stream) : launch_halo2<64, false>(pl, stream);
-    if (pl->N == 128) return st ? launch_halo2<128, true>(pl, stream) : launch_halo2<128, false>(pl, stream);
-    if (pl->N == 256) return st ? launch_halo2<256, true>(pl, stream) : launch_halo2<256, false>(pl, stream);
+    if (e.in_stats) {                                               // fused input transform (block2 convs: always with stats)
+        GTTS_REQUIRE(st, "conv_tc_halo2: the fused-input variant is built with GroupNorm statistics only");
+        if (pl->N == 64) return launch_halo2<64, true, true>(pl, stream);
+        if (pl->N == 128) return launch_halo2<128, true, true>(pl, stream);
+        if (pl->N == 256) return launch_halo2<256, true, true>(pl, stream);
+    } else {
+        if (pl->N == 64) return st ? launch_halo2<64, true, false>(pl, stream) : launch_halo2<64, false, false>(pl, stream);
+        if (pl->N == 128) return st ? launch_halo2<128, true, false>(pl, stream) : launch_halo2<128, false, false>(pl, stream);
+        if (pl->N == 256) return st ? launch_halo2<256, true, false>(pl, stream) : launch_halo2<256, false, false>(pl, stream);
+    }
     set_error("conv_tc_halo2: unsupported Cout");
     return 2;
 }

@@ -99,6 +99,9 @@ struct Decoder {
     bool use_graph = true;
     int conv_impl_bf16 = 1;   // 1: tcgen05, 0: FFMA (debug cross-check)
     int fused_attn = 1;       // bf16, C <= 128: fused k-projection + context kernel (no kv tensor)
+    int fuse_gn = 0;          // 1: block2 convs apply block1's GroupNorm+Mish(+time bias, mask) on their operand tiles (no gn_apply
+                              // pass).  Bitwise identical, but measured SLOWER (64->64 @L0: 435 us vs 134 + 103 us): GN+Mish at
+                              // 5 TB/s already needs a whole SM's issue/MUFU capacity, four transform warps cannot supply it.
     int halo_mode = 2;        // 3x3 convs: 0 = per-tap boxes, 1/2 = halo box (18x16 / 18x10) + shifted descriptor views
     std::map<std::string, float*> params;
     std::map<std::string, size_t> param_numel;
@@ -378,11 +381,25 @@ struct PlanBuilder {
     }
 
     // Registers one convolution.  GN statistics are requested by passing a stats buffer.
+    struct InFuse { const float* stats; const float* gamma; const float* beta; const float* tbias; int tb_bstride; const float* mask; };
+
+    // true when a 3x3 conv with this geometry would run on the CTA-pair halo kernel (the only one with the fused input path)
+    bool can_fuse_input(const ConvGeom& g) const {
+        if (!use_tc() || !d->fuse_gn || d->halo_mode != 2 || !conv_tc_cta2_enabled() || !conv_tc_halo_eligible(g)) return false;
+        if (getenv("GTTS_FUSE_GN") && atoi(getenv("GTTS_FUSE_GN")) == 0) return false;
+        const long tiles = (long)g.B * ((g.Hg + 7) / 8) * ((g.Wg + 15) / 16);
+        return g.Cin1 == 0 && tiles >= 2 && d->num_sms >= 2;
+    }
+
     void add_conv(const ConvGeom& g, const void* src0, const void* src1, const void* w, int wrows, const float* bias,
-                  const void* residual, const float* mask, void* out, float* gn_stats) {
+                  const void* residual, const float* mask, void* out, float* gn_stats, const InFuse* fuse = nullptr) {
         ConvEpilogue e;
         memset(&e, 0, sizeof(e));
         e.bias = bias; e.residual = residual; e.mask = mask; e.out = out;
+        if (fuse) {
+            e.in_stats = fuse->stats; e.in_gamma = fuse->gamma; e.in_beta = fuse->beta; e.in_tbias = fuse->tbias;
+            e.in_tb_bstride = fuse->tb_bstride; e.in_mask = fuse->mask;
+        }
         if (gn_stats) {
             e.gn_partials = pl->partials; e.gn_stats = gn_stats; e.gn_counters = pl->counters; e.gn_eps = 1e-5f;
             if (slots_for(g) > pl->partial_slots) { set_error("internal: GN partial buffer too small"); failed = true; return; }
@@ -448,8 +465,15 @@ struct PlanBuilder {
         } else {
             add_conv(geom_3x3(B, H[lvl], W[lvl], c0, c1, Co, 1), x0, x1, R.b1.w, 9 * Co, R.b1.bias, nullptr, nullptr, raw1, st1);
         }
-        add_gn_apply(lvl, Co, raw1, st1, R.b1, tb, nullptr, false, a1);
-        add_conv(geom_3x3(B, H[lvl], W[lvl], Co, 0, Co, 1), a1, nullptr, R.b2.w, 9 * Co, R.b2.bias, nullptr, nullptr, raw2, st2);
+        const ConvGeom g2 = geom_3x3(B, H[lvl], W[lvl], Co, 0, Co, 1);
+        if (can_fuse_input(g2)) {
+            // block1's GroupNorm + Mish + time bias + mask are applied by block2's conv on its operand tiles
+            InFuse fz{st1, R.b1.gamma, R.b1.beta, tb, pl->est_mode ? 1792 : 0, lmask[lvl]};
+            add_conv(g2, raw1, nullptr, R.b2.w, 9 * Co, R.b2.bias, nullptr, nullptr, raw2, st2, &fz);
+        } else {
+            add_gn_apply(lvl, Co, raw1, st1, R.b1, tb, nullptr, false, a1);
+            add_conv(g2, a1, nullptr, R.b2.w, 9 * Co, R.b2.bias, nullptr, nullptr, raw2, st2);
+        }
         const void* resid = nullptr;
         bool first_res = false;
         if (r == 0) {
@@ -702,7 +726,7 @@ int plan_create(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde,
 int get_plan(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, Plan** out) {
     std::string key = std::to_string((int)kind) + ":" + std::to_string(B) + ":" + std::to_string(T) + ":" +
                       (est_mode ? "e" : "s") + (sde ? "n" : "o") + (d->use_graph ? "g" : "x") +
-                      std::to_string(d->conv_impl_bf16) + std::to_string(d->halo_mode) + std::to_string(d->fused_attn);
+                      std::to_string(d->conv_impl_bf16) + std::to_string(d->halo_mode) + std::to_string(d->fused_attn) + std::to_string(d->fuse_gn);
     auto it = d->plans.find(key);
     if (it != d->plans.end()) { *out = it->second; return 0; }
     // keep at most a handful of plans alive (each owns its workspace)
@@ -904,6 +928,7 @@ int decoder_set_option(Decoder* d, const char* key, int value) {
     else if (k == "conv_impl_bf16") d->conv_impl_bf16 = value;
     else if (k == "halo_mode") d->halo_mode = value;
     else if (k == "fused_attn") d->fused_attn = value;
+    else if (k == "fuse_gn") d->fuse_gn = value;
     else { set_error("unknown option " + k); return 2; }
     return 0;
 }

@@ -42,6 +42,15 @@ struct ConvEpilogue {
     float* gn_stats;          // [B][8][2] mean, rstd
     unsigned int* gn_counters;
     float gn_eps;
+    // Input transform fused into the operand path (CTA-pair halo kernel only; null in_stats = off): the conv reads the RAW
+    // output of the previous conv and applies  (Mish(GroupNorm(raw)) + tbias) * mask  while the tile sits in shared memory
+    // (reference: Block.forward + the time-embedding add of ResnetBlock, model/diffusion.py:52-58, 75-77).
+    const float* in_stats;    // [B][8][2] mean, rstd of the previous conv
+    const float* in_gamma;    // [Cin]
+    const float* in_beta;     // [Cin]
+    const float* in_tbias;    // [B or 1][Cin] (stride in_tb_bstride floats per sample; 0 = shared)
+    int in_tb_bstride;
+    const float* in_mask;     // [B][W]
 };
 
 // CUDA-core implicit GEMM (fp32 accumulate, FFMA).  Strict-fp32 path and debugging cross-check.

@@ -89,6 +89,21 @@ def test_batch_chunking_is_bitwise_invariant(pkg, synth):
     assert torch.equal(y_all[3:4], y_one)
 
 
+def test_fused_gn_input_is_bitwise_equal_to_separate_pass(pkg, synth):
+    """block2 convs that apply block1's GroupNorm+Mish(+time bias, mask) on their operand tiles (option fuse_gn=1) must give
+    exactly the bits of the separate gn_apply pass (fuse_gn=0, the default): same formulas, same bf16 rounding point."""
+    import ctypes
+    outs = []
+    for fuse in (1, 0):
+        dec, _ = _module(pkg, synth, 247, 3, "bf16")
+        z, mask, mu, spk, _ = synth.make_inputs(3, 88, 247, seed=21)
+        h = dec.estimator._get_handle()
+        pkg._lib.check(pkg._lib.load().gtts_decoder_set_option(h, b"fuse_gn", fuse), "set_option")
+        outs.append(dec(z.to(DEV), mask.to(DEV), mu.to(DEV), 3, False, spk.to(DEV)))
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_sde_extension_matches_restatement(pkg, synth):
     n_spks, B, T, n = 1, 2, 40, 3
     dec, sd = _module(pkg, synth, n_spks, 0, "fp32")
