@@ -198,6 +198,19 @@ int gtts_decoder_profile_step(gtts_decoder* h, int B, int T, int flags, int reps
 long gtts_decoder_launches_last_call(const gtts_decoder* h) { return h ? decoder_launches_last_call(h->impl) : 0; }
 
 // ------------------------------------------------------------------------------------------------ test hooks
+int gtts_test_attn_xk(const void* x_bf16, const void* wkv_bf16, float* partials, int B, int n, int C, int chunks, int chunk_len,
+                      int use_tc, void* stream) {
+    GTTS_REQUIRE(x_bf16 && wkv_bf16 && partials, "null argument");
+    if (use_tc) {
+        GTTS_REQUIRE(C == 64, "gtts_test_attn_xk: the tcgen05 kernel is built for C = 64");
+        return attn_xk_tc64(x_bf16, wkv_bf16, partials, B, n, chunks, chunk_len, (cudaStream_t)stream);
+    }
+    setenv("GTTS_ATTN_TC", "0", 1);
+    int rc = attn_xk(x_bf16, wkv_bf16, partials, B, n, C, chunks, chunk_len, (cudaStream_t)stream);
+    unsetenv("GTTS_ATTN_TC");
+    return rc;
+}
+
 int gtts_test_issue_microbench(int N, int n_mma, int n_commit, int iters, int wait_each, int grid, double* issue_cycles,
                                double* total_cycles) {
     GTTS_REQUIRE((N == 64 || N == 128 || N == 256) && grid >= 1 && grid <= 1024 && iters >= 1,

@@ -96,6 +96,12 @@ int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, i
                    const void* residual, const float* mask, void* out, float* gn_stats, int per_sample_weights,
                    void* stream);
 
+/* Test hook: fused k-projection + softmax + context partials of the linear attention (model/diffusion.py:90-100).
+ * x: [B][n][C] bf16, wkv: [256][C] bf16 (k rows then v rows), partials: [B][4][chunks][1088] floats
+ * (m[32], l[32], ctx[32][32] per head and chunk).  use_tc = 1: tcgen05 kernel (C = 64), 0: mma.sync kernel. */
+int gtts_test_attn_xk(const void* x_bf16, const void* wkv_bf16, float* partials, int B, int n, int C, int chunks, int chunk_len,
+                      int use_tc, void* stream);
+
 /* Test hook: tcgen05 issue-path micro-benchmark (cycles per CTA, averaged over `grid` CTAs): `iters` rounds of
  * {n_mma tcgen05.mma M128xNx16, n_commit tcgen05.commit}, optionally waiting on the last commit every round. */
 int gtts_test_issue_microbench(int N, int n_mma, int n_commit, int iters, int wait_each, int grid, double* issue_cycles,

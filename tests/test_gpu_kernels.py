@@ -61,3 +61,52 @@ def test_tc_matches_ffma_bitwise_inputs():
     a, _ = gu.run_conv(c, 0, 1)
     b, _ = gu.run_conv(c, 1, 1)
     assert float((a - b).abs().max()) <= 4e-2
+
+
+def _attn_reference(x, wkv):
+    """softmax over positions of k = Wk x per (head, dim); ctx[h, d, e] = sum_n p[h, d, n] v[h, e, n]  (diffusion.py:93-97)."""
+    B, n, C = x.shape
+    k = torch.einsum("bnc,dc->bdn", x, wkv[:128]).view(B, 4, 32, n)
+    v = torch.einsum("bnc,ec->ben", x, wkv[128:]).view(B, 4, 32, n)
+    p = torch.softmax(k, dim=-1)
+    return torch.einsum("bhdn,bhen->bhde", p, v)
+
+
+def _merge_partials(part):
+    m, l, ctx = part[..., :32], part[..., 32:64], part[..., 64:].reshape(*part.shape[:-1], 32, 32)
+    M = m.max(dim=2, keepdim=True).values
+    w = torch.exp(m - M)                                    # [B, 4, chunks, 32]
+    num = (w.unsqueeze(-1) * ctx).sum(dim=2)
+    den = (w * l).sum(dim=2)
+    return num / den.unsqueeze(-1)
+
+
+@pytest.mark.parametrize("use_tc", [0, 1])
+@pytest.mark.parametrize("B,n,chunks,chunk_len,scale", [(2, 1000, 3, 384, 1.0), (1, 4096, 4, 1024, 1.0), (3, 700, 1, 768, 6.0)])
+def test_attn_xk_matches_reference(use_tc, B, n, chunks, chunk_len, scale, monkeypatch):
+    """Fused k-projection + online softmax + context (tcgen05 and mma.sync kernels) against the plain formula.  scale = 6
+    makes the running maximum jump between tiles (exercises the lazy rescale of the TMEM accumulator); GTTS_ATTN_TAU=0 forces a
+    rescale on every increase."""
+    import ctypes
+    import importlib
+    pkg = importlib.import_module("grad-tts_b200")
+    if scale != 1.0:
+        monkeypatch.setenv("GTTS_ATTN_TAU", "0")
+    g = torch.Generator().manual_seed(n + B)
+    C = 64
+    x = (torch.randn(B, n, C, generator=g) * scale).to(torch.bfloat16)
+    ramp = torch.linspace(0.2, 1.5, n).view(1, n, 1)        # later pixels are larger: the maximum keeps growing
+    x = (x.float() * ramp).to(torch.bfloat16)
+    wkv = (torch.randn(256, C, generator=g) / C ** 0.5).to(torch.bfloat16)
+    xd, wd = x.cuda(), wkv.cuda()
+    part = torch.full((B, 4, chunks, 1088), float("nan"), device="cuda")
+    lib = pkg._lib.load()
+    rc = lib.gtts_test_attn_xk(ctypes.c_void_p(xd.data_ptr()), ctypes.c_void_p(wd.data_ptr()), ctypes.c_void_p(part.data_ptr()),
+                               B, n, C, chunks, chunk_len, use_tc, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    pkg._lib.check(rc, "gtts_test_attn_xk")
+    torch.cuda.synchronize()
+    got = _merge_partials(part.cpu())
+    ref = _attn_reference(x.float(), wkv.float())
+    assert torch.isfinite(got).all()
+    err = float((got - ref).abs().max()) / float(ref.abs().max())
+    assert err <= 2e-2, f"use_tc={use_tc}: relative max error {err}"          # bf16 P and bf16 S
