@@ -604,9 +604,9 @@ int attn_xk(const void* x, const void* wkv_bf16, float* partials, int B, int n, 
             cudaStream_t s) {
     GTTS_REQUIRE(C == 64 || C == 128, "attn_xk: C must be 64 or 128");
     GTTS_REQUIRE(chunks >= 1 && chunks <= 64 && chunk_len % kXkSub == 0, "attn_xk: bad chunk plan");
-    if (C == 64) {
+    {
         const char* tc = getenv("GTTS_ATTN_TC");
-        if (!tc || atoi(tc) != 0) return attn_xk_tc64(x, wkv_bf16, partials, B, n, chunks, chunk_len, s);   // tcgen05 path
+        if (!tc || atoi(tc) != 0) return attn_xk_tc(x, wkv_bf16, partials, B, n, C, chunks, chunk_len, s);   // tcgen05 path
     }
     const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
     const __nv_bfloat16* wk = reinterpret_cast<const __nv_bfloat16*>(wkv_bf16);

@@ -41,19 +41,34 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// C = 64 only: one 64-channel swizzle atom per operand row.
+// SWIZZLE_128B descriptor with an explicit leading byte offset (MN-major operands wider than one 64-element atom)
+__device__ __forceinline__ uint64_t make_sw128_desc_lbo(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// Persistent: grid = min(#SMs, B * chunks); a CTA walks work items (sample, chunk) = blockIdx.x + k * gridDim.x, so Wk / Wv,
+// the TMEM allocation and the barriers are set up once per CTA and the tail imbalance is one item, not one CTA wave.
+// Operands wider than 64 channels are stored as C/64 swizzle atoms of [128 rows][64 ch] (16 KB each).
+template <int C>
 __global__ void __launch_bounds__(256, 1)
 attn_xk_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW,
-                  float* __restrict__ partials, int n, int chunks, int chunk_len, float tau) {
-    constexpr int C = 64;
-    constexpr int kXBytes = kAtTile * 128;                  // 128 px x 64 ch bf16 = 16 KB
+                  float* __restrict__ partials, int B, int n, int chunks, int chunk_len, float tau) {
+    constexpr int kAtoms = C / 64;
+    constexpr int kXBytes = kAtTile * 128 * kAtoms;         // 128 px x C ch bf16
+    constexpr int kWBytes = 128 * 128 * kAtoms;             // 128 rows x C ch bf16
     constexpr int kPBytes = 128 * kAtTile * 2;              // 128 d x 128 px bf16 = 32 KB (two 16 KB K-atoms)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-    uint8_t* s_wk = smem;                                   // [128 d][64 ch]  K-major SW128
-    uint8_t* s_wv = s_wk + 16384;                           // [128 e'][64 ch]
-    uint8_t* s_x = s_wv + 16384;                            // kAtStages x [128 px][64 ch]
+    uint8_t* s_wk = smem;                                   // kAtoms x [128 d][64 ch]  K-major SW128
+    uint8_t* s_wv = s_wk + kWBytes;                         // kAtoms x [128 e'][64 ch]
+    uint8_t* s_x = s_wv + kWBytes;                          // kAtStages x kAtoms x [128 px][64 ch]
     uint8_t* s_p = s_x + kAtStages * kXBytes;               // 2 x [128 d][128 px]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + 2 * kPBytes);
     uint64_t* wfull = bars;                                 // [1]
@@ -63,14 +78,13 @@ attn_xk_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     uint64_t* d1empty = bars + 9;                           // [2]
     uint64_t* pfull = bars + 11;                            // [2]
     uint64_t* pempty = bars + 13;                           // [2]
-    uint64_t* sfull = bars + 15;                            // [1]
-    uint64_t* ofull = bars + 16;                            // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    uint64_t* sfull = bars + 15;                            // [1] S (bf16) staged for the Wv product
+    uint64_t* ofull = bars + 16;                            // [1] Wv product done
+    uint64_t* odone = bars + 17;                            // [1] its result has been read: D1[0] / P[0] reusable
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int chunk = blockIdx.x, b = blockIdx.y;
-    const int n0 = chunk * chunk_len, n1 = min(n, n0 + chunk_len);
-    const int nt = (n1 - n0 + kAtTile - 1) / kAtTile;
+    const int n_items = B * chunks;
 
     pdl_trigger();
     if (warp == 0 && lane == 0) {
@@ -81,6 +95,7 @@ attn_xk_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         for (int i = 0; i < 2; ++i) { mbar_init(&d1full[i], 1); mbar_init(&d1empty[i], 4); mbar_init(&pfull[i], 4); mbar_init(&pempty[i], 1); }
         mbar_init(sfull, 4);
         mbar_init(ofull, 1);
+        mbar_init(odone, 4);
         mbar_fence_init();
     } else if (warp == 2) {
         tmem_alloc(tmem_slot, 512);
@@ -91,49 +106,66 @@ attn_xk_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     tc_fence_after();
     pdl_wait();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t t_d1 = tmem, t_s = tmem + 256;           // D1[0] cols 0..127, D1[1] cols 128..255, S cols 256..319
+    const uint32_t t_d1 = tmem, t_s = tmem + 256;           // D1[0] cols 0..127, D1[1] cols 128..255, S cols 256..256+C
+
+    auto item_range = [&](int item, int& b, int& chunk, int& n0, int& nt, int& n1) {
+        b = item / chunks; chunk = item - b * chunks;
+        n0 = chunk * chunk_len; n1 = min(n, n0 + chunk_len);
+        nt = n1 > n0 ? (n1 - n0 + kAtTile - 1) / kAtTile : 0;
+    };
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_expect_tx(wfull, 32768u);
-            tma_load_2d(&mapW, wfull, s_wk, 0, 0);          // k rows
-            tma_load_2d(&mapW, wfull, s_wv, 0, 128);        // v rows
-            for (int i = 0; i < nt; ++i) {
-                const int s = i % kAtStages;
-                mbar_wait(&xempty[s], (uint32_t)((i / kAtStages) & 1) ^ 1u);
-                mbar_expect_tx(&xfull[s], (uint32_t)kXBytes);
-                tma_load_2d(&mapX, &xfull[s], s_x + s * kXBytes, 0, b * n + n0 + i * kAtTile);    // rows past the tensor: zeros
+            mbar_expect_tx(wfull, (uint32_t)(2 * kWBytes));
+#pragma unroll
+            for (int a = 0; a < kAtoms; ++a) {
+                tma_load_2d(&mapW, wfull, s_wk + a * 16384, a * 64, 0);          // k rows
+                tma_load_2d(&mapW, wfull, s_wv + a * 16384, a * 64, 128);        // v rows
+            }
+            int g = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int b, chunk, n0, nt, n1;
+                item_range(item, b, chunk, n0, nt, n1);
+                for (int i = 0; i < nt; ++i, ++g) {
+                    const int s = g % kAtStages;
+                    mbar_wait(&xempty[s], (uint32_t)((g / kAtStages) & 1) ^ 1u);
+                    mbar_expect_tx(&xfull[s], (uint32_t)kXBytes);
+#pragma unroll
+                    for (int a = 0; a < kAtoms; ++a)                             // rows past the tensor: zeros
+                        tma_load_2d(&mapX, &xfull[s], s_x + s * kXBytes + a * 16384, a * 64, b * n + n0 + i * kAtTile);
+                }
             }
         }
     } else if (warp == 1) {
-        // ---- MMA issuer: G1(0); { G1(i+1); G2(i) }...; final S.Wv^T
+        // ---- MMA issuer, per item: G1(0); { G1(i+1); G2(i) }...; then S(bf16) . Wv^T
         constexpr uint32_t kIdG1 = make_idesc<128>();                       // M128 N128, A/B K-major
-        constexpr uint32_t kIdG2 = make_idesc<C>() | (1u << 16);            // M128 N64, B MN-major
-        const uint64_t wk_desc = make_sw128_kmajor_desc(smem_u32(s_wk));
-        const uint64_t wv_desc = make_sw128_kmajor_desc(smem_u32(s_wv));
-        auto g1 = [&](int i) {
-            const int s = i % kAtStages, bb = i & 1;
-            mbar_wait(&xfull[s], (uint32_t)((i / kAtStages) & 1));
-            mbar_wait(&d1empty[bb], (uint32_t)((i >> 1) & 1) ^ 1u);
+        constexpr uint32_t kIdG2 = make_idesc<C>() | (1u << 16);            // M128 N=C, B MN-major
+        const uint32_t wk_addr = smem_u32(s_wk), wv_addr = smem_u32(s_wv);
+        auto g1 = [&](int g) {
+            const int s = g % kAtStages, bb = g & 1;
+            mbar_wait(&xfull[s], (uint32_t)((g / kAtStages) & 1));
+            mbar_wait(&d1empty[bb], (uint32_t)((g >> 1) & 1) ^ 1u);
             tc_fence_after();
             if (elect_one()) {
-                const uint64_t xd = make_sw128_kmajor_desc(smem_u32(s_x + s * kXBytes));
+                const uint32_t xa = smem_u32(s_x + s * kXBytes);
 #pragma unroll
                 for (int k = 0; k < C / 16; ++k)
-                    tc_mma_f16(t_d1 + (uint32_t)(bb * 128), wk_desc + (uint64_t)(2 * k), xd + (uint64_t)(2 * k), kIdG1, (uint32_t)(k != 0));
+                    tc_mma_f16(t_d1 + (uint32_t)(bb * 128), make_sw128_kmajor_desc(wk_addr + (k >> 2) * 16384) + (uint64_t)(2 * (k & 3)),
+                               make_sw128_kmajor_desc(xa + (k >> 2) * 16384) + (uint64_t)(2 * (k & 3)), kIdG1, (uint32_t)(k != 0));
                 tc_commit(&d1full[bb]);
             }
             __syncwarp();
         };
-        auto g2 = [&](int i) {
-            const int s = i % kAtStages, bb = i & 1;
-            mbar_wait(&pfull[bb], (uint32_t)((i >> 1) & 1));
+        auto g2 = [&](int g, int i) {
+            const int s = g % kAtStages, bb = g & 1;
+            mbar_wait(&pfull[bb], (uint32_t)((g >> 1) & 1));
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
                 for (int kk = 0; kk < kAtTile / 16; ++kk) {
                     const uint64_t pd = make_sw128_kmajor_desc(smem_u32(s_p + bb * kPBytes + (kk >> 2) * 16384)) + (uint64_t)(2 * (kk & 3));
-                    const uint64_t xd = make_sw128_kmajor_desc(smem_u32(s_x + s * kXBytes + kk * 2048));      // 16 px rows further
+                    // x tile as an MN-major operand: 8-pixel groups 1 KB apart (SBO), 64-channel atoms 16 KB apart (LBO)
+                    const uint64_t xd = make_sw128_desc_lbo(smem_u32(s_x + s * kXBytes + kk * 2048), 16384u, 1024u);
                     tc_mma_f16(t_s, pd, xd, kIdG2, (uint32_t)((i | kk) != 0));
                 }
                 tc_commit(&pempty[bb]);
@@ -142,139 +174,163 @@ attn_xk_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             __syncwarp();
         };
         mbar_wait(wfull, 0u);
-        g1(0);
-        for (int i = 0; i < nt; ++i) {
-            if (i + 1 < nt) g1(i + 1);
-            g2(i);
-        }
-        // ctx = S(bf16) . Wv^T into D1[0]
-        mbar_wait(sfull, 0u);
-        tc_fence_after();
-        if (elect_one()) {
-            const uint64_t sd = make_sw128_kmajor_desc(smem_u32(s_p));
+        int g = 0, it_n = 0;                                                // it_n: items this CTA has processed
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int b, chunk, n0, nt, n1;
+            item_range(item, b, chunk, n0, nt, n1);
+            if (nt == 0) continue;
+            if (it_n > 0) mbar_wait(odone, (uint32_t)((it_n - 1) & 1));     // previous item's result has left D1[0]
+            g1(g);
+            for (int i = 0; i < nt; ++i) {
+                if (i + 1 < nt) g1(g + i + 1);
+                g2(g + i, i);
+            }
+            g += nt;
+            mbar_wait(sfull, (uint32_t)(it_n & 1));
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t sa = smem_u32(s_p);
 #pragma unroll
-            for (int k = 0; k < C / 16; ++k)
-                tc_mma_f16(t_d1, sd + (uint64_t)(2 * k), wv_desc + (uint64_t)(2 * k), kIdG1, (uint32_t)(k != 0));
-            tc_commit(ofull);
+                for (int k = 0; k < C / 16; ++k)
+                    tc_mma_f16(t_d1, make_sw128_kmajor_desc(sa + (k >> 2) * 16384) + (uint64_t)(2 * (k & 3)),
+                               make_sw128_kmajor_desc(wv_addr + (k >> 2) * 16384) + (uint64_t)(2 * (k & 3)), kIdG1, (uint32_t)(k != 0));
+                tc_commit(ofull);
+            }
+            __syncwarp();
+            ++it_n;
         }
-        __syncwarp();
     } else if (warp >= 4) {
         // ---- softmax: thread = k-channel d = 32 (warp-4) + lane = TMEM lane
         const int wq = warp - 4, d = wq * 32 + lane;
         const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-        float m_ref = -INFINITY, l = 0.f;
-        for (int i = 0; i < nt; ++i) {
-            const int bb = i & 1;
-            const int nvalid = n1 - (n0 + i * kAtTile);                       // pixels of this tile inside the chunk
-            mbar_wait(&d1full[bb], (uint32_t)((i >> 1) & 1));
-            tc_fence_after();
-            const uint32_t td = t_d1 + lane_base + (uint32_t)(bb * 128);
-            // one TMEM read of my whole row (128 k values stay in registers), then the buffer goes back to the MMA warp
-            uint32_t r[kAtTile];
-#pragma unroll
-            for (int c0 = 0; c0 < kAtTile; c0 += 32) tmem_ld32(td + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[32]>(&r[c0]));
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&d1empty[bb]);
-            if (nvalid < kAtTile) {                                          // ragged last tile: pixels past the chunk never count
-#pragma unroll
-                for (int q = 0; q < kAtTile; ++q) if (q >= nvalid) r[q] = 0xff800000u;   // -inf
+        int g = 0, it_n = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            int b, chunk, n0, nt, n1;
+            item_range(item, b, chunk, n0, nt, n1);
+            if (nt == 0) {                                                     // empty chunk: neutral element of the merge
+                float* part = partials + (((size_t)b * 4 + wq) * chunks + chunk) * 1088;
+                part[lane] = -INFINITY;
+                part[32 + lane] = 0.f;
+                for (int e = 0; e < 32; ++e) part[64 + lane * 32 + e] = 0.f;
+                continue;
             }
-            float mx = -INFINITY;
-#pragma unroll
-            for (int q = 0; q < kAtTile; q += 4)
-                mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(r[q]), __uint_as_float(r[q + 1])),
-                                     fmaxf(__uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]))));
-            // lazy reference maximum: raise it (and rescale S, l) only when the tile exceeds it by more than tau
-            const bool raise = mx > m_ref + tau;                              // first tile: m_ref = -inf -> true
-            float factor = 1.0f;
-            if (raise) { factor = (i == 0) ? 0.f : __expf(m_ref - mx); m_ref = mx; }
-            if (i > 0 && __any_sync(0xffffffffu, raise)) {
-                // GEMM2(i-1) must have retired before S is touched
-                mbar_wait(&pempty[(i - 1) & 1], (uint32_t)(((i - 1) >> 1) & 1));
+            float m_ref = -INFINITY, l = 0.f;
+            for (int i = 0; i < nt; ++i, ++g) {
+                const int bb = g & 1;
+                const int nvalid = n1 - (n0 + i * kAtTile);                   // pixels of this tile inside the chunk
+                mbar_wait(&d1full[bb], (uint32_t)((g >> 1) & 1));
                 tc_fence_after();
+                const uint32_t td = t_d1 + lane_base + (uint32_t)(bb * 128);
+                // one TMEM read of my whole row (128 k values stay in registers), then the buffer goes back to the MMA warp
+                uint32_t r[kAtTile];
+#pragma unroll
+                for (int c0 = 0; c0 < kAtTile; c0 += 32) tmem_ld32(td + (uint32_t)c0, *reinterpret_cast<uint32_t(*)[32]>(&r[c0]));
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d1empty[bb]);
+                if (nvalid < kAtTile) {                                      // ragged last tile: pixels past the chunk never count
+#pragma unroll
+                    for (int q = 0; q < kAtTile; ++q) if (q >= nvalid) r[q] = 0xff800000u;   // -inf
+                }
+                float mx = -INFINITY;
+#pragma unroll
+                for (int q = 0; q < kAtTile; q += 4)
+                    mx = fmaxf(mx, fmaxf(fmaxf(__uint_as_float(r[q]), __uint_as_float(r[q + 1])),
+                                         fmaxf(__uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]))));
+                // lazy reference maximum: raise it (and rescale S, l) only when the tile exceeds it by more than tau
+                const bool raise = mx > m_ref + tau;                          // first tile: m_ref = -inf -> true
+                float factor = 1.0f;
+                if (raise) { factor = (i == 0) ? 0.f : __expf(m_ref - mx); m_ref = mx; }
+                if (i > 0 && __any_sync(0xffffffffu, raise)) {
+                    // GEMM2 of the previous tile must have retired before S is touched
+                    mbar_wait(&pempty[(g - 1) & 1], (uint32_t)(((g - 1) >> 1) & 1));
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int c0 = 0; c0 < C; c0 += 32) {
+                        uint32_t sr[32];
+                        tmem_ld32(t_s + lane_base + (uint32_t)c0, sr);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) sr[q] = __float_as_uint(__uint_as_float(sr[q]) * factor);
+                        tmem_st32(t_s + lane_base + (uint32_t)c0, sr);
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                }
+                l *= factor;
+                // P buffer bb free again? (GEMM2 two tiles back retired)
+                mbar_wait(&pempty[bb], (uint32_t)((g >> 1) & 1) ^ 1u);
+                // p = 2^(k*log2e - m_ref*log2e) -> bf16 -> SMEM (K-major, 128-byte swizzle); row sum of the ROUNDED values.
+                // exp(-inf) = 0 takes care of the masked pixels.
+                uint8_t* prow = s_p + bb * kPBytes + d * 128;
+                const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f);
+                const float2 nm = make_float2(-m_ref * 1.4426950408889634f, -m_ref * 1.4426950408889634f);
+                float2 ls2 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int c16 = 0; c16 < kAtTile / 8; ++c16) {                 // 16-byte chunks of 8 pixels
+                    uint32_t w[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 tq = ffma2(make_float2(__uint_as_float(r[c16 * 8 + 2 * q]), __uint_as_float(r[c16 * 8 + 2 * q + 1])), l2e, nm);
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(ex2_approx(tq.x), ex2_approx(tq.y));
+                        w[q] = *reinterpret_cast<uint32_t*>(&h2);
+                        ls2 = fadd2(ls2, make_float2(__uint_as_float(w[q] << 16), __uint_as_float(w[q] & 0xffff0000u)));
+                    }
+                    uint8_t* dst = prow + (c16 >> 3) * 16384 + (((c16 & 7) ^ (d & 7)) << 4);
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                l += ls2.x + ls2.y;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&pfull[bb]);
+            }
+            // ---- end of chunk: S -> bf16 A operand (C/64 atoms in P[0]), one MMA with Wv, then my head's 32 columns
+            mbar_wait(&pempty[(g - 1) & 1], (uint32_t)(((g - 1) >> 1) & 1));
+            tc_fence_after();
+            {
+                uint8_t* srow = s_p + d * 128;
 #pragma unroll 1
                 for (int c0 = 0; c0 < C; c0 += 32) {
                     uint32_t sr[32];
                     tmem_ld32(t_s + lane_base + (uint32_t)c0, sr);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) sr[q] = __float_as_uint(__uint_as_float(sr[q]) * factor);
-                    tmem_st32(t_s + lane_base + (uint32_t)c0, sr);
-                }
-                tmem_st_wait();
-                tc_fence_before();
-            }
-            l *= factor;
-            // P buffer bb free again? (GEMM2(i-2) retired)
-            mbar_wait(&pempty[bb], (uint32_t)((i >> 1) & 1) ^ 1u);
-            // p = 2^(k*log2e - m_ref*log2e) -> bf16 -> SMEM (K-major, 128-byte swizzle); row sum of the ROUNDED values.
-            // exp(-inf) = 0 takes care of the masked pixels.
-            uint8_t* prow = s_p + bb * kPBytes + d * 128;
-            const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f);
-            const float2 nm = make_float2(-m_ref * 1.4426950408889634f, -m_ref * 1.4426950408889634f);
-            float2 ls2 = make_float2(0.f, 0.f);
+                    for (int c16 = 0; c16 < 4; ++c16) {
+                        uint32_t w[4];
 #pragma unroll
-            for (int c16 = 0; c16 < kAtTile / 8; ++c16) {                     // 16-byte chunks of 8 pixels
-                uint32_t w[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float2 tq = ffma2(make_float2(__uint_as_float(r[c16 * 8 + 2 * q]), __uint_as_float(r[c16 * 8 + 2 * q + 1])), l2e, nm);
-                    __nv_bfloat162 h2 = __floats2bfloat162_rn(ex2_approx(tq.x), ex2_approx(tq.y));
-                    w[q] = *reinterpret_cast<uint32_t*>(&h2);
-                    ls2 = fadd2(ls2, make_float2(__uint_as_float(w[q] << 16), __uint_as_float(w[q] & 0xffff0000u)));
-                }
-                uint8_t* dst = prow + (c16 >> 3) * 16384 + (((c16 & 7) ^ (d & 7)) << 4);
-                *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-            const float lsum = ls2.x + ls2.y;
-            l += lsum;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&pfull[bb]);
-        }
-        // ---- end of chunk: S -> bf16 A operand, one MMA with Wv, then my head's 32 columns
-        mbar_wait(&pempty[(nt - 1) & 1], (uint32_t)(((nt - 1) >> 1) & 1));
-        tc_fence_after();
-        {
-            uint8_t* srow = s_p + d * 128;
-#pragma unroll 1
-            for (int c0 = 0; c0 < C; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(t_s + lane_base + (uint32_t)c0, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int c16 = 0; c16 < 4; ++c16) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r[c16 * 8 + 2 * q]), __uint_as_float(r[c16 * 8 + 2 * q + 1]));
-                        w[q] = *reinterpret_cast<uint32_t*>(&h2);
+                        for (int q = 0; q < 4; ++q) {
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(sr[c16 * 8 + 2 * q]), __uint_as_float(sr[c16 * 8 + 2 * q + 1]));
+                            w[q] = *reinterpret_cast<uint32_t*>(&h2);
+                        }
+                        const int ch = (c0 >> 3) + c16;                       // 16-byte chunk along the C channels
+                        *reinterpret_cast<uint4*>(srow + (ch >> 3) * 16384 + (((ch & 7) ^ (d & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
-                    const int ch = (c0 >> 3) + c16;                           // 16-byte chunk along the 64 channels (0..7)
-                    *reinterpret_cast<uint4*>(srow + ((ch ^ (d & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
+                tc_fence_before();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sfull);
             }
-            tc_fence_before();
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(sfull);
-        }
-        mbar_wait(ofull, 0u);
-        tc_fence_after();
-        {
-            uint32_t r[32];
-            tmem_ld32(t_d1 + lane_base + (uint32_t)(wq * 32), r);             // columns of my head
-            tmem_ld_wait();
-            float* part = partials + (((size_t)b * 4 + wq) * chunks + chunk) * 1088;
-            part[lane] = m_ref;
-            part[32 + lane] = l;
+            mbar_wait(ofull, (uint32_t)(it_n & 1));
+            tc_fence_after();
+            {
+                uint32_t o[32];
+                tmem_ld32(t_d1 + lane_base + (uint32_t)(wq * 32), o);         // columns of my head
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(odone);
+                float* part = partials + (((size_t)b * 4 + wq) * chunks + chunk) * 1088;
+                part[lane] = m_ref;
+                part[32 + lane] = l;
 #pragma unroll
-            for (int e4 = 0; e4 < 8; ++e4)
-                *reinterpret_cast<float4*>(&part[64 + lane * 32 + e4 * 4]) =
-                    make_float4(__uint_as_float(r[4 * e4]), __uint_as_float(r[4 * e4 + 1]), __uint_as_float(r[4 * e4 + 2]),
-                                __uint_as_float(r[4 * e4 + 3]));
+                for (int e4 = 0; e4 < 8; ++e4)
+                    *reinterpret_cast<float4*>(&part[64 + lane * 32 + e4 * 4]) =
+                        make_float4(__uint_as_float(o[4 * e4]), __uint_as_float(o[4 * e4 + 1]), __uint_as_float(o[4 * e4 + 2]),
+                                    __uint_as_float(o[4 * e4 + 3]));
+            }
+            ++it_n;
         }
     }
     tc_fence_before();
@@ -285,34 +341,47 @@ attn_xk_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     }
 }
 
-}  // namespace
-
-// x: [B*n][64] bf16 (NHWC activations flattened), wkv: [256][64] bf16 (k rows, then v rows)
-int attn_xk_tc64(const void* x, const void* wkv_bf16, float* partials, int B, int n, int chunks, int chunk_len, cudaStream_t s) {
-    CUtensorMap mapX, mapW;
-    {
-        const uint64_t dims[2] = {64, (uint64_t)B * (uint64_t)n};
-        const uint64_t str[1] = {128};
-        const uint32_t box[2] = {64, (uint32_t)kAtTile};
-        if (!encode_map(&mapX, x, 2, dims, str, box)) return 1;
-    }
-    {
-        const uint64_t dims[2] = {64, 256};
-        const uint64_t str[1] = {128};
-        const uint32_t box[2] = {64, 128};
-        if (!encode_map(&mapW, wkv_bf16, 2, dims, str, box)) return 1;
-    }
-    const size_t smem = 16384 * 2 + (size_t)kAtStages * kAtTile * 128 + 2 * 128 * kAtTile * 2 + 256 + 1024;
+template <int C>
+int launch_attn_tc(const CUtensorMap& mapX, const CUtensorMap& mapW, float* partials, int B, int n, int chunks, int chunk_len,
+                   cudaStream_t s) {
+    const size_t smem = (size_t)2 * 128 * 128 * (C / 64) + (size_t)kAtStages * kAtTile * 128 * (C / 64) + 2 * 128 * kAtTile * 2 + 256 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        GTTS_CHECK_CUDA(cudaFuncSetAttribute(attn_xk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GTTS_CHECK_CUDA(cudaFuncSetAttribute(attn_xk_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     float tau = kLazyTau;
     if (const char* t = getenv("GTTS_ATTN_TAU")) tau = (float)atof(t);        // 0: rescale on every increase (exercises the correction path)
-    GTTS_CHECK_CUDA(launch_pdl(attn_xk_tc_kernel, dim3(chunks, B), dim3(256), smem, s, 1, mapX, mapW, partials, n, chunks, chunk_len, tau));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int items = B * chunks;
+    GTTS_CHECK_CUDA(launch_pdl(attn_xk_tc_kernel<C>, dim3(items < sms ? items : sms), dim3(256), smem, s, 1, mapX, mapW, partials, B, n,
+                               chunks, chunk_len, tau));
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+}  // namespace
+
+// x: [B*n][C] bf16 (NHWC activations flattened), wkv: [256][C] bf16 (k rows, then v rows); C = 64 or 128
+int attn_xk_tc(const void* x, const void* wkv_bf16, float* partials, int B, int n, int C, int chunks, int chunk_len, cudaStream_t s) {
+    GTTS_REQUIRE(C == 64 || C == 128, "attn_xk_tc: C must be 64 or 128");
+    CUtensorMap mapX, mapW;
+    {
+        const uint64_t dims[2] = {(uint64_t)C, (uint64_t)B * (uint64_t)n};
+        const uint64_t str[1] = {(uint64_t)C * 2};
+        const uint32_t box[2] = {64, (uint32_t)kAtTile};
+        if (!encode_map(&mapX, x, 2, dims, str, box)) return 1;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)C, 256};
+        const uint64_t str[1] = {(uint64_t)C * 2};
+        const uint32_t box[2] = {64, 128};
+        if (!encode_map(&mapW, wkv_bf16, 2, dims, str, box)) return 1;
+    }
+    return C == 64 ? launch_attn_tc<64>(mapX, mapW, partials, B, n, chunks, chunk_len, s)
+                   : launch_attn_tc<128>(mapX, mapW, partials, B, n, chunks, chunk_len, s);
 }
 
 }  // namespace gtts

@@ -202,8 +202,7 @@ int gtts_test_attn_xk(const void* x_bf16, const void* wkv_bf16, float* partials,
                       int use_tc, void* stream) {
     GTTS_REQUIRE(x_bf16 && wkv_bf16 && partials, "null argument");
     if (use_tc) {
-        GTTS_REQUIRE(C == 64, "gtts_test_attn_xk: the tcgen05 kernel is built for C = 64");
-        return attn_xk_tc64(x_bf16, wkv_bf16, partials, B, n, chunks, chunk_len, (cudaStream_t)stream);
+        return attn_xk_tc(x_bf16, wkv_bf16, partials, B, n, C, chunks, chunk_len, (cudaStream_t)stream);
     }
     setenv("GTTS_ATTN_TC", "0", 1);
     int rc = attn_xk(x_bf16, wkv_bf16, partials, B, n, C, chunks, chunk_len, (cudaStream_t)stream);

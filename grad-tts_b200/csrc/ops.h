@@ -152,8 +152,8 @@ void attn_ctx_plan(int n, int* chunks, int* chunk_len);
 // fused k-projection + context for bf16 activations with C = 64 / 128 (attention.cu): reads x only
 int attn_xk(const void* x, const void* wkv_bf16 /*[256][C]*/, float* partials, int B, int n, int C, int chunks,
             int chunk_len, cudaStream_t s);                  // writes attn_merge-format partials
-// tcgen05 version for C = 64 (attention_tc.cu)
-int attn_xk_tc64(const void* x, const void* wkv_bf16, float* partials, int B, int n, int chunks, int chunk_len, cudaStream_t s);
+// tcgen05 version (attention_tc.cu), C = 64 / 128
+int attn_xk_tc(const void* x, const void* wkv_bf16, float* partials, int B, int n, int C, int chunks, int chunk_len, cudaStream_t s);
 // per-sample folded weights M_b = g * Wout * blockdiag(ctxn^T) * Wq  -> [B*C][C] in weight type
 int attn_fold(ActKind wkind, const float* ctxn, const float* wout /*[C][128]*/, const float* wq /*[128][C]*/,
               float g, void* mb_out, int B, int C, cudaStream_t s);

@@ -82,8 +82,10 @@ def _merge_partials(part):
 
 
 @pytest.mark.parametrize("use_tc", [0, 1])
-@pytest.mark.parametrize("B,n,chunks,chunk_len,scale", [(2, 1000, 3, 384, 1.0), (1, 4096, 4, 1024, 1.0), (3, 700, 1, 768, 6.0)])
-def test_attn_xk_matches_reference(use_tc, B, n, chunks, chunk_len, scale, monkeypatch):
+@pytest.mark.parametrize("C", [64, 128])
+@pytest.mark.parametrize("B,n,chunks,chunk_len,scale", [(2, 1000, 3, 384, 1.0), (1, 4096, 4, 1024, 1.0), (3, 700, 1, 768, 6.0),
+                                                        (5, 3000, 40, 128, 1.0)])
+def test_attn_xk_matches_reference(use_tc, C, B, n, chunks, chunk_len, scale, monkeypatch):
     """Fused k-projection + online softmax + context (tcgen05 and mma.sync kernels) against the plain formula.  scale = 6
     makes the running maximum jump between tiles (exercises the lazy rescale of the TMEM accumulator); GTTS_ATTN_TAU=0 forces a
     rescale on every increase."""
@@ -93,7 +95,6 @@ def test_attn_xk_matches_reference(use_tc, B, n, chunks, chunk_len, scale, monke
     if scale != 1.0:
         monkeypatch.setenv("GTTS_ATTN_TAU", "0")
     g = torch.Generator().manual_seed(n + B)
-    C = 64
     x = (torch.randn(B, n, C, generator=g) * scale).to(torch.bfloat16)
     ramp = torch.linspace(0.2, 1.5, n).view(1, n, 1)        # later pixels are larger: the maximum keeps growing
     x = (x.float() * ramp).to(torch.bfloat16)
