@@ -197,6 +197,18 @@ int gtts_decoder_profile_step(gtts_decoder* h, int B, int T, int flags, int reps
 
 long gtts_decoder_launches_last_call(const gtts_decoder* h) { return h ? decoder_launches_last_call(h->impl) : 0; }
 
+// ------------------------------------------------------------------------------------------------ alignment stage
+int gtts_align_log_prior(const float* mu_x, const float* y, float* log_prior, int B, int n_feats, int t_x, int t_y, void* stream) {
+    GTTS_REQUIRE(mu_x && y && log_prior, "null argument");
+    return align_log_prior(mu_x, y, log_prior, B, n_feats, t_x, t_y, (cudaStream_t)stream);
+}
+
+int gtts_align_outputs(const float* attn, const float* mu_x, const float* x_mask, float* logw, float* mu_y, int B, int n_feats,
+                       int t_x, int t_y, void* stream) {
+    GTTS_REQUIRE(attn && mu_x && (logw == nullptr || x_mask != nullptr), "null argument");
+    return align_outputs(attn, mu_x, x_mask, logw, mu_y, B, n_feats, t_x, t_y, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------------------------ test hooks
 int gtts_test_attn_xk(const void* x_bf16, const void* wkv_bf16, float* partials, int B, int n, int C, int chunks, int chunk_len,
                       int use_tc, void* stream) {

@@ -158,6 +158,11 @@ int attn_xk_tc(const void* x, const void* wkv_bf16, float* partials, int B, int 
 int attn_fold(ActKind wkind, const float* ctxn, const float* wout /*[C][128]*/, const float* wq /*[128][C]*/,
               float g, void* mb_out, int B, int C, cudaStream_t s);
 
+// alignment stage around MAS (align.cu): log-prior (tts.py:143-149), durations and aligned means (tts.py:155,184-185)
+int align_log_prior(const float* mu_x, const float* y, float* log_prior, int B, int C, int tx, int ty, cudaStream_t s);
+int align_outputs(const float* attn, const float* mu_x, const float* x_mask, float* logw, float* mu_y, int B, int C, int tx,
+                  int ty, cudaStream_t s);
+
 // weight packing helpers (device side, fp32 source in PyTorch layout)
 int pack_conv_weight(ActKind wkind, const float* w_oihw, void* packed, int Cout, int Cin, int kh, int kw,
                      cudaStream_t s);                       // -> [(ky*kw+kx)*Cout + co][ci]

@@ -11,7 +11,7 @@ import math
 
 import torch
 
-from . import monotonic_align
+from . import align, monotonic_align
 from .base import BaseModule
 from .diffusion import Diffusion
 from .utils import sequence_mask, generate_path, duration_loss, fix_len_compatibility  # noqa: F401
@@ -90,17 +90,17 @@ class GradTTS(BaseModule):
 
     @torch.no_grad()
     def align(self, mu_x, x_mask, y, y_mask):
-        """MAS between encoder outputs and a mel (reference model/tts.py:139-152, 224-231): builds the
-        log-prior with two device matmuls and runs `monotonic_align.maximum_path` on device."""
+        """MAS between encoder outputs and a mel (reference model/tts.py:139-152, 224-231): the
+        log-prior kernel (csrc/align.cu) followed by `monotonic_align.maximum_path`, both on the device."""
         attn_mask = x_mask.unsqueeze(-1) * y_mask.unsqueeze(2)
-        const = -0.5 * math.log(2 * math.pi) * self.n_feats
-        factor = -0.5 * torch.ones(mu_x.shape, dtype=mu_x.dtype, device=mu_x.device)
-        y_square = torch.matmul(factor.transpose(1, 2), y ** 2)
-        y_mu_double = torch.matmul(2.0 * (factor * mu_x).transpose(1, 2), y)
-        mu_square = torch.sum(factor * (mu_x ** 2), 1).unsqueeze(-1)
-        log_prior = y_square - y_mu_double + mu_square + const
+        log_prior = align.log_prior(mu_x, y)                                             # :143-149, one kernel
         attn = monotonic_align.maximum_path(log_prior, attn_mask.squeeze(1))
         return attn.detach()
+
+    @torch.no_grad()
+    def align_outputs(self, attn, mu_x, x_mask):
+        """(logw_, mu_y) derived from a MAS path (reference model/tts.py:155, 184-185)."""
+        return align.logw_from_path(attn, x_mask), align.mu_y_from_path(attn, mu_x)
 
     def get_score_model(self, x, x_lengths, y, y_lengths, spk=None):
         """Score model for a speech/text pair (reference model/tts.py:197-254): encoder + device MAS +
@@ -112,7 +112,7 @@ class GradTTS(BaseModule):
         y_max_length = y.shape[-1]
         y_mask = sequence_mask(y_lengths, y_max_length).unsqueeze(1).to(x_mask)
         attn = self.align(mu_x, x_mask, y, y_mask)
-        mu_y = torch.matmul(attn.squeeze(1).transpose(1, 2), mu_x.transpose(1, 2)).transpose(1, 2)
+        mu_y = align.mu_y_from_path(attn, mu_x)                                          # :184-185 / :233-234
         estimator = self.decoder.estimator
 
         class ScoreModel(torch.nn.Module):

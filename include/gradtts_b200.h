@@ -9,6 +9,7 @@
  * Reference interfaces replaced (paths relative to /root/reference):
  *   gtts_mas_maximum_path          model/monotonic_align/__init__.py:8-23  maximum_path(value, mask)
  *   gtts_mas_maximum_path_c        model/monotonic_align/core.pyx:40-45    maximum_path_c(paths, values, t_xs, t_ys, max_neg_val)
+ *   gtts_align_log_prior / _outputs model/tts.py:143-149,155,184-185       log-prior ahead of MAS, durations and mu_y after it
  *   gtts_decoder_reverse_diffusion model/diffusion.py:254-272  Diffusion.forward / reverse_diffusion(z, mask, mu, n_timesteps, stoc, spk)
  *   gtts_decoder_estimator         model/diffusion.py:174-216  GradLogPEstimator2d.forward(x, mask, mu, t, spk)
  *   gtts_decoder_create/set_param  model/diffusion.py:128-172,227-242  module construction + load_state_dict
@@ -52,6 +53,16 @@ int gtts_mas_maximum_path_c(int32_t* paths, const float* values, const int32_t* 
 /* Host-buffer convenience (pinned or pageable): H2D, kernel, D2H, stream sync. Returns status via *status_host. */
 int gtts_mas_maximum_path_host(const float* value_host, const float* mask_host, float* path_host, int B, int t_x,
                                int t_y, int32_t* status_host, int device);
+
+/* ---- Alignment stage around MAS (training / scoring path, model/tts.py:139-185) ---------------------
+ * gtts_align_log_prior  model/tts.py:143-149  log_prior[b,i,j] = log N(y[b,:,j]; mu_x[b,:,i], I): the value MAS maximises.
+ *   mu_x: [B][n_feats][t_x], y: [B][n_feats][t_y], log_prior: [B][t_x][t_y], fp32 device pointers.
+ * gtts_align_outputs    model/tts.py:155      logw_[b,i] = log(1e-8 + sum_j attn[b,i,j]) * x_mask[b,i]   (logw may be NULL)
+ *                       model/tts.py:184-185  mu_y[b,:,j] = sum_i attn[b,i,j] mu_x[b,:,i]                 (mu_y may be NULL)
+ *   attn: [B][t_x][t_y] fp32 path from gtts_mas_maximum_path, x_mask: [B][t_x]. */
+int gtts_align_log_prior(const float* mu_x, const float* y, float* log_prior, int B, int n_feats, int t_x, int t_y, void* stream);
+int gtts_align_outputs(const float* attn, const float* mu_x, const float* x_mask, float* logw, float* mu_y, int B, int n_feats,
+                       int t_x, int t_y, void* stream);
 
 /* ---- Decoder --------------------------------------------------------------------------------------
  * n_spks follows the reference constructor: 1 (or <2) = two input channels; >1 = speaker channel, spk

@@ -84,6 +84,49 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
         print(name, "y absmax", float(y.abs().max()))
 
+    # Alignment stage (tts.py:139-185): vectors captured from the reference's own GradTTS.compute_loss -- mu_x from the encoder,
+    # the log_prior / mask handed to maximum_path, the path it returned, logw_ (argument of duration_loss) and mu_y (argument of
+    # decoder.compute_loss).  Random-init reference model, seeded inputs.
+    import model.tts as ref_tts
+    for name, B, n_vocab, tx, ty, seed in [("align_b3_17x61", 3, 40, 17, 61, 31), ("align_b2_50x200", 2, 60, 50, 200, 32)]:
+        torch.manual_seed(seed)
+        net = ref_tts.GradTTS(n_vocab, 1, 64, 192, 768, 256, 2, 2, 3, 0.0, 4, 80, 64, 0.05, 20.0, 1000).eval()
+        g = torch.Generator().manual_seed(seed + 1)
+        x_len = torch.randint(max(1, tx // 2), tx + 1, (B,), generator=g); x_len[0] = tx
+        y_len = torch.randint(max(tx, ty // 2), ty + 1, (B,), generator=g); y_len[0] = ty
+        x = torch.randint(0, n_vocab, (B, tx), generator=g)
+        y = torch.randn(B, 80, ty, generator=g)
+        cap = {}
+        orig_mp, orig_dl, orig_cl = ref_tts.monotonic_align.maximum_path, ref_tts.duration_loss, net.decoder.compute_loss
+
+        def mp(value, mask):
+            cap["log_prior"], cap["mask"] = value.clone(), mask.clone()
+            cap["attn"] = orig_mp(value, mask)
+            return cap["attn"]
+
+        def dl(logw, logw_, lengths):
+            cap["logw_"] = logw_.clone()
+            return orig_dl(logw, logw_, lengths)
+
+        def cl(y_, y_mask, mu_y, spk=None):
+            cap["mu_y"] = mu_y.clone()
+            return torch.zeros(()), y_
+
+        hook = net.encoder.register_forward_hook(lambda m, i, o: cap.__setitem__("enc", [t.clone() for t in o]))
+        ref_tts.monotonic_align.maximum_path, ref_tts.duration_loss, net.decoder.compute_loss = mp, dl, cl
+        try:
+            with torch.no_grad():
+                net.compute_loss(x, x_len, y, y_len, spk=None, out_size=None)
+        finally:
+            ref_tts.monotonic_align.maximum_path, ref_tts.duration_loss, net.decoder.compute_loss = orig_mp, orig_dl, orig_cl
+            hook.remove()
+        mu_x, _, x_mask = cap["enc"]
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), mu_x=mu_x.numpy(), x_mask=x_mask.numpy(), y=y.numpy(),
+                            y_len=y_len.numpy(), x_len=x_len.numpy(), log_prior=cap["log_prior"].numpy(),
+                            mask=cap["mask"].numpy(), attn=cap["attn"].numpy().astype(np.int8), logw_=cap["logw_"].numpy(),
+                            mu_y=cap["mu_y"].numpy())
+        print(name, "log_prior absmax", float(cap["log_prior"].abs().max()), "path cells", int(cap["attn"].sum()))
+
     # MAS: value/mask regenerated from the seed in the tests; only the int8 path is stored.
     mas_cases = [("mas_b4_20x50", 4, 20, 50, 11, True), ("mas_b3_33x33", 3, 33, 33, 12, False),
                  ("mas_b5_1x9", 5, 1, 9, 13, True), ("mas_b2_64x257", 2, 64, 257, 14, True),

@@ -86,3 +86,20 @@ def test_mas_oracle_matches_compiled_reference(synth):
         mas_oracle.maximum_path_c(p2, v2, txs, tys)
         assert np.array_equal(p1, p2)
         assert np.array_equal(v1, v2)          # the in-place DP table is bit-identical too
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Alignment stage: oracle restatement vs vectors captured from the reference's GradTTS.compute_loss
+@pytest.mark.parametrize("name", ["align_b3_17x61", "align_b2_50x200"])
+def test_align_oracle_matches_reference_capture(name):
+    import numpy as np
+    import torch
+    from oracle import align_oracle, mas_oracle
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    mu_x, y, x_mask = torch.from_numpy(g["mu_x"]), torch.from_numpy(g["y"]), torch.from_numpy(g["x_mask"])
+    lp = align_oracle.log_prior(mu_x, y, 80)
+    assert torch.equal(lp, torch.from_numpy(g["log_prior"]))                 # same ops on the same CPU: bit-identical
+    attn = mas_oracle.maximum_path(torch.from_numpy(g["log_prior"]), torch.from_numpy(g["mask"]))
+    assert torch.equal(attn.to(torch.int8), torch.from_numpy(g["attn"]))
+    assert torch.equal(align_oracle.logw_from_path(attn, x_mask), torch.from_numpy(g["logw_"]))
+    assert torch.equal(align_oracle.mu_y_from_path(attn, mu_x), torch.from_numpy(g["mu_y"]))

@@ -200,6 +200,46 @@ def stage_mbench():
                   + (f"  ({b.value / iters / nm:6.1f}/mma)" if nm else ""), flush=True)
 
 
+def stage_align():
+    """Alignment stage at BASELINE C2 (64 x 200 x 1000): log-prior + MAS + durations/mu_y on the device vs the CPU restatement."""
+    import time
+    from oracle import align_oracle, mas_oracle
+    al = importlib.import_module("grad-tts_b200.model.align")
+    ma = importlib.import_module("grad-tts_b200.model.monotonic_align")
+    B, tx, ty = 64, 200, 1000
+    gen = torch.Generator().manual_seed(1234)
+    mu_x, y = torch.randn(B, 80, tx, generator=gen), torch.randn(B, 80, ty, generator=gen)
+    xl = torch.randint(100, 201, (B,), generator=gen); yl = torch.randint(600, 1001, (B,), generator=gen); xl[0], yl[0] = tx, ty
+    x_mask = (torch.arange(tx)[None] < xl[:, None]).float().unsqueeze(1)
+    y_mask = (torch.arange(ty)[None] < yl[:, None]).float().unsqueeze(1)
+    mask = (x_mask.unsqueeze(-1) * y_mask.unsqueeze(2)).squeeze(1)
+    d = [t.to(DEV) for t in (mu_x, y, x_mask, mask)]
+
+    def dev_chain():
+        lp = al.log_prior(d[0], d[1])
+        attn = ma.maximum_path(lp, d[3], check=False)
+        return lp, attn, al.logw_from_path(attn, d[2]), al.mu_y_from_path(attn, d[0])
+
+    for _ in range(3):
+        out = dev_chain()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        out = dev_chain()
+    e1.record(); torch.cuda.synchronize()
+    t_dev = e0.elapsed_time(e1) / 10
+    t0 = time.perf_counter()
+    lp = align_oracle.log_prior(mu_x, y, 80)
+    attn = mas_oracle.maximum_path(lp, mask)
+    lw, my = align_oracle.logw_from_path(attn, x_mask), align_oracle.mu_y_from_path(attn, mu_x)
+    t_cpu = (time.perf_counter() - t0) * 1e3
+    same = bool(torch.equal(out[1].cpu(), attn))
+    print(f"align C2 (64x200x1000): device {t_dev:.3f} ms (log_prior + MAS + logw + mu_y), CPU restatement {t_cpu:.1f} ms "
+          f"({torch.get_num_threads()} threads), path identical: {same}, "
+          f"log_prior max err {float((out[0].cpu() - lp).abs().max()):.2e}", flush=True)
+
+
 def stage_profile():
     import ctypes, json
     for (n_spks, B, T) in [(1, 16, 1720), (1, 1, 400)]:
@@ -231,6 +271,6 @@ if __name__ == "__main__":
     print(f"===== stage {st} on {torch.cuda.get_device_name(0)}", flush=True)
     {"mas": stage_mas, "conv_ffma": lambda: (stage_conv(0, 0), stage_conv(0, 1)), "conv_tc": lambda: stage_conv(1, 1),
      "dec_fp32": lambda: stage_dec("fp32"), "dec_bf16_ffma": lambda: stage_dec("bf16", 0),
-     "dec_bf16_tc": lambda: stage_dec("bf16", 1), "perf": stage_perf, "profile": stage_profile, "halo": stage_halo, "convdbg": stage_convdbg, "mbench": stage_mbench}[st]()
+     "dec_bf16_tc": lambda: stage_dec("bf16", 1), "perf": stage_perf, "profile": stage_profile, "halo": stage_halo, "convdbg": stage_convdbg, "mbench": stage_mbench, "align": stage_align}[st]()
     torch.cuda.synchronize()
     print(f"===== stage {st} done", flush=True)
