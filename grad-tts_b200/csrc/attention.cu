@@ -517,56 +517,80 @@ attn_merge_kernel(AttnCtxArgs a) {
     }
 }
 
-// grid (C/16 output-row tiles, C/64 input-column tiles, B), 256 threads.  Each CTA builds 16 rows of
-// P = Wout * blockdiag(ctxn^T) (cheap, recomputed per column tile) and multiplies them with a 128 x 64 slice of
-// Wq staged in shared memory.
+// grid (C/64 output-row tiles, C/64 input-column tiles, B), 256 threads, register-tiled fp32:
+//   phase 1: P[64 co][128 hd] = Wout[co][h*32 + e] . ctxn[h][d][e]      (4 rows x 8 columns per thread, K = 32 per head)
+//   phase 2: M[64 co][64 ci]  = g * P[64][128] . Wq[128][ci0 + 64]      (4 x 4 per thread, K = 128)
+// (The first version used 16-row tiles with one output row per thread: two shared-memory loads per FMA, LSU-bound, and
+// four times as many CTAs re-loading the same operands: 19-45 us per launch for 1-17 MFLOP per sample.)
 template <typename WT>
 __global__ void __launch_bounds__(256)
 attn_fold_kernel(const float* __restrict__ ctxn, const float* __restrict__ wout, const float* __restrict__ wq,
                  float g, WT* __restrict__ mb, int C) {
     pdl_trigger();
     pdl_wait();
-    __shared__ __align__(16) float buf[128 * 64];                    // phase 1: cs + ws ; phase 2: Wq slice
-    __shared__ float P[16 * 129];
-    float* cs = buf;                                                 // [4*32][33]
-    float* ws = buf + 4 * 32 * 33;                                   // [16][128]
-    float* qs = buf;                                                 // [128][64]
-    const int tid = threadIdx.x, b = blockIdx.z, co0 = blockIdx.x * 16, ci0 = blockIdx.y * 64;
-    for (int i = tid; i < 4096; i += 256) {
-        const int h = i >> 10, d = (i >> 5) & 31, e = i & 31;
-        cs[(h * 32 + d) * 33 + e] = ctxn[(size_t)b * 4096 + i];
-    }
-    for (int i = tid; i < 16 * 128; i += 256) ws[i] = wout[(size_t)(co0 + (i >> 7)) * 128 + (i & 127)];
+    extern __shared__ __align__(16) float fold_smem[];
+    float* P = fold_smem;                       // [64][129]
+    float* buf = fold_smem + 64 * 129;          // phase 1: cs [128][33] + ws [64][129] ; phase 2: qs [128][64]
+    float* cs = buf;                            // ctxn[h*32 + d][e], pitch 33
+    float* ws = buf + 128 * 33;                 // Wout rows co0.., [64][129]
+    float* qs = buf;                            // Wq[hd][ci0..ci0+63], pitch 64
+    const int tid = threadIdx.x, b = blockIdx.z, co0 = blockIdx.x * 64, ci0 = blockIdx.y * 64;
+    for (int i = tid; i < 4096; i += 256) cs[(i >> 5) * 33 + (i & 31)] = ctxn[(size_t)b * 4096 + i];
+    for (int i = tid; i < 64 * 128; i += 256) ws[(i >> 7) * 129 + (i & 127)] = wout[(size_t)(co0 + (i >> 7)) * 128 + (i & 127)];
     __syncthreads();
-    {   // P[cl][h*32+d] = sum_e Wout[co][h*32+e] * ctxn[h][d][e]
-        const int cl = tid >> 4, part = tid & 15;
+    {
+        const int r0 = (tid >> 4) * 4, c0 = (tid & 15) * 8, h = c0 >> 5;        // 8 consecutive hd columns lie in one head
+        float acc[4][8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int hd = part + 16 * k, h = hd >> 5;
-            float s = 0.f;
-#pragma unroll 8
-            for (int e = 0; e < 32; ++e) s = fmaf(ws[cl * 128 + h * 32 + e], cs[hd * 33 + e], s);
-            P[cl * 129 + hd] = s;
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+        for (int e = 0; e < 32; ++e) {
+            float wv[4], cv[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) wv[i] = ws[(r0 + i) * 129 + h * 32 + e];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cv[j] = cs[(c0 + j) * 33 + e];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(wv[i], cv[j], acc[i][j]);
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) P[(r0 + i) * 129 + c0 + j] = acc[i][j];
     }
-    __syncthreads();
-    for (int i = tid; i < 128 * 16; i += 256) {                      // 128 rows x 16 float4
+    __syncthreads();                                                             // P complete, cs / ws dead
+    for (int i = tid; i < 128 * 16; i += 256) {                                  // 128 rows x 16 float4
         const int r = i >> 4, c4 = i & 15;
-        *reinterpret_cast<float4*>(&qs[r * 64 + c4 * 4]) =
-            __ldg(reinterpret_cast<const float4*>(wq + (size_t)r * C + ci0 + c4 * 4));
+        *reinterpret_cast<float4*>(&qs[r * 64 + c4 * 4]) = __ldg(reinterpret_cast<const float4*>(wq + (size_t)r * C + ci0 + c4 * 4));
     }
     __syncthreads();
-    {   // M[co][ci] = g * sum_hd P[cl][hd] * Wq[hd][ci]: thread -> (row cl, 4 consecutive columns)
-        const int cl = tid >> 4, cq = (tid & 15) * 4;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    {
+        const int r0 = (tid >> 4) * 4, cq = (tid & 15) * 4;
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 #pragma unroll 8
         for (int hd = 0; hd < 128; ++hd) {
-            const float pv = P[cl * 129 + hd];
             const float4 q4 = *reinterpret_cast<const float4*>(&qs[hd * 64 + cq]);
-            a0 = fmaf(pv, q4.x, a0); a1 = fmaf(pv, q4.y, a1); a2 = fmaf(pv, q4.z, a2); a3 = fmaf(pv, q4.w, a3);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float pv = P[(r0 + i) * 129 + hd];
+                acc[i][0] = fmaf(pv, q4.x, acc[i][0]); acc[i][1] = fmaf(pv, q4.y, acc[i][1]);
+                acc[i][2] = fmaf(pv, q4.z, acc[i][2]); acc[i][3] = fmaf(pv, q4.w, acc[i][3]);
+            }
         }
-        WT* o = mb + ((size_t)b * C + co0 + cl) * C + ci0 + cq;
-        Act<WT>::st(o + 0, g * a0); Act<WT>::st(o + 1, g * a1); Act<WT>::st(o + 2, g * a2); Act<WT>::st(o + 3, g * a3);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            WT* o = mb + ((size_t)b * C + co0 + r0 + i) * C + ci0 + cq;
+            Act<WT>::st(o + 0, g * acc[i][0]); Act<WT>::st(o + 1, g * acc[i][1]);
+            Act<WT>::st(o + 2, g * acc[i][2]); Act<WT>::st(o + 3, g * acc[i][3]);
+        }
     }
 }
 
@@ -638,9 +662,16 @@ int attn_merge(const AttnCtxArgs& a, bool strict, cudaStream_t s) {
 int attn_fold(ActKind wkind, const float* ctxn, const float* wout, const float* wq, float g, void* mb_out, int B,
               int C, cudaStream_t s) {
     GTTS_REQUIRE(C % 64 == 0 && C <= 256, "attn_fold: C must be a multiple of 64 and <= 256");
-    dim3 grid(C / 16, C / 64, B);
-    if (wkind == ACT_F32) GTTS_CHECK_CUDA(launch_pdl(attn_fold_kernel<float>, grid, dim3(256), 0, s, 1, ctxn, wout, wq, g, (float*)mb_out, C));
-    else GTTS_CHECK_CUDA(launch_pdl(attn_fold_kernel<__nv_bfloat16>, grid, dim3(256), 0, s, 1, ctxn, wout, wq, g, (__nv_bfloat16*)mb_out, C));
+    dim3 grid(C / 64, C / 64, B);
+    const size_t smem = (size_t)(64 * 129 + 128 * 33 + 64 * 129) * sizeof(float);          // P + (ctx, Wout rows | Wq slice)
+    static bool set_f = false, set_h = false;
+    if (wkind == ACT_F32) {
+        if (!set_f) { GTTS_CHECK_CUDA(cudaFuncSetAttribute(attn_fold_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set_f = true; }
+        GTTS_CHECK_CUDA(launch_pdl(attn_fold_kernel<float>, grid, dim3(256), smem, s, 1, ctxn, wout, wq, g, (float*)mb_out, C));
+    } else {
+        if (!set_h) { GTTS_CHECK_CUDA(cudaFuncSetAttribute(attn_fold_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set_h = true; }
+        GTTS_CHECK_CUDA(launch_pdl(attn_fold_kernel<__nv_bfloat16>, grid, dim3(256), smem, s, 1, ctxn, wout, wq, g, (__nv_bfloat16*)mb_out, C));
+    }
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
