@@ -306,7 +306,8 @@ int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, i
     }
     int rc = 0;
     if (impl >= 1) {
-        GTTS_REQUIRE(!halo_mode || (conv_tc_halo_eligible(g) && !residual && !mask), "halo test: geometry not eligible");
+        GTTS_REQUIRE(!halo_mode || (conv_tc_halo_eligible(g) && !residual && !mask) || (halo_mode == 2 && conv_tc_convT_halo_eligible(g) && mask && !residual),
+                     "halo test: geometry not eligible");
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -203,6 +203,14 @@ bool conv_tc_halo_eligible(const ConvGeom& g) {
            g.Hg >= 16 && g.Wg >= 8;
 }
 
+// Transposed 4x4 stride-2 conv on the CTA-pair halo kernel (conv_tc_halo2.cu, kConvT): 64 / 128 channels, mask epilogue.
+bool conv_tc_convT_halo_eligible(const ConvGeom& g) {
+    if (getenv("GTTS_CONVT_HALO") && atoi(getenv("GTTS_CONVT_HALO")) == 0) return false;
+    return conv_tc_cta2_enabled() && g.nphase == 4 && g.ntaps == 4 && g.out_step == 2 && g.stride == 1 && g.w_batch_rows == 0 &&
+           g.Cin1 == 0 && g.Cin0 == g.Cout && (g.Cout == 64 || g.Cout == 128) && g.Hg >= 16 && g.Wg >= 18 &&
+           (long)g.B * ((g.Hg + 7) / 8) * ((g.Wg + 15) / 16) >= 2;
+}
+
 size_t conv_tc_halo_partials_slots(const ConvGeom&) { return 256; }    // one partial per (sample, CTA); grid <= #SMs
 
 TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void* src1, const void* weight,
@@ -214,7 +222,9 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
     TcConvPlan* pl = new TcConvPlan();
     memset(pl, 0, sizeof(*pl));
     TcParams& p = pl->p;
-    if (halo_mode && !conv_tc_halo_eligible(g)) halo_mode = 0;
+    const bool convT_halo = halo_mode == 2 && conv_tc_convT_halo_eligible(g) && e.mask && !e.residual && !e.gn_partials &&
+                            num_sms >= 2;
+    if (halo_mode && !convT_halo && (!conv_tc_halo_eligible(g) || e.residual || e.mask)) halo_mode = 0;
     p.halo_mode = halo_mode;
     if (halo_mode) {
         // 128-pixel halo tile: 16 rows x 8 pixels (8-row UMMA groups run along W), or transposed 8 rows x 16 pixels with
@@ -229,11 +239,12 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
     else pick_tile(g.Hg, g.Wg, &p.bh, &p.bw);
     p.tiles_h = (g.Hg + p.bh - 1) / p.bh;
     p.tiles_w = (g.Wg + p.bw - 1) / p.bw;
-    p.nphase = g.nphase; p.B = g.B;
+    p.nphase = convT_halo ? 1 : g.nphase; p.B = g.B;               // ConvT on the halo kernel walks spatial tiles, 4 phases each
+    p.ph_inner = convT_halo ? 4 : 0;
     p.Hg = g.Hg; p.Wg = g.Wg; p.Hout = g.Hout; p.Wout = g.Wout; p.out_step = g.out_step;
     p.ntaps = g.ntaps; p.nchunk0 = g.Cin0 / 64; p.nchunk1 = g.Cin1 / 64; p.Cin0 = g.Cin0;
     p.stride2 = (g.stride == 2); p.w_batch_rows = g.w_batch_rows;
-    p.num_tiles = g.B * g.nphase * p.tiles_h * p.tiles_w;
+    p.num_tiles = g.B * p.nphase * p.tiles_h * p.tiles_w;
     p.a_bytes = p.bh * p.bw * 128;
     memcpy(p.dy, g.dy, sizeof(p.dy)); memcpy(p.dx, g.dx, sizeof(p.dx));
     memcpy(p.wrow, g.wrow, sizeof(p.wrow)); memcpy(p.oy, g.oy, sizeof(p.oy)); memcpy(p.ox, g.ox, sizeof(p.ox));
@@ -243,7 +254,7 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
     const int budget = 227 * 1024 - kMiscBytes - 1024;
     if (halo_mode) {
         // A ring: halo boxes of 18 x 16 pixels x 64 ch (36 KB); B: resident (all 9*nck tiles) if it fits, else a ring
-        const int nck = p.nchunk0 + p.nchunk1, btile = g.Cout * 128, ntiles_b = 9 * nck;
+        const int nck = p.nchunk0 + p.nchunk1, btile = g.Cout * 128, ntiles_b = (convT_halo ? 16 : 9) * nck;
         const int pw = halo_mode == 2 ? 10 : 16;
         const int abytes = (18 * pw * 128 + 1023) / 1024 * 1024;     // stage stride keeps every stage 1024-aligned
         p.a_bytes = abytes;
@@ -253,7 +264,7 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
         if (const char* ms = getenv("GTTS_HALO_STAGES")) max_st = atoi(ms);
         // CTA pairs for every halo conv (measured, chunk 16x1720: 64->64 174 -> 136 us, 128->128 134 -> 108 us,
         // 256->64 192 -> 131 us, 512->128 144 -> 125 us, 256->256 134 -> 123 us).  GTTS_CTA2=0: single-CTA kernels.
-        const bool cta2 = halo_mode == 2 && conv_tc_cta2_enabled() && p.num_tiles >= 2 && num_sms >= 2;
+        const bool cta2 = convT_halo || (halo_mode == 2 && conv_tc_cta2_enabled() && p.num_tiles >= 2 && num_sms >= 2);
         if (cta2) {
             // CTA pair: every CTA holds half of each weight tile (Cout/2 rows)
             const int bhalf = g.Cout * 64;
@@ -263,10 +274,11 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
                 p.stages = (budget - ntiles_b * bhalf) / abytes;
                 if (p.stages > max_st) p.stages = max_st;
             } else {
-                p.b_resident = 0; p.stages = 3;
-                p.b_slots = (budget - 3 * abytes) / bhalf;
+                p.b_resident = 0; p.stages = convT_halo ? 2 * nck : 3;   // ConvT keeps all chunks of a tile resident over its 4 phases
+                p.b_slots = (budget - p.stages * abytes) / bhalf;
                 if (p.b_slots > 16) p.b_slots = 16;
             }
+            if (convT_halo && p.stages < nck) { set_error("conv_tc: ConvT halo variant: not enough A stages"); delete pl; return nullptr; }
             pl->smem = (size_t)p.stages * abytes + (size_t)p.b_slots * bhalf + kMiscBytes + 1024;
         } else {
         if (ntiles_b <= 16 && max_st >= 6 && ntiles_b * btile + 6 * abytes <= budget) { p.stages = 6; p.b_resident = 1; p.b_slots = ntiles_b; }

@@ -33,6 +33,7 @@ struct TcParams {
     int ntaps, nchunk0, nchunk1, Cin0;
     int stride2, w_batch_rows, num_tiles, a_bytes, stages;
     int halo_mode, b_slots, b_resident, halo_prefetch;   // conv_tc_halo.cu only
+    int ph_inner;                                  // > 1: that many output phases per spatial tile, consecutive epilogue iterations (ConvT on the halo kernel)
     int halo_t;                                    // 1: halo tile is 8 rows x 16 pixels with H as the fast box dimension
     int pass_tiles;                                // streamed weights: A tiles that share one pass of the weight ring (1 or 2)
     int mc;                                        // 1: 2-CTA cluster, weight tiles multicast (conv_tc.cu); 2: CTA pair, cta_group::2 MMAs (conv_tc_halo2.cu)
@@ -236,13 +237,20 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
     const float* s_bias = sh.s_bias;
     TileWalk tw;
     const int G = (int)gridDim.x;
-    tw.init(p, (int)blockIdx.x + grp * G, 2 * G);
-    const int n_it = tc_num_iters(p);
+    // Epilogue iteration `it` = accumulator index.  Normally one per tile (this group takes every second tile); with
+    // ph_inner = P > 1 the walk is over spatial tiles and iteration it = P * tile_iteration + phase.
+    const int nph = p.ph_inner > 1 ? p.ph_inner : 1;
+    if (nph > 1) tw.init(p, (int)blockIdx.x, G);
+    else tw.init(p, (int)blockIdx.x + grp * G, 2 * G);
+    const int n_it = tc_num_iters(p) * nph;
+    int walk_it = 0;                                                 // spatial iteration tw currently points at (nph > 1)
     long long c_wait = 0, c_ld = 0, c_sring = 0, c_math = 0, c_store = 0, c_red = 0;
     const long long te0 = GTTS_EPI_CLK();
-    for (int it = grp; it < n_it; it += 2, tw.advance(2 * G)) {
+    for (int it = grp; it < n_it; it += 2) {
+        if (nph > 1) { while (walk_it < it / nph) { tw.advance(G); ++walk_it; } }
+        else if (it != grp) tw.advance(2 * G);
         const int buf = it % kBufs;
-        const int b = tw.b, ph = tw.ph;
+        const int b = tw.b, ph = nph > 1 ? it % nph : tw.ph;
         const int j = tw.th * p.bh + hl, i = tw.tw * p.bw + wl;
         const bool valid = row_in_tile && (j < p.Hg) && (i < p.Wg) && (tw.tile < p.num_tiles);
         const bool all_valid = __all_sync(0xffffffffu, valid);

@@ -34,7 +34,11 @@ constexpr int kFuseWarps = 4;                       // transform warps of the fu
 // activation through HBM) and is bitwise identical to it -- but it is OFF by default (decoder option fuse_gn): measured
 // 435 us vs 134 (conv) + 103 (gn_apply) us for 64->64 at 80x1720x16.  GN+Mish at 5 TB/s already needs a whole SM's issue and
 // MUFU capacity (32 warps); four latency-bound transform warps, which also redo the 41 % halo overlap, cannot supply it.
-template <int N, bool kStats, bool kFuse>
+// kConvT: transposed 4x4 stride-2 conv (Upsample, model/diffusion.py:21-27) as four output phases of 2x2 taps each: all 16
+// (phase, tap) operands are shifted views of ONE halo box of the input tile, so the input crosses L2->SMEM once instead of 16
+// times (the per-tap kernel is fill-bound there: 372 TFLOP/s).  Every phase has its own accumulator and epilogue iteration
+// (TcParams::ph_inner = 4, phases innermost); the epilogue multiplies by the mask (kMask).
+template <int N, bool kStats, bool kFuse, bool kMask = false, bool kConvT = false>
 __global__ void __launch_bounds__(kThreads + (kFuse ? kFuseWarps * 32 : 0), 1)
 conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                      const __grid_constant__ CUtensorMap mapWh, const TcParams p) {
@@ -96,9 +100,16 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
             if (resident) {                                          // all my half tiles, counted on the leader's fullb[0]
                 if (rank == 0) mbar_expect_tx(&sh.fullb[0], (uint32_t)(2 * nslot * kBHalf));
                 const uint32_t fb = mapa_u32(smem_u32(&sh.fullb[0]), 0u);
-                for (int ck = 0; ck < nck; ++ck)
-                    for (int tap = 0; tap < 9; ++tap)
-                        tma_load_2d_2sm(&mapWh, fb, smem_b + (size_t)(ck * 9 + tap) * kBHalf, ck * 64, p.wrow[0][tap] + wrow_off);
+                if (kConvT) {                                        // slot (ph*4 + t)*nck + ck
+                    for (int pt = 0; pt < 16; ++pt)
+                        for (int ck = 0; ck < nck; ++ck)
+                            tma_load_2d_2sm(&mapWh, fb, smem_b + (size_t)(pt * nck + ck) * kBHalf, ck * 64,
+                                            p.wrow[pt >> 2][pt & 3] + wrow_off);
+                } else {
+                    for (int ck = 0; ck < nck; ++ck)
+                        for (int tap = 0; tap < 9; ++tap)
+                            tma_load_2d_2sm(&mapWh, fb, smem_b + (size_t)(ck * 9 + tap) * kBHalf, ck * 64, p.wrow[0][tap] + wrow_off);
+                }
             }
             for (int it = 0; it < n_it; ++it, tw.advance(G)) {
                 if (kStats && (it == n_it - 8 || it == n_it - 1)) prefetch_l2(p.e.gn_counters);
@@ -115,7 +126,7 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
                                         (ck < nck0 ? ck : ck - nck0) * 64, ht ? h0 - 1 : w0 - 1, ht ? w0 - 1 : h0 - 1, b);
                     }
                     if (++sa == nstage) { sa = 0; pha ^= 1u; }
-                    if (!resident) {
+                    if (!resident && !kConvT) {
                         for (int tap = 0; tap < 9; ++tap) {
                             mbar_wait(&sh.emptyb[sb], phb ^ 1u);
                             if (rank == 0) mbar_expect_tx(&sh.fullb[sb], (uint32_t)(2 * kBHalf));
@@ -124,6 +135,16 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
                             if (++sb == nslot) { sb = 0; phb ^= 1u; }
                         }
                     }
+                }
+                if (kConvT && !resident) {                           // streamed weights in the order the MMA warp uses them
+                    for (int pt = 0; pt < 16; ++pt)
+                        for (int ck = 0; ck < nck; ++ck) {
+                            mbar_wait(&sh.emptyb[sb], phb ^ 1u);
+                            if (rank == 0) mbar_expect_tx(&sh.fullb[sb], (uint32_t)(2 * kBHalf));
+                            tma_load_2d_2sm(&mapWh, mapa_u32(smem_u32(&sh.fullb[sb]), 0u), smem_b + (size_t)sb * kBHalf, ck * 64,
+                                            p.wrow[pt >> 2][pt & 3] + wrow_off);
+                            if (++sb == nslot) { sb = 0; phb ^= 1u; }
+                        }
                 }
             }
         }
@@ -140,6 +161,60 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
                 tap_off[t] = (uint64_t)(((p.halo_t ? (t % 3) * pw + (t / 3) : (t / 3) * pw + (t % 3)) * 128) >> 4);
             int sa = 0, sb = 0;
             uint32_t pha = 0, phb = 0;
+            if (kConvT) {
+                // per spatial tile: wait for its nck halo boxes, then phase by phase 4 taps x nck chunks x 4 MMAs into the
+                // phase's own accumulator (epilogue iteration 4*it + ph)
+                uint64_t ct_off[16];
+#pragma unroll
+                for (int pt = 0; pt < 16; ++pt) {
+                    const int dy = p.dy[pt >> 2][pt & 3] + 1, dx = p.dx[pt >> 2][pt & 3] + 1;
+                    ct_off[pt] = (uint64_t)(((p.halo_t ? dx * pw + dy : dy * pw + dx) * 128) >> 4);
+                }
+                for (int it = 0; it < n_it; ++it) {
+                    const int sa0 = sa;
+                    for (int ck = 0; ck < nck; ++ck) {
+                        mbar_wait(&sh.full[sa], pha);
+                        if (++sa == nstage) { sa = 0; pha ^= 1u; }
+                    }
+                    if (resident && it == 0) mbar_wait(&sh.fullb[0], 0u);
+#pragma unroll
+                    for (int ph = 0; ph < 4; ++ph) {
+                        const int e = it * 4 + ph, buf = e % kBufs;
+                        mbar_wait(&sh.tempty[buf], ((uint32_t)(e / kBufs) & 1u) ^ 1u);
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            for (int ck = 0; ck < nck; ++ck) {
+                                int st = sa0 + ck; if (st >= nstage) st -= nstage;
+                                const uint64_t adesc = a_desc0 + (uint64_t)st * a_stage_step + ct_off[ph * 4 + t];
+                                uint64_t bdesc;
+                                if (resident) bdesc = b_desc0 + (uint64_t)((ph * 4 + t) * nck + ck) * b_slot_step;
+                                else { mbar_wait(&sh.fullb[sb], phb); tc_fence_after(); bdesc = b_desc0 + (uint64_t)sb * b_slot_step; }
+                                if (elect_one()) {
+                                    if (!(dbg & 1)) {
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k)
+                                            tc_mma2_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
+                                                        (uint32_t)((t | ck | k) != 0));
+                                    }
+                                    if (!resident) tc_commit2_mc(&sh.emptyb[sb], (uint16_t)3);
+                                    if (t == 3 && ck == nck - 1) {
+                                        tc_commit2_mc(&sh.tfull[buf], (uint16_t)3);
+                                        if (ph == 3)
+                                            for (int c2 = 0; c2 < nck; ++c2) {
+                                                int s2 = sa0 + c2; if (s2 >= nstage) s2 -= nstage;
+                                                tc_commit2_mc(&sh.empty[s2], (uint16_t)3);
+                                            }
+                                    }
+                                }
+                                __syncwarp();
+                                if (!resident) { if (++sb == nslot) { sb = 0; phb ^= 1u; } }
+                            }
+                        }
+                    }
+                }
+            } else
             for (int it = 0; it < n_it; ++it) {
                 const int buf = it % kBufs;
                 mbar_wait(&sh.tempty[buf], ((uint32_t)(it / kBufs) & 1u) ^ 1u);
@@ -196,7 +271,7 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
     } else if (warp == 3) {
         tc_stats_loop<kStats>(p, sh, lane);
     } else if (warp >= 4 && warp < kThreads / 32) {
-        tc_epilogue_loop<N, kStats, false, false>(p, sh, tmem_base, warp, lane);
+        tc_epilogue_loop<N, kStats, false, kMask>(p, sh, tmem_base, warp, lane);
     } else if (kFuse && warp >= kThreads / 32) {
         // ================================================================ input transform (both CTAs)
         // thread -> 16-byte chunk j (8 channels) of rows r0, r0+16, ...; the 128-byte swizzle puts chunk j of row r at
@@ -270,10 +345,10 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
     tc_teardown<N, kStats, true>(p, sh, smem, tmem_base, tid, warp, lane);
 }
 
-template <int N, bool kStats, bool kFuse>
+template <int N, bool kStats, bool kFuse, bool kMask = false, bool kConvT = false>
 int launch_halo2(const TcConvPlan* pl, cudaStream_t stream) {
     static bool attr_set = false;
-    auto k = conv_tc_halo2_kernel<N, kStats, kFuse>;
+    auto k = conv_tc_halo2_kernel<N, kStats, kFuse, kMask, kConvT>;
     if (!attr_set) {
         GTTS_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
@@ -288,6 +363,14 @@ int launch_halo2(const TcConvPlan* pl, cudaStream_t stream) {
 
 int conv_tc_halo2_launch(const TcConvPlan* pl, cudaStream_t stream) {
     const ConvEpilogue& e = pl->p.e;
+    if (pl->p.ph_inner == 4) {                                      // transposed conv: mask epilogue, no statistics
+        GTTS_REQUIRE(e.residual == nullptr && e.mask != nullptr && e.gn_partials == nullptr && !e.in_stats,
+                     "conv_tc_halo2: ConvT variant is built with the mask epilogue only");
+        if (pl->N == 64) return launch_halo2<64, false, false, true, true>(pl, stream);
+        if (pl->N == 128) return launch_halo2<128, false, false, true, true>(pl, stream);
+        set_error("conv_tc_halo2: ConvT variant supports 64 / 128 channels");
+        return 2;
+    }
     GTTS_REQUIRE(e.residual == nullptr && e.mask == nullptr, "conv_tc_halo2: plain or GN-statistics epilogue only");
     const bool st = e.gn_partials != nullptr;
     if (e.in_stats) {                                               // fused input transform (block2 convs: always with stats)

@@ -414,7 +414,7 @@ struct PlanBuilder {
         std::string name = std::string(g.nphase == 4 ? "convT4x4" : (g.ntaps == 9 ? (g.stride == 2 ? "conv3x3s2" : "conv3x3") : "conv1x1")) +
                            "_" + std::to_string((int)cin) + "_" + std::to_string(g.Cout) + "_h" + std::to_string(g.Hin);
         if (use_tc()) {
-            TcConvPlan* tp = conv_tc_plan_create(g, src0, src1, w, wrows, e, d->num_sms, (residual || mask) ? 0 : d->halo_mode);
+            TcConvPlan* tp = conv_tc_plan_create(g, src0, src1, w, wrows, e, d->num_sms, d->halo_mode);   // the plan drops the halo path where the epilogue or geometry rules it out
             if (!tp) { failed = true; return; }
             pl->tc_plans.push_back(tp);
             pl->push(name, 1, flops, bytes, [tp](cudaStream_t s) { return conv_tc_launch(tp, s); });

@@ -70,6 +70,7 @@ void conv_tc_plan_destroy(TcConvPlan* p);
 void conv_tc_plan_set_debug(TcConvPlan* p, unsigned long long* dbg_out);   // per-CTA cycle counters (experiments)
 int conv_tc_plan_grid(const TcConvPlan* p);
 bool conv_tc_cta2_enabled();
+bool conv_tc_convT_halo_eligible(const ConvGeom& g);
 int microbench_issue(int N, int n_mma, int n_commit, int iters, int wait_each, int grid, unsigned long long* out_dev,
                      cudaStream_t stream);                                  // tcgen05 issue-path micro-benchmark
 int conv_tc_launch(const TcConvPlan* p, cudaStream_t stream);

@@ -54,6 +54,29 @@ def test_conv_halo(name, kw, impl, monkeypatch):
     assert serr <= 2e-3, f"{name}: GN stats err {serr}"
 
 
+CONVT_HALO_CASES = [
+    ("convT_64_h40", dict(kind=3, B=2, H=40, W=36, Cin0=64, Cin1=0, Cout=64, mask=True)),            # resident weights
+    ("convT_128_h20", dict(kind=3, B=3, H=20, W=44, Cin0=128, Cin1=0, Cout=128, mask=True)),         # streamed weights, 2 chunks
+    ("convT_64_odd", dict(kind=3, B=1, H=16, W=18, Cin0=64, Cin1=0, Cout=64, mask=True)),            # odd tile count (dummy tile)
+    ("convT_128_many", dict(kind=3, B=7, H=24, W=130, Cin0=128, Cin1=0, Cout=128, mask=True)),       # several tiles per CTA pair
+]
+
+
+@pytest.mark.parametrize("name,kw", CONVT_HALO_CASES)
+def test_convT_halo(name, kw):
+    """Transposed conv on the CTA-pair halo kernel (4 phases x 4 taps as views of one halo box) vs torch CPU and vs the
+    per-tap kernel."""
+    gu = _gu()
+    c = gu.conv_case(seed=hash(name) % 1000, **kw)
+    out, _ = gu.run_conv(c, 3, 1)
+    ref, _ = gu.conv_reference(c, round_bf16=True)
+    assert not torch.isnan(out).any(), "output has unwritten (NaN) entries"
+    err = float((out - ref).abs().max())
+    assert err <= 4e-2, f"{name}: max-abs err {err}"
+    tap, _ = gu.run_conv(c, 1, 1)
+    assert float((out - tap).abs().max()) <= 4e-2
+
+
 def test_tc_matches_ffma_bitwise_inputs():
     """Same bf16 operands through both implementations: only accumulation order differs."""
     gu = _gu()
