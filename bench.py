@@ -21,6 +21,12 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# The CPU legs (--impl reference, cpu_baseline) must see every host core: torchrun exports OMP_NUM_THREADS=1 for its
+# workers, which caps the OpenMP/MKL pools before torch is imported.
+if "--impl" in sys.argv and "reference" in sys.argv or os.environ.get("OMP_NUM_THREADS") == "1":
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 WORKLOADS = {
     # name: (n_spks, global batch, T, euler steps)
     "C5": (1, 128, 1720, 100),     # long-form throughput sweep (BASELINE.json configs[4]) -- the headline
