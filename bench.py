@@ -231,6 +231,8 @@ def main():
     ms_per_step = ms_total / args.steps
     value = B * T / (ms_per_step * 1e-3)
     finite = bool(torch.isfinite(y).all())
+    if not finite:
+        raise SystemExit("bench: the sampler output contains non-finite values -- the measurement is invalid")
 
     # ---- e2e: host (pinned) buffers through the C-ABI host entry point, copies inside the timed region
     zp, mp, mup = zl.pin_memory(), maskl.pin_memory(), mul.pin_memory()

@@ -11,6 +11,9 @@
 // M_b; the product M_b x runs as a 1x1 conv with per-sample weights on the tensor cores (conv_tc.cu).
 #include "common.cuh"
 #include "ops.h"
+#include <vector>
+#include <cmath>
+#include <cstring>
 
 namespace gtts {
 
@@ -630,7 +633,26 @@ int attn_xk(const void* x, const void* wkv_bf16, float* partials, int B, int n, 
     GTTS_REQUIRE(chunks >= 1 && chunks <= 64 && chunk_len % kXkSub == 0, "attn_xk: bad chunk plan");
     {
         const char* tc = getenv("GTTS_ATTN_TC");
-        if (!tc || atoi(tc) != 0) return attn_xk_tc(x, wkv_bf16, partials, B, n, C, chunks, chunk_len, s);   // tcgen05 path
+        const char* only = getenv("GTTS_ATTN_TC_ONLY");                 // debug: tcgen05 path for one width / one size only
+        const bool sel = !only || atoi(only) == C || atoi(only) == n;
+        if ((!tc || atoi(tc) != 0) && sel) {
+            int rc = attn_xk_tc(x, wkv_bf16, partials, B, n, C, chunks, chunk_len, s);   // tcgen05 path
+            if (getenv("GTTS_ATTN_CHECK")) {                          // debug: scan input and partials on the host
+                cudaStreamSynchronize(s);
+                std::vector<uint16_t> hx((size_t)B * n * C);
+                cudaMemcpy(hx.data(), x, hx.size() * 2, cudaMemcpyDeviceToHost);
+                size_t bad_x = 0; float amax = 0.f;
+                for (uint16_t v : hx) { uint32_t u = (uint32_t)v << 16; float f; memcpy(&f, &u, 4); if (!(f == f) || fabsf(f) > 3e38f) ++bad_x; else if (fabsf(f) > amax) amax = fabsf(f); }
+                std::vector<float> hp((size_t)B * 4 * chunks * 1088);
+                cudaMemcpy(hp.data(), partials, hp.size() * 4, cudaMemcpyDeviceToHost);
+                size_t bad_p = 0, first = (size_t)-1;
+                for (size_t i = 0; i < hp.size(); ++i) { const float f = hp[i]; const bool is_m = (i % 1088) < 32; if (!(f == f) || (!is_m && fabsf(f) > 3e38f)) { if (first == (size_t)-1) first = i; ++bad_p; } }
+                fprintf(stderr, "[attn check] n=%d C=%d chunks=%d len=%d: x nonfinite %zu absmax %.4g; partial nonfinite %zu", n, C, chunks, chunk_len, bad_x, amax, bad_p);
+                if (bad_p) { size_t slot = first / 1088; fprintf(stderr, " first at b=%zu head=%zu chunk=%zu idx=%zu", slot / ((size_t)4 * chunks), (slot / chunks) % 4, slot % chunks, first % 1088); }
+                fprintf(stderr, "\n");
+            }
+            return rc;
+        }
     }
     const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
     const __nv_bfloat16* wk = reinterpret_cast<const __nv_bfloat16*>(wkv_bf16);

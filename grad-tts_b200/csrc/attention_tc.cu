@@ -264,15 +264,17 @@ attn_xk_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 // p = 2^(k*log2e - m_ref*log2e) -> bf16 -> SMEM (K-major, 128-byte swizzle); row sum of the ROUNDED values.
                 // exp(-inf) = 0 takes care of the masked pixels.
                 uint8_t* prow = s_p + bb * kPBytes + d * 128;
+                // (k - m_ref) FIRST, then * log2(e): with the product k*log2(e) - m_ref*log2(e) the two roundings differ by up to an
+                // ulp of the product, which for |k| ~ 1e17 (diverging random-weight runs) is 1e10 in the exponent -> inf -> NaN.
                 const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f);
-                const float2 nm = make_float2(-m_ref * 1.4426950408889634f, -m_ref * 1.4426950408889634f);
+                const float2 nm = make_float2(-m_ref, -m_ref);
                 float2 ls2 = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int c16 = 0; c16 < kAtTile / 8; ++c16) {                 // 16-byte chunks of 8 pixels
                     uint32_t w[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float2 tq = ffma2(make_float2(__uint_as_float(r[c16 * 8 + 2 * q]), __uint_as_float(r[c16 * 8 + 2 * q + 1])), l2e, nm);
+                        const float2 tq = fmul2(fadd2(make_float2(__uint_as_float(r[c16 * 8 + 2 * q]), __uint_as_float(r[c16 * 8 + 2 * q + 1])), nm), l2e);
                         __nv_bfloat162 h2 = __floats2bfloat162_rn(ex2_approx(tq.x), ex2_approx(tq.y));
                         w[q] = *reinterpret_cast<uint32_t*>(&h2);
                         ls2 = fadd2(ls2, make_float2(__uint_as_float(w[q] << 16), __uint_as_float(w[q] & 0xffff0000u)));

@@ -104,6 +104,19 @@ def test_fused_gn_input_is_bitwise_equal_to_separate_pass(pkg, synth):
     assert torch.equal(outs[0], outs[1])
 
 
+def test_long_random_weight_run_stays_finite(pkg, synth, monkeypatch):
+    """100 Euler steps with random weights drive internal activations to ~1e16 (the bench workload does this): the output must
+    stay finite on both attention kernels (regression: the tcgen05 softmax once formed k*log2e - m*log2e with two roundings)."""
+    z, mask, mu, _, _ = synth.make_inputs(2, 344, 1, seed=7, ragged=False)
+    outs = {}
+    for tc in ("1", "0"):
+        monkeypatch.setenv("GTTS_ATTN_TC", tc)
+        dec, _ = _module(pkg, synth, 1, 0, "bf16")
+        outs[tc] = dec(z.to(DEV), mask.to(DEV), mu.to(DEV), 100)
+        assert torch.isfinite(outs[tc]).all(), f"GTTS_ATTN_TC={tc}: non-finite output"
+    assert float(outs["1"].abs().max()) > 0.0
+
+
 def test_sde_extension_matches_restatement(pkg, synth):
     n_spks, B, T, n = 1, 2, 40, 3
     dec, sd = _module(pkg, synth, n_spks, 0, "fp32")
