@@ -34,6 +34,9 @@ SIGNATURES = {
     "gtts_decoder_launches_last_call": (_l, [_vp]),
     "gtts_align_log_prior": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "gtts_align_outputs": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "gtts_score_loss_workspace_bytes": (_sz, []),
+    "gtts_forward_diffusion": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _d, _d, _vp]),
+    "gtts_score_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _i, _i, _i, _d, _d, _vp]),
     "gtts_test_attn_xk": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "gtts_test_issue_microbench": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp]),
     "gtts_test_conv": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),

@@ -209,6 +209,22 @@ int gtts_align_outputs(const float* attn, const float* mu_x, const float* x_mask
     return align_outputs(attn, mu_x, x_mask, logw, mu_y, B, n_feats, t_x, t_y, (cudaStream_t)stream);
 }
 
+size_t gtts_score_loss_workspace_bytes(void) { return score_loss_workspace_bytes(); }
+
+int gtts_forward_diffusion(const float* x0, const float* mask, const float* mu, const float* t, const float* noise, float* xt,
+                           float* z_masked, int B, int n_feats, int T, double beta_min, double beta_max, void* stream) {
+    GTTS_REQUIRE(x0 && mask && mu && t && noise && xt && z_masked, "null argument");
+    return forward_diffusion(x0, mask, mu, t, noise, xt, z_masked, B, n_feats, T, (float)beta_min, (float)beta_max,
+                             (cudaStream_t)stream);
+}
+
+int gtts_score_loss(const float* noise_estimation, const float* z_masked, const float* mask, const float* t, void* ws,
+                    size_t ws_bytes, float* loss, int B, int n_feats, int T, double beta_min, double beta_max, void* stream) {
+    GTTS_REQUIRE(noise_estimation && z_masked && mask && t && loss, "null argument");
+    return score_loss(noise_estimation, z_masked, mask, t, ws, ws_bytes, loss, B, n_feats, T, (float)beta_min, (float)beta_max,
+                      (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------------------------ test hooks
 int gtts_test_attn_xk(const void* x_bf16, const void* wkv_bf16, float* partials, int B, int n, int C, int chunks, int chunk_len,
                       int use_tc, void* stream) {

@@ -164,6 +164,13 @@ int align_log_prior(const float* mu_x, const float* y, float* log_prior, int B, 
 int align_outputs(const float* attn, const float* mu_x, const float* x_mask, float* logw, float* mu_y, int B, int C, int tx,
                   int ty, cudaStream_t s);
 
+// forward half of the training objective (loss.cu): model/diffusion.py:244-252 and :274-281, forward value only
+size_t score_loss_workspace_bytes();
+int forward_diffusion(const float* x0, const float* mask, const float* mu, const float* t, const float* z, float* xt, float* zm,
+                      int B, int C, int T, float beta_min, float beta_max, cudaStream_t s);
+int score_loss(const float* est, const float* zm, const float* mask, const float* t, void* ws, size_t ws_bytes, float* loss, int B,
+               int C, int T, float beta_min, float beta_max, cudaStream_t s);
+
 // weight packing helpers (device side, fp32 source in PyTorch layout)
 int pack_conv_weight(ActKind wkind, const float* w_oihw, void* packed, int Cout, int Cin, int kh, int kw,
                      cudaStream_t s);                       // -> [(ky*kw+kx)*Cout + co][ci]

@@ -133,7 +133,7 @@ class GradLogPEstimator2d(BaseModule):
             raise RuntimeError(f"{name} is on {t.device} but the decoder parameters are on {device}")
         return t.detach().to(torch.float32).contiguous()
 
-    def _check_shapes(self, x, mask, mu, spk):
+    def _check_shapes(self, x, mask, mu, spk, need_spk=True):
         if x.dim() != 3 or x.shape[1] != self.n_feats or mu.shape != x.shape:
             raise ValueError(f"expected x and mu of shape (B, {self.n_feats}, T), got {tuple(x.shape)}, {tuple(mu.shape)}")
         B, _, T = x.shape
@@ -141,7 +141,7 @@ class GradLogPEstimator2d(BaseModule):
             raise ValueError(f"expected mask of shape (B, 1, T) = {(B, 1, T)}, got {tuple(mask.shape)}")
         if T % 4 != 0:
             raise ValueError("T must be a multiple of 4 (model/utils.py fix_len_compatibility)")
-        if self.n_spks > 1:
+        if self.n_spks > 1 and need_spk:
             if spk is None or tuple(spk.shape) != (B, self.spk_emb_dim):
                 raise ValueError(f"n_spks > 1: spk of shape (B, {self.spk_emb_dim}) is required")
         return B, T
@@ -257,21 +257,59 @@ class Diffusion(BaseModule):
         _lib.check(rc, "reverse_diffusion_host")
         return out
 
-    # ---- training-side members of the reference class: outside this round's scope --------------------
-    def forward_diffusion(self, x0, mask, mu, t):
-        # model/diffusion.py:244-252; pure elementwise PyTorch, kept for callers
-        time = t.unsqueeze(-1).unsqueeze(-1)
-        cum_noise = get_noise(time, self.beta_min, self.beta_max, cumulative=True)
-        mean = x0 * torch.exp(-0.5 * cum_noise) + mu * (1.0 - torch.exp(-0.5 * cum_noise))
-        variance = 1.0 - torch.exp(-cum_noise)
-        z = torch.randn(x0.shape, dtype=x0.dtype, device=x0.device, requires_grad=False)
-        xt = mean + z * torch.sqrt(variance)
-        return xt * mask, z * mask
+    # ---- training-side members of the reference class: forward VALUE only (no estimator backward yet) ----
+    def _fd_args(self, x0, mask, mu, t):
+        est = self.estimator
+        dev = next(self.parameters()).device
+        x_, mask_, mu_ = (est._prep(v, n, dev) for v, n in ((x0, "x0"), (mask, "mask"), (mu, "mu")))
+        B, T = est._check_shapes(x_, mask_, mu_, None, need_spk=False)
+        t_ = est._prep(t, "t", dev).reshape(-1)
+        if t_.numel() != B:
+            raise ValueError("t must have one entry per sample")
+        return dev, x_, mask_, mu_, t_, B, T
 
-    def loss_t(self, x0, mask, mu, t, spk=None):
-        raise NotImplementedError("training (estimator backward) is not part of the sm_100a hot path yet; "
-                                  "see DESIGN.md 'next' rows")
+    @torch.no_grad()
+    def forward_diffusion(self, x0, mask, mu, t, noise=None):
+        """model/diffusion.py:244-252 as one kernel.  `noise` (B,80,T) replaces the reference's internal torch.randn draw
+        (default: drawn here with torch.randn on the device, like the reference).  Returns (xt * mask, z * mask)."""
+        dev, x_, mask_, mu_, t_, B, T = self._fd_args(x0, mask, mu, t)
+        if noise is None:
+            noise = torch.randn(x_.shape, dtype=torch.float32, device=dev)
+        z_ = self.estimator._prep(noise, "noise", dev)
+        if z_.shape != x_.shape:
+            raise ValueError("noise must have the shape of x0")
+        xt, zm = torch.empty_like(x_), torch.empty_like(x_)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = _lib.load().gtts_forward_diffusion(x_.data_ptr(), mask_.data_ptr(), mu_.data_ptr(), t_.data_ptr(), z_.data_ptr(),
+                                                    xt.data_ptr(), zm.data_ptr(), B, self.n_feats, T, float(self.beta_min),
+                                                    float(self.beta_max), ctypes.c_void_p(stream))
+        _lib.check(rc, "forward_diffusion")
+        return xt.to(x0.dtype), zm.to(x0.dtype)
+
+    def loss_t(self, x0, mask, mu, t, spk=None, noise=None):
+        """Forward value of model/diffusion.py:274-281 -> (loss, xt): forward diffusion, estimator, squared-error reduction,
+        all on the device.  There is no estimator backward yet: the returned loss carries no autograd
+        graph, so with gradients enabled this raises instead of silently training nothing."""
+        if torch.is_grad_enabled():
+            raise NotImplementedError("loss_t computes the forward value only (the estimator backward is not built): call it "
+                                      "under torch.no_grad(), e.g. for validation loss; see DESIGN.md 'next' rows")
+        dev, x_, mask_, mu_, t_, B, T = self._fd_args(x0, mask, mu, t)
+        xt, zm = self.forward_diffusion(x_, mask_, mu_, t_, noise)
+        est = self.estimator(xt, mask_, mu_, t_, spk)
+        lib = _lib.load()
+        ws = torch.empty(int(lib.gtts_score_loss_workspace_bytes()), dtype=torch.uint8, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = lib.gtts_score_loss(est.data_ptr(), zm.data_ptr(), mask_.data_ptr(), t_.data_ptr(), ws.data_ptr(), ws.numel(),
+                                     loss.data_ptr(), B, self.n_feats, T, float(self.beta_min), float(self.beta_max),
+                                     ctypes.c_void_p(stream))
+        _lib.check(rc, "score_loss")
+        return loss.to(x0.dtype), xt.to(x0.dtype)
 
     def compute_loss(self, x0, mask, mu, spk=None, offset=1e-5):
-        raise NotImplementedError("training (estimator backward) is not part of the sm_100a hot path yet; "
-                                  "see DESIGN.md 'next' rows")
+        # model/diffusion.py:283-287
+        t = torch.rand(x0.shape[0], dtype=x0.dtype, device=x0.device, requires_grad=False)
+        t = torch.clamp(t, offset, 1.0 - offset)
+        return self.loss_t(x0, mask, mu, t, spk)

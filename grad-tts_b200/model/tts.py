@@ -8,6 +8,7 @@ pass `encoder=` (any module with the reference `TextEncoder.forward(x, x_lengths
 contract), or leave it None inside the reference tree and `model.text_encoder.TextEncoder` is used.
 """
 import math
+import random
 
 import torch
 
@@ -127,5 +128,41 @@ class GradTTS(BaseModule):
         return ScoreModel(), mu_y, spk, y_mask
 
     def compute_loss(self, x, x_lengths, y, y_lengths, spk=None, out_size=None):
-        raise NotImplementedError("training losses need the estimator backward, which is outside this round's "
-                                  "hot path; `align()` provides the on-device MAS used by compute_loss")
+        """Forward VALUES of the three training losses (reference model/tts.py:110-194): duration loss against the MAS
+        durations, prior loss, diffusion loss.  The alignment stage, forward diffusion, estimator and loss reduction run as
+        sm_100a kernels.  The estimator backward is not built, so the losses carry no autograd graph for the decoder: this
+        raises when gradients are enabled (use it under torch.no_grad() for validation)."""
+        if torch.is_grad_enabled():
+            raise NotImplementedError("compute_loss returns forward values only (the estimator backward is not built): call "
+                                      "it under torch.no_grad(); see DESIGN.md 'next' rows")
+        x, x_lengths, y, y_lengths = self.relocate_input([x, x_lengths, y, y_lengths])
+        if self.n_spks > 1:
+            spk = self.spk_emb(spk)                                                       # :130-136
+        mu_x, logw, x_mask = self.encoder(x, x_lengths, spk)                              # :139
+        y_max_length = y.shape[-1]
+        y_mask = sequence_mask(y_lengths, y_max_length).unsqueeze(1).to(x_mask)
+        attn = self.align(mu_x, x_mask, y, y_mask)                                        # :146-152
+        logw_ = align.logw_from_path(attn, x_mask)                                        # :155
+        dur_loss = duration_loss(logw, logw_, x_lengths)
+
+        if out_size is not None:                                                          # :159-181, random segment per item
+            max_offset = (y_lengths - out_size).clamp(0).tolist()
+            offsets = [random.choice(range(0, end)) if end > 0 else 0 for end in max_offset]
+            attn_cut = torch.zeros(attn.shape[0], attn.shape[1], out_size, dtype=attn.dtype, device=attn.device)
+            y_cut = torch.zeros(y.shape[0], self.n_feats, out_size, dtype=y.dtype, device=y.device)
+            cut_lengths = []
+            for i, lo in enumerate(offsets):
+                n = out_size + min(int(y_lengths[i]) - out_size, 0)
+                cut_lengths.append(n)
+                y_cut[i, :, :n] = y[i, :, lo:lo + n]
+                attn_cut[i, :, :n] = attn[i, :, lo:lo + n]
+            y_mask = sequence_mask(torch.tensor(cut_lengths, device=y.device)).unsqueeze(1).to(y_mask)
+            if y_mask.shape[-1] < out_size:
+                y_mask = torch.nn.functional.pad(y_mask, (0, out_size - y_mask.shape[-1]))
+            attn, y = attn_cut, y_cut
+
+        mu_y = align.mu_y_from_path(attn, mu_x)                                           # :184-185
+        diff_loss, _ = self.decoder.compute_loss(y, y_mask, mu_y, spk)                    # :188
+        prior_loss = torch.sum(0.5 * ((y - mu_y) ** 2 + math.log(2 * math.pi)) * y_mask)  # :191-192
+        prior_loss = prior_loss / (torch.sum(y_mask) * self.n_feats)
+        return dur_loss, prior_loss, diff_loss

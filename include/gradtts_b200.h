@@ -10,6 +10,7 @@
  *   gtts_mas_maximum_path          model/monotonic_align/__init__.py:8-23  maximum_path(value, mask)
  *   gtts_mas_maximum_path_c        model/monotonic_align/core.pyx:40-45    maximum_path_c(paths, values, t_xs, t_ys, max_neg_val)
  *   gtts_align_log_prior / _outputs model/tts.py:143-149,155,184-185       log-prior ahead of MAS, durations and mu_y after it
+ *   gtts_forward_diffusion / gtts_score_loss model/diffusion.py:244-252,274-281  forward_diffusion, the scalar of loss_t (forward value)
  *   gtts_decoder_reverse_diffusion model/diffusion.py:254-272  Diffusion.forward / reverse_diffusion(z, mask, mu, n_timesteps, stoc, spk)
  *   gtts_decoder_estimator         model/diffusion.py:174-216  GradLogPEstimator2d.forward(x, mask, mu, t, spk)
  *   gtts_decoder_create/set_param  model/diffusion.py:128-172,227-242  module construction + load_state_dict
@@ -63,6 +64,20 @@ int gtts_mas_maximum_path_host(const float* value_host, const float* mask_host, 
 int gtts_align_log_prior(const float* mu_x, const float* y, float* log_prior, int B, int n_feats, int t_x, int t_y, void* stream);
 int gtts_align_outputs(const float* attn, const float* mu_x, const float* x_mask, float* logw, float* mu_y, int B, int n_feats,
                        int t_x, int t_y, void* stream);
+
+/* ---- Forward value of the training objective (model/diffusion.py:244-252, :274-281) -----------------
+ * gtts_forward_diffusion  Diffusion.forward_diffusion with caller-supplied N(0,1) noise (the reference draws it with
+ *   torch.randn inside, :249): xt = (x0 e^{-c/2} + mu (1 - e^{-c/2}) + noise sqrt(1 - e^{-c})) mask, z_masked = noise mask,
+ *   c = beta_min t + 0.5 (beta_max - beta_min) t^2 per sample.  x0, mu, noise, xt, z_masked: [B][n_feats][T]; mask: [B][T];
+ *   t: [B]; T % 4 == 0.
+ * gtts_score_loss         the scalar of Diffusion.loss_t (:278-280) given the estimator output:
+ *   loss = sum (noise_estimation sqrt(1 - e^{-c}) + z_masked)^2 / (sum(mask) n_feats), one fp32 on the device.
+ *   ws: gtts_score_loss_workspace_bytes() bytes of device scratch.  Forward value only: there is no backward. */
+size_t gtts_score_loss_workspace_bytes(void);
+int gtts_forward_diffusion(const float* x0, const float* mask, const float* mu, const float* t, const float* noise, float* xt,
+                           float* z_masked, int B, int n_feats, int T, double beta_min, double beta_max, void* stream);
+int gtts_score_loss(const float* noise_estimation, const float* z_masked, const float* mask, const float* t, void* ws,
+                    size_t ws_bytes, float* loss, int B, int n_feats, int T, double beta_min, double beta_max, void* stream);
 
 /* ---- Decoder --------------------------------------------------------------------------------------
  * n_spks follows the reference constructor: 1 (or <2) = two input channels; >1 = speaker channel, spk

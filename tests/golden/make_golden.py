@@ -1,7 +1,8 @@
 """Generate the golden fixtures in tests/golden/ by running the REAL reference on CPU.
 
 Run in the build container only (needs /root/reference):
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py          # everything
+    python tests/golden/make_golden.py loss     # only the loss_t vectors
 It copies /root/reference/model to a temp dir, builds the reference's Cython extension with the
 reference's own setup.py (README.md:31), imports `model`, loads seeded synthetic weights
 (grad-tts_b200/synth.py) with strict=True into the reference modules, runs them in fp32 on CPU
@@ -54,9 +55,52 @@ def decoder_cases():
     ]
 
 
+def loss_cases():
+    # name, n_spks, B, T, weight seed, input seed
+    return [("loss_spk1_b2_t48", 1, 2, 48, 0, 41), ("loss_spk247_b3_t40", 247, 3, 40, 3, 42)]
+
+
+def make_loss_vectors():
+    """Diffusion.loss_t (model/diffusion.py:274-281) on seeded inputs: the noise the reference drew (captured from
+    forward_diffusion's second return value), xt, the estimator output it saw and the loss."""
+    from model.diffusion import Diffusion
+    for name, n_spks, B, T, wseed, iseed in loss_cases():
+        sd = synth.make_decoder_state_dict(n_spks, seed=wseed, g=0.05)
+        dec = Diffusion(80, 64, n_spks, 64, 0.05, 20.0, 1000).eval()
+        dec.load_state_dict(sd, strict=True)
+        x0, mask, mu, spk, lengths = synth.make_inputs(B, T, n_spks, seed=iseed, ragged=True)
+        gen = torch.Generator().manual_seed(iseed + 100)
+        t = torch.rand(B, generator=gen).clamp(1e-5, 1 - 1e-5)
+        cap = {}
+        orig_fd = dec.forward_diffusion
+
+        def fd(*a):
+            xt, zm = orig_fd(*a)
+            cap["xt"], cap["zm"] = xt.clone(), zm.clone()
+            return xt, zm
+
+        dec.forward_diffusion = fd
+        hook = dec.estimator.register_forward_hook(lambda m, i, o: cap.__setitem__("est", o.clone()))
+        torch.manual_seed(iseed + 200)
+        with torch.no_grad():
+            loss, xt = dec.loss_t(x0, mask, mu, t, spk)
+        hook.remove()
+        assert torch.equal(xt, cap["xt"])
+        out = dict(x0=x0.numpy(), mask=mask.numpy(), mu=mu.numpy(), t=t.numpy(), zm=cap["zm"].numpy(), xt=xt.numpy(),
+                   est=cap["est"].numpy(), loss=np.float32(loss.item()), n_spks=np.int64(n_spks), wseed=np.int64(wseed),
+                   sd_sha256=np.array(sd_digest(sd)))
+        if spk is not None:
+            out["spk"] = spk.numpy()
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+        print(name, "loss", float(loss))
+
+
 def main():
     torch.set_num_threads(8)
     import_reference()
+    if sys.argv[1:] == ["loss"]:
+        return make_loss_vectors()
+    make_loss_vectors()
     from model.diffusion import Diffusion
     from model.monotonic_align import maximum_path
 

@@ -103,3 +103,23 @@ def test_align_oracle_matches_reference_capture(name):
     assert torch.equal(attn.to(torch.int8), torch.from_numpy(g["attn"]))
     assert torch.equal(align_oracle.logw_from_path(attn, x_mask), torch.from_numpy(g["logw_"]))
     assert torch.equal(align_oracle.mu_y_from_path(attn, mu_x), torch.from_numpy(g["mu_y"]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Forward value of the training objective: oracle vs vectors captured from the reference's Diffusion.loss_t
+@pytest.mark.parametrize("name", ["loss_spk1_b2_t48", "loss_spk247_b3_t40"])
+def test_loss_oracle_matches_reference_capture(name, synth):
+    from oracle import loss_oracle
+    torch.set_num_threads(8)
+    g = _load(name)
+    n_spks = int(g["n_spks"])
+    x0, mask, mu, t, zm = (torch.from_numpy(g[k]) for k in ("x0", "mask", "mu", "t", "zm"))
+    spk = torch.from_numpy(g["spk"]) if "spk" in g else None
+    xt, zm2 = loss_oracle.forward_diffusion(x0, mask, mu, t, zm)            # the masked draw is enough: xt is masked anyway
+    assert torch.equal(xt, torch.from_numpy(g["xt"])) and torch.equal(zm2, zm)   # same ops, same CPU: bit-identical
+    loss = loss_oracle.score_loss(torch.from_numpy(g["est"]), zm, mask, t)
+    assert abs(float(loss) - float(g["loss"])) <= 1e-6 * float(g["loss"])
+    sd = synth.make_decoder_state_dict(n_spks, seed=int(g["wseed"]), g=0.05)
+    with torch.no_grad():
+        full, _ = loss_oracle.loss_t(sd, x0, mask, mu, t, zm, spk, n_spks)
+    assert abs(float(full) - float(g["loss"])) <= 1e-5 * float(g["loss"])
