@@ -188,3 +188,75 @@ def test_gradtts_forward_dropin(pkg, synth):
         ref = do.reverse_diffusion(sd, z.cpu(), y_mask, mu_y, 3)
     assert float((enc_out.cpu() - mu_y[:, :, :y_max]).abs().max()) <= 1e-5
     assert float((dec_out.cpu() - ref[:, :, :y_max]).abs().max()) <= 1e-3
+
+
+def test_c_abi_writes_stay_inside_the_caller_buffers(pkg, synth):
+    """Own bounds check (no sanitizer on the pool): inputs and outputs handed to the C ABI live inside larger buffers filled with a
+    canary; after sampler, estimator, MAS and alignment calls at sizes that leave ragged tile tails, every canary is intact and
+    the outputs equal those of the ordinary (unguarded) call bit for bit."""
+    import ctypes
+    lib = pkg._lib.load()
+    G, CAN = 4096, -777.25
+
+    def guarded(src=None, numel=None):
+        n = src.numel() if src is not None else numel
+        buf = torch.full((n + 2 * G,), CAN, dtype=torch.float32, device=DEV)
+        if src is not None:
+            buf[G:G + n] = src.reshape(-1).to(DEV)
+        return buf, buf[G:G + n]
+
+    def intact(buf):
+        return bool((buf[:G] == CAN).all()) and bool((buf[-G:] == CAN).all())
+
+    for n_spks, wseed, B, T in [(1, 0, 3, 44), (247, 3, 2, 36)]:
+        dec, _ = _module(pkg, synth, n_spks, wseed, "bf16")
+        z, mask, mu, spk, _ = synth.make_inputs(B, T, n_spks, seed=17)
+        ref = dec(z.to(DEV), mask.to(DEV), mu.to(DEV), 3, False, spk.to(DEV) if spk is not None else None)
+        t = torch.tensor([0.2, 0.7, 0.95][:B])
+        ref_e = dec.estimator((z * mask).to(DEV), mask.to(DEV), mu.to(DEV), t.to(DEV), spk.to(DEV) if spk is not None else None)
+        bufs = [guarded(v) for v in (z, mask, mu)] + [guarded(numel=z.numel())]
+        sb = guarded(spk) if spk is not None else (None, None)
+        h = dec.estimator._get_handle()
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        ptr = lambda v: v.data_ptr() if v is not None else None
+        rc = lib.gtts_decoder_reverse_diffusion(h, ptr(bufs[0][1]), ptr(bufs[1][1]), ptr(bufs[2][1]), ptr(sb[1]), ptr(bufs[3][1]),
+                                                B, T, 3, dec.estimator._flags(), None, stream)
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert all(intact(b) for b, _ in bufs) and (sb[0] is None or intact(sb[0]))
+        assert torch.equal(bufs[3][1].reshape(B, 80, T), ref)
+        assert torch.equal(bufs[0][1].cpu(), z.reshape(-1))                    # inputs untouched
+        zb, tb, ob = guarded(z * mask), guarded(t), guarded(numel=z.numel())
+        rc = lib.gtts_decoder_estimator(h, ptr(zb[1]), ptr(bufs[1][1]), ptr(bufs[2][1]), ptr(tb[1]), ptr(sb[1]), ptr(ob[1]), B, T,
+                                        dec.estimator._flags(), stream)
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert intact(zb[0]) and intact(tb[0]) and intact(ob[0]) and all(intact(b) for b, _ in bufs)
+        assert torch.equal(ob[1].reshape(B, 80, T), ref_e)
+
+    # MAS + alignment stage, odd sizes
+    B, tx, ty = 3, 37, 131
+    value, mmask, _, _ = synth.make_mas_inputs(B, tx, ty, seed=5, ragged=True)
+    vb, mb, pb = guarded(value), guarded(mmask), guarded(numel=value.numel())
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ws_bytes = int(lib.gtts_mas_workspace_bytes(B, tx, ty))
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=DEV)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = lib.gtts_mas_maximum_path(vb[1].data_ptr(), mb[1].data_ptr(), pb[1].data_ptr(), B, tx, ty, ws.data_ptr(), ws_bytes,
+                                   status.data_ptr(), stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert intact(vb[0]) and intact(mb[0]) and intact(pb[0]) and int(status) == 0
+    ma = __import__("importlib").import_module("grad-tts_b200.model.monotonic_align")
+    assert torch.equal(pb[1].reshape(B, tx, ty), ma.maximum_path(value.to(DEV), mmask.to(DEV)))
+    gen = torch.Generator().manual_seed(6)
+    mu_x, y = torch.randn(B, 80, tx, generator=gen), torch.randn(B, 80, ty, generator=gen)
+    xb, yb, lb = guarded(mu_x), guarded(y), guarded(numel=B * tx * ty)
+    assert lib.gtts_align_log_prior(xb[1].data_ptr(), yb[1].data_ptr(), lb[1].data_ptr(), B, 80, tx, ty, stream) == 0
+    xm = guarded(torch.ones(B, tx))
+    wb, ub = guarded(numel=B * tx), guarded(numel=B * 80 * ty)
+    assert lib.gtts_align_outputs(pb[1].data_ptr(), xb[1].data_ptr(), xm[1].data_ptr(), wb[1].data_ptr(), ub[1].data_ptr(), B, 80,
+                                  tx, ty, stream) == 0
+    torch.cuda.synchronize()
+    assert all(intact(b) for b, _ in (xb, yb, lb, xm, wb, ub, pb))
+    assert not bool((lb[1] == CAN).any()) and not bool((ub[1] == CAN).any()) and not bool((wb[1] == CAN).any())   # fully written
