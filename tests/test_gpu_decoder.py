@@ -260,3 +260,63 @@ def test_c_abi_writes_stay_inside_the_caller_buffers(pkg, synth):
     torch.cuda.synchronize()
     assert all(intact(b) for b, _ in (xb, yb, lb, xm, wb, ub, pb))
     assert not bool((lb[1] == CAN).any()) and not bool((ub[1] == CAN).any()) and not bool((wb[1] == CAN).any())   # fully written
+
+
+def _oracle_est(sd, x, mask, mu, t, spk=None, n_spks=1):
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        return decoder_oracle.estimator_forward(sd, x, mask, mu, t, spk, n_spks)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 5e-2)])
+def test_edge_shapes_and_masks_against_oracle(pkg, synth, precision, tol):
+    """Edge cases of the estimator (the reference has no tests; the oracle is the checker): the smallest legal T (level 2 is one
+    frame wide), a batch holding an empty (length 0) and a one-frame utterance, and an arbitrary non-prefix binary mask, which the
+    reference API accepts (model/diffusion.py:174)."""
+    dec, sd = _module(pkg, synth, 1, 0, precision)
+    gen = torch.Generator().manual_seed(77)
+    cases = []
+    for B, T, kind in [(1, 4, "full"), (2, 8, "full"), (3, 24, "empty+one"), (2, 40, "random")]:
+        x, mu = torch.randn(B, 80, T, generator=gen), torch.randn(B, 80, T, generator=gen)
+        if kind == "full":
+            mask = torch.ones(B, 1, T)
+        elif kind == "empty+one":
+            lengths = torch.tensor([0, 1, T])
+            mask = (torch.arange(T)[None] < lengths[:, None]).float().unsqueeze(1)
+        else:
+            mask = (torch.rand(B, 1, T, generator=gen) > 0.35).float()
+        t = torch.rand(B, generator=gen).clamp(1e-5, 1 - 1e-5)
+        cases.append((x * mask, mask, mu, t))
+    for x, mask, mu, t in cases:
+        ref = _oracle_est(sd, x, mask, mu, t)
+        got = dec.estimator(x.to(DEV), mask.to(DEV), mu.to(DEV), t.to(DEV)).cpu()
+        assert torch.isfinite(got).all()
+        assert float((got * (1 - mask)).abs().max()) == 0.0
+        err = float((got - ref).abs().max())
+        assert err <= tol, f"T={x.shape[-1]} B={x.shape[0]}: max-abs {err} (|ref|max {float(ref.abs().max())})"
+
+
+def test_long_utterance_against_oracle(pkg, synth):
+    """One utterance of 6000 frames (480 000 attention positions at level 0, 70 s of audio): index arithmetic, attention chunking and
+    tile tails far from the fixture sizes.  bf16 mode, same bounds as the fixtures (max-abs 5e-2 on a score of O(1); rel-rms 2e-2,
+    measured 1.2e-2 / 2.5e-2 max-abs)."""
+    dec, sd = _module(pkg, synth, 1, 0, "bf16")
+    B, T = 1, 6000
+    x, mask, mu, _, _ = synth.make_inputs(B, T, 1, seed=91, ragged=False)
+    mask[:, :, 5555:] = 0
+    t = torch.tensor([0.37])
+    ref = _oracle_est(sd, x * mask, mask, mu, t)
+    got = dec.estimator((x * mask).to(DEV), mask.to(DEV), mu.to(DEV), t.to(DEV)).cpu()
+    err = float((got - ref).abs().max())
+    rel = float((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())
+    assert err <= 5e-2 and rel <= 2e-2, (err, rel, float(ref.abs().max()))
+
+
+def test_batch_larger_than_one_workspace_chunk(pkg, synth):
+    """65 utterances = one chunk of 64 and one of 1 (max_chunk is 64): every sample equals its single-sample run bit for bit."""
+    dec, _ = _module(pkg, synth, 1, 0, "bf16")
+    z, mask, mu, _, _ = synth.make_inputs(65, 8, 1, seed=13)
+    y = dec(z.to(DEV), mask.to(DEV), mu.to(DEV), 2)
+    for b in (0, 31, 63, 64):
+        yb = dec(z[b:b + 1].to(DEV), mask[b:b + 1].to(DEV), mu[b:b + 1].to(DEV), 2)
+        assert torch.equal(y[b:b + 1], yb), b
