@@ -104,10 +104,11 @@ __global__ void temb_kernel(TembWeights w, const float* __restrict__ t, const in
 
 // ------------------------------------------------------------------------------------------------ first conv
 // Block.conv of downs.0.0.block1 on stack([mu, x, (s)]) * mask  (:181-184, 52-57), straight from the fp32 planes.
-// Thread = 4 consecutive pixels x 16 output channels (4 threads cover the 64 channels of a pixel quad), so every
+// Thread = 4 consecutive pixels x 16 output channels (the 4 warps of a CTA cover the 64 channels of 32 pixel quads), so every
 // 16-byte weight read from shared memory feeds 16 FMAs.  A CTA walks kFcTiles tiles of 128 pixels of one sample and
 // publishes ONE GroupNorm partial (one fence + ticket per CTA).
 constexpr int kFcTiles = 8;
+constexpr int kFcSpan = kFcTiles * 128 + 2;           // staged pixels per row: the CTA's pixels and one neighbour on either side
 
 template <typename T, int CIN>
 __global__ void __launch_bounds__(128)
@@ -115,8 +116,9 @@ first_conv_kernel(FirstConvArgs a) {
     pdl_trigger();
     pdl_wait();
     __shared__ __align__(16) float wT[CIN * 9 * 64];
+    __shared__ __align__(16) float s_in[2][3][kFcSpan + 6];              // element i + 3 <-> pixel P0 - 1 + i: a quad is 16-byte aligned
+    __shared__ __align__(16) float s_mk[kFcSpan + 6];
     __shared__ float sb[64];
-    __shared__ float s_part[4][16];
     __shared__ float s_tile[16];
     __shared__ double s_red[8 * 16];
     __shared__ int s_flag;
@@ -126,12 +128,41 @@ first_conv_kernel(FirstConvArgs a) {
     __syncthreads();
 
     const int H = a.H, W = a.W, HW = H * W;
-    const int q = tid & 3, quad = tid >> 2;               // channels q*16..q*16+15 ; pixel quad within the tile
-    const float* mrow = a.mask + (size_t)b * W;
+    // warp = channel block (channels q*16..q*16+15), lane = pixel quad: every weight read is warp-uniform (one shared-memory
+    // wavefront).  With q = tid & 3 the 128-bit weight reads of a quarter-warp hit 4 addresses on 2 banks groups: 8 wavefronts
+    // per read, and ncu showed the shared-memory pipe 71 % busy -- the kernel's limiter (206 -> 175 us at 16 x 80 x 1720).
+    // What is left is still LSU-bound: a warp-uniform LDS.128 costs 4 wavefronts, 308 per tile and warp against 1152 FMA-pipe
+    // cycles shared by 4 warps; 4 CTAs per SM (128 registers) changes nothing.
+    const int q = tid >> 5, quad = tid & 31;
     float st[4] = {0.f, 0.f, 0.f, 0.f};                   // sums of my two groups, then their sums of squares
 
+    // Stage the CTA's input window once: pixels [P0-1, P0+kFcTiles*128] of the rows above / at / below, both planes already
+    // multiplied by the frame mask, plus the mask itself.  (Loading them per tile straight from global left the kernel waiting
+    // on the loads with 12 warps per SM: ncu showed 41 % issue-active and 2.4 warps per issue in long-scoreboard stalls.)
+    const int P0 = blockIdx.x * (kFcTiles * 128);
+    {
+        const float* mrow = a.mask + (size_t)b * W;
+        const float* mup = a.mu + (size_t)b * HW;
+        const float* xp = a.x + (size_t)b * HW;
+        for (int i = tid; i < kFcSpan; i += 128) {
+            const int p = P0 - 1 + i;                      // linear pixel of the middle row
+            float mv = 0.f;
+            if (p >= 0 && p < HW) mv = mrow[p % W];
+            s_mk[i + 3] = mv;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int qq = p + (r - 1) * W;
+                const bool ok = p >= 0 && p < HW && qq >= 0 && qq < HW;
+                s_in[0][r][i + 3] = ok ? mup[qq] * mv : 0.f;
+                s_in[1][r][i + 3] = ok ? xp[qq] * mv : 0.f;
+            }
+        }
+    }
+    __syncthreads();
+
     for (int t = 0; t < kFcTiles; ++t) {
-        const int p0 = (blockIdx.x * kFcTiles + t) * 128 + quad * 4;      // first pixel of my quad (W % 4 == 0)
+        const int local = t * 128 + quad * 4;
+        const int p0 = P0 + local;                                        // first pixel of my quad (W % 4 == 0)
         if (p0 >= HW) break;                               // uniform per quad; later tiles are out of range too
         const int h = p0 / W, w0 = p0 - h * W;
         float2 acc[4][8];                                  // packed channel pairs: FFMA2 halves the issue slots
@@ -143,21 +174,20 @@ first_conv_kernel(FirstConvArgs a) {
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
             const int ww = w0 - 1 + i;
-            mk[i] = (ww >= 0 && ww < W) ? mrow[ww] : 0.f;
+            mk[i] = (ww >= 0 && ww < W) ? s_mk[local + 3 + i] : 0.f;
         }
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
             const int hh = h + ky - 1;
             if (hh < 0 || hh >= H) continue;
             float in[CIN][6];
-            const size_t rowoff = ((size_t)b * H + hh) * W;
             const float sv = CIN == 3 ? a.splane[b * H + hh] : 0.f;
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
                 const int ww = w0 - 1 + i;
                 const bool inb = ww >= 0 && ww < W;
-                in[0][i] = inb ? a.mu[rowoff + ww] * mk[i] : 0.f;
-                in[1][i] = inb ? a.x[rowoff + ww] * mk[i] : 0.f;
+                in[0][i] = inb ? s_in[0][ky][local + 3 + i] : 0.f;
+                in[1][i] = inb ? s_in[1][ky][local + 3 + i] : 0.f;
                 if (CIN == 3) in[CIN - 1][i] = sv * mk[i];
             }
 #pragma unroll
@@ -209,20 +239,16 @@ first_conv_kernel(FirstConvArgs a) {
         }
     }
     // GroupNorm statistics (8 groups of 8 channels) over the unmasked conv output   (:53)
-    // reduce over the 8 quads of the warp that share q (lanes q, q+4, ...), fixed order
+    // the whole warp shares q: fixed butterfly over the 32 quads, lane 0 owns groups 2q, 2q+1
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        st[k] += __shfl_xor_sync(0xffffffffu, st[k], 4);
-        st[k] += __shfl_xor_sync(0xffffffffu, st[k], 8);
-        st[k] += __shfl_xor_sync(0xffffffffu, st[k], 16);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) st[k] += __shfl_xor_sync(0xffffffffu, st[k], o);
     }
-    if (lane < 4) {
-        // lane = q: groups 2q, 2q+1 -> slots [g] (sum) and [8+g] (sum of squares)
-        s_part[warp][2 * lane] = st[0];     s_part[warp][2 * lane + 1] = st[1];
-        s_part[warp][8 + 2 * lane] = st[2]; s_part[warp][8 + 2 * lane + 1] = st[3];
+    if (lane == 0) {
+        s_tile[2 * warp] = st[0];     s_tile[2 * warp + 1] = st[1];         // sums
+        s_tile[8 + 2 * warp] = st[2]; s_tile[8 + 2 * warp + 1] = st[3];     // sums of squares
     }
-    __syncthreads();
-    if (tid < 16) s_tile[tid] = (s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]);
     __syncthreads();
     GnStatsOut go{a.gn_partials, a.gn_stats, a.gn_counters, (int)gridDim.x, 1.0f / (8.0f * H * W), a.gn_eps};
     gn_stats_publish(go, b, blockIdx.x, tid, 128, s_tile, s_red, &s_flag, [] { __syncthreads(); });
