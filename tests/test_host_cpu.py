@@ -122,3 +122,23 @@ def test_sharded_call_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0 and "ok" in o, o
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU leg the driver runs beside ours) prints one JSON line with the agreed keys.  C1 workload
+    (1 x 400 frames) so the whole run is a few seconds; no GPU is touched."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "C1", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "decoder_mel_frames_per_sec" and line["unit"] == "frames/s"
+    assert line["higher_is_better"] is True and line["gpu_launches"] == 0 and line["vs_baseline"] is None
+    assert line["value"] > 0 and line["ms_per_step"] > 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "oracle/decoder_oracle.py" in cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["workload"].startswith("C1")
