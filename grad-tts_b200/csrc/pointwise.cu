@@ -144,17 +144,33 @@ first_conv_kernel(FirstConvArgs a) {
         const float* mrow = a.mask + (size_t)b * W;
         const float* mup = a.mu + (size_t)b * HW;
         const float* xp = a.x + (size_t)b * HW;
-        for (int i = tid; i < kFcSpan; i += 128) {
-            const int p = P0 - 1 + i;                      // linear pixel of the middle row
-            float mv = 0.f;
-            if (p >= 0 && p < HW) mv = mrow[p % W];
-            s_mk[i + 3] = mv;
+        // all loads of the window are issued before the first use (9 x 7 independent loads per thread); a rolled loop that
+        // loaded, multiplied and stored one element at a time took half of the kernel's time (ncu source view)
+        constexpr int kIt = (kFcSpan + 127) / 128;
+        float mv[kIt], v[kIt][6];
+#pragma unroll
+        for (int k = 0; k < kIt; ++k) {
+            const int i = tid + k * 128, p = P0 - 1 + i;   // linear pixel of the middle row
+            const bool okp = i < kFcSpan && p >= 0 && p < HW;
+            mv[k] = okp ? mrow[p % W] : 0.f;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const int qq = p + (r - 1) * W;
-                const bool ok = p >= 0 && p < HW && qq >= 0 && qq < HW;
-                s_in[0][r][i + 3] = ok ? mup[qq] * mv : 0.f;
-                s_in[1][r][i + 3] = ok ? xp[qq] * mv : 0.f;
+                const bool ok = okp && qq >= 0 && qq < HW;
+                v[k][r] = ok ? mup[qq] : 0.f;
+                v[k][3 + r] = ok ? xp[qq] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kIt; ++k) {
+            const int i = tid + k * 128;
+            if (i < kFcSpan) {
+                s_mk[i + 3] = mv[k];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    s_in[0][r][i + 3] = v[k][r] * mv[k];
+                    s_in[1][r][i + 3] = v[k][3 + r] * mv[k];
+                }
             }
         }
     }
