@@ -3,6 +3,7 @@
 Run in the build container only (needs /root/reference):
     python tests/golden/make_golden.py          # everything
     python tests/golden/make_golden.py loss     # only the loss_t vectors
+    python tests/golden/make_golden.py NAME...  # only the named decoder cases
 It copies /root/reference/model to a temp dir, builds the reference's Cython extension with the
 reference's own setup.py (README.md:31), imports `model`, loads seeded synthetic weights
 (grad-tts_b200/synth.py) with strict=True into the reference modules, runs them in fp32 on CPU
@@ -52,6 +53,8 @@ def decoder_cases():
         ("dec_spk1_b1_t64_n10", 1, 1, 64, 10, 0, 5),
         ("dec_spk1_b3_t56_n4", 1, 3, 56, 4, 7, 8),
         ("dec_spk247_b2_t40_n3", 247, 2, 40, 3, 3, 6),
+        # third mode (params_tedlium.py:22-23): n_spks = -1, spk_mlp exists and is evaluated, the U-Net takes two channels
+        ("dec_spkm1_b2_t32_n3", -1, 2, 32, 3, 9, 10),
     ]
 
 
@@ -100,15 +103,21 @@ def main():
     import_reference()
     if sys.argv[1:] == ["loss"]:
         return make_loss_vectors()
-    make_loss_vectors()
+    only = set(sys.argv[1:])                                   # optional: names of decoder cases to (re)generate
+    if not only:
+        make_loss_vectors()
     from model.diffusion import Diffusion
     from model.monotonic_align import maximum_path
 
     for name, n_spks, B, T, n_steps, wseed, iseed in decoder_cases():
+        if only and name not in only:
+            continue
         sd = synth.make_decoder_state_dict(n_spks, seed=wseed, g=0.05)
         dec = Diffusion(80, 64, n_spks, 64, 0.05, 20.0, 1000).eval()
         dec.load_state_dict(sd, strict=True)
         z, mask, mu, spk, lengths = synth.make_inputs(B, T, n_spks, seed=iseed, ragged=True)
+        if n_spks == -1:
+            spk = torch.randn(B, 64, generator=torch.Generator().manual_seed(iseed + 300))
         out = {}
         with torch.no_grad():
             if n_steps == 0:
@@ -127,6 +136,8 @@ def main():
             out["spk"] = spk.numpy()
         np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
         print(name, "y absmax", float(y.abs().max()))
+    if only:
+        return
 
     # Alignment stage (tts.py:139-185): vectors captured from the reference's own GradTTS.compute_loss -- mu_x from the encoder,
     # the log_prior / mask handed to maximum_path, the path it returned, logw_ (argument of duration_loss) and mu_y (argument of
