@@ -269,13 +269,13 @@ def main():
         f_conv = sum(o["flops"] for o in conv)
         tf_peak, hbm_peak, which = peaks()
         ach = f_conv / t_conv / 1e12
-        # DRAM bytes per launch from the committed ncu capture of this command (profiles/r01_conv_dram_v7.json: 40 conv
+        # DRAM bytes per launch from the committed ncu capture of this command (profiles/r01_conv_dram_v11.json: 40 conv
         # launches of one Euler step at chunk 64 x 1720); only quoted when this run uses the same chunk shape
         traffic, traffic_src = None, None
         try:
-            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_conv_dram_v7.json")))
+            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_conv_dram_v11.json")))
             if rep["B"] == tj.get("chunk_batch", 64) and T == 1720 and tj["launches"] == len(conv):
-                traffic, traffic_src = tj["traffic_bytes_per_launch"], "profiles/r01_conv_dram_v7.json (ncu dram__bytes_read+write)"
+                traffic, traffic_src = tj["traffic_bytes_per_launch"], "profiles/r01_conv_dram_v11.json (ncu dram__bytes_read+write)"
         except (OSError, KeyError, ValueError):
             pass
         roof = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convolutions (conv_tc / conv_tc_halo / conv_tc_halo2, all launches of one Euler step)",
