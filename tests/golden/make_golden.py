@@ -58,6 +58,46 @@ def decoder_cases():
     ]
 
 
+def baseline_shape_cases():
+    """Fixtures at the shapes BASELINE.json names.  Only the reference OUTPUT is stored (plus a digest of the inputs): the
+    inputs are regenerated from the seed by grad-tts_b200/synth.py (CPU torch.Generator), like the MAS fixtures.
+    name, n_spks, B, T, n_steps, weight seed, input seed, ragged"""
+    return [
+        # C1: LJSpeech single speaker, batch 1 x 400 frames, 10 Euler steps -- the exact weights/inputs bench.py uses
+        ("c1_spk1_b1_t400_n10", 1, 1, 400, 10, 0, 1, False),
+        # C1 shape with a second, shorter utterance in the batch (padding participates in GroupNorm / softmax)
+        ("c1r_spk1_b2_t400_n10", 1, 2, 400, 10, 0, 21, True),
+        # C3 shape: Libri-TTS multispeaker (n_spks=247, speaker channel), 800 frames, stoc=True passed (a no-op in the fork)
+        ("c3_spk247_b2_t800_n3", 247, 2, 800, 3, 0, 22, True),
+    ]
+
+
+def tensors_digest(*ts):
+    h = hashlib.sha256()
+    for t in ts:
+        if t is not None:
+            h.update(t.contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def make_baseline_shape_vectors(only=()):
+    from model.diffusion import Diffusion
+    for name, n_spks, B, T, n_steps, wseed, iseed, ragged in baseline_shape_cases():
+        if only and name not in only:
+            continue
+        sd = synth.make_decoder_state_dict(n_spks, seed=wseed, g=0.05)
+        dec = Diffusion(80, 64, n_spks, 64, 0.05, 20.0, 1000).eval()
+        dec.load_state_dict(sd, strict=True)
+        z, mask, mu, spk, lengths = synth.make_inputs(B, T, n_spks, seed=iseed, ragged=ragged)
+        with torch.no_grad():
+            y = dec(z, mask, mu, n_steps, True, spk)
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), y=y.numpy(), n_spks=np.int64(n_spks), n_steps=np.int64(n_steps),
+                            wseed=np.int64(wseed), iseed=np.int64(iseed), ragged=np.bool_(ragged), shape=np.array([B, T]),
+                            lengths=lengths.numpy(), sd_sha256=np.array(sd_digest(sd)),
+                            in_sha256=np.array(tensors_digest(z, mask, mu, spk)))
+        print(name, "y absmax", float(y.abs().max()))
+
+
 def loss_cases():
     # name, n_spks, B, T, weight seed, input seed
     return [("loss_spk1_b2_t48", 1, 2, 48, 0, 41), ("loss_spk247_b3_t40", 247, 3, 40, 3, 42)]
@@ -104,6 +144,7 @@ def main():
     if sys.argv[1:] == ["loss"]:
         return make_loss_vectors()
     only = set(sys.argv[1:])                                   # optional: names of decoder cases to (re)generate
+    make_baseline_shape_vectors(only)
     if not only:
         make_loss_vectors()
     from model.diffusion import Diffusion

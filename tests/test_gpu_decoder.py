@@ -11,13 +11,14 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN
+from conftest import GOLDEN, decoder_case_names, load_decoder_case
 from oracle import decoder_oracle
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-DEC = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-             if os.path.basename(p).startswith(("est_", "dec_")))
+# est_*/dec_*: small fixtures; c1*/c3*: the shapes BASELINE.json names (C1 = 1 x 400 frames x 10 steps, the bench's own weights and
+# inputs; C3 shape = n_spks 247, 800 frames, ragged)
+DEC = decoder_case_names(("est_", "dec_", "c1", "c3"))
 
 
 def _module(pkg, synth, n_spks, wseed, precision):
@@ -31,16 +32,16 @@ def _module(pkg, synth, n_spks, wseed, precision):
 
 
 def _run_golden(pkg, synth, name, precision):
-    g = np.load(os.path.join(GOLDEN, name + ".npz"))
-    n_spks, n_steps = int(g["n_spks"]), int(g["n_steps"])
-    dec, _ = _module(pkg, synth, n_spks, int(g["wseed"]), precision)
-    z, mask, mu = (torch.from_numpy(g[k]).to(DEV) for k in ("z", "mask", "mu"))
-    spk = torch.from_numpy(g["spk"]).to(DEV) if "spk" in g else None
+    g = load_decoder_case(name)
+    n_spks, n_steps = g["n_spks"], g["n_steps"]
+    dec, _ = _module(pkg, synth, n_spks, g["wseed"], precision)
+    z, mask, mu = (g[k].to(DEV) for k in ("z", "mask", "mu"))
+    spk = g["spk"].to(DEV) if g["spk"] is not None else None
     if n_steps == 0:
-        y = dec.estimator(z * mask, mask, mu, torch.from_numpy(g["t"]).to(DEV), spk)
+        y = dec.estimator(z * mask, mask, mu, g["t"].to(DEV), spk)
     else:
         y = dec(z, mask, mu, n_steps, True, spk)            # stoc=True: ignored like the reference
-    return y.cpu(), torch.from_numpy(g["y"]), n_steps
+    return y.cpu(), g["y"], n_steps
 
 
 @pytest.mark.parametrize("name", DEC)
@@ -320,3 +321,30 @@ def test_batch_larger_than_one_workspace_chunk(pkg, synth):
     for b in (0, 31, 63, 64):
         yb = dec(z[b:b + 1].to(DEV), mask[b:b + 1].to(DEV), mu[b:b + 1].to(DEV), 2)
         assert torch.equal(y[b:b + 1], yb), b
+
+
+@pytest.mark.parametrize("precision,tol_abs,tol_rel", [("bf16", 5e-2, 2e-2), ("fp32", 1e-4, 2e-5)])
+def test_bench_chunk_shape_against_oracle(pkg, synth, precision, tol_abs, tol_rel):
+    """The bench workload's own chunk shape (BASELINE config 5: 64 utterances x 1720 frames per workspace chunk, the bench's
+    weights and inputs): one estimator call and one Euler step on the full chunk; samples 0, 31 and 63 are compared with the CPU
+    oracle run on those samples alone (the maths is per-sample, so the oracle need not run all 64)."""
+    B, T = 64, 1720
+    dec, sd = _module(pkg, synth, 1, 0, precision)
+    z, mask, mu, _, _ = synth.make_inputs(B, T, 1, seed=1, ragged=False)
+    mask[31, :, 1500:] = 0                                   # one padded utterance inside the chunk
+    pick = [0, 31, 63]
+    t = torch.full((B,), 0.995)                              # t of the first of 100 Euler steps
+    zd, md, mud = z.to(DEV), mask.to(DEV), mu.to(DEV)
+    got_e = dec.estimator(zd * md, md, mud, t.to(DEV))[pick].cpu()
+    got_s = dec(zd, md, mud, 1)[pick].cpu()
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    with torch.no_grad():
+        ref_e = decoder_oracle.estimator_forward(sd, (z * mask)[pick], mask[pick], mu[pick], t[pick], None, 1)
+        ref_s = decoder_oracle.reverse_diffusion(sd, z[pick], mask[pick], mu[pick], 1, False, None, 1)
+    err_e = float((got_e - ref_e).abs().max())
+    rel_e = float((got_e - ref_e).pow(2).mean().sqrt() / ref_e.pow(2).mean().sqrt())
+    assert err_e <= tol_abs and rel_e <= tol_rel, (err_e, rel_e, float(ref_e.abs().max()))
+    # one Euler step with n_timesteps=1: h = 1, beta(0.5) = 10.0 -> the update is 5x the score error
+    err_s = float((got_s - ref_s).abs().max())
+    assert err_s <= 5.5 * tol_abs, (err_s, float(ref_s.abs().max()))
+    assert float((got_s * (1 - mask[pick])).abs().max()) == 0.0

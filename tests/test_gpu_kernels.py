@@ -11,11 +11,17 @@ def _gu():
     return gpu_util
 
 
+def _seed(name):
+    """Stable per-case seed (Python's hash() of a str is salted per process, which made failures unrepeatable)."""
+    import zlib
+    return zlib.crc32(name.encode()) % 1000
+
+
 @pytest.mark.parametrize("name,kw", gpu_util.CONV_CASES)
 @pytest.mark.parametrize("impl,act", [(0, 0), (0, 1), (1, 1)])
 def test_conv_variants(name, kw, impl, act):
     gu = _gu()
-    c = gu.conv_case(seed=hash(name) % 1000, **kw)
+    c = gu.conv_case(seed=_seed(name), **kw)
     stats_ok = c["kind"] in (0, 1) and c["r"] is None and c["m"] is None and not c["per_sample"]
     out, st = gu.run_conv(c, impl, act, want_stats=stats_ok)
     ref, raw = gu.conv_reference(c, round_bf16=bool(act))
@@ -43,7 +49,7 @@ def test_conv_halo(name, kw, impl, monkeypatch):
     """Halo-box tcgen05 kernel (resident or streamed weights, one or two tiles per weight pass) vs torch CPU."""
     monkeypatch.setenv("GTTS_HALO256", "1")          # Cout = 256 is opt-in (the per-tap kernel is faster there)
     gu = _gu()
-    c = gu.conv_case(seed=hash(name) % 1000, **kw)
+    c = gu.conv_case(seed=_seed(name), **kw)
     out, st = gu.run_conv(c, impl, 1, want_stats=True)
     ref, raw = gu.conv_reference(c, round_bf16=True)
     assert not torch.isnan(out).any(), "output has unwritten (NaN) entries"
@@ -67,7 +73,7 @@ def test_convT_halo(name, kw):
     """Transposed conv on the CTA-pair halo kernel (4 phases x 4 taps as views of one halo box) vs torch CPU and vs the
     per-tap kernel."""
     gu = _gu()
-    c = gu.conv_case(seed=hash(name) % 1000, **kw)
+    c = gu.conv_case(seed=_seed(name), **kw)
     out, _ = gu.run_conv(c, 3, 1)
     ref, _ = gu.conv_reference(c, round_bf16=True)
     assert not torch.isnan(out).any(), "output has unwritten (NaN) entries"

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN
+from conftest import GOLDEN, decoder_case_names, load_decoder_case
 from oracle import build_oracle, decoder_oracle, mas_oracle
 
 
@@ -14,8 +14,7 @@ def _load(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
 
 
-DEC = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-             if os.path.basename(p).startswith(("est_", "dec_")))
+DEC = decoder_case_names(("est_", "dec_", "c1", "c3"))      # c1*/c3*: BASELINE.json config shapes (C1: 1 x 400 x 10 steps, C3: n_spks=247, 800 frames)
 MAS = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "mas_*.npz")))
 
 
@@ -30,17 +29,16 @@ def golden_path(g, B, tx, ty):
 @pytest.mark.parametrize("name", DEC)
 def test_decoder_oracle_matches_reference(name, synth):
     torch.set_num_threads(8)
-    g = _load(name)
-    n_spks, n_steps = int(g["n_spks"]), int(g["n_steps"])
-    sd = synth.make_decoder_state_dict(n_spks, seed=int(g["wseed"]), g=0.05)
-    z, mask, mu = (torch.from_numpy(g[k]) for k in ("z", "mask", "mu"))
-    spk = torch.from_numpy(g["spk"]) if "spk" in g else None
+    g = load_decoder_case(name)
+    n_spks, n_steps = g["n_spks"], g["n_steps"]
+    sd = synth.make_decoder_state_dict(n_spks, seed=g["wseed"], g=0.05)
+    z, mask, mu, spk = g["z"], g["mask"], g["mu"], g["spk"]
     with torch.no_grad():
         if n_steps == 0:
-            y = decoder_oracle.estimator_forward(sd, z * mask, mask, mu, torch.from_numpy(g["t"]), spk, n_spks)
+            y = decoder_oracle.estimator_forward(sd, z * mask, mask, mu, g["t"], spk, n_spks)
         else:
             y = decoder_oracle.reverse_diffusion(sd, z, mask, mu, n_steps, True, spk, n_spks)
-    ref = torch.from_numpy(g["y"])
+    ref = g["y"]
     # same ATen kernels, same thread count: tolerance covers only op-order noise (|y|max up to ~140)
     tol = 2e-5 * max(1.0, float(ref.abs().max()))
     assert float((y - ref).abs().max()) <= tol
