@@ -32,6 +32,7 @@ SIGNATURES = {
     "gtts_decoder_reverse_diffusion_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
     "gtts_decoder_profile_step": (_i, [_vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "gtts_decoder_launches_last_call": (_l, [_vp]),
+    "gtts_decoder_cache_info": (_i, [_vp, _vp, _i]),
     "gtts_align_log_prior": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "gtts_align_outputs": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "gtts_score_loss_workspace_bytes": (_sz, []),

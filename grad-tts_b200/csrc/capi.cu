@@ -197,6 +197,11 @@ int gtts_decoder_profile_step(gtts_decoder* h, int B, int T, int flags, int reps
 
 long gtts_decoder_launches_last_call(const gtts_decoder* h) { return h ? decoder_launches_last_call(h->impl) : 0; }
 
+int gtts_decoder_cache_info(const gtts_decoder* h, long long* out, int n) {
+    GTTS_REQUIRE(h != nullptr, "null decoder handle");
+    return decoder_cache_info(h->impl, out, n);
+}
+
 // ------------------------------------------------------------------------------------------------ alignment stage
 int gtts_align_log_prior(const float* mu_x, const float* y, float* log_prior, int B, int n_feats, int t_x, int t_y, void* stream) {
     GTTS_REQUIRE(mu_x && y && log_prior, "null argument");

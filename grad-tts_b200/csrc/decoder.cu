@@ -50,16 +50,41 @@ __global__ void copy_cols_kernel(const float* src, float* dst, int rows, int col
 struct DevMem {
     std::vector<void*> ptrs;
     size_t total = 0;
+    // zeroing runs on the legacy default stream: whoever uses the buffer on another stream synchronises stream 0 first
+    // (plan_create does, before its dry run)
     void* alloc(size_t bytes, bool zero = false) {
         void* p = nullptr;
         if (bytes == 0) bytes = 16;
         if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-        if (zero) cudaMemset(p, 0, bytes);
+        if (zero) cudaMemsetAsync(p, 0, bytes, 0);
         ptrs.push_back(p);
         total += bytes;
         return p;
     }
     ~DevMem() { for (void* p : ptrs) cudaFree(p); }
+};
+
+// Workspace pool of one decoder.  Plans never run concurrently (calls on one handle are ordered, see enter_call), and nothing a
+// plan keeps in pooled memory outlives a call, so ALL plans draw their activation buffers from the same blocks: a new (B, T)
+// shape reuses the blocks of earlier shapes wherever they are large enough, and only descriptors + graph are rebuilt.
+// Sizes are rounded up to 1/8 of their power of two (<= 12.5 % slack) so that neighbouring T land in the same size classes.
+struct Pool {
+    struct Block { void* p; size_t bytes; };
+    std::vector<Block> blocks;
+    size_t total = 0;
+    static size_t round_size(size_t bytes) {
+        if (bytes < 4096) return 4096;
+        size_t p2 = 1;
+        while (p2 * 2 <= bytes) p2 *= 2;
+        const size_t gran = p2 / 8;
+        return (bytes + gran - 1) / gran * gran;
+    }
+    void clear() {
+        for (auto& b : blocks) cudaFree(b.p);
+        blocks.clear();
+        total = 0;
+    }
+    ~Pool() { clear(); }
 };
 
 const char* kResnetNames[12] = {"downs.0.0", "downs.0.1", "downs.1.0", "downs.1.1", "downs.2.0", "downs.2.1",
@@ -107,8 +132,18 @@ struct Decoder {
     std::map<std::string, size_t> param_numel;
     DevMem param_mem;
     std::unique_ptr<Packed> packed[2];
-    std::map<std::string, Plan*> plans;
+    struct CachedPlan { Plan* plan; unsigned long long last_use; };
+    std::map<std::string, CachedPlan> plans;
+    unsigned long long use_clock = 0;
+    int max_plans = 24;       // LRU bound on cached (descriptors + graph) plans; their activation memory is the shared pool
+    Pool pool;
+    // calls on one handle are ordered across streams: the event is recorded at the end of every call, and a call on a different
+    // stream waits for it (plans share the pool, and each plan's state buffers are reused from call to call)
+    cudaEvent_t done_ev = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool has_done = false;
     long launches_last_call = 0;
+    long plans_created = 0;
     ~Decoder();
 };
 
@@ -330,10 +365,11 @@ struct Plan {
     float *xt = nullptr, *mu = nullptr, *m0 = nullptr, *m1 = nullptr, *m2 = nullptr, *splane = nullptr, *spk = nullptr;
     float *tb = nullptr, *t_tab = nullptr, *beta_tab = nullptr, *t_per_sample = nullptr, *score = nullptr;
     int* step = nullptr;
-    const float** noise_slot = nullptr;
+    NoiseSlot* noise_slot = nullptr;
     float* h_dev = nullptr;
-    size_t noise_step_stride = 0;
     int max_steps = 4096;
+    size_t pooled_bytes = 0;      // peak of live pooled activation memory of this plan (after liveness reuse)
+    size_t unpooled_bytes = 0;    // what one-buffer-per-tensor allocation would have needed (reported for comparison)
     float* partials = nullptr;
     unsigned int* counters = nullptr;
     size_t partial_slots = 0;
@@ -347,7 +383,8 @@ struct Plan {
 };
 
 Decoder::~Decoder() {
-    for (auto& kv : plans) delete kv.second;
+    for (auto& kv : plans) delete kv.second.plan;
+    if (done_ev) cudaEventDestroy(done_ev);
 }
 
 namespace {
@@ -361,16 +398,50 @@ struct PlanBuilder {
     int B, T;
     int H[3], W[3];
     const float* lmask[3];
-    bool failed = false;
+    bool failed = false, oom = false;
+    std::vector<char> in_use;     // per pool block: live in THIS plan (other plans alias the same blocks)
+    size_t live_bytes = 0;
 
-    void* act(int lvl, int C) {
-        void* p = pl->mem.alloc((size_t)B * H[lvl] * W[lvl] * C * esize(kind));
-        if (!p) failed = true;
-        return p;
+    void fail_oom(size_t bytes) {
+        failed = true; oom = true;
+        set_error("out of device memory building the decoder plan for B=" + std::to_string(B) + ", T=" + std::to_string(T) +
+                  " (request of " + std::to_string(bytes >> 20) + " MiB on top of " + std::to_string(d->pool.total >> 20) +
+                  " MiB of pooled workspace); lower max_chunk or free device memory");
     }
+    // Liveness-based reuse: a buffer goes back to the free list (release) once its last consumer has been enqueued; all
+    // launches of a plan are ordered on one stream, so the next producer cannot overtake that consumer.
+    void* pooled(size_t bytes) {
+        const size_t want = Pool::round_size(bytes);
+        pl->unpooled_bytes += want;
+        auto& blocks = d->pool.blocks;
+        in_use.resize(blocks.size(), 0);
+        int best = -1;
+        for (int i = 0; i < (int)blocks.size(); ++i)
+            if (!in_use[i] && blocks[i].bytes >= want && blocks[i].bytes <= want + want / 2 &&
+                (best < 0 || blocks[i].bytes < blocks[best].bytes)) best = i;
+        if (best < 0) {
+            void* p = nullptr;
+            if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); fail_oom(want); return nullptr; }
+            blocks.push_back(Pool::Block{p, want});
+            d->pool.total += want;
+            in_use.push_back(0);
+            best = (int)blocks.size() - 1;
+        }
+        in_use[best] = 1;
+        live_bytes += blocks[best].bytes;
+        pl->pooled_bytes = std::max(pl->pooled_bytes, live_bytes);
+        return blocks[best].p;
+    }
+    void release(const void* p) {
+        if (!p) return;
+        auto& blocks = d->pool.blocks;
+        for (int i = 0; i < (int)blocks.size(); ++i)
+            if (blocks[i].p == p && in_use[i]) { in_use[i] = 0; live_bytes -= blocks[i].bytes; return; }
+    }
+    void* act(int lvl, int C) { return pooled((size_t)B * H[lvl] * W[lvl] * C * esize(kind)); }
     float* stats() {
         float* p = (float*)pl->mem.alloc((size_t)B * 16 * 4, true);
-        if (!p) failed = true;
+        if (!p) fail_oom((size_t)B * 64);
         return p;
     }
     bool use_tc() const { return kind == ACT_BF16 && d->conv_impl_bf16 == 1; }
@@ -448,7 +519,9 @@ struct PlanBuilder {
         const ResnetW& R = P->res[r];
         const int Co = R.cout;
         const float* tb = pl->tb + R.tb_off;
-        void* raw1 = act(lvl, Co); void* a1 = act(lvl, Co); void* raw2 = act(lvl, Co); void* out = act(lvl, Co);
+        const ConvGeom g2 = geom_3x3(B, H[lvl], W[lvl], Co, 0, Co, 1);
+        const bool fuse2 = can_fuse_input(g2);           // block2's conv applies block1's GroupNorm+Mish itself: no a1 tensor
+        void* raw1 = act(lvl, Co); void* a1 = fuse2 ? nullptr : act(lvl, Co); void* raw2 = act(lvl, Co); void* out = act(lvl, Co);
         float* st1 = stats(); float* st2 = stats();
         if (failed) return nullptr;
         if (r == 0) {
@@ -465,8 +538,7 @@ struct PlanBuilder {
         } else {
             add_conv(geom_3x3(B, H[lvl], W[lvl], c0, c1, Co, 1), x0, x1, R.b1.w, 9 * Co, R.b1.bias, nullptr, nullptr, raw1, st1);
         }
-        const ConvGeom g2 = geom_3x3(B, H[lvl], W[lvl], Co, 0, Co, 1);
-        if (can_fuse_input(g2)) {
+        if (fuse2) {
             // block1's GroupNorm + Mish + time bias + mask are applied by block2's conv on its operand tiles
             InFuse fz{st1, R.b1.gamma, R.b1.beta, tb, pl->est_mode ? 1792 : 0, lmask[lvl]};
             add_conv(g2, raw1, nullptr, R.b2.w, 9 * Co, R.b2.bias, nullptr, nullptr, raw2, st2, &fz);
@@ -486,6 +558,8 @@ struct PlanBuilder {
             resid = x0;                                   // Identity(x * mask): x is stored masked
         }
         add_gn_apply(lvl, Co, raw2, st2, R.b2, nullptr, resid, first_res, out);
+        release(raw1); release(a1); release(raw2);
+        if (resid != x0) release(resid);
         return out;
     }
 
@@ -527,6 +601,7 @@ struct PlanBuilder {
         pl->push("attn_fold_" + std::to_string(C), 0, 2.0 * B * ((double)C * 128 * 32 + (double)C * C * 128), 0.0,
                  [k, ctxn, wout, wq, g, mb, Bb, C](cudaStream_t s) { return attn_fold(k, ctxn, wout, wq, g, mb, Bb, C, s); });
         add_conv(geom_1x1(B, H[lvl], W[lvl], C, 0, C, C), x, nullptr, mb, B * C, A.gb, x, lmask[lvl], out, nullptr);
+        release(ca.kv);
         return out;
     }
 
@@ -549,9 +624,9 @@ struct PlanBuilder {
         H[0] = d->n_feats; W[0] = T; H[1] = H[0] / 2; W[1] = T / 2; H[2] = H[0] / 4; W[2] = T / 4;
         // plan-owned state
         const size_t plane = (size_t)B * H[0] * T;
-        pl->xt = (float*)pl->mem.alloc(plane * 4);
-        pl->mu = (float*)pl->mem.alloc(plane * 4);
-        pl->score = (float*)pl->mem.alloc(plane * 4);
+        pl->xt = (float*)pooled(plane * 4);              // rewritten at the start of every call, like mu and the masks
+        pl->mu = (float*)pooled(plane * 4);
+        pl->score = (float*)pooled(plane * 4);
         pl->m0 = (float*)pl->mem.alloc((size_t)B * T * 4);
         pl->m1 = (float*)pl->mem.alloc((size_t)B * T / 2 * 4);
         pl->m2 = (float*)pl->mem.alloc((size_t)B * T / 4 * 4);
@@ -562,7 +637,7 @@ struct PlanBuilder {
         pl->beta_tab = (float*)pl->mem.alloc(pl->max_steps * 4, true);
         pl->t_per_sample = (float*)pl->mem.alloc((size_t)B * 4, true);
         pl->step = (int*)pl->mem.alloc(16, true);
-        pl->noise_slot = (const float**)pl->mem.alloc(16, true);
+        pl->noise_slot = (NoiseSlot*)pl->mem.alloc(sizeof(NoiseSlot), true);
         pl->h_dev = (float*)pl->mem.alloc(16, true);
         pl->counters = (unsigned int*)pl->mem.alloc((size_t)(B + 32) * 4, true);   // per-sample tickets or 1 + 16 group tickets
         // GN partial buffer: the largest slot count of any conv (level 0, either tiling)
@@ -580,8 +655,9 @@ struct PlanBuilder {
             pl->partial_slots = std::max(s, std::max(s2, s3));
             pl->partials = (float*)pl->mem.alloc((size_t)B * pl->partial_slots * 16 * 4);
         }
-        if (!pl->xt || !pl->mu || !pl->score || !pl->m0 || !pl->m1 || !pl->m2 || !pl->partials) {
-            set_error("out of device memory building the decoder plan");
+        if (failed) return 4;
+        if (!pl->m0 || !pl->m1 || !pl->m2 || !pl->partials || !pl->counters || !pl->tb) {
+            fail_oom((size_t)B * pl->partial_slots * 64);
             return 4;
         }
         lmask[0] = pl->m0; lmask[1] = pl->m1; lmask[2] = pl->m2;
@@ -600,34 +676,40 @@ struct PlanBuilder {
                 return temb_bias(tw, tsrc, step, is_table, pes, tb, nb, st_, s);
             });
         }
-        // ---- U-Net (:189-211)
+        // ---- U-Net (:189-211).  `next(y)` makes y the running activation and frees the previous one unless a skip keeps it.
         void* x = nullptr;
         void* skip[3] = {nullptr, nullptr, nullptr};
-        x = resnet(0, 0, nullptr, 0, nullptr, 0);
-        x = failed ? nullptr : resnet(1, 0, x, 64, nullptr, 0);
-        x = failed ? nullptr : attention(0, 0, x);
-        skip[0] = x;
-        x = failed ? nullptr : downsample(0, 0, x);
-        x = failed ? nullptr : resnet(2, 1, x, 64, nullptr, 0);
-        x = failed ? nullptr : resnet(3, 1, x, 128, nullptr, 0);
-        x = failed ? nullptr : attention(1, 1, x);
+        auto next = [&](void* y, bool keep_prev = false) {
+            if (!keep_prev) release(x);
+            x = y;
+        };
+        next(resnet(0, 0, nullptr, 0, nullptr, 0));
+        if (!failed) next(resnet(1, 0, x, 64, nullptr, 0));
+        if (!failed) next(attention(0, 0, x));
+        skip[0] = x;                                         // hiddens[0]: stored by the reference but never consumed (two up stages)
+        if (!failed) next(downsample(0, 0, x));
+        if (!failed) next(resnet(2, 1, x, 64, nullptr, 0));
+        if (!failed) next(resnet(3, 1, x, 128, nullptr, 0));
+        if (!failed) next(attention(1, 1, x));
         skip[1] = x;
-        x = failed ? nullptr : downsample(1, 1, x);
-        x = failed ? nullptr : resnet(4, 2, x, 128, nullptr, 0);
-        x = failed ? nullptr : resnet(5, 2, x, 256, nullptr, 0);
-        x = failed ? nullptr : attention(2, 2, x);
+        if (!failed) next(downsample(1, 1, x), true);
+        if (!failed) next(resnet(4, 2, x, 128, nullptr, 0));
+        if (!failed) next(resnet(5, 2, x, 256, nullptr, 0));
+        if (!failed) next(attention(2, 2, x));
         skip[2] = x;                                         // downs.2.3 = Identity (:158)
-        x = failed ? nullptr : resnet(6, 2, x, 256, nullptr, 0);
-        x = failed ? nullptr : attention(3, 2, x);
-        x = failed ? nullptr : resnet(7, 2, x, 256, nullptr, 0);
-        x = failed ? nullptr : resnet(8, 2, x, 256, skip[2], 256);   // cat((x, hiddens.pop()), 1) (:207)
-        x = failed ? nullptr : resnet(9, 2, x, 128, nullptr, 0);
-        x = failed ? nullptr : attention(4, 2, x);
-        x = failed ? nullptr : upsample(0, 2, x);
-        x = failed ? nullptr : resnet(10, 1, x, 128, skip[1], 128);
-        x = failed ? nullptr : resnet(11, 1, x, 64, nullptr, 0);
-        x = failed ? nullptr : attention(5, 1, x);
-        x = failed ? nullptr : upsample(1, 1, x);
+        if (!failed) next(resnet(6, 2, x, 256, nullptr, 0), true);
+        if (!failed) next(attention(3, 2, x));
+        if (!failed) next(resnet(7, 2, x, 256, nullptr, 0));
+        if (!failed) next(resnet(8, 2, x, 256, skip[2], 256));   // cat((x, hiddens.pop()), 1) (:207)
+        release(skip[2]);
+        if (!failed) next(resnet(9, 2, x, 128, nullptr, 0));
+        if (!failed) next(attention(4, 2, x));
+        if (!failed) next(upsample(0, 2, x));
+        if (!failed) next(resnet(10, 1, x, 128, skip[1], 128));
+        release(skip[1]);
+        if (!failed) next(resnet(11, 1, x, 64, nullptr, 0));
+        if (!failed) next(attention(5, 1, x));
+        if (!failed) next(upsample(1, 1, x));
         // ---- final block + final conv + Euler update (:212-216, 265-267)
         void* rawf = failed ? nullptr : act(0, 64);
         float* stf = failed ? nullptr : stats();
@@ -641,18 +723,13 @@ struct PlanBuilder {
             e.wf = P->wf; e.bf = P->bf; e.mask = pl->m0; e.mu = pl->mu; e.xt = pl->xt;
             e.score_out = pl->est_mode ? pl->score : nullptr;
             e.beta_tab = pl->beta_tab; e.step = pl->step; e.h_ptr = pl->h_dev;
-            e.noise_slot = pl->noise_slot; e.noise_step_stride = 0; e.sde = pl->sde ? 1 : 0;
+            e.noise_slot = pl->noise_slot; e.sde = pl->sde ? 1 : 0;
             e.update = pl->est_mode ? 0 : 1;
             e.B = B; e.H = H[0]; e.W = W[0];
-            Plan* plan = pl;
             ActKind k = kind;
             bool st_ = strict;
             const double px = (double)B * H[0] * W[0];
-            pl->push("euler_step", 0, 0.0, px * (64 * esize(kind) + 12), [k, e, st_, plan](cudaStream_t s) {
-                EulerArgs ee = e;
-                ee.noise_step_stride = plan->noise_step_stride;
-                return euler_step(k, ee, st_, s);
-            });
+            pl->push("euler_step", 0, 0.0, px * (64 * esize(kind) + 12), [k, e, st_](cudaStream_t s) { return euler_step(k, e, st_, s); });
             int* step = pl->step;
             pl->push("advance_step", 0, 0.0, 0.0, [step](cudaStream_t s) { return advance_step(step, s); });
         }
@@ -671,11 +748,9 @@ int plan_create(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde,
     pb.B = B; pb.T = T;
     int rc = pb.build();
     if (rc == 0 && pb.failed) rc = 5;
-    if (rc) {
-        if (pb.failed && cudaPeekAtLastError() == cudaSuccess) { /* error string already set */ }
-        return rc;
-    }
+    if (rc) return pb.oom ? 4 : rc;                  // 4 = out of device memory (get_plan drops cached plans + pool and retries)
     // ---- dry run on zeroed state (validates every launch), then capture the step as a CUDA graph
+    GTTS_CHECK_CUDA(cudaStreamSynchronize(0));       // the zero-fills of the plan-owned buffers ran on the legacy stream
     cudaStream_t cs;
     GTTS_CHECK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
     auto run_ops = [&](cudaStream_t s) -> int {
@@ -691,7 +766,7 @@ int plan_create(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde,
     schedule_kernel<<<1, 32, 0, cs>>>(pl->t_tab, pl->beta_tab, pl->h_dev, 1, d->beta_min, d->beta_max);
     {
         // point the SDE noise slot at something readable for the dry run
-        const float* dummy = pl->score;
+        const NoiseSlot dummy{pl->score, 0ull};
         GTTS_CHECK_CUDA(cudaMemcpyAsync((void*)pl->noise_slot, &dummy, sizeof(dummy), cudaMemcpyHostToDevice, cs));
     }
     rc = run_ops(cs);
@@ -723,21 +798,60 @@ int plan_create(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde,
     return 0;
 }
 
-int get_plan(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, Plan** out) {
+void drop_plans(Decoder* d, bool drop_pool) {
+    cudaDeviceSynchronize();                         // nothing may still be running out of the memory about to be freed
+    for (auto& kv : d->plans) delete kv.second.plan;
+    d->plans.clear();
+    if (drop_pool) d->pool.clear();
+}
+
+int get_plan(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, cudaStream_t stream, Plan** out) {
     std::string key = std::to_string((int)kind) + ":" + std::to_string(B) + ":" + std::to_string(T) + ":" +
                       (est_mode ? "e" : "s") + (sde ? "n" : "o") + (d->use_graph ? "g" : "x") +
                       std::to_string(d->conv_impl_bf16) + std::to_string(d->halo_mode) + std::to_string(d->fused_attn) + std::to_string(d->fuse_gn);
     auto it = d->plans.find(key);
-    if (it != d->plans.end()) { *out = it->second; return 0; }
-    // keep at most a handful of plans alive (each owns its workspace)
-    if (d->plans.size() >= 6) {
-        for (auto& kv : d->plans) delete kv.second;
-        d->plans.clear();
+    if (it != d->plans.end()) {
+        it->second.last_use = ++d->use_clock;
+        *out = it->second.plan;
+        return 0;
+    }
+    // Slow path.  The new plan's dry run writes into pool blocks that launches already queued by this call (an earlier chunk)
+    // or by an earlier call may still be using: wait for them.
+    GTTS_CHECK_CUDA(cudaStreamSynchronize(stream));
+    if (d->has_done) GTTS_CHECK_CUDA(cudaEventSynchronize(d->done_ev));
+    // LRU bound on the number of cached plans (descriptors + graph; the activation memory is the shared pool)
+    while ((int)d->plans.size() >= std::max(1, d->max_plans)) {
+        auto lru = d->plans.begin();
+        for (auto j = d->plans.begin(); j != d->plans.end(); ++j)
+            if (j->second.last_use < lru->second.last_use) lru = j;
+        delete lru->second.plan;
+        d->plans.erase(lru);
     }
     Plan* pl = nullptr;
-    if (int rc = plan_create(d, kind, B, T, est_mode, sde, &pl)) return rc;
-    d->plans[key] = pl;
+    int rc = plan_create(d, kind, B, T, est_mode, sde, &pl);
+    if (rc == 4) {
+        // out of device memory: give back everything this handle caches (all plans and the whole pool) and try once more
+        drop_plans(d, true);
+        rc = plan_create(d, kind, B, T, est_mode, sde, &pl);
+    }
+    if (rc) return rc;
+    d->plans_created++;
+    d->plans[key] = Decoder::CachedPlan{pl, ++d->use_clock};
     *out = pl;
+    return 0;
+}
+
+// Calls on one handle are ordered even when they arrive on different streams (plans share pooled workspace and keep per-call
+// state): a call waits for the event the previous call recorded, unless it runs on the same stream.
+int enter_call(Decoder* d, cudaStream_t stream) {
+    GTTS_CHECK_CUDA(cudaSetDevice(d->device));
+    if (d->has_done && d->last_stream != stream) GTTS_CHECK_CUDA(cudaStreamWaitEvent(stream, d->done_ev, 0));
+    return 0;
+}
+int leave_call(Decoder* d, cudaStream_t stream) {
+    GTTS_CHECK_CUDA(cudaEventRecord(d->done_ev, stream));
+    d->last_stream = stream;
+    d->has_done = true;
     return 0;
 }
 
@@ -769,14 +883,14 @@ int decoder_reverse_diffusion(Decoder* d, const float* z, const float* mask, con
     GTTS_REQUIRE(n_timesteps >= 1 && n_timesteps <= 4096, "n_timesteps must be in [1, 4096]");
     const bool sde = (flags & 2) != 0;
     GTTS_REQUIRE(!sde || noise != nullptr, "SDE update requested without a noise tensor");
-    GTTS_CHECK_CUDA(cudaSetDevice(d->device));
+    if (int rc = enter_call(d, stream)) return rc;
     const ActKind kind = (flags & 1) ? ACT_F32 : ACT_BF16;
     const size_t plane = (size_t)d->n_feats * T;
     d->launches_last_call = 0;
     for (int b0 = 0; b0 < B; b0 += d->max_chunk) {
         const int Bc = std::min(d->max_chunk, B - b0);
         Plan* pl = nullptr;
-        if (int rc = get_plan(d, kind, Bc, T, false, sde, &pl)) return rc;
+        if (int rc = get_plan(d, kind, Bc, T, false, sde, stream, &pl)) return rc;
         Packed* P = d->packed[kind].get();
         if (int rc = build_level_masks(mask + (size_t)b0 * T, pl->m0, pl->m1, pl->m2, Bc, T, stream)) return rc;
         GTTS_CHECK_CUDA(cudaMemcpyAsync(pl->mu, mu + b0 * plane, Bc * plane * 4, cudaMemcpyDeviceToDevice, stream));
@@ -788,40 +902,30 @@ int decoder_reverse_diffusion(Decoder* d, const float* z, const float* mask, con
                                                                       d->beta_min, d->beta_max);
         GTTS_CHECK_CUDA(cudaMemsetAsync(pl->step, 0, 4, stream));
         if (sde) {
-            const float* nb = noise + b0 * plane;
-            pl->noise_step_stride = (size_t)B * plane;
-            GTTS_CHECK_CUDA(cudaMemcpyAsync((void*)pl->noise_slot, &nb, sizeof(nb), cudaMemcpyHostToDevice, stream));
-            if (pl->graph_exec) {
-                // the stride is baked into the captured Euler node: SDE mode replays eagerly instead
-                for (int i = 0; i < n_timesteps; ++i)
-                    for (auto& op : pl->ops)
-                        if (int r = op(stream)) return r;
-            } else {
-                for (int i = 0; i < n_timesteps; ++i)
-                    if (int rc = plan_step(pl, stream)) return rc;
-            }
-        } else {
-            for (int i = 0; i < n_timesteps; ++i)
-                if (int rc = plan_step(pl, stream)) return rc;
+            // base of this chunk's noise and the stride between Euler steps go to device memory: the captured graph reads them
+            const NoiseSlot ns{noise + b0 * plane, (unsigned long long)((size_t)B * plane)};
+            GTTS_CHECK_CUDA(cudaMemcpyAsync((void*)pl->noise_slot, &ns, sizeof(ns), cudaMemcpyHostToDevice, stream));
         }
+        for (int i = 0; i < n_timesteps; ++i)
+            if (int rc = plan_step(pl, stream)) return rc;
         GTTS_CHECK_CUDA(cudaMemcpyAsync(out + b0 * plane, pl->xt, Bc * plane * 4, cudaMemcpyDeviceToDevice, stream));
         d->launches_last_call += pl->kernels_per_step * n_timesteps + 5;
     }
     GTTS_CHECK_CUDA(cudaGetLastError());
-    return 0;
+    return leave_call(d, stream);
 }
 
 int decoder_estimator(Decoder* d, const float* x, const float* mask, const float* mu, const float* t, const float* spk,
                       float* out, int B, int T, int flags, cudaStream_t stream) {
     if (int rc = common_checks(d, B, T, spk)) return rc;
-    GTTS_CHECK_CUDA(cudaSetDevice(d->device));
+    if (int rc = enter_call(d, stream)) return rc;
     const ActKind kind = (flags & 1) ? ACT_F32 : ACT_BF16;
     const size_t plane = (size_t)d->n_feats * T;
     d->launches_last_call = 0;
     for (int b0 = 0; b0 < B; b0 += d->max_chunk) {
         const int Bc = std::min(d->max_chunk, B - b0);
         Plan* pl = nullptr;
-        if (int rc = get_plan(d, kind, Bc, T, true, false, &pl)) return rc;
+        if (int rc = get_plan(d, kind, Bc, T, true, false, stream, &pl)) return rc;
         Packed* P = d->packed[kind].get();
         if (int rc = build_level_masks(mask + (size_t)b0 * T, pl->m0, pl->m1, pl->m2, Bc, T, stream)) return rc;
         GTTS_CHECK_CUDA(cudaMemcpyAsync(pl->mu, mu + b0 * plane, Bc * plane * 4, cudaMemcpyDeviceToDevice, stream));
@@ -836,7 +940,7 @@ int decoder_estimator(Decoder* d, const float* x, const float* mask, const float
         d->launches_last_call += pl->kernels_per_step + 3;
     }
     GTTS_CHECK_CUDA(cudaGetLastError());
-    return 0;
+    return leave_call(d, stream);
 }
 
 // Runs one step of the cached sampler plan for (B<=max_chunk, T) eagerly, `reps` times, with a CUDA event pair
@@ -846,8 +950,9 @@ int decoder_profile_step(Decoder* d, int B, int T, int flags, int reps, char* bu
     GTTS_REQUIRE(buf != nullptr && buflen > 64 && reps >= 1, "profile: bad arguments");
     const ActKind kind = (flags & 1) ? ACT_F32 : ACT_BF16;
     const int Bc = std::min(d->max_chunk, B);
+    if (int rc = enter_call(d, stream)) return rc;
     Plan* pl = nullptr;
-    if (int rc = get_plan(d, kind, Bc, T, false, false, &pl)) return rc;
+    if (int rc = get_plan(d, kind, Bc, T, false, false, stream, &pl)) return rc;
     const size_t nops = pl->ops.size();
     std::vector<cudaEvent_t> ev(2 * nops);
     for (auto& e : ev) GTTS_CHECK_CUDA(cudaEventCreate(&e));
@@ -866,7 +971,11 @@ int decoder_profile_step(Decoder* d, int B, int T, int flags, int reps, char* bu
         }
     }
     for (auto& e : ev) cudaEventDestroy(e);
-    std::string js = "{\"B\":" + std::to_string(Bc) + ",\"T\":" + std::to_string(T) + ",\"ops\":[";
+    std::string js = "{\"B\":" + std::to_string(Bc) + ",\"T\":" + std::to_string(T) +
+                     ",\"workspace_bytes\":" + std::to_string(pl->pooled_bytes + pl->mem.total) +
+                     ",\"workspace_bytes_without_reuse\":" + std::to_string(pl->unpooled_bytes + pl->mem.total) +
+                     ",\"pool_bytes\":" + std::to_string(d->pool.total) + ",\"plans_cached\":" + std::to_string(d->plans.size()) +
+                     ",\"plans_created\":" + std::to_string(d->plans_created) + ",\"ops\":[";
     for (size_t i = 0; i < nops; ++i) {
         char tmp[512];
         snprintf(tmp, sizeof(tmp), "%s{\"name\":\"%s\",\"is_conv\":%d,\"flops\":%.6e,\"bytes\":%.6e,\"ms\":%.6f}",
@@ -876,7 +985,7 @@ int decoder_profile_step(Decoder* d, int B, int T, int flags, int reps, char* bu
     js += "]}";
     GTTS_REQUIRE(js.size() + 1 <= buflen, "profile: report buffer too small");
     memcpy(buf, js.c_str(), js.size() + 1);
-    return 0;
+    return leave_call(d, stream);
 }
 
 Decoder* decoder_new(int n_spks, int n_feats, int dim, double beta_min, double beta_max, double pe_scale, int device) {
@@ -892,6 +1001,9 @@ Decoder* decoder_new(int n_spks, int n_feats, int dim, double beta_min, double b
     d->n_feats = n_feats; d->dim = dim;
     d->beta_min = beta_min; d->beta_max = beta_max; d->pe_scale = pe_scale;
     d->device = device; d->num_sms = prop.multiProcessorCount;
+    if (cudaEventCreateWithFlags(&d->done_ev, cudaEventDisableTiming) != cudaSuccess) {
+        set_error("cudaEventCreate failed"); cudaGetLastError(); delete d; return nullptr;
+    }
     return d;
 }
 
@@ -909,12 +1021,16 @@ int decoder_set_param(Decoder* d, const char* name, const float* data, size_t nu
         d->params[n] = dst;
         d->param_numel[n] = numel;
     }
-    GTTS_CHECK_CUDA(cudaMemcpy(dst, data, numel * 4, cudaMemcpyDefault));
-    // any packed weights / plans built from the old values are stale
-    d->packed[0].reset();
-    d->packed[1].reset();
-    for (auto& kv : d->plans) delete kv.second;
-    d->plans.clear();
+    // any packed weights / plans built from the old values are stale; nothing may still be running from them
+    if (!d->plans.empty() || d->packed[0] || d->packed[1]) {
+        drop_plans(d, false);
+        d->packed[0].reset();
+        d->packed[1].reset();
+    }
+    // Ordered on the legacy stream, which pack_weights synchronises before anything reads the parameters.  The SOURCE must be
+    // complete when this is called: the Python host synchronises the producing stream before uploading (model/diffusion.py).
+    GTTS_CHECK_CUDA(cudaMemcpyAsync(dst, data, numel * 4, cudaMemcpyDefault, 0));
+    GTTS_CHECK_CUDA(cudaStreamSynchronize(0));        // `data` (host or device) may be released by the caller on return
     return 0;
 }
 
@@ -924,6 +1040,8 @@ int decoder_set_option(Decoder* d, const char* key, int value) {
     GTTS_REQUIRE(d != nullptr && key != nullptr, "null argument");
     std::string k(key);
     if (k == "max_chunk") { GTTS_REQUIRE(value >= 1 && value <= 64, "max_chunk must be in [1, 64]"); d->max_chunk = value; }
+    else if (k == "max_plans") { GTTS_REQUIRE(value >= 1, "max_plans must be >= 1"); d->max_plans = value; }
+    else if (k == "trim") drop_plans(d, true);                  // give back every cached plan and the pooled workspace
     else if (k == "use_graph") d->use_graph = value != 0;
     else if (k == "conv_impl_bf16") d->conv_impl_bf16 = value;
     else if (k == "halo_mode") d->halo_mode = value;
@@ -934,6 +1052,20 @@ int decoder_set_option(Decoder* d, const char* key, int value) {
 }
 
 long decoder_launches_last_call(const Decoder* d) { return d ? d->launches_last_call : 0; }
+
+// out[0] plans cached, [1] plans created since the handle exists, [2] pooled workspace bytes, [3] largest per-plan live
+// workspace (pooled peak + plan-owned), [4] what that plan would need with one buffer per tensor
+int decoder_cache_info(const Decoder* d, long long* out, int n) {
+    GTTS_REQUIRE(d != nullptr && out != nullptr && n >= 5, "cache_info: bad arguments");
+    long long live = 0, flat = 0;
+    for (auto& kv : d->plans) {
+        const Plan* p = kv.second.plan;
+        const long long l = (long long)(p->pooled_bytes + p->mem.total);
+        if (l > live) { live = l; flat = (long long)(p->unpooled_bytes + p->mem.total); }
+    }
+    out[0] = (long long)d->plans.size(); out[1] = d->plans_created; out[2] = (long long)d->pool.total; out[3] = live; out[4] = flat;
+    return 0;
+}
 int decoder_device(const Decoder* d) { return d ? d->device : -1; }
 
 }  // namespace gtts

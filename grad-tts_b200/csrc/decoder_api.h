@@ -16,5 +16,6 @@ int decoder_estimator(Decoder* d, const float* x, const float* mask, const float
                       float* out, int B, int T, int flags, cudaStream_t stream);
 int decoder_profile_step(Decoder* d, int B, int T, int flags, int reps, char* buf, size_t buflen, cudaStream_t stream);
 long decoder_launches_last_call(const Decoder* d);
+int decoder_cache_info(const Decoder* d, long long* out, int n);
 int decoder_device(const Decoder* d);
 }  // namespace gtts

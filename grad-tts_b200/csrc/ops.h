@@ -123,6 +123,10 @@ struct GnApplyArgs {
 };
 int gn_apply(ActKind act, const GnApplyArgs& a, bool strict, cudaStream_t s);
 
+// SDE extension: base pointer and per-step stride of the caller's noise tensor [n_timesteps][B][80][T], kept in DEVICE memory so
+// that the captured Euler node does not bake either in (the same graph serves every call and every chunk offset).
+struct NoiseSlot { const float* base; unsigned long long step_stride; };
+
 // final Block's norm/act + final 1x1 conv + masks + Euler update  (diffusion.py:212-216, 259-267)
 struct EulerArgs {
     const void* raw; const float* stats; const float* gamma; const float* beta;   // final_block conv output
@@ -131,7 +135,7 @@ struct EulerArgs {
     const float* mu; float* xt;                                                   // (B,80,T) fp32, xt updated
     float* score_out;                                                             // (B,80,T) or null
     const float* beta_tab; const int* step; const float* h_ptr;                   // beta_t per step, step index, h
-    const float* const* noise_slot; size_t noise_step_stride; int sde;            // SDE extension (noise base via slot)
+    const NoiseSlot* noise_slot; int sde;                                         // SDE extension (noise base + stride via slot)
     int update;                                                                   // 0: only write score
     int B, H, W;
 };

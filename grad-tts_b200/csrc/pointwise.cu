@@ -533,8 +533,10 @@ euler_kernel(EulerArgs a) {
     const float beta_t = a.update ? a.beta_tab[*a.step] : 0.f;
     const float hh = a.update ? *a.h_ptr : 0.f;
     float noise_v = 0.f;
-    if (a.update && a.sde && mypix < npix)
-        noise_v = (*a.noise_slot)[(size_t)(*a.step) * a.noise_step_stride + mypix];
+    if (a.update && a.sde && mypix < npix) {
+        const NoiseSlot ns = *a.noise_slot;
+        noise_v = ns.base[(size_t)(*a.step) * (size_t)ns.step_stride + mypix];
+    }
 #pragma unroll
     for (int k = 0; k < kEuPix; ++k) {
         const bool valid = pbase + k < npix;
@@ -582,10 +584,13 @@ euler_kernel(EulerArgs a) {
             d = __fmul_rn(__fmul_rn(d, beta_t), hh);
             nx = __fmul_rn(__fsub_rn(xt, d), m);
         } else {
-            // north-star SDE form (upstream Grad-TTS): x - (0.5*(mu-x) - score)*beta*h + sqrt(beta*h)*z
+            // upstream Grad-TTS stochastic branch (huawei-noah, deleted in this fork), same operation order:
+            //   dxt_det = (0.5*(mu - xt) - est) * noise_t * h ; dxt_stoc = z * sqrt(noise_t * h) ; xt = (xt - (dxt_det + dxt_stoc)) * mask
+            // i.e. the noise is SUBTRACTED.  BASELINE.json's north-star line writes "+ sqrt(beta*h)*z": the same process with -z
+            // (negation is exact), so a caller who wants that literal form passes -noise.
             float d = __fsub_rn(__fmul_rn(0.5f, __fsub_rn(mu, xt)), score);
             d = __fmul_rn(__fmul_rn(d, beta_t), hh);
-            d = __fsub_rn(d, __fmul_rn(sqrtf(__fmul_rn(beta_t, hh)), noise_v));
+            d = __fadd_rn(d, __fmul_rn(noise_v, sqrtf(__fmul_rn(beta_t, hh))));
             nx = __fmul_rn(__fsub_rn(xt, d), m);
         }
         a.xt[pix] = nx;

@@ -73,10 +73,19 @@ class GradLogPEstimator2d(BaseModule):
         self._handle = None
         self._handle_key = None
         self._uploaded = None
+        self._plist = None
+        self._opts = {}
 
     # ---- handle management -------------------------------------------------------------------------
     def _param_signature(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        # flat list cached: walking the module tree (176 tensors) on every forward cost more than the C call at batch 1
+        if self._plist is None:
+            self._plist = list(self.parameters())
+        return tuple((p.data_ptr(), p._version) for p in self._plist)
+
+    def _apply(self, fn, *a, **k):          # .to() / .cuda() / .float() may replace the Parameter objects
+        self._plist = None
+        return super()._apply(fn, *a, **k)
 
     def _get_handle(self):
         lib = _lib.load()
@@ -90,9 +99,12 @@ class GradLogPEstimator2d(BaseModule):
             rc = lib.gtts_decoder_create(ctypes.byref(h), int(self.n_spks), int(self.n_feats), int(self.dim),
                                          float(self.beta_min), float(self.beta_max), float(self.pe_scale), dev)
             _lib.check(rc, "decoder_create")
-            self._handle, self._handle_key, self._uploaded = h, key, None
+            self._handle, self._handle_key, self._uploaded, self._opts = h, key, None, {}
         sig = self._param_signature()
         if self._uploaded != sig:
+            # the parameters may have been produced on a side stream (optimizer step, .to() under torch.cuda.stream):
+            # the upload below is ordered on the library's legacy stream only, so finish the producer first
+            torch.cuda.current_stream(p0.device).synchronize()
             for name, p in self.named_parameters():
                 t = p.detach()
                 if t.dtype != torch.float32 or not t.is_contiguous():
@@ -100,8 +112,15 @@ class GradLogPEstimator2d(BaseModule):
                 rc = lib.gtts_decoder_set_param(self._handle, ("estimator." + name).encode(), t.data_ptr(), t.numel())
                 _lib.check(rc, f"decoder_set_param({name})")
             self._uploaded = sig
-        _lib.check(lib.gtts_decoder_set_option(self._handle, b"max_chunk", int(self.max_chunk)), "set_option")
+        if self._opts.get("max_chunk") != int(self.max_chunk):
+            _lib.check(lib.gtts_decoder_set_option(self._handle, b"max_chunk", int(self.max_chunk)), "set_option")
+            self._opts["max_chunk"] = int(self.max_chunk)
         return self._handle
+
+    def set_option(self, key, value):
+        """Library option on this module's native handle (include/gradtts_b200.h: gtts_decoder_set_option)."""
+        h = self._get_handle()
+        _lib.check(_lib.load().gtts_decoder_set_option(h, key.encode(), int(value)), f"set_option({key})")
 
     def _release(self):
         if getattr(self, "_handle", None) is not None:
@@ -116,7 +135,7 @@ class GradLogPEstimator2d(BaseModule):
 
     def __getstate__(self):
         d = self.__dict__.copy()          # the native handle is per-process: never pickled / deep-copied
-        d["_handle"], d["_handle_key"], d["_uploaded"] = None, None, None
+        d["_handle"], d["_handle_key"], d["_uploaded"], d["_plist"], d["_opts"] = None, None, None, None, {}
         return d
 
     def _flags(self):
@@ -167,6 +186,15 @@ class GradLogPEstimator2d(BaseModule):
         _lib.check(rc, "estimator")
         return out.to(x.dtype)
 
+    def cache_info(self):
+        """Workspace bookkeeping of the native handle (gtts_decoder_cache_info)."""
+        if self._handle is None:
+            return {}
+        a = (ctypes.c_longlong * 5)()
+        _lib.check(_lib.load().gtts_decoder_cache_info(self._handle, a, 5), "cache_info")
+        return dict(plans_cached=int(a[0]), plans_created=int(a[1]), pool_bytes=int(a[2]), plan_workspace_bytes=int(a[3]),
+                    plan_workspace_bytes_without_reuse=int(a[4]))
+
     def launches_last_call(self):
         return int(_lib.load().gtts_decoder_launches_last_call(self._handle)) if self._handle is not None else 0
 
@@ -207,8 +235,10 @@ class Diffusion(BaseModule):
         """N Euler steps of the reverse ODE (model/diffusion.py:254-268).
 
         `stoc` is accepted and ignored, exactly like the reference fork (it never reads the flag).
-        `sde_noise` (n_timesteps, B, 80, T) is an extension that switches on the upstream SDE update
-        x <- x - (0.5*(mu-x) - score)*beta*h + sqrt(beta*h)*noise with caller-supplied noise.
+        `sde_noise` (n_timesteps, B, 80, T) is an extension that switches on the upstream (huawei-noah Grad-TTS) stochastic
+        branch this fork deleted, with caller-supplied noise in place of its torch.randn draw:
+        x <- (x - ((0.5*(mu-x) - score)*beta*h + noise*sqrt(beta*h))) * mask   (the noise is subtracted, as upstream does;
+        BASELINE.json's "+ sqrt(beta*h)*z" form is the same update with -noise).
         """
         est = self.estimator
         est.beta_min, est.beta_max, est.pe_scale = self.beta_min, self.beta_max, self.pe_scale
@@ -244,13 +274,19 @@ class Diffusion(BaseModule):
         """Same computation through the host-buffer C entry point: CPU (ideally pinned) tensors in, CPU tensor
         out; the H2D/D2H copies happen inside the call (this is what bench.py's `e2e` leg times)."""
         est = self.estimator
+        est.beta_min, est.beta_max, est.pe_scale = self.beta_min, self.beta_max, self.pe_scale
         h = est._get_handle()
-        for t, n in ((z, "z"), (mask, "mask"), (mu, "mu")):
+        for t, n in ((z, "z"), (mask, "mask"), (mu, "mu")) + (((spk, "spk"),) if spk is not None else ()):
             if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
                 raise ValueError(f"{n} must be a contiguous float32 CPU tensor")
-        B, _, T = z.shape
+        B, T = est._check_shapes(z, mask, mu, spk)
+        if self.n_spks <= 1:
+            spk = None
         if out is None:
             out = torch.empty_like(z)
+        elif out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous() or out.shape != z.shape:
+            raise ValueError("out must be a contiguous float32 CPU tensor of the shape of z")
+        # ordering against earlier calls on other streams is done inside the library (one event per handle)
         rc = _lib.load().gtts_decoder_reverse_diffusion_host(
             h, z.data_ptr(), mask.data_ptr(), mu.data_ptr(), spk.data_ptr() if spk is not None else None,
             out.data_ptr(), B, T, int(n_timesteps), est._flags())

@@ -28,7 +28,9 @@ extern "C" {
 typedef struct gtts_decoder gtts_decoder;
 
 #define GTTS_FLAG_FP32 1   /* true-fp32 arithmetic (FFMA convs, precise libm); default is bf16 tensor-core mode */
-#define GTTS_FLAG_SDE  2   /* north-star SDE update with caller-supplied noise (extension; the reference fork is ODE-only) */
+#define GTTS_FLAG_SDE  2   /* upstream Grad-TTS stochastic update with caller-supplied noise (extension; the reference fork is ODE-only):
+                              x <- (x - ((0.5*(mu-x) - score)*beta*h + noise*sqrt(beta*h))) * mask -- the noise is subtracted, as upstream
+                              does; BASELINE.json's "+ sqrt(beta*h)*z" form is the same update with -noise */
 
 int gtts_version(void);
 const char* gtts_last_error(void);
@@ -88,7 +90,8 @@ void gtts_decoder_destroy(gtts_decoder* d);
 /* Upload one tensor of Diffusion.state_dict() (key e.g. "estimator.downs.0.0.block1.block.0.weight"),
  * fp32, contiguous, PyTorch layout; `data` may be a host or a device pointer.  Invalidates packed weights/plans. */
 int gtts_decoder_set_param(gtts_decoder* d, const char* name, const float* data, size_t numel);
-/* options: "max_chunk" (samples per workspace chunk), "use_graph" (0/1), "conv_impl_bf16" (1 tcgen05, 0 FFMA cross-check),
+/* options: "max_chunk" (samples per workspace chunk, <= 64), "max_plans" (LRU bound on cached per-(B,T) plans; default 24),
+ * "trim" (any value: free every cached plan and the pooled workspace), "use_graph" (0/1), "conv_impl_bf16" (1 tcgen05, 0 FFMA cross-check),
  * "halo_mode" (3x3 convs: 0 per-tap TMA boxes, 1 / 2 halo box 18x16 / 18x10 + shifted descriptor views),
  * "fused_attn" (1: fused k-projection + context kernel for C <= 128, 0: 1x1 kv conv + context kernel) */
 int gtts_decoder_set_option(gtts_decoder* d, const char* key, int value);
@@ -111,6 +114,10 @@ int gtts_decoder_reverse_diffusion_host(gtts_decoder* d, const float* z_host, co
 int gtts_decoder_profile_step(gtts_decoder* d, int B, int T, int flags, int reps, char* buf, size_t buflen, void* stream);
 /* kernels launched by the last reverse_diffusion / estimator call on this handle */
 long gtts_decoder_launches_last_call(const gtts_decoder* d);
+/* Workspace bookkeeping (n >= 5): out[0] plans cached, [1] plans created so far, [2] bytes of pooled activation workspace shared by
+ * all plans of the handle, [3] live workspace of the largest cached plan after liveness-based buffer reuse, [4] the same plan's
+ * footprint with one buffer per tensor.  Calls on one handle are ordered by the library even across streams (plans share the pool). */
+int gtts_decoder_cache_info(const gtts_decoder* d, long long* out, int n);
 
 /* ---- Kernel-level test hooks (used by tests/ only) --------------------------------------------------
  * conv: kind 0 = 3x3 s1, 1 = 1x1, 2 = 3x3 s2, 3 = convT 4x4 s2 p1.  impl 0 = FFMA, 1 = tcgen05 per-tap boxes,

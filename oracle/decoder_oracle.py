@@ -126,10 +126,11 @@ def reverse_diffusion(sd, z, mask, mu, n_timesteps, stoc=False, spk=None, n_spks
     """Diffusion.reverse_diffusion (model/diffusion.py:254-268).
 
     `stoc` is accepted and ignored exactly like the reference fork (it never reads the flag).
-    `sde_noise` (n_timesteps,B,80,T) switches on the *upstream* SDE update named in
-    BASELINE.json's north star, which this fork deleted; that branch restates the north-star
-    formula  x <- x - (0.5*(mu-x) - score)*beta*h + sqrt(beta*h)*z  and is NOT pinned by the
-    reference (parity unpinned for that branch only).
+    `sde_noise` (n_timesteps,B,80,T) switches on the *upstream* (huawei-noah Grad-TTS) stochastic
+    branch, which this fork deleted: dxt_det = (0.5*(mu-xt) - est)*noise_t*h, dxt_stoc =
+    z*sqrt(noise_t*h), xt = (xt - (dxt_det + dxt_stoc))*mask -- the injected noise is SUBTRACTED.
+    BASELINE.json's north-star line writes "+ sqrt(beta*h)*z", which is the same update with -z.
+    This branch is NOT pinned by the reference (it has no such code): parity unpinned for it only.
     """
     h = 1.0 / n_timesteps
     xt = z * mask
@@ -142,8 +143,9 @@ def reverse_diffusion(sd, z, mask, mu, n_timesteps, stoc=False, spk=None, n_spks
             dxt = 0.5 * (mu - xt - est)
             dxt = dxt * noise_t * h
         else:
-            dxt = (0.5 * (mu - xt) - est) * noise_t * h
-            dxt = dxt - torch.sqrt(noise_t * h) * sde_noise[i]
+            dxt_det = (0.5 * (mu - xt) - est) * noise_t * h
+            dxt_stoc = sde_noise[i] * torch.sqrt(noise_t * h)
+            dxt = dxt_det + dxt_stoc
         xt = (xt - dxt) * mask
     return xt
 
