@@ -1,13 +1,17 @@
 #!/usr/bin/env python
-"""Benchmark of the Grad-TTS hot path (reverse-diffusion mel decoder) on B200.
+"""Benchmark of the Grad-TTS hot path (reverse-diffusion mel decoder + MAS) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C5|C3|C1] [--euler N]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C5|C3|C4|C1] [--euler N]
 
 A "step" is one full pass of the hot path over one batch: `Diffusion.forward` (all n Euler steps) on the
 workload's synthetic batch.  Metric (BASELINE.json): decoder mel-frames/s = B*T / time; RTF = 86.13 / (frames/s)
 (reference inference.py:91).  Workload at N=1 is BASELINE config 5 (batch 128 x 1720 frames, 100 Euler steps); with
 N ranks the 128 utterances are split across the ranks (no data-path collective; one all-gather of the mels).
-Prints ONE JSON line on rank 0.
+Prints ONE JSON line on rank 0.  With the default workload the line also carries, as sub-records measured in the same
+run: every other BASELINE config (`configs`: C1, C3, C4, C5 at 10/50/100 Euler steps), MAS at config 2 (`mas`), the
+fp32-tolerance mode (`fp32_strict`), the reference's PyTorch ops run eagerly on this GPU (`gpu_eager_baseline`, cuDNN TF32 and
+bf16 autocast), a weak-scaling record at N > 1 (`weak`), a variable-length serving pattern (`varlen`), per-rank timings
+(`ranks`) and a one-Euler-step error of the timed batch against the CPU oracle (`parity_check`).
 """
 import argparse
 import importlib
@@ -35,6 +39,7 @@ WORKLOADS = {
     "C1": (1, 1, 400, 10),         # LJSpeech single utterance (latency)
 }
 FLOP_PER_FRAME_STEP = {1: 134.154e6, 247: 134.257e6}      # SURVEY 8d / BASELINE.md section 3
+CPU_SAMPLE_BATCH = 4                                       # reduced batch of 4-8 at the workload's T
 
 
 def peaks():
@@ -74,7 +79,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
-        sm, smax, reasons = [], None, set()
+        sm, smax, reasons, pw = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
@@ -83,6 +88,7 @@ class ClockSampler:
             try:
                 sm.append(float(f[0]))
                 smax = float(f[1])
+                pw.append(float(f[2]))
             except ValueError:
                 continue
             for n, v in zip(names, f[3:7]):
@@ -90,10 +96,10 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
-def cpu_reference_leg(n_spks, T, euler, budget_s=20.0):
+def cpu_reference_leg(n_spks, T, euler, budget_s=20.0, want_output=False):
     """The reference's CPU path restated (oracle/decoder_oracle.py, torch fp32, all host threads) on a bounded
     sample of the workload: B_s samples x 1 Euler step at the workload's T; frames/s at `euler` steps =
     B_s*T / (t_step * euler).  (Every Euler step costs the same and samples are independent.)"""
@@ -103,25 +109,31 @@ def cpu_reference_leg(n_spks, T, euler, budget_s=20.0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = pkg.synth.make_decoder_state_dict(n_spks, seed=0, g=0.05)
-    bs = 2
-    z, mask, mu, spk, _ = pkg.synth.make_inputs(bs, T, n_spks, seed=1, ragged=False)
+    B = WORKLOADS_BY_SHAPE.get((n_spks, T), CPU_SAMPLE_BATCH)
+    bs = min(CPU_SAMPLE_BATCH, B)
+    z, mask, mu, spk, _ = pkg.synth.make_inputs(max(bs, 1), T, n_spks, seed=1, ragged=False)
+    y = None
     with torch.no_grad():
         decoder_oracle.reverse_diffusion(sd, z[:1, :, :64].contiguous(), mask[:1, :, :64].contiguous(),
                                          mu[:1, :, :64].contiguous(), 1, False, None if spk is None else spk[:1], n_spks)
         t0 = time.perf_counter()
         reps = 0
         while True:
-            decoder_oracle.reverse_diffusion(sd, z, mask, mu, 1, False, spk, n_spks)
+            y = decoder_oracle.reverse_diffusion(sd, z, mask, mu, 1, False, spk, n_spks)
             reps += 1
             dt = time.perf_counter() - t0
             if dt > budget_s or reps >= 3:
                 break
     t_step = dt / reps
     fps = bs * T / (t_step * euler)
-    return {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{bs} samples x {T} frames x 1 Euler step, {reps} reps ({t_step:.2f} s/step), "
-                      f"scaled to {euler} Euler steps; oracle/decoder_oracle.py (torch fp32 CPU restatement of "
-                      f"model/diffusion.py) with {cores} threads"}
+    res = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+           "sample": f"{bs} samples x {T} frames x 1 Euler step, {reps} reps ({t_step:.2f} s/step), "
+                     f"scaled to {euler} Euler steps; oracle/decoder_oracle.py (torch fp32 CPU restatement of "
+                     f"model/diffusion.py) with {cores} threads"}
+    return (res, y) if want_output else res
+
+
+WORKLOADS_BY_SHAPE = {(v[0], v[2]): v[1] for v in WORKLOADS.values()}
 
 
 def main():
@@ -135,6 +147,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=64)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="main record only (no sub-records for the other configs)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -143,16 +156,19 @@ def main():
     n_spks, B, T, euler = WORKLOADS[args.workload]
     if args.euler:
         euler = args.euler
-    config = {"workload": f"{args.workload}: Grad-TTS decoder n_spks={n_spks}, batch {B} x {T} frames, {euler} Euler steps, "
-                          f"random-init weights, synthetic mu/z, all-ones mask",
-              "global_batch": B, "frames": T, "euler_steps": euler, "parallelism": f"batch-sharded x{world}",
-              "l2": "inputs+workspace larger than L2 (126 MB); no explicit flush"}
+
+    def config_of(name, n_spks_, B_, T_, euler_):
+        return {"workload": f"{name}: Grad-TTS decoder n_spks={n_spks_}, batch {B_} x {T_} frames, {euler_} Euler steps, "
+                            f"random-init weights, synthetic mu/z, all-ones mask",
+                "global_batch": B_, "frames": T_, "euler_steps": euler_, "parallelism": f"batch-sharded x{world}",
+                "l2": "inputs+workspace larger than L2 (126 MB); no explicit flush"}
+
+    config = config_of(args.workload, n_spks, B, T, euler)
 
     # ------------------------------------------------------------------ reference arm: CPU oracle, rank 0 only
     if args.impl == "reference":
         if rank != 0:
             return
-        total = 0.0
         res = None
         for _ in range(max(1, args.warmup // 3)):
             cpu_reference_leg(n_spks, T, euler, budget_s=2.0)
@@ -173,68 +189,116 @@ def main():
         return
 
     # ------------------------------------------------------------------ our arm
+    import ctypes
     import torch
     import torch.distributed as dist
     pkg = importlib.import_module("grad-tts_b200")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a B200; there is no CPU fallback")
+    if world > B:
+        raise SystemExit(f"bench: workload {args.workload} has {B} item(s); it cannot be sharded over {world} ranks")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    tf_peak, hbm_peak, which_peak = peaks()
 
-    lo, hi = pkg.dist.shard_bounds(B, world, rank)
-    Bl = hi - lo
-    sd = pkg.synth.make_decoder_state_dict(n_spks, seed=0, g=0.05)
-    dec = pkg.Diffusion(80, 64, n_spks, 64, 0.05, 20.0, 1000)
-    dec.load_state_dict(sd)
-    dec = dec.to(dev)
-    dec.precision = args.precision
-    dec.estimator.max_chunk = args.chunk
-    z, mask, mu, spk, _ = pkg.synth.make_inputs(B, T, n_spks, seed=1, ragged=False)
-    zl, maskl, mul = (t[lo:hi].contiguous() for t in (z, mask, mu))
-    spkl = spk[lo:hi].contiguous() if spk is not None else None
-    zd, maskd, mud = zl.to(dev), maskl.to(dev), mul.to(dev)
-    spkd = spkl.to(dev) if spkl is not None else None
+    decoders = {}
+
+    def get_decoder(n_spks_, precision="bf16"):
+        if n_spks_ not in decoders:
+            sd_ = pkg.synth.make_decoder_state_dict(n_spks_, seed=0, g=0.05)
+            d_ = pkg.Diffusion(80, 64, n_spks_, 64, 0.05, 20.0, 1000)
+            d_.load_state_dict(sd_)
+            decoders[n_spks_] = d_.to(dev)
+        d_ = decoders[n_spks_]
+        d_.precision = precision
+        d_.estimator.max_chunk = args.chunk
+        return d_
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def one_step():
-        y = dec(zd, maskd, mud, euler, False, spkd)
-        if world > 1:
-            y = pkg.dist.all_gather_batch(y, B)
-        return y
+    def gather_floats(v):
+        """[v of rank 0, v of rank 1, ...] on every rank."""
+        t = torch.tensor([float(v)], device=dev, dtype=torch.float64)
+        if world == 1:
+            return [float(v)]
+        out = torch.empty(world, device=dev, dtype=torch.float64)
+        dist.all_gather_into_tensor(out, t)
+        return [float(x) for x in out.cpu()]
 
-    for _ in range(args.warmup):
-        y = one_step()
-    barrier()
+    def shard_inputs(n_spks_, B_, T_, seed=1, tile_one_mu=False):
+        z, mask, mu, spk, _ = pkg.synth.make_inputs(B_, T_, n_spks_, seed=seed, ragged=False)
+        if tile_one_mu:                                   # n-best: one utterance's mu, B different z (BASELINE config 4)
+            mu = mu[:1].expand(B_, -1, -1).contiguous()
+            g = torch.Generator().manual_seed(seed + 1000)
+            z = mu + torch.randn(mu.shape, generator=g) / 1.5
+        lo, hi = pkg.dist.shard_bounds(B_, world, rank)
+        host = [t[lo:hi].contiguous() for t in (z, mask, mu)] + [spk[lo:hi].contiguous() if spk is not None else None]
+        devt = [t.to(dev) if t is not None else None for t in host]
+        return host, devt, hi - lo
+
+    def timed_decoder(dec, devt, B_, euler_, steps, warmup, out_buf=None):
+        """Device-timed throughput of `steps` calls (max over ranks), plus this rank's split into compute and all-gather."""
+        zd, maskd, mud, spkd = devt
+
+        def one(ev=None):
+            y = dec(zd, maskd, mud, euler_, False, spkd)
+            if ev is not None:
+                ev[0].record()
+            if world > 1:
+                y = pkg.dist.all_gather_batch(y, B_, out=out_buf)
+            return y
+
+        y = None
+        for _ in range(warmup):
+            y = one()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        mids = [[torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)] for _ in range(steps)]
+        launches = 0
+        barrier()
+        e0.record()
+        for i in range(steps):
+            y = one(mids[i])
+            mids[i][1].record()
+            launches += dec.estimator.launches_last_call()
+        e1.record()
+        barrier()
+        ms_local = e0.elapsed_time(e1)
+        gather_ms = sum(a.elapsed_time(b) for a, b in mids) / steps
+        per_rank = gather_floats(ms_local / steps)
+        return y, max(per_rank), per_rank, gather_floats(gather_ms), launches
+
+    def record(name, value, ms, n_spks_, B_, T_, euler_, extra=None):
+        fs = value * euler_
+        r = {"workload": name, "value": value, "unit": "frames/s", "ms_per_step": ms, "rtf": 86.1328125 / value,
+             "global_batch": B_, "frames": T_, "euler_steps": euler_, "frame_steps_per_sec": fs,
+             "model_tflops": fs * FLOP_PER_FRAME_STEP.get(n_spks_, 134.154e6) / 1e12}
+        r["frac_of_bf16_peak_x_gpus"] = r["model_tflops"] / (tf_peak * world)
+        if extra:
+            r.update(extra)
+        return r
+
+    # ================================================================== main record
+    dec = get_decoder(n_spks, args.precision)
+    host, devt, Bl = shard_inputs(n_spks, B, T, tile_one_mu=(args.workload == "C4"))
+    out_buf = torch.empty((B, 80, T), dtype=torch.float32, device=dev) if world > 1 else None
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    launches = 0
-    for _ in range(args.steps):
-        y = one_step()
-        launches += dec.estimator.launches_last_call()
-    e1.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    ms_per_step = ms_total / args.steps
+    sampler.start()
+    y, ms_per_step, per_rank_ms, per_rank_gather, launches = timed_decoder(dec, devt, B, euler, args.steps, args.warmup, out_buf)
+    clocks = sampler.stop()
     value = B * T / (ms_per_step * 1e-3)
     finite = bool(torch.isfinite(y).all())
     if not finite:
         raise SystemExit("bench: the sampler output contains non-finite values -- the measurement is invalid")
+    rank_clocks = gather_floats(clocks["sm_mhz"] or 0.0)
 
     # ---- e2e: host (pinned) buffers through the C-ABI host entry point, copies inside the timed region
+    zl, maskl, mul, spkl = host
     zp, mp, mup = zl.pin_memory(), maskl.pin_memory(), mul.pin_memory()
     spkp = spkl.pin_memory() if spkl is not None else None
     outp = torch.empty_like(zl).pin_memory()
@@ -244,17 +308,14 @@ def main():
     for _ in range(args.steps):
         dec.reverse_diffusion_host(zp, mp, mup, euler, spkp, outp)
     barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = B * T / (float(e2e_s.item()) / args.steps)
+    e2e_s = max(gather_floats(time.perf_counter() - t0))
+    e2e_value = B * T / (e2e_s / args.steps)
     h2d = (zl.numel() + mul.numel() + maskl.numel() + (spkl.numel() if spkl is not None else 0)) * 4
     d2h = zl.numel() * 4
 
     # ---- roofline of the dominant kernel (the tcgen05 implicit-GEMM conv), measured live with CUDA events
-    roof = None
+    roof, workspace = None, None
     if rank == 0:
-        import ctypes
         buf = ctypes.create_string_buffer(1 << 17)
         h = dec.estimator._get_handle()
         flags = 1 if args.precision == "fp32" else 0
@@ -267,44 +328,281 @@ def main():
         t_conv = sum(o["ms"] for o in conv) * 1e-3
         t_all = sum(o["ms"] for o in rep["ops"]) * 1e-3
         f_conv = sum(o["flops"] for o in conv)
-        tf_peak, hbm_peak, which = peaks()
         ach = f_conv / t_conv / 1e12
-        # DRAM bytes per launch from the committed ncu capture of this command (profiles/r01_conv_dram_v11.json: 40 conv
-        # launches of one Euler step at chunk 64 x 1720); only quoted when this run uses the same chunk shape
+        # DRAM bytes per launch from the committed ncu capture of this command (40 conv launches of one Euler step at chunk
+        # 64 x 1720); only quoted when this run uses the same chunk shape
         traffic, traffic_src = None, None
-        try:
-            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_conv_dram_v11.json")))
-            if rep["B"] == tj.get("chunk_batch", 64) and T == 1720 and tj["launches"] == len(conv):
-                traffic, traffic_src = tj["traffic_bytes_per_launch"], "profiles/r01_conv_dram_v11.json (ncu dram__bytes_read+write)"
-        except (OSError, KeyError, ValueError):
-            pass
-        roof = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convolutions (conv_tc / conv_tc_halo / conv_tc_halo2, all launches of one Euler step)",
+        for tj_name in ("r02_conv_dram.json", "r01_conv_dram_v11.json"):
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", tj_name)))
+                if rep["B"] == tj.get("chunk_batch", 64) and T == 1720 and tj["launches"] == len(conv):
+                    traffic = tj["traffic_bytes_per_launch"]
+                    traffic_src = f"profiles/{tj_name} (ncu dram__bytes_read+write)"
+                    break
+            except (OSError, KeyError, ValueError):
+                pass
+        roof = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convolutions (conv_tc / conv_tc_halo2, all launches of one Euler step)",
                 "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": traffic,
                 "traffic_source": traffic_src, "algorithmic_bytes_per_launch": sum(o.get("bytes", 0) for o in conv) / len(conv),
-                "peak_source": f"{which} (bf16_tflops_sustained)", "launches_per_step": len(conv),
+                "peak_source": f"{which_peak} (bf16_tflops_sustained)", "launches_per_step": len(conv),
                 "avg_launch_ms": 1e3 * t_conv / len(conv), "conv_share_of_step": t_conv / t_all,
-                "chunk_batch": rep["B"],
+                "chunk_batch": rep["B"], "euler_step_ms_eager_sum": 1e3 * t_all,
+                "whole_step_frac": (value * euler * FLOP_PER_FRAME_STEP.get(n_spks, 134.154e6) / 1e12) / (tf_peak * world),
                 "non_conv_ms": {k: sum(o["ms"] for o in rep["ops"] if o["name"].startswith(k))
                                 for k in ("gn_apply", "attn_xk", "attn_ctx", "attn_merge", "attn_fold", "first_conv", "euler", "temb")}}
+        workspace = {k: rep.get(k) for k in ("workspace_bytes", "workspace_bytes_without_reuse", "pool_bytes", "plans_cached",
+                                             "plans_created")}
 
-    cpu = None
+    # ---- CPU baseline (rank 0) and the one-Euler-step parity check of the TIMED batch against it
+    cpu, parity = None, None
+    y1 = dec(devt[0], devt[1], devt[2], 1, False, devt[3])[:CPU_SAMPLE_BATCH].cpu() if rank == 0 else None
     if rank == 0 and not args.no_cpu_baseline:
-        cpu = cpu_reference_leg(n_spks, T, euler, budget_s=15.0)
+        cpu, yref = cpu_reference_leg(n_spks, T, euler, budget_s=15.0, want_output=True)
+        nb = min(yref.shape[0], y1.shape[0])
+        if args.workload != "C4":                          # C4 tiles one mu: the CPU sample uses the plain inputs
+            d = (y1[:nb] - yref[:nb])
+            parity = {"what": f"first {nb} utterances of the timed batch, one Euler step (n_timesteps=1) inside the full chunk, "
+                              f"{args.precision} kernels vs oracle/decoder_oracle.py (fp32 CPU)",
+                      "max_abs_err": float(d.abs().max()), "rel_rms": float(d.pow(2).mean().sqrt() / yref[:nb].pow(2).mean().sqrt()),
+                      "ref_absmax": float(yref[:nb].abs().max()),
+                      "tolerance": "bf16: rel-rms <= 2e-2; fp32: max-abs <= 1e-3 (tests/test_gpu_decoder.py)"}
 
+    line = None
     if rank == 0:
-        fs = value * euler
+        line = record(args.workload, value, ms_per_step, n_spks, B, T, euler)
+        line.pop("workload")
         line = {"metric": "decoder_mel_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-                "config": config, "rtf": 86.1328125 / value, "frame_steps_per_sec": fs,
-                "model_tflops": fs * FLOP_PER_FRAME_STEP.get(n_spks, 134.154e6) / 1e12,
-                "output_finite": finite, "clocks": clocks,
+                "config": config, "rtf": line["rtf"], "frame_steps_per_sec": line["frame_steps_per_sec"],
+                "model_tflops": line["model_tflops"], "output_finite": finite, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "gtts_decoder_reverse_diffusion_host (C ABI, pinned host buffers)"},
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "parity_check": parity,
+                "workspace": workspace,
+                "ranks": {"ms_per_step": per_rank_ms, "all_gather_ms": per_rank_gather, "sm_mhz_median": rank_clocks,
+                          "utterances_per_rank": pkg.dist.shard_counts(B, world),
+                          "note": "device time of each rank for one step (CUDA events), time spent in the single all-gather "
+                                  "inside it, and each rank's median SM clock under load"}}
+
+    # ================================================================== sub-records (default workload only)
+    subs = args.workload == "C5" and not args.euler and not args.no_sub and args.precision == "bf16"
+    if subs:
+        configs = {}
+        if rank == 0:
+            configs["C5@100"] = record("C5@100", value, ms_per_step, n_spks, B, T, euler, {"e2e_value": e2e_value})
+        for name, wl, eu in (("C5@50", "C5", 50), ("C5@10", "C5", 10), ("C3", "C3", 50), ("C4", "C4", 10)):
+            ns_, B_, T_, _ = WORKLOADS[wl]
+            if world > B_:
+                continue
+            d_ = get_decoder(ns_)
+            if wl == "C5":
+                devt_, ob_ = devt, out_buf
+            else:
+                _, devt_, _ = shard_inputs(ns_, B_, T_, tile_one_mu=(wl == "C4"))
+                ob_ = torch.empty((B_, 80, T_), dtype=torch.float32, device=dev) if world > 1 else None
+            y_, ms_, prm_, _, _ = timed_decoder(d_, devt_, B_, eu, 2, 1, ob_)
+            if rank == 0:
+                configs[name] = record(name, B_ * T_ / (ms_ * 1e-3), ms_, ns_, B_, T_, eu,
+                                       {"output_finite": bool(torch.isfinite(y_).all()), "ms_per_rank": prm_,
+                                        "utterances_per_rank": pkg.dist.shard_counts(B_, world)})
+            del y_
+        # ---- weak scaling: the full 128 x 1720 batch on EVERY rank (N x 128 utterances in total), 100 Euler steps
+        weak = None
+        if world > 1:
+            zw, mw, muw, spw, _ = pkg.synth.make_inputs(B, T, n_spks, seed=1, ragged=False)
+            zd, maskd, mud = zw.to(dev), mw.to(dev), muw.to(dev)
+            d_ = get_decoder(n_spks)
+
+            def weak_step():
+                return d_(zd, maskd, mud, euler, False, None)
+            weak_step()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            weak_step()
+            e1.record()
+            barrier()
+            prm = gather_floats(e0.elapsed_time(e1))
+            if rank == 0:
+                weak = record(f"C5 weak: {B} utterances per rank, no gather", world * B * T / (max(prm) * 1e-3), max(prm), n_spks,
+                              world * B, T, euler, {"scaling": "weak", "ms_per_rank": prm})
+            del zd, maskd, mud
+        # ---- rank-0-only records: latency config, MAS, fp32 mode, GPU eager baseline, variable lengths
+        if rank == 0:
+            c1 = single_gpu_config(pkg, torch, get_decoder, dev, "C1", tf_peak)
+            configs["C1"] = c1
+            mas = mas_record(pkg, torch, dev, hbm_peak)
+            fp32 = fp32_record(pkg, torch, get_decoder, dev, devt, Bl, T)
+            eager = gpu_eager_record(pkg, torch, dev, configs, line)
+            varlen = varlen_record(pkg, torch, get_decoder, dev)
+            line["configs"] = configs
+            line["mas"] = mas
+            line["fp32_strict"] = fp32
+            line["gpu_eager_baseline"] = eager
+            line["weak"] = weak
+            line["varlen"] = varlen
+        barrier()
+
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------- sub-records
+def _event_time_ms(torch, fn, reps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def single_gpu_config(pkg, torch, get_decoder, dev, wl, tf_peak):
+    """A config that does not shard (C1: one utterance): measured on rank 0's GPU, device-timed and end to end."""
+    ns_, B_, T_, eu = WORKLOADS[wl]
+    d_ = get_decoder(ns_)
+    z, mask, mu, spk, _ = pkg.synth.make_inputs(B_, T_, ns_, seed=1, ragged=False)
+    a = [t.to(dev) if t is not None else None for t in (z, mask, mu, spk)]
+    ms = _event_time_ms(torch, lambda: d_(a[0], a[1], a[2], eu, False, a[3]), 20, 5)
+    zp, mp, mup = z.pin_memory(), mask.pin_memory(), mu.pin_memory()
+    outp = torch.empty_like(z).pin_memory()
+    d_.reverse_diffusion_host(zp, mp, mup, eu, None, outp)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        d_.reverse_diffusion_host(zp, mp, mup, eu, None, outp)
+    e2e_ms = (time.perf_counter() - t0) / 20 * 1e3
+    v = B_ * T_ / (ms * 1e-3)
+    fs = v * eu
+    return {"workload": wl, "value": v, "unit": "frames/s", "ms_per_step": ms, "rtf": 86.1328125 / v, "global_batch": B_, "frames": T_,
+            "euler_steps": eu, "frame_steps_per_sec": fs, "model_tflops": fs * FLOP_PER_FRAME_STEP[1] / 1e12,
+            "frac_of_bf16_peak_x_gpus": fs * FLOP_PER_FRAME_STEP[1] / 1e12 / tf_peak, "e2e_ms": e2e_ms,
+            "e2e_value": B_ * T_ / (e2e_ms * 1e-3), "output_finite": bool(torch.isfinite(outp).all()),
+            "note": "latency config: one utterance on one GPU (rank 0) whatever N is"}
+
+
+def mas_record(pkg, torch, dev, hbm_peak):
+    """BASELINE config 2: maximum_path, batch 64, text 200 x mel 1000 -- device time, host-buffer time, bit-exactness against the
+    CPU restatement of the Cython kernel (oracle/mas_oracle.c) and that restatement's single-thread time."""
+    from oracle import mas_oracle
+    B_, tx, ty = 64, 200, 1000
+    value, mask, _, _ = pkg.synth.make_mas_inputs(B_, tx, ty, seed=1234)
+    v, m = value.to(dev), mask.to(dev)
+    ms = _event_time_ms(torch, lambda: pkg.maximum_path(v, m, check=False), 20, 3)
+    got = pkg.maximum_path(v, m).cpu()
+    t0 = time.perf_counter()
+    ref = mas_oracle.maximum_path(value, mask)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    lib = pkg._lib.load()
+    path_h = torch.empty_like(value).pin_memory()
+    vh, mh = value.pin_memory(), mask.pin_memory()
+    st = torch.zeros(1, dtype=torch.int32)
+    lib.gtts_mas_maximum_path_host(vh.data_ptr(), mh.data_ptr(), path_h.data_ptr(), B_, tx, ty, st.data_ptr(), dev.index or 0)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        rc = lib.gtts_mas_maximum_path_host(vh.data_ptr(), mh.data_ptr(), path_h.data_ptr(), B_, tx, ty, st.data_ptr(), dev.index or 0)
+    host_ms = (time.perf_counter() - t0) / 3 * 1e3
+    cells = B_ * tx * ty
+    alg = 12.0 * cells                                   # value + mask read, path write (the mask multiply is fused)
+    return {"workload": "C2: monotonic_align.maximum_path batch 64, text 200 x mel 1000 (ragged lengths, item 0 full size)",
+            "device_ms": ms, "cells_per_sec": cells / (ms * 1e-3), "algorithmic_bytes": alg,
+            "achieved_gbs": alg / (ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak, "frac_of_hbm": alg / (ms * 1e-3) / 1e9 / hbm_peak,
+            "bound": "latency: t_y = 1000 dependent column steps per utterance, one CTA per utterance (64 CTAs)",
+            "host_buffers_ms": host_ms, "host_rc": int(rc), "bit_exact_vs_cpu": bool(torch.equal(got, ref)) and bool(torch.equal(path_h, ref)),
+            "cpu_reference_ms": cpu_ms, "cpu_reference": "oracle/mas_oracle.c (plain-C restatement of core.pyx, 1 thread) incl. the wrapper's "
+                                                         "value*mask and casts"}
+
+
+def fp32_record(pkg, torch, get_decoder, dev, devt, Bl, T):
+    """The fp32-tolerance mode (precision='fp32': the mode that meets max-abs 1e-3 against the fp32 reference), timed."""
+    d_ = get_decoder(1, "fp32")
+    ns_, B1, T1, eu1 = WORKLOADS["C1"]
+    z, mask, mu, _, _ = pkg.synth.make_inputs(B1, T1, 1, seed=1, ragged=False)
+    a = [t.to(dev) for t in (z, mask, mu)]
+    ms1 = _event_time_ms(torch, lambda: d_(a[0], a[1], a[2], eu1), 3, 1)
+    nsteps = 2
+    ms5 = _event_time_ms(torch, lambda: d_(devt[0], devt[1], devt[2], nsteps, False, devt[3]), 1, 1)
+    fs = Bl * T * nsteps / (ms5 * 1e-3)
+    d_.precision = "bf16"
+    return {"mode": d_.estimator.fp32_conv_impl() if hasattr(d_.estimator, "fp32_conv_impl") else "ffma",
+            "C1": {"ms_per_step": ms1, "value": B1 * T1 / (ms1 * 1e-3), "unit": "frames/s", "euler_steps": eu1},
+            "C5_shape": {"batch": Bl, "frames": T, "euler_steps_timed": nsteps, "ms": ms5, "frame_steps_per_sec": fs,
+                         "frames_per_sec_at_100_steps": fs / 100.0, "model_tflops": fs * FLOP_PER_FRAME_STEP[1] / 1e12,
+                         "note": "this rank's shard of the C5 batch, 2 Euler steps (every step costs the same)"}}
+
+
+def gpu_eager_record(pkg, torch, dev, configs, line):
+    """Second reported baseline: the reference's own PyTorch op sequence (oracle/decoder_oracle.py, a functional
+    restatement of model/diffusion.py that runs on any device) executed EAGERLY on this B200 -- cuDNN/cuBLAS with torch's defaults
+    (TF32 convolutions) and under bf16 autocast.  Bounded sample, scaled linearly in batch and Euler steps, like the CPU leg."""
+    from oracle import decoder_oracle
+    out = {"what": "torch eager on the same GPU: F.conv2d / group_norm / softplus / tanh / softmax / einsum as model/diffusion.py issues "
+                   "them; no CUDA graph, default stream; torch " + torch.__version__,
+           "allow_tf32": {"cudnn": bool(torch.backends.cudnn.allow_tf32), "matmul": bool(torch.backends.cuda.matmul.allow_tf32)}}
+    for wl, bs, steps in (("C1", 1, 10), ("C3", 32, 2), ("C5", 16, 2)):
+        ns_, B_, T_, eu = WORKLOADS[wl]
+        sd = {k: v.to(dev) for k, v in pkg.synth.make_decoder_state_dict(ns_, seed=0, g=0.05).items()}
+        z, mask, mu, spk, _ = pkg.synth.make_inputs(bs, T_, ns_, seed=1, ragged=False)
+        a = [t.to(dev) if t is not None else None for t in (z, mask, mu, spk)]
+        rec = {"sample": f"{bs} x {T_} frames x {steps} Euler steps, scaled to batch {B_} x {eu} steps"}
+        for mode in ("tf32_default", "bf16_autocast"):
+            def run():
+                with torch.no_grad():
+                    if mode == "bf16_autocast":
+                        with torch.autocast("cuda", dtype=torch.bfloat16):
+                            return decoder_oracle.reverse_diffusion(sd, a[0], a[1], a[2], steps, False, a[3], ns_)
+                    return decoder_oracle.reverse_diffusion(sd, a[0], a[1], a[2], steps, False, a[3], ns_)
+            try:
+                ms = _event_time_ms(torch, run, 2, 1)
+                rec[mode] = {"ms_sample": ms, "value": bs * T_ / (ms * 1e-3 / steps * eu), "unit": "frames/s"}
+            except Exception as e:  # the baseline must never take the bench down
+                rec[mode] = {"error": repr(e)[:200]}
+                torch.cuda.empty_cache()
+        best = max((rec[m].get("value", 0.0) for m in ("tf32_default", "bf16_autocast")), default=0.0)
+        ours = line["value"] if wl == "C5" else (configs.get(wl) or {}).get("value")
+        rec["best_eager_value"] = best
+        rec["ours_value"] = ours
+        rec["n_gpus_ours"] = line["n_gpus"] if wl != "C1" else 1
+        rec["vs_gpu_eager"] = (ours / (best * rec["n_gpus_ours"])) if (ours and best) else None
+        out[wl] = rec
+        del sd, a
+        torch.cuda.empty_cache()
+    out["note"] = "vs_gpu_eager = our frames/s per GPU / best eager frames/s on one GPU, same config"
+    return out
+
+
+def varlen_record(pkg, torch, get_decoder, dev):
+    """Serving pattern: every call has a different mel length (plans are keyed on (B, T); T cannot be bucketed because GroupNorm
+    and the attention softmax include the padding).  First pass builds the plans (descriptors + graph; the activation memory comes
+    from the shared pool), second pass hits the plan cache."""
+    d_ = get_decoder(1)
+    g = torch.Generator().manual_seed(5)
+    Ts = sorted({int(t) // 4 * 4 for t in torch.randint(400, 1721, (12,), generator=g)})
+    Bv, eu = 8, 10
+    ins = []
+    for T_ in Ts:
+        z, mask, mu, _, _ = pkg.synth.make_inputs(Bv, T_, 1, seed=T_, ragged=True)
+        ins.append([t.to(dev) for t in (z, mask, mu)])
+    before = d_.estimator.cache_info()
+    res = {}
+    for name in ("first_pass_builds_plans", "second_pass_cached"):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for a in ins:
+            d_(a[0], a[1], a[2], eu)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        res[name] = {"seconds": dt, "value": Bv * sum(Ts) / dt, "unit": "frames/s"}
+    after = d_.estimator.cache_info()
+    res.update({"lengths": Ts, "batch": Bv, "euler_steps": eu, "plans_created": after["plans_created"] - before["plans_created"],
+                "pool_bytes_before": before["pool_bytes"], "pool_bytes_after": after["pool_bytes"]})
+    return res
 
 
 if __name__ == "__main__":

@@ -8,7 +8,7 @@ import ctypes
 
 import torch
 
-from .. import _lib
+from .. import _lib, ops  # noqa: F401  (ops registers torch.ops.gradtts_b200.*)
 
 
 def _stream(t):
@@ -23,13 +23,7 @@ def log_prior(mu_x, y):
         raise ValueError(f"log_prior expects (B, n_feats, t_x) and (B, n_feats, t_y), got {tuple(mu_x.shape)} and {tuple(y.shape)}")
     m = mu_x.detach().to(torch.float32).contiguous()
     v = y.detach().to(torch.float32).contiguous()
-    B, C, tx = m.shape
-    ty = v.shape[2]
-    out = torch.empty(B, tx, ty, dtype=torch.float32, device=m.device)
-    with torch.cuda.device(m.device):
-        rc = _lib.load().gtts_align_log_prior(m.data_ptr(), v.data_ptr(), out.data_ptr(), B, C, tx, ty, _stream(m))
-    _lib.check(rc, "log_prior")
-    return out.to(mu_x.dtype)
+    return torch.ops.gradtts_b200.log_prior(m, v).to(mu_x.dtype)
 
 
 def _outputs(attn, mu_x, x_mask, want_logw, want_mu_y):
@@ -43,19 +37,12 @@ def _outputs(attn, mu_x, x_mask, want_logw, want_mu_y):
     C = m.shape[1]
     if m.shape[0] != B or m.shape[2] != tx:
         raise ValueError(f"attn {tuple(attn.shape)} and mu_x {tuple(mu_x.shape)} do not match")
-    logw = mu_y = xm = None
+    xm = None
     if want_logw:
         _lib.require_cuda_tensor(x_mask, "x_mask")
         xm = x_mask.detach().to(torch.float32).reshape(B, tx).contiguous()
-        logw = torch.empty(B, 1, tx, dtype=torch.float32, device=a.device)
-    if want_mu_y:
-        mu_y = torch.empty(B, C, ty, dtype=torch.float32, device=a.device)
-    with torch.cuda.device(a.device):
-        rc = _lib.load().gtts_align_outputs(a.data_ptr(), m.data_ptr(), xm.data_ptr() if xm is not None else None,
-                                            logw.data_ptr() if logw is not None else None,
-                                            mu_y.data_ptr() if mu_y is not None else None, B, C, tx, ty, _stream(a))
-    _lib.check(rc, "align_outputs")
-    return logw, mu_y
+    logw, mu_y = torch.ops.gradtts_b200.align_outputs(a, m, xm, bool(want_mu_y))
+    return (logw if want_logw else None), (mu_y if want_mu_y else None)
 
 
 def logw_from_path(attn, x_mask):

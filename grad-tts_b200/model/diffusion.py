@@ -10,7 +10,7 @@ import math
 
 import torch
 
-from .. import _lib, synth
+from .. import _lib, ops, synth  # noqa: F401  (ops registers torch.ops.gradtts_b200.*)
 from .base import BaseModule
 
 
@@ -177,13 +177,7 @@ class GradLogPEstimator2d(BaseModule):
         if t_.numel() != B:
             raise ValueError("t must have one entry per sample")
         spk_ = self._prep(spk, "spk", dev) if (spk is not None and self.n_spks > 1) else None
-        out = torch.empty_like(x_)
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            rc = _lib.load().gtts_decoder_estimator(h, x_.data_ptr(), mask_.data_ptr(), mu_.data_ptr(), t_.data_ptr(),
-                                                    spk_.data_ptr() if spk_ is not None else None, out.data_ptr(),
-                                                    B, T, self._flags(), ctypes.c_void_p(stream))
-        _lib.check(rc, "estimator")
+        out = torch.ops.gradtts_b200.estimator(int(h.value), x_, mask_, mu_, t_, spk_, self._flags())
         return out.to(x.dtype)
 
     def cache_info(self):
@@ -255,14 +249,7 @@ class Diffusion(BaseModule):
             if tuple(noise_.shape) != (n_timesteps, B, self.n_feats, T):
                 raise ValueError("sde_noise must have shape (n_timesteps, B, 80, T)")
             flags |= _lib.FLAG_SDE
-        out = torch.empty_like(z_)
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            rc = _lib.load().gtts_decoder_reverse_diffusion(
-                h, z_.data_ptr(), mask_.data_ptr(), mu_.data_ptr(), spk_.data_ptr() if spk_ is not None else None,
-                out.data_ptr(), B, T, n_timesteps, flags, noise_.data_ptr() if noise_ is not None else None,
-                ctypes.c_void_p(stream))
-        _lib.check(rc, "reverse_diffusion")
+        out = torch.ops.gradtts_b200.reverse_diffusion(int(h.value), z_, mask_, mu_, spk_, noise_, n_timesteps, flags)
         return out.to(z.dtype)
 
     @torch.no_grad()
@@ -314,13 +301,7 @@ class Diffusion(BaseModule):
         z_ = self.estimator._prep(noise, "noise", dev)
         if z_.shape != x_.shape:
             raise ValueError("noise must have the shape of x0")
-        xt, zm = torch.empty_like(x_), torch.empty_like(x_)
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            rc = _lib.load().gtts_forward_diffusion(x_.data_ptr(), mask_.data_ptr(), mu_.data_ptr(), t_.data_ptr(), z_.data_ptr(),
-                                                    xt.data_ptr(), zm.data_ptr(), B, self.n_feats, T, float(self.beta_min),
-                                                    float(self.beta_max), ctypes.c_void_p(stream))
-        _lib.check(rc, "forward_diffusion")
+        xt, zm = torch.ops.gradtts_b200.forward_diffusion(x_, mask_, mu_, t_, z_, float(self.beta_min), float(self.beta_max))
         return xt.to(x0.dtype), zm.to(x0.dtype)
 
     def loss_t(self, x0, mask, mu, t, spk=None, noise=None):
@@ -333,15 +314,8 @@ class Diffusion(BaseModule):
         dev, x_, mask_, mu_, t_, B, T = self._fd_args(x0, mask, mu, t)
         xt, zm = self.forward_diffusion(x_, mask_, mu_, t_, noise)
         est = self.estimator(xt, mask_, mu_, t_, spk)
-        lib = _lib.load()
-        ws = torch.empty(int(lib.gtts_score_loss_workspace_bytes()), dtype=torch.uint8, device=dev)
-        loss = torch.empty((), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            rc = lib.gtts_score_loss(est.data_ptr(), zm.data_ptr(), mask_.data_ptr(), t_.data_ptr(), ws.data_ptr(), ws.numel(),
-                                     loss.data_ptr(), B, self.n_feats, T, float(self.beta_min), float(self.beta_max),
-                                     ctypes.c_void_p(stream))
-        _lib.check(rc, "score_loss")
+        loss = torch.ops.gradtts_b200.score_loss(est.to(torch.float32).contiguous(), zm, mask_, t_, float(self.beta_min),
+                                                 float(self.beta_max))
         return loss.to(x0.dtype), xt.to(x0.dtype)
 
     def compute_loss(self, x0, mask, mu, spk=None, offset=1e-5):

@@ -9,7 +9,7 @@ import ctypes
 import torch
 
 from .. import utils  # noqa: F401  (keeps `model.utils` importable next to this module, like the reference)
-from ... import _lib
+from ... import _lib, ops  # noqa: F401  (ops registers torch.ops.gradtts_b200.*)
 
 
 def maximum_path(value, mask, check=True):
@@ -23,23 +23,13 @@ def maximum_path(value, mask, check=True):
     if value.dim() != 3 or mask.shape != value.shape:
         raise ValueError(f"maximum_path expects value and mask of the same [b, t_x, t_y] shape, got "
                          f"{tuple(value.shape)} and {tuple(mask.shape)}")
-    lib = _lib.load()
     dtype = value.dtype
     v = value.detach().to(torch.float32).contiguous()
     m = mask.detach().to(torch.float32).contiguous()
     b, tx, ty = v.shape
-    path = torch.empty_like(v)
-    status = torch.empty(1, dtype=torch.int32, device=v.device)
     if b == 0 or tx == 0 or ty == 0:
         return torch.zeros_like(value)
-    ws_bytes = lib.gtts_mas_workspace_bytes(b, tx, ty)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=v.device) if ws_bytes else None
-    with torch.cuda.device(v.device):
-        stream = torch.cuda.current_stream(v.device).cuda_stream
-        rc = lib.gtts_mas_maximum_path(v.data_ptr(), m.data_ptr(), path.data_ptr(), b, tx, ty,
-                                       ws.data_ptr() if ws is not None else None, ws_bytes,
-                                       status.data_ptr(), ctypes.c_void_p(stream))
-    _lib.check(rc, "maximum_path")
+    path, status = torch.ops.gradtts_b200.maximum_path(v, m)
     if check and int(status.item()) != 0:
         raise RuntimeError("maximum_path: an item has t_x > t_y (more text rows than mel frames); "
                            "the reference's result is undefined for that input")

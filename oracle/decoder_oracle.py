@@ -66,7 +66,7 @@ def sinusoidal_pos_emb(t, dim=64, scale=1000.0):
     # model/diffusion.py:113-125
     half = dim // 2
     c = math.log(10000) / (half - 1)
-    emb = torch.exp(torch.arange(half, dtype=torch.float32).to(t.dtype) * -c)
+    emb = torch.exp(torch.arange(half, dtype=torch.float32, device=t.device).to(t.dtype) * -c)
     emb = scale * t.unsqueeze(1) * emb.unsqueeze(0)
     return torch.cat((emb.sin(), emb.cos()), dim=-1)
 
@@ -135,7 +135,7 @@ def reverse_diffusion(sd, z, mask, mu, n_timesteps, stoc=False, spk=None, n_spks
     h = 1.0 / n_timesteps
     xt = z * mask
     for i in range(n_timesteps):
-        t = (1.0 - (i + 0.5) * h) * torch.ones(z.shape[0], dtype=z.dtype)
+        t = (1.0 - (i + 0.5) * h) * torch.ones(z.shape[0], dtype=z.dtype, device=z.device)
         time = t.unsqueeze(-1).unsqueeze(-1)
         noise_t = beta_min + (beta_max - beta_min) * time           # get_noise, :219-224
         est = estimator_forward(sd, xt, mask, mu, t, spk, n_spks, pe_scale)

@@ -108,6 +108,16 @@ out = pkg.dist.sharded_call(fake, [z, mu, None], n)
 assert out.shape == z.shape and torch.equal(out, z * 2 + mu), "gathered result differs from the 1-rank result"
 lo, hi = pkg.dist.shard_bounds(n, 2, dist.get_rank())
 assert (hi - lo) == (4 if dist.get_rank() == 0 else 3)
+# even split: shards land straight in the output tensor
+out8 = pkg.dist.sharded_call(fake, [z[:6], mu[:6], None], 6)
+assert torch.equal(out8, z[:6] * 2 + mu[:6])
+# fewer items than ranks: refused on EVERY rank before any collective (a rank-local raise would hang the others)
+try:
+    pkg.dist.sharded_call(fake, [z[:1], mu[:1], None], 1)
+    raise SystemExit("expected a RuntimeError")
+except RuntimeError as e:
+    assert "cannot shard" in str(e)
+dist.barrier()
 dist.destroy_process_group()
 print("ok")
 """
@@ -142,3 +152,29 @@ def test_bench_reference_arm_contract():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "oracle/decoder_oracle.py" in cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["workload"].startswith("C1")
+
+
+def test_torch_library_ops_are_registered(pkg):
+    """The hot path is exposed as torch.library custom ops over the C ABI: every op exists in the dispatcher, propagates
+    shapes under FakeTensorMode without touching a device, and has NO CPU kernel (CPU tensors fail in the dispatcher)."""
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    ops = importlib.import_module("grad-tts_b200.ops")
+    for name in ops.OPS:
+        assert hasattr(torch.ops.gradtts_b200, name), name
+    with FakeTensorMode():
+        z, m = torch.empty(3, 80, 44, device="cuda"), torch.empty(3, 1, 44, device="cuda")
+        t = torch.empty(3, device="cuda")
+        assert torch.ops.gradtts_b200.reverse_diffusion(0, z, m, z, None, None, 10, 0).shape == z.shape
+        assert torch.ops.gradtts_b200.estimator(0, z, m, z, t, None, 0).shape == z.shape
+        v = torch.empty(2, 7, 19, device="cuda")
+        path, status = torch.ops.gradtts_b200.maximum_path(v, v)
+        assert path.shape == v.shape and status.shape == (1,) and status.dtype == torch.int32
+        assert torch.ops.gradtts_b200.log_prior(torch.empty(2, 80, 7, device="cuda"), torch.empty(2, 80, 19, device="cuda")).shape == (2, 7, 19)
+        logw, mu_y = torch.ops.gradtts_b200.align_outputs(v, torch.empty(2, 80, 7, device="cuda"), torch.empty(2, 7, device="cuda"), True)
+        assert logw.shape == (2, 1, 7) and mu_y.shape == (2, 80, 19)
+        xt, zm = torch.ops.gradtts_b200.forward_diffusion(z, m, z, t, z, 0.05, 20.0)
+        assert xt.shape == z.shape and zm.shape == z.shape
+        assert torch.ops.gradtts_b200.score_loss(z, z, m, t, 0.05, 20.0).shape == ()
+    with pytest.raises(NotImplementedError):
+        torch.ops.gradtts_b200.log_prior(torch.zeros(1, 80, 3), torch.zeros(1, 80, 5))
