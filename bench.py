@@ -111,7 +111,10 @@ def cpu_reference_leg(n_spks, T, euler, budget_s=20.0, want_output=False):
     sd = pkg.synth.make_decoder_state_dict(n_spks, seed=0, g=0.05)
     B = WORKLOADS_BY_SHAPE.get((n_spks, T), CPU_SAMPLE_BATCH)
     bs = min(CPU_SAMPLE_BATCH, B)
-    z, mask, mu, spk, _ = pkg.synth.make_inputs(max(bs, 1), T, n_spks, seed=1, ragged=False)
+    # the first bs utterances of the workload's own batch (the generator stream depends on the batch size, so draw the full batch)
+    z, mask, mu, spk, _ = pkg.synth.make_inputs(B, T, n_spks, seed=1, ragged=False)
+    z, mask, mu = z[:bs].contiguous(), mask[:bs].contiguous(), mu[:bs].contiguous()
+    spk = spk[:bs].contiguous() if spk is not None else None
     y = None
     with torch.no_grad():
         decoder_oracle.reverse_diffusion(sd, z[:1, :, :64].contiguous(), mask[:1, :, :64].contiguous(),

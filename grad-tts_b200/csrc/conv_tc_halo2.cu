@@ -26,6 +26,320 @@ __device__ __forceinline__ constexpr uint32_t make_idesc2() {      // as make_id
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((256u >> 4) << 24);
 }
 
+
+// ================================================================================================ fused GroupNorm-apply epilogue
+// kApply: the conv does not write its raw output.  Every accumulator tile stays in TMEM while the epilogue warps read it once for
+// the GroupNorm sums (pass 1); when the LAST tile of a sample has been summed anywhere in the grid (per-sample grid barrier through
+// two global counters), every CTA reduces the sample's per-CTA partial rows itself, in the same fixed order, to (mean, rstd); the
+// epilogue warps then read their tiles of that sample a second time (pass 2), apply GroupNorm + Mish (+ time bias) (+ residual) and
+// the frame mask, and store the finished activation.  What this removes per Block: one bf16 write of the raw tensor and the whole
+// gn_apply pass (a read and a write), i.e. the pass that measured 23 % of the Euler step at 84-99 % of HBM bandwidth.
+//
+// Tiles of one sample are consecutive in every CTA's walk ("run"); a run must fit the TMEM accumulator ring (host check:
+// ceil(tiles per sample / grid) <= acc_bufs<N>()), otherwise the MMA warp would wait for a buffer that pass 2 can only free after
+// the barrier.  All CTAs must be co-resident for the barrier to complete: the grid is clamped to what cudaOccupancyMaxActiveClusters
+// reports (conv_tc_halo2_max_grid).  Shared memory: [misc+4096, +8192) holds the per-channel affine tables of two runs in flight
+// (scale = rstd*gamma, shift = (bias - mean)*scale + beta), the kApplyExtra bytes behind misc hold the time-bias rows and four
+// mbarriers (aff_full / aff_empty per table slot).
+constexpr int kApplyExtra = 3072;
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct ApplyShared {
+    float* s_sc;            // [2][N]
+    float* s_sh;            // [2][N]
+    float* s_tb;            // [2][N]
+    float* s_mr;            // [16] mean[8], rstd[8] of the run being finalised (statistics warp only)
+    uint64_t* aff_full;     // [2] statistics warp -> epilogue warps: tables of slot s are valid
+    uint64_t* aff_empty;    // [2] 16 epilogue warps -> statistics warp: slot s may be overwritten
+};
+template <int N>
+__device__ __forceinline__ ApplyShared apply_shared(uint8_t* misc) {
+    ApplyShared a;
+    a.s_sc = reinterpret_cast<float*>(misc + 4096);
+    a.s_sh = a.s_sc + 2 * N;
+    a.s_tb = reinterpret_cast<float*>(misc + kMiscBytes);
+    a.aff_full = reinterpret_cast<uint64_t*>(misc + kMiscBytes + 2048);
+    a.aff_empty = a.aff_full + 2;
+    a.s_mr = reinterpret_cast<float*>(misc + kMiscBytes + 2048 + 64);
+    return a;
+}
+
+// iterations [it, it_end) of this CTA that belong to the sample of iteration `it` (tile = blockIdx.x + it * gridDim.x); a dummy
+// tile (index past the end, odd tail of a CTA pair) is a run of its own without a sample (b = -1)
+__device__ __forceinline__ int apply_run_end(const TcParams& p, int it, int n_it, int tps, int* b_out) {
+    const int G = (int)gridDim.x;
+    const int tile0 = (int)blockIdx.x + it * G;
+    if (tile0 >= p.num_tiles) { *b_out = -1; return it + 1; }
+    const int b = tile0 / tps;
+    const int last_tile = (b + 1) * tps - 1;
+    int it_end = it + (last_tile - tile0) / G + 1;
+    if (it_end > n_it) it_end = n_it;
+    *b_out = b;
+    return it_end;
+}
+
+// Statistics warp (warp 3) of the kApply variant.
+template <int N>
+__device__ __forceinline__ void tc_stats_apply_loop(const TcParams& p, const TcShared& sh, int lane) {
+    constexpr int kGsz = N / 8;
+    const ConvEpilogue& e = p.e;
+    const ApplyShared ap = apply_shared<N>(sh.misc);
+    const int G = (int)gridDim.x, bx = (int)blockIdx.x;
+    const int tps = p.tiles_h * p.tiles_w;
+    const int n_it = tc_num_iters(p);
+    const int g = lane & 7, which = (lane >> 3) & 1, half = g >> 2, idx = which * 4 + (g & 3);
+    const int nrows = tps < G ? tps : G;                             // CTAs that hold tiles of any one sample
+    const double inv_count = 1.0 / ((double)kGsz * (double)p.Hout * (double)p.Wout);
+    unsigned int* cnt = e.gn_counters + 32;                          // [2b] arrivals, [2b+1] departures of sample b
+    int run = 0;
+    for (int it = 0; it < n_it;) {
+        int b;
+        const int it_end = apply_run_end(p, it, n_it, tps, &b);
+        float acc = 0.f;
+        for (int j = it; j < it_end; ++j) {
+            const int slot = j % kStatSlots;
+            mbar_wait(&sh.sfull[slot], (uint32_t)(j / kStatSlots) & 1u);
+            if (lane < 16 && b >= 0) {
+                const float* r = sh.s_ring + (slot * 8 + half * 4) * 8 + idx;
+                acc += (r[0] + r[8]) + (r[16] + r[24]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.sempty[slot]);
+        }
+        it = it_end;
+        if (b < 0) continue;
+        // ---- my partial row of sample b, then the per-sample grid barrier
+        if (lane < 16) e.gn_partials[((size_t)b * G + bx) * 16 + lane] = acc;
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+            atomicAdd(&cnt[2 * b], 1u);
+            while (ld_acquire_gpu_u32(&cnt[2 * b]) < (unsigned int)nrows) { }
+        }
+        __syncwarp();
+        // ---- every CTA reduces the rows of the contributing CTAs itself, all in the same order (deterministic; double)
+        const int start = tps < G ? (int)(((long long)b * tps) % G) : 0;
+        {
+            const int q = lane & 3, r0 = lane >> 2;
+            const float4* pp = reinterpret_cast<const float4*>(e.gn_partials + (size_t)b * G * 16) + q;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            for (int base = 0; base < nrows; base += 64) {
+                float4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int k = base + r0 + 8 * i;
+                    int c = start + k; if (c >= G) c -= G;
+                    v[i] = k < nrows ? __ldcg(pp + (size_t)c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    a0 += (double)v[i].x; a1 += (double)v[i].y; a2 += (double)v[i].z; a3 += (double)v[i].w;
+                }
+            }
+#pragma unroll
+            for (int off = 4; off < 32; off <<= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+                a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+                a3 += __shfl_xor_sync(0xffffffffu, a3, off);
+            }
+            // lanes 0,1 hold the sums of groups 4q..4q+3; lanes 2,3 the matching sums of squares
+            const double q0 = __shfl_sync(0xffffffffu, a0, (lane + 2) & 31), q1 = __shfl_sync(0xffffffffu, a1, (lane + 2) & 31);
+            const double q2 = __shfl_sync(0xffffffffu, a2, (lane + 2) & 31), q3 = __shfl_sync(0xffffffffu, a3, (lane + 2) & 31);
+            if (lane < 2) {
+                const double su[4] = {a0, a1, a2, a3}, sq[4] = {q0, q1, q2, q3};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double mean = su[j] * inv_count;
+                    double var = sq[j] * inv_count - mean * mean;
+                    if (var < 0.0) var = 0.0;
+                    const float mf = (float)mean, rf = (float)rsqrt(var + (double)e.gn_eps);
+                    const int gg = lane * 4 + j;
+                    ap.s_mr[gg] = mf; ap.s_mr[8 + gg] = rf;
+                    if (bx == start) {                               // one CTA publishes the statistics for later consumers / tests
+                        e.gn_stats[((size_t)b * 8 + gg) * 2 + 0] = mf;
+                        e.gn_stats[((size_t)b * 8 + gg) * 2 + 1] = rf;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // ---- affine tables of this run (slot = run parity); the slot is free once all 16 epilogue warps are done with run - 2
+        const int sl = run & 1;
+        mbar_wait(&ap.aff_empty[sl], ((uint32_t)(run >> 1) & 1u) ^ 1u);
+        for (int c = lane; c < N; c += 32) {
+            const int gg = c / kGsz;
+            const float sc = ap.s_mr[8 + gg] * __ldg(e.ap_gamma + c);
+            ap.s_sc[sl * N + c] = sc;
+            ap.s_sh[sl * N + c] = fmaf(sh.s_bias[c] - ap.s_mr[gg], sc, __ldg(e.ap_beta + c));
+            ap.s_tb[sl * N + c] = e.ap_tbias ? __ldg(e.ap_tbias + (size_t)b * e.ap_tb_bstride + c) : 0.f;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&ap.aff_full[sl]);                           // release: orders this warp's table writes (after __syncwarp)
+            // departure: whoever leaves last resets both counters for the next launch (everyone has finished polling by then)
+            if (atomicAdd(&cnt[2 * b + 1], 1u) == (unsigned int)(nrows - 1)) { cnt[2 * b] = 0u; cnt[2 * b + 1] = 0u; }
+        }
+        ++run;
+    }
+}
+
+// Epilogue warps (warps 4..19) of the kApply variant: two groups of 8 warps take alternate tile iterations, as in tc_epilogue_loop.
+template <int N, bool kTb, bool kRes>
+__device__ __forceinline__ void tc_epilogue_apply_loop(const TcParams& p, const TcShared& sh, uint32_t tmem_base, int warp, int lane) {
+    constexpr int kColsPerWarp = N / 2;
+    constexpr int kGsz = N / 8;
+    constexpr int kBufs = acc_bufs<N>();
+    const ApplyShared ap = apply_shared<N>(sh.misc);
+    const int ew16 = warp - 4, grp = ew16 >> 3, ew = ew16 & 7, wq = ew & 3, half = ew >> 2;
+    const int row = wq * 32 + lane;
+    const ConvEpilogue& e = p.e;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.out);
+    const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(e.residual);
+    const int cbase = half * kColsPerWarp;
+    int hl = row / p.bw, wl = row - hl * p.bw;
+    if (p.halo_t) { wl = row >> 3; hl = row & 7; }
+    const bool row_in_tile = hl < p.bh;
+    const float* s_bias = sh.s_bias;
+    const int G = (int)gridDim.x, tps = p.tiles_h * p.tiles_w;
+    const int n_it = tc_num_iters(p);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)cbase;
+    const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f);
+    TileWalk tw;
+    tw.init(p, (int)blockIdx.x, G);
+    int run = 0;
+    for (int it = 0; it < n_it;) {
+        int b;
+        const int it_end = apply_run_end(p, it, n_it, tps, &b);
+        // ------------------------------------------------------------ pass 1: GroupNorm sums of my tiles of this run
+        {
+            TileWalk w1 = tw;
+            for (int j = it; j < it_end; ++j, w1.advance(G)) {
+                if ((j & 1) != grp) continue;
+                const int buf = j % kBufs;
+                const int jj = w1.th * p.bh + hl, ii = w1.tw * p.bw + wl;
+                const bool valid = row_in_tile && (jj < p.Hg) && (ii < p.Wg) && (b >= 0);
+                mbar_wait(&sh.tfull[buf], (uint32_t)(j / kBufs) & 1u);
+                tc_fence_after();
+                float2 ssum[4], ssq[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) { ssum[g] = make_float2(0.f, 0.f); ssq[g] = make_float2(0.f, 0.f); }
+#pragma unroll
+                for (int c0 = 0; c0 < kColsPerWarp; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(lane_addr + (uint32_t)(buf * N + c0), r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q4 = 0; q4 < 8; ++q4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[cbase + c0 + q4 * 4]);
+                        float2 f0 = fadd2(make_float2(__uint_as_float(r[q4 * 4 + 0]), __uint_as_float(r[q4 * 4 + 1])), make_float2(b4.x, b4.y));
+                        float2 f1 = fadd2(make_float2(__uint_as_float(r[q4 * 4 + 2]), __uint_as_float(r[q4 * 4 + 3])), make_float2(b4.z, b4.w));
+                        // select, not multiply: rows outside the image hold whatever the zero-filled box produced (bias only) or garbage
+                        if (!valid) { f0 = make_float2(0.f, 0.f); f1 = make_float2(0.f, 0.f); }
+                        const int g0 = (c0 + q4 * 4) / kGsz, g1 = (c0 + q4 * 4 + 2) / kGsz;
+                        ssum[g0] = fadd2(ssum[g0], f0); ssq[g0] = ffma2(f0, f0, ssq[g0]);
+                        ssum[g1] = fadd2(ssum[g1], f1); ssq[g1] = ffma2(f1, f1, ssq[g1]);
+                    }
+                }
+                if (b < 0) {                                         // dummy tile: nothing to apply later, hand the buffer back now
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&sh.tempty[buf]), 0u));
+                }
+                float st[8];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) { st[g] = ssum[g].x + ssum[g].y; st[4 + g] = ssq[g].x + ssq[g].y; }
+                const float t = warp_reduce8(st, lane);
+                const int slot = j % kStatSlots;
+                mbar_wait(&sh.sempty[slot], ((uint32_t)(j / kStatSlots) & 1u) ^ 1u);
+                if ((lane & 3) == 0) sh.s_ring[(slot * 8 + ew) * 8 + (lane >> 2)] = t;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh.sfull[slot]);
+            }
+        }
+        // ------------------------------------------------------------ pass 2: normalise + Mish (+ bias) (+ residual), mask, store
+        if (b >= 0) {
+            const int sl = run & 1;
+            mbar_wait(&ap.aff_full[sl], (uint32_t)(run >> 1) & 1u);
+            const float* t_sc = ap.s_sc + sl * N + cbase;
+            const float* t_sh = ap.s_sh + sl * N + cbase;
+            const float* t_tb = ap.s_tb + sl * N + cbase;
+            TileWalk w2 = tw;
+            for (int j = it; j < it_end; ++j, w2.advance(G)) {
+                if ((j & 1) != grp) continue;
+                const int buf = j % kBufs;
+                const int jj = w2.th * p.bh + hl, ii = w2.tw * p.bw + wl;
+                const bool valid = row_in_tile && (jj < p.Hg) && (ii < p.Wg);
+                const size_t opix = valid ? ((size_t)b * p.Hout + jj) * p.Wout + ii : 0;
+                const float m = valid ? e.mask[(size_t)b * p.Wout + ii] : 0.f;
+                const float2 m2 = make_float2(m, m);
+#pragma unroll
+                for (int c0 = 0; c0 < kColsPerWarp; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(lane_addr + (uint32_t)(buf * N + c0), r);
+                    tmem_ld_wait();
+                    if (c0 + 32 >= kColsPerWarp) {                   // last TMEM read of this buffer: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&sh.tempty[buf]), 0u));
+                    }
+                    if (!valid) continue;
+                    float2 f[16];
+#pragma unroll
+                    for (int q4 = 0; q4 < 8; ++q4) {
+                        const float4 sc4 = *reinterpret_cast<const float4*>(&t_sc[c0 + q4 * 4]);
+                        const float4 sh4 = *reinterpret_cast<const float4*>(&t_sh[c0 + q4 * 4]);
+                        const float2 y0 = ffma2(make_float2(__uint_as_float(r[q4 * 4 + 0]), __uint_as_float(r[q4 * 4 + 1])),
+                                                make_float2(sc4.x, sc4.y), make_float2(sh4.x, sh4.y));
+                        const float2 y1 = ffma2(make_float2(__uint_as_float(r[q4 * 4 + 2]), __uint_as_float(r[q4 * 4 + 3])),
+                                                make_float2(sc4.z, sc4.w), make_float2(sh4.z, sh4.w));
+                        f[q4 * 2 + 0] = mish2_fast(y0, fmul2(y0, l2e));
+                        f[q4 * 2 + 1] = mish2_fast(y1, fmul2(y1, l2e));
+                        if (kTb) {
+                            const float4 tb4 = *reinterpret_cast<const float4*>(&t_tb[c0 + q4 * 4]);
+                            f[q4 * 2 + 0] = fadd2(f[q4 * 2 + 0], make_float2(tb4.x, tb4.y));
+                            f[q4 * 2 + 1] = fadd2(f[q4 * 2 + 1], make_float2(tb4.z, tb4.w));
+                        }
+                    }
+                    if (kRes) {
+                        const __nv_bfloat16* rp = res + opix * N + cbase + c0;
+#pragma unroll
+                        for (int v8 = 0; v8 < 2; ++v8) {
+                            uint32_t w[8];
+                            ld_global_nc_256(rp + v8 * 16, w);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                f[v8 * 8 + k] = fadd2(f[v8 * 8 + k], make_float2(__uint_as_float(w[k] << 16), __uint_as_float(w[k] & 0xffff0000u)));
+                        }
+                    }
+                    __nv_bfloat16* op = out + opix * N + cbase + c0;
+#pragma unroll
+                    for (int v8 = 0; v8 < 2; ++v8) {
+                        uint32_t w[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float2 o = fmul2(f[v8 * 8 + k], m2);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(o.x, o.y);
+                            w[k] = *reinterpret_cast<uint32_t*>(&h2);
+                        }
+                        st_global_256(op + v8 * 16, w);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ap.aff_empty[sl]);
+            ++run;
+        }
+        for (int j = it; j < it_end; ++j) tw.advance(G);
+        it = it_end;
+    }
+}
+
 constexpr int kFuseWarps = 4;                       // transform warps of the fused-input variant (warps 20..23, one per SMSP)
 
 // kFuse: the A tiles are the RAW output of the previous conv; four extra warps apply (Mish(GroupNorm(raw)) + tbias) * mask
@@ -38,7 +352,8 @@ constexpr int kFuseWarps = 4;                       // transform warps of the fu
 // (phase, tap) operands are shifted views of ONE halo box of the input tile, so the input crosses L2->SMEM once instead of 16
 // times (the per-tap kernel is fill-bound there: 372 TFLOP/s).  Every phase has its own accumulator and epilogue iteration
 // (TcParams::ph_inner = 4, phases innermost); the epilogue multiplies by the mask (kMask).
-template <int N, bool kStats, bool kFuse, bool kMask = false, bool kConvT = false>
+// kApply: 0 = off, 1 = GroupNorm-apply epilogue with time bias (block1 of a ResnetBlock), 2 = with residual (block2)
+template <int N, bool kStats, bool kFuse, bool kMask = false, bool kConvT = false, int kApply = 0>
 __global__ void __launch_bounds__(kThreads + (kFuse ? kFuseWarps * 32 : 0), 1)
 conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                      const __grid_constant__ CUtensorMap mapWh, const TcParams p) {
@@ -71,6 +386,10 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
         if (kFuse) for (int s = 0; s < nstage; ++s) mbar_init(&rawfull[s], 1);
         for (int i = 0; i < kBufs; ++i) { mbar_init(&sh.tfull[i], 1); mbar_init(&sh.tempty[i], 16); }   // 8 warps x 2 CTAs
         for (int i = 0; i < kStatSlots; ++i) { mbar_init(&sh.sfull[i], 8); mbar_init(&sh.sempty[i], 1); }
+        if (kApply) {
+            const ApplyShared ap = apply_shared<N>(sh.misc);
+            for (int i = 0; i < 2; ++i) { mbar_init(&ap.aff_full[i], 1); mbar_init(&ap.aff_empty[i], 16); }
+        }
         mbar_fence_init();
     } else if (warp == 2) {
         tmem_alloc2(sh.tmem_slot, kBufs * N);
@@ -269,9 +588,11 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
             }
         }
     } else if (warp == 3) {
-        tc_stats_loop<kStats>(p, sh, lane);
+        if (kApply) tc_stats_apply_loop<N>(p, sh, lane);
+        else tc_stats_loop<kStats>(p, sh, lane);
     } else if (warp >= 4 && warp < kThreads / 32) {
-        tc_epilogue_loop<N, kStats, false, kMask>(p, sh, tmem_base, warp, lane);
+        if (kApply) tc_epilogue_apply_loop<N, kApply == 1, kApply == 2>(p, sh, tmem_base, warp, lane);
+        else tc_epilogue_loop<N, kStats, false, kMask>(p, sh, tmem_base, warp, lane);
     } else if (kFuse && warp >= kThreads / 32) {
         // ================================================================ input transform (both CTAs)
         // thread -> 16-byte chunk j (8 channels) of rows r0, r0+16, ...; the 128-byte swizzle puts chunk j of row r at
@@ -342,13 +663,13 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
             }
         }
     }
-    tc_teardown<N, kStats, true>(p, sh, smem, tmem_base, tid, warp, lane);
+    tc_teardown<N, kStats && !kApply, true>(p, sh, smem, tmem_base, tid, warp, lane);   // kApply finalises its statistics per sample, in the loop
 }
 
-template <int N, bool kStats, bool kFuse, bool kMask = false, bool kConvT = false>
+template <int N, bool kStats, bool kFuse, bool kMask = false, bool kConvT = false, int kApply = 0>
 int launch_halo2(const TcConvPlan* pl, cudaStream_t stream) {
     static bool attr_set = false;
-    auto k = conv_tc_halo2_kernel<N, kStats, kFuse, kMask, kConvT>;
+    auto k = conv_tc_halo2_kernel<N, kStats, kFuse, kMask, kConvT, kApply>;
     if (!attr_set) {
         GTTS_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
@@ -361,6 +682,32 @@ int launch_halo2(const TcConvPlan* pl, cudaStream_t stream) {
 
 }  // namespace
 
+// Largest grid (CTAs, even) whose 2-CTA clusters are all co-resident for the apply variant with this much dynamic shared memory: the
+// per-sample grid barrier needs every CTA of the grid on an SM at the same time.  0 if the query fails.
+namespace {
+template <int N, int kApply>
+int max_grid_of(size_t smem) {
+    auto k = conv_tc_halo2_kernel<N, true, false, false, false, kApply>;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) { cudaGetLastError(); return 0; }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return 2 * n;
+}
+}  // namespace
+
+int conv_tc_halo2_max_grid(int N, bool residual, size_t smem) {
+    if (residual) return N == 64 ? max_grid_of<64, 2>(smem) : (N == 128 ? max_grid_of<128, 2>(smem) : max_grid_of<256, 2>(smem));
+    return N == 64 ? max_grid_of<64, 1>(smem) : (N == 128 ? max_grid_of<128, 1>(smem) : max_grid_of<256, 1>(smem));
+}
+int conv_tc_halo2_apply_extra_smem() { return kApplyExtra; }
+
 int conv_tc_halo2_launch(const TcConvPlan* pl, cudaStream_t stream) {
     const ConvEpilogue& e = pl->p.e;
     if (pl->p.ph_inner == 4) {                                      // transposed conv: mask epilogue, no statistics
@@ -369,6 +716,22 @@ int conv_tc_halo2_launch(const TcConvPlan* pl, cudaStream_t stream) {
         if (pl->N == 64) return launch_halo2<64, false, false, true, true>(pl, stream);
         if (pl->N == 128) return launch_halo2<128, false, false, true, true>(pl, stream);
         set_error("conv_tc_halo2: ConvT variant supports 64 / 128 channels");
+        return 2;
+    }
+    if (e.apply) {                                                  // GroupNorm-apply epilogue: time-bias or residual flavour
+        GTTS_REQUIRE(e.gn_partials && e.gn_stats && e.gn_counters && e.mask && e.ap_gamma && e.ap_beta && !e.in_stats,
+                     "conv_tc_halo2: the apply epilogue needs statistics buffers, affine parameters and the mask");
+        GTTS_REQUIRE((e.residual != nullptr) != (e.ap_tbias != nullptr), "conv_tc_halo2: the apply epilogue takes a time bias or a residual");
+        if (e.residual) {
+            if (pl->N == 64) return launch_halo2<64, true, false, false, false, 2>(pl, stream);
+            if (pl->N == 128) return launch_halo2<128, true, false, false, false, 2>(pl, stream);
+            if (pl->N == 256) return launch_halo2<256, true, false, false, false, 2>(pl, stream);
+        } else {
+            if (pl->N == 64) return launch_halo2<64, true, false, false, false, 1>(pl, stream);
+            if (pl->N == 128) return launch_halo2<128, true, false, false, false, 1>(pl, stream);
+            if (pl->N == 256) return launch_halo2<256, true, false, false, false, 1>(pl, stream);
+        }
+        set_error("conv_tc_halo2: unsupported Cout");
         return 2;
     }
     GTTS_REQUIRE(e.residual == nullptr && e.mask == nullptr, "conv_tc_halo2: plain or GN-statistics epilogue only");

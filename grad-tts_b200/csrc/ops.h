@@ -51,6 +51,16 @@ struct ConvEpilogue {
     const float* in_tbias;    // [B or 1][Cin] (stride in_tb_bstride floats per sample; 0 = shared)
     int in_tb_bstride;
     const float* in_mask;     // [B][W]
+    // GroupNorm apply fused into THIS conv's epilogue (CTA-pair halo kernel only; apply = 0: off).  The kernel keeps every
+    // accumulator tile of a sample in TMEM until the sample's statistics are complete (per-sample grid barrier), then writes
+    //     out = (Mish(GroupNorm(acc + bias)) [+ ap_tbias] [+ residual]) * mask
+    // so the raw conv output never goes to HBM and the separate gn_apply pass disappears (reference: Block.forward and the two
+    // adds of ResnetBlock.forward, model/diffusion.py:52-58, 75-78).  Needs gn_partials / gn_stats / gn_counters and mask.
+    int apply;
+    const float* ap_gamma;    // [Cout]
+    const float* ap_beta;     // [Cout]
+    const float* ap_tbias;    // [B or 1][Cout] added after Mish (stride ap_tb_bstride floats per sample; null = off)
+    int ap_tb_bstride;
 };
 
 // CUDA-core implicit GEMM (fp32 accumulate, FFMA).  Strict-fp32 path and debugging cross-check.
@@ -71,6 +81,10 @@ void conv_tc_plan_set_debug(TcConvPlan* p, unsigned long long* dbg_out);   // pe
 int conv_tc_plan_grid(const TcConvPlan* p);
 bool conv_tc_cta2_enabled();
 bool conv_tc_convT_halo_eligible(const ConvGeom& g);
+// true when a 3x3 stride-1 conv of this geometry can run with the GroupNorm-apply epilogue (ConvEpilogue::apply): CTA-pair halo
+// kernel, and no CTA owns more tiles of one sample than there are TMEM accumulator buffers
+bool conv_tc_apply_eligible(const ConvGeom& g, int num_sms);
+size_t conv_tc_counter_words(int B);   // unsigned ints in ConvEpilogue::gn_counters for a batch of B samples
 int microbench_issue(int N, int n_mma, int n_commit, int iters, int wait_each, int grid, unsigned long long* out_dev,
                      cudaStream_t stream);                                  // tcgen05 issue-path micro-benchmark
 int conv_tc_launch(const TcConvPlan* p, cudaStream_t stream);
