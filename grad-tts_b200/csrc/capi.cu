@@ -263,6 +263,64 @@ int gtts_test_issue_microbench(int N, int n_mma, int n_commit, int iters, int wa
     return 0;
 }
 
+// 3x3 stride-1 conv with the GroupNorm-apply epilogue (conv_tc_halo2.cu, kApply): out = (Mish(GN(conv + bias)) [+ tbias] [+ residual]) * mask
+int gtts_test_conv_apply(int B, int H, int W, int Cin0, int Cin1, int Cout, const void* src0, const void* src1, const float* weight_pt,
+                         const float* bias, const float* gamma, const float* beta, const float* tbias, int tb_bstride,
+                         const void* residual, const float* mask, void* out, float* gn_stats, int reps, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    GTTS_REQUIRE(src0 && weight_pt && gamma && beta && mask && out && gn_stats, "null argument");
+    const int Cin = Cin0 + Cin1;
+    ConvGeom g;
+    memset(&g, 0, sizeof(g));
+    g.B = B; g.Hin = H; g.Win = W; g.Hg = H; g.Wg = W; g.Hout = H; g.Wout = W;
+    g.Cin0 = Cin0; g.Cin1 = Cin1; g.Cout = Cout; g.ntaps = 9; g.nphase = 1; g.stride = 1; g.out_step = 1;
+    for (int t = 0; t < 9; ++t) { g.dy[0][t] = (int8_t)(t / 3 - 1); g.dx[0][t] = (int8_t)(t % 3 - 1); g.wrow[0][t] = t * Cout; }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    GTTS_REQUIRE(conv_tc_apply_eligible(g, sms), "gtts_test_conv_apply: geometry not eligible for the apply epilogue");
+    void* wpk = nullptr;
+    float* partials = nullptr;
+    unsigned int* counters = nullptr;
+    GTTS_CHECK_CUDA(cudaMalloc(&wpk, (size_t)9 * Cout * Cin * 2));
+    if (int rc = pack_conv_weight(ACT_BF16, weight_pt, wpk, Cout, Cin, 3, 3, s)) return rc;
+    GTTS_CHECK_CUDA(cudaMalloc(&partials, (size_t)B * conv_tc_halo_partials_slots(g) * 16 * 4));
+    GTTS_CHECK_CUDA(cudaMalloc(&counters, conv_tc_counter_words(B) * 4));
+    GTTS_CHECK_CUDA(cudaMemsetAsync(counters, 0, conv_tc_counter_words(B) * 4, s));
+    ConvEpilogue e;
+    memset(&e, 0, sizeof(e));
+    e.bias = bias; e.residual = residual; e.mask = mask; e.out = out;
+    e.gn_partials = partials; e.gn_stats = gn_stats; e.gn_counters = counters; e.gn_eps = 1e-5f;
+    e.apply = 1; e.ap_gamma = gamma; e.ap_beta = beta; e.ap_tbias = tbias; e.ap_tb_bstride = tb_bstride;
+    int rc = 0;
+    TcConvPlan* tp = conv_tc_plan_create(g, src0, src1, wpk, 9 * Cout, e, sms, 2);
+    if (!tp) rc = 1;
+    else {
+        rc = conv_tc_launch(tp, s);                       // the counters return to zero by themselves: launch again and again
+        if (reps > 1 && rc == 0) {
+            cudaEvent_t e0, e1;
+            cudaEventCreate(&e0); cudaEventCreate(&e1);
+            cudaEventRecord(e0, s);
+            for (int i = 1; i < reps && rc == 0; ++i) rc = conv_tc_launch(tp, s);
+            cudaEventRecord(e1, s);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            fprintf(stderr, "[gtts_test_conv_apply] B=%d H=%d W=%d Cin=%d Cout=%d grid=%d: %.1f us/launch\n", B, H, W, Cin, Cout,
+                    conv_tc_plan_grid(tp), 1e3f * ms / (reps - 1));
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+        }
+        cudaStreamSynchronize(s);
+        conv_tc_plan_destroy(tp);
+    }
+    cudaError_t ce = cudaStreamSynchronize(s);
+    cudaFree(wpk); cudaFree(partials); cudaFree(counters);
+    if (rc) return rc;
+    GTTS_CHECK_CUDA(ce);
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, int Cin1, int Cout, const void* src0,
                    const void* src1, const float* weight_pt, const float* bias, const void* residual,
                    const float* mask, void* out, float* gn_stats, int per_sample_weights, void* stream) {
@@ -321,8 +379,8 @@ int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, i
         size_t slots = impl >= 1 ? conv_tc_partials_slots(g) : conv_ffma_partials_slots(g);
         if (halo_mode && conv_tc_halo_eligible(g)) slots = conv_tc_halo_partials_slots(g);
         GTTS_CHECK_CUDA(cudaMalloc(&partials, (size_t)B * slots * 16 * 4));
-        GTTS_CHECK_CUDA(cudaMalloc(&counters, (size_t)(B + 32) * 4));
-        GTTS_CHECK_CUDA(cudaMemsetAsync(counters, 0, (size_t)(B + 32) * 4, s));
+        GTTS_CHECK_CUDA(cudaMalloc(&counters, conv_tc_counter_words(B) * 4));
+        GTTS_CHECK_CUDA(cudaMemsetAsync(counters, 0, conv_tc_counter_words(B) * 4, s));
         e.gn_partials = partials; e.gn_stats = gn_stats; e.gn_counters = counters; e.gn_eps = 1e-5f;
     }
     int rc = 0;

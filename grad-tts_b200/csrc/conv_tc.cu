@@ -213,18 +213,68 @@ bool conv_tc_convT_halo_eligible(const ConvGeom& g) {
 
 size_t conv_tc_halo_partials_slots(const ConvGeom&) { return 256; }    // one partial per (sample, CTA); grid <= #SMs
 
+// [0] root ticket, [1..16] group tickets (tc_teardown), [32 + 2b] / [33 + 2b] arrivals / departures of sample b at the per-sample
+// grid barrier of the GroupNorm-apply epilogue (conv_tc_halo2.cu)
+size_t conv_tc_counter_words(int B) { return (size_t)32 + 2 * (size_t)B + 32; }
+
+namespace {
+// halo tiling of the CTA-pair kernel (must match conv_tc_plan_create)
+void halo2_tiles(const ConvGeom& g, int* tiles_h, int* tiles_w) {
+    int bh = 16, bw = 8;
+    if (g.Hg >= 10 && g.Wg >= 18 && !getenv("GTTS_HALO_NO_T")) {
+        const long t0 = (long)((g.Hg + 15) / 16) * ((g.Wg + 7) / 8), t1 = (long)((g.Hg + 7) / 8) * ((g.Wg + 15) / 16);
+        if (t1 < t0) { bh = 8; bw = 16; }
+    }
+    *tiles_h = (g.Hg + bh - 1) / bh;
+    *tiles_w = (g.Wg + bw - 1) / bw;
+}
+// A sample's tiles must fit the TMEM accumulator ring of every CTA pair: a pair works on tiles 2q, 2q+1 of each walk step, so
+// when a sample can start on an odd tile index (odd tile count per sample) the two CTAs' runs of that sample are offset by one step.
+bool apply_run_fits(int tps, int grid, int N) {
+    const int bufs = N <= 64 ? 8 : (N <= 128 ? 4 : 2);
+    const int run = (tps + grid - 1) / grid + ((tps & 1) ? 1 : 0);
+    return run <= bufs;
+}
+int apply_grid(long num_tiles, int num_sms) {
+    int gmax = num_sms & ~1;
+    if (gmax > 256) gmax = 256;
+    const long need = (num_tiles + 1) & ~1L;
+    return (int)(need < gmax ? need : gmax);
+}
+}  // namespace
+
+bool conv_tc_apply_eligible(const ConvGeom& g, int num_sms) {
+    if (const char* e = getenv("GTTS_APPLY")) { if (atoi(e) == 0) return false; }
+    if (!conv_tc_cta2_enabled() || !conv_tc_halo_eligible(g) || num_sms < 2) return false;
+    int th, tw;
+    halo2_tiles(g, &th, &tw);
+    const int tps = th * tw;
+    const long num_tiles = (long)g.B * tps;
+    if (num_tiles < 2) return false;
+    int min_h = 0;                                                   // GTTS_APPLY_MAXH: only levels with H <= this (experiments)
+    if (const char* e = getenv("GTTS_APPLY_MAXH")) min_h = atoi(e);
+    if (min_h && g.Hg > min_h) return false;
+    // 16 CTAs of margin: the grid is clamped to the clusters that can be co-resident (conv_tc_halo2_max_grid), known only on the device
+    const int grid = apply_grid(num_tiles, num_sms);
+    return apply_run_fits(tps, grid > 32 ? grid - 16 : grid, g.Cout);
+}
+
 TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void* src1, const void* weight,
                                 int weight_rows, const ConvEpilogue& e, int num_sms, int halo_mode) {
     if (!(g.Cout == 64 || g.Cout == 128 || g.Cout == 256)) { set_error("conv_tc: Cout must be 64/128/256"); return nullptr; }
     if (g.Cin0 % 64 || g.Cin1 % 64 || g.Cin0 <= 0) { set_error("conv_tc: Cin must be a multiple of 64"); return nullptr; }
     if (g.stride == 2 && (g.Cin1 != 0 || (g.Hin & 1) || (g.Win & 1))) { set_error("conv_tc: bad stride-2 geometry"); return nullptr; }
-    if (e.gn_partials && (g.nphase != 1 || e.residual || e.mask)) { set_error("conv_tc: GN statistics only on plain convs"); return nullptr; }
+    if (e.gn_partials && !e.apply && (g.nphase != 1 || e.residual || e.mask)) { set_error("conv_tc: GN statistics only on plain convs"); return nullptr; }
+    if (e.apply && !(halo_mode == 2 && conv_tc_halo_eligible(g) && conv_tc_cta2_enabled() && e.gn_partials && e.mask)) {
+        set_error("conv_tc: the GroupNorm-apply epilogue needs the CTA-pair halo kernel, statistics buffers and a mask");
+        return nullptr;
+    }
     TcConvPlan* pl = new TcConvPlan();
     memset(pl, 0, sizeof(*pl));
     TcParams& p = pl->p;
     const bool convT_halo = halo_mode == 2 && conv_tc_convT_halo_eligible(g) && e.mask && !e.residual && !e.gn_partials &&
                             num_sms >= 2;
-    if (halo_mode && !convT_halo && (!conv_tc_halo_eligible(g) || e.residual || e.mask)) halo_mode = 0;
+    if (halo_mode && !convT_halo && !e.apply && (!conv_tc_halo_eligible(g) || e.residual || e.mask)) halo_mode = 0;
     p.halo_mode = halo_mode;
     if (halo_mode) {
         // 128-pixel halo tile: 16 rows x 8 pixels (8-row UMMA groups run along W), or transposed 8 rows x 16 pixels with
@@ -251,7 +301,8 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
     p.e = e;
     { const char* dbg = getenv("GTTS_CONV_DBG"); p.dbg = dbg ? atoi(dbg) : 0; }
     pl->N = g.Cout;
-    const int budget = 227 * 1024 - kMiscBytes - 1024;
+    const int apply_extra = e.apply ? conv_tc_halo2_apply_extra_smem() : 0;
+    const int budget = 227 * 1024 - kMiscBytes - 1024 - apply_extra;
     if (halo_mode) {
         // A ring: halo boxes of 18 x 16 pixels x 64 ch (36 KB); B: resident (all 9*nck tiles) if it fits, else a ring
         const int nck = p.nchunk0 + p.nchunk1, btile = g.Cout * 128, ntiles_b = (convT_halo ? 16 : 9) * nck;
@@ -279,7 +330,7 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
                 if (p.b_slots > 16) p.b_slots = 16;
             }
             if (convT_halo && p.stages < nck) { set_error("conv_tc: ConvT halo variant: not enough A stages"); delete pl; return nullptr; }
-            pl->smem = (size_t)p.stages * abytes + (size_t)p.b_slots * bhalf + kMiscBytes + 1024;
+            pl->smem = (size_t)p.stages * abytes + (size_t)p.b_slots * bhalf + kMiscBytes + 1024 + apply_extra;
         } else {
         if (ntiles_b <= 16 && max_st >= 6 && ntiles_b * btile + 6 * abytes <= budget) { p.stages = 6; p.b_resident = 1; p.b_slots = ntiles_b; }
         else if (ntiles_b <= 16 && ntiles_b * btile + 4 * abytes <= budget) { p.stages = 4; p.b_resident = 1; p.b_slots = ntiles_b; }
@@ -326,6 +377,18 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
             if (gmax > 256) gmax = 256;
             const int need = (p.num_tiles + 1) & ~1;
             pl->grid = need < gmax ? need : gmax;
+        }
+    }
+    if (e.apply) {
+        // per-sample grid barrier: every CTA of the grid must be on an SM at the same time
+        if (p.mc != 2) { set_error("conv_tc: the GroupNorm-apply epilogue needs the CTA-pair halo kernel (geometry not eligible)"); delete pl; return nullptr; }
+        const int cores = conv_tc_halo2_max_grid(g.Cout, e.residual != nullptr, pl->smem);
+        if (cores >= 2 && cores < pl->grid) pl->grid = cores & ~1;
+        if (const char* ge = getenv("GTTS_APPLY_GRID")) { const int gg = atoi(ge) & ~1; if (gg >= 2 && gg < pl->grid) pl->grid = gg; }
+        if (!apply_run_fits(p.tiles_h * p.tiles_w, pl->grid, g.Cout)) {
+            set_error("conv_tc: GroupNorm-apply epilogue: a sample's tiles do not fit the TMEM accumulator ring at grid " + std::to_string(pl->grid));
+            delete pl;
+            return nullptr;
         }
     }
 

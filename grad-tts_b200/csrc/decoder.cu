@@ -127,6 +127,8 @@ struct Decoder {
     int fuse_gn = 0;          // 1: block2 convs apply block1's GroupNorm+Mish(+time bias, mask) on their operand tiles (no gn_apply
                               // pass).  Bitwise identical, but measured SLOWER (64->64 @L0: 435 us vs 134 + 103 us): GN+Mish at
                               // 5 TB/s already needs a whole SM's issue/MUFU capacity, four transform warps cannot supply it.
+    int fuse_epi = 1;         // 1: Block convs apply GroupNorm+Mish(+time bias / residual, mask) in their own epilogue (accumulators wait in
+                              // TMEM for the sample's statistics, per-sample grid barrier): no raw tensor, no gn_apply pass
     int halo_mode = 2;        // 3x3 convs: 0 = per-tap boxes, 1/2 = halo box (18x16 / 18x10) + shifted descriptor views
     std::map<std::string, float*> params;
     std::map<std::string, size_t> param_numel;
@@ -462,11 +464,22 @@ struct PlanBuilder {
         return g.Cin1 == 0 && tiles >= 2 && d->num_sms >= 2;
     }
 
+    struct Apply { const float* gamma; const float* beta; const float* tbias; int tb_bstride; };
+
+    // true when a Block conv of this geometry can finish GroupNorm+Mish in its own epilogue (ConvEpilogue::apply)
+    bool can_apply(const ConvGeom& g) const {
+        return use_tc() && d->fuse_epi && d->halo_mode == 2 && conv_tc_apply_eligible(g, d->num_sms);
+    }
+
     void add_conv(const ConvGeom& g, const void* src0, const void* src1, const void* w, int wrows, const float* bias,
-                  const void* residual, const float* mask, void* out, float* gn_stats, const InFuse* fuse = nullptr) {
+                  const void* residual, const float* mask, void* out, float* gn_stats, const InFuse* fuse = nullptr,
+                  const Apply* apply = nullptr) {
         ConvEpilogue e;
         memset(&e, 0, sizeof(e));
         e.bias = bias; e.residual = residual; e.mask = mask; e.out = out;
+        if (apply) {
+            e.apply = 1; e.ap_gamma = apply->gamma; e.ap_beta = apply->beta; e.ap_tbias = apply->tbias; e.ap_tb_bstride = apply->tb_bstride;
+        }
         if (fuse) {
             e.in_stats = fuse->stats; e.in_gamma = fuse->gamma; e.in_beta = fuse->beta; e.in_tbias = fuse->tbias;
             e.in_tb_bstride = fuse->tb_bstride; e.in_mask = fuse->mask;
@@ -482,7 +495,7 @@ struct PlanBuilder {
         // algorithmic bytes: read every input once, write every output once, weights once
         const double bytes = ((double)g.B * g.Hin * g.Win * cin + (double)g.B * g.Hout * g.Wout * g.Cout * (residual ? 2 : 1)) * es +
                              (double)wrows * cin * es;
-        std::string name = std::string(g.nphase == 4 ? "convT4x4" : (g.ntaps == 9 ? (g.stride == 2 ? "conv3x3s2" : "conv3x3") : "conv1x1")) +
+        std::string name = std::string(g.nphase == 4 ? "convT4x4" : (g.ntaps == 9 ? (g.stride == 2 ? "conv3x3s2" : (apply ? "conv3x3gn" : "conv3x3")) : "conv1x1")) +
                            "_" + std::to_string((int)cin) + "_" + std::to_string(g.Cout) + "_h" + std::to_string(g.Hin);
         if (use_tc()) {
             TcConvPlan* tp = conv_tc_plan_create(g, src0, src1, w, wrows, e, d->num_sms, d->halo_mode);   // the plan drops the halo path where the epilogue or geometry rules it out
@@ -519,9 +532,16 @@ struct PlanBuilder {
         const ResnetW& R = P->res[r];
         const int Co = R.cout;
         const float* tb = pl->tb + R.tb_off;
+        const int tb_bstride = pl->est_mode ? 1792 : 0;
+        const ConvGeom g1 = geom_3x3(B, H[lvl], W[lvl], r == 0 ? 64 : c0, r == 0 ? 0 : c1, Co, 1);
         const ConvGeom g2 = geom_3x3(B, H[lvl], W[lvl], Co, 0, Co, 1);
-        const bool fuse2 = can_fuse_input(g2);           // block2's conv applies block1's GroupNorm+Mish itself: no a1 tensor
-        void* raw1 = act(lvl, Co); void* a1 = fuse2 ? nullptr : act(lvl, Co); void* raw2 = act(lvl, Co); void* out = act(lvl, Co);
+        const bool ap1 = r != 0 && can_apply(g1);        // block1 writes Mish(GN(conv)) + time bias itself (r == 0: the first conv is not a tcgen05 kernel)
+        const bool ap2 = r != 0 && can_apply(g2);        // block2 writes Mish(GN(conv)) + residual itself (r == 0: residual computed inline by gn_apply)
+        const bool fuse2 = !ap1 && !ap2 && can_fuse_input(g2);   // older variant: block2's conv applies block1's GroupNorm+Mish on its operand tiles
+        void* raw1 = ap1 ? nullptr : act(lvl, Co);
+        void* a1 = fuse2 ? nullptr : act(lvl, Co);
+        void* raw2 = ap2 ? nullptr : act(lvl, Co);
+        void* out = act(lvl, Co);
         float* st1 = stats(); float* st2 = stats();
         if (failed) return nullptr;
         if (r == 0) {
@@ -535,17 +555,13 @@ struct PlanBuilder {
             const double px = (double)B * H[0] * W[0];
             pl->push("first_conv", 0, 2.0 * px * 64 * 9 * d->cin_first, px * (8 + 64 * esize(kind)),
                      [k, f](cudaStream_t s) { return first_conv(k, f, s); });
+        } else if (ap1) {
+            Apply ap{R.b1.gamma, R.b1.beta, tb, tb_bstride};
+            add_conv(g1, x0, x1, R.b1.w, 9 * Co, R.b1.bias, nullptr, lmask[lvl], a1, st1, nullptr, &ap);
         } else {
-            add_conv(geom_3x3(B, H[lvl], W[lvl], c0, c1, Co, 1), x0, x1, R.b1.w, 9 * Co, R.b1.bias, nullptr, nullptr, raw1, st1);
+            add_conv(g1, x0, x1, R.b1.w, 9 * Co, R.b1.bias, nullptr, nullptr, raw1, st1);
         }
-        if (fuse2) {
-            // block1's GroupNorm + Mish + time bias + mask are applied by block2's conv on its operand tiles
-            InFuse fz{st1, R.b1.gamma, R.b1.beta, tb, pl->est_mode ? 1792 : 0, lmask[lvl]};
-            add_conv(g2, raw1, nullptr, R.b2.w, 9 * Co, R.b2.bias, nullptr, nullptr, raw2, st2, &fz);
-        } else {
-            add_gn_apply(lvl, Co, raw1, st1, R.b1, tb, nullptr, false, a1);
-            add_conv(g2, a1, nullptr, R.b2.w, 9 * Co, R.b2.bias, nullptr, nullptr, raw2, st2);
-        }
+        // the residual branch first: the fused block2 epilogue adds it
         const void* resid = nullptr;
         bool first_res = false;
         if (r == 0) {
@@ -557,7 +573,21 @@ struct PlanBuilder {
         } else {
             resid = x0;                                   // Identity(x * mask): x is stored masked
         }
-        add_gn_apply(lvl, Co, raw2, st2, R.b2, nullptr, resid, first_res, out);
+        if (failed) return nullptr;
+        if (fuse2) {
+            // block1's GroupNorm + Mish + time bias + mask are applied by block2's conv on its operand tiles
+            InFuse fz{st1, R.b1.gamma, R.b1.beta, tb, tb_bstride, lmask[lvl]};
+            add_conv(g2, raw1, nullptr, R.b2.w, 9 * Co, R.b2.bias, nullptr, nullptr, raw2, st2, &fz);
+        } else {
+            if (!ap1) add_gn_apply(lvl, Co, raw1, st1, R.b1, tb, nullptr, false, a1);
+            if (ap2) {
+                Apply ap{R.b2.gamma, R.b2.beta, nullptr, 0};
+                add_conv(g2, a1, nullptr, R.b2.w, 9 * Co, R.b2.bias, resid, lmask[lvl], out, st2, nullptr, &ap);
+            } else {
+                add_conv(g2, a1, nullptr, R.b2.w, 9 * Co, R.b2.bias, nullptr, nullptr, raw2, st2);
+            }
+        }
+        if (!ap2) add_gn_apply(lvl, Co, raw2, st2, R.b2, nullptr, resid, first_res, out);
         release(raw1); release(a1); release(raw2);
         if (resid != x0) release(resid);
         return out;
@@ -639,7 +669,7 @@ struct PlanBuilder {
         pl->step = (int*)pl->mem.alloc(16, true);
         pl->noise_slot = (NoiseSlot*)pl->mem.alloc(sizeof(NoiseSlot), true);
         pl->h_dev = (float*)pl->mem.alloc(16, true);
-        pl->counters = (unsigned int*)pl->mem.alloc((size_t)(B + 32) * 4, true);   // per-sample tickets or 1 + 16 group tickets
+        pl->counters = (unsigned int*)pl->mem.alloc(conv_tc_counter_words(B) * 4, true);   // tickets + per-sample barrier counters
         // GN partial buffer: the largest slot count of any conv (level 0, either tiling)
         {
             ConvGeom g0 = geom_3x3(B, H[0], W[0], 64, 0, 64, 1);
@@ -808,7 +838,8 @@ void drop_plans(Decoder* d, bool drop_pool) {
 int get_plan(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, cudaStream_t stream, Plan** out) {
     std::string key = std::to_string((int)kind) + ":" + std::to_string(B) + ":" + std::to_string(T) + ":" +
                       (est_mode ? "e" : "s") + (sde ? "n" : "o") + (d->use_graph ? "g" : "x") +
-                      std::to_string(d->conv_impl_bf16) + std::to_string(d->halo_mode) + std::to_string(d->fused_attn) + std::to_string(d->fuse_gn);
+                      std::to_string(d->conv_impl_bf16) + std::to_string(d->halo_mode) + std::to_string(d->fused_attn) + std::to_string(d->fuse_gn) +
+                      std::to_string(d->fuse_epi);
     auto it = d->plans.find(key);
     if (it != d->plans.end()) {
         it->second.last_use = ++d->use_clock;
@@ -1047,6 +1078,7 @@ int decoder_set_option(Decoder* d, const char* key, int value) {
     else if (k == "halo_mode") d->halo_mode = value;
     else if (k == "fused_attn") d->fused_attn = value;
     else if (k == "fuse_gn") d->fuse_gn = value;
+    else if (k == "fuse_epi") d->fuse_epi = value;
     else { set_error("unknown option " + k); return 2; }
     return 0;
 }

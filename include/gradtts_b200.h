@@ -93,7 +93,9 @@ int gtts_decoder_set_param(gtts_decoder* d, const char* name, const float* data,
 /* options: "max_chunk" (samples per workspace chunk, <= 64), "max_plans" (LRU bound on cached per-(B,T) plans; default 24),
  * "trim" (any value: free every cached plan and the pooled workspace), "use_graph" (0/1), "conv_impl_bf16" (1 tcgen05, 0 FFMA cross-check),
  * "halo_mode" (3x3 convs: 0 per-tap TMA boxes, 1 / 2 halo box 18x16 / 18x10 + shifted descriptor views),
- * "fused_attn" (1: fused k-projection + context kernel for C <= 128, 0: 1x1 kv conv + context kernel) */
+ * "fused_attn" (1: fused k-projection + context kernel for C <= 128, 0: 1x1 kv conv + context kernel),
+ * "fuse_epi" (1, default: Block convs finish GroupNorm+Mish(+time bias / residual) in their own epilogue -- no gn_apply pass; 0: separate pass),
+ * "fuse_gn" (1: block2 convs apply block1's GroupNorm+Mish on their operand tiles; only used with fuse_epi = 0) */
 int gtts_decoder_set_option(gtts_decoder* d, const char* key, int value);
 
 /* z, mu, out: [B][80][T] fp32; mask: [B][1][T] fp32 with entries in {0,1}; spk: [B][64] or NULL;
@@ -128,6 +130,14 @@ int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, i
                    const void* src0, const void* src1, const float* weight_pt, const float* bias,
                    const void* residual, const float* mask, void* out, float* gn_stats, int per_sample_weights,
                    void* stream);
+
+/* Test hook: 3x3 stride-1 bf16 conv with the GroupNorm-apply epilogue (the Block of model/diffusion.py:49-58 plus one of the two adds
+ * of ResnetBlock.forward, :75-78, in ONE kernel): out = (Mish(GroupNorm8(conv(src) + bias)) [+ tbias[b]] [+ residual]) * mask[b][w].
+ * Exactly one of tbias ([B or 1][Cout], stride tb_bstride) / residual (NHWC bf16) is given.  gn_stats: [B][8][2] mean, rstd out.
+ * reps > 1 re-launches and prints the time per launch to stderr. */
+int gtts_test_conv_apply(int B, int H, int W, int Cin0, int Cin1, int Cout, const void* src0, const void* src1, const float* weight_pt,
+                         const float* bias, const float* gamma, const float* beta, const float* tbias, int tb_bstride,
+                         const void* residual, const float* mask, void* out, float* gn_stats, int reps, void* stream);
 
 /* Test hook: fused k-projection + softmax + context partials of the linear attention (model/diffusion.py:90-100).
  * x: [B][n][C] bf16, wkv: [256][C] bf16 (k rows then v rows), partials: [B][4][chunks][1088] floats

@@ -99,10 +99,30 @@ def test_fused_gn_input_is_bitwise_equal_to_separate_pass(pkg, synth):
         dec, _ = _module(pkg, synth, 247, 3, "bf16")
         z, mask, mu, spk, _ = synth.make_inputs(3, 88, 247, seed=21)
         h = dec.estimator._get_handle()
+        dec.estimator.set_option("fuse_epi", 0)                # the operand-side variant only exists without the epilogue fusion
         pkg._lib.check(pkg._lib.load().gtts_decoder_set_option(h, b"fuse_gn", fuse), "set_option")
         outs.append(dec(z.to(DEV), mask.to(DEV), mu.to(DEV), 3, False, spk.to(DEV)))
     assert torch.isfinite(outs[0]).all()
     assert torch.equal(outs[0], outs[1])
+
+
+def test_apply_epilogue_agrees_with_separate_gn_pass(pkg, synth):
+    """Default plan (Block convs finish GroupNorm+Mish in their epilogue, fuse_epi=1) against the plan with the separate gn_apply
+    pass (fuse_epi=0).  Not bitwise: the fused epilogue normalises the fp32 accumulator, the separate pass its bf16 rounding; both
+    must sit inside the bf16 tolerance of the oracle and close to each other; and the fused plan launches fewer kernels."""
+    outs, launches = [], []
+    z, mask, mu, spk, _ = synth.make_inputs(3, 88, 247, seed=21)
+    for fuse in (1, 0):
+        dec, sd = _module(pkg, synth, 247, 3, "bf16")
+        dec.estimator.set_option("fuse_epi", fuse)
+        outs.append(dec(z.to(DEV), mask.to(DEV), mu.to(DEV), 3, False, spk.to(DEV)).cpu())
+        launches.append(dec.estimator.launches_last_call())
+    with torch.no_grad():
+        ref = decoder_oracle.reverse_diffusion(sd, z, mask, mu, 3, False, spk, 247)
+    rr = lambda a, b: float((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt())
+    assert rr(outs[0], ref) <= 2e-2 and rr(outs[1], ref) <= 2e-2, (rr(outs[0], ref), rr(outs[1], ref))
+    assert rr(outs[0], outs[1]) <= 2e-2
+    assert launches[0] < launches[1], launches
 
 
 def test_long_random_weight_run_stays_finite(pkg, synth, monkeypatch):

@@ -143,3 +143,75 @@ def test_attn_xk_matches_reference(use_tc, C, B, n, chunks, chunk_len, scale, mo
     assert torch.isfinite(got).all()
     err = float((got - ref).abs().max()) / float(ref.abs().max())
     assert err <= 2e-2, f"use_tc={use_tc}: relative max error {err}"          # bf16 P and bf16 S
+
+
+APPLY_CASES = [
+    # name, B, H, W, Cin0, Cin1, Cout, residual (else time bias), per-sample time bias
+    ("l1_128_128_tb", 3, 40, 52, 128, 0, 128, False, False),        # 3 x 21 tiles (odd count per sample): runs straddle CTA pairs
+    ("l1_128_128_res", 2, 40, 64, 128, 0, 128, True, False),
+    ("l2_256_256_tb_persample", 5, 20, 44, 256, 0, 256, False, True),
+    ("l2_256_256_res", 4, 20, 108, 256, 0, 256, True, False),
+    ("l2_cat_512_128_tb", 2, 20, 30, 256, 256, 128, False, False),
+    ("l1_256_64_cat_tb", 2, 40, 30, 128, 128, 64, False, False),
+    ("l1_64_64_res", 3, 40, 36, 64, 0, 64, True, False),
+    ("l0_64_64_tb_small", 2, 80, 24, 64, 0, 64, False, False),
+    ("l1_many_tiles", 12, 40, 216, 128, 0, 128, True, False),        # 12 x 135 tiles over 148 CTAs: up to two runs in flight per CTA
+    ("l2_many_tiles", 40, 20, 216, 256, 0, 256, False, False),       # 40 x 42 tiles, two TMEM buffers: tile-level pipelining
+    ("l1_runs_of_two", 2, 40, 860, 128, 0, 128, False, False),       # 270 tiles per sample on 148 CTAs: two tiles of a sample wait in TMEM
+    ("l0_long_runs", 1, 80, 1200, 64, 0, 64, True, False),           # 750 tiles of ONE sample: up to six accumulators per CTA wait for the barrier
+]
+
+
+@pytest.mark.parametrize("case", APPLY_CASES, ids=[c[0] for c in APPLY_CASES])
+def test_conv_apply_epilogue(case):
+    """Block conv with the GroupNorm-apply epilogue (accumulators wait in TMEM for the per-sample grid barrier) vs torch CPU:
+    out = (mish(group_norm(conv(x) + b)) + time bias | + residual) * mask, bf16 operands, fp32 everything else."""
+    import ctypes
+    import torch.nn.functional as F
+    name, B, H, W, Cin0, Cin1, Cout, use_res, per_sample = case
+    gu = _gu()
+    lib = gu._lib.load()
+    g = torch.Generator().manual_seed(_seed(name))
+    Cin = Cin0 + Cin1
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    gamma = 1.0 + 0.1 * torch.randn(Cout, generator=g)
+    beta = 0.1 * torch.randn(Cout, generator=g)
+    mask = (torch.rand(B, W, generator=g) > 0.25).float()
+    x = x * mask[:, None, None, :]                                   # the decoder's inputs are stored masked
+    tb = torch.randn(B if per_sample else 1, Cout, generator=g) if not use_res else None
+    res = torch.randn(B, Cout, H, W, generator=g) if use_res else None
+    rb = lambda t: t.to(torch.bfloat16).float()
+    y = F.conv2d(rb(x), rb(w), b, padding=1)
+    sref = gu.gn_stats_reference(y)
+    y = F.group_norm(y, 8, gamma, beta, eps=1e-5)
+    y = y * torch.tanh(F.softplus(y))
+    if tb is not None:
+        y = y + (tb if per_sample else tb.expand(B, -1))[:, :, None, None]
+    if res is not None:
+        y = y + rb(res)
+    ref = y * mask[:, None, None, :]
+    dev = torch.device("cuda:0")
+    dt = torch.bfloat16
+    x0 = gu.nhwc(x[:, :Cin0], dt).to(dev)
+    x1 = gu.nhwc(x[:, Cin0:], dt).to(dev) if Cin1 else None
+    out = torch.full((B, H, W, Cout), float("nan"), dtype=dt, device=dev)
+    stats = torch.zeros(B, 8, 2, dtype=torch.float32, device=dev)
+    d = lambda t: t.float().contiguous().to(dev) if t is not None else None
+    wd, bd, gd, bed, md, tbd = d(w), d(b), d(gamma), d(beta), d(mask), d(tb)
+    rd = gu.nhwc(res, dt).to(dev) if res is not None else None
+    p = lambda t: t.data_ptr() if t is not None else None
+    rc = lib.gtts_test_conv_apply(B, H, W, Cin0, Cin1, Cout, p(x0), p(x1), p(wd), p(bd), p(gd), p(bed), p(tbd),
+                                  Cout if per_sample else 0, p(rd), p(md), p(out), p(stats), 3,
+                                  ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    gu._lib.check(rc, "gtts_test_conv_apply")
+    torch.cuda.synchronize()
+    got = gu.nchw(out.float().cpu())
+    live = mask[:, None, None, :].expand_as(ref) > 0
+    assert not torch.isnan(got).any(), "output has unwritten (NaN) entries"
+    err = float((got - ref).abs().max())
+    assert err <= 4e-2, f"{name}: max-abs err {err} (|ref|max {float(ref.abs().max())})"
+    assert float(got[~live].abs().max() if (~live).any() else 0.0) == 0.0
+    serr = float(((stats.cpu() - sref).abs() / (sref.abs() + 1.0)).max())
+    assert serr <= 2e-3, f"{name}: GN stats err {serr}"
