@@ -127,8 +127,12 @@ struct Decoder {
     int fuse_gn = 0;          // 1: block2 convs apply block1's GroupNorm+Mish(+time bias, mask) on their operand tiles (no gn_apply
                               // pass).  Bitwise identical, but measured SLOWER (64->64 @L0: 435 us vs 134 + 103 us): GN+Mish at
                               // 5 TB/s already needs a whole SM's issue/MUFU capacity, four transform warps cannot supply it.
-    int fuse_epi = 1;         // 1: Block convs apply GroupNorm+Mish(+time bias / residual, mask) in their own epilogue (accumulators wait in
-                              // TMEM for the sample's statistics, per-sample grid barrier): no raw tensor, no gn_apply pass
+    int fuse_epi = 1;         // Block convs apply GroupNorm+Mish(+time bias / residual, mask) in their own epilogue (accumulators wait in
+                              // TMEM for the sample's statistics, per-sample grid barrier): no raw tensor, no gn_apply pass.
+                              // 0 = never, 1 = for plans of at most fuse_epi_max_b samples, 2 = always.  Measured (profiles/r02_gn_fusion.md):
+                              // wins where launches are latency-bound (B = 1, T = 400: 21 us vs 17 + 8.6 us per Block) and loses on big
+                              // batches (chunk 16 x 1720: 128->128 @h40 249 vs 109 + 57 us) because every sample costs one grid barrier.
+    int fuse_epi_max_b = 2;
     int halo_mode = 2;        // 3x3 convs: 0 = per-tap boxes, 1/2 = halo box (18x16 / 18x10) + shifted descriptor views
     std::map<std::string, float*> params;
     std::map<std::string, size_t> param_numel;
@@ -460,6 +464,7 @@ struct PlanBuilder {
     bool can_fuse_input(const ConvGeom& g) const {
         if (!use_tc() || !d->fuse_gn || d->halo_mode != 2 || !conv_tc_cta2_enabled() || !conv_tc_halo_eligible(g)) return false;
         if (getenv("GTTS_FUSE_GN") && atoi(getenv("GTTS_FUSE_GN")) == 0) return false;
+        if (const char* e = getenv("GTTS_FUSE_GN_MINC")) { if (g.Cout < atoi(e)) return false; }
         const long tiles = (long)g.B * ((g.Hg + 7) / 8) * ((g.Wg + 15) / 16);
         return g.Cin1 == 0 && tiles >= 2 && d->num_sms >= 2;
     }
@@ -468,7 +473,8 @@ struct PlanBuilder {
 
     // true when a Block conv of this geometry can finish GroupNorm+Mish in its own epilogue (ConvEpilogue::apply)
     bool can_apply(const ConvGeom& g) const {
-        return use_tc() && d->fuse_epi && d->halo_mode == 2 && conv_tc_apply_eligible(g, d->num_sms);
+        if (!use_tc() || d->halo_mode != 2 || d->fuse_epi == 0 || (d->fuse_epi == 1 && B > d->fuse_epi_max_b)) return false;
+        return conv_tc_apply_eligible(g, d->num_sms);
     }
 
     void add_conv(const ConvGeom& g, const void* src0, const void* src1, const void* w, int wrows, const float* bias,
@@ -839,7 +845,7 @@ int get_plan(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, cu
     std::string key = std::to_string((int)kind) + ":" + std::to_string(B) + ":" + std::to_string(T) + ":" +
                       (est_mode ? "e" : "s") + (sde ? "n" : "o") + (d->use_graph ? "g" : "x") +
                       std::to_string(d->conv_impl_bf16) + std::to_string(d->halo_mode) + std::to_string(d->fused_attn) + std::to_string(d->fuse_gn) +
-                      std::to_string(d->fuse_epi);
+                      std::to_string(d->fuse_epi) + "." + std::to_string(d->fuse_epi_max_b);
     auto it = d->plans.find(key);
     if (it != d->plans.end()) {
         it->second.last_use = ++d->use_clock;
@@ -1032,6 +1038,9 @@ Decoder* decoder_new(int n_spks, int n_feats, int dim, double beta_min, double b
     d->n_feats = n_feats; d->dim = dim;
     d->beta_min = beta_min; d->beta_max = beta_max; d->pe_scale = pe_scale;
     d->device = device; d->num_sms = prop.multiProcessorCount;
+    // experiment switches (profiling runs): defaults of the two GroupNorm fusion options
+    if (const char* e = getenv("GTTS_FUSE_EPI")) d->fuse_epi = atoi(e);
+    if (const char* e = getenv("GTTS_FUSE_GN")) d->fuse_gn = atoi(e);
     if (cudaEventCreateWithFlags(&d->done_ev, cudaEventDisableTiming) != cudaSuccess) {
         set_error("cudaEventCreate failed"); cudaGetLastError(); delete d; return nullptr;
     }
@@ -1079,6 +1088,7 @@ int decoder_set_option(Decoder* d, const char* key, int value) {
     else if (k == "fused_attn") d->fused_attn = value;
     else if (k == "fuse_gn") d->fuse_gn = value;
     else if (k == "fuse_epi") d->fuse_epi = value;
+    else if (k == "fuse_epi_max_b") d->fuse_epi_max_b = value;
     else { set_error("unknown option " + k); return 2; }
     return 0;
 }

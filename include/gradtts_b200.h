@@ -94,7 +94,8 @@ int gtts_decoder_set_param(gtts_decoder* d, const char* name, const float* data,
  * "trim" (any value: free every cached plan and the pooled workspace), "use_graph" (0/1), "conv_impl_bf16" (1 tcgen05, 0 FFMA cross-check),
  * "halo_mode" (3x3 convs: 0 per-tap TMA boxes, 1 / 2 halo box 18x16 / 18x10 + shifted descriptor views),
  * "fused_attn" (1: fused k-projection + context kernel for C <= 128, 0: 1x1 kv conv + context kernel),
- * "fuse_epi" (1, default: Block convs finish GroupNorm+Mish(+time bias / residual) in their own epilogue -- no gn_apply pass; 0: separate pass),
+ * "fuse_epi" (Block convs finish GroupNorm+Mish(+time bias / residual) in their own epilogue -- no raw tensor, no gn_apply pass:
+ *  0 never, 1 (default) for plans of at most "fuse_epi_max_b" (default 2) samples, where it wins; 2 always),
  * "fuse_gn" (1: block2 convs apply block1's GroupNorm+Mish on their operand tiles; only used with fuse_epi = 0) */
 int gtts_decoder_set_option(gtts_decoder* d, const char* key, int value);
 

@@ -114,7 +114,7 @@ def test_apply_epilogue_agrees_with_separate_gn_pass(pkg, synth):
     z, mask, mu, spk, _ = synth.make_inputs(3, 88, 247, seed=21)
     for fuse in (1, 0):
         dec, sd = _module(pkg, synth, 247, 3, "bf16")
-        dec.estimator.set_option("fuse_epi", fuse)
+        dec.estimator.set_option("fuse_epi", 2 if fuse else 0)          # 2 = always (the default, 1, fuses only small batches)
         outs.append(dec(z.to(DEV), mask.to(DEV), mu.to(DEV), 3, False, spk.to(DEV)).cpu())
         launches.append(dec.estimator.launches_last_call())
     with torch.no_grad():
