@@ -13,5 +13,6 @@ from .model import GradTTS  # noqa: F401
 from .model.diffusion import Diffusion, GradLogPEstimator2d  # noqa: F401
 from .model.monotonic_align import maximum_path  # noqa: F401
 from . import dist  # noqa: F401
+from . import likelihood  # noqa: F401
 
-__all__ = ["GradTTS", "Diffusion", "GradLogPEstimator2d", "maximum_path", "synth", "dist"]
+__all__ = ["GradTTS", "Diffusion", "GradLogPEstimator2d", "maximum_path", "synth", "dist", "likelihood"]

@@ -509,6 +509,10 @@ attn_merge_kernel(AttnCtxArgs a) {
         float l = 0.f;
         for (int c = 0; c < nch; ++c) l += s_w[c][tid] * pbase[(size_t)c * 1088 + 32 + tid];
         s_scale[tid] = 1.0f / l;
+        if (a.ml && blockIdx.z == 0) {                                  // kept for the backward pass
+            a.ml[((size_t)b * 4 + head) * 64 + tid] = s_m[tid];
+            a.ml[((size_t)b * 4 + head) * 64 + 32 + tid] = l;
+        }
     }
     __syncthreads();
     {   // blockIdx.z selects a quarter of the 32x32 outputs: one output per thread

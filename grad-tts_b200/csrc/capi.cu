@@ -151,6 +151,12 @@ int gtts_decoder_estimator(gtts_decoder* h, const float* x, const float* mask, c
     return decoder_estimator(h->impl, x, mask, mu, t, spk, out, B, T, flags, (cudaStream_t)stream);
 }
 
+int gtts_decoder_estimator_vjp(gtts_decoder* h, const float* x, const float* mask, const float* mu, const float* t, const float* spk,
+                               const float* v, float* out_score, float* out_gx, int B, int T, int flags, void* stream) {
+    GTTS_REQUIRE(h && x && mask && mu && t && v && out_gx, "estimator_vjp: null pointer");
+    return decoder_estimator_vjp(h->impl, x, mask, mu, t, spk, v, out_score, out_gx, B, T, flags, (cudaStream_t)stream);
+}
+
 int gtts_decoder_reverse_diffusion_host(gtts_decoder* h, const float* z_host, const float* mask_host,
                                         const float* mu_host, const float* spk_host, float* out_host, int B, int T,
                                         int n_timesteps, int flags) {

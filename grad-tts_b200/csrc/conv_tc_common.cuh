@@ -39,8 +39,8 @@ struct TcParams {
     int mc;                                        // 1: 2-CTA cluster, weight tiles multicast (conv_tc.cu); 2: CTA pair, cta_group::2 MMAs (conv_tc_halo2.cu)
     unsigned long long* dbg_out;                   // optional per-CTA cycle counters (GTTS_CONV_TIMING), 16 per CTA
     int dbg;                                       // experiment switches (GTTS_CONV_DBG): 1 no MMA issue, 2 no epilogue work, 4 no A loads (halo), 8 no stats ring
-    int8_t dy[4][9], dx[4][9];
-    int wrow[4][9];
+    int8_t dy[4][16], dx[4][16];
+    int wrow[4][16];
     int oy[4], ox[4];
     ConvEpilogue e;
 };

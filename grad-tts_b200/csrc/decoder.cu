@@ -108,6 +108,15 @@ struct Packed {
     BlockW final_block;
     const float* wf = nullptr;
     float bf = 0.f;
+    // ---- data-gradient weights (built on the first VJP plan): the same convolutions transposed
+    struct ResnetB { void* d1[2]; void* d2; void* rT[2]; };   // block1 dgrad per input source, block2 dgrad, res_conv^T per source
+    struct AttnB { void* wq; void* woT; void* wqT; void* wkvT; };   // Wq [128][C], g * Wout^T [128][C], Wq^T [C][128], Wkv^T [C][256]
+    bool bwd_ready = false;
+    ResnetB bres[12];
+    AttnB battn[6];
+    void* bdown[2] = {nullptr, nullptr};
+    void* bup[2] = {nullptr, nullptr};
+    void* bfinal = nullptr;
 };
 
 }  // namespace
@@ -303,6 +312,77 @@ int pack_weights(Decoder* d, ActKind kind) {
     return 0;
 }
 
+// Transposed / flipped copies of every convolution weight for the backward pass w.r.t. the input (backward.cu).
+int pack_backward_weights(Decoder* d, ActKind kind) {
+    Packed* P = d->packed[kind].get();
+    if (P->bwd_ready) return 0;
+    cudaStream_t s = 0;
+    auto get = [&](const std::string& n) -> const float* {
+        auto it = d->params.find("estimator." + n);
+        return it == d->params.end() ? nullptr : it->second;
+    };
+    const int res_c0[12] = {0, 64, 64, 128, 128, 256, 256, 256, 256, 128, 128, 64};      // channels of the first / second input source
+    const int res_c1[12] = {0, 0, 0, 0, 0, 0, 0, 0, 256, 0, 128, 0};
+    const size_t es = esize(kind);
+    for (int r = 0; r < 12; ++r) {
+        Packed::ResnetB& Bw = P->bres[r];
+        Bw.d1[0] = Bw.d1[1] = Bw.d2 = Bw.rT[0] = Bw.rT[1] = nullptr;
+        const ResnetW& R = P->res[r];
+        const std::string n = kResnetNames[r];
+        const float* w1 = get(n + ".block1.block.0.weight");
+        const float* w2 = get(n + ".block2.block.0.weight");
+        const float* wr = get(n + ".res_conv.weight");
+        Bw.d2 = P->mem.alloc((size_t)9 * R.cout * R.cout * es);
+        if (!Bw.d2) { set_error("out of device memory packing backward weights"); return 4; }
+        if (pack_dgrad3(kind, w2, Bw.d2, R.cout, R.cout, 0, R.cout, s)) return 1;
+        if (r == 0) continue;                                  // first conv / first res_conv: first_bwd reads the forward weights
+        const int cs[2] = {res_c0[r], res_c1[r]};
+        int off = 0;
+        for (int k = 0; k < 2; ++k) {
+            if (cs[k] == 0) continue;
+            Bw.d1[k] = P->mem.alloc((size_t)9 * cs[k] * R.cout * es);
+            if (!Bw.d1[k]) { set_error("out of device memory packing backward weights"); return 4; }
+            if (pack_dgrad3(kind, w1, Bw.d1[k], R.cout, R.cin, off, cs[k], s)) return 1;
+            if (wr) {
+                Bw.rT[k] = P->mem.alloc((size_t)cs[k] * R.cout * es);
+                if (pack_t1(kind, wr, Bw.rT[k], R.cout, R.cin, off, cs[k], 1.0f, s)) return 1;
+            }
+            off += cs[k];
+        }
+    }
+    const char* attn_names[6] = {"downs.0.2", "downs.1.2", "downs.2.2", "mid_attn", "ups.0.2", "ups.1.2"};
+    for (int a = 0; a < 6; ++a) {
+        const AttnW& A = P->attn[a];
+        Packed::AttnB& Bw = P->battn[a];
+        const std::string n = attn_names[a];
+        const float* wqkv = get(n + ".fn.fn.to_qkv.weight");
+        Bw.wq = P->mem.alloc((size_t)128 * A.C * es);
+        if (!Bw.wq || pack_conv_weight(kind, wqkv, Bw.wq, 128, A.C, 1, 1, s)) return 1;
+        Bw.woT = P->mem.alloc((size_t)128 * A.C * es);
+        Bw.wqT = P->mem.alloc((size_t)A.C * 128 * es);
+        Bw.wkvT = P->mem.alloc((size_t)A.C * 256 * es);
+        if (!Bw.woT || !Bw.wqT || !Bw.wkvT) { set_error("out of device memory packing backward weights"); return 4; }
+        if (pack_t1(kind, A.wout, Bw.woT, A.C, 128, 0, 128, A.g, s)) return 1;                       // rows e (128), cols c: g * Wout[c][e]
+        if (pack_t1(kind, wqkv, Bw.wqT, 128, A.C, 0, A.C, 1.0f, s)) return 1;                        // rows c, cols hd (q rows of to_qkv)
+        if (pack_t1(kind, wqkv + (size_t)128 * A.C, Bw.wkvT, 256, A.C, 0, A.C, 1.0f, s)) return 1;   // rows c, cols k|v
+    }
+    for (int i = 0; i < 2; ++i) {
+        const int Cd = i == 0 ? 64 : 128, Cu = i == 0 ? 128 : 64;
+        P->bdown[i] = P->mem.alloc((size_t)16 * Cd * Cd * es);
+        P->bup[i] = P->mem.alloc((size_t)16 * Cu * Cu * es);
+        if (!P->bdown[i] || !P->bup[i]) { set_error("out of device memory packing backward weights"); return 4; }
+        if (pack_down_dgrad(kind, get("downs." + std::to_string(i) + ".3.conv.weight"), P->bdown[i], Cd, s)) return 1;
+        if (pack_up_dgrad(kind, get("ups." + std::to_string(i) + ".3.conv.weight"), P->bup[i], Cu, s)) return 1;
+    }
+    P->bfinal = P->mem.alloc((size_t)9 * 64 * 64 * es);
+    if (!P->bfinal) { set_error("out of device memory packing backward weights"); return 4; }
+    if (pack_dgrad3(kind, get("final_block.block.0.weight"), P->bfinal, 64, 64, 0, 64, s)) return 1;
+    GTTS_CHECK_CUDA(cudaStreamSynchronize(s));
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    P->bwd_ready = true;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ geometry helpers
 ConvGeom geom_base(int B, int Hin, int Win, int Cin0, int Cin1, int Cout) {
     ConvGeom g;
@@ -348,6 +428,40 @@ ConvGeom geom_convT(int B, int H, int W, int C) {
     return g;
 }
 
+// data gradient of the 3x3 stride-2 Downsample: gradient at (Hc, Wc) -> gradient at (2Hc, 2Wc), four output parities
+ConvGeom geom_down_dgrad(int B, int Hc, int Wc, int C) {
+    ConvGeom g = geom_base(B, Hc, Wc, C, 0, C);
+    g.ntaps = 4; g.nphase = 4; g.out_step = 2; g.Hout = 2 * Hc; g.Wout = 2 * Wc;
+    const int dd[2][2] = {{0, 0}, {1, 0}};            // parity 0: tap 0 reads j (tap 1 has zero weights); parity 1: j+1, j
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+            const int ph = py * 2 + px;
+            g.oy[ph] = py; g.ox[ph] = px;
+            for (int ty = 0; ty < 2; ++ty)
+                for (int tx = 0; tx < 2; ++tx) {
+                    const int t = ty * 2 + tx;
+                    g.dy[ph][t] = (int8_t)dd[py][ty];
+                    g.dx[ph][t] = (int8_t)dd[px][tx];
+                    g.wrow[ph][t] = (ph * 4 + t) * C;
+                }
+        }
+    return g;
+}
+// data gradient of the 4x4 stride-2 transposed conv (Upsample): a 16-tap stride-2 conv from (2Hc, 2Wc) down to (Hc, Wc)
+ConvGeom geom_up_dgrad(int B, int Hc, int Wc, int C) {
+    ConvGeom g = geom_base(B, 2 * Hc, 2 * Wc, C, 0, C);
+    g.Hg = Hc; g.Wg = Wc; g.Hout = Hc; g.Wout = Wc;
+    g.ntaps = 16; g.stride = 2;
+    for (int ky = 0; ky < 4; ++ky)
+        for (int kx = 0; kx < 4; ++kx) {
+            const int t = ky * 4 + kx;
+            g.dy[0][t] = (int8_t)(ky - 1);
+            g.dx[0][t] = (int8_t)(kx - 1);
+            g.wrow[0][t] = t * C;
+        }
+    return g;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ plan
@@ -374,6 +488,8 @@ struct Plan {
     NoiseSlot* noise_slot = nullptr;
     float* h_dev = nullptr;
     int max_steps = 4096;
+    bool vjp = false;             // forward (est mode, every intermediate kept) followed by the backward pass w.r.t. x
+    float *vin = nullptr, *gx = nullptr;      // (B,80,T) cotangent in, J^T v out
     size_t pooled_bytes = 0;      // peak of live pooled activation memory of this plan (after liveness reuse)
     size_t unpooled_bytes = 0;    // what one-buffer-per-tensor allocation would have needed (reported for comparison)
     float* partials = nullptr;
@@ -407,6 +523,12 @@ struct PlanBuilder {
     bool failed = false, oom = false;
     std::vector<char> in_use;     // per pool block: live in THIS plan (other plans alias the same blocks)
     size_t live_bytes = 0;
+    // ---- VJP plans (forward + backward w.r.t. x): nothing is released during the forward half (the backward half reads the raw
+    // conv outputs, the statistics, the attention inputs / kv / contexts); every forward module pushes its backward onto `tape`
+    bool vjp = false, keep_all = false;
+    std::vector<std::function<void()>> tape;
+    std::map<const void*, void*> grad;          // activation -> gradient accumulated so far
+    float* gn_bwd_partials = nullptr;
 
     void fail_oom(size_t bytes) {
         failed = true; oom = true;
@@ -439,7 +561,7 @@ struct PlanBuilder {
         return blocks[best].p;
     }
     void release(const void* p) {
-        if (!p) return;
+        if (!p || keep_all) return;
         auto& blocks = d->pool.blocks;
         for (int i = 0; i < (int)blocks.size(); ++i)
             if (blocks[i].p == p && in_use[i]) { in_use[i] = 0; live_bytes -= blocks[i].bytes; return; }
@@ -462,6 +584,7 @@ struct PlanBuilder {
 
     // true when a 3x3 conv with this geometry would run on the CTA-pair halo kernel (the only one with the fused input path)
     bool can_fuse_input(const ConvGeom& g) const {
+        if (vjp) return false;
         if (!use_tc() || !d->fuse_gn || d->halo_mode != 2 || !conv_tc_cta2_enabled() || !conv_tc_halo_eligible(g)) return false;
         if (getenv("GTTS_FUSE_GN") && atoi(getenv("GTTS_FUSE_GN")) == 0) return false;
         if (const char* e = getenv("GTTS_FUSE_GN_MINC")) { if (g.Cout < atoi(e)) return false; }
@@ -473,7 +596,7 @@ struct PlanBuilder {
 
     // true when a Block conv of this geometry can finish GroupNorm+Mish in its own epilogue (ConvEpilogue::apply)
     bool can_apply(const ConvGeom& g) const {
-        if (!use_tc() || d->halo_mode != 2 || d->fuse_epi == 0 || (d->fuse_epi == 1 && B > d->fuse_epi_max_b)) return false;
+        if (vjp || !use_tc() || d->halo_mode != 2 || d->fuse_epi == 0 || (d->fuse_epi == 1 && B > d->fuse_epi_max_b)) return false;
         return conv_tc_apply_eligible(g, d->num_sms);
     }
 
@@ -596,7 +719,200 @@ struct PlanBuilder {
         if (!ap2) add_gn_apply(lvl, Co, raw2, st2, R.b2, nullptr, resid, first_res, out);
         release(raw1); release(a1); release(raw2);
         if (resid != x0) release(resid);
+        if (vjp) {
+            const bool identity = (r != 0 && !R.wres);
+            tape.push_back([=]() { resnet_backward(r, lvl, x0, c0, x1, c1, raw1, st1, raw2, st2, out, identity); });
+        }
         return out;
+    }
+
+    // ------------------------------------------------------------------------------------------------ backward (VJP plans)
+    void* take_grad(const void* act_ptr) {
+        auto it = grad.find(act_ptr);
+        if (it == grad.end()) { set_error("internal: backward reached a tensor without a gradient"); failed = true; return nullptr; }
+        void* g = it->second;
+        grad.erase(it);
+        return g;
+    }
+    void* peek_grad(const void* act_ptr) {
+        auto it = grad.find(act_ptr);
+        return it == grad.end() ? nullptr : it->second;
+    }
+    // conv on the gradient path: CUDA-core implicit GEMM in the plan's activation type (generic over every geometry)
+    void add_bconv(const char* what, const ConvGeom& g, const void* src, const void* w, const void* residual, void* out) {
+        ConvEpilogue e;
+        memset(&e, 0, sizeof(e));
+        e.residual = residual; e.out = out;
+        const double npx = (double)g.B * g.nphase * g.Hg * g.Wg;
+        const double flops = 2.0 * npx * g.Cout * g.ntaps * (g.Cin0 + g.Cin1);
+        ActKind k = kind;
+        pl->push(std::string("bwd_") + what + "_" + std::to_string(g.Cin0) + "_" + std::to_string(g.Cout) + "_h" + std::to_string(g.Hout), 1, flops, 0.0,
+                 [k, g, src, w, e](cudaStream_t s) { return conv_ffma(k, g, src, nullptr, w, e, s); });
+    }
+    void add_mask_mul(int lvl, int C, const void* in, void* out) {
+        ActKind k = kind;
+        const float* m = lmask[lvl];
+        int Bb = B, Hh = H[lvl], Ww = W[lvl];
+        pl->push("bwd_mask", 0, 0.0, 0.0, [k, in, m, out, Bb, Hh, Ww, C](cudaStream_t s) { return mask_mul(k, in, m, out, Bb, Hh, Ww, C, s); });
+    }
+    void add_gn_bwd(int lvl, int C, const void* raw, const float* st, const BlockW& bw, const void* gy, void* graw) {
+        GnBwdArgs a;
+        memset(&a, 0, sizeof(a));
+        a.raw = raw; a.stats = st; a.gamma = bw.gamma; a.beta = bw.beta; a.mask = lmask[lvl]; a.gy = gy; a.graw = graw;
+        a.partials = gn_bwd_partials; a.B = B; a.H = H[lvl]; a.W = W[lvl]; a.C = C;
+        ActKind k = kind;
+        pl->push("bwd_gn_" + std::to_string(C) + "_h" + std::to_string(H[lvl]), 0, 0.0, 0.0, [k, a](cudaStream_t s) { return gn_bwd(k, a, s); });
+        pl->kernels_per_step++;                               // two launches
+    }
+    void add_add(int lvl, int C, const void* a, const void* b, void* out) {
+        ActKind k = kind;
+        const size_t numel = (size_t)B * H[lvl] * W[lvl] * C;
+        pl->push("bwd_add", 0, 0.0, 0.0, [k, a, b, out, numel](cudaStream_t s) { return add_tensors(k, a, b, out, numel, s); });
+    }
+
+    // ResnetBlock backward: gradient of `out` -> gradients of its input source(s) (or, for the first block, of the x plane)
+    void resnet_backward(int r, int lvl, const void* x0, int c0, const void* x1, int c1, void* raw1, float* st1, void* raw2, float* st2,
+                         void* out, bool identity) {
+        const ResnetW& R = P->res[r];
+        const Packed::ResnetB& Bw = P->bres[r];
+        const int Co = R.cout;
+        void* g_out = take_grad(out);
+        if (failed) return;
+        void* gpre = act(lvl, Co);                            // out = (Mish(GN(raw2)) + residual) * mask
+        void* g_raw2 = act(lvl, Co);
+        void* g_a1 = act(lvl, Co);
+        if (failed) return;
+        add_mask_mul(lvl, Co, g_out, gpre);
+        release(g_out);
+        add_gn_bwd(lvl, Co, raw2, st2, R.b2, gpre, g_raw2);
+        add_bconv("dgrad3", geom_3x3(B, H[lvl], W[lvl], Co, 0, Co, 1), g_raw2, Bw.d2, nullptr, g_a1);
+        release(g_raw2);
+        void* g_raw1 = act(lvl, Co);                          // a1 = (Mish(GN(raw1)) + time bias) * mask
+        if (failed) return;
+        add_gn_bwd(lvl, Co, raw1, st1, R.b1, g_a1, g_raw1);
+        release(g_a1);
+        if (r == 0) {
+            ActKind k = kind;
+            const float *w1t = P->first_wT, *wres = P->fr_w, *m = lmask[0];
+            float* gx = pl->gx;
+            int Bb = B, Hh = H[0], Ww = W[0], cin = d->cin_first;
+            pl->push("bwd_first", 0, 0.0, 0.0, [k, g_raw1, gpre, w1t, wres, m, gx, Bb, Hh, Ww, cin](cudaStream_t s) {
+                return first_bwd(k, g_raw1, gpre, w1t, wres, m, gx, Bb, Hh, Ww, cin, s);
+            });
+            release(g_raw1); release(gpre);
+            return;
+        }
+        const void* xs[2] = {x0, x1};
+        const int cs[2] = {c0, c1};
+        for (int k = 0; k < 2; ++k) {
+            if (cs[k] == 0) continue;
+            void* prev = peek_grad(xs[k]);                     // gradient the source already received from later consumers
+            if (prev) grad.erase(xs[k]);
+            const void* acc = prev;
+            void* owned = prev;
+            if (k == 0 && identity) {                          // Identity residual: the source also receives gpre itself
+                if (prev) {
+                    void* t = act(lvl, cs[k]);
+                    if (failed) return;
+                    add_add(lvl, cs[k], prev, gpre, t);
+                    release(prev);
+                    acc = t; owned = t;
+                } else {
+                    acc = gpre; owned = nullptr;
+                }
+            }
+            void* gn = act(lvl, cs[k]);
+            if (failed) return;
+            add_bconv("dgrad3", geom_3x3(B, H[lvl], W[lvl], Co, 0, cs[k], 1), g_raw1, Bw.d1[k], acc, gn);
+            release(owned);
+            if (Bw.rT[k]) {                                    // res_conv (1x1) transposed, on top
+                void* gn2 = act(lvl, cs[k]);
+                if (failed) return;
+                add_bconv("dgrad1", geom_1x1(B, H[lvl], W[lvl], Co, 0, cs[k], 0), gpre, Bw.rT[k], gn, gn2);
+                release(gn);
+                gn = gn2;
+            }
+            grad[xs[k]] = gn;
+        }
+        release(g_raw1); release(gpre);
+    }
+
+    // Residual(Rezero(LinearAttention)) backward.  Forward kept: x, kv = [k | v] (1x1 conv of x), ctxn (normalised contexts), ml.
+    void attention_backward(int a, int lvl, const void* x, void* out, void* kv, float* ctxn, float* ml, int chunks, int chunk_len) {
+        const AttnW& A = P->attn[a];
+        const Packed::AttnB& Bw = P->battn[a];
+        const int C = A.C, n = H[lvl] * W[lvl];
+        void* g_out = take_grad(out);
+        if (failed) return;
+        void* G = act(lvl, C);
+        void* q = act(lvl, 128);
+        void* go = act(lvl, 128);
+        float* opart = (float*)pl->mem.alloc((size_t)B * 4 * chunks * 1024 * 4);
+        float* gctx = (float*)pl->mem.alloc((size_t)B * 4 * 1024 * 4);
+        float* sdot = (float*)pl->mem.alloc((size_t)B * 4 * 32 * 4);
+        if (failed || !opart || !gctx || !sdot) { if (!failed) fail_oom((size_t)B * 4 * chunks * 4096); return; }
+        add_mask_mul(lvl, C, g_out, G);                       // out = (M_b x + g b_out + x) * mask
+        release(g_out);
+        add_bconv("attn_q", geom_1x1(B, H[lvl], W[lvl], C, 0, 128, 0), x, Bw.wq, nullptr, q);
+        add_bconv("attn_go", geom_1x1(B, H[lvl], W[lvl], C, 0, 128, 0), G, Bw.woT, nullptr, go);
+        {
+            ActKind k = kind;
+            int Bb = B;
+            pl->push("bwd_attn_outer", 0, 0.0, 0.0, [k, q, go, opart, ctxn, gctx, sdot, Bb, n, chunks, chunk_len](cudaStream_t s) {
+                return attn_outer(k, q, go, opart, ctxn, gctx, sdot, Bb, n, chunks, chunk_len, s);
+            });
+            pl->kernels_per_step++;
+        }
+        release(q);
+        void* gq = act(lvl, 128);
+        void* gkv = act(lvl, 256);
+        if (failed) return;
+        {
+            ActKind k = kind;
+            int Bb = B;
+            pl->push("bwd_attn_pos", 0, 0.0, 0.0, [k, kv, go, ctxn, gctx, ml, sdot, gq, gkv, Bb, n](cudaStream_t s) {
+                return attn_pos_bwd(k, kv, go, ctxn, gctx, ml, sdot, gq, gkv, Bb, n, s);
+            });
+        }
+        release(go);
+        void* prev = peek_grad(x);
+        const void* acc = G;
+        void* owned = nullptr;
+        if (prev) {
+            grad.erase(x);
+            void* t = act(lvl, C);
+            if (failed) return;
+            add_add(lvl, C, prev, G, t);
+            release(prev);
+            acc = t; owned = t;
+        }
+        void* g1 = act(lvl, C);
+        void* g2 = act(lvl, C);
+        if (failed) return;
+        add_bconv("attn_gq", geom_1x1(B, H[lvl], W[lvl], 128, 0, C, 0), gq, Bw.wqT, acc, g1);
+        add_bconv("attn_gkv", geom_1x1(B, H[lvl], W[lvl], 256, 0, C, 0), gkv, Bw.wkvT, g1, g2);
+        release(owned); release(G); release(gq); release(gkv); release(g1);
+        grad[x] = g2;
+    }
+
+    void resample_backward(bool down, int i, int lvl_in, const void* x, void* out) {
+        // down: x at lvl_in -> out at lvl_in + 1 ; up: x at lvl_in -> out at lvl_in - 1
+        const int lvl_out = down ? lvl_in + 1 : lvl_in - 1;
+        const int C = down ? P->down[i].C : P->up[i].C;
+        void* g_out = take_grad(out);
+        if (failed) return;
+        void* gm = act(lvl_out, C);
+        if (failed) return;
+        add_mask_mul(lvl_out, C, g_out, gm);
+        release(g_out);
+        void* prev = peek_grad(x);
+        if (prev) grad.erase(x);
+        void* gn = act(lvl_in, C);
+        if (failed) return;
+        if (down) add_bconv("down", geom_down_dgrad(B, H[lvl_out], W[lvl_out], C), gm, P->bdown[i], prev, gn);
+        else add_bconv("up", geom_up_dgrad(B, H[lvl_in], W[lvl_in], C), gm, P->bup[i], prev, gn);
+        release(prev); release(gm);
+        grad[x] = gn;
     }
 
     // Residual(Rezero(LinearAttention)) (:39-46, 82-110)
@@ -615,7 +931,11 @@ struct PlanBuilder {
         float* partials = (float*)pl->mem.alloc((size_t)B * 4 * chunks * 1088 * 4);
         if (!partials) { failed = true; return nullptr; }
         AttnCtxArgs ca{nullptr, B, n, partials, ctxn, chunks, chunk_len};
-        if (kind == ACT_BF16 && C <= 128 && d->fused_attn) {
+        if (vjp) {
+            ca.ml = (float*)pl->mem.alloc((size_t)B * 4 * 64 * 4);
+            if (!ca.ml) { fail_oom((size_t)B * 1024); return nullptr; }
+        }
+        if (kind == ACT_BF16 && C <= 128 && d->fused_attn && !vjp) {
             // fused k-projection + context: reads x only, k and v are never written to HBM
             const void* wk = A.wkv;                                  // packed bf16 [256][C]: k rows, then v rows
             pl->push("attn_xk_" + std::to_string(C) + "_h" + std::to_string(H[lvl]), 0,
@@ -638,6 +958,11 @@ struct PlanBuilder {
                  [k, ctxn, wout, wq, g, mb, Bb, C](cudaStream_t s) { return attn_fold(k, ctxn, wout, wq, g, mb, Bb, C, s); });
         add_conv(geom_1x1(B, H[lvl], W[lvl], C, 0, C, C), x, nullptr, mb, B * C, A.gb, x, lmask[lvl], out, nullptr);
         release(ca.kv);
+        if (vjp) {
+            void* kvp = const_cast<void*>(ca.kv);
+            float* mlp = ca.ml;
+            tape.push_back([=]() { attention_backward(a, lvl, x, out, kvp, ctxn, mlp, chunks, chunk_len); });
+        }
         return out;
     }
 
@@ -646,6 +971,7 @@ struct PlanBuilder {
         void* out = act(lvl + 1, S.C);
         if (failed) return nullptr;
         add_conv(geom_3x3(B, H[lvl], W[lvl], S.C, 0, S.C, 2), x, nullptr, S.w, 9 * S.C, S.bias, nullptr, lmask[lvl + 1], out, nullptr);
+        if (vjp) tape.push_back([=]() { resample_backward(true, i, lvl, x, out); });
         return out;
     }
     void* upsample(int i, int lvl, const void* x) {
@@ -653,6 +979,7 @@ struct PlanBuilder {
         void* out = act(lvl - 1, S.C);
         if (failed) return nullptr;
         add_conv(geom_convT(B, H[lvl], W[lvl], S.C), x, nullptr, S.w, 16 * S.C, S.bias, nullptr, lmask[lvl - 1], out, nullptr);
+        if (vjp) tape.push_back([=]() { resample_backward(false, i, lvl, x, out); });
         return out;
     }
 
@@ -663,6 +990,13 @@ struct PlanBuilder {
         pl->xt = (float*)pooled(plane * 4);              // rewritten at the start of every call, like mu and the masks
         pl->mu = (float*)pooled(plane * 4);
         pl->score = (float*)pooled(plane * 4);
+        if (vjp) {
+            pl->vin = (float*)pooled(plane * 4);
+            pl->gx = (float*)pooled(plane * 4);
+            gn_bwd_partials = (float*)pl->mem.alloc((size_t)B * 256 * 16 * 4);
+            if (!gn_bwd_partials) { fail_oom((size_t)B * 16384); return 4; }
+            keep_all = true;
+        }
         pl->m0 = (float*)pl->mem.alloc((size_t)B * T * 4);
         pl->m1 = (float*)pl->mem.alloc((size_t)B * T / 2 * 4);
         pl->m2 = (float*)pl->mem.alloc((size_t)B * T / 4 * 4);
@@ -769,17 +1103,41 @@ struct PlanBuilder {
             int* step = pl->step;
             pl->push("advance_step", 0, 0.0, 0.0, [step](cudaStream_t s) { return advance_step(step, s); });
         }
+        if (vjp) {
+            // ---- backward half: cotangent v of the score -> J^T v w.r.t. x, modules in reverse order
+            keep_all = false;
+            void* ghf = act(0, 64);
+            void* g_rawf = act(0, 64);
+            void* gin = act(0, 64);
+            if (failed) return 5;
+            {
+                ActKind k = kind;
+                const float *v = pl->vin, *wf = P->wf, *m = pl->m0;
+                int Bb = B, Hh = H[0], Ww = W[0];
+                pl->push("bwd_final", 0, 0.0, 0.0, [k, v, wf, m, ghf, Bb, Hh, Ww](cudaStream_t s) { return final_bwd(k, v, wf, m, ghf, Bb, Hh, Ww, s); });
+            }
+            add_gn_bwd(0, 64, rawf, stf, P->final_block, ghf, g_rawf);
+            release(ghf);
+            add_bconv("dgrad3", geom_3x3(B, H[0], W[0], 64, 0, 64, 1), g_rawf, P->bfinal, nullptr, gin);
+            release(g_rawf);
+            grad[x] = gin;
+            for (int i = (int)tape.size() - 1; i >= 0 && !failed; --i) tape[i]();
+            if (failed) return 5;
+            if (!grad.empty()) { set_error("internal: backward left " + std::to_string(grad.size()) + " gradient(s) unconsumed"); return 5; }
+        }
         return 0;
     }
 };
 
 
-int plan_create(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, Plan** out) {
+int plan_create(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, bool vjp, Plan** out) {
     if (int rc = pack_weights(d, kind)) return rc;
+    if (vjp) { if (int rc = pack_backward_weights(d, kind)) return rc; }
     std::unique_ptr<Plan> pl(new Plan());
     pl->d = d; pl->kind = kind; pl->strict = (kind == ACT_F32); pl->B = B; pl->T = T;
-    pl->est_mode = est_mode; pl->sde = sde;
+    pl->est_mode = est_mode; pl->sde = sde; pl->vjp = vjp;
     PlanBuilder pb;
+    pb.vjp = vjp;
     pb.pl = pl.get(); pb.d = d; pb.P = d->packed[kind].get(); pb.kind = kind; pb.strict = pl->strict;
     pb.B = B; pb.T = T;
     int rc = pb.build();
@@ -799,6 +1157,7 @@ int plan_create(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde,
     GTTS_CHECK_CUDA(cudaMemsetAsync(pl->m0, 0, (size_t)B * T * 4, cs));
     GTTS_CHECK_CUDA(cudaMemsetAsync(pl->m1, 0, (size_t)B * T / 2 * 4, cs));
     GTTS_CHECK_CUDA(cudaMemsetAsync(pl->m2, 0, (size_t)B * T / 4 * 4, cs));
+    if (vjp) GTTS_CHECK_CUDA(cudaMemsetAsync(pl->vin, 0, (size_t)B * d->n_feats * T * 4, cs));
     schedule_kernel<<<1, 32, 0, cs>>>(pl->t_tab, pl->beta_tab, pl->h_dev, 1, d->beta_min, d->beta_max);
     {
         // point the SDE noise slot at something readable for the dry run
@@ -841,9 +1200,9 @@ void drop_plans(Decoder* d, bool drop_pool) {
     if (drop_pool) d->pool.clear();
 }
 
-int get_plan(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, cudaStream_t stream, Plan** out) {
+int get_plan(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, cudaStream_t stream, Plan** out, bool vjp = false) {
     std::string key = std::to_string((int)kind) + ":" + std::to_string(B) + ":" + std::to_string(T) + ":" +
-                      (est_mode ? "e" : "s") + (sde ? "n" : "o") + (d->use_graph ? "g" : "x") +
+                      (est_mode ? "e" : "s") + (sde ? "n" : "o") + (vjp ? "v" : "-") + (d->use_graph ? "g" : "x") +
                       std::to_string(d->conv_impl_bf16) + std::to_string(d->halo_mode) + std::to_string(d->fused_attn) + std::to_string(d->fuse_gn) +
                       std::to_string(d->fuse_epi) + "." + std::to_string(d->fuse_epi_max_b);
     auto it = d->plans.find(key);
@@ -865,11 +1224,11 @@ int get_plan(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, cu
         d->plans.erase(lru);
     }
     Plan* pl = nullptr;
-    int rc = plan_create(d, kind, B, T, est_mode, sde, &pl);
+    int rc = plan_create(d, kind, B, T, est_mode, sde, vjp, &pl);
     if (rc == 4) {
         // out of device memory: give back everything this handle caches (all plans and the whole pool) and try once more
         drop_plans(d, true);
-        rc = plan_create(d, kind, B, T, est_mode, sde, &pl);
+        rc = plan_create(d, kind, B, T, est_mode, sde, vjp, &pl);
     }
     if (rc) return rc;
     d->plans_created++;
@@ -975,6 +1334,39 @@ int decoder_estimator(Decoder* d, const float* x, const float* mask, const float
         if (int rc = plan_step(pl, stream)) return rc;
         GTTS_CHECK_CUDA(cudaMemcpyAsync(out + b0 * plane, pl->score, Bc * plane * 4, cudaMemcpyDeviceToDevice, stream));
         d->launches_last_call += pl->kernels_per_step + 3;
+    }
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return leave_call(d, stream);
+}
+
+// Score and vector-Jacobian product in one pass: out_score = estimator(x, mask, mu, t, spk), out_gx = (d out_score / d x)^T v.
+// This is what the Hutchinson divergence of the probability-flow ODE needs (reference n_best/likelihood/likelihood.py:27-38).
+int decoder_estimator_vjp(Decoder* d, const float* x, const float* mask, const float* mu, const float* t, const float* spk,
+                          const float* v, float* out_score, float* out_gx, int B, int T, int flags, cudaStream_t stream) {
+    if (int rc = common_checks(d, B, T, spk)) return rc;
+    if (int rc = enter_call(d, stream)) return rc;
+    const ActKind kind = (flags & 1) ? ACT_F32 : ACT_BF16;
+    const size_t plane = (size_t)d->n_feats * T;
+    const int chunk = std::min(d->max_chunk, 16);             // every intermediate of the U-Net is kept for the backward half
+    d->launches_last_call = 0;
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int Bc = std::min(chunk, B - b0);
+        Plan* pl = nullptr;
+        if (int rc = get_plan(d, kind, Bc, T, true, false, stream, &pl, true)) return rc;
+        Packed* P = d->packed[kind].get();
+        if (int rc = build_level_masks(mask + (size_t)b0 * T, pl->m0, pl->m1, pl->m2, Bc, T, stream)) return rc;
+        GTTS_CHECK_CUDA(cudaMemcpyAsync(pl->mu, mu + b0 * plane, Bc * plane * 4, cudaMemcpyDeviceToDevice, stream));
+        GTTS_CHECK_CUDA(cudaMemcpyAsync(pl->xt, x + b0 * plane, Bc * plane * 4, cudaMemcpyDeviceToDevice, stream));
+        GTTS_CHECK_CUDA(cudaMemcpyAsync(pl->vin, v + b0 * plane, Bc * plane * 4, cudaMemcpyDeviceToDevice, stream));
+        GTTS_CHECK_CUDA(cudaMemcpyAsync(pl->t_per_sample, t + b0, Bc * 4, cudaMemcpyDeviceToDevice, stream));
+        if (d->n_spks_mode == 1)
+            if (int rc = spk_mlp(spk + (size_t)b0 * 64, P->spk_w0t, P->spk_b0, P->spk_w2t, P->spk_b2, pl->splane, Bc,
+                                 d->n_feats, pl->strict, stream)) return rc;
+        GTTS_CHECK_CUDA(cudaMemsetAsync(pl->step, 0, 4, stream));
+        if (int rc = plan_step(pl, stream)) return rc;
+        if (out_score) GTTS_CHECK_CUDA(cudaMemcpyAsync(out_score + b0 * plane, pl->score, Bc * plane * 4, cudaMemcpyDeviceToDevice, stream));
+        GTTS_CHECK_CUDA(cudaMemcpyAsync(out_gx + b0 * plane, pl->gx, Bc * plane * 4, cudaMemcpyDeviceToDevice, stream));
+        d->launches_last_call += pl->kernels_per_step + 4;
     }
     GTTS_CHECK_CUDA(cudaGetLastError());
     return leave_call(d, stream);

@@ -14,6 +14,8 @@ int decoder_reverse_diffusion(Decoder* d, const float* z, const float* mask, con
                               cudaStream_t stream);
 int decoder_estimator(Decoder* d, const float* x, const float* mask, const float* mu, const float* t, const float* spk,
                       float* out, int B, int T, int flags, cudaStream_t stream);
+int decoder_estimator_vjp(Decoder* d, const float* x, const float* mask, const float* mu, const float* t, const float* spk,
+                          const float* v, float* out_score, float* out_gx, int B, int T, int flags, cudaStream_t stream);
 int decoder_profile_step(Decoder* d, int B, int T, int flags, int reps, char* buf, size_t buflen, cudaStream_t stream);
 long decoder_launches_last_call(const Decoder* d);
 int decoder_cache_info(const Decoder* d, long long* out, int n);

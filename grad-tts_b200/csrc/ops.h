@@ -26,8 +26,8 @@ struct ConvGeom {
     int Hout, Wout;           // output tensor spatial size
     int Cin0, Cin1, Cout;
     int ntaps, nphase, stride, out_step;
-    int8_t dy[4][9], dx[4][9];
-    int wrow[4][9];
+    int8_t dy[4][16], dx[4][16];   // up to 16 taps per phase (the 4x4 stride-2 conv that is the Upsample's data gradient)
+    int wrow[4][16];
     int oy[4], ox[4];
     int w_batch_rows;         // 0, or Cout for per-sample weights
 };
@@ -164,6 +164,7 @@ struct AttnCtxArgs {
     float* partials;              // [B][4][chunks][1088]
     float* ctxn;                  // [B][4][32][32]  ctx[d][e] / l[d]
     int chunks, chunk_len;
+    float* ml;                    // optional [B][4][64]: global max m[32] and sum l[32] of the key softmax (kept for the backward pass)
 };
 int attn_ctx(ActKind act, const AttnCtxArgs& a, bool strict, cudaStream_t s);      // per-chunk partials
 int attn_merge(const AttnCtxArgs& a, bool strict, cudaStream_t s);                   // partials -> ctxn
@@ -188,6 +189,35 @@ int forward_diffusion(const float* x0, const float* mask, const float* mu, const
                       int B, int C, int T, float beta_min, float beta_max, cudaStream_t s);
 int score_loss(const float* est, const float* zm, const float* mask, const float* t, void* ws, size_t ws_bytes, float* loss, int B,
                int C, int T, float beta_min, float beta_max, cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------------
+// Backward w.r.t. the network input (backward.cu): point-wise / reduction kernels and dgrad weight packing
+// ------------------------------------------------------------------------------------------------
+struct GnBwdArgs {
+    const void* raw; const float* stats;        // saved conv output (NHWC act) and its [B][8][2] mean, rstd
+    const float* gamma; const float* beta;      // [C]
+    const float* mask;                          // [B][W]
+    const void* gy;                             // gradient w.r.t. the Block output (NHWC act)
+    void* graw;                                 // out: gradient w.r.t. the conv output (NHWC act)
+    float* partials;                            // scratch [B][gn_bwd_blocks][16]
+    int B, H, W, C;
+};
+int gn_bwd_blocks(int H, int W);
+int gn_bwd(ActKind act, const GnBwdArgs& a, cudaStream_t s);
+int final_bwd(ActKind act, const float* v, const float* wf, const float* mask, void* ghf, int B, int H, int W, cudaStream_t s);
+int first_bwd(ActKind act, const void* graw1, const void* gres, const float* w1t, const float* wres, const float* mask, float* gx,
+              int B, int H, int W, int cin, cudaStream_t s);
+int mask_mul(ActKind act, const void* in, const float* mask, void* out, int B, int H, int W, int C, cudaStream_t s);
+int add_tensors(ActKind act, const void* a, const void* b, void* out, size_t numel, cudaStream_t s);
+// g_ctx = sum_n q go^T per (sample, head) (partials [B][4][chunks][1024]) and sdot[b][h][d] = sum_e g_ctx[d][e] ctxn[d][e]
+int attn_outer(ActKind act, const void* q, const void* go, float* partials, const float* ctxn, float* gctx, float* sdot, int B, int n,
+               int chunks, int chunk_len, cudaStream_t s);
+int attn_pos_bwd(ActKind act, const void* kv, const void* go, const float* ctxn, const float* gctx, const float* ml, const float* sdot,
+                 void* gq, void* gkv, int B, int n, cudaStream_t s);
+int pack_dgrad3(ActKind wkind, const float* w_oihw, void* out, int Cout, int Cin, int ci_off, int Cn, cudaStream_t s);
+int pack_t1(ActKind wkind, const float* w_oi, void* out, int Cout, int Cin, int ci_off, int Cn, float scale, cudaStream_t s);
+int pack_down_dgrad(ActKind wkind, const float* w_oihw, void* out, int C, cudaStream_t s);
+int pack_up_dgrad(ActKind wkind, const float* w_iohw, void* out, int C, cudaStream_t s);
 
 // weight packing helpers (device side, fp32 source in PyTorch layout)
 int pack_conv_weight(ActKind wkind, const float* w_oihw, void* packed, int Cout, int Cin, int kh, int kw,

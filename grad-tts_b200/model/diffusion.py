@@ -146,11 +146,13 @@ class GradLogPEstimator2d(BaseModule):
         raise ValueError(f"precision must be 'bf16' or 'fp32', got {self.precision!r}")
 
     @staticmethod
-    def _prep(t, name, device):
+    def _prep(t, name, device, keep_graph=False):
         _lib.require_cuda_tensor(t, name)
         if t.device != device:
             raise RuntimeError(f"{name} is on {t.device} but the decoder parameters are on {device}")
-        return t.detach().to(torch.float32).contiguous()
+        if not keep_graph:
+            t = t.detach()
+        return t.to(torch.float32).contiguous()
 
     def _check_shapes(self, x, mask, mu, spk, need_spk=True):
         if x.dim() != 3 or x.shape[1] != self.n_feats or mu.shape != x.shape:
@@ -166,12 +168,16 @@ class GradLogPEstimator2d(BaseModule):
         return B, T
 
     # ---- reference API -----------------------------------------------------------------------------
-    @torch.no_grad()
     def forward(self, x, mask, mu, t, spk=None):
-        """Score estimate, reference model/diffusion.py:174-216. x, mu: (B,80,T); mask: (B,1,T); t: (B,)."""
+        """Score estimate, reference model/diffusion.py:174-216. x, mu: (B,80,T); mask: (B,1,T); t: (B,).
+
+        Differentiable w.r.t. `x` (torch.autograd.grad(sum(est(x) * eps), x) works, as the reference's likelihood code does it,
+        n_best/likelihood/likelihood.py:30-34); gradients w.r.t. the parameters / mu / t are not built."""
         h = self._get_handle()
         dev = next(self.parameters()).device
-        x_, mask_, mu_ = (self._prep(v, n, dev) for v, n in ((x, "x"), (mask, "mask"), (mu, "mu")))
+        track = torch.is_grad_enabled() and isinstance(x, torch.Tensor) and x.requires_grad
+        x_ = self._prep(x, "x", dev, keep_graph=track)
+        mask_, mu_ = (self._prep(v, n, dev) for v, n in ((mask, "mask"), (mu, "mu")))
         B, T = self._check_shapes(x_, mask_, mu_, spk)
         t_ = self._prep(t, "t", dev).reshape(-1)
         if t_.numel() != B:
@@ -179,6 +185,23 @@ class GradLogPEstimator2d(BaseModule):
         spk_ = self._prep(spk, "spk", dev) if (spk is not None and self.n_spks > 1) else None
         out = torch.ops.gradtts_b200.estimator(int(h.value), x_, mask_, mu_, t_, spk_, self._flags())
         return out.to(x.dtype)
+
+    @torch.no_grad()
+    def vjp(self, x, mask, mu, t, v, spk=None):
+        """(score, J^T v): the estimator and its vector-Jacobian product w.r.t. x in ONE pass (forward + backward share the
+        intermediates on the device).  Equals (est(x), torch.autograd.grad(sum(est(x) * v), x)[0]) of the reference."""
+        h = self._get_handle()
+        dev = next(self.parameters()).device
+        x_, mask_, mu_, v_ = (self._prep(a, n, dev) for a, n in ((x, "x"), (mask, "mask"), (mu, "mu"), (v, "v")))
+        B, T = self._check_shapes(x_, mask_, mu_, spk)
+        if v_.shape != x_.shape:
+            raise ValueError("v must have the shape of x")
+        t_ = self._prep(t, "t", dev).reshape(-1)
+        if t_.numel() != B:
+            raise ValueError("t must have one entry per sample")
+        spk_ = self._prep(spk, "spk", dev) if (spk is not None and self.n_spks > 1) else None
+        score, gx = torch.ops.gradtts_b200.estimator_vjp(int(h.value), x_, mask_, mu_, t_, spk_, v_, self._flags())
+        return score.to(x.dtype), gx.to(x.dtype)
 
     def cache_info(self):
         """Workspace bookkeeping of the native handle (gtts_decoder_cache_info)."""
@@ -309,8 +332,9 @@ class Diffusion(BaseModule):
         all on the device.  There is no estimator backward yet: the returned loss carries no autograd
         graph, so with gradients enabled this raises instead of silently training nothing."""
         if torch.is_grad_enabled():
-            raise NotImplementedError("loss_t computes the forward value only (the estimator backward is not built): call it "
-                                      "under torch.no_grad(), e.g. for validation loss; see DESIGN.md 'next' rows")
+            raise NotImplementedError("loss_t computes the forward value only (the estimator's PARAMETER gradients are not built; "
+                                      "only the gradient w.r.t. the input x is): call it under torch.no_grad(), e.g. for "
+                                      "validation loss; see DESIGN.md 'next' rows")
         dev, x_, mask_, mu_, t_, B, T = self._fd_args(x0, mask, mu, t)
         xt, zm = self.forward_diffusion(x_, mask_, mu_, t_, noise)
         est = self.estimator(xt, mask_, mu_, t_, spk)

@@ -8,7 +8,8 @@ with CPU tensors fails in the dispatcher -- there is no CPU implementation to fa
 (`estimator_vjp` is what `GradLogPEstimator2d.forward`'s backward calls).
 
     torch.ops.gradtts_b200.reverse_diffusion(handle, z, mask, mu, spk, noise, n_timesteps, flags) -> xt
-    torch.ops.gradtts_b200.estimator(handle, x, mask, mu, t, spk, flags)                          -> score
+    torch.ops.gradtts_b200.estimator(handle, x, mask, mu, t, spk, flags)                          -> score   (autograd w.r.t. x)
+    torch.ops.gradtts_b200.estimator_vjp(handle, x, mask, mu, t, spk, v, flags)                   -> (score, J^T v)
     torch.ops.gradtts_b200.maximum_path(value, mask)                                               -> (path, status)
     torch.ops.gradtts_b200.log_prior(mu_x, y)                                                      -> log_prior
     torch.ops.gradtts_b200.align_outputs(attn, mu_x, x_mask)                                       -> (logw_, mu_y)
@@ -71,6 +72,46 @@ def estimator(handle: int, x: Tensor, mask: Tensor, mu: Tensor, t: Tensor, spk: 
 @estimator.register_fake
 def _(handle, x, mask, mu, t, spk, flags):
     return torch.empty_like(x)
+
+
+@torch.library.custom_op(f"{NS}::estimator_vjp", mutates_args=(), device_types="cuda")
+def estimator_vjp(handle: int, x: Tensor, mask: Tensor, mu: Tensor, t: Tensor, spk: Optional[Tensor], v: Tensor,
+                  flags: int) -> Tuple[Tensor, Tensor]:
+    """(score, (d score / d x)^T v) in one pass -> gtts_decoder_estimator_vjp.  The gradient torch.autograd.grad takes through the
+    score network in the Hutchinson divergence (reference n_best/likelihood/likelihood.py:27-38)."""
+    B, _, T = x.shape
+    score, gx = torch.empty_like(x), torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().gtts_decoder_estimator_vjp(ctypes.c_void_p(handle), x.data_ptr(), mask.data_ptr(), mu.data_ptr(), t.data_ptr(),
+                                                    _ptr(spk), v.data_ptr(), score.data_ptr(), gx.data_ptr(), B, T, flags, _stream(x))
+    _lib.check(rc, "estimator_vjp")
+    return score, gx
+
+
+@estimator_vjp.register_fake
+def _(handle, x, mask, mu, t, spk, v, flags):
+    return torch.empty_like(x), torch.empty_like(x)
+
+
+# autograd for `estimator` w.r.t. x only (the reference differentiates the score model w.r.t. its input in the likelihood code; the
+# parameter gradients of training are not built).  The backward re-runs the forward inside gtts_decoder_estimator_vjp: nothing is
+# kept alive between the two calls.
+def _estimator_setup(ctx, inputs, output):
+    handle, x, mask, mu, t, spk, flags = inputs
+    ctx.handle, ctx.flags = handle, flags
+    ctx.save_for_backward(x, mask, mu, t, *([spk] if spk is not None else []))
+    ctx.has_spk = spk is not None
+
+
+def _estimator_backward(ctx, grad_out):
+    saved = ctx.saved_tensors
+    x, mask, mu, t = saved[:4]
+    spk = saved[4] if ctx.has_spk else None
+    _, gx = torch.ops.gradtts_b200.estimator_vjp(ctx.handle, x, mask, mu, t, spk, grad_out.contiguous().to(torch.float32), ctx.flags)
+    return None, gx, None, None, None, None, None
+
+
+estimator.register_autograd(_estimator_backward, setup_context=_estimator_setup)
 
 
 # ---------------------------------------------------------------------------------------------------------------- MAS + alignment
@@ -174,4 +215,4 @@ def _(est, z_masked, mask, t, beta_min, beta_max):
     return est.new_empty(())
 
 
-OPS = ("reverse_diffusion", "estimator", "maximum_path", "log_prior", "align_outputs", "forward_diffusion", "score_loss")
+OPS = ("reverse_diffusion", "estimator", "estimator_vjp", "maximum_path", "log_prior", "align_outputs", "forward_diffusion", "score_loss")

@@ -107,6 +107,12 @@ int gtts_decoder_reverse_diffusion(gtts_decoder* d, const float* z, const float*
 /* one score-network evaluation with per-sample times t[B] */
 int gtts_decoder_estimator(gtts_decoder* d, const float* x, const float* mask, const float* mu, const float* t,
                            const float* spk, float* out, int B, int T, int flags, void* stream);
+/* Score AND vector-Jacobian product w.r.t. the input in one pass (the backward of GradLogPEstimator2d.forward for its `x` argument):
+ *   out_score = estimator(x, mask, mu, t, spk)  (may be NULL),  out_gx = (d out_score / d x)^T v,  all [B][80][T] fp32.
+ * This is the gradient torch.autograd.grad(sum(fn(x, t) * eps), x) takes through the score network in the Hutchinson divergence of the
+ * probability-flow likelihood (reference n_best/likelihood/likelihood.py:27-38).  Parameter gradients are not computed. */
+int gtts_decoder_estimator_vjp(gtts_decoder* d, const float* x, const float* mask, const float* mu, const float* t, const float* spk,
+                               const float* v, float* out_score, float* out_gx, int B, int T, int flags, void* stream);
 /* Host-buffer variant of reverse_diffusion: copies inputs H2D, runs, copies the mel D2H, synchronises. */
 int gtts_decoder_reverse_diffusion_host(gtts_decoder* d, const float* z_host, const float* mask_host,
                                         const float* mu_host, const float* spk_host, float* out_host, int B, int T,

@@ -138,15 +138,79 @@ def make_loss_vectors():
         print(name, "loss", float(loss))
 
 
+def vjp_cases():
+    # name, n_spks, B, T, weight seed, input seed
+    return [("vjp_spk1_b2_t48", 1, 2, 48, 0, 51), ("vjp_spk247_b2_t40", 247, 2, 40, 3, 52)]
+
+
+def make_vjp_vectors():
+    """The gradient the reference's likelihood code takes through the score network (n_best/likelihood/likelihood.py:30-34):
+    torch.autograd.grad(sum(estimator(x, mask, mu, t, spk) * v), x) on the real reference modules, seeded inputs."""
+    from model.diffusion import Diffusion
+    for name, n_spks, B, T, wseed, iseed in vjp_cases():
+        sd = synth.make_decoder_state_dict(n_spks, seed=wseed, g=0.05)
+        dec = Diffusion(80, 64, n_spks, 64, 0.05, 20.0, 1000).eval()
+        dec.load_state_dict(sd, strict=True)
+        z, mask, mu, spk, _ = synth.make_inputs(B, T, n_spks, seed=iseed, ragged=True)
+        gen = torch.Generator().manual_seed(iseed + 100)
+        t = torch.rand(B, generator=gen).clamp(1e-5, 1 - 1e-5)
+        v = torch.randn(B, 80, T, generator=gen)
+        x = (z * mask).clone().requires_grad_(True)
+        score = dec.estimator(x, mask, mu, t, spk)
+        gx = torch.autograd.grad(torch.sum(score * v), x)[0]
+        out = dict(x=x.detach().numpy(), mask=mask.numpy(), mu=mu.numpy(), t=t.numpy(), v=v.numpy(), score=score.detach().numpy(),
+                   gx=gx.numpy(), n_spks=np.int64(n_spks), wseed=np.int64(wseed), sd_sha256=np.array(sd_digest(sd)))
+        if spk is not None:
+            out["spk"] = spk.numpy()
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+        print(name, "gx absmax", float(gx.abs().max()), "score absmax", float(score.abs().max()))
+
+
+def make_likelihood_vectors():
+    """The reference's probability-flow likelihood (n_best/likelihood/likelihood.py get_likelihood_fn with euler > 0, SPEECHSDE from
+    sde_lib.py) driven exactly as n_best/get_score_parallel.py:77-83 does, on the real reference estimator with seeded weights."""
+    import types
+    for m in ("matplotlib", "matplotlib.pyplot"):                 # likelihood.py imports pyplot at module level and never uses it
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.path.insert(0, "/root/reference/n_best")
+    from likelihood import likelihood as ref_lik, sde_lib as ref_sde
+    from model.diffusion import Diffusion
+    for name, n_spks, B, T, n_euler, wseed, iseed in [("lik_spk1_b2_t48_e3", 1, 2, 48, 3, 0, 61)]:
+        sd = synth.make_decoder_state_dict(n_spks, seed=wseed, g=0.05)
+        dec = Diffusion(80, 64, n_spks, 64, 0.05, 20.0, 1000).eval()
+        dec.load_state_dict(sd, strict=True)
+        y, mask, mu, spk, _ = synth.make_inputs(B, T, n_spks, seed=iseed, ragged=True)
+
+        class ScoreModel(torch.nn.Module):                         # model/tts.py:237-250
+            def forward(self, x, t):
+                return dec.estimator(x=x, mask=mask, mu=mu, t=t, spk=spk)
+
+        sde = ref_sde.SPEECHSDE(beta_min=0.05, beta_max=20.0, N=1000, mu=mu, spk=spk, mask=mask)
+        fn = ref_lik.get_likelihood_fn(sde, lambda x: x, rtol=1e-3, atol=1e-3, euler=n_euler)
+        torch.manual_seed(iseed + 7)
+        eps_draw = torch.randint_like(y, low=0, high=2).float() * 2 - 1.0        # the draw likelihood_fn makes first (likelihood.py:87)
+        torch.manual_seed(iseed + 7)
+        bpd, prior_logp, delta_logp, z = fn(ScoreModel(), y)
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), y=y.numpy(), mask=mask.numpy(), mu=mu.numpy(), eps=eps_draw.numpy(),
+                            bpd=bpd.numpy(), prior_logp=prior_logp.numpy(), delta_logp=delta_logp.numpy(), z=z.numpy(),
+                            n_spks=np.int64(n_spks), n_euler=np.int64(n_euler), wseed=np.int64(wseed), sd_sha256=np.array(sd_digest(sd)))
+        print(name, "bpd", bpd.tolist(), "delta_logp", delta_logp.tolist())
+
+
 def main():
     torch.set_num_threads(8)
     import_reference()
     if sys.argv[1:] == ["loss"]:
         return make_loss_vectors()
+    if sys.argv[1:] == ["vjp"]:
+        make_vjp_vectors()
+        return make_likelihood_vectors()
     only = set(sys.argv[1:])                                   # optional: names of decoder cases to (re)generate
     make_baseline_shape_vectors(only)
     if not only:
         make_loss_vectors()
+        make_vjp_vectors()
+        make_likelihood_vectors()
     from model.diffusion import Diffusion
     from model.monotonic_align import maximum_path
 

@@ -121,3 +121,32 @@ def test_loss_oracle_matches_reference_capture(name, synth):
     with torch.no_grad():
         full, _ = loss_oracle.loss_t(sd, x0, mask, mu, t, zm, spk, n_spks)
     assert abs(float(full) - float(g["loss"])) <= 1e-5 * float(g["loss"])
+
+
+@pytest.mark.parametrize("name", ["vjp_spk1_b2_t48", "vjp_spk247_b2_t40"])
+def test_vjp_oracle_matches_reference_autograd(name, synth):
+    """oracle/likelihood_oracle.estimator_vjp against the gradient the REAL reference modules gave under torch.autograd."""
+    from oracle import likelihood_oracle
+    torch.set_num_threads(8)
+    g = _load(name)
+    n_spks = int(g["n_spks"])
+    sd = synth.make_decoder_state_dict(n_spks, seed=int(g["wseed"]), g=0.05)
+    t = lambda k: torch.from_numpy(g[k])
+    spk = t("spk") if "spk" in g else None
+    score, gx = likelihood_oracle.estimator_vjp(sd, t("x"), t("mask"), t("mu"), t("t"), t("v"), spk, n_spks)
+    assert float((score - t("score")).abs().max()) <= 2e-5
+    assert float((gx - t("gx")).abs().max()) <= 2e-5
+
+
+def test_likelihood_oracle_matches_reference(synth):
+    """oracle/likelihood_oracle.likelihood against the reference's own get_likelihood_fn(..., euler=3) (bpd, prior, delta_logp, z)."""
+    from oracle import likelihood_oracle
+    torch.set_num_threads(8)
+    g = _load("lik_spk1_b2_t48_e3")
+    sd = synth.make_decoder_state_dict(1, seed=int(g["wseed"]), g=0.05)
+    t = lambda k: torch.from_numpy(g[k])
+    bpd, prior, dlogp, z = likelihood_oracle.likelihood(sd, t("y"), t("mask"), t("mu"), int(g["n_euler"]), t("eps"))
+    assert float((z - t("z")).abs().max()) <= 1e-4
+    assert torch.allclose(dlogp, t("delta_logp"), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(prior, t("prior_logp"), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(bpd, t("bpd"), rtol=1e-4, atol=1e-2)
