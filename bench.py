@@ -439,6 +439,7 @@ def main():
             fp32 = fp32_record(pkg, torch, get_decoder, dev, devt, Bl, T)
             eager = gpu_eager_record(pkg, torch, dev, configs, line)
             varlen = varlen_record(pkg, torch, get_decoder, dev)
+            line["likelihood"] = likelihood_record(pkg, torch, get_decoder, dev)
             line["configs"] = configs
             line["mas"] = mas
             line["fp32_strict"] = fp32
@@ -577,6 +578,54 @@ def gpu_eager_record(pkg, torch, dev, configs, line):
         del sd, a
         torch.cuda.empty_cache()
     out["note"] = "vs_gpu_eager = our frames/s per GPU / best eager frames/s on one GPU, same config"
+    return out
+
+
+def likelihood_record(pkg, torch, get_decoder, dev):
+    """n-best rescoring shape of the reference (n_best/config/generate_scores.yaml:3-4: 100 hypotheses per utterance, n_euler 10):
+    probability-flow log-likelihood of 100 mels of 400 frames, 10 fixed steps, Hutchinson divergence.  Ours: one fused score + VJP
+    call per step, state on the device (grad-tts_b200/likelihood.py).  Baseline: the reference's algorithm (oracle/likelihood_oracle.py:
+    two estimator forwards + torch.autograd per step) run eagerly on this GPU on 10 hypotheses, scaled to 100."""
+    from oracle import likelihood_oracle
+    B_, T_, eu = 100, 400, 10
+    lik = pkg.likelihood
+    z, mask, mu, _, _ = pkg.synth.make_inputs(B_, T_, 1, seed=3, ragged=False)
+    mu = mu[:1].expand(B_, -1, -1).contiguous()                       # one text, 100 candidate mels
+    y, maskd, mud = (mu + (z - mu)).to(dev), mask.to(dev), mu.to(dev)
+    g = torch.Generator().manual_seed(4)
+    eps = (torch.randint(0, 2, y.shape, generator=g).float() * 2 - 1).to(dev)
+    out = {"workload": f"{B_} hypotheses x {T_} frames, {eu} Euler steps of the probability-flow ODE with Hutchinson divergence "
+                       "(n_best/config/generate_scores.yaml shape)"}
+
+    class Score(torch.nn.Module):
+        def __init__(self, est):
+            super().__init__()
+            self.estimator, self.y_mask, self.mu_y, self.spk = est, maskd, mud, None
+
+    vals = {}
+    for prec in ("fp32", "bf16"):
+        d_ = get_decoder(1, prec)
+        sde = lik.SPEECHSDE(0.05, 20.0, 1000, mud, None, maskd)
+        fn = lik.get_likelihood_fn(sde, euler=eu)
+        model = Score(d_.estimator)
+        ms = _event_time_ms(torch, lambda: fn(model, y, epsilon=eps), 2, 1)
+        bpd = fn(model, y, epsilon=eps)[0]
+        vals[prec] = bpd
+        out[prec] = {"ms": ms, "hypotheses_per_sec": B_ / (ms * 1e-3), "finite": bool(torch.isfinite(bpd).all())}
+    d_.precision = "bf16"
+    out["bf16_vs_fp32_rel_err_of_bpd"] = float(((vals["bf16"] - vals["fp32"]).abs() / vals["fp32"].abs()).max())
+    try:
+        bs = 10
+        sd = {k: v.to(dev) for k, v in pkg.synth.make_decoder_state_dict(1, seed=0, g=0.05).items()}
+        run = lambda: likelihood_oracle.likelihood(sd, y[:bs], maskd[:bs], mud[:bs], eu, eps[:bs])
+        ms = _event_time_ms(torch, run, 1, 1)
+        ref = run()[0]
+        out["gpu_eager"] = {"ms_sample": ms, "sample": f"{bs} hypotheses, scaled to {B_}", "hypotheses_per_sec": bs / (ms * 1e-3),
+                            "what": "reference algorithm (two estimator forwards + torch.autograd per step, cuDNN TF32) on this GPU"}
+        out["vs_gpu_eager"] = {p_: out[p_]["hypotheses_per_sec"] / out["gpu_eager"]["hypotheses_per_sec"] for p_ in ("fp32", "bf16")}
+        out["fp32_vs_eager_rel_err_of_bpd"] = float(((vals["fp32"][:bs] - ref).abs() / ref.abs()).max())
+    except Exception as e:
+        out["gpu_eager"] = {"error": repr(e)[:200]}
     return out
 
 

@@ -86,11 +86,19 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 gn_bwd_apply_kernel(GnBwdArgs a, int blocks, int stat_blocks) {
     __shared__ double s_red[16];
+    __shared__ double s_part[16][16];
     const int b = blockIdx.y;
+    {   // fixed-order reduction of the sample's partial rows: 16 row slices in parallel, then the slices in order
+        const int col = threadIdx.x & 15, slice = threadIdx.x >> 4;
+        double s = 0.0;
+        const float* pp = a.partials + (size_t)b * stat_blocks * 16 + col;
+        for (int i = slice; i < stat_blocks; i += 16) s += (double)__ldcg(pp + (size_t)i * 16);
+        s_part[slice][col] = s;
+    }
+    __syncthreads();
     if (threadIdx.x < 16) {
         double s = 0.0;
-        const float* pp = a.partials + (size_t)b * stat_blocks * 16 + threadIdx.x;
-        for (int i = 0; i < stat_blocks; ++i) s += (double)pp[(size_t)i * 16];
+        for (int i = 0; i < 16; ++i) s += s_part[i][threadIdx.x];
         s_red[threadIdx.x] = s;
     }
     __syncthreads();
@@ -410,7 +418,7 @@ inline unsigned int nblk(size_t n, int bs) { return (unsigned int)((n + bs - 1) 
 
 int gn_bwd_blocks(int H, int W) {
     const int hw = H * W;
-    int blocks = (hw + 2047) / 2048;
+    int blocks = (hw + 127) / 128;                    // ~128 pixels per CTA: a 20 x 100 level still gives 16 CTAs per sample
     if (blocks < 1) blocks = 1;
     if (blocks > 256) blocks = 256;
     return blocks;

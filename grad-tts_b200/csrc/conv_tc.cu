@@ -96,10 +96,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         mbar_expect_tx(&full[stage], (uint32_t)((dummy ? 0 : p.a_bytes) + (resident ? 0 : kBBytes)));
                         if (dummy) {
                         } else if (p.stride2) {
-                            // 5-D view (2C, W/2, 2, H/2, B): input pixel 2*o + d, d in {-1,0,1}
+                            // 5-D view (2C, W/2, 2, H/2, B): input pixel 2*o + d = pair (o + floor(d/2)), parity d & 1; d in {-1,0,1} for
+                            // the 3x3 Downsample, {-1,0,1,2} for the 4x4 conv that is the Upsample's data gradient
                             const int px = dx & 1, py = dy & 1;
-                            tma_load_5d(&mapA0, &full[stage], sa, px * p.Cin0 + ck * 64, w0 + (dx < 0 ? -1 : 0), py,
-                                        h0 + (dy < 0 ? -1 : 0), b);
+                            tma_load_5d(&mapA0, &full[stage], sa, px * p.Cin0 + ck * 64, w0 + (dx >> 1), py, h0 + (dy >> 1), b);
                         } else if (ck < p.nchunk0) {
                             tma_load_4d(&mapA0, &full[stage], sa, ck * 64, w0 + dx, h0 + dy, b);
                         } else {

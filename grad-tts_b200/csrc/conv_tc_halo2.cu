@@ -39,8 +39,10 @@ __device__ __forceinline__ constexpr uint32_t make_idesc2() {      // as make_id
 // ceil(tiles per sample / grid) <= acc_bufs<N>()), otherwise the MMA warp would wait for a buffer that pass 2 can only free after
 // the barrier.  All CTAs must be co-resident for the barrier to complete: the grid is clamped to what cudaOccupancyMaxActiveClusters
 // reports (conv_tc_halo2_max_grid).  Shared memory: [misc+4096, +8192) holds the per-channel affine tables of two runs in flight
-// (scale = rstd*gamma, shift = (bias - mean)*scale + beta), the kApplyExtra bytes behind misc hold the time-bias rows and four
-// mbarriers (aff_full / aff_empty per table slot).
+// (scale = rstd*gamma, shift = beta - mean*scale), the kApplyExtra bytes behind misc hold the time-bias rows and four mbarriers
+// (aff_full / aff_empty per table slot).  Pass 2 first rounds (accumulator + bias) to bf16, i.e. to the value the unfused plan
+// stores, and then uses gn_apply's own formulas: the two plans are bitwise identical (the decoder picks the plan by batch size, and
+// a sample's result must not depend on that).
 constexpr int kApplyExtra = 3072;
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
@@ -128,13 +130,15 @@ __device__ __forceinline__ void tc_stats_apply_loop(const TcParams& p, const TcS
             const int q = lane & 3, r0 = lane >> 2;
             const float4* pp = reinterpret_cast<const float4*>(e.gn_partials + (size_t)b * G * 16) + q;
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            for (int base = 0; base < nrows; base += 64) {
+            // rows in CTA order 0..G-1, exactly the order (and lane pattern) of tc_teardown's finalisation: a CTA that holds no tile of
+            // this sample contributes zero there and is skipped here, so both kernels add the same numbers in the same order
+            for (int base = 0; base < G; base += 64) {
                 float4 v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int k = base + r0 + 8 * i;
-                    int c = start + k; if (c >= G) c -= G;
-                    v[i] = k < nrows ? __ldcg(pp + (size_t)c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int c = base + r0 + 8 * i;
+                    int rel = c - start; if (rel < 0) rel += G;
+                    v[i] = (c < G && rel < nrows) ? __ldcg(pp + (size_t)c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -176,7 +180,7 @@ __device__ __forceinline__ void tc_stats_apply_loop(const TcParams& p, const TcS
             const int gg = c / kGsz;
             const float sc = ap.s_mr[8 + gg] * __ldg(e.ap_gamma + c);
             ap.s_sc[sl * N + c] = sc;
-            ap.s_sh[sl * N + c] = fmaf(sh.s_bias[c] - ap.s_mr[gg], sc, __ldg(e.ap_beta + c));
+            ap.s_sh[sl * N + c] = fmaf(-ap.s_mr[gg], sc, __ldg(e.ap_beta + c));       // the same expression as gn_apply (pointwise.cu)
             ap.s_tb[sl * N + c] = e.ap_tbias ? __ldg(e.ap_tbias + (size_t)b * e.ap_tb_bstride + c) : 0.f;
         }
         __syncwarp();
@@ -294,9 +298,16 @@ __device__ __forceinline__ void tc_epilogue_apply_loop(const TcParams& p, const 
                     for (int q4 = 0; q4 < 8; ++q4) {
                         const float4 sc4 = *reinterpret_cast<const float4*>(&t_sc[c0 + q4 * 4]);
                         const float4 sh4 = *reinterpret_cast<const float4*>(&t_sh[c0 + q4 * 4]);
-                        const float2 y0 = ffma2(make_float2(__uint_as_float(r[q4 * 4 + 0]), __uint_as_float(r[q4 * 4 + 1])),
+                        const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[cbase + c0 + q4 * 4]);
+                        // conv + bias rounded to bf16 exactly as the unfused plan stores it, so both plans give the same bits
+                        // (a sample must not depend on which plan its batch size selects)
+                        const float2 a0 = fadd2(make_float2(__uint_as_float(r[q4 * 4 + 0]), __uint_as_float(r[q4 * 4 + 1])), make_float2(b4.x, b4.y));
+                        const float2 a1 = fadd2(make_float2(__uint_as_float(r[q4 * 4 + 2]), __uint_as_float(r[q4 * 4 + 3])), make_float2(b4.z, b4.w));
+                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(a0.x, a0.y), h1 = __floats2bfloat162_rn(a1.x, a1.y);
+                        const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0), u1 = *reinterpret_cast<const uint32_t*>(&h1);
+                        const float2 y0 = ffma2(make_float2(__uint_as_float(u0 << 16), __uint_as_float(u0 & 0xffff0000u)),
                                                 make_float2(sc4.x, sc4.y), make_float2(sh4.x, sh4.y));
-                        const float2 y1 = ffma2(make_float2(__uint_as_float(r[q4 * 4 + 2]), __uint_as_float(r[q4 * 4 + 3])),
+                        const float2 y1 = ffma2(make_float2(__uint_as_float(u1 << 16), __uint_as_float(u1 & 0xffff0000u)),
                                                 make_float2(sc4.z, sc4.w), make_float2(sh4.z, sh4.w));
                         f[q4 * 2 + 0] = mish2_fast(y0, fmul2(y0, l2e));
                         f[q4 * 2 + 1] = mish2_fast(y1, fmul2(y1, l2e));
@@ -620,7 +631,7 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const float s0 = rstd * __ldg(e.in_gamma + c0 + 2 * q), s1 = rstd * __ldg(e.in_gamma + c0 + 2 * q + 1);
-                        const float h0f = __ldg(e.in_beta + c0 + 2 * q) - mean * s0, h1f = __ldg(e.in_beta + c0 + 2 * q + 1) - mean * s1;
+                        const float h0f = fmaf(-mean, s0, __ldg(e.in_beta + c0 + 2 * q)), h1f = fmaf(-mean, s1, __ldg(e.in_beta + c0 + 2 * q + 1));
                         sc[q] = make_float2(s0, s1);
                         sh2[q] = make_float2(h0f, h1f);
                         tb[q] = e.in_tbias ? make_float2(__ldg(e.in_tbias + (size_t)b * e.in_tb_bstride + c0 + 2 * q),

@@ -746,8 +746,16 @@ struct PlanBuilder {
         const double npx = (double)g.B * g.nphase * g.Hg * g.Wg;
         const double flops = 2.0 * npx * g.Cout * g.ntaps * (g.Cin0 + g.Cin1);
         ActKind k = kind;
-        pl->push(std::string("bwd_") + what + "_" + std::to_string(g.Cin0) + "_" + std::to_string(g.Cout) + "_h" + std::to_string(g.Hout), 1, flops, 0.0,
-                 [k, g, src, w, e](cudaStream_t s) { return conv_ffma(k, g, src, nullptr, w, e, s); });
+        const std::string name = std::string("bwd_") + what + "_" + std::to_string(g.Cin0) + "_" + std::to_string(g.Cout) + "_h" + std::to_string(g.Hout);
+        if (use_tc()) {
+            // bf16 mode: the data gradients run on the same tcgen05 kernels as the forward convolutions
+            TcConvPlan* tp = conv_tc_plan_create(g, src, nullptr, w, g.ntaps * g.nphase * g.Cout, e, d->num_sms, d->halo_mode);
+            if (!tp) { failed = true; return; }
+            pl->tc_plans.push_back(tp);
+            pl->push(name, 1, flops, 0.0, [tp](cudaStream_t s) { return conv_tc_launch(tp, s); });
+            return;
+        }
+        pl->push(name, 1, flops, 0.0, [k, g, src, w, e](cudaStream_t s) { return conv_ffma(k, g, src, nullptr, w, e, s); });
     }
     void add_mask_mul(int lvl, int C, const void* in, void* out) {
         ActKind k = kind;
@@ -1378,10 +1386,11 @@ int decoder_profile_step(Decoder* d, int B, int T, int flags, int reps, char* bu
     if (int rc = common_checks(d, B, T, (const float*)1)) return rc;
     GTTS_REQUIRE(buf != nullptr && buflen > 64 && reps >= 1, "profile: bad arguments");
     const ActKind kind = (flags & 1) ? ACT_F32 : ACT_BF16;
-    const int Bc = std::min(d->max_chunk, B);
+    const bool vjp = (flags & 4) != 0;                       // bit 2: the forward + backward (VJP) plan instead of the sampler step
+    const int Bc = std::min(vjp ? std::min(d->max_chunk, 16) : d->max_chunk, B);
     if (int rc = enter_call(d, stream)) return rc;
     Plan* pl = nullptr;
-    if (int rc = get_plan(d, kind, Bc, T, false, false, stream, &pl)) return rc;
+    if (int rc = get_plan(d, kind, Bc, T, vjp, false, stream, &pl, vjp)) return rc;
     const size_t nops = pl->ops.size();
     std::vector<cudaEvent_t> ev(2 * nops);
     for (auto& e : ev) GTTS_CHECK_CUDA(cudaEventCreate(&e));

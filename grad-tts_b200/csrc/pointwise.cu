@@ -405,7 +405,8 @@ gn_apply_fast_kernel(GnApplyArgs a) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const float s0 = rstd * __ldg(a.gamma + c0 + 2 * q), s1 = rstd * __ldg(a.gamma + c0 + 2 * q + 1);
-        const float h0 = __ldg(a.beta + c0 + 2 * q) - mean * s0, h1 = __ldg(a.beta + c0 + 2 * q + 1) - mean * s1;
+        // explicit fma: the GroupNorm-apply epilogue of the conv (conv_tc_halo2.cu) must reproduce these bits
+        const float h0 = fmaf(-mean, s0, __ldg(a.beta + c0 + 2 * q)), h1 = fmaf(-mean, s1, __ldg(a.beta + c0 + 2 * q + 1));
         sc[q] = make_float2(s0, s1);                   sh[q] = make_float2(h0, h1);
         tb[q] = kTb ? make_float2(__ldg(a.tbias + (size_t)b * a.tbias_bstride + c0 + 2 * q),
                                      __ldg(a.tbias + (size_t)b * a.tbias_bstride + c0 + 2 * q + 1))

@@ -42,10 +42,10 @@ def likelihood(sd, data, mask, mu, n_euler, eps, spk=None, n_spks=1, beta_min=0.
 
     x = data * mask                                                  # likelihood.py:110
     B = x.shape[0]
-    logp = torch.zeros(B)
+    logp = torch.zeros(B, device=x.device)
     h = 1.0 / n_euler
     for i in range(n_euler):                                         # likelihood.py:99-107
-        t = torch.ones(B) * ((i + 0.5) * h)
+        t = torch.ones(B, device=x.device) * ((i + 0.5) * h)
         with torch.no_grad():
             d = drift_fn(x, t)
         dv = div_fn(x, t)

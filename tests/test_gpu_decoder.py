@@ -106,23 +106,20 @@ def test_fused_gn_input_is_bitwise_equal_to_separate_pass(pkg, synth):
     assert torch.equal(outs[0], outs[1])
 
 
-def test_apply_epilogue_agrees_with_separate_gn_pass(pkg, synth):
-    """Default plan (Block convs finish GroupNorm+Mish in their epilogue, fuse_epi=1) against the plan with the separate gn_apply
-    pass (fuse_epi=0).  Not bitwise: the fused epilogue normalises the fp32 accumulator, the separate pass its bf16 rounding; both
-    must sit inside the bf16 tolerance of the oracle and close to each other; and the fused plan launches fewer kernels."""
+def test_apply_epilogue_is_bitwise_equal_to_separate_gn_pass(pkg, synth):
+    """Plan whose Block convs finish GroupNorm+Mish(+time bias / residual) in their own epilogue (fuse_epi=2: always; the default
+    uses it for small batches) against the plan with the separate gn_apply pass (fuse_epi=0): the same bits -- the fused epilogue
+    rounds conv+bias to bf16 like the stored raw tensor and uses gn_apply's formulas -- with 22 fewer launches per Euler step."""
     outs, launches = [], []
     z, mask, mu, spk, _ = synth.make_inputs(3, 88, 247, seed=21)
-    for fuse in (1, 0):
+    for fuse in (2, 0):
         dec, sd = _module(pkg, synth, 247, 3, "bf16")
-        dec.estimator.set_option("fuse_epi", 2 if fuse else 0)          # 2 = always (the default, 1, fuses only small batches)
+        dec.estimator.set_option("fuse_epi", fuse)
         outs.append(dec(z.to(DEV), mask.to(DEV), mu.to(DEV), 3, False, spk.to(DEV)).cpu())
         launches.append(dec.estimator.launches_last_call())
-    with torch.no_grad():
-        ref = decoder_oracle.reverse_diffusion(sd, z, mask, mu, 3, False, spk, 247)
-    rr = lambda a, b: float((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt())
-    assert rr(outs[0], ref) <= 2e-2 and rr(outs[1], ref) <= 2e-2, (rr(outs[0], ref), rr(outs[1], ref))
-    assert rr(outs[0], outs[1]) <= 2e-2
-    assert launches[0] < launches[1], launches
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1])
+    assert launches[0] == launches[1] - 3 * 22, launches
 
 
 def test_long_random_weight_run_stays_finite(pkg, synth, monkeypatch):

@@ -211,7 +211,10 @@ def test_conv_apply_epilogue(case):
     live = mask[:, None, None, :].expand_as(ref) > 0
     assert not torch.isnan(got).any(), "output has unwritten (NaN) entries"
     err = float((got - ref).abs().max())
-    assert err <= 4e-2, f"{name}: max-abs err {err} (|ref|max {float(ref.abs().max())})"
+    # bf16 output (half an ulp is 0.031 at |y| ~ 9) on top of the bf16 rounding of conv + bias that the kernel applies on purpose
+    # (bitwise equality with the unfused plan)
+    tol = max(4e-2, 6e-3 * float(ref.abs().max()))
+    assert err <= tol, f"{name}: max-abs err {err} (|ref|max {float(ref.abs().max())})"
     assert float(got[~live].abs().max() if (~live).any() else 0.0) == 0.0
     serr = float(((stats.cpu() - sref).abs() / (sref.abs() + 1.0)).max())
     assert serr <= 2e-3, f"{name}: GN stats err {serr}"

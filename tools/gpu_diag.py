@@ -240,6 +240,32 @@ def stage_align():
           f"log_prior max err {float((out[0].cpu() - lp).abs().max()):.2e}", flush=True)
 
 
+def stage_profile_vjp():
+    """per-op times of the forward + backward (VJP) plan, both precisions"""
+    import ctypes, json
+    for prec, flags in (("bf16", 4), ("fp32", 5)):
+        dec, _ = _decoder(1, 0, prec)
+        B, T = 16, 400
+        buf = ctypes.create_string_buffer(1 << 18)
+        h = dec.estimator._get_handle()
+        rc = pkg._lib.load().gtts_decoder_profile_step(h, B, T, flags, 3, buf, len(buf), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        pkg._lib.check(rc, "profile")
+        rep = json.loads(buf.value.decode())
+        tot = sum(o["ms"] for o in rep["ops"])
+        print(f"--- VJP profile {prec} B={B} T={T}: total {tot:.3f} ms over {len(rep['ops'])} ops")
+        agg = {}
+        for o in rep["ops"]:
+            import re
+            k = re.sub(r"(_\d+)*(_h\d+)?$", "", o["name"])
+            agg[k] = agg.get(k, 0.0) + o["ms"]
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1]):
+            print(f"   {k:28s} {v * 1e3:9.1f} us  {100 * v / tot:5.1f}%")
+        for o in rep["ops"]:
+            if o["name"].startswith("bwd_"):
+                tf = o["flops"] / (o["ms"] * 1e-3) / 1e12 if o["ms"] > 0 else 0
+                print(f"      {o['name']:32s} {o['ms'] * 1e3:9.1f} us  {tf:8.1f} TFLOP/s")
+
+
 def stage_profile():
     import ctypes, json
     for (n_spks, B, T) in [(1, 16, 1720), (1, 1, 400)]:
@@ -269,7 +295,7 @@ def stage_profile():
 if __name__ == "__main__":
     st = sys.argv[1]
     print(f"===== stage {st} on {torch.cuda.get_device_name(0)}", flush=True)
-    {"mas": stage_mas, "conv_ffma": lambda: (stage_conv(0, 0), stage_conv(0, 1)), "conv_tc": lambda: stage_conv(1, 1),
+    {"profile_vjp": stage_profile_vjp, "mas": stage_mas, "conv_ffma": lambda: (stage_conv(0, 0), stage_conv(0, 1)), "conv_tc": lambda: stage_conv(1, 1),
      "dec_fp32": lambda: stage_dec("fp32"), "dec_bf16_ffma": lambda: stage_dec("bf16", 0),
      "dec_bf16_tc": lambda: stage_dec("bf16", 1), "perf": stage_perf, "profile": stage_profile, "halo": stage_halo, "convdbg": stage_convdbg, "mbench": stage_mbench, "align": stage_align}[st]()
     torch.cuda.synchronize()
