@@ -533,8 +533,12 @@ def fp32_record(pkg, torch, get_decoder, dev, devt, Bl, T):
     nsteps = 2
     ms5 = _event_time_ms(torch, lambda: d_(devt[0], devt[1], devt[2], nsteps, False, devt[3]), 1, 1)
     fs = Bl * T * nsteps / (ms5 * 1e-3)
+    # the CUDA-core FFMA convolutions of round 1, for comparison (same tolerance, option fp32_tc=0)
+    d_.estimator.set_option("fp32_tc", 0)
+    ms5_ffma = _event_time_ms(torch, lambda: d_(devt[0], devt[1], devt[2], nsteps, False, devt[3]), 1, 1)
+    d_.estimator.set_option("fp32_tc", 1)
     d_.precision = "bf16"
-    return {"mode": d_.estimator.fp32_conv_impl() if hasattr(d_.estimator, "fp32_conv_impl") else "ffma",
+    return {"mode": d_.estimator.fp32_conv_impl(), "ffma_convs_frame_steps_per_sec": Bl * T * nsteps / (ms5_ffma * 1e-3),
             "C1": {"ms_per_step": ms1, "value": B1 * T1 / (ms1 * 1e-3), "unit": "frames/s", "euler_steps": eu1},
             "C5_shape": {"batch": Bl, "frames": T, "euler_steps_timed": nsteps, "ms": ms5, "frame_steps_per_sec": fs,
                          "frames_per_sec_at_100_steps": fs / 100.0, "model_tflops": fs * FLOP_PER_FRAME_STEP[1] / 1e12,

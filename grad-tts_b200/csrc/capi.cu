@@ -332,8 +332,10 @@ int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, i
                    const float* mask, void* out, float* gn_stats, int per_sample_weights, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const ActKind ak = act ? ACT_BF16 : ACT_F32;
-    GTTS_REQUIRE(impl == 0 || ak == ACT_BF16, "tcgen05 conv needs bf16 activations");
-    const int halo_mode = impl >= 2 ? impl - 1 : 0;            // impl 2 -> halo box 18x16, 3 -> halo box 18x10
+    const bool split = impl == 4;                              // fp32 tensors through the six-term bf16 split on the tensor cores
+    GTTS_REQUIRE(impl == 0 || split || ak == ACT_BF16, "tcgen05 conv needs bf16 activations");
+    GTTS_REQUIRE(!split || (ak == ACT_F32 && !per_sample_weights), "split conv: fp32 activations, shared weights");
+    const int halo_mode = split ? 2 : (impl >= 2 ? impl - 1 : 0);   // impl 2 -> halo box 18x16, 3 -> halo box 18x10
     const int Cin = Cin0 + Cin1;
     ConvGeom g;
     memset(&g, 0, sizeof(g));
@@ -390,13 +392,26 @@ int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, i
         e.gn_partials = partials; e.gn_stats = gn_stats; e.gn_counters = counters; e.gn_eps = 1e-5f;
     }
     int rc = 0;
+    void *p0 = nullptr, *p1 = nullptr, *w3 = nullptr;
+    if (split) {
+        const size_t npix = (size_t)B * H * W;
+        GTTS_CHECK_CUDA(cudaMalloc(&p0, npix * 3 * Cin0 * 2));
+        if (Cin1) GTTS_CHECK_CUDA(cudaMalloc(&p1, npix * 3 * Cin1 * 2));
+        GTTS_CHECK_CUDA(cudaMalloc(&w3, wrows * 6 * Cin * 2));
+        if (int r = split_f32_planes((const float*)src0, p0, npix, Cin0, s)) return r;
+        if (Cin1) if (int r = split_f32_planes((const float*)src1, p1, npix, Cin1, s)) return r;
+        if (int r = split_pack_weights((const float*)wpk, w3, wrows, Cin, s)) return r;
+        g.split = 1;
+        e.out_f32 = 1;
+    }
     if (impl >= 1) {
-        GTTS_REQUIRE(!halo_mode || (conv_tc_halo_eligible(g) && !residual && !mask) || (halo_mode == 2 && conv_tc_convT_halo_eligible(g) && mask && !residual),
+        GTTS_REQUIRE(split || !halo_mode || (conv_tc_halo_eligible(g) && !residual && !mask) || (halo_mode == 2 && conv_tc_convT_halo_eligible(g) && mask && !residual),
                      "halo test: geometry not eligible");
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        TcConvPlan* tp = conv_tc_plan_create(g, src0, src1, wpk, (int)wrows, e, sms, halo_mode);
+        TcConvPlan* tp = split ? conv_tc_plan_create(g, p0, p1, w3, (int)wrows, e, sms, halo_mode)
+                               : conv_tc_plan_create(g, src0, src1, wpk, (int)wrows, e, sms, halo_mode);
         if (!tp) rc = 1;
         else {
             rc = conv_tc_launch(tp, s);
@@ -483,7 +498,7 @@ int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, i
         rc = conv_ffma(ak, g, src0, src1, wpk, e, s);
     }
     cudaError_t ce = cudaStreamSynchronize(s);
-    cudaFree(wpk); cudaFree(partials); cudaFree(counters);
+    cudaFree(wpk); cudaFree(partials); cudaFree(counters); cudaFree(p0); cudaFree(p1); cudaFree(w3);
     if (rc) return rc;
     GTTS_CHECK_CUDA(ce);
     GTTS_CHECK_CUDA(cudaGetLastError());

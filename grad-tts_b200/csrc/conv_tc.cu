@@ -30,7 +30,7 @@ using namespace tc;
 namespace {
 
 // kStats: GroupNorm partial statistics of (acc + bias); kRes: + residual; kMask: * mask[b][w]
-template <int N, bool kStats, bool kRes, bool kMask>
+template <int N, bool kStats, bool kRes, bool kMask, bool kOutF32 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapWh, const TcParams p) {
@@ -99,11 +99,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             // 5-D view (2C, W/2, 2, H/2, B): input pixel 2*o + d = pair (o + floor(d/2)), parity d & 1; d in {-1,0,1} for
                             // the 3x3 Downsample, {-1,0,1,2} for the 4x4 conv that is the Upsample's data gradient
                             const int px = dx & 1, py = dy & 1;
-                            tma_load_5d(&mapA0, &full[stage], sa, px * p.Cin0 + ck * 64, w0 + (dx >> 1), py, h0 + (dy >> 1), b);
-                        } else if (ck < p.nchunk0) {
-                            tma_load_4d(&mapA0, &full[stage], sa, ck * 64, w0 + dx, h0 + dy, b);
+                            int which, chan;
+                            tc_chunk_src(p, ck, &which, &chan);
+                            tma_load_5d(&mapA0, &full[stage], sa, px * p.Cin0 + chan, w0 + (dx >> 1), py, h0 + (dy >> 1), b);
                         } else {
-                            tma_load_4d(&mapA1, &full[stage], sa, (ck - p.nchunk0) * 64, w0 + dx, h0 + dy, b);
+                            int which, chan;
+                            tc_chunk_src(p, ck, &which, &chan);
+                            tma_load_4d(which ? &mapA1 : &mapA0, &full[stage], sa, chan, w0 + dx, h0 + dy, b);
                         }
                         if (resident) {
                         } else if (p.mc) {
@@ -161,7 +163,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     } else if (warp == 3) {
         tc_stats_loop<kStats>(p, sh, lane);
     } else if (warp >= 4) {
-        tc_epilogue_loop<N, kStats, kRes, kMask>(p, sh, tmem_base, warp, lane);
+        tc_epilogue_loop<N, kStats, kRes, kMask, kOutF32>(p, sh, tmem_base, warp, lane);
     }
     tc_teardown<N, kStats>(p, sh, smem, tmem_base, tid, warp, lane);
 }
@@ -273,8 +275,13 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
     memset(pl, 0, sizeof(*pl));
     TcParams& p = pl->p;
     const bool convT_halo = halo_mode == 2 && conv_tc_convT_halo_eligible(g) && e.mask && !e.residual && !e.gn_partials &&
-                            num_sms >= 2;
+                            num_sms >= 2 && !g.split;    // split convs: the ConvT halo variant keeps 2*nck A stages resident -- too many chunks
+    if (g.split && (e.apply || e.in_stats)) { set_error("conv_tc: split (fp32) convs take the plain epilogues only"); return nullptr; }
+    if (g.split && 6 * (g.Cin0 + g.Cin1) / 64 > 48) { set_error("conv_tc: split conv with more than 48 K chunks"); return nullptr; }
     if (halo_mode && !convT_halo && !e.apply && (!conv_tc_halo_eligible(g) || e.residual || e.mask)) halo_mode = 0;
+    // split convs know the CTA-pair halo kernel and the per-tap kernel only (the single-CTA halo kernel has no chunk table)
+    if (g.split && halo_mode && (halo_mode != 2 || !conv_tc_cta2_enabled() || num_sms < 2 ||
+                                 (long)g.B * ((g.Hg + 15) / 16) * ((g.Wg + 7) / 8) < 2)) halo_mode = 0;
     p.halo_mode = halo_mode;
     if (halo_mode) {
         // 128-pixel halo tile: 16 rows x 8 pixels (8-row UMMA groups run along W), or transposed 8 rows x 16 pixels with
@@ -293,6 +300,21 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
     p.ph_inner = convT_halo ? 4 : 0;
     p.Hg = g.Hg; p.Wg = g.Wg; p.Hout = g.Hout; p.Wout = g.Wout; p.out_step = g.out_step;
     p.ntaps = g.ntaps; p.nchunk0 = g.Cin0 / 64; p.nchunk1 = g.Cin1 / 64; p.Cin0 = g.Cin0;
+    if (g.split) {
+        // K = 6 * Cin: terms (plane of x, part of w) = (h,l) (m,m) (h,m) (l,h) (m,h) (h,h); within a term source 0 then source 1.
+        // Smallest terms first: the tensor core's fp32 accumulation truncates (measured: error grows linearly with the number of
+        // accumulation steps taken while the accumulator is large, 3e-5 relative at K = 2304 with the big term first), so the
+        // five correction terms are summed while the accumulator is still ~2^-8 of its final size and only the K/16 steps of the
+        // (h,h) term run at full magnitude.
+        const int plane_of_term[6] = {0, 1, 0, 2, 1, 0};
+        int ck = 0;
+        for (int t = 0; t < 6; ++t) {
+            for (int c = 0; c < g.Cin0 / 64; ++c, ++ck) { p.a_map[ck] = 0; p.a_off[ck] = (int16_t)(plane_of_term[t] * g.Cin0 + c * 64); }
+            for (int c = 0; c < g.Cin1 / 64; ++c, ++ck) { p.a_map[ck] = 1; p.a_off[ck] = (int16_t)(plane_of_term[t] * g.Cin1 + c * 64); }
+        }
+        p.split = 1; p.nchunk0 = ck; p.nchunk1 = 0;
+        p.Cin0 = 3 * g.Cin0;                           // channels per pixel of the plane tensor (stride-2 5-D view)
+    }
     p.stride2 = (g.stride == 2); p.w_batch_rows = g.w_batch_rows;
     p.num_tiles = g.B * p.nphase * p.tiles_h * p.tiles_w;
     p.a_bytes = p.bh * p.bw * 128;
@@ -316,6 +338,7 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
         // CTA pairs for every halo conv (measured, chunk 16x1720: 64->64 174 -> 136 us, 128->128 134 -> 108 us,
         // 256->64 192 -> 131 us, 512->128 144 -> 125 us, 256->256 134 -> 123 us).  GTTS_CTA2=0: single-CTA kernels.
         const bool cta2 = convT_halo || (halo_mode == 2 && conv_tc_cta2_enabled() && p.num_tiles >= 2 && num_sms >= 2);
+        if (g.split && !cta2) { set_error("conv_tc: split convs need the CTA-pair halo kernel or per-tap boxes"); delete pl; return nullptr; }
         if (cta2) {
             // CTA pair: every CTA holds half of each weight tile (Cout/2 rows)
             const int bhalf = g.Cout * 64;
@@ -413,11 +436,12 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
             return encode_map(m, src, 5, dims, str, box);
         }
     };
-    ok = ok && make_a(&pl->mapA0, src0, g.Cin0);
-    if (g.Cin1 > 0) ok = ok && make_a(&pl->mapA1, src1, g.Cin1);
+    const int cmul = g.split ? 3 : 1;                  // split: [hi | mid | lo] planes per pixel
+    ok = ok && make_a(&pl->mapA0, src0, cmul * g.Cin0);
+    if (g.Cin1 > 0) ok = ok && make_a(&pl->mapA1, src1, cmul * g.Cin1);
     else pl->mapA1 = pl->mapA0;
     {
-        const uint64_t K = (uint64_t)(g.Cin0 + g.Cin1);
+        const uint64_t K = (uint64_t)(g.split ? 6 : 1) * (uint64_t)(g.Cin0 + g.Cin1);
         uint64_t dims[2] = {K, (uint64_t)weight_rows};
         uint64_t str[1] = {K * 2};
         uint32_t box[2] = {64, (uint32_t)g.Cout};
@@ -439,10 +463,10 @@ int conv_tc_plan_grid(const TcConvPlan* p) { return p->grid; }
 void conv_tc_plan_set_debug(TcConvPlan* p, unsigned long long* dbg_out) { p->p.dbg_out = dbg_out; }
 
 namespace {
-template <int N, bool kStats, bool kRes, bool kMask>
+template <int N, bool kStats, bool kRes, bool kMask, bool kOutF32 = false>
 int launch_variant(const TcConvPlan* pl, cudaStream_t stream) {
     static bool attr_set = false;
-    auto k = conv_tc_kernel<N, kStats, kRes, kMask>;
+    auto k = conv_tc_kernel<N, kStats, kRes, kMask, kOutF32>;
     if (!attr_set) {
         GTTS_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
@@ -456,6 +480,13 @@ template <int N>
 int launch_n(const TcConvPlan* pl, cudaStream_t stream) {
     const ConvEpilogue& e = pl->p.e;
     const bool st = e.gn_partials != nullptr, rs = e.residual != nullptr, mk = e.mask != nullptr;
+    if (e.out_f32) {                                   // fp32 activations (fp32 mode on the tensor cores)
+        if (st) return launch_variant<N, true, false, false, true>(pl, stream);
+        if (rs && mk) return launch_variant<N, false, true, true, true>(pl, stream);
+        if (rs) return launch_variant<N, false, true, false, true>(pl, stream);
+        if (mk) return launch_variant<N, false, false, true, true>(pl, stream);
+        return launch_variant<N, false, false, false, true>(pl, stream);
+    }
     if (st) return launch_variant<N, true, false, false>(pl, stream);
     if (rs && mk) return launch_variant<N, false, true, true>(pl, stream);
     if (rs) return launch_variant<N, false, true, false>(pl, stream);

@@ -42,6 +42,10 @@ struct TcParams {
     int8_t dy[4][16], dx[4][16];
     int wrow[4][16];
     int oy[4], ox[4];
+    // split (fp32-on-tensor-cores) convs: K chunk ck reads source a_map[ck] at channel a_off[ck] of its 3*Cin-channel plane tensor
+    int split;
+    int16_t a_off[48];
+    int8_t a_map[48];
     ConvEpilogue e;
 };
 
@@ -88,6 +92,13 @@ template <int N>
 __device__ __forceinline__ constexpr uint32_t make_idesc() {
     // kind::f16: D=f32 (bit 4), A=bf16 (bit 7), B=bf16 (bit 10), K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// (source, channel offset) of K chunk ck
+__device__ __forceinline__ void tc_chunk_src(const TcParams& p, int ck, int* which, int* chan) {
+    if (p.split) { *which = p.a_map[ck]; *chan = p.a_off[ck]; }
+    else if (ck < p.nchunk0) { *which = 0; *chan = ck * 64; }
+    else { *which = 1; *chan = (ck - p.nchunk0) * 64; }
 }
 
 // Number of tile iterations of this CTA.  With weight multicast both CTAs of a pair must run the same count, so the
@@ -219,7 +230,7 @@ __device__ __forceinline__ void tc_stats_loop(const TcParams& p, const TcShared&
 // Epilogue warps (warps 4..19): TMEM -> registers -> (+bias, stats, +residual, *mask) -> bf16 NHWC stores.
 // Two groups of 8 warps take alternate tiles (group = tile iteration parity), so one group's TMEM reads, arithmetic
 // and stores overlap the other's; within a group two warps share each TMEM lane quarter and split the columns.
-template <int N, bool kStats, bool kRes, bool kMask>
+template <int N, bool kStats, bool kRes, bool kMask, bool kOutF32 = false>
 __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShared& sh, uint32_t tmem_base, int warp,
                                                  int lane) {
     constexpr int kColsPerWarp = N / 2;            // two epilogue warps share each TMEM lane quarter
@@ -319,7 +330,28 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
             }
             const long long tm1 = GTTS_EPI_CLK();
             c_math += tm1 - tm0;
-            if (valid) {
+            if (valid && kOutF32) {
+                // fp32 activations (fp32 mode on the tensor cores): 32 columns = 128 bytes per pixel, four 32-byte stores
+                float* op = reinterpret_cast<float*>(e.out) + opix * N + cbase + c0;
+                const float* rp = reinterpret_cast<const float*>(e.residual) + opix * N + cbase + c0;
+#pragma unroll
+                for (int v8 = 0; v8 < 4; ++v8) {
+                    uint32_t w[8];
+                    if (kRes) {
+                        uint32_t rr[8];
+                        ld_global_nc_256(rp + v8 * 8, rr);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            f[v8 * 4 + k] = fadd2(f[v8 * 4 + k], make_float2(__uint_as_float(rr[2 * k]), __uint_as_float(rr[2 * k + 1])));
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 o = kMask ? fmul2(f[v8 * 4 + k], m2) : f[v8 * 4 + k];
+                        w[2 * k] = __float_as_uint(o.x); w[2 * k + 1] = __float_as_uint(o.y);
+                    }
+                    st_global_256(op + v8 * 8, w);
+                }
+            } else if (valid) {
                 if (kRes) {
                     const __nv_bfloat16* rp = res + opix * N + cbase + c0;
 #pragma unroll

@@ -364,7 +364,7 @@ constexpr int kFuseWarps = 4;                       // transform warps of the fu
 // times (the per-tap kernel is fill-bound there: 372 TFLOP/s).  Every phase has its own accumulator and epilogue iteration
 // (TcParams::ph_inner = 4, phases innermost); the epilogue multiplies by the mask (kMask).
 // kApply: 0 = off, 1 = GroupNorm-apply epilogue with time bias (block1 of a ResnetBlock), 2 = with residual (block2)
-template <int N, bool kStats, bool kFuse, bool kMask = false, bool kConvT = false, int kApply = 0>
+template <int N, bool kStats, bool kFuse, bool kMask = false, bool kConvT = false, int kApply = 0, bool kOutF32 = false>
 __global__ void __launch_bounds__(kThreads + (kFuse ? kFuseWarps * 32 : 0), 1)
 conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                      const __grid_constant__ CUtensorMap mapWh, const TcParams p) {
@@ -422,7 +422,7 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
         if (lane == 0) {
             int sa = 0, sb = 0;
             uint32_t pha = 0, phb = 0;
-            const int G = (int)gridDim.x, nck0 = p.nchunk0, ht = p.halo_t;
+            const int G = (int)gridDim.x, ht = p.halo_t;
             const uint32_t a_tx = (uint32_t)(18 * pw * 128);
             const int wrow_off = (int)rank * (N / 2);                // my half of the weight rows
             TileWalk tw;
@@ -446,14 +446,16 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
                 const int b = tw.b, h0 = tw.th * p.bh, w0 = tw.tw * p.bw;
                 for (int ck = 0; ck < nck; ++ck) {
                     mbar_wait(&sh.empty[sa], pha ^ 1u);
+                    int which, chan;
+                    tc_chunk_src(p, ck, &which, &chan);
                     if (kFuse) {
                         mbar_expect_tx(&rawfull[sa], a_tx);          // my own tile only; the transform warps pass it on
-                        tma_load_4d(ck < nck0 ? &mapA0 : &mapA1, &rawfull[sa], smem + (size_t)sa * a_stage,
-                                    (ck < nck0 ? ck : ck - nck0) * 64, ht ? h0 - 1 : w0 - 1, ht ? w0 - 1 : h0 - 1, b);
+                        tma_load_4d(which ? &mapA1 : &mapA0, &rawfull[sa], smem + (size_t)sa * a_stage,
+                                    chan, ht ? h0 - 1 : w0 - 1, ht ? w0 - 1 : h0 - 1, b);
                     } else {
                         if (rank == 0) mbar_expect_tx(&sh.full[sa], 2u * a_tx);
-                        tma_load_4d_2sm(ck < nck0 ? &mapA0 : &mapA1, mapa_u32(smem_u32(&sh.full[sa]), 0u), smem + (size_t)sa * a_stage,
-                                        (ck < nck0 ? ck : ck - nck0) * 64, ht ? h0 - 1 : w0 - 1, ht ? w0 - 1 : h0 - 1, b);
+                        tma_load_4d_2sm(which ? &mapA1 : &mapA0, mapa_u32(smem_u32(&sh.full[sa]), 0u), smem + (size_t)sa * a_stage,
+                                        chan, ht ? h0 - 1 : w0 - 1, ht ? w0 - 1 : h0 - 1, b);
                     }
                     if (++sa == nstage) { sa = 0; pha ^= 1u; }
                     if (!resident && !kConvT) {
@@ -603,7 +605,7 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
         else tc_stats_loop<kStats>(p, sh, lane);
     } else if (warp >= 4 && warp < kThreads / 32) {
         if (kApply) tc_epilogue_apply_loop<N, kApply == 1, kApply == 2>(p, sh, tmem_base, warp, lane);
-        else tc_epilogue_loop<N, kStats, false, kMask>(p, sh, tmem_base, warp, lane);
+        else tc_epilogue_loop<N, kStats, false, kMask, kOutF32>(p, sh, tmem_base, warp, lane);
     } else if (kFuse && warp >= kThreads / 32) {
         // ================================================================ input transform (both CTAs)
         // thread -> 16-byte chunk j (8 channels) of rows r0, r0+16, ...; the 128-byte swizzle puts chunk j of row r at
@@ -677,10 +679,10 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
     tc_teardown<N, kStats && !kApply, true>(p, sh, smem, tmem_base, tid, warp, lane);   // kApply finalises its statistics per sample, in the loop
 }
 
-template <int N, bool kStats, bool kFuse, bool kMask = false, bool kConvT = false, int kApply = 0>
+template <int N, bool kStats, bool kFuse, bool kMask = false, bool kConvT = false, int kApply = 0, bool kOutF32 = false>
 int launch_halo2(const TcConvPlan* pl, cudaStream_t stream) {
     static bool attr_set = false;
-    auto k = conv_tc_halo2_kernel<N, kStats, kFuse, kMask, kConvT, kApply>;
+    auto k = conv_tc_halo2_kernel<N, kStats, kFuse, kMask, kConvT, kApply, kOutF32>;
     if (!attr_set) {
         GTTS_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
@@ -747,6 +749,12 @@ int conv_tc_halo2_launch(const TcConvPlan* pl, cudaStream_t stream) {
     }
     GTTS_REQUIRE(e.residual == nullptr && e.mask == nullptr, "conv_tc_halo2: plain or GN-statistics epilogue only");
     const bool st = e.gn_partials != nullptr;
+    if (e.out_f32) {                                                // fp32 activations (fp32 mode on the tensor cores)
+        GTTS_REQUIRE(!e.in_stats, "conv_tc_halo2: fp32 output excludes the fused input transform");
+        if (pl->N == 64) return st ? launch_halo2<64, true, false, false, false, 0, true>(pl, stream) : launch_halo2<64, false, false, false, false, 0, true>(pl, stream);
+        if (pl->N == 128) return st ? launch_halo2<128, true, false, false, false, 0, true>(pl, stream) : launch_halo2<128, false, false, false, false, 0, true>(pl, stream);
+        if (pl->N == 256) return st ? launch_halo2<256, true, false, false, false, 0, true>(pl, stream) : launch_halo2<256, false, false, false, false, 0, true>(pl, stream);
+    }
     if (e.in_stats) {                                               // fused input transform (block2 convs: always with stats)
         GTTS_REQUIRE(st, "conv_tc_halo2: the fused-input variant is built with GroupNorm statistics only");
         if (pl->N == 64) return launch_halo2<64, true, true>(pl, stream);

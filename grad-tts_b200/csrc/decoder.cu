@@ -111,6 +111,7 @@ struct Packed {
     // ---- data-gradient weights (built on the first VJP plan): the same convolutions transposed
     struct ResnetB { void* d1[2]; void* d2; void* rT[2]; };   // block1 dgrad per input source, block2 dgrad, res_conv^T per source
     struct AttnB { void* wq; void* woT; void* wqT; void* wkvT; };   // Wq [128][C], g * Wout^T [128][C], Wq^T [C][128], Wkv^T [C][256]
+    std::map<const void*, void*> w3cache;      // fp32 packed weight -> its [wh wh wh wm wm wl] bf16 expansion (fp32_tc)
     bool bwd_ready = false;
     ResnetB bres[12];
     AttnB battn[6];
@@ -142,6 +143,8 @@ struct Decoder {
                               // wins where launches are latency-bound (B = 1, T = 400: 21 us vs 17 + 8.6 us per Block) and loses on big
                               // batches (chunk 16 x 1720: 128->128 @h40 249 vs 109 + 57 us) because every sample costs one grid barrier.
     int fuse_epi_max_b = 2;
+    int fp32_tc = 1;          // fp32 mode: 1 = convolutions on the tensor cores as six bf16 partial products of [hi|mid|lo] splits (fp32
+                              // accuracy, ~1/6 of the bf16 MMA rate), 0 = CUDA-core FFMA convolutions
     int halo_mode = 2;        // 3x3 convs: 0 = per-tap boxes, 1/2 = halo box (18x16 / 18x10) + shifted descriptor views
     std::map<std::string, float*> params;
     std::map<std::string, size_t> param_numel;
@@ -560,8 +563,8 @@ struct PlanBuilder {
         pl->pooled_bytes = std::max(pl->pooled_bytes, live_bytes);
         return blocks[best].p;
     }
-    void release(const void* p) {
-        if (!p || keep_all) return;
+    void release(const void* p, bool temporary = false) {    // temporary: scratch that even a VJP plan does not keep
+        if (!p || (keep_all && !temporary)) return;
         auto& blocks = d->pool.blocks;
         for (int i = 0; i < (int)blocks.size(); ++i)
             if (blocks[i].p == p && in_use[i]) { in_use[i] = 0; live_bytes -= blocks[i].bytes; return; }
@@ -573,7 +576,44 @@ struct PlanBuilder {
         return p;
     }
     bool use_tc() const { return kind == ACT_BF16 && d->conv_impl_bf16 == 1; }
+    // fp32 mode on the tensor cores (six bf16 partial products per MAC, fp32 TMEM accumulation); per-sample weights stay on FFMA
+    bool use_split(const ConvGeom& g) const {
+        return kind == ACT_F32 && d->fp32_tc == 1 && g.w_batch_rows == 0 && g.Cin0 > 0 && g.Cin0 % 64 == 0 && g.Cin1 % 64 == 0 &&
+               (g.Cout == 64 || g.Cout == 128 || g.Cout == 256) && 6 * (g.Cin0 + g.Cin1) / 64 <= 48;
+    }
+    // fp32 activations -> [hi | mid | lo] bf16 planes, fp32 packed weights -> 6-term bf16 rows, then the tcgen05 conv with fp32 output
+    bool add_split_conv(const std::string& name, const ConvGeom& g, const void* src0, const void* src1, const void* w, int wrows,
+                        const ConvEpilogue& e, double flops, double bytes) {
+        const size_t npix = (size_t)g.B * g.Hin * g.Win;
+        void* p0 = pooled(npix * 3 * g.Cin0 * 2);
+        void* p1 = g.Cin1 ? pooled(npix * 3 * g.Cin1 * 2) : nullptr;
+        if (failed) return false;
+        void* w3 = nullptr;
+        auto it = P->w3cache.find(w);
+        if (it != P->w3cache.end()) w3 = it->second;
+        else {
+            const int K = g.Cin0 + g.Cin1;
+            w3 = P->mem.alloc((size_t)wrows * 6 * K * 2);
+            if (!w3) { fail_oom((size_t)wrows * 12 * K); return false; }
+            if (split_pack_weights((const float*)w, w3, (size_t)wrows, K, 0)) { failed = true; return false; }   // stream 0: synchronised before the dry run
+            P->w3cache[w] = w3;
+        }
+        const int C0 = g.Cin0, C1 = g.Cin1;
+        pl->push("split_planes", 0, 0.0, 0.0, [src0, p0, npix, C0](cudaStream_t s) { return split_f32_planes((const float*)src0, p0, npix, C0, s); });
+        if (p1) pl->push("split_planes", 0, 0.0, 0.0, [src1, p1, npix, C1](cudaStream_t s) { return split_f32_planes((const float*)src1, p1, npix, C1, s); });
+        ConvGeom gs = g;
+        gs.split = 1;
+        ConvEpilogue es = e;
+        es.out_f32 = 1;
+        TcConvPlan* tp = conv_tc_plan_create(gs, p0, p1, w3, wrows, es, d->num_sms, d->halo_mode);
+        if (!tp) { failed = true; return false; }
+        pl->tc_plans.push_back(tp);
+        pl->push(name, 1, flops, bytes, [tp](cudaStream_t s) { return conv_tc_launch(tp, s); });
+        release(p0, true); release(p1, true);
+        return true;
+    }
     size_t slots_for(const ConvGeom& g) const {
+        if (use_split(g)) return d->halo_mode && conv_tc_halo_eligible(g) ? conv_tc_halo_partials_slots(g) : conv_tc_partials_slots(g);
         if (!use_tc()) return conv_ffma_partials_slots(g);
         if (d->halo_mode && conv_tc_halo_eligible(g)) return conv_tc_halo_partials_slots(g);
         return conv_tc_partials_slots(g);
@@ -626,7 +666,9 @@ struct PlanBuilder {
                              (double)wrows * cin * es;
         std::string name = std::string(g.nphase == 4 ? "convT4x4" : (g.ntaps == 9 ? (g.stride == 2 ? "conv3x3s2" : (apply ? "conv3x3gn" : "conv3x3")) : "conv1x1")) +
                            "_" + std::to_string((int)cin) + "_" + std::to_string(g.Cout) + "_h" + std::to_string(g.Hin);
-        if (use_tc()) {
+        if (use_split(g)) {
+            add_split_conv(name + "_x3", g, src0, src1, w, wrows, e, flops, bytes);
+        } else if (use_tc()) {
             TcConvPlan* tp = conv_tc_plan_create(g, src0, src1, w, wrows, e, d->num_sms, d->halo_mode);   // the plan drops the halo path where the epilogue or geometry rules it out
             if (!tp) { failed = true; return; }
             pl->tc_plans.push_back(tp);
@@ -747,6 +789,10 @@ struct PlanBuilder {
         const double flops = 2.0 * npx * g.Cout * g.ntaps * (g.Cin0 + g.Cin1);
         ActKind k = kind;
         const std::string name = std::string("bwd_") + what + "_" + std::to_string(g.Cin0) + "_" + std::to_string(g.Cout) + "_h" + std::to_string(g.Hout);
+        if (use_split(g)) {
+            add_split_conv(name + "_x3", g, src, nullptr, w, g.ntaps * g.nphase * g.Cout, e, flops, 0.0);
+            return;
+        }
         if (use_tc()) {
             // bf16 mode: the data gradients run on the same tcgen05 kernels as the forward convolutions
             TcConvPlan* tp = conv_tc_plan_create(g, src, nullptr, w, g.ntaps * g.nphase * g.Cout, e, d->num_sms, d->halo_mode);
@@ -1212,7 +1258,7 @@ int get_plan(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, cu
     std::string key = std::to_string((int)kind) + ":" + std::to_string(B) + ":" + std::to_string(T) + ":" +
                       (est_mode ? "e" : "s") + (sde ? "n" : "o") + (vjp ? "v" : "-") + (d->use_graph ? "g" : "x") +
                       std::to_string(d->conv_impl_bf16) + std::to_string(d->halo_mode) + std::to_string(d->fused_attn) + std::to_string(d->fuse_gn) +
-                      std::to_string(d->fuse_epi) + "." + std::to_string(d->fuse_epi_max_b);
+                      std::to_string(d->fuse_epi) + "." + std::to_string(d->fuse_epi_max_b) + "." + std::to_string(d->fp32_tc);
     auto it = d->plans.find(key);
     if (it != d->plans.end()) {
         it->second.last_use = ++d->use_clock;
@@ -1442,6 +1488,7 @@ Decoder* decoder_new(int n_spks, int n_feats, int dim, double beta_min, double b
     // experiment switches (profiling runs): defaults of the two GroupNorm fusion options
     if (const char* e = getenv("GTTS_FUSE_EPI")) d->fuse_epi = atoi(e);
     if (const char* e = getenv("GTTS_FUSE_GN")) d->fuse_gn = atoi(e);
+    if (const char* e = getenv("GTTS_FP32_TC")) d->fp32_tc = atoi(e);
     if (cudaEventCreateWithFlags(&d->done_ev, cudaEventDisableTiming) != cudaSuccess) {
         set_error("cudaEventCreate failed"); cudaGetLastError(); delete d; return nullptr;
     }
@@ -1490,6 +1537,7 @@ int decoder_set_option(Decoder* d, const char* key, int value) {
     else if (k == "fuse_gn") d->fuse_gn = value;
     else if (k == "fuse_epi") d->fuse_epi = value;
     else if (k == "fuse_epi_max_b") d->fuse_epi_max_b = value;
+    else if (k == "fp32_tc") d->fp32_tc = value;
     else { set_error("unknown option " + k); return 2; }
     return 0;
 }

@@ -30,6 +30,11 @@ struct ConvGeom {
     int wrow[4][16];
     int oy[4], ox[4];
     int w_batch_rows;         // 0, or Cout for per-sample weights
+    // fp32 arithmetic on the tensor cores: the sources are [hi | mid | lo] bf16 planes of fp32 activations (3*Cin channels per
+    // pixel, split_f32_planes) and the weight matrix has 6*Cin columns [wl wm wm wh wh wh] (split_pack_weights): the six partial
+    // products hl, mm, hm, lh, mh, hh accumulate, smallest first, in the fp32 TMEM accumulator (the three products below 2^-24
+    // relative are dropped, like fp32 rounding would)
+    int split;
 };
 
 struct ConvEpilogue {
@@ -37,6 +42,7 @@ struct ConvEpilogue {
     const void* residual;     // NHWC at output resolution, activation type, or null
     const float* mask;        // [B][Wout] or null (output multiplied by mask[b][w])
     void* out;                // NHWC activation type
+    int out_f32;              // tcgen05 kernels: out / residual are fp32 NHWC instead of bf16 (the fp32 mode on tensor cores)
     // GroupNorm statistics of (acc + bias) over the whole sample (null partials = off)
     float* gn_partials;
     float* gn_stats;          // [B][8][2] mean, rstd
@@ -218,6 +224,11 @@ int pack_dgrad3(ActKind wkind, const float* w_oihw, void* out, int Cout, int Cin
 int pack_t1(ActKind wkind, const float* w_oi, void* out, int Cout, int Cin, int ci_off, int Cn, float scale, cudaStream_t s);
 int pack_down_dgrad(ActKind wkind, const float* w_oihw, void* out, int C, cudaStream_t s);
 int pack_up_dgrad(ActKind wkind, const float* w_iohw, void* out, int C, cudaStream_t s);
+
+// fp32 -> three bf16 planes with x = hi + mid + lo exactly (24 = 8 + 8 + 8 mantissa bits): in [P][C] fp32 -> out [P][3C] bf16
+int split_f32_planes(const float* in, void* out, size_t npix, int C, cudaStream_t s);
+// packed fp32 weight rows [rows][K] -> bf16 [rows][6K] = [wl | wm | wm | wh | wh | wh]
+int split_pack_weights(const float* w, void* out, size_t rows, int K, cudaStream_t s);
 
 // weight packing helpers (device side, fp32 source in PyTorch layout)
 int pack_conv_weight(ActKind wkind, const float* w_oihw, void* packed, int Cout, int Cin, int kh, int kw,

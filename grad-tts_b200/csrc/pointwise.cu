@@ -638,9 +638,66 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
     dst[(size_t)c * rows + r] = src[i];
 }
 
+// ------------------------------------------------------------------------------------------------ fp32 -> 3 x bf16
+// x = hi + mid + lo exactly: hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid) (the differences are exact in fp32)
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l) {
+    h = __float2bfloat16_rn(x);
+    const float r1 = __fsub_rn(x, __bfloat162float(h));
+    m = __float2bfloat16_rn(r1);
+    const float r2 = __fsub_rn(r1, __bfloat162float(m));
+    l = __float2bfloat16_rn(r2);
+}
+
+// in [P][C] fp32 -> out [P][3C] bf16 = [hi | mid | lo]; thread = 8 channels of one pixel
+__global__ void __launch_bounds__(256)
+split_planes_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t nvec, int C8) {
+    pdl_trigger();
+    pdl_wait();
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= nvec) return;
+    const size_t pix = i / C8;
+    const int c0 = (int)(i % C8) * 8, C = C8 * 8;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(in + i * 8)), b = __ldg(reinterpret_cast<const float4*>(in + i * 8) + 1);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    __align__(16) __nv_bfloat16 h[8], m[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split3(v[j], h[j], m[j], l[j]);
+    __nv_bfloat16* o = out + pix * (size_t)(3 * C) + c0;
+    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(o + C) = *reinterpret_cast<const uint4*>(m);
+    *reinterpret_cast<uint4*>(o + 2 * C) = *reinterpret_cast<const uint4*>(l);
+}
+
+// packed fp32 weights [rows][K] -> bf16 [rows][6K] = [wl | wm | wm | wh | wh | wh] (the term order of conv_tc_plan_create: smallest first)
+__global__ void split_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, size_t n, int K) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const size_t row = i / K;
+    const int c = (int)(i % K);
+    __nv_bfloat16 h, m, l;
+    split3(w[i], h, m, l);
+    __nv_bfloat16* o = out + row * (size_t)(6 * K) + c;
+    o[0] = l; o[K] = m; o[2 * K] = m; o[3 * K] = h; o[4 * K] = h; o[5 * K] = h;
+}
+
 inline unsigned int nblk(size_t n, int bs) { return (unsigned int)((n + bs - 1) / bs); }
 
 }  // namespace
+
+int split_f32_planes(const float* in, void* out, size_t npix, int C, cudaStream_t s) {
+    GTTS_REQUIRE(C % 8 == 0, "split_f32_planes: C must be a multiple of 8");
+    const size_t nvec = npix * (size_t)(C / 8);
+    GTTS_CHECK_CUDA(launch_pdl(split_planes_kernel, dim3(nblk(nvec, 256)), dim3(256), 0, s, 1, in, (__nv_bfloat16*)out, nvec, C / 8));
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int split_pack_weights(const float* w, void* out, size_t rows, int K, cudaStream_t s) {
+    const size_t n = rows * (size_t)K;
+    split_weights_kernel<<<nblk(n, 256), 256, 0, s>>>(w, (__nv_bfloat16*)out, n, K);
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int build_level_masks(const float* mask, float* m0, float* m1, float* m2, int B, int T, cudaStream_t s) {
     level_masks_kernel<<<nblk((size_t)B * T, 256), 256, 0, s>>>(mask, m0, m1, m2, B, T);

@@ -117,10 +117,15 @@ class GradLogPEstimator2d(BaseModule):
             self._opts["max_chunk"] = int(self.max_chunk)
         return self._handle
 
+    def fp32_conv_impl(self):
+        """What precision='fp32' runs its convolutions on (library option fp32_tc)."""
+        return "ffma" if self._opts.get("fp32_tc", 1) == 0 else "tcgen05 bf16x3 split (six partial products, fp32 TMEM accumulation)"
+
     def set_option(self, key, value):
         """Library option on this module's native handle (include/gradtts_b200.h: gtts_decoder_set_option)."""
         h = self._get_handle()
         _lib.check(_lib.load().gtts_decoder_set_option(h, key.encode(), int(value)), f"set_option({key})")
+        self._opts[key] = int(value)
 
     def _release(self):
         if getattr(self, "_handle", None) is not None:

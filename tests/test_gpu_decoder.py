@@ -122,6 +122,21 @@ def test_apply_epilogue_is_bitwise_equal_to_separate_gn_pass(pkg, synth):
     assert launches[0] == launches[1] - 3 * 22, launches
 
 
+def test_fp32_mode_tensor_core_and_ffma_convs_agree(pkg, synth):
+    """precision='fp32' runs its convolutions on the tensor cores by default (bf16 x 3 split, six partial products, fp32 accumulate);
+    option fp32_tc=0 selects the CUDA-core FFMA kernels.  Both meet the fp32 tolerance; they agree to accumulation-order noise."""
+    z, mask, mu, spk, _ = synth.make_inputs(2, 72, 247, seed=33)
+    outs = []
+    for tc in (1, 0):
+        dec, sd = _module(pkg, synth, 247, 3, "fp32")
+        dec.estimator.set_option("fp32_tc", tc)
+        outs.append(dec(z.to(DEV), mask.to(DEV), mu.to(DEV), 3, False, spk.to(DEV)).cpu())
+    with torch.no_grad():
+        ref = decoder_oracle.reverse_diffusion(sd, z, mask, mu, 3, False, spk, 247)
+    assert float((outs[0] - ref).abs().max()) <= 1e-3 and float((outs[1] - ref).abs().max()) <= 1e-3
+    assert float((outs[0] - outs[1]).abs().max()) <= 5e-4, float((outs[0] - outs[1]).abs().max())
+
+
 def test_long_random_weight_run_stays_finite(pkg, synth, monkeypatch):
     """100 Euler steps with random weights drive internal activations to ~1e16 (the bench workload does this): the output must
     stay finite on both attention kernels (regression: the tcgen05 softmax once formed k*log2e - m*log2e with two roundings)."""

@@ -218,3 +218,25 @@ def test_conv_apply_epilogue(case):
     assert float(got[~live].abs().max() if (~live).any() else 0.0) == 0.0
     serr = float(((stats.cpu() - sref).abs() / (sref.abs() + 1.0)).max())
     assert serr <= 2e-3, f"{name}: GN stats err {serr}"
+
+
+@pytest.mark.parametrize("name,kw", [(n, kw) for (n, kw) in gpu_util.CONV_CASES if not kw.get("per_sample")] +
+                         [("3x3_128_128_pass", dict(kind=0, B=3, H=40, W=52, Cin0=128, Cin1=0, Cout=128)),
+                          ("3x3_256_256_many", dict(kind=0, B=8, H=20, W=216, Cin0=256, Cin1=0, Cout=256))])
+def test_conv_fp32_on_tensor_cores(name, kw):
+    """fp32 mode on the tensor cores: fp32 NHWC in, [hi|mid|lo] bf16 planes x [wh wh wh wm wm wl] weights (six partial products
+    accumulated in fp32 TMEM), fp32 out -- every conv variant against torch CPU fp32 with the FFMA kernel's tolerance."""
+    gu = _gu()
+    c = gu.conv_case(seed=_seed(name), **kw)
+    stats_ok = c["kind"] in (0, 1) and c["r"] is None and c["m"] is None
+    out, st = gu.run_conv(c, 4, 0, want_stats=stats_ok)
+    ref, raw = gu.conv_reference(c, round_bf16=False)
+    assert not torch.isnan(out).any(), "output has unwritten (NaN) entries"
+    err = float((out - ref).abs().max())
+    assert err <= 2e-4, f"{name}: max-abs err {err} (|ref|max {float(ref.abs().max())})"
+    ffma, _ = gu.run_conv(c, 0, 0)
+    # the two fp32 implementations agree to accumulation noise (the tensor core truncates its fp32 accumulation: ~K/16 * 2^-24)
+    assert float((out - ffma).abs().max()) <= 6e-5, float((out - ffma).abs().max())
+    if stats_ok:
+        sref = gu.gn_stats_reference(raw)
+        assert float(((st - sref).abs() / (sref.abs() + 1.0)).max()) <= 1e-4
