@@ -524,11 +524,12 @@ attn_merge_kernel(AttnCtxArgs a) {
     }
 }
 
-// grid (C/64 output-row tiles, C/64 input-column tiles, B), 256 threads, register-tiled fp32:
-//   phase 1: P[64 co][128 hd] = Wout[co][h*32 + e] . ctxn[h][d][e]      (4 rows x 8 columns per thread, K = 32 per head)
-//   phase 2: M[64 co][64 ci]  = g * P[64][128] . Wq[128][ci0 + 64]      (4 x 4 per thread, K = 128)
-// (The first version used 16-row tiles with one output row per thread: two shared-memory loads per FMA, LSU-bound, and
-// four times as many CTAs re-loading the same operands: 19-45 us per launch for 1-17 MFLOP per sample.)
+// grid (C/16 output-row tiles, C/64 input-column tiles, B), 256 threads, fp32:
+//   phase 1: P[16 co][128 hd] = Wout[co][h*32 + e] . ctxn[h][d][e]      (8 outputs per thread, K = 32 per head)
+//   phase 2: M[16 co][64 ci]  = g * P[16][128] . Wq[128][ci0 + 64]      (4 outputs per thread, K = 128)
+// Latency-bound by construction (1-17 MFLOP per sample): every global load of the CTA -- the contexts, its Wout rows and its Wq
+// slice, 56 KB -- is in flight before the first use, and 16-row tiles give 4x the CTAs of the first version (64-row tiles, loads
+// phase by phase: 20-27 us per launch at any size, 16 % of the batch-1 Euler step in the ncu launch list).
 template <typename WT>
 __global__ void __launch_bounds__(256)
 attn_fold_kernel(const float* __restrict__ ctxn, const float* __restrict__ wout, const float* __restrict__ wq,
@@ -536,68 +537,56 @@ attn_fold_kernel(const float* __restrict__ ctxn, const float* __restrict__ wout,
     pdl_trigger();
     pdl_wait();
     extern __shared__ __align__(16) float fold_smem[];
-    float* P = fold_smem;                       // [64][129]
-    float* buf = fold_smem + 64 * 129;          // phase 1: cs [128][33] + ws [64][129] ; phase 2: qs [128][64]
-    float* cs = buf;                            // ctxn[h*32 + d][e], pitch 33
-    float* ws = buf + 128 * 33;                 // Wout rows co0.., [64][129]
-    float* qs = buf;                            // Wq[hd][ci0..ci0+63], pitch 64
-    const int tid = threadIdx.x, b = blockIdx.z, co0 = blockIdx.x * 64, ci0 = blockIdx.y * 64;
-    for (int i = tid; i < 4096; i += 256) cs[(i >> 5) * 33 + (i & 31)] = ctxn[(size_t)b * 4096 + i];
-    for (int i = tid; i < 64 * 128; i += 256) ws[(i >> 7) * 129 + (i & 127)] = wout[(size_t)(co0 + (i >> 7)) * 128 + (i & 127)];
+    float* cs = fold_smem;                      // ctxn[h*32 + d][e], pitch 33            [128][33]
+    float* ws = cs + 128 * 33;                  // Wout rows co0.., pitch 129             [16][129]
+    float* P = ws + 16 * 129;                   //                                        [16][129]
+    float* qs = P + 16 * 129;                   // Wq[hd][ci0..ci0+63], pitch 64          [128][64]
+    const int tid = threadIdx.x, b = blockIdx.z, co0 = blockIdx.x * 16, ci0 = blockIdx.y * 64;
+    {
+        float c_[16], w_[8];
+        float4 q_[8];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) c_[k] = ctxn[(size_t)b * 4096 + tid + k * 256];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int i = tid + k * 256; w_[k] = wout[(size_t)(co0 + (i >> 7)) * 128 + (i & 127)]; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int i = tid + k * 256; q_[k] = __ldg(reinterpret_cast<const float4*>(wq + (size_t)(i >> 4) * C + ci0 + (i & 15) * 4)); }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { const int i = tid + k * 256; cs[(i >> 5) * 33 + (i & 31)] = c_[k]; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int i = tid + k * 256; ws[(i >> 7) * 129 + (i & 127)] = w_[k]; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int i = tid + k * 256; *reinterpret_cast<float4*>(&qs[(i >> 4) * 64 + (i & 15) * 4]) = q_[k]; }
+    }
     __syncthreads();
     {
-        const int r0 = (tid >> 4) * 4, c0 = (tid & 15) * 8, h = c0 >> 5;        // 8 consecutive hd columns lie in one head
-        float acc[4][8];
+        const int r = tid >> 4, c0 = (tid & 15) * 8, h = c0 >> 5;               // 8 consecutive hd columns lie in one head
+        float acc[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-#pragma unroll 4
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll 8
         for (int e = 0; e < 32; ++e) {
-            float wv[4], cv[8];
+            const float wv = ws[r * 129 + h * 32 + e];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) wv[i] = ws[(r0 + i) * 129 + h * 32 + e];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) cv[j] = cs[(c0 + j) * 33 + e];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(wv[i], cv[j], acc[i][j]);
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(wv, cs[(c0 + j) * 33 + e], acc[j]);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) P[(r0 + i) * 129 + c0 + j] = acc[i][j];
-    }
-    __syncthreads();                                                             // P complete, cs / ws dead
-    for (int i = tid; i < 128 * 16; i += 256) {                                  // 128 rows x 16 float4
-        const int r = i >> 4, c4 = i & 15;
-        *reinterpret_cast<float4*>(&qs[r * 64 + c4 * 4]) = __ldg(reinterpret_cast<const float4*>(wq + (size_t)r * C + ci0 + c4 * 4));
+        for (int j = 0; j < 8; ++j) P[r * 129 + c0 + j] = acc[j];
     }
     __syncthreads();
     {
-        const int r0 = (tid >> 4) * 4, cq = (tid & 15) * 4;
-        float acc[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        const int r = tid >> 4, cq = (tid & 15) * 4;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 8
         for (int hd = 0; hd < 128; ++hd) {
             const float4 q4 = *reinterpret_cast<const float4*>(&qs[hd * 64 + cq]);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float pv = P[(r0 + i) * 129 + hd];
-                acc[i][0] = fmaf(pv, q4.x, acc[i][0]); acc[i][1] = fmaf(pv, q4.y, acc[i][1]);
-                acc[i][2] = fmaf(pv, q4.z, acc[i][2]); acc[i][3] = fmaf(pv, q4.w, acc[i][3]);
-            }
+            const float pv = P[r * 129 + hd];
+            acc[0] = fmaf(pv, q4.x, acc[0]); acc[1] = fmaf(pv, q4.y, acc[1]);
+            acc[2] = fmaf(pv, q4.z, acc[2]); acc[3] = fmaf(pv, q4.w, acc[3]);
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            WT* o = mb + ((size_t)b * C + co0 + r0 + i) * C + ci0 + cq;
-            Act<WT>::st(o + 0, g * acc[i][0]); Act<WT>::st(o + 1, g * acc[i][1]);
-            Act<WT>::st(o + 2, g * acc[i][2]); Act<WT>::st(o + 3, g * acc[i][3]);
-        }
+        WT* o = mb + ((size_t)b * C + co0 + r) * C + ci0 + cq;
+        Act<WT>::st(o + 0, g * acc[0]); Act<WT>::st(o + 1, g * acc[1]);
+        Act<WT>::st(o + 2, g * acc[2]); Act<WT>::st(o + 3, g * acc[3]);
     }
 }
 
@@ -688,8 +677,8 @@ int attn_merge(const AttnCtxArgs& a, bool strict, cudaStream_t s) {
 int attn_fold(ActKind wkind, const float* ctxn, const float* wout, const float* wq, float g, void* mb_out, int B,
               int C, cudaStream_t s) {
     GTTS_REQUIRE(C % 64 == 0 && C <= 256, "attn_fold: C must be a multiple of 64 and <= 256");
-    dim3 grid(C / 64, C / 64, B);
-    const size_t smem = (size_t)(64 * 129 + 128 * 33 + 64 * 129) * sizeof(float);          // P + (ctx, Wout rows | Wq slice)
+    dim3 grid(C / 16, C / 64, B);
+    const size_t smem = (size_t)(128 * 33 + 2 * 16 * 129 + 128 * 64) * sizeof(float);       // ctx, Wout rows, P, Wq slice
     static bool set_f = false, set_h = false;
     if (wkind == ACT_F32) {
         if (!set_f) { GTTS_CHECK_CUDA(cudaFuncSetAttribute(attn_fold_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set_f = true; }

@@ -284,7 +284,12 @@ int gtts_test_conv_apply(int B, int H, int W, int Cin0, int Cin1, int Cout, cons
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    GTTS_REQUIRE(conv_tc_apply_eligible(g, sms), "gtts_test_conv_apply: geometry not eligible for the apply epilogue");
+    const bool async_apply = reps < 0;                   // negative reps: the asynchronous apply-warp variant (raw tile to a scratch tensor)
+    if (reps < 0) reps = -reps;
+    GTTS_REQUIRE(async_apply ? conv_tc_apply_async_eligible(g, sms) : conv_tc_apply_eligible(g, sms),
+                 "gtts_test_conv_apply: geometry not eligible for the apply epilogue");
+    void* raw_scratch = nullptr;
+    if (async_apply) GTTS_CHECK_CUDA(cudaMalloc(&raw_scratch, (size_t)B * H * W * Cout * 2));
     void* wpk = nullptr;
     float* partials = nullptr;
     unsigned int* counters = nullptr;
@@ -298,6 +303,7 @@ int gtts_test_conv_apply(int B, int H, int W, int Cin0, int Cin1, int Cout, cons
     e.bias = bias; e.residual = residual; e.mask = mask; e.out = out;
     e.gn_partials = partials; e.gn_stats = gn_stats; e.gn_counters = counters; e.gn_eps = 1e-5f;
     e.apply = 1; e.ap_gamma = gamma; e.ap_beta = beta; e.ap_tbias = tbias; e.ap_tb_bstride = tb_bstride;
+    if (async_apply) { e.apply = 2; e.ap_out = out; e.out = raw_scratch; }
     int rc = 0;
     TcConvPlan* tp = conv_tc_plan_create(g, src0, src1, wpk, 9 * Cout, e, sms, 2);
     if (!tp) rc = 1;
@@ -320,7 +326,7 @@ int gtts_test_conv_apply(int B, int H, int W, int Cin0, int Cin1, int Cout, cons
         conv_tc_plan_destroy(tp);
     }
     cudaError_t ce = cudaStreamSynchronize(s);
-    cudaFree(wpk); cudaFree(partials); cudaFree(counters);
+    cudaFree(wpk); cudaFree(partials); cudaFree(counters); cudaFree(raw_scratch);
     if (rc) return rc;
     GTTS_CHECK_CUDA(ce);
     GTTS_CHECK_CUDA(cudaGetLastError());

@@ -261,6 +261,16 @@ bool conv_tc_apply_eligible(const ConvGeom& g, int num_sms) {
     return apply_run_fits(tps, grid > 32 ? grid - 16 : grid, g.Cout);
 }
 
+bool conv_tc_apply_async_eligible(const ConvGeom& g, int num_sms) {
+    if (const char* e = getenv("GTTS_APPLY_ASYNC")) { if (atoi(e) == 0) return false; }
+    if (!conv_tc_cta2_enabled() || !conv_tc_halo_eligible(g) || num_sms < 2 || g.split) return false;
+    int th, tw;
+    halo2_tiles(g, &th, &tw);
+    if (const char* e = getenv("GTTS_APPLY_ASYNC_MAXH")) { if (g.Hg > atoi(e)) return false; }
+    if (const char* e = getenv("GTTS_APPLY_ASYNC_MINH")) { if (g.Hg < atoi(e)) return false; }
+    return (long)g.B * th * tw >= 2;
+}
+
 TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void* src1, const void* weight,
                                 int weight_rows, const ConvEpilogue& e, int num_sms, int halo_mode) {
     if (!(g.Cout == 64 || g.Cout == 128 || g.Cout == 256)) { set_error("conv_tc: Cout must be 64/128/256"); return nullptr; }
@@ -323,7 +333,7 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
     p.e = e;
     { const char* dbg = getenv("GTTS_CONV_DBG"); p.dbg = dbg ? atoi(dbg) : 0; }
     pl->N = g.Cout;
-    const int apply_extra = e.apply ? conv_tc_halo2_apply_extra_smem() : 0;
+    const int apply_extra = e.apply == 1 ? conv_tc_halo2_apply_extra_smem() : 0;
     const int budget = 227 * 1024 - kMiscBytes - 1024 - apply_extra;
     if (halo_mode) {
         // A ring: halo boxes of 18 x 16 pixels x 64 ch (36 KB); B: resident (all 9*nck tiles) if it fits, else a ring
@@ -405,10 +415,10 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
     if (e.apply) {
         // per-sample grid barrier: every CTA of the grid must be on an SM at the same time
         if (p.mc != 2) { set_error("conv_tc: the GroupNorm-apply epilogue needs the CTA-pair halo kernel (geometry not eligible)"); delete pl; return nullptr; }
-        const int cores = conv_tc_halo2_max_grid(g.Cout, e.residual != nullptr, pl->smem);
+        const int cores = conv_tc_halo2_max_grid(g.Cout, e.residual != nullptr, pl->smem, e.apply == 2);
         if (cores >= 2 && cores < pl->grid) pl->grid = cores & ~1;
         if (const char* ge = getenv("GTTS_APPLY_GRID")) { const int gg = atoi(ge) & ~1; if (gg >= 2 && gg < pl->grid) pl->grid = gg; }
-        if (!apply_run_fits(p.tiles_h * p.tiles_w, pl->grid, g.Cout)) {
+        if (e.apply == 1 && !apply_run_fits(p.tiles_h * p.tiles_w, pl->grid, g.Cout)) {
             set_error("conv_tc: GroupNorm-apply epilogue: a sample's tiles do not fit the TMEM accumulator ring at grid " + std::to_string(pl->grid));
             delete pl;
             return nullptr;

@@ -351,6 +351,182 @@ __device__ __forceinline__ void tc_epilogue_apply_loop(const TcParams& p, const 
     }
 }
 
+
+// ================================================================================================ asynchronous apply warps
+// kApply = 3 / 4: like 1 / 2 the GroupNorm-apply happens inside the conv kernel, but NOT out of TMEM.  The ordinary epilogue writes
+// the raw bf16 tile to global memory (where it stays in the 126 MB L2 for the few microseconds that matter) and feeds the
+// statistics ring; the statistics warp publishes the CTA's partial row when its run of a sample ends and bumps the sample's arrival
+// counter WITHOUT waiting; eight extra warps (kApplyWarps) follow behind: for every run of this CTA they wait until the sample's
+// counter shows that every contributing CTA has arrived (by then all raw tiles of the sample are visible: every CTA's epilogue
+// stores precede its statistics warp's __threadfence + atomicAdd), reduce the partial rows in the fixed order, and turn the CTA's
+// own tiles of that sample into the finished activation with gn_apply's formulas.  The MMA / epilogue pipeline never waits for a
+// sample to complete, so TMEM capacity does not limit anything (any T, any batch); what the separate gn_apply pass cost -- its
+// HBM time -- is spent while the tensor pipe is busy with the next tiles.  Bitwise identical to the unfused plan.
+constexpr int kApplyWarps = 8;
+
+template <int N>
+__device__ __forceinline__ void tc_stats_async_loop(const TcParams& p, const TcShared& sh, int lane) {
+    const ConvEpilogue& e = p.e;
+    const int G = (int)gridDim.x, bx = (int)blockIdx.x;
+    const int tps = p.tiles_h * p.tiles_w;
+    const int n_it = tc_num_iters(p);
+    const int g = lane & 7, which = (lane >> 3) & 1, half = g >> 2, idx = which * 4 + (g & 3);
+    unsigned int* cnt = e.gn_counters + 32;
+    for (int it = 0; it < n_it;) {
+        int b;
+        const int it_end = apply_run_end(p, it, n_it, tps, &b);
+        float acc = 0.f;
+        for (int j = it; j < it_end; ++j) {
+            const int slot = j % kStatSlots;
+            mbar_wait(&sh.sfull[slot], (uint32_t)(j / kStatSlots) & 1u);
+            if (lane < 16 && b >= 0) {
+                const float* r = sh.s_ring + (slot * 8 + half * 4) * 8 + idx;
+                acc += (r[0] + r[8]) + (r[16] + r[24]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.sempty[slot]);
+        }
+        it = it_end;
+        if (b < 0) continue;
+        if (lane < 16) e.gn_partials[((size_t)b * G + bx) * 16 + lane] = acc;
+        // gpu-scope fence, cumulative: it also covers the epilogue warps' raw-tile stores that this warp observed through the ring
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(&cnt[2 * b], 1u);
+    }
+}
+
+// the eight apply warps (tid_a = 0..255 within the group)
+template <int N, bool kTb, bool kRes>
+__device__ __forceinline__ void tc_apply_async_loop(const TcParams& p, const TcShared& sh, int tid_a) {
+    constexpr int kGsz = N / 8;
+    constexpr int C8 = N / 8;                                        // 16-byte vectors per pixel
+    constexpr int kPStep = 256 / C8;                                 // pixels per pass of the 256 apply threads
+    const ConvEpilogue& e = p.e;
+    const int lane = tid_a & 31, warp_a = tid_a >> 5;
+    const int G = (int)gridDim.x, bx = (int)blockIdx.x;
+    const int tps = p.tiles_h * p.tiles_w;
+    const int n_it = tc_num_iters(p);
+    const int nrows = tps < G ? tps : G;
+    const double inv_count = 1.0 / ((double)kGsz * (double)p.Hout * (double)p.Wout);
+    unsigned int* cnt = e.gn_counters + 32;
+    float* s_sc = reinterpret_cast<float*>(sh.misc + 4096);          // [N]   (the per-sample rows area of the plain kernel)
+    float* s_sh = s_sc + N;                                          // [N]
+    float* s_tb = s_sh + N;                                          // [N]
+    float* s_mr = s_tb + N;                                          // [16]
+    const int vec = tid_a % C8, pslot = tid_a / C8, c0 = vec * 8;
+    const __nv_bfloat16* raw = reinterpret_cast<const __nv_bfloat16*>(e.out);
+    const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(e.residual);
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.ap_out);
+    const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f);
+    TileWalk tw;
+    tw.init(p, bx, G);
+    for (int it = 0; it < n_it;) {
+        int b;
+        const int it_end = apply_run_end(p, it, n_it, tps, &b);
+        if (b >= 0) {
+            if (warp_a == 0) {
+                if (lane == 0) { while (ld_acquire_gpu_u32(&cnt[2 * b]) < (unsigned int)nrows) { __nanosleep(64); } }
+                __syncwarp();
+                const int start = tps < G ? (int)(((long long)b * tps) % G) : 0;
+                const int q = lane & 3, r0 = lane >> 2;
+                const float4* pp = reinterpret_cast<const float4*>(e.gn_partials + (size_t)b * G * 16) + q;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                for (int base = 0; base < G; base += 64) {           // CTA order 0..G-1, the order of tc_teardown's finalisation
+                    float4 v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int c = base + r0 + 8 * i;
+                        int rel = c - start; if (rel < 0) rel += G;
+                        v[i] = (c < G && rel < nrows) ? __ldcg(pp + (size_t)c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        a0 += (double)v[i].x; a1 += (double)v[i].y; a2 += (double)v[i].z; a3 += (double)v[i].w;
+                    }
+                }
+#pragma unroll
+                for (int off = 4; off < 32; off <<= 1) {
+                    a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+                    a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+                    a3 += __shfl_xor_sync(0xffffffffu, a3, off);
+                }
+                const double q0 = __shfl_sync(0xffffffffu, a0, (lane + 2) & 31), q1 = __shfl_sync(0xffffffffu, a1, (lane + 2) & 31);
+                const double q2 = __shfl_sync(0xffffffffu, a2, (lane + 2) & 31), q3 = __shfl_sync(0xffffffffu, a3, (lane + 2) & 31);
+                if (lane < 2) {
+                    const double su[4] = {a0, a1, a2, a3}, sq[4] = {q0, q1, q2, q3};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double mean = su[j] * inv_count;
+                        double var = sq[j] * inv_count - mean * mean;
+                        if (var < 0.0) var = 0.0;
+                        const float mf = (float)mean, rf = (float)rsqrt(var + (double)e.gn_eps);
+                        const int gg = lane * 4 + j;
+                        s_mr[gg] = mf; s_mr[8 + gg] = rf;
+                        if (bx == start) {
+                            e.gn_stats[((size_t)b * 8 + gg) * 2 + 0] = mf;
+                            e.gn_stats[((size_t)b * 8 + gg) * 2 + 1] = rf;
+                        }
+                    }
+                }
+                __syncwarp();
+                for (int c = lane; c < N; c += 32) {
+                    const int gg = c / kGsz;
+                    const float sc = s_mr[8 + gg] * __ldg(e.ap_gamma + c);
+                    s_sc[c] = sc;
+                    s_sh[c] = fmaf(-s_mr[gg], sc, __ldg(e.ap_beta + c));             // gn_apply's expression (pointwise.cu)
+                    s_tb[c] = e.ap_tbias ? __ldg(e.ap_tbias + (size_t)b * e.ap_tb_bstride + c) : 0.f;
+                }
+                if (lane == 0) {                                     // departure: the last reader resets the counters for the next launch
+                    if (atomicAdd(&cnt[2 * b + 1], 1u) == (unsigned int)(nrows - 1)) { cnt[2 * b] = 0u; cnt[2 * b + 1] = 0u; }
+                }
+            }
+            named_bar_sync(1, kApplyWarps * 32);                     // tables of this run are in shared memory
+            float2 sc2[4], sh2[4], tb2[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                sc2[q] = make_float2(s_sc[c0 + 2 * q], s_sc[c0 + 2 * q + 1]);
+                sh2[q] = make_float2(s_sh[c0 + 2 * q], s_sh[c0 + 2 * q + 1]);
+                tb2[q] = make_float2(s_tb[c0 + 2 * q], s_tb[c0 + 2 * q + 1]);
+            }
+            TileWalk w2 = tw;
+            for (int j = it; j < it_end; ++j, w2.advance(G)) {
+#pragma unroll 2
+                for (int row = pslot; row < 128; row += kPStep) {
+                    int hl = row / p.bw, wl = row - hl * p.bw;
+                    if (p.halo_t) { wl = row >> 3; hl = row & 7; }
+                    const int jj = w2.th * p.bh + hl, ii = w2.tw * p.bw + wl;
+                    if (hl >= p.bh || jj >= p.Hg || ii >= p.Wg) continue;
+                    const size_t pix = ((size_t)b * p.Hout + jj) * p.Wout + ii;
+                    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(raw + pix * N + c0));
+                    uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+                    if (kRes) rv = __ldg(reinterpret_cast<const uint4*>(res + pix * N + c0));
+                    const float m = e.mask[(size_t)b * p.Wout + ii];
+                    const float2 m2 = make_float2(m, m);
+                    const uint32_t wv[4] = {v.x, v.y, v.z, v.w}, rw[4] = {rv.x, rv.y, rv.z, rv.w};
+                    uint32_t ow[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 x = make_float2(__uint_as_float(wv[q] << 16), __uint_as_float(wv[q] & 0xffff0000u));
+                        const float2 y = ffma2(x, sc2[q], sh2[q]);
+                        float2 o = mish2_fast(y, fmul2(y, l2e));
+                        if (kTb) o = fadd2(o, tb2[q]);
+                        if (kRes) o = fadd2(o, make_float2(__uint_as_float(rw[q] << 16), __uint_as_float(rw[q] & 0xffff0000u)));
+                        o = fmul2(o, m2);
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(o.x, o.y);
+                        ow[q] = *reinterpret_cast<uint32_t*>(&h2);
+                    }
+                    *reinterpret_cast<uint4*>(out + pix * N + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                }
+            }
+            named_bar_sync(1, kApplyWarps * 32);                     // everyone is done with the tables before the next run overwrites them
+        }
+        for (int j = it; j < it_end; ++j) tw.advance(G);
+        it = it_end;
+    }
+}
+
 constexpr int kFuseWarps = 4;                       // transform warps of the fused-input variant (warps 20..23, one per SMSP)
 
 // kFuse: the A tiles are the RAW output of the previous conv; four extra warps apply (Mish(GroupNorm(raw)) + tbias) * mask
@@ -363,9 +539,10 @@ constexpr int kFuseWarps = 4;                       // transform warps of the fu
 // (phase, tap) operands are shifted views of ONE halo box of the input tile, so the input crosses L2->SMEM once instead of 16
 // times (the per-tap kernel is fill-bound there: 372 TFLOP/s).  Every phase has its own accumulator and epilogue iteration
 // (TcParams::ph_inner = 4, phases innermost); the epilogue multiplies by the mask (kMask).
-// kApply: 0 = off, 1 = GroupNorm-apply epilogue with time bias (block1 of a ResnetBlock), 2 = with residual (block2)
+// kApply: 0 = off; 1 / 2 = GroupNorm-apply epilogue out of TMEM with time bias (block1 of a ResnetBlock) / with residual (block2);
+// 3 / 4 = the same two flavours done by asynchronous apply warps from the raw tile in global memory
 template <int N, bool kStats, bool kFuse, bool kMask = false, bool kConvT = false, int kApply = 0, bool kOutF32 = false>
-__global__ void __launch_bounds__(kThreads + (kFuse ? kFuseWarps * 32 : 0), 1)
+__global__ void __launch_bounds__(kThreads + (kFuse ? kFuseWarps * 32 : 0) + (kApply >= 3 ? kApplyWarps * 32 : 0), 1)
 conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                      const __grid_constant__ CUtensorMap mapWh, const TcParams p) {
     constexpr int kBHalf = N * 64;                                  // bytes of this CTA's half of one weight tile
@@ -397,7 +574,7 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
         if (kFuse) for (int s = 0; s < nstage; ++s) mbar_init(&rawfull[s], 1);
         for (int i = 0; i < kBufs; ++i) { mbar_init(&sh.tfull[i], 1); mbar_init(&sh.tempty[i], 16); }   // 8 warps x 2 CTAs
         for (int i = 0; i < kStatSlots; ++i) { mbar_init(&sh.sfull[i], 8); mbar_init(&sh.sempty[i], 1); }
-        if (kApply) {
+        if (kApply == 1 || kApply == 2) {
             const ApplyShared ap = apply_shared<N>(sh.misc);
             for (int i = 0; i < 2; ++i) { mbar_init(&ap.aff_full[i], 1); mbar_init(&ap.aff_empty[i], 16); }
         }
@@ -601,11 +778,14 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
             }
         }
     } else if (warp == 3) {
-        if (kApply) tc_stats_apply_loop<N>(p, sh, lane);
+        if (kApply >= 3) tc_stats_async_loop<N>(p, sh, lane);
+        else if (kApply) tc_stats_apply_loop<N>(p, sh, lane);
         else tc_stats_loop<kStats>(p, sh, lane);
     } else if (warp >= 4 && warp < kThreads / 32) {
-        if (kApply) tc_epilogue_apply_loop<N, kApply == 1, kApply == 2>(p, sh, tmem_base, warp, lane);
+        if (kApply == 1 || kApply == 2) tc_epilogue_apply_loop<N, kApply == 1, kApply == 2>(p, sh, tmem_base, warp, lane);
         else tc_epilogue_loop<N, kStats, false, kMask, kOutF32>(p, sh, tmem_base, warp, lane);
+    } else if (kApply >= 3 && warp >= kThreads / 32) {
+        tc_apply_async_loop<N, kApply == 3, kApply == 4>(p, sh, tid - kThreads);
     } else if (kFuse && warp >= kThreads / 32) {
         // ================================================================ input transform (both CTAs)
         // thread -> 16-byte chunk j (8 channels) of rows r0, r0+16, ...; the 128-byte swizzle puts chunk j of row r at
@@ -687,8 +867,8 @@ int launch_halo2(const TcConvPlan* pl, cudaStream_t stream) {
         GTTS_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    GTTS_CHECK_CUDA(launch_pdl(k, dim3(pl->grid), dim3(kThreads + (kFuse ? kFuseWarps * 32 : 0)), pl->smem, stream, 2, pl->mapA0,
-                               pl->mapA1, pl->mapWh, pl->p));
+    GTTS_CHECK_CUDA(launch_pdl(k, dim3(pl->grid), dim3(kThreads + (kFuse ? kFuseWarps * 32 : 0) + (kApply >= 3 ? kApplyWarps * 32 : 0)), pl->smem,
+                               stream, 2, pl->mapA0, pl->mapA1, pl->mapWh, pl->p));
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -704,7 +884,7 @@ int max_grid_of(size_t smem) {
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) { cudaGetLastError(); return 0; }
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem;
+    cfg.gridDim = dim3(2); cfg.blockDim = dim3(kThreads + (kApply >= 3 ? kApplyWarps * 32 : 0)); cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -715,7 +895,11 @@ int max_grid_of(size_t smem) {
 }
 }  // namespace
 
-int conv_tc_halo2_max_grid(int N, bool residual, size_t smem) {
+int conv_tc_halo2_max_grid(int N, bool residual, size_t smem, bool async_apply) {
+    if (async_apply) {
+        if (residual) return N == 64 ? max_grid_of<64, 4>(smem) : (N == 128 ? max_grid_of<128, 4>(smem) : max_grid_of<256, 4>(smem));
+        return N == 64 ? max_grid_of<64, 3>(smem) : (N == 128 ? max_grid_of<128, 3>(smem) : max_grid_of<256, 3>(smem));
+    }
     if (residual) return N == 64 ? max_grid_of<64, 2>(smem) : (N == 128 ? max_grid_of<128, 2>(smem) : max_grid_of<256, 2>(smem));
     return N == 64 ? max_grid_of<64, 1>(smem) : (N == 128 ? max_grid_of<128, 1>(smem) : max_grid_of<256, 1>(smem));
 }
@@ -735,6 +919,20 @@ int conv_tc_halo2_launch(const TcConvPlan* pl, cudaStream_t stream) {
         GTTS_REQUIRE(e.gn_partials && e.gn_stats && e.gn_counters && e.mask && e.ap_gamma && e.ap_beta && !e.in_stats,
                      "conv_tc_halo2: the apply epilogue needs statistics buffers, affine parameters and the mask");
         GTTS_REQUIRE((e.residual != nullptr) != (e.ap_tbias != nullptr), "conv_tc_halo2: the apply epilogue takes a time bias or a residual");
+        if (e.apply == 2) {                                         // asynchronous apply warps: raw tile to e.out, finished activation to e.ap_out
+            GTTS_REQUIRE(e.ap_out != nullptr, "conv_tc_halo2: the asynchronous apply variant needs ap_out");
+            if (e.residual) {
+                if (pl->N == 64) return launch_halo2<64, true, false, false, false, 4>(pl, stream);
+                if (pl->N == 128) return launch_halo2<128, true, false, false, false, 4>(pl, stream);
+                if (pl->N == 256) return launch_halo2<256, true, false, false, false, 4>(pl, stream);
+            } else {
+                if (pl->N == 64) return launch_halo2<64, true, false, false, false, 3>(pl, stream);
+                if (pl->N == 128) return launch_halo2<128, true, false, false, false, 3>(pl, stream);
+                if (pl->N == 256) return launch_halo2<256, true, false, false, false, 3>(pl, stream);
+            }
+            set_error("conv_tc_halo2: unsupported Cout");
+            return 2;
+        }
         if (e.residual) {
             if (pl->N == 64) return launch_halo2<64, true, false, false, false, 2>(pl, stream);
             if (pl->N == 128) return launch_halo2<128, true, false, false, false, 2>(pl, stream);

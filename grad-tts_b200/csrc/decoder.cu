@@ -143,6 +143,11 @@ struct Decoder {
                               // wins where launches are latency-bound (B = 1, T = 400: 21 us vs 17 + 8.6 us per Block) and loses on big
                               // batches (chunk 16 x 1720: 128->128 @h40 249 vs 109 + 57 us) because every sample costs one grid barrier.
     int fuse_epi_max_b = 2;
+    int fuse_async = 0;       // 1: GroupNorm+Mish(+time bias / residual) by asynchronous apply warps inside the Block conv (the raw tile goes
+                              // through L2, the MMA pipeline never waits).  Correct and bitwise equal to the separate pass, but OFF: with the
+                              // registers the conv leaves (72 per thread at 896 threads) eight apply warps keep only ~8 KB of loads in flight
+                              // per SM and the kernel becomes bound by them (chunk 16 x 1720: 128->128 @h40 380 us vs 109 + 57 us;
+                              // profiles/r02_gn_fusion.md).  0 = separate gn_apply pass
     int fp32_tc = 1;          // fp32 mode: 1 = convolutions on the tensor cores as six bf16 partial products of [hi|mid|lo] splits (fp32
                               // accuracy, ~1/6 of the bf16 MMA rate), 0 = CUDA-core FFMA convolutions
     int halo_mode = 2;        // 3x3 convs: 0 = per-tap boxes, 1/2 = halo box (18x16 / 18x10) + shifted descriptor views
@@ -632,12 +637,17 @@ struct PlanBuilder {
         return g.Cin1 == 0 && tiles >= 2 && d->num_sms >= 2;
     }
 
-    struct Apply { const float* gamma; const float* beta; const float* tbias; int tb_bstride; };
+    struct Apply { const float* gamma; const float* beta; const float* tbias; int tb_bstride; void* async_out; };
 
     // true when a Block conv of this geometry can finish GroupNorm+Mish in its own epilogue (ConvEpilogue::apply)
     bool can_apply(const ConvGeom& g) const {
         if (vjp || !use_tc() || d->halo_mode != 2 || d->fuse_epi == 0 || (d->fuse_epi == 1 && B > d->fuse_epi_max_b)) return false;
         return conv_tc_apply_eligible(g, d->num_sms);
+    }
+    // ... or by the asynchronous apply warps (any batch; used where the TMEM-resident variant is not)
+    bool can_apply_async(const ConvGeom& g) const {
+        if (vjp || !use_tc() || d->halo_mode != 2 || !d->fuse_async) return false;
+        return conv_tc_apply_async_eligible(g, d->num_sms);
     }
 
     void add_conv(const ConvGeom& g, const void* src0, const void* src1, const void* w, int wrows, const float* bias,
@@ -647,7 +657,8 @@ struct PlanBuilder {
         memset(&e, 0, sizeof(e));
         e.bias = bias; e.residual = residual; e.mask = mask; e.out = out;
         if (apply) {
-            e.apply = 1; e.ap_gamma = apply->gamma; e.ap_beta = apply->beta; e.ap_tbias = apply->tbias; e.ap_tb_bstride = apply->tb_bstride;
+            e.apply = apply->async_out ? 2 : 1; e.ap_out = apply->async_out;
+            e.ap_gamma = apply->gamma; e.ap_beta = apply->beta; e.ap_tbias = apply->tbias; e.ap_tb_bstride = apply->tb_bstride;
         }
         if (fuse) {
             e.in_stats = fuse->stats; e.in_gamma = fuse->gamma; e.in_beta = fuse->beta; e.in_tbias = fuse->tbias;
@@ -664,7 +675,7 @@ struct PlanBuilder {
         // algorithmic bytes: read every input once, write every output once, weights once
         const double bytes = ((double)g.B * g.Hin * g.Win * cin + (double)g.B * g.Hout * g.Wout * g.Cout * (residual ? 2 : 1)) * es +
                              (double)wrows * cin * es;
-        std::string name = std::string(g.nphase == 4 ? "convT4x4" : (g.ntaps == 9 ? (g.stride == 2 ? "conv3x3s2" : (apply ? "conv3x3gn" : "conv3x3")) : "conv1x1")) +
+        std::string name = std::string(g.nphase == 4 ? "convT4x4" : (g.ntaps == 9 ? (g.stride == 2 ? "conv3x3s2" : (apply ? (apply->async_out ? "conv3x3ga" : "conv3x3gn") : "conv3x3")) : "conv1x1")) +
                            "_" + std::to_string((int)cin) + "_" + std::to_string(g.Cout) + "_h" + std::to_string(g.Hin);
         if (use_split(g)) {
             add_split_conv(name + "_x3", g, src0, src1, w, wrows, e, flops, bytes);
@@ -708,7 +719,9 @@ struct PlanBuilder {
         const ConvGeom g2 = geom_3x3(B, H[lvl], W[lvl], Co, 0, Co, 1);
         const bool ap1 = r != 0 && can_apply(g1);        // block1 writes Mish(GN(conv)) + time bias itself (r == 0: the first conv is not a tcgen05 kernel)
         const bool ap2 = r != 0 && can_apply(g2);        // block2 writes Mish(GN(conv)) + residual itself (r == 0: residual computed inline by gn_apply)
-        const bool fuse2 = !ap1 && !ap2 && can_fuse_input(g2);   // older variant: block2's conv applies block1's GroupNorm+Mish on its operand tiles
+        const bool as1 = r != 0 && !ap1 && can_apply_async(g1);   // the same two fusions done by asynchronous apply warps (raw tile via L2)
+        const bool as2 = r != 0 && !ap2 && can_apply_async(g2);
+        const bool fuse2 = !ap1 && !ap2 && !as1 && !as2 && can_fuse_input(g2);   // older variant: block2's conv applies block1's GroupNorm+Mish on its operand tiles
         void* raw1 = ap1 ? nullptr : act(lvl, Co);
         void* a1 = fuse2 ? nullptr : act(lvl, Co);
         void* raw2 = ap2 ? nullptr : act(lvl, Co);
@@ -727,8 +740,11 @@ struct PlanBuilder {
             pl->push("first_conv", 0, 2.0 * px * 64 * 9 * d->cin_first, px * (8 + 64 * esize(kind)),
                      [k, f](cudaStream_t s) { return first_conv(k, f, s); });
         } else if (ap1) {
-            Apply ap{R.b1.gamma, R.b1.beta, tb, tb_bstride};
+            Apply ap{R.b1.gamma, R.b1.beta, tb, tb_bstride, nullptr};
             add_conv(g1, x0, x1, R.b1.w, 9 * Co, R.b1.bias, nullptr, lmask[lvl], a1, st1, nullptr, &ap);
+        } else if (as1) {
+            Apply ap{R.b1.gamma, R.b1.beta, tb, tb_bstride, a1};
+            add_conv(g1, x0, x1, R.b1.w, 9 * Co, R.b1.bias, nullptr, lmask[lvl], raw1, st1, nullptr, &ap);
         } else {
             add_conv(g1, x0, x1, R.b1.w, 9 * Co, R.b1.bias, nullptr, nullptr, raw1, st1);
         }
@@ -750,15 +766,18 @@ struct PlanBuilder {
             InFuse fz{st1, R.b1.gamma, R.b1.beta, tb, tb_bstride, lmask[lvl]};
             add_conv(g2, raw1, nullptr, R.b2.w, 9 * Co, R.b2.bias, nullptr, nullptr, raw2, st2, &fz);
         } else {
-            if (!ap1) add_gn_apply(lvl, Co, raw1, st1, R.b1, tb, nullptr, false, a1);
+            if (!ap1 && !as1) add_gn_apply(lvl, Co, raw1, st1, R.b1, tb, nullptr, false, a1);
             if (ap2) {
-                Apply ap{R.b2.gamma, R.b2.beta, nullptr, 0};
+                Apply ap{R.b2.gamma, R.b2.beta, nullptr, 0, nullptr};
                 add_conv(g2, a1, nullptr, R.b2.w, 9 * Co, R.b2.bias, resid, lmask[lvl], out, st2, nullptr, &ap);
+            } else if (as2) {
+                Apply ap{R.b2.gamma, R.b2.beta, nullptr, 0, out};
+                add_conv(g2, a1, nullptr, R.b2.w, 9 * Co, R.b2.bias, resid, lmask[lvl], raw2, st2, nullptr, &ap);
             } else {
                 add_conv(g2, a1, nullptr, R.b2.w, 9 * Co, R.b2.bias, nullptr, nullptr, raw2, st2);
             }
         }
-        if (!ap2) add_gn_apply(lvl, Co, raw2, st2, R.b2, nullptr, resid, first_res, out);
+        if (!ap2 && !as2) add_gn_apply(lvl, Co, raw2, st2, R.b2, nullptr, resid, first_res, out);
         release(raw1); release(a1); release(raw2);
         if (resid != x0) release(resid);
         if (vjp) {
@@ -1258,7 +1277,7 @@ int get_plan(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, cu
     std::string key = std::to_string((int)kind) + ":" + std::to_string(B) + ":" + std::to_string(T) + ":" +
                       (est_mode ? "e" : "s") + (sde ? "n" : "o") + (vjp ? "v" : "-") + (d->use_graph ? "g" : "x") +
                       std::to_string(d->conv_impl_bf16) + std::to_string(d->halo_mode) + std::to_string(d->fused_attn) + std::to_string(d->fuse_gn) +
-                      std::to_string(d->fuse_epi) + "." + std::to_string(d->fuse_epi_max_b) + "." + std::to_string(d->fp32_tc);
+                      std::to_string(d->fuse_epi) + "." + std::to_string(d->fuse_epi_max_b) + "." + std::to_string(d->fp32_tc) + std::to_string(d->fuse_async);
     auto it = d->plans.find(key);
     if (it != d->plans.end()) {
         it->second.last_use = ++d->use_clock;
@@ -1489,6 +1508,7 @@ Decoder* decoder_new(int n_spks, int n_feats, int dim, double beta_min, double b
     if (const char* e = getenv("GTTS_FUSE_EPI")) d->fuse_epi = atoi(e);
     if (const char* e = getenv("GTTS_FUSE_GN")) d->fuse_gn = atoi(e);
     if (const char* e = getenv("GTTS_FP32_TC")) d->fp32_tc = atoi(e);
+    if (const char* e = getenv("GTTS_FUSE_ASYNC")) d->fuse_async = atoi(e);
     if (cudaEventCreateWithFlags(&d->done_ev, cudaEventDisableTiming) != cudaSuccess) {
         set_error("cudaEventCreate failed"); cudaGetLastError(); delete d; return nullptr;
     }
@@ -1538,6 +1558,7 @@ int decoder_set_option(Decoder* d, const char* key, int value) {
     else if (k == "fuse_epi") d->fuse_epi = value;
     else if (k == "fuse_epi_max_b") d->fuse_epi_max_b = value;
     else if (k == "fp32_tc") d->fp32_tc = value;
+    else if (k == "fuse_async") d->fuse_async = value;
     else { set_error("unknown option " + k); return 2; }
     return 0;
 }

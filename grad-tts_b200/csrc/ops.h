@@ -62,7 +62,10 @@ struct ConvEpilogue {
     //     out = (Mish(GroupNorm(acc + bias)) [+ ap_tbias] [+ residual]) * mask
     // so the raw conv output never goes to HBM and the separate gn_apply pass disappears (reference: Block.forward and the two
     // adds of ResnetBlock.forward, model/diffusion.py:52-58, 75-78).  Needs gn_partials / gn_stats / gn_counters and mask.
-    int apply;
+    int apply;                // 1: out of TMEM (above); 2: asynchronous apply warps -- the raw bf16 tile goes to `out` as in a plain conv,
+                              // eight extra warps write the finished activation to `ap_out` once the sample's statistics are complete
+                              // (no TMEM limit, the MMA pipeline never waits; conv_tc_halo2.cu kApply 3/4)
+    void* ap_out;
     const float* ap_gamma;    // [Cout]
     const float* ap_beta;     // [Cout]
     const float* ap_tbias;    // [B or 1][Cout] added after Mish (stride ap_tb_bstride floats per sample; null = off)
@@ -90,6 +93,7 @@ bool conv_tc_convT_halo_eligible(const ConvGeom& g);
 // true when a 3x3 stride-1 conv of this geometry can run with the GroupNorm-apply epilogue (ConvEpilogue::apply): CTA-pair halo
 // kernel, and no CTA owns more tiles of one sample than there are TMEM accumulator buffers
 bool conv_tc_apply_eligible(const ConvGeom& g, int num_sms);
+bool conv_tc_apply_async_eligible(const ConvGeom& g, int num_sms);   // the asynchronous variant: any run length
 size_t conv_tc_counter_words(int B);   // unsigned ints in ConvEpilogue::gn_counters for a batch of B samples
 int microbench_issue(int N, int n_mma, int n_commit, int iters, int wait_each, int grid, unsigned long long* out_dev,
                      cudaStream_t stream);                                  // tcgen05 issue-path micro-benchmark

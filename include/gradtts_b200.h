@@ -96,6 +96,8 @@ int gtts_decoder_set_param(gtts_decoder* d, const char* name, const float* data,
  * "fused_attn" (1: fused k-projection + context kernel for C <= 128, 0: 1x1 kv conv + context kernel),
  * "fuse_epi" (Block convs finish GroupNorm+Mish(+time bias / residual) in their own epilogue -- no raw tensor, no gn_apply pass:
  *  0 never, 1 (default) for plans of at most "fuse_epi_max_b" (default 2) samples, where it wins; 2 always),
+ * "fuse_async" (1, default: in larger plans the same fusion is done by asynchronous apply warps inside the conv, raw tile via L2; 0: gn_apply pass),
+ * "fp32_tc" (1, default: fp32 mode runs its convolutions on the tensor cores as six bf16 partial products; 0: CUDA-core FFMA),
  * "fuse_gn" (1: block2 convs apply block1's GroupNorm+Mish on their operand tiles; only used with fuse_epi = 0) */
 int gtts_decoder_set_option(gtts_decoder* d, const char* key, int value);
 
@@ -141,7 +143,8 @@ int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, i
 /* Test hook: 3x3 stride-1 bf16 conv with the GroupNorm-apply epilogue (the Block of model/diffusion.py:49-58 plus one of the two adds
  * of ResnetBlock.forward, :75-78, in ONE kernel): out = (Mish(GroupNorm8(conv(src) + bias)) [+ tbias[b]] [+ residual]) * mask[b][w].
  * Exactly one of tbias ([B or 1][Cout], stride tb_bstride) / residual (NHWC bf16) is given.  gn_stats: [B][8][2] mean, rstd out.
- * reps > 1 re-launches and prints the time per launch to stderr. */
+ * |reps| > 1 re-launches and prints the time per launch to stderr; reps < 0 selects the asynchronous apply-warp variant (the raw tile
+ * goes to a scratch tensor, eight extra warps finish the activation behind the per-sample counter) instead of the TMEM-resident one. */
 int gtts_test_conv_apply(int B, int H, int W, int Cin0, int Cin1, int Cout, const void* src0, const void* src1, const float* weight_pt,
                          const float* bias, const float* gamma, const float* beta, const float* tbias, int tb_bstride,
                          const void* residual, const float* mask, void* out, float* gn_stats, int reps, void* stream);

@@ -99,7 +99,8 @@ def test_fused_gn_input_is_bitwise_equal_to_separate_pass(pkg, synth):
         dec, _ = _module(pkg, synth, 247, 3, "bf16")
         z, mask, mu, spk, _ = synth.make_inputs(3, 88, 247, seed=21)
         h = dec.estimator._get_handle()
-        dec.estimator.set_option("fuse_epi", 0)                # the operand-side variant only exists without the epilogue fusion
+        dec.estimator.set_option("fuse_epi", 0)                # the operand-side variant only exists without the epilogue fusions
+        dec.estimator.set_option("fuse_async", 0)
         pkg._lib.check(pkg._lib.load().gtts_decoder_set_option(h, b"fuse_gn", fuse), "set_option")
         outs.append(dec(z.to(DEV), mask.to(DEV), mu.to(DEV), 3, False, spk.to(DEV)))
     assert torch.isfinite(outs[0]).all()
@@ -112,14 +113,15 @@ def test_apply_epilogue_is_bitwise_equal_to_separate_gn_pass(pkg, synth):
     rounds conv+bias to bf16 like the stored raw tensor and uses gn_apply's formulas -- with 22 fewer launches per Euler step."""
     outs, launches = [], []
     z, mask, mu, spk, _ = synth.make_inputs(3, 88, 247, seed=21)
-    for fuse in (2, 0):
+    for fuse_epi, fuse_async in ((2, 0), (0, 1), (0, 0)):           # TMEM-resident apply / asynchronous apply warps / separate pass
         dec, sd = _module(pkg, synth, 247, 3, "bf16")
-        dec.estimator.set_option("fuse_epi", fuse)
+        dec.estimator.set_option("fuse_epi", fuse_epi)
+        dec.estimator.set_option("fuse_async", fuse_async)
         outs.append(dec(z.to(DEV), mask.to(DEV), mu.to(DEV), 3, False, spk.to(DEV)).cpu())
         launches.append(dec.estimator.launches_last_call())
     assert torch.isfinite(outs[0]).all()
-    assert torch.equal(outs[0], outs[1])
-    assert launches[0] == launches[1] - 3 * 22, launches
+    assert torch.equal(outs[0], outs[2]) and torch.equal(outs[1], outs[2])
+    assert launches[0] == launches[2] - 3 * 22 and launches[1] == launches[2] - 3 * 22, launches
 
 
 def test_fp32_mode_tensor_core_and_ffma_convs_agree(pkg, synth):
