@@ -333,7 +333,7 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
     p.e = e;
     { const char* dbg = getenv("GTTS_CONV_DBG"); p.dbg = dbg ? atoi(dbg) : 0; }
     pl->N = g.Cout;
-    const int apply_extra = e.apply == 1 ? conv_tc_halo2_apply_extra_smem() : 0;
+    const int apply_extra = e.apply ? conv_tc_halo2_apply_extra_smem(e.apply) : 0;
     const int budget = 227 * 1024 - kMiscBytes - 1024 - apply_extra;
     if (halo_mode) {
         // A ring: halo boxes of 18 x 16 pixels x 64 ch (36 KB); B: resident (all 9*nck tiles) if it fits, else a ring

@@ -526,7 +526,7 @@ struct TcConvPlan {
 int conv_tc_halo_launch(const TcConvPlan* pl, cudaStream_t stream);      // conv_tc_halo.cu
 int conv_tc_halo2_launch(const TcConvPlan* pl, cudaStream_t stream);     // conv_tc_halo2.cu
 int conv_tc_halo2_max_grid(int N, bool residual, size_t smem, bool async_apply);   // co-resident CTAs of the GroupNorm-apply variants
-int conv_tc_halo2_apply_extra_smem();
+int conv_tc_halo2_apply_extra_smem(int apply);
 
 namespace tc {
 // ------------------------------------------------------------------------------------------------ host helpers

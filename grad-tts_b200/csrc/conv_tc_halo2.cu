@@ -396,131 +396,198 @@ __device__ __forceinline__ void tc_stats_async_loop(const TcParams& p, const TcS
     }
 }
 
-// the eight apply warps (tid_a = 0..255 within the group)
-template <int N, bool kTb, bool kRes>
-__device__ __forceinline__ void tc_apply_async_loop(const TcParams& p, const TcShared& sh, int tid_a) {
+// The eight apply warps.  Warp 0 is the FINALISER: for every run of this CTA it waits for the sample's arrival counter, reduces the
+// partial rows and builds the per-channel tables (scale, shift, time bias) in one of two table slots -- it works ahead of the
+// seven STREAMING warps, which turn the CTA's tiles of that sample into finished activations with kInFlight rows of loads in
+// flight per thread (the first version did both jobs with all eight warps in lock-step, two loads in flight: the kernel was bound
+// by them, 380 us against 109 us of convolution at 128->128 @h40).
+constexpr int kStreamWarps = kApplyWarps - 1;
+constexpr int kStreamThreads = kStreamWarps * 32;
+
+struct AsyncShared {
+    float* tab;             // [2 slots][3][N]: scale, shift, time bias
+    float* s_mr;            // [16]
+    uint64_t* tab_full;     // [2] finaliser -> streaming warps
+    uint64_t* tab_empty;    // [2] streaming warps (kStreamWarps arrivals) -> finaliser
+};
+template <int N>
+__device__ __forceinline__ AsyncShared async_shared(uint8_t* misc) {
+    AsyncShared a;
+    a.tab = reinterpret_cast<float*>(misc + kMiscBytes);             // 2 * 3 * N * 4 <= 6144 bytes
+    a.s_mr = reinterpret_cast<float*>(misc + 4096);
+    a.tab_full = reinterpret_cast<uint64_t*>(misc + 4096 + 64);
+    a.tab_empty = a.tab_full + 2;
+    return a;
+}
+constexpr int kAsyncExtra = 6144;
+
+template <int N>
+__device__ __forceinline__ void tc_apply_finaliser(const TcParams& p, const TcShared& sh, int lane) {
     constexpr int kGsz = N / 8;
-    constexpr int C8 = N / 8;                                        // 16-byte vectors per pixel
-    constexpr int kPStep = 256 / C8;                                 // pixels per pass of the 256 apply threads
     const ConvEpilogue& e = p.e;
-    const int lane = tid_a & 31, warp_a = tid_a >> 5;
+    const AsyncShared as = async_shared<N>(sh.misc);
     const int G = (int)gridDim.x, bx = (int)blockIdx.x;
     const int tps = p.tiles_h * p.tiles_w;
     const int n_it = tc_num_iters(p);
     const int nrows = tps < G ? tps : G;
     const double inv_count = 1.0 / ((double)kGsz * (double)p.Hout * (double)p.Wout);
     unsigned int* cnt = e.gn_counters + 32;
-    float* s_sc = reinterpret_cast<float*>(sh.misc + 4096);          // [N]   (the per-sample rows area of the plain kernel)
-    float* s_sh = s_sc + N;                                          // [N]
-    float* s_tb = s_sh + N;                                          // [N]
-    float* s_mr = s_tb + N;                                          // [16]
-    const int vec = tid_a % C8, pslot = tid_a / C8, c0 = vec * 8;
+    int run = 0;
+    for (int it = 0; it < n_it;) {
+        int b;
+        const int it_end = apply_run_end(p, it, n_it, tps, &b);
+        it = it_end;
+        if (b < 0) continue;
+        if (lane == 0) { while (ld_acquire_gpu_u32(&cnt[2 * b]) < (unsigned int)nrows) { __nanosleep(32); } }
+        __syncwarp();
+        const int start = tps < G ? (int)(((long long)b * tps) % G) : 0;
+        const int q = lane & 3, r0 = lane >> 2;
+        const float4* pp = reinterpret_cast<const float4*>(e.gn_partials + (size_t)b * G * 16) + q;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        for (int base = 0; base < G; base += 64) {                   // CTA order 0..G-1, the order of tc_teardown's finalisation
+            float4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = base + r0 + 8 * i;
+                int rel = c - start; if (rel < 0) rel += G;
+                v[i] = (c < G && rel < nrows) ? __ldcg(pp + (size_t)c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                a0 += (double)v[i].x; a1 += (double)v[i].y; a2 += (double)v[i].z; a3 += (double)v[i].w;
+            }
+        }
+#pragma unroll
+        for (int off = 4; off < 32; off <<= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+            a3 += __shfl_xor_sync(0xffffffffu, a3, off);
+        }
+        const double q0 = __shfl_sync(0xffffffffu, a0, (lane + 2) & 31), q1 = __shfl_sync(0xffffffffu, a1, (lane + 2) & 31);
+        const double q2 = __shfl_sync(0xffffffffu, a2, (lane + 2) & 31), q3 = __shfl_sync(0xffffffffu, a3, (lane + 2) & 31);
+        if (lane < 2) {
+            const double su[4] = {a0, a1, a2, a3}, sq[4] = {q0, q1, q2, q3};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double mean = su[j] * inv_count;
+                double var = sq[j] * inv_count - mean * mean;
+                if (var < 0.0) var = 0.0;
+                const float mf = (float)mean, rf = (float)rsqrt(var + (double)e.gn_eps);
+                const int gg = lane * 4 + j;
+                as.s_mr[gg] = mf; as.s_mr[8 + gg] = rf;
+                if (bx == start) {
+                    e.gn_stats[((size_t)b * 8 + gg) * 2 + 0] = mf;
+                    e.gn_stats[((size_t)b * 8 + gg) * 2 + 1] = rf;
+                }
+            }
+        }
+        __syncwarp();
+        const int sl = run & 1;
+        mbar_wait(&as.tab_empty[sl], ((uint32_t)(run >> 1) & 1u) ^ 1u);          // the streaming warps are done with run - 2
+        float* t_sc = as.tab + (size_t)sl * 3 * N;
+        for (int c = lane; c < N; c += 32) {
+            const int gg = c / kGsz;
+            const float sc = as.s_mr[8 + gg] * __ldg(e.ap_gamma + c);
+            t_sc[c] = sc;
+            t_sc[N + c] = fmaf(-as.s_mr[gg], sc, __ldg(e.ap_beta + c));          // gn_apply's expression (pointwise.cu)
+            t_sc[2 * N + c] = e.ap_tbias ? __ldg(e.ap_tbias + (size_t)b * e.ap_tb_bstride + c) : 0.f;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&as.tab_full[sl]);
+            // departure: the last reader resets the counters for the next launch
+            if (atomicAdd(&cnt[2 * b + 1], 1u) == (unsigned int)(nrows - 1)) { cnt[2 * b] = 0u; cnt[2 * b + 1] = 0u; }
+        }
+        ++run;
+    }
+}
+
+// (row, 16-byte vector) item `item` of tile w: element offset of its 8 channels, first channel, frame index; false outside the image
+__device__ __forceinline__ bool stream_item(const TcParams& p, const TileWalk& w, int b, int item, int C8, int N, size_t* off, int* c0, int* ii_out) {
+    const int row = item / C8, vec = item - row * C8;
+    int hl, wl;
+    if (p.halo_t) { wl = row >> 3; hl = row & 7; }
+    else { hl = row >> 3; wl = row & 7; }                            // halo tiles are 16 rows x 8 pixels (or 8 x 16 transposed)
+    const int jj = w.th * p.bh + hl, ii = w.tw * p.bw + wl;
+    *c0 = vec * 8; *ii_out = ii;
+    *off = (((size_t)b * p.Hout + jj) * p.Wout + ii) * N + vec * 8;
+    return row < 128 && hl < p.bh && jj < p.Hg && ii < p.Wg;
+}
+
+template <int N, bool kTb, bool kRes>
+__device__ __forceinline__ void tc_apply_stream(const TcParams& p, const TcShared& sh, int tid_s) {
+    constexpr int C8 = N / 8;                                        // 16-byte vectors per pixel
+    constexpr int kInFlight = kRes ? 5 : 8;                          // items (16-byte loads, x2 with a residual) in flight per thread
+    const ConvEpilogue& e = p.e;
+    const AsyncShared as = async_shared<N>(sh.misc);
+    const int lane = tid_s & 31;
+    const int G = (int)gridDim.x, bx = (int)blockIdx.x;
+    const int tps = p.tiles_h * p.tiles_w;
+    const int n_it = tc_num_iters(p);
+    // (row, vector) items of a 128-pixel tile, strided over the streaming threads; a thread's channel vector changes from item to
+    // item when kStreamThreads is not a multiple of C8, so the per-channel constants are read from the shared-memory tables
+    constexpr int kItems = 128 * C8;
     const __nv_bfloat16* raw = reinterpret_cast<const __nv_bfloat16*>(e.out);
     const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(e.residual);
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(e.ap_out);
     const float2 l2e = make_float2(1.4426950408889634f, 1.4426950408889634f);
     TileWalk tw;
     tw.init(p, bx, G);
+    int run = 0;
     for (int it = 0; it < n_it;) {
         int b;
         const int it_end = apply_run_end(p, it, n_it, tps, &b);
         if (b >= 0) {
-            if (warp_a == 0) {
-                if (lane == 0) { while (ld_acquire_gpu_u32(&cnt[2 * b]) < (unsigned int)nrows) { __nanosleep(64); } }
-                __syncwarp();
-                const int start = tps < G ? (int)(((long long)b * tps) % G) : 0;
-                const int q = lane & 3, r0 = lane >> 2;
-                const float4* pp = reinterpret_cast<const float4*>(e.gn_partials + (size_t)b * G * 16) + q;
-                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-                for (int base = 0; base < G; base += 64) {           // CTA order 0..G-1, the order of tc_teardown's finalisation
-                    float4 v[8];
+            const int sl = run & 1;
+            mbar_wait(&as.tab_full[sl], (uint32_t)(run >> 1) & 1u);
+            const float* t_sc = as.tab + (size_t)sl * 3 * N;
+            TileWalk w2 = tw;
+            for (int j = it; j < it_end && !(p.dbg & 256); ++j, w2.advance(G)) {    // dbg 256: finaliser only, no streaming
+                for (int i0 = tid_s; i0 < kItems; i0 += kStreamThreads * kInFlight) {
+                    // loads of kInFlight items first; only the data stays in registers, coordinates are recomputed afterwards
+                    uint4 v[kInFlight], rv[kRes ? kInFlight : 1];
+                    float mk[kInFlight];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int c = base + r0 + 8 * i;
-                        int rel = c - start; if (rel < 0) rel += G;
-                        v[i] = (c < G && rel < nrows) ? __ldcg(pp + (size_t)c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        a0 += (double)v[i].x; a1 += (double)v[i].y; a2 += (double)v[i].z; a3 += (double)v[i].w;
-                    }
-                }
-#pragma unroll
-                for (int off = 4; off < 32; off <<= 1) {
-                    a0 += __shfl_xor_sync(0xffffffffu, a0, off);
-                    a1 += __shfl_xor_sync(0xffffffffu, a1, off);
-                    a2 += __shfl_xor_sync(0xffffffffu, a2, off);
-                    a3 += __shfl_xor_sync(0xffffffffu, a3, off);
-                }
-                const double q0 = __shfl_sync(0xffffffffu, a0, (lane + 2) & 31), q1 = __shfl_sync(0xffffffffu, a1, (lane + 2) & 31);
-                const double q2 = __shfl_sync(0xffffffffu, a2, (lane + 2) & 31), q3 = __shfl_sync(0xffffffffu, a3, (lane + 2) & 31);
-                if (lane < 2) {
-                    const double su[4] = {a0, a1, a2, a3}, sq[4] = {q0, q1, q2, q3};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const double mean = su[j] * inv_count;
-                        double var = sq[j] * inv_count - mean * mean;
-                        if (var < 0.0) var = 0.0;
-                        const float mf = (float)mean, rf = (float)rsqrt(var + (double)e.gn_eps);
-                        const int gg = lane * 4 + j;
-                        s_mr[gg] = mf; s_mr[8 + gg] = rf;
-                        if (bx == start) {
-                            e.gn_stats[((size_t)b * 8 + gg) * 2 + 0] = mf;
-                            e.gn_stats[((size_t)b * 8 + gg) * 2 + 1] = rf;
+                    for (int u = 0; u < kInFlight; ++u) {
+                        size_t off; int c0, ii;
+                        mk[u] = -1.f;
+                        if (stream_item(p, w2, b, i0 + u * kStreamThreads, C8, N, &off, &c0, &ii)) {
+                            v[u] = __ldcg(reinterpret_cast<const uint4*>(raw + off));
+                            if (kRes) rv[u] = __ldg(reinterpret_cast<const uint4*>(res + off));
+                            mk[u] = e.mask[(size_t)b * p.Wout + ii];
                         }
                     }
-                }
-                __syncwarp();
-                for (int c = lane; c < N; c += 32) {
-                    const int gg = c / kGsz;
-                    const float sc = s_mr[8 + gg] * __ldg(e.ap_gamma + c);
-                    s_sc[c] = sc;
-                    s_sh[c] = fmaf(-s_mr[gg], sc, __ldg(e.ap_beta + c));             // gn_apply's expression (pointwise.cu)
-                    s_tb[c] = e.ap_tbias ? __ldg(e.ap_tbias + (size_t)b * e.ap_tb_bstride + c) : 0.f;
-                }
-                if (lane == 0) {                                     // departure: the last reader resets the counters for the next launch
-                    if (atomicAdd(&cnt[2 * b + 1], 1u) == (unsigned int)(nrows - 1)) { cnt[2 * b] = 0u; cnt[2 * b + 1] = 0u; }
-                }
-            }
-            named_bar_sync(1, kApplyWarps * 32);                     // tables of this run are in shared memory
-            float2 sc2[4], sh2[4], tb2[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                sc2[q] = make_float2(s_sc[c0 + 2 * q], s_sc[c0 + 2 * q + 1]);
-                sh2[q] = make_float2(s_sh[c0 + 2 * q], s_sh[c0 + 2 * q + 1]);
-                tb2[q] = make_float2(s_tb[c0 + 2 * q], s_tb[c0 + 2 * q + 1]);
-            }
-            TileWalk w2 = tw;
-            for (int j = it; j < it_end; ++j, w2.advance(G)) {
-#pragma unroll 2
-                for (int row = pslot; row < 128; row += kPStep) {
-                    int hl = row / p.bw, wl = row - hl * p.bw;
-                    if (p.halo_t) { wl = row >> 3; hl = row & 7; }
-                    const int jj = w2.th * p.bh + hl, ii = w2.tw * p.bw + wl;
-                    if (hl >= p.bh || jj >= p.Hg || ii >= p.Wg) continue;
-                    const size_t pix = ((size_t)b * p.Hout + jj) * p.Wout + ii;
-                    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(raw + pix * N + c0));
-                    uint4 rv = make_uint4(0u, 0u, 0u, 0u);
-                    if (kRes) rv = __ldg(reinterpret_cast<const uint4*>(res + pix * N + c0));
-                    const float m = e.mask[(size_t)b * p.Wout + ii];
-                    const float2 m2 = make_float2(m, m);
-                    const uint32_t wv[4] = {v.x, v.y, v.z, v.w}, rw[4] = {rv.x, rv.y, rv.z, rv.w};
-                    uint32_t ow[4];
+                    for (int u = 0; u < kInFlight; ++u) {
+                        if (mk[u] < 0.f) continue;
+                        size_t off; int c0, ii;
+                        stream_item(p, w2, b, i0 + u * kStreamThreads, C8, N, &off, &c0, &ii);
+                        const float2 m2 = make_float2(mk[u], mk[u]);
+                        const uint32_t wv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                        const uint4 rr = rv[kRes ? u : 0];
+                        const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+                        uint32_t ow[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float2 x = make_float2(__uint_as_float(wv[q] << 16), __uint_as_float(wv[q] & 0xffff0000u));
-                        const float2 y = ffma2(x, sc2[q], sh2[q]);
-                        float2 o = mish2_fast(y, fmul2(y, l2e));
-                        if (kTb) o = fadd2(o, tb2[q]);
-                        if (kRes) o = fadd2(o, make_float2(__uint_as_float(rw[q] << 16), __uint_as_float(rw[q] & 0xffff0000u)));
-                        o = fmul2(o, m2);
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(o.x, o.y);
-                        ow[q] = *reinterpret_cast<uint32_t*>(&h2);
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 sc2 = *reinterpret_cast<const float2*>(&t_sc[c0 + 2 * q]);
+                            const float2 sh2 = *reinterpret_cast<const float2*>(&t_sc[N + c0 + 2 * q]);
+                            const float2 x = make_float2(__uint_as_float(wv[q] << 16), __uint_as_float(wv[q] & 0xffff0000u));
+                            const float2 y = ffma2(x, sc2, sh2);
+                            float2 o = mish2_fast(y, fmul2(y, l2e));
+                            if (kTb) o = fadd2(o, *reinterpret_cast<const float2*>(&t_sc[2 * N + c0 + 2 * q]));
+                            if (kRes) o = fadd2(o, make_float2(__uint_as_float(rw[q] << 16), __uint_as_float(rw[q] & 0xffff0000u)));
+                            o = fmul2(o, m2);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(o.x, o.y);
+                            ow[q] = *reinterpret_cast<uint32_t*>(&h2);
+                        }
+                        *reinterpret_cast<uint4*>(out + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                     }
-                    *reinterpret_cast<uint4*>(out + pix * N + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                 }
             }
-            named_bar_sync(1, kApplyWarps * 32);                     // everyone is done with the tables before the next run overwrites them
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&as.tab_empty[sl]);
+            ++run;
         }
         for (int j = it; j < it_end; ++j) tw.advance(G);
         it = it_end;
@@ -577,6 +644,10 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
         if (kApply == 1 || kApply == 2) {
             const ApplyShared ap = apply_shared<N>(sh.misc);
             for (int i = 0; i < 2; ++i) { mbar_init(&ap.aff_full[i], 1); mbar_init(&ap.aff_empty[i], 16); }
+        }
+        if (kApply >= 3) {
+            const AsyncShared as = async_shared<N>(sh.misc);
+            for (int i = 0; i < 2; ++i) { mbar_init(&as.tab_full[i], 1); mbar_init(&as.tab_empty[i], kStreamWarps); }
         }
         mbar_fence_init();
     } else if (warp == 2) {
@@ -784,8 +855,10 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
     } else if (warp >= 4 && warp < kThreads / 32) {
         if (kApply == 1 || kApply == 2) tc_epilogue_apply_loop<N, kApply == 1, kApply == 2>(p, sh, tmem_base, warp, lane);
         else tc_epilogue_loop<N, kStats, false, kMask, kOutF32>(p, sh, tmem_base, warp, lane);
-    } else if (kApply >= 3 && warp >= kThreads / 32) {
-        tc_apply_async_loop<N, kApply == 3, kApply == 4>(p, sh, tid - kThreads);
+    } else if (kApply >= 3 && warp == kThreads / 32) {
+        if (!(p.dbg & 128)) tc_apply_finaliser<N>(p, sh, lane);       // dbg 128: no apply work at all (timing experiments)
+    } else if (kApply >= 3 && warp > kThreads / 32) {
+        if (!(p.dbg & 128)) tc_apply_stream<N, kApply == 3, kApply == 4>(p, sh, tid - kThreads - 32);
     } else if (kFuse && warp >= kThreads / 32) {
         // ================================================================ input transform (both CTAs)
         // thread -> 16-byte chunk j (8 channels) of rows r0, r0+16, ...; the 128-byte swizzle puts chunk j of row r at
@@ -903,7 +976,7 @@ int conv_tc_halo2_max_grid(int N, bool residual, size_t smem, bool async_apply) 
     if (residual) return N == 64 ? max_grid_of<64, 2>(smem) : (N == 128 ? max_grid_of<128, 2>(smem) : max_grid_of<256, 2>(smem));
     return N == 64 ? max_grid_of<64, 1>(smem) : (N == 128 ? max_grid_of<128, 1>(smem) : max_grid_of<256, 1>(smem));
 }
-int conv_tc_halo2_apply_extra_smem() { return kApplyExtra; }
+int conv_tc_halo2_apply_extra_smem(int apply) { return apply == 2 ? kAsyncExtra : kApplyExtra; }
 
 int conv_tc_halo2_launch(const TcConvPlan* pl, cudaStream_t stream) {
     const ConvEpilogue& e = pl->p.e;
