@@ -163,10 +163,17 @@ final_bwd_kernel(const float* __restrict__ v, const float* __restrict__ wf, cons
 template <typename T>
 __global__ void __launch_bounds__(128)
 first_bwd_kernel(const T* __restrict__ graw1, const T* __restrict__ gres, const float* __restrict__ w1t, const float* __restrict__ wres,
-                 const float* __restrict__ mask, float* __restrict__ gx, int B, int H, int W, int cin) {
-    __shared__ float s_w[9 * 64 + 64];
-    for (int i = threadIdx.x; i < 9 * 64; i += 128) s_w[i] = w1t[(size_t)(9 + i / 64) * 64 + (i % 64)];   // ci = 1: rows 9..17
-    for (int i = threadIdx.x; i < 64; i += 128) s_w[576 + i] = wres[(size_t)i * cin + 1];
+                 const float* __restrict__ mask, float* __restrict__ gx, float* __restrict__ gmu, float* __restrict__ gs, int B, int H, int W,
+                 int cin) {
+    __shared__ float s_w[3][9 * 64 + 64];                              // per input channel: 9 taps x 64 co of W1, then 64 co of Wres
+    for (int i = threadIdx.x; i < 3 * 9 * 64; i += 128) {
+        const int ci = i / 576, r = i % 576;
+        s_w[ci][r] = ci < cin ? w1t[(size_t)(ci * 9 + r / 64) * 64 + (r % 64)] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 3 * 64; i += 128) {
+        const int ci = i / 64, c = i % 64;
+        s_w[ci][576 + c] = ci < cin ? wres[(size_t)c * cin + ci] : 0.f;
+    }
     __syncthreads();
     const size_t pix = (size_t)blockIdx.x * 128 + threadIdx.x;
     const size_t npix = (size_t)B * H * W;
@@ -174,8 +181,14 @@ first_bwd_kernel(const T* __restrict__ graw1, const T* __restrict__ gres, const 
     const int b = (int)(pix / ((size_t)H * W));
     const int rem = (int)(pix % ((size_t)H * W)), h = rem / W, w = rem % W;
     const float m = mask[(size_t)b * W + w];
-    if (m == 0.f) { gx[pix] = 0.f; return; }
-    float acc = 0.f;
+    if (m == 0.f) {
+        gx[pix] = 0.f;
+        if (gmu) gmu[pix] = 0.f;
+        if (gs) gs[pix] = 0.f;
+        return;
+    }
+    const bool want0 = gmu != nullptr, want2 = gs != nullptr && cin == 3;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     for (int ky = 0; ky < 3; ++ky) {
         const int hh = h - ky + 1;
         if (hh < 0 || hh >= H) continue;
@@ -183,13 +196,17 @@ first_bwd_kernel(const T* __restrict__ graw1, const T* __restrict__ gres, const 
             const int ww = w - kx + 1;
             if (ww < 0 || ww >= W) continue;
             const T* gp = graw1 + (((size_t)b * H + hh) * W + ww) * 64;
-            const float* wp = &s_w[(ky * 3 + kx) * 64];
+            const int t = (ky * 3 + kx) * 64;
 #pragma unroll
             for (int c8 = 0; c8 < 8; ++c8) {
                 float gv[8];
                 Act<T>::load8(gp + c8 * 8, gv);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc = fmaf(wp[c8 * 8 + j], gv[j], acc);
+                for (int j = 0; j < 8; ++j) {
+                    a1 = fmaf(s_w[1][t + c8 * 8 + j], gv[j], a1);
+                    if (want0) a0 = fmaf(s_w[0][t + c8 * 8 + j], gv[j], a0);
+                    if (want2) a2 = fmaf(s_w[2][t + c8 * 8 + j], gv[j], a2);
+                }
             }
         }
     }
@@ -200,10 +217,16 @@ first_bwd_kernel(const T* __restrict__ graw1, const T* __restrict__ gres, const 
             float gv[8];
             Act<T>::load8(gp + c8 * 8, gv);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc = fmaf(s_w[576 + c8 * 8 + j], gv[j], acc);
+            for (int j = 0; j < 8; ++j) {
+                a1 = fmaf(s_w[1][576 + c8 * 8 + j], gv[j], a1);
+                if (want0) a0 = fmaf(s_w[0][576 + c8 * 8 + j], gv[j], a0);
+                if (want2) a2 = fmaf(s_w[2][576 + c8 * 8 + j], gv[j], a2);
+            }
         }
     }
-    gx[pix] = acc * m;
+    gx[pix] = a1 * m;
+    if (gmu) gmu[pix] = a0 * m;
+    if (gs) gs[pix] = want2 ? a2 * m : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------ element-wise helpers
@@ -320,7 +343,8 @@ attn_outer_merge_kernel(const float* __restrict__ partials, const float* __restr
 template <typename T>
 __global__ void __launch_bounds__(256)
 attn_pos_bwd_kernel(const T* __restrict__ kv, const T* __restrict__ go, const float* __restrict__ ctxn, const float* __restrict__ gctx,
-                    const float* __restrict__ ml, const float* __restrict__ sdot, T* __restrict__ gq, T* __restrict__ gkv, int n) {
+                    const float* __restrict__ ml, const float* __restrict__ sdot, T* __restrict__ gq, T* __restrict__ gkv, int n,
+                    const T* __restrict__ q, T* __restrict__ ao) {
     __shared__ float s_ctx[32 * 33], s_g[32 * 33], s_m[32], s_il[32], s_s[32];
     const int tid = threadIdx.x, head = blockIdx.y, b = blockIdx.z;
     const size_t bh = (size_t)b * 4 + head;
@@ -361,6 +385,20 @@ attn_pos_bwd_kernel(const T* __restrict__ kv, const T* __restrict__ go, const fl
     Act<T>::store8(gq + base * 128 + head * 32 + j * 8, oq);
     Act<T>::store8(gkv + base * 256 + head * 32 + j * 8, ok);
     Act<T>::store8(gkv + base * 256 + 128 + head * 32 + j * 8, ov);
+    if (ao) {                                                          // attention output before to_out (needed for dWout): ao[e] = sum_d ctxn[d][e] q[d]
+        float qq[32], oa[8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Act<T>::load8(q + base * 128 + head * 32 + c * 8, *reinterpret_cast<float(*)[8]>(&qq[c * 8]));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int ee = j * 8 + i;
+            float a = 0.f;
+#pragma unroll
+            for (int d = 0; d < 32; ++d) a = fmaf(s_ctx[d * 33 + ee], qq[d], a);
+            oa[i] = a;
+        }
+        Act<T>::store8(ao + base * 128 + head * 32 + j * 8, oa);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ dgrad weight packing
@@ -448,10 +486,10 @@ int final_bwd(ActKind act, const float* v, const float* wf, const float* mask, v
 }
 
 int first_bwd(ActKind act, const void* graw1, const void* gres, const float* w1t, const float* wres, const float* mask, float* gx,
-              int B, int H, int W, int cin, cudaStream_t s) {
+              float* gmu, float* gs, int B, int H, int W, int cin, cudaStream_t s) {
     const size_t n = (size_t)B * H * W;
-    if (act == ACT_F32) first_bwd_kernel<float><<<nblk(n, 128), 128, 0, s>>>((const float*)graw1, (const float*)gres, w1t, wres, mask, gx, B, H, W, cin);
-    else first_bwd_kernel<__nv_bfloat16><<<nblk(n, 128), 128, 0, s>>>((const __nv_bfloat16*)graw1, (const __nv_bfloat16*)gres, w1t, wres, mask, gx, B, H, W, cin);
+    if (act == ACT_F32) first_bwd_kernel<float><<<nblk(n, 128), 128, 0, s>>>((const float*)graw1, (const float*)gres, w1t, wres, mask, gx, gmu, gs, B, H, W, cin);
+    else first_bwd_kernel<__nv_bfloat16><<<nblk(n, 128), 128, 0, s>>>((const __nv_bfloat16*)graw1, (const __nv_bfloat16*)gres, w1t, wres, mask, gx, gmu, gs, B, H, W, cin);
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -483,13 +521,14 @@ int attn_outer(ActKind act, const void* q, const void* go, float* partials, cons
 }
 
 int attn_pos_bwd(ActKind act, const void* kv, const void* go, const float* ctxn, const float* gctx, const float* ml, const float* sdot,
-                 void* gq, void* gkv, int B, int n, cudaStream_t s) {
+                 void* gq, void* gkv, int B, int n, const void* q, void* ao, cudaStream_t s) {
     dim3 grid((n + 63) / 64, 4, B);
     if (act == ACT_F32)
-        attn_pos_bwd_kernel<float><<<grid, 256, 0, s>>>((const float*)kv, (const float*)go, ctxn, gctx, ml, sdot, (float*)gq, (float*)gkv, n);
+        attn_pos_bwd_kernel<float><<<grid, 256, 0, s>>>((const float*)kv, (const float*)go, ctxn, gctx, ml, sdot, (float*)gq, (float*)gkv, n,
+                                                       (const float*)q, (float*)ao);
     else
         attn_pos_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)kv, (const __nv_bfloat16*)go, ctxn, gctx, ml, sdot,
-                                                               (__nv_bfloat16*)gq, (__nv_bfloat16*)gkv, n);
+                                                               (__nv_bfloat16*)gq, (__nv_bfloat16*)gkv, n, (const __nv_bfloat16*)q, (__nv_bfloat16*)ao);
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

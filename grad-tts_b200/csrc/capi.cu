@@ -157,6 +157,19 @@ int gtts_decoder_estimator_vjp(gtts_decoder* h, const float* x, const float* mas
     return decoder_estimator_vjp(h->impl, x, mask, mu, t, spk, v, out_score, out_gx, B, T, flags, (cudaStream_t)stream);
 }
 
+int gtts_decoder_estimator_backward(gtts_decoder* h, const float* x, const float* mask, const float* mu, const float* t, const float* spk,
+                                    const float* v, float* out_score, float* out_gx, float* out_gmu, float* out_gs_pix, float* out_gtb,
+                                    int B, int T, int flags, void* stream) {
+    GTTS_REQUIRE(h && x && mask && mu && t && v && out_gx, "estimator_backward: null pointer");
+    return decoder_estimator_backward(h->impl, x, mask, mu, t, spk, v, out_score, out_gx, out_gmu, out_gs_pix, out_gtb, B, T, flags,
+                                      (cudaStream_t)stream);
+}
+
+int gtts_decoder_get_param_grad(gtts_decoder* h, const char* name, float* dst, size_t numel, void* stream) {
+    GTTS_REQUIRE(h != nullptr, "null decoder handle");
+    return decoder_get_param_grad(h->impl, name, dst, numel, (cudaStream_t)stream);
+}
+
 int gtts_decoder_reverse_diffusion_host(gtts_decoder* h, const float* z_host, const float* mask_host,
                                         const float* mu_host, const float* spk_host, float* out_host, int B, int T,
                                         int n_timesteps, int flags) {

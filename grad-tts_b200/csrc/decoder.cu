@@ -167,6 +167,10 @@ struct Decoder {
     bool has_done = false;
     long launches_last_call = 0;
     long plans_created = 0;
+    // parameter gradients of the last estimator_backward call (flat, fp32, PyTorch layouts; offsets in pg_layout)
+    std::map<std::string, std::pair<size_t, size_t>> pg_layout;   // full name -> (offset, numel)
+    size_t pg_floats = 0;
+    float* pg_accum = nullptr;
     ~Decoder();
 };
 
@@ -497,7 +501,9 @@ struct Plan {
     float* h_dev = nullptr;
     int max_steps = 4096;
     bool vjp = false;             // forward (est mode, every intermediate kept) followed by the backward pass w.r.t. x
+    bool pgrads = false;          // ... and the gradients of every parameter, of mu, of the speaker plane and of the time biases
     float *vin = nullptr, *gx = nullptr;      // (B,80,T) cotangent in, J^T v out
+    float *gmu = nullptr, *gs_pix = nullptr, *gtb = nullptr, *pg_flat = nullptr;   // (B,80,T), (B,80,T), (B,1792), flat parameter grads
     size_t pooled_bytes = 0;      // peak of live pooled activation memory of this plan (after liveness reuse)
     size_t unpooled_bytes = 0;    // what one-buffer-per-tensor allocation would have needed (reported for comparison)
     float* partials = nullptr;
@@ -515,6 +521,7 @@ struct Plan {
 Decoder::~Decoder() {
     for (auto& kv : plans) delete kv.second.plan;
     if (done_ev) cudaEventDestroy(done_ev);
+    if (pg_accum) cudaFree(pg_accum);
 }
 
 namespace {
@@ -537,6 +544,7 @@ struct PlanBuilder {
     std::vector<std::function<void()>> tape;
     std::map<const void*, void*> grad;          // activation -> gradient accumulated so far
     float* gn_bwd_partials = nullptr;
+    const void* a1_of[12] = {nullptr};          // block2's input of every ResnetBlock (for its weight gradient)
 
     void fail_oom(size_t bytes) {
         failed = true; oom = true;
@@ -782,6 +790,7 @@ struct PlanBuilder {
         if (resid != x0) release(resid);
         if (vjp) {
             const bool identity = (r != 0 && !R.wres);
+            a1_of[r] = a1;
             tape.push_back([=]() { resnet_backward(r, lvl, x0, c0, x1, c1, raw1, st1, raw2, st2, out, identity); });
         }
         return out;
@@ -843,6 +852,55 @@ struct PlanBuilder {
         pl->push("bwd_add", 0, 0.0, 0.0, [k, a, b, out, numel](cudaStream_t s) { return add_tensors(k, a, b, out, numel, s); });
     }
 
+    // ---- parameter gradients (plans with pgrads): every destination is a slice of pl->pg_flat in the parameter's PyTorch layout
+    bool pgrads = false;
+    float* pg(const std::string& name) {
+        auto it = d->pg_layout.find("estimator." + name);
+        if (it == d->pg_layout.end()) { set_error("internal: no gradient slot for estimator." + name); failed = true; return pl->pg_flat; }
+        return pl->pg_flat + it->second.first;
+    }
+    const float* param(const std::string& name) {
+        auto it = d->params.find("estimator." + name);
+        return it == d->params.end() ? nullptr : it->second;
+    }
+    // dW and db of one conv: gout = gradient of its (pre-norm / pre-mask) output, x0 / x1 = its saved input(s)
+    void add_conv_param_grads(const std::string& prefix, const ConvGeom& gfwd, const void* gout, const void* x0, const void* x1, int kind_layout,
+                              float* dw_override = nullptr, bool want_bias = true) {
+        int slices;
+        const size_t pf = wgrad_partial_floats(gfwd, &slices);
+        float* part = (float*)pooled(pf * 4);
+        float* bpart = (float*)pooled((size_t)256 * gfwd.Cout * 4);
+        if (failed) return;
+        float* dw = dw_override ? dw_override : pg(prefix + ".weight");
+        float* db = want_bias ? pg(prefix + ".bias") : nullptr;
+        ActKind k = kind;
+        ConvGeom g = gfwd;
+        const long npix_out = (long)g.B * g.Hout * g.Wout;
+        pl->push("bwd_wgrad_" + std::to_string(g.Cin0 + g.Cin1) + "_" + std::to_string(g.Cout) + "_h" + std::to_string(g.Hin), 0,
+                 2.0 * (double)g.B * g.nphase * g.Hg * g.Wg * g.Cout * g.ntaps * (g.Cin0 + g.Cin1), 0.0,
+                 [k, g, gout, x0, x1, part, dw, kind_layout, db, bpart, npix_out](cudaStream_t s) {
+                     if (int rc = conv_wgrad(k, g, gout, x0, x1, part, dw, kind_layout, 1.0f, 0, s)) return rc;
+                     if (db) return col_sums(k, gout, bpart, db, npix_out, g.Cout, 1.0f, 0, s);
+                     return 0;
+                 });
+        pl->kernels_per_step += db ? 3 : 1;
+        release(part, true); release(bpart, true);
+    }
+    void add_gn_param_grads(const std::string& prefix, int lvl, int C, const void* raw, const float* st, const BlockW& bw, const void* gy) {
+        GnBwdArgs a;
+        memset(&a, 0, sizeof(a));
+        a.raw = raw; a.stats = st; a.gamma = bw.gamma; a.beta = bw.beta; a.mask = lmask[lvl]; a.gy = gy;
+        a.B = B; a.H = H[lvl]; a.W = W[lvl]; a.C = C;
+        float* part = (float*)pooled((size_t)B * 256 * 2 * C * 4);
+        if (failed) return;
+        float* dga = pg(prefix + ".block.1.weight");
+        float* dbe = pg(prefix + ".block.1.bias");
+        ActKind k = kind;
+        pl->push("bwd_gn_params", 0, 0.0, 0.0, [k, a, part, dga, dbe](cudaStream_t s) { return gn_param_grad(k, a, part, dga, dbe, s); });
+        pl->kernels_per_step++;
+        release(part, true);
+    }
+
     // ResnetBlock backward: gradient of `out` -> gradients of its input source(s) (or, for the first block, of the x plane)
     void resnet_backward(int r, int lvl, const void* x0, int c0, const void* x1, int c1, void* raw1, float* st1, void* raw2, float* st2,
                          void* out, bool identity) {
@@ -855,25 +913,71 @@ struct PlanBuilder {
         void* g_raw2 = act(lvl, Co);
         void* g_a1 = act(lvl, Co);
         if (failed) return;
+        const std::string rn = kResnetNames[r];
         add_mask_mul(lvl, Co, g_out, gpre);
         release(g_out);
         add_gn_bwd(lvl, Co, raw2, st2, R.b2, gpre, g_raw2);
+        if (pgrads) {
+            add_gn_param_grads(rn + ".block2", lvl, Co, raw2, st2, R.b2, gpre);
+            add_conv_param_grads(rn + ".block2.block.0", geom_3x3(B, H[lvl], W[lvl], Co, 0, Co, 1), g_raw2, a1_of[r], nullptr, 0);
+        }
         add_bconv("dgrad3", geom_3x3(B, H[lvl], W[lvl], Co, 0, Co, 1), g_raw2, Bw.d2, nullptr, g_a1);
         release(g_raw2);
         void* g_raw1 = act(lvl, Co);                          // a1 = (Mish(GN(raw1)) + time bias) * mask
         if (failed) return;
         add_gn_bwd(lvl, Co, raw1, st1, R.b1, g_a1, g_raw1);
+        if (pgrads) {
+            add_gn_param_grads(rn + ".block1", lvl, Co, raw1, st1, R.b1, g_a1);
+            {   // time bias: d tb[b][c] = sum_p g_a1[b][p][c] * mask
+                float* part = (float*)pooled((size_t)B * 64 * Co * 4);
+                if (failed) return;
+                ActKind k = kind;
+                const float* m = lmask[lvl];
+                float* dst = pl->gtb + R.tb_off;
+                int Bb = B, Hh = H[lvl], Ww = W[lvl];
+                pl->push("bwd_tbias", 0, 0.0, 0.0, [k, g_a1, m, part, dst, Bb, Hh, Ww, Co](cudaStream_t s) {
+                    return col_sums_per_sample(k, g_a1, m, part, dst, Bb, Hh, Ww, Co, 1792, s);
+                });
+                pl->kernels_per_step++;
+                release(part, true);
+            }
+        }
         release(g_a1);
         if (r == 0) {
             ActKind k = kind;
             const float *w1t = P->first_wT, *wres = P->fr_w, *m = lmask[0];
-            float* gx = pl->gx;
+            float *gx = pl->gx, *gmu = pgrads ? pl->gmu : nullptr, *gs = pgrads ? pl->gs_pix : nullptr;
             int Bb = B, Hh = H[0], Ww = W[0], cin = d->cin_first;
-            pl->push("bwd_first", 0, 0.0, 0.0, [k, g_raw1, gpre, w1t, wres, m, gx, Bb, Hh, Ww, cin](cudaStream_t s) {
-                return first_bwd(k, g_raw1, gpre, w1t, wres, m, gx, Bb, Hh, Ww, cin, s);
+            pl->push("bwd_first", 0, 0.0, 0.0, [k, g_raw1, gpre, w1t, wres, m, gx, gmu, gs, Bb, Hh, Ww, cin](cudaStream_t s) {
+                return first_bwd(k, g_raw1, gpre, w1t, wres, m, gx, gmu, gs, Bb, Hh, Ww, cin, s);
             });
+            if (pgrads) {
+                // first conv (K = cin*9) and first res_conv (K = cin) weights + biases in one small kernel, then scattered
+                const int nk = cin * 9 + cin + 2, blocks = first_param_blocks(Hh, Ww);
+                float* part = (float*)pooled((size_t)B * blocks * 64 * nk * 4);
+                float* tmp = (float*)pl->mem.alloc((size_t)64 * nk * 4);
+                if (failed || !tmp) { if (!failed) fail_oom(64 * nk * 4); return; }
+                const float *mu = pl->mu, *xx = pl->xt, *sp = pl->splane;
+                float *dw1 = pg(rn + ".block1.block.0.weight"), *db1 = pg(rn + ".block1.block.0.bias");
+                float *dwr = pg(rn + ".res_conv.weight"), *dbr = pg(rn + ".res_conv.bias");
+                pl->push("bwd_first_params", 0, 0.0, 0.0, [k, g_raw1, gpre, mu, xx, sp, m, part, tmp, dw1, db1, dwr, dbr, Bb, Hh, Ww, cin, nk](cudaStream_t s) {
+                    if (int rc = first_param_grad(k, g_raw1, gpre, mu, xx, sp, m, part, tmp, Bb, Hh, Ww, cin, 0, s)) return rc;
+                    const size_t ld = (size_t)nk * 4;
+                    GTTS_CHECK_CUDA(cudaMemcpy2DAsync(dw1, (size_t)cin * 9 * 4, tmp, ld, (size_t)cin * 9 * 4, 64, cudaMemcpyDeviceToDevice, s));
+                    GTTS_CHECK_CUDA(cudaMemcpy2DAsync(dwr, (size_t)cin * 4, tmp + cin * 9, ld, (size_t)cin * 4, 64, cudaMemcpyDeviceToDevice, s));
+                    GTTS_CHECK_CUDA(cudaMemcpy2DAsync(db1, 4, tmp + cin * 9 + cin, ld, 4, 64, cudaMemcpyDeviceToDevice, s));
+                    GTTS_CHECK_CUDA(cudaMemcpy2DAsync(dbr, 4, tmp + cin * 9 + cin + 1, ld, 4, 64, cudaMemcpyDeviceToDevice, s));
+                    return 0;
+                });
+                pl->kernels_per_step += 5;
+                release(part, true);
+            }
             release(g_raw1); release(gpre);
             return;
+        }
+        if (pgrads) {
+            add_conv_param_grads(rn + ".block1.block.0", geom_3x3(B, H[lvl], W[lvl], c0, c1, Co, 1), g_raw1, x0, x1, 0);
+            if (R.wres) add_conv_param_grads(rn + ".res_conv", geom_1x1(B, H[lvl], W[lvl], c0, c1, Co, 0), gpre, x0, x1, 0);
         }
         const void* xs[2] = {x0, x1};
         const int cs[2] = {c0, c1};
@@ -936,18 +1040,48 @@ struct PlanBuilder {
             });
             pl->kernels_per_step++;
         }
-        release(q);
+        if (!pgrads) release(q);
         void* gq = act(lvl, 128);
         void* gkv = act(lvl, 256);
+        void* ao = pgrads ? act(lvl, 128) : nullptr;          // attention output before to_out (for dWout)
         if (failed) return;
         {
             ActKind k = kind;
             int Bb = B;
-            pl->push("bwd_attn_pos", 0, 0.0, 0.0, [k, kv, go, ctxn, gctx, ml, sdot, gq, gkv, Bb, n](cudaStream_t s) {
-                return attn_pos_bwd(k, kv, go, ctxn, gctx, ml, sdot, gq, gkv, Bb, n, s);
+            const void* qp = pgrads ? q : nullptr;
+            pl->push("bwd_attn_pos", 0, 0.0, 0.0, [k, kv, go, ctxn, gctx, ml, sdot, gq, gkv, Bb, n, qp, ao](cudaStream_t s) {
+                return attn_pos_bwd(k, kv, go, ctxn, gctx, ml, sdot, gq, gkv, Bb, n, qp, ao, s);
             });
         }
         release(go);
+        if (pgrads) {
+            release(q);
+            const char* attn_names[6] = {"downs.0.2", "downs.1.2", "downs.2.2", "mid_attn", "ups.0.2", "ups.1.2"};
+            const std::string an = std::string(attn_names[a]) + ".fn";
+            // to_qkv (384, C): rows [0,128) from gq, rows [128,384) from gkv; no bias
+            float* dqkv = pg(an + ".fn.to_qkv.weight");
+            add_conv_param_grads("", geom_1x1(B, H[lvl], W[lvl], C, 0, 128, 0), gq, x, nullptr, 0, dqkv, false);
+            add_conv_param_grads("", geom_1x1(B, H[lvl], W[lvl], C, 0, 256, 0), gkv, x, nullptr, 0, dqkv + (size_t)128 * C, false);
+            // to_out behind the Rezero gate: raw A = sum G (x) ao and s = sum G, then dWout = g A, dbout = g s, dg = <Wout, A> + <bout, s>
+            float* Araw = (float*)pl->mem.alloc((size_t)C * 128 * 4);
+            float* sraw = (float*)pl->mem.alloc((size_t)C * 4);
+            float* bpart = (float*)pooled((size_t)256 * C * 4);
+            if (failed || !Araw || !sraw) { if (!failed) fail_oom((size_t)C * 512); return; }
+            add_conv_param_grads("", geom_1x1(B, H[lvl], W[lvl], 128, 0, C, 0), G, ao, nullptr, 0, Araw, false);
+            {
+                ActKind k = kind;
+                const long npix = (long)B * n;
+                const float *wout = A.wout, *bout = param(an + ".fn.to_out.bias");
+                const float g = A.g;
+                float *dwo = pg(an + ".fn.to_out.weight"), *dbo = pg(an + ".fn.to_out.bias"), *dg = pg(an + ".g");
+                pl->push("bwd_attn_out_params", 0, 0.0, 0.0, [k, G, bpart, sraw, npix, C, Araw, wout, bout, g, dwo, dbo, dg](cudaStream_t s) {
+                    if (int rc = col_sums(k, G, bpart, sraw, npix, C, 1.0f, 0, s)) return rc;
+                    return attn_out_grads(Araw, sraw, wout, bout, g, dwo, dbo, dg, C, s);
+                });
+                pl->kernels_per_step += 2;
+            }
+            release(bpart, true); release(ao);
+        }
         void* prev = peek_grad(x);
         const void* acc = G;
         void* owned = nullptr;
@@ -982,6 +1116,10 @@ struct PlanBuilder {
         if (prev) grad.erase(x);
         void* gn = act(lvl_in, C);
         if (failed) return;
+        if (pgrads) {
+            if (down) add_conv_param_grads("downs." + std::to_string(i) + ".3.conv", geom_3x3(B, H[lvl_in], W[lvl_in], C, 0, C, 2), gm, x, nullptr, 0);
+            else add_conv_param_grads("ups." + std::to_string(i) + ".3.conv", geom_convT(B, H[lvl_in], W[lvl_in], C), gm, x, nullptr, 1);
+        }
         if (down) add_bconv("down", geom_down_dgrad(B, H[lvl_out], W[lvl_out], C), gm, P->bdown[i], prev, gn);
         else add_bconv("up", geom_up_dgrad(B, H[lvl_in], W[lvl_in], C), gm, P->bup[i], prev, gn);
         release(prev); release(gm);
@@ -1069,6 +1207,27 @@ struct PlanBuilder {
             gn_bwd_partials = (float*)pl->mem.alloc((size_t)B * 256 * 16 * 4);
             if (!gn_bwd_partials) { fail_oom((size_t)B * 16384); return 4; }
             keep_all = true;
+            if (pgrads) {
+                if (d->pg_layout.empty()) {
+                    // every estimator parameter except the time / speaker MLPs (their gradients come from the time-bias and
+                    // speaker-plane gradients through PyTorch autograd on the host side): flat buffer in map (= name) order
+                    size_t off = 0;
+                    for (auto& kv : d->params) {
+                        const std::string& n = kv.first;
+                        if (n.rfind("estimator.", 0) != 0) continue;
+                        if (n.find(".mlp.") != std::string::npos || n.rfind("estimator.mlp.", 0) == 0 || n.rfind("estimator.spk_mlp.", 0) == 0) continue;
+                        const size_t numel = d->param_numel[n];
+                        d->pg_layout[n] = std::make_pair(off, numel);
+                        off += (numel + 3) / 4 * 4;
+                    }
+                    d->pg_floats = off;
+                }
+                pl->pg_flat = (float*)pl->mem.alloc(d->pg_floats * 4, true);
+                pl->gmu = (float*)pooled(plane * 4);
+                pl->gs_pix = (float*)pooled(plane * 4);
+                pl->gtb = (float*)pl->mem.alloc((size_t)B * 1792 * 4, true);
+                if (failed || !pl->pg_flat || !pl->gtb) { if (!failed) fail_oom(d->pg_floats * 4); return 4; }
+            }
         }
         pl->m0 = (float*)pl->mem.alloc((size_t)B * T * 4);
         pl->m1 = (float*)pl->mem.alloc((size_t)B * T / 2 * 4);
@@ -1190,6 +1349,26 @@ struct PlanBuilder {
                 pl->push("bwd_final", 0, 0.0, 0.0, [k, v, wf, m, ghf, Bb, Hh, Ww](cudaStream_t s) { return final_bwd(k, v, wf, m, ghf, Bb, Hh, Ww, s); });
             }
             add_gn_bwd(0, 64, rawf, stf, P->final_block, ghf, g_rawf);
+            if (pgrads) {
+                add_gn_param_grads("final_block", 0, 64, rawf, stf, P->final_block, ghf);
+                add_conv_param_grads("final_block.block.0", geom_3x3(B, H[0], W[0], 64, 0, 64, 1), g_rawf, x, nullptr, 0);
+                // final_conv (64 -> 1): dwf[c] = sum v * mask * hf[c], dbf = sum v * mask
+                float* part = (float*)pooled((size_t)256 * 65 * 4);
+                float* tmp = (float*)pl->mem.alloc(65 * 4);
+                if (failed || !tmp) { if (!failed) fail_oom(260); return 5; }
+                ActKind k = kind;
+                const float *st = stf, *ga = P->final_block.gamma, *be = P->final_block.beta, *v = pl->vin, *m = pl->m0;
+                float *dwf = pg("final_conv.weight"), *dbf = pg("final_conv.bias");
+                int Bb = B, Hh = H[0], Ww = W[0];
+                pl->push("bwd_final_params", 0, 0.0, 0.0, [k, rawf, st, ga, be, v, m, part, tmp, dwf, dbf, Bb, Hh, Ww](cudaStream_t s) {
+                    if (int rc = final_param_grad(k, rawf, st, ga, be, v, m, part, tmp, Bb, Hh, Ww, 0, s)) return rc;
+                    GTTS_CHECK_CUDA(cudaMemcpyAsync(dwf, tmp, 64 * 4, cudaMemcpyDeviceToDevice, s));
+                    GTTS_CHECK_CUDA(cudaMemcpyAsync(dbf, tmp + 64, 4, cudaMemcpyDeviceToDevice, s));
+                    return 0;
+                });
+                pl->kernels_per_step += 3;
+                release(part, true);
+            }
             release(ghf);
             add_bconv("dgrad3", geom_3x3(B, H[0], W[0], 64, 0, 64, 1), g_rawf, P->bfinal, nullptr, gin);
             release(g_rawf);
@@ -1203,14 +1382,14 @@ struct PlanBuilder {
 };
 
 
-int plan_create(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, bool vjp, Plan** out) {
+int plan_create(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, bool vjp, bool pgrads, Plan** out) {
     if (int rc = pack_weights(d, kind)) return rc;
     if (vjp) { if (int rc = pack_backward_weights(d, kind)) return rc; }
     std::unique_ptr<Plan> pl(new Plan());
     pl->d = d; pl->kind = kind; pl->strict = (kind == ACT_F32); pl->B = B; pl->T = T;
-    pl->est_mode = est_mode; pl->sde = sde; pl->vjp = vjp;
+    pl->est_mode = est_mode; pl->sde = sde; pl->vjp = vjp; pl->pgrads = pgrads;
     PlanBuilder pb;
-    pb.vjp = vjp;
+    pb.vjp = vjp; pb.pgrads = pgrads;
     pb.pl = pl.get(); pb.d = d; pb.P = d->packed[kind].get(); pb.kind = kind; pb.strict = pl->strict;
     pb.B = B; pb.T = T;
     int rc = pb.build();
@@ -1273,9 +1452,10 @@ void drop_plans(Decoder* d, bool drop_pool) {
     if (drop_pool) d->pool.clear();
 }
 
-int get_plan(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, cudaStream_t stream, Plan** out, bool vjp = false) {
+int get_plan(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, cudaStream_t stream, Plan** out, bool vjp = false,
+             bool pgrads = false) {
     std::string key = std::to_string((int)kind) + ":" + std::to_string(B) + ":" + std::to_string(T) + ":" +
-                      (est_mode ? "e" : "s") + (sde ? "n" : "o") + (vjp ? "v" : "-") + (d->use_graph ? "g" : "x") +
+                      (est_mode ? "e" : "s") + (sde ? "n" : "o") + (vjp ? (pgrads ? "p" : "v") : "-") + (d->use_graph ? "g" : "x") +
                       std::to_string(d->conv_impl_bf16) + std::to_string(d->halo_mode) + std::to_string(d->fused_attn) + std::to_string(d->fuse_gn) +
                       std::to_string(d->fuse_epi) + "." + std::to_string(d->fuse_epi_max_b) + "." + std::to_string(d->fp32_tc) + std::to_string(d->fuse_async);
     auto it = d->plans.find(key);
@@ -1297,11 +1477,11 @@ int get_plan(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, cu
         d->plans.erase(lru);
     }
     Plan* pl = nullptr;
-    int rc = plan_create(d, kind, B, T, est_mode, sde, vjp, &pl);
+    int rc = plan_create(d, kind, B, T, est_mode, sde, vjp, pgrads, &pl);
     if (rc == 4) {
         // out of device memory: give back everything this handle caches (all plans and the whole pool) and try once more
         drop_plans(d, true);
-        rc = plan_create(d, kind, B, T, est_mode, sde, vjp, &pl);
+        rc = plan_create(d, kind, B, T, est_mode, sde, vjp, pgrads, &pl);
     }
     if (rc) return rc;
     d->plans_created++;
@@ -1442,6 +1622,58 @@ int decoder_estimator_vjp(Decoder* d, const float* x, const float* mask, const f
         d->launches_last_call += pl->kernels_per_step + 4;
     }
     GTTS_CHECK_CUDA(cudaGetLastError());
+    return leave_call(d, stream);
+}
+
+// Full backward of one estimator call (training): score, J^T v w.r.t. x AND mu, the per-pixel gradient of the speaker plane, the gradient
+// of the 1792 per-block time biases, and the gradient of every convolution / GroupNorm / attention parameter (kept in the handle, fetched
+// with decoder_get_param_grad).  Chunks of at most 16 samples; the parameter gradients are summed over the chunks.
+int decoder_estimator_backward(Decoder* d, const float* x, const float* mask, const float* mu, const float* t, const float* spk,
+                               const float* v, float* out_score, float* out_gx, float* out_gmu, float* out_gs_pix, float* out_gtb, int B,
+                               int T, int flags, cudaStream_t stream) {
+    if (int rc = common_checks(d, B, T, spk)) return rc;
+    if (int rc = enter_call(d, stream)) return rc;
+    const ActKind kind = (flags & 1) ? ACT_F32 : ACT_BF16;
+    const size_t plane = (size_t)d->n_feats * T;
+    const int chunk = std::min(d->max_chunk, 16);
+    d->launches_last_call = 0;
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int Bc = std::min(chunk, B - b0);
+        Plan* pl = nullptr;
+        if (int rc = get_plan(d, kind, Bc, T, true, false, stream, &pl, true, true)) return rc;
+        if (!d->pg_accum) {
+            GTTS_CHECK_CUDA(cudaMalloc(&d->pg_accum, d->pg_floats * 4));
+        }
+        Packed* P = d->packed[kind].get();
+        if (int rc = build_level_masks(mask + (size_t)b0 * T, pl->m0, pl->m1, pl->m2, Bc, T, stream)) return rc;
+        GTTS_CHECK_CUDA(cudaMemcpyAsync(pl->mu, mu + b0 * plane, Bc * plane * 4, cudaMemcpyDeviceToDevice, stream));
+        GTTS_CHECK_CUDA(cudaMemcpyAsync(pl->xt, x + b0 * plane, Bc * plane * 4, cudaMemcpyDeviceToDevice, stream));
+        GTTS_CHECK_CUDA(cudaMemcpyAsync(pl->vin, v + b0 * plane, Bc * plane * 4, cudaMemcpyDeviceToDevice, stream));
+        GTTS_CHECK_CUDA(cudaMemcpyAsync(pl->t_per_sample, t + b0, Bc * 4, cudaMemcpyDeviceToDevice, stream));
+        if (d->n_spks_mode == 1)
+            if (int rc = spk_mlp(spk + (size_t)b0 * 64, P->spk_w0t, P->spk_b0, P->spk_w2t, P->spk_b2, pl->splane, Bc,
+                                 d->n_feats, pl->strict, stream)) return rc;
+        GTTS_CHECK_CUDA(cudaMemsetAsync(pl->step, 0, 4, stream));
+        if (int rc = plan_step(pl, stream)) return rc;
+        if (out_score) GTTS_CHECK_CUDA(cudaMemcpyAsync(out_score + b0 * plane, pl->score, Bc * plane * 4, cudaMemcpyDeviceToDevice, stream));
+        GTTS_CHECK_CUDA(cudaMemcpyAsync(out_gx + b0 * plane, pl->gx, Bc * plane * 4, cudaMemcpyDeviceToDevice, stream));
+        if (out_gmu) GTTS_CHECK_CUDA(cudaMemcpyAsync(out_gmu + b0 * plane, pl->gmu, Bc * plane * 4, cudaMemcpyDeviceToDevice, stream));
+        if (out_gs_pix) GTTS_CHECK_CUDA(cudaMemcpyAsync(out_gs_pix + b0 * plane, pl->gs_pix, Bc * plane * 4, cudaMemcpyDeviceToDevice, stream));
+        if (out_gtb) GTTS_CHECK_CUDA(cudaMemcpyAsync(out_gtb + (size_t)b0 * 1792, pl->gtb, (size_t)Bc * 1792 * 4, cudaMemcpyDeviceToDevice, stream));
+        if (int rc = accumulate_floats(d->pg_accum, pl->pg_flat, d->pg_floats, b0 > 0 ? 1 : 0, stream)) return rc;
+        d->launches_last_call += pl->kernels_per_step + 8;
+    }
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return leave_call(d, stream);
+}
+
+int decoder_get_param_grad(Decoder* d, const char* name, float* dst, size_t numel, cudaStream_t stream) {
+    GTTS_REQUIRE(d != nullptr && name != nullptr && dst != nullptr, "null argument");
+    auto it = d->pg_layout.find(name);
+    GTTS_REQUIRE(it != d->pg_layout.end(), "get_param_grad: this parameter has no device-side gradient (time / speaker MLPs go through the time-bias and speaker-plane gradients)");
+    GTTS_REQUIRE(it->second.second == numel && d->pg_accum != nullptr, "get_param_grad: wrong size, or no backward call yet");
+    if (int rc = enter_call(d, stream)) return rc;
+    GTTS_CHECK_CUDA(cudaMemcpyAsync(dst, d->pg_accum + it->second.first, numel * 4, cudaMemcpyDeviceToDevice, stream));
     return leave_call(d, stream);
 }
 

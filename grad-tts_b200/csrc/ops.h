@@ -215,15 +215,18 @@ struct GnBwdArgs {
 int gn_bwd_blocks(int H, int W);
 int gn_bwd(ActKind act, const GnBwdArgs& a, cudaStream_t s);
 int final_bwd(ActKind act, const float* v, const float* wf, const float* mask, void* ghf, int B, int H, int W, cudaStream_t s);
+// gradient planes of the network input: gx (x channel) always; gmu (mu channel) and gs (speaker channel, per pixel; the caller sums it
+// over frames) when non-null
 int first_bwd(ActKind act, const void* graw1, const void* gres, const float* w1t, const float* wres, const float* mask, float* gx,
-              int B, int H, int W, int cin, cudaStream_t s);
+              float* gmu, float* gs, int B, int H, int W, int cin, cudaStream_t s);
 int mask_mul(ActKind act, const void* in, const float* mask, void* out, int B, int H, int W, int C, cudaStream_t s);
 int add_tensors(ActKind act, const void* a, const void* b, void* out, size_t numel, cudaStream_t s);
 // g_ctx = sum_n q go^T per (sample, head) (partials [B][4][chunks][1024]) and sdot[b][h][d] = sum_e g_ctx[d][e] ctxn[d][e]
 int attn_outer(ActKind act, const void* q, const void* go, float* partials, const float* ctxn, float* gctx, float* sdot, int B, int n,
                int chunks, int chunk_len, cudaStream_t s);
+// q / ao optional: ao[b][n][128] = attention output before to_out (for its weight gradient)
 int attn_pos_bwd(ActKind act, const void* kv, const void* go, const float* ctxn, const float* gctx, const float* ml, const float* sdot,
-                 void* gq, void* gkv, int B, int n, cudaStream_t s);
+                 void* gq, void* gkv, int B, int n, const void* q, void* ao, cudaStream_t s);
 int pack_dgrad3(ActKind wkind, const float* w_oihw, void* out, int Cout, int Cin, int ci_off, int Cn, cudaStream_t s);
 int pack_t1(ActKind wkind, const float* w_oi, void* out, int Cout, int Cin, int ci_off, int Cn, float scale, cudaStream_t s);
 int pack_down_dgrad(ActKind wkind, const float* w_oihw, void* out, int C, cudaStream_t s);
@@ -233,6 +236,25 @@ int pack_up_dgrad(ActKind wkind, const float* w_iohw, void* out, int C, cudaStre
 int split_f32_planes(const float* in, void* out, size_t npix, int C, cudaStream_t s);
 // packed fp32 weight rows [rows][K] -> bf16 [rows][6K] = [wl | wm | wm | wh | wh | wh]
 int split_pack_weights(const float* w, void* out, size_t rows, int K, cudaStream_t s);
+
+// ---- parameter gradients (backward_params.cu): reductions of the activation gradients against the saved forward tensors
+size_t wgrad_partial_floats(const ConvGeom& g, int* slices_out);
+// dW of any conv geometry; dst in the PyTorch layout: kind 0 = Conv2d (Cout, Cin, kh, kw) (also 1x1), 1 = ConvTranspose2d (Cin, Cout, 4, 4),
+// 2 = packed rows [n_pt * Cout][Cin] as is
+int conv_wgrad(ActKind act, const ConvGeom& g, const void* gout, const void* x0, const void* x1, float* partial, float* dst, int kind,
+               float scale, int accumulate, cudaStream_t s);
+int col_sums(ActKind act, const void* gsrc, float* partial, float* dst, long npix, int C, float scale, int accumulate, cudaStream_t s);
+int col_sums_per_sample(ActKind act, const void* gsrc, const float* mask, float* partial, float* dst, int B, int H, int W, int C, int dst_ld,
+                        cudaStream_t s);
+int gn_param_grad(ActKind act, const GnBwdArgs& a, float* partial, float* dgamma, float* dbeta, cudaStream_t s);
+int attn_out_grads(const float* A, const float* sv, const float* wout, const float* bout, float g, float* dwout, float* dbout, float* dg,
+                   int C, cudaStream_t s);
+int accumulate_floats(float* dst, const float* src, size_t n, int accumulate, cudaStream_t s);
+int final_param_grad(ActKind act, const void* rawf, const float* stats, const float* gamma, const float* beta, const float* v,
+                     const float* mask, float* partial, float* dwf_dbf, int B, int H, int W, int accumulate, cudaStream_t s);
+int first_param_blocks(int H, int W);
+int first_param_grad(ActKind act, const void* graw1, const void* gres, const float* mu, const float* x, const float* splane,
+                     const float* mask, float* partial, float* dst, int B, int H, int W, int cin, int accumulate, cudaStream_t s);
 
 // weight packing helpers (device side, fp32 source in PyTorch layout)
 int pack_conv_weight(ActKind wkind, const float* w_oihw, void* packed, int Cout, int Cin, int kh, int kw,

@@ -51,6 +51,63 @@ def _default_init(name, shape):
 _default_init.last_fan_in = 1
 
 
+_RESNET_ORDER = ("downs.0.0", "downs.0.1", "downs.1.0", "downs.1.1", "downs.2.0", "downs.2.1",
+                 "mid_block1", "mid_block2", "ups.0.0", "ups.0.1", "ups.1.0", "ups.1.1")      # rows of the 1792 time biases
+
+
+def _mish(x):
+    return x * torch.tanh(torch.nn.functional.softplus(x))
+
+
+def _is_host_side(name):
+    """Parameters whose gradients PyTorch computes on the host side of the op (tiny MLPs): time MLP, per-block Linear, spk_mlp."""
+    return ".mlp." in name or name.startswith("mlp.") or name.startswith("spk_mlp.")
+
+
+class _EstimatorTrainFn(torch.autograd.Function):
+    """Training-mode estimator call: forward = gtts_decoder_estimator, backward = gtts_decoder_estimator_backward.
+
+    Inputs after the module: x, mask, mu, t, spk (raw), tb (B,1792) and splane (B,80)|None -- the per-block time biases and the
+    speaker plane recomputed with PyTorch ops ONLY to tie the tiny time / speaker MLPs into the autograd graph (the device code
+    computes its own copies for the forward value) -- then every convolution / GroupNorm / attention parameter."""
+
+    @staticmethod
+    def forward(ctx, est, x, mask, mu, t, spk, tb, splane, *params):
+        h = est._get_handle()
+        ctx.est, ctx.flags = est, est._flags()
+        ctx.save_for_backward(x, mask, mu, t, *([spk] if spk is not None else []))
+        ctx.has_spk, ctx.has_splane = spk is not None, splane is not None
+        return torch.ops.gradtts_b200.estimator(int(h.value), x, mask, mu, t, spk, ctx.flags)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        est = ctx.est
+        saved = ctx.saved_tensors
+        x, mask, mu, t = saved[:4]
+        spk = saved[4] if ctx.has_spk else None
+        h = est._get_handle()
+        lib = _lib.load()
+        B, _, T = x.shape
+        g = g.contiguous().to(torch.float32)
+        gx, gmu, gs = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+        gtb = torch.empty(B, 1792, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            rc = lib.gtts_decoder_estimator_backward(h, x.data_ptr(), mask.data_ptr(), mu.data_ptr(), t.data_ptr(),
+                                                     spk.data_ptr() if spk is not None else None, g.data_ptr(), None, gx.data_ptr(),
+                                                     gmu.data_ptr(), gs.data_ptr(), gtb.data_ptr(), B, T, ctx.flags, stream)
+            _lib.check(rc, "estimator_backward")
+            pgrads = []
+            for name, p in est._device_params():
+                gp = torch.empty(p.shape, dtype=torch.float32, device=x.device)
+                rc = lib.gtts_decoder_get_param_grad(h, ("estimator." + name).encode(), gp.data_ptr(), gp.numel(), stream)
+                _lib.check(rc, f"get_param_grad({name})")
+                pgrads.append(gp.to(p.dtype))
+        gsplane = gs.sum(-1) if ctx.has_splane else None
+        return (None, gx, None, gmu, None, None, gtb, gsplane, *pgrads)
+
+
 class GradLogPEstimator2d(BaseModule):
     """Score U-Net (reference model/diffusion.py:128-216). Parameters only; the maths lives in csrc/."""
 
@@ -173,13 +230,49 @@ class GradLogPEstimator2d(BaseModule):
         return B, T
 
     # ---- reference API -----------------------------------------------------------------------------
+    def _device_params(self):
+        """(name, parameter) of everything the device-side backward produces a gradient for, in a fixed order."""
+        return [(n, p) for n, p in self.named_parameters() if not _is_host_side(n)]
+
+    def _time_biases_torch(self, t):
+        """The 1792 per-block time biases with PyTorch ops (model/diffusion.py:113-125, 143-144, 64-65): only to give the
+        training backward an autograd path into the time MLP and the twelve Linear(64, C) layers."""
+        P = dict(self.named_parameters())
+        half = 32
+        emb = torch.exp(torch.arange(half, device=t.device).float() * -(math.log(10000) / (half - 1)))
+        emb = self.pe_scale * t.unsqueeze(1) * emb.unsqueeze(0)
+        temb = torch.cat((emb.sin(), emb.cos()), dim=-1)
+        temb = torch.nn.functional.linear(temb, P["mlp.0.weight"], P["mlp.0.bias"])
+        temb = torch.nn.functional.linear(_mish(temb), P["mlp.2.weight"], P["mlp.2.bias"])
+        a = _mish(temb)
+        return torch.cat([torch.nn.functional.linear(a, P[r + ".mlp.1.weight"], P[r + ".mlp.1.bias"]) for r in _RESNET_ORDER], dim=1)
+
+    def _spk_plane_torch(self, spk):
+        P = dict(self.named_parameters())                 # model/diffusion.py:139-141, 176
+        s = torch.nn.functional.linear(spk, P["spk_mlp.0.weight"], P["spk_mlp.0.bias"])
+        return torch.nn.functional.linear(_mish(s), P["spk_mlp.2.weight"], P["spk_mlp.2.bias"])
+
     def forward(self, x, mask, mu, t, spk=None):
         """Score estimate, reference model/diffusion.py:174-216. x, mu: (B,80,T); mask: (B,1,T); t: (B,).
 
-        Differentiable w.r.t. `x` (torch.autograd.grad(sum(est(x) * eps), x) works, as the reference's likelihood code does it,
-        n_best/likelihood/likelihood.py:30-34); gradients w.r.t. the parameters / mu / t are not built."""
+        Autograd: in training mode (`module.train()`, gradients enabled) the call is differentiable w.r.t. x, mu, spk and EVERY
+        parameter (gtts_decoder_estimator_backward: data gradients on the tensor cores, weight gradients as fp32 reductions; the tiny
+        time / speaker MLPs through PyTorch).  In eval mode it is differentiable w.r.t. `x` only
+        (torch.autograd.grad(sum(est(x) * eps), x) as in the reference's likelihood code, n_best/likelihood/likelihood.py:30-34)."""
         h = self._get_handle()
         dev = next(self.parameters()).device
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            x_ = self._prep(x, "x", dev, keep_graph=True)
+            mu_ = self._prep(mu, "mu", dev, keep_graph=True)
+            mask_ = self._prep(mask, "mask", dev)
+            B, T = self._check_shapes(x_, mask_, mu_, spk)
+            t_ = self._prep(t, "t", dev).reshape(-1)
+            use_spk = spk is not None and self.n_spks > 1
+            spk_ = self._prep(spk, "spk", dev, keep_graph=True) if use_spk else None
+            tb = self._time_biases_torch(t_)
+            splane = self._spk_plane_torch(spk_) if use_spk else None
+            params = [p for _, p in self._device_params()]
+            return _EstimatorTrainFn.apply(self, x_, mask_, mu_, t_, spk_.detach() if use_spk else None, tb, splane, *params).to(x.dtype)
         track = torch.is_grad_enabled() and isinstance(x, torch.Tensor) and x.requires_grad
         x_ = self._prep(x, "x", dev, keep_graph=track)
         mask_, mu_ = (self._prep(v, n, dev) for v, n in ((mask, "mask"), (mu, "mu")))
@@ -333,13 +426,22 @@ class Diffusion(BaseModule):
         return xt.to(x0.dtype), zm.to(x0.dtype)
 
     def loss_t(self, x0, mask, mu, t, spk=None, noise=None):
-        """Forward value of model/diffusion.py:274-281 -> (loss, xt): forward diffusion, estimator, squared-error reduction,
-        all on the device.  There is no estimator backward yet: the returned loss carries no autograd
-        graph, so with gradients enabled this raises instead of silently training nothing."""
-        if torch.is_grad_enabled():
-            raise NotImplementedError("loss_t computes the forward value only (the estimator's PARAMETER gradients are not built; "
-                                      "only the gradient w.r.t. the input x is): call it under torch.no_grad(), e.g. for "
-                                      "validation loss; see DESIGN.md 'next' rows")
+        """model/diffusion.py:274-281 -> (loss, xt).  In training mode (`train()`, gradients enabled) the loss carries the autograd
+        graph: loss.backward() fills .grad of every estimator parameter and flows back into mu / spk.  Otherwise the forward value
+        is computed entirely on the device (forward diffusion, estimator, squared-error reduction kernels)."""
+        if torch.is_grad_enabled() and self.estimator.training:
+            # training: the elementwise parts (model/diffusion.py:244-252, 276-280) stay PyTorch ops so that autograd carries the loss
+            # back to mu (the text encoder) and into the estimator call, whose backward is gtts_decoder_estimator_backward
+            time = t.unsqueeze(-1).unsqueeze(-1)
+            cum_noise = get_noise(time, self.beta_min, self.beta_max, cumulative=True)
+            mean = x0 * torch.exp(-0.5 * cum_noise) + mu * (1.0 - torch.exp(-0.5 * cum_noise))
+            variance = 1.0 - torch.exp(-cum_noise)
+            z = noise if noise is not None else torch.randn(x0.shape, dtype=x0.dtype, device=x0.device, requires_grad=False)
+            xt = (mean + z * torch.sqrt(variance)) * mask
+            z = z * mask
+            noise_estimation = self.estimator(xt, mask, mu, t, spk) * torch.sqrt(1.0 - torch.exp(-cum_noise))
+            loss = torch.sum((noise_estimation + z) ** 2) / (torch.sum(mask) * self.n_feats)
+            return loss, xt
         dev, x_, mask_, mu_, t_, B, T = self._fd_args(x0, mask, mu, t)
         xt, zm = self.forward_diffusion(x_, mask_, mu_, t_, noise)
         est = self.estimator(xt, mask_, mu_, t_, spk)

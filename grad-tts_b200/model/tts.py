@@ -128,13 +128,11 @@ class GradTTS(BaseModule):
         return ScoreModel(), mu_y, spk, y_mask
 
     def compute_loss(self, x, x_lengths, y, y_lengths, spk=None, out_size=None):
-        """Forward VALUES of the three training losses (reference model/tts.py:110-194): duration loss against the MAS
-        durations, prior loss, diffusion loss.  The alignment stage, forward diffusion, estimator and loss reduction run as
-        sm_100a kernels.  The estimator backward is not built, so the losses carry no autograd graph for the decoder: this
-        raises when gradients are enabled (use it under torch.no_grad() for validation)."""
-        if torch.is_grad_enabled():
-            raise NotImplementedError("compute_loss returns forward values only (the estimator backward is not built): call "
-                                      "it under torch.no_grad(); see DESIGN.md 'next' rows")
+        """The three training losses (reference model/tts.py:110-194): duration loss against the MAS durations, prior loss,
+        diffusion loss.  The alignment stage (log-prior, MAS), the estimator forward and its backward run as sm_100a kernels.
+        In training mode with gradients enabled the losses carry the autograd graph (diffusion loss -> estimator parameters, mu_y ->
+        encoder; duration / prior losses -> encoder), so `sum(losses).backward()` trains the model like the reference's train.py."""
+        train = torch.is_grad_enabled() and self.training
         x, x_lengths, y, y_lengths = self.relocate_input([x, x_lengths, y, y_lengths])
         if self.n_spks > 1:
             spk = self.spk_emb(spk)                                                       # :130-136
@@ -161,7 +159,10 @@ class GradTTS(BaseModule):
                 y_mask = torch.nn.functional.pad(y_mask, (0, out_size - y_mask.shape[-1]))
             attn, y = attn_cut, y_cut
 
-        mu_y = align.mu_y_from_path(attn, mu_x)                                           # :184-185
+        if train:                                                                         # :184-185 (autograd into the encoder)
+            mu_y = torch.matmul(attn.transpose(1, 2), mu_x.transpose(1, 2)).transpose(1, 2)
+        else:
+            mu_y = align.mu_y_from_path(attn, mu_x)
         diff_loss, _ = self.decoder.compute_loss(y, y_mask, mu_y, spk)                    # :188
         prior_loss = torch.sum(0.5 * ((y - mu_y) ** 2 + math.log(2 * math.pi)) * y_mask)  # :191-192
         prior_loss = prior_loss / (torch.sum(y_mask) * self.n_feats)

@@ -115,6 +115,20 @@ int gtts_decoder_estimator(gtts_decoder* d, const float* x, const float* mask, c
  * probability-flow likelihood (reference n_best/likelihood/likelihood.py:27-38).  Parameter gradients are not computed. */
 int gtts_decoder_estimator_vjp(gtts_decoder* d, const float* x, const float* mask, const float* mu, const float* t, const float* spk,
                                const float* v, float* out_score, float* out_gx, int B, int T, int flags, void* stream);
+/* Full backward of one estimator call (what loss.backward() does to GradLogPEstimator2d in the reference's training step,
+ * model/diffusion.py:274-281 reached from train*.py): given the cotangent v of the score,
+ *   out_gx, out_gmu  [B][80][T]   gradients w.r.t. the x and mu input planes
+ *   out_gs_pix       [B][80][T]   per-pixel gradient of the speaker plane (sum it over T for d/d spk_mlp output; zeros unless n_spks > 1)
+ *   out_gtb          [B][1792]    gradient of the 12 per-ResnetBlock time biases (rows in the order of the reference's ModuleList walk:
+ *                                 downs.0.0, downs.0.1, downs.1.0, ..., mid_block1, mid_block2, ups.0.0, ..., ups.1.1)
+ * and, kept in the handle until the next call, the gradient of every Conv2d / ConvTranspose2d / GroupNorm / Rezero parameter of the
+ * estimator in its PyTorch layout, summed over the batch: fetch each with gtts_decoder_get_param_grad (name = state_dict key, e.g.
+ * "estimator.downs.0.1.block2.block.0.weight").  The time MLP, the per-block Linear(64, C) and spk_mlp are differentiated by the host
+ * (PyTorch) from out_gtb / out_gs_pix.  out_score, out_gmu, out_gs_pix, out_gtb may be NULL. */
+int gtts_decoder_estimator_backward(gtts_decoder* d, const float* x, const float* mask, const float* mu, const float* t, const float* spk,
+                                    const float* v, float* out_score, float* out_gx, float* out_gmu, float* out_gs_pix, float* out_gtb,
+                                    int B, int T, int flags, void* stream);
+int gtts_decoder_get_param_grad(gtts_decoder* d, const char* name, float* dst, size_t numel, void* stream);
 /* Host-buffer variant of reverse_diffusion: copies inputs H2D, runs, copies the mel D2H, synchronises. */
 int gtts_decoder_reverse_diffusion_host(gtts_decoder* d, const float* z_host, const float* mask_host,
                                         const float* mu_host, const float* spk_host, float* out_host, int B, int T,

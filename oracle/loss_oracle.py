@@ -36,3 +36,17 @@ def loss_t(sd, x0, mask, mu, t, noise, spk=None, n_spks=1, beta_min=0.05, beta_m
     xt, zm = forward_diffusion(x0, mask, mu, t, noise, beta_min, beta_max)
     est = decoder_oracle.estimator_forward(sd, xt, mask, mu, t, spk, n_spks, pe_scale)
     return score_loss(est, zm, mask, t, x0.shape[1], beta_min, beta_max), xt
+
+
+def loss_t_grads(sd, x0, mask, mu, t, noise, spk=None, n_spks=1):
+    """loss_t with torch.autograd: (loss, {name: d loss / d parameter}, d loss / d mu, d loss / d spk) -- what loss.backward() leaves in
+    .grad in the reference's training step (train.py -> GradTTS.compute_loss -> Diffusion.compute_loss -> loss_t)."""
+    with torch.enable_grad():
+        sdg = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+        mug = mu.detach().clone().requires_grad_(True)
+        spkg = spk.detach().clone().requires_grad_(True) if spk is not None else None
+        loss, _ = loss_t(sdg, x0, mask, mug, t, noise, spkg, n_spks)
+        names = [k for k in sdg]
+        grads = torch.autograd.grad(loss, [sdg[k] for k in names] + [mug] + ([spkg] if spkg is not None else []), allow_unused=True)
+    out = {k: (g if g is not None else torch.zeros_like(sd[k])) for k, g in zip(names, grads[:len(names)])}
+    return loss.detach(), out, grads[len(names)], (grads[len(names) + 1] if spkg is not None else None)

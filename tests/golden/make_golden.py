@@ -166,6 +166,53 @@ def make_vjp_vectors():
         print(name, "gx absmax", float(gx.abs().max()), "score absmax", float(score.abs().max()))
 
 
+def make_train_grad_vectors():
+    """loss.backward() through the REAL reference Diffusion.loss_t (model/diffusion.py:274-281) in train mode: the loss, a digest of
+    every parameter gradient (sum, sum of absolute values, the first 16 entries) and the full gradient of a few tensors, d loss / d mu."""
+    from model.diffusion import Diffusion
+    for name, n_spks, B, T, wseed, iseed in [("grad_spk1_b2_t48", 1, 2, 48, 0, 71), ("grad_spk247_b2_t40", 247, 2, 40, 3, 72)]:
+        sd = synth.make_decoder_state_dict(n_spks, seed=wseed, g=0.05)
+        dec = Diffusion(80, 64, n_spks, 64, 0.05, 20.0, 1000).train()
+        dec.load_state_dict(sd, strict=True)
+        x0, mask, mu, spk, _ = synth.make_inputs(B, T, n_spks, seed=iseed, ragged=True)
+        gen = torch.Generator().manual_seed(iseed + 100)
+        t = torch.rand(B, generator=gen).clamp(1e-5, 1 - 1e-5)
+        cap = {}
+        orig_fd = dec.forward_diffusion
+
+        def fd(*a):
+            xt, zm = orig_fd(*a)
+            cap["zm"] = zm.clone()
+            return xt, zm
+
+        dec.forward_diffusion = fd
+        mu_g = mu.clone().requires_grad_(True)
+        spk_g = spk.clone().requires_grad_(True) if spk is not None else None
+        torch.manual_seed(iseed + 200)
+        loss, _ = dec.loss_t(x0, mask, mu_g, t, spk_g)
+        loss.backward()
+        out = dict(x0=x0.numpy(), mask=mask.numpy(), mu=mu.numpy(), t=t.numpy(), zm=cap["zm"].detach().numpy(), loss=np.float32(loss.item()),
+                   gmu=mu_g.grad.numpy(), n_spks=np.int64(n_spks), wseed=np.int64(wseed), sd_sha256=np.array(sd_digest(sd)))
+        if spk is not None:
+            out["spk"] = spk.numpy()
+            out["gspk"] = spk_g.grad.numpy()
+        names, dig = [], []
+        for k, p in dec.state_dict(keep_vars=True).items():
+            g = p.grad if p.grad is not None else torch.zeros_like(p)
+            names.append(k)
+            flat = g.reshape(-1)
+            head = torch.zeros(16)
+            head[: min(16, flat.numel())] = flat[:16]
+            dig.append(torch.cat([flat.double().sum().float().reshape(1), flat.abs().double().sum().float().reshape(1), head]))
+        out["grad_names"] = np.array(names)
+        out["grad_digest"] = torch.stack(dig).numpy()
+        for k in ("estimator.downs.1.0.block1.block.0.weight", "estimator.mid_attn.fn.fn.to_qkv.weight", "estimator.ups.1.3.conv.weight",
+                  "estimator.downs.0.0.block1.block.0.weight", "estimator.mlp.0.weight", "estimator.final_conv.weight"):
+            out["full:" + k] = dict(dec.named_parameters())[k].grad.numpy()
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+        print(name, "loss", float(loss), "params", len(names))
+
+
 def make_likelihood_vectors():
     """The reference's probability-flow likelihood (n_best/likelihood/likelihood.py get_likelihood_fn with euler > 0, SPEECHSDE from
     sde_lib.py) driven exactly as n_best/get_score_parallel.py:77-83 does, on the real reference estimator with seeded weights."""
@@ -205,12 +252,15 @@ def main():
     if sys.argv[1:] == ["vjp"]:
         make_vjp_vectors()
         return make_likelihood_vectors()
+    if sys.argv[1:] == ["grad"]:
+        return make_train_grad_vectors()
     only = set(sys.argv[1:])                                   # optional: names of decoder cases to (re)generate
     make_baseline_shape_vectors(only)
     if not only:
         make_loss_vectors()
         make_vjp_vectors()
         make_likelihood_vectors()
+        make_train_grad_vectors()
     from model.diffusion import Diffusion
     from model.monotonic_align import maximum_path
 

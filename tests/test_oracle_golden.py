@@ -150,3 +150,31 @@ def test_likelihood_oracle_matches_reference(synth):
     assert torch.allclose(dlogp, t("delta_logp"), rtol=1e-4, atol=1e-2)
     assert torch.allclose(prior, t("prior_logp"), rtol=1e-4, atol=1e-2)
     assert torch.allclose(bpd, t("bpd"), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("name", ["grad_spk1_b2_t48", "grad_spk247_b2_t40"])
+def test_training_gradient_oracle_matches_reference_backward(name, synth):
+    """oracle/loss_oracle.loss_t_grads (torch.autograd through the functional restatement) against loss.backward() through the REAL
+    reference modules: loss, d loss / d mu, a digest of every parameter gradient and the full gradient of six tensors."""
+    from oracle import loss_oracle
+    torch.set_num_threads(8)
+    g = _load(name)
+    n_spks = int(g["n_spks"])
+    sd = synth.make_decoder_state_dict(n_spks, seed=int(g["wseed"]), g=0.05)
+    t = lambda k: torch.from_numpy(g[k])
+    spk = t("spk") if "spk" in g else None
+    loss, grads, gmu, gspk = loss_oracle.loss_t_grads(sd, t("x0"), t("mask"), t("mu"), t("t"), t("zm"), spk, n_spks)
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5
+    assert float((gmu - t("gmu")).abs().max()) <= 1e-6
+    if spk is not None:
+        assert float((gspk - t("gspk")).abs().max()) <= 1e-6
+    dig = t("grad_digest")
+    for i, k in enumerate([str(s) for s in g["grad_names"]]):
+        flat = grads[k].reshape(-1)
+        assert abs(float(flat.double().sum()) - float(dig[i, 0])) <= 1e-4 * max(1.0, float(dig[i, 1])), k
+        n = min(16, flat.numel())
+        assert float((flat[:n] - dig[i, 2:2 + n]).abs().max()) <= 2e-5 * max(1.0, float(flat.abs().max())), k
+    for k in g.files:
+        if k.startswith("full:"):
+            ref = t(k)
+            assert float((grads[k[5:]] - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max())), k
