@@ -14,5 +14,6 @@ from .model.diffusion import Diffusion, GradLogPEstimator2d  # noqa: F401
 from .model.monotonic_align import maximum_path  # noqa: F401
 from . import dist  # noqa: F401
 from . import likelihood  # noqa: F401
+from . import hifigan  # noqa: F401
 
-__all__ = ["GradTTS", "Diffusion", "GradLogPEstimator2d", "maximum_path", "synth", "dist", "likelihood"]
+__all__ = ["GradTTS", "Diffusion", "GradLogPEstimator2d", "maximum_path", "synth", "dist", "likelihood", "hifigan"]

@@ -36,6 +36,15 @@ SIGNATURES = {
     "gtts_decoder_profile_step": (_i, [_vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "gtts_decoder_launches_last_call": (_l, [_vp]),
     "gtts_decoder_cache_info": (_i, [_vp, _vp, _i]),
+    "gtts_vocoder_create": (_i, [_c.POINTER(_vp), _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i]),
+    "gtts_vocoder_destroy": (None, [_vp]),
+    "gtts_vocoder_set_param": (_i, [_vp, _cp, _vp, _sz]),
+    "gtts_vocoder_set_option": (_i, [_vp, _cp, _c.c_longlong]),
+    "gtts_vocoder_hop": (_i, [_vp]),
+    "gtts_vocoder_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "gtts_vocoder_forward_host": (_i, [_vp, _vp, _vp, _i, _i, _i]),
+    "gtts_vocoder_profile": (_i, [_vp, _i, _i, _i, _vp, _sz, _vp]),
+    "gtts_vocoder_launches_last_call": (_l, [_vp]),
     "gtts_align_log_prior": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "gtts_align_outputs": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "gtts_score_loss_workspace_bytes": (_sz, []),

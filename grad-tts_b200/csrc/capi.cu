@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "decoder_api.h"
 #include "ops.h"
+#include "vocoder_api.h"
 #include <vector>
 
 namespace gtts {
@@ -28,6 +29,13 @@ struct gtts_decoder {
     // staging for the host-buffer entry point
     float *z = nullptr, *mask = nullptr, *mu = nullptr, *spk = nullptr, *out = nullptr;
     size_t cap_plane = 0, cap_mask = 0, cap_spk = 0;
+    cudaStream_t stream = nullptr;
+};
+
+struct gtts_vocoder {
+    Vocoder* impl;
+    float *mel = nullptr, *audio = nullptr;          // staging for the host-buffer entry point
+    size_t cap_mel = 0, cap_audio = 0;
     cudaStream_t stream = nullptr;
 };
 
@@ -523,5 +531,80 @@ int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, i
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ vocoder
+int gtts_vocoder_create(gtts_vocoder** out, int resblock, int n_ups, const int* upsample_rates, const int* upsample_kernel_sizes,
+                        int upsample_initial_channel, int n_rb, const int* resblock_kernel_sizes, const int* resblock_dilation_sizes,
+                        int n_dil, int num_mels, int device) {
+    GTTS_REQUIRE(out != nullptr, "null out pointer");
+    Vocoder* v = vocoder_new(resblock, n_ups, upsample_rates, upsample_kernel_sizes, upsample_initial_channel, n_rb, resblock_kernel_sizes,
+                             resblock_dilation_sizes, n_dil, num_mels, device);
+    if (!v) return 1;
+    gtts_vocoder* h = new gtts_vocoder();
+    h->impl = v;
+    *out = h;
+    return 0;
+}
+
+void gtts_vocoder_destroy(gtts_vocoder* h) {
+    if (!h) return;
+    cudaSetDevice(vocoder_device(h->impl));
+    cudaDeviceSynchronize();
+    cudaFree(h->mel); cudaFree(h->audio);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    vocoder_delete(h->impl);
+    delete h;
+}
+
+int gtts_vocoder_set_param(gtts_vocoder* h, const char* name, const float* data, size_t numel) {
+    GTTS_REQUIRE(h != nullptr, "null vocoder handle");
+    return vocoder_set_param(h->impl, name, data, numel);
+}
+
+int gtts_vocoder_set_option(gtts_vocoder* h, const char* key, long long value) {
+    GTTS_REQUIRE(h != nullptr, "null vocoder handle");
+    return vocoder_set_option(h->impl, key, value);
+}
+
+int gtts_vocoder_hop(const gtts_vocoder* h) { return h ? vocoder_total_upsampling(h->impl) : 0; }
+
+int gtts_vocoder_forward(gtts_vocoder* h, const float* mel, float* audio, int B, int T, int flags, void* stream) {
+    GTTS_REQUIRE(h && mel && audio, "vocoder_forward: null pointer");
+    return vocoder_forward(h->impl, mel, audio, B, T, flags, (cudaStream_t)stream);
+}
+
+int gtts_vocoder_forward_host(gtts_vocoder* h, const float* mel_host, float* audio_host, int B, int T, int flags) {
+    GTTS_REQUIRE(h && mel_host && audio_host, "vocoder_forward_host: null pointer");
+    GTTS_REQUIRE(B >= 1 && T >= 1, "vocoder_forward_host: bad batch or length");
+    GTTS_CHECK_CUDA(cudaSetDevice(vocoder_device(h->impl)));
+    if (!h->stream) GTTS_CHECK_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const size_t n_audio = (size_t)B * T * vocoder_total_upsampling(h->impl);
+    // the mel staging size depends on num_mels, which the caller's buffer layout fixes: (B, num_mels, T); num_mels = n_mel / (B*T)
+    // is not known here, so the handle keeps what vocoder_new was given
+    const size_t n_mel = (size_t)B * T * (size_t)vocoder_num_mels(h->impl);
+    if (n_mel > h->cap_mel) {
+        cudaFree(h->mel); h->mel = nullptr; h->cap_mel = 0;
+        GTTS_CHECK_CUDA(cudaMalloc(&h->mel, n_mel * 4));
+        h->cap_mel = n_mel;
+    }
+    if (n_audio > h->cap_audio) {
+        cudaFree(h->audio); h->audio = nullptr; h->cap_audio = 0;
+        GTTS_CHECK_CUDA(cudaMalloc(&h->audio, n_audio * 4));
+        h->cap_audio = n_audio;
+    }
+    cudaStream_t s = h->stream;
+    GTTS_CHECK_CUDA(cudaMemcpyAsync(h->mel, mel_host, n_mel * 4, cudaMemcpyHostToDevice, s));
+    if (int rc = vocoder_forward(h->impl, h->mel, h->audio, B, T, flags, s)) return rc;
+    GTTS_CHECK_CUDA(cudaMemcpyAsync(audio_host, h->audio, n_audio * 4, cudaMemcpyDeviceToHost, s));
+    GTTS_CHECK_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int gtts_vocoder_profile(gtts_vocoder* h, int B, int T, int flags, char* buf, size_t buflen, void* stream) {
+    GTTS_REQUIRE(h != nullptr, "null vocoder handle");
+    return vocoder_profile(h->impl, B, T, flags, buf, buflen, (cudaStream_t)stream);
+}
+
+long gtts_vocoder_launches_last_call(const gtts_vocoder* h) { return h ? vocoder_launches_last_call(h->impl) : 0; }
 
 }  // extern "C"

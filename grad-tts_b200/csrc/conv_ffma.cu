@@ -101,7 +101,9 @@ conv_ffma_kernel(ConvGeom g, const T* __restrict__ src0, const T* __restrict__ s
             ssq += v * v;
             if (res) v += Act<T>::ld(res + opix * g.Cout + co);
             if (e.mask) v *= m;
-            Act<T>::st(out + opix * g.Cout + co, v);
+            const float lv = v > 0.f ? v : v * e.act_slope;      // 1-D conv stacks (ConvEpilogue::act_out / out2)
+            Act<T>::st(out + opix * g.Cout + co, e.act_out ? lv : v);
+            if (e.out2) Act<T>::st(reinterpret_cast<T*>(e.out2) + opix * g.Cout + co, lv);
         }
     }
     if (e.gn_partials == nullptr) return;

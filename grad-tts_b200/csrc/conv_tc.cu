@@ -30,7 +30,7 @@ using namespace tc;
 namespace {
 
 // kStats: GroupNorm partial statistics of (acc + bias); kRes: + residual; kMask: * mask[b][w]
-template <int N, bool kStats, bool kRes, bool kMask, bool kOutF32 = false>
+template <int N, bool kStats, bool kRes, bool kMask, bool kOutF32 = false, bool kAct = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapWh, const TcParams p) {
@@ -163,7 +163,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     } else if (warp == 3) {
         tc_stats_loop<kStats>(p, sh, lane);
     } else if (warp >= 4) {
-        tc_epilogue_loop<N, kStats, kRes, kMask, kOutF32>(p, sh, tmem_base, warp, lane);
+        tc_epilogue_loop<N, kStats, kRes, kMask, kOutF32, kAct>(p, sh, tmem_base, warp, lane);
     }
     tc_teardown<N, kStats>(p, sh, smem, tmem_base, tid, warp, lane);
 }
@@ -287,6 +287,11 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
     const bool convT_halo = halo_mode == 2 && conv_tc_convT_halo_eligible(g) && e.mask && !e.residual && !e.gn_partials &&
                             num_sms >= 2 && !g.split;    // split convs: the ConvT halo variant keeps 2*nck A stages resident -- too many chunks
     if (g.split && (e.apply || e.in_stats)) { set_error("conv_tc: split (fp32) convs take the plain epilogues only"); return nullptr; }
+    if ((e.act_out || e.out2) && (e.out_f32 || e.mask || e.gn_partials || e.apply || e.in_stats || halo_mode && conv_tc_halo_eligible(g))) {
+        set_error("conv_tc: leaky-ReLU outputs are for the per-tap kernel with bf16 activations only");
+        return nullptr;
+    }
+    if (e.act_out && e.out2) { set_error("conv_tc: act_out and out2 are exclusive"); return nullptr; }
     if (g.split && 6 * (g.Cin0 + g.Cin1) / 64 > 48) { set_error("conv_tc: split conv with more than 48 K chunks"); return nullptr; }
     if (halo_mode && !convT_halo && !e.apply && (!conv_tc_halo_eligible(g) || e.residual || e.mask)) halo_mode = 0;
     // split convs know the CTA-pair halo kernel and the per-tap kernel only (the single-CTA halo kernel has no chunk table)
@@ -473,10 +478,10 @@ int conv_tc_plan_grid(const TcConvPlan* p) { return p->grid; }
 void conv_tc_plan_set_debug(TcConvPlan* p, unsigned long long* dbg_out) { p->p.dbg_out = dbg_out; }
 
 namespace {
-template <int N, bool kStats, bool kRes, bool kMask, bool kOutF32 = false>
+template <int N, bool kStats, bool kRes, bool kMask, bool kOutF32 = false, bool kAct = false>
 int launch_variant(const TcConvPlan* pl, cudaStream_t stream) {
     static bool attr_set = false;
-    auto k = conv_tc_kernel<N, kStats, kRes, kMask, kOutF32>;
+    auto k = conv_tc_kernel<N, kStats, kRes, kMask, kOutF32, kAct>;
     if (!attr_set) {
         GTTS_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
@@ -496,6 +501,10 @@ int launch_n(const TcConvPlan* pl, cudaStream_t stream) {
         if (rs) return launch_variant<N, false, true, false, true>(pl, stream);
         if (mk) return launch_variant<N, false, false, true, true>(pl, stream);
         return launch_variant<N, false, false, false, true>(pl, stream);
+    }
+    if (e.act_out || e.out2) {                         // 1-D conv stacks: leaky-ReLU output(s), optional residual
+        if (rs) return launch_variant<N, false, true, false, false, true>(pl, stream);
+        return launch_variant<N, false, false, false, false, true>(pl, stream);
     }
     if (st) return launch_variant<N, true, false, false>(pl, stream);
     if (rs && mk) return launch_variant<N, false, true, true>(pl, stream);

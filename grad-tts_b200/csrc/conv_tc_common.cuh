@@ -230,7 +230,7 @@ __device__ __forceinline__ void tc_stats_loop(const TcParams& p, const TcShared&
 // Epilogue warps (warps 4..19): TMEM -> registers -> (+bias, stats, +residual, *mask) -> bf16 NHWC stores.
 // Two groups of 8 warps take alternate tiles (group = tile iteration parity), so one group's TMEM reads, arithmetic
 // and stores overlap the other's; within a group two warps share each TMEM lane quarter and split the columns.
-template <int N, bool kStats, bool kRes, bool kMask, bool kOutF32 = false>
+template <int N, bool kStats, bool kRes, bool kMask, bool kOutF32 = false, bool kAct = false>
 __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShared& sh, uint32_t tmem_base, int warp,
                                                  int lane) {
     constexpr int kColsPerWarp = N / 2;            // two epilogue warps share each TMEM lane quarter
@@ -369,6 +369,28 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
                     for (int q = 0; q < 16; ++q) f[q] = fmul2(f[q], m2);
                 }
                 __nv_bfloat16* op = out + opix * N + cbase + c0;
+                if (kAct) {
+                    // leaky-ReLU outputs of the 1-D conv stacks (ConvEpilogue::act_out / out2)
+                    const float sl = e.act_slope;
+                    if (!e.act_out) {
+#pragma unroll
+                        for (int v8 = 0; v8 < 2; ++v8) {
+                            uint32_t w[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[v8 * 8 + k].x, f[v8 * 8 + k].y);
+                                w[k] = *reinterpret_cast<uint32_t*>(&h2);
+                            }
+                            st_global_256(op + v8 * 16, w);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        f[q].x = f[q].x > 0.f ? f[q].x : f[q].x * sl;
+                        f[q].y = f[q].y > 0.f ? f[q].y : f[q].y * sl;
+                    }
+                    if (!e.act_out) op = reinterpret_cast<__nv_bfloat16*>(e.out2) + opix * N + cbase + c0;
+                }
 #pragma unroll
                 for (int v8 = 0; v8 < 2; ++v8) {                     // one full 32-byte sector per store instruction
                     uint32_t w[8];

@@ -70,6 +70,12 @@ struct ConvEpilogue {
     const float* ap_beta;     // [Cout]
     const float* ap_tbias;    // [B or 1][Cout] added after Mish (stride ap_tb_bstride floats per sample; null = off)
     int ap_tb_bstride;
+    // Leaky-ReLU outputs of the 1-D conv stacks (HiFi-GAN generator, hifi-gan/models.py:38-45,104-113; per-tap tcgen05 kernel and
+    // conv_ffma only): with v = acc + bias (+ residual),  out = act_out ? lrelu(v) : v  and, when out2 is set,  out2 = lrelu(v)
+    // -- the next conv's input and the next residual come out of one epilogue.
+    float act_slope;
+    int act_out;
+    void* out2;
 };
 
 // CUDA-core implicit GEMM (fp32 accumulate, FFMA).  Strict-fp32 path and debugging cross-check.

@@ -128,3 +128,65 @@ def make_mas_inputs(B, t_x, t_y, seed=1234, ragged=True):
     ym = (torch.arange(t_y)[None, :] < ty[:, None]).float()
     mask = xm[:, :, None] * ym[:, None, :]
     return value.contiguous(), mask.contiguous(), tx, ty
+
+
+# ---------------------------------------------------------------------------------------------------------------- vocoder
+VOCODER_CONFIGS = {
+    # checkpts/hifigan-config.json (HiFi-GAN V1)
+    "v1": dict(resblock="1", upsample_rates=[8, 8, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4], upsample_initial_channel=512,
+               resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]]),
+    # a ResBlock2 stack (the shape family of the upstream V3 config): two dilations per block, stride-4 upsampling with kernel 8
+    "rb2": dict(resblock="2", upsample_rates=[8, 4, 4], upsample_kernel_sizes=[16, 8, 8], upsample_initial_channel=256,
+                resblock_kernel_sizes=[3, 5, 7], resblock_dilation_sizes=[[1, 2], [2, 6], [3, 12]]),
+}
+
+
+def vocoder_param_shapes(cfg):
+    """(module name, weight shape, transposed) for every conv of hifi-gan/models.py::Generator(h), in state_dict order."""
+    c0 = cfg["upsample_initial_channel"]
+    s = [("conv_pre", (c0, 80, 7), False)]
+    for i, k in enumerate(cfg["upsample_kernel_sizes"]):
+        s.append((f"ups.{i}", (c0 // 2 ** i, c0 // 2 ** (i + 1), k), True))
+    n = 0
+    ch = c0
+    for i in range(len(cfg["upsample_rates"])):
+        ch = c0 // 2 ** (i + 1)
+        for k, d in zip(cfg["resblock_kernel_sizes"], cfg["resblock_dilation_sizes"]):
+            groups = ("convs1", "convs2") if str(cfg["resblock"]) == "1" else ("convs",)
+            for grp in groups:
+                for m in range(len(d)):
+                    s.append((f"resblocks.{n}.{grp}.{m}", (ch, ch, k), False))
+            n += 1
+    s.append(("conv_post", (1, ch, 7), False))
+    return s
+
+
+def make_vocoder_state_dict(cfg, seed=0):
+    """Weight-normed state dict (`*.weight_g`, `*.weight_v`, `*.bias`) with gains that keep the activations O(1) through the
+    stack (the reference's own init, N(0, 0.01), gives a near-constant output -- useless as a test signal)."""
+    gen = torch.Generator().manual_seed(seed)
+    sd = {}
+    rates = cfg["upsample_rates"]
+    for name, shape, transposed in vocoder_param_shapes(cfg):
+        v = torch.randn(*shape, generator=gen)
+        if transposed:
+            u = rates[int(name.split(".")[1])]
+            gain = math.sqrt(u / 2.0)
+        elif name.startswith("resblocks"):
+            gain = 0.6
+        else:
+            gain = 1.2
+        g = gain * (1.0 + 0.2 * torch.randn(shape[0], 1, 1, generator=gen))
+        nb = shape[1] if transposed else shape[0]
+        sd[name + ".weight_g"] = g
+        sd[name + ".weight_v"] = v
+        sd[name + ".bias"] = 0.1 * torch.randn(nb, generator=gen)
+    return sd
+
+
+def make_mel(B, T, seed=1):
+    """A mel-like input: smooth in time, roughly the range of log-mel features."""
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, N_FEATS, T + 8, generator=gen)
+    x = torch.nn.functional.avg_pool1d(x, 5, stride=1, padding=2)[..., 4:4 + T]
+    return (2.0 * x - 1.0).contiguous()

@@ -14,6 +14,7 @@
  *   gtts_decoder_reverse_diffusion model/diffusion.py:254-272  Diffusion.forward / reverse_diffusion(z, mask, mu, n_timesteps, stoc, spk)
  *   gtts_decoder_estimator         model/diffusion.py:174-216  GradLogPEstimator2d.forward(x, mask, mu, t, spk)
  *   gtts_decoder_create/set_param  model/diffusion.py:128-172,227-242  module construction + load_state_dict
+ *   gtts_vocoder_create/set_param/forward  hifi-gan/models.py:77-118  Generator(h), load_state_dict + remove_weight_norm, forward(mel)
  */
 #ifndef GRADTTS_B200_H
 #define GRADTTS_B200_H
@@ -173,6 +174,29 @@ int gtts_test_attn_xk(const void* x_bf16, const void* wkv_bf16, float* partials,
  * {n_mma tcgen05.mma M128xNx16, n_commit tcgen05.commit}, optionally waiting on the last commit every round. */
 int gtts_test_issue_microbench(int N, int n_mma, int n_commit, int iters, int wait_each, int grid, double* issue_cycles,
                                double* total_cycles);
+
+/* ---- HiFi-GAN generator (vocoder; the step after the decoder, inference.py:73-76,97) ---------------------
+ * Configuration = the fields of checkpts/hifigan-config.json that hifi-gan/models.py:77-99 reads: resblock ("1" / "2"),
+ * upsample_rates / upsample_kernel_sizes (n_ups entries), upsample_initial_channel, resblock_kernel_sizes (n_rb <= 3 entries) and
+ * resblock_dilation_sizes (n_rb rows of n_dil entries, row-major).  Parameters are set by their reference state_dict key AFTER
+ * remove_weight_norm ("conv_pre.weight", "ups.0.bias", "resblocks.4.convs1.2.weight", "conv_post.bias", ...), fp32, PyTorch layout,
+ * host or device pointer.  forward: mel (B, num_mels, T) fp32 -> audio (B, 1, T * prod(upsample_rates)) fp32, as Generator.forward.
+ * flags: GTTS_FLAG_FP32 = fp32 activations and CUDA-core FFMA convs; default bf16 activations, tcgen05 convs, fp32 accumulation.
+ * Options: "max_chunk" (utterances per workspace chunk, default 32), "workspace_mb", "use_graph", "force_ffma". */
+typedef struct gtts_vocoder gtts_vocoder;
+int gtts_vocoder_create(gtts_vocoder** out, int resblock, int n_ups, const int* upsample_rates, const int* upsample_kernel_sizes,
+                        int upsample_initial_channel, int n_rb, const int* resblock_kernel_sizes, const int* resblock_dilation_sizes,
+                        int n_dil, int num_mels, int device);
+void gtts_vocoder_destroy(gtts_vocoder* v);
+int gtts_vocoder_set_param(gtts_vocoder* v, const char* name, const float* data, size_t numel);
+int gtts_vocoder_set_option(gtts_vocoder* v, const char* key, long long value);
+int gtts_vocoder_hop(const gtts_vocoder* v);                     /* output samples per mel frame */
+int gtts_vocoder_forward(gtts_vocoder* v, const float* mel, float* audio, int B, int T, int flags, void* stream);
+/* same with HOST buffers: H2D, forward, D2H, synchronised */
+int gtts_vocoder_forward_host(gtts_vocoder* v, const float* mel_host, float* audio_host, int B, int T, int flags);
+/* per-launch CUDA-event times of one forward of (min(B, max_chunk), T) as a text table */
+int gtts_vocoder_profile(gtts_vocoder* v, int B, int T, int flags, char* buf, size_t buflen, void* stream);
+long gtts_vocoder_launches_last_call(const gtts_vocoder* v);
 
 #ifdef __cplusplus
 }

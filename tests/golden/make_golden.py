@@ -244,8 +244,43 @@ def make_likelihood_vectors():
         print(name, "bpd", bpd.tolist(), "delta_logp", delta_logp.tolist())
 
 
+def vocoder_cases():
+    # name, config, B, T, weight seed, input seed
+    return [("voc_v1_b2_t24", "v1", 2, 24, 21, 22), ("voc_v1_b1_t100", "v1", 1, 100, 23, 24), ("voc_rb2_b2_t16", "rb2", 2, 16, 25, 26)]
+
+
+def make_vocoder_vectors():
+    """hifi-gan/models.py::Generator run as inference.py:73-76,97 does: load_state_dict, eval, remove_weight_norm, forward."""
+    import types
+    for name in ("matplotlib", "matplotlib.pylab"):             # hifi-gan/xutils.py imports matplotlib for its plot helper only
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.use = lambda *a, **k: None
+            sys.modules[name] = m
+    sys.modules["matplotlib"].pylab = sys.modules["matplotlib.pylab"]
+    sys.path.insert(0, "/root/reference/hifi-gan")
+    sys.dont_write_bytecode = True
+    from models import Generator
+    from env import AttrDict
+    for name, cfg_name, B, T, wseed, iseed in vocoder_cases():
+        cfg = synth.VOCODER_CONFIGS[cfg_name]
+        sd = synth.make_vocoder_state_dict(cfg, seed=wseed)
+        gen = Generator(AttrDict(cfg))
+        gen.load_state_dict(sd, strict=True)
+        gen.eval()
+        gen.remove_weight_norm()
+        mel = synth.make_mel(B, T, seed=iseed)
+        with torch.no_grad():
+            y = gen(mel)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), mel=mel.numpy(), y=y.numpy(), cfg=cfg_name,
+                            wseed=wseed, sd_digest=sd_digest(sd))
+        print(name, tuple(y.shape), float(y.abs().mean()), float(y.abs().max()))
+
+
 def main():
     torch.set_num_threads(8)
+    if sys.argv[1:] == ["voc"]:
+        return make_vocoder_vectors()
     import_reference()
     if sys.argv[1:] == ["loss"]:
         return make_loss_vectors()
@@ -257,6 +292,7 @@ def main():
     only = set(sys.argv[1:])                                   # optional: names of decoder cases to (re)generate
     make_baseline_shape_vectors(only)
     if not only:
+        make_vocoder_vectors()
         make_loss_vectors()
         make_vjp_vectors()
         make_likelihood_vectors()

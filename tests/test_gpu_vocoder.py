@@ -1,0 +1,127 @@
+"""GPU: the HiFi-GAN generator (csrc/vocoder.cu behind gtts_vocoder_*) against the golden vectors made by the reference's
+own hifi-gan/models.py::Generator, and against the oracle at larger sizes."""
+import ctypes
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+VOC = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "voc_*.npz")))
+
+# tolerances.  fp32 mode: fp32 FFMA convs against the reference's fp32 CPU convs, output in [-1, 1]: max-abs 2e-4.
+# bf16 mode: bf16 operands and activations, fp32 accumulation, ~50 convs deep with a residual stream: rel-rms 3e-2.
+FP32_MAX_ABS = 2e-4
+BF16_REL_RMS = 3e-2
+
+
+def _make(pkg, synth, cfg_name, wseed, weight_norm=True):
+    cfg = synth.VOCODER_CONFIGS[cfg_name]
+    sd = synth.make_vocoder_state_dict(cfg, seed=wseed)
+    gen = pkg.hifigan.Generator(pkg.hifigan.AttrDict(cfg))
+    gen.load_state_dict(sd, strict=True)
+    gen = gen.cuda().eval()
+    if not weight_norm:
+        gen.remove_weight_norm()
+    return gen, cfg, sd
+
+
+def _rel_rms(a, b):
+    return float(((a - b).pow(2).mean() / b.pow(2).mean()).sqrt())
+
+
+@pytest.mark.parametrize("name", VOC)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_vocoder_matches_reference_golden(name, precision, pkg, synth):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    gen, cfg, _ = _make(pkg, synth, str(g["cfg"]), int(g["wseed"]), weight_norm=False)
+    gen.precision = precision
+    y = gen(torch.from_numpy(g["mel"]).cuda()).cpu()
+    ref = torch.from_numpy(g["y"])
+    assert y.shape == ref.shape and torch.isfinite(y).all()
+    if precision == "fp32":
+        assert float((y - ref).abs().max()) <= FP32_MAX_ABS
+    else:
+        assert _rel_rms(y, ref) <= BF16_REL_RMS
+        assert gen.launches_last_call() > 0
+
+
+def test_vocoder_weight_norm_and_removed_weight_norm_agree(pkg, synth):
+    """inference.py:74-76 calls remove_weight_norm() after loading; forward before and after must give the same audio."""
+    gen, cfg, _ = _make(pkg, synth, "v1", 31, weight_norm=True)
+    mel = synth.make_mel(2, 12, seed=3).cuda()
+    y0 = gen(mel)
+    gen.remove_weight_norm()
+    y1 = gen(mel)
+    assert torch.equal(y0, y1)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_vocoder_chunking_is_bitwise_invariant(precision, pkg, synth):
+    gen, cfg, _ = _make(pkg, synth, "v1", 32)
+    gen.precision = precision
+    mel = synth.make_mel(3, 20, seed=4).cuda()
+    y_all = gen(mel)
+    gen.max_chunk = 2                                           # 2 + 1
+    y_chunks = gen(mel)
+    y_single = torch.cat([gen(mel[i:i + 1]) for i in range(3)])
+    assert torch.equal(y_all, y_chunks)
+    assert torch.equal(y_all, y_single)
+
+
+@pytest.mark.parametrize("T", [1, 3, 129])
+def test_vocoder_edge_lengths_against_oracle(T, pkg, synth):
+    """one frame, a length below every tile size, a length that straddles a 128-position tile at the first stage"""
+    from oracle import vocoder_oracle
+    gen, cfg, sd = _make(pkg, synth, "v1", 33)
+    mel = synth.make_mel(2, T, seed=5)
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        ref = vocoder_oracle.generator_forward(sd, cfg, mel)
+    gen.precision = "fp32"
+    y = gen(mel.cuda()).cpu()
+    assert y.shape == ref.shape
+    assert float((y - ref).abs().max()) <= FP32_MAX_ABS
+    gen.precision = "bf16"
+    y = gen(mel.cuda()).cpu()
+    assert _rel_rms(y, ref) <= BF16_REL_RMS
+
+
+def test_vocoder_tensor_core_and_ffma_bf16_paths_agree(pkg, synth):
+    """same bf16 operands through the tcgen05 kernels and through the CUDA-core kernel: only the accumulation order differs"""
+    gen, cfg, _ = _make(pkg, synth, "rb2", 34)
+    mel = synth.make_mel(2, 40, seed=6).cuda()
+    y_tc = gen(mel)
+    gen.set_option("force_ffma", 1)
+    y_ffma = gen(mel)
+    gen.set_option("force_ffma", 0)
+    assert _rel_rms(y_tc, y_ffma) <= 1e-2
+
+
+def test_vocoder_host_entry_point(pkg, synth):
+    gen, cfg, _ = _make(pkg, synth, "v1", 35)
+    mel = synth.make_mel(2, 16, seed=7)
+    y_dev = gen(mel.cuda()).cpu()
+    lib = pkg._lib.load()
+    out = torch.empty(2, 1, 16 * gen.hop)
+    rc = lib.gtts_vocoder_forward_host(gen._handle, mel.data_ptr(), out.data_ptr(), 2, 16, 0)
+    pkg._lib.check(rc, "vocoder_forward_host")
+    assert torch.equal(out, y_dev)
+
+
+def test_vocoder_rejects_bad_input(pkg, synth):
+    gen, cfg, _ = _make(pkg, synth, "v1", 36)
+    with pytest.raises(ValueError):
+        gen(torch.zeros(1, 79, 8, device="cuda"))
+    with pytest.raises(RuntimeError):
+        gen(torch.zeros(1, 80, 8))
+    lib = pkg._lib.load()
+    h = ctypes.c_void_p()
+    arr = lambda xs: (ctypes.c_int * len(xs))(*xs)               # noqa: E731
+    # upsample kernel smaller than its rate
+    assert lib.gtts_vocoder_create(ctypes.byref(h), 1, 1, arr([8]), arr([4]), 64, 1, arr([3]), arr([1]), 1, 80, 0) != 0

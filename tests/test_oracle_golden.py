@@ -178,3 +178,45 @@ def test_training_gradient_oracle_matches_reference_backward(name, synth):
         if k.startswith("full:"):
             ref = t(k)
             assert float((grads[k[5:]] - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max())), k
+
+
+VOC = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "voc_*.npz")))
+
+
+@pytest.mark.parametrize("name", VOC)
+def test_vocoder_oracle_matches_reference_generator(name, synth):
+    """oracle/vocoder_oracle.py vs the reference's hifi-gan Generator (weight-normed state dict loaded, remove_weight_norm, forward)."""
+    from oracle import vocoder_oracle
+    g = _load(name)
+    cfg = synth.VOCODER_CONFIGS[str(g["cfg"])]
+    sd = synth.make_vocoder_state_dict(cfg, seed=int(g["wseed"]))
+    import hashlib
+    h = hashlib.sha256()
+    for k in sd:
+        h.update(k.encode())
+        h.update(sd[k].numpy().tobytes())
+    assert h.hexdigest() == str(g["sd_digest"]), "synthetic vocoder weights differ from the ones the fixture was made with"
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        y = vocoder_oracle.generator_forward(sd, cfg, torch.from_numpy(g["mel"]))
+    assert y.shape == g["y"].shape
+    err = float((y - torch.from_numpy(g["y"])).abs().max())
+    assert err <= 2e-6, err                                     # tolerance: fp32 reassociation inside conv1d only
+
+
+def test_vocoder_module_has_the_reference_state_dict_layout(pkg, synth):
+    """Generator(h).state_dict() carries the reference's weight-norm keys and shapes (strict load of a reference-shaped dict),
+    and remove_weight_norm() leaves `weight` = g * v / ||v||."""
+    from oracle import vocoder_oracle
+    for cfg_name, cfg in synth.VOCODER_CONFIGS.items():
+        sd = synth.make_vocoder_state_dict(cfg, seed=5)
+        gen = pkg.hifigan.Generator(pkg.hifigan.AttrDict(cfg))
+        assert list(gen.state_dict().keys()) == list(sd.keys()), cfg_name
+        gen.load_state_dict(sd, strict=True)
+        gen.remove_weight_norm()
+        sd2 = gen.state_dict()
+        for name, shape, _ in synth.vocoder_param_shapes(cfg):
+            assert tuple(sd2[name + ".weight"].shape) == tuple(shape)
+            assert torch.allclose(sd2[name + ".weight"], vocoder_oracle.effective_weight(sd, name), atol=1e-7)
+    with pytest.raises(RuntimeError):
+        gen.forward(torch.zeros(1, 80, 8))                       # CPU tensors: no fallback

@@ -292,11 +292,50 @@ def stage_profile():
             print(f"   {o['name']:28s} {o['ms'] * 1e3:9.1f} us  {tf:8.1f} TFLOP/s  {gb:8.0f} GB/s(alg)")
 
 
+def stage_vocoder():
+    """HiFi-GAN generator: error against the goldens in both precisions, per-launch profile and whole-forward time"""
+    import glob
+    import numpy as np
+    synth = pkg.synth
+    for path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "voc_*.npz"))):
+        g = np.load(path)
+        cfg = synth.VOCODER_CONFIGS[str(g["cfg"])]
+        gen = pkg.hifigan.Generator(pkg.hifigan.AttrDict(cfg))
+        gen.load_state_dict(synth.make_vocoder_state_dict(cfg, seed=int(g["wseed"])))
+        gen = gen.to(DEV).eval()
+        ref = torch.from_numpy(g["y"])
+        for prec in ("fp32", "bf16"):
+            gen.precision = prec
+            y = gen(torch.from_numpy(g["mel"]).to(DEV)).cpu()
+            print(f"{os.path.basename(path)} {prec}: max-abs {float((y - ref).abs().max()):.3e} rel-rms "
+                  f"{float(((y - ref).pow(2).mean() / ref.pow(2).mean()).sqrt()):.3e} finite {bool(torch.isfinite(y).all())}", flush=True)
+    cfg = synth.VOCODER_CONFIGS["v1"]
+    gen = pkg.hifigan.Generator(pkg.hifigan.AttrDict(cfg))
+    gen.load_state_dict(synth.make_vocoder_state_dict(cfg, seed=1))
+    gen = gen.to(DEV).eval()
+    for (B, T) in [(16, 1720), (1, 400)]:
+        gen.max_chunk = B
+        mel = synth.make_mel(B, T, seed=2).to(DEV)
+        for _ in range(2):
+            y = gen(mel)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            y = gen(mel)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        print(f"--- vocoder forward B={B} T={T}: {ms:.3f} ms  ({B * T / ms * 1e3:.0f} frames/s, {gen.launches_last_call()} launches, "
+              f"finite {bool(torch.isfinite(y).all())})", flush=True)
+        print(gen.profile(B, T), flush=True)
+
+
 if __name__ == "__main__":
     st = sys.argv[1]
     print(f"===== stage {st} on {torch.cuda.get_device_name(0)}", flush=True)
     {"profile_vjp": stage_profile_vjp, "mas": stage_mas, "conv_ffma": lambda: (stage_conv(0, 0), stage_conv(0, 1)), "conv_tc": lambda: stage_conv(1, 1),
      "dec_fp32": lambda: stage_dec("fp32"), "dec_bf16_ffma": lambda: stage_dec("bf16", 0),
-     "dec_bf16_tc": lambda: stage_dec("bf16", 1), "perf": stage_perf, "profile": stage_profile, "halo": stage_halo, "convdbg": stage_convdbg, "mbench": stage_mbench, "align": stage_align}[st]()
+     "dec_bf16_tc": lambda: stage_dec("bf16", 1), "perf": stage_perf, "profile": stage_profile, "halo": stage_halo, "convdbg": stage_convdbg, "mbench": stage_mbench, "align": stage_align, "vocoder": stage_vocoder}[st]()
     torch.cuda.synchronize()
     print(f"===== stage {st} done", flush=True)
