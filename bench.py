@@ -440,6 +440,7 @@ def main():
             eager = gpu_eager_record(pkg, torch, dev, configs, line)
             varlen = varlen_record(pkg, torch, get_decoder, dev)
             line["likelihood"] = likelihood_record(pkg, torch, get_decoder, dev)
+            line["vocoder"] = vocoder_record(pkg, torch, dev, line["value"])
             line["configs"] = configs
             line["mas"] = mas
             line["fp32_strict"] = fp32
@@ -630,6 +631,73 @@ def likelihood_record(pkg, torch, get_decoder, dev):
         out["fp32_vs_eager_rel_err_of_bpd"] = float(((vals["fp32"][:bs] - ref).abs() / ref.abs()).max())
     except Exception as e:
         out["gpu_eager"] = {"error": repr(e)[:200]}
+    return out
+
+
+def vocoder_record(pkg, torch, dev, decoder_fps):
+    """The step after the decoder in inference.py:97: HiFi-GAN V1 generator (hifi-gan/models.py:77-118) on mels of the headline
+    shape.  Ours: csrc/vocoder.cu (tcgen05 1-D convs, bf16 activations; and the strict fp32 mode).  Baseline: the reference's op
+    sequence (oracle/vocoder_oracle.py = F.conv1d / conv_transpose1d / leaky_relu as models.py issues them) run eagerly on this GPU."""
+    from oracle import vocoder_oracle
+    cfg = pkg.synth.VOCODER_CONFIGS["v1"]
+    sd = pkg.synth.make_vocoder_state_dict(cfg, seed=1)
+    gen = pkg.hifigan.Generator(pkg.hifigan.AttrDict(cfg))
+    gen.load_state_dict(sd)
+    gen = gen.to(dev).eval()
+    gen.remove_weight_norm()
+    Bv, T_ = 32, 1720
+    out = {"workload": f"HiFi-GAN V1 generator, {Bv} mels x {T_} frames -> {T_ * 256} samples each (22.05 kHz)", "unit": "frames/s"}
+    mel = pkg.synth.make_mel(Bv, T_, seed=2)
+    mel_d = mel.to(dev)
+    y = gen(mel_d)
+    ms = _event_time_ms(torch, lambda: gen(mel_d), 3, 1)
+    out["bf16"] = {"ms": ms, "value": Bv * T_ / (ms * 1e-3), "launches": gen.launches_last_call(), "output_finite": bool(torch.isfinite(y).all()),
+                   "audio_seconds_per_second": Bv * T_ * 256 / 22050 / (ms * 1e-3)}
+    # end to end with host buffers through the C ABI (H2D of the mels, D2H of the waveforms inside the timed region)
+    mel_h = mel.pin_memory()
+    wav_h = torch.empty(Bv, 1, T_ * 256).pin_memory()
+    lib = pkg._lib.load()
+    t0 = time.perf_counter()
+    pkg._lib.check(lib.gtts_vocoder_forward_host(gen._handle, mel_h.data_ptr(), wav_h.data_ptr(), Bv, T_, 0), "vocoder_forward_host")
+    dt = time.perf_counter() - t0
+    out["bf16"]["e2e_value"] = Bv * T_ / dt
+    out["bf16"]["h2d_bytes"], out["bf16"]["d2h_bytes"] = mel_h.numel() * 4, wav_h.numel() * 4
+    # parity of the timed batch: first 2 utterances against the fp32 eager run below
+    sd_d = {k: v.to(dev) for k, v in sd.items()}
+    with torch.no_grad():
+        ref = vocoder_oracle.generator_forward(sd_d, cfg, mel_d[:2])
+    out["bf16"]["rel_rms_vs_eager_fp32"] = float(((y[:2] - ref).pow(2).mean() / ref.pow(2).mean()).sqrt())
+    del y
+    gen.precision = "fp32"
+    gen.max_chunk = 4
+    y32 = gen(mel_d[:4])
+    ms32 = _event_time_ms(torch, lambda: gen(mel_d[:4]), 2, 1)
+    out["fp32_strict"] = {"ms": ms32, "value": 4 * T_ / (ms32 * 1e-3), "sample": f"4 x {T_} frames",
+                          "max_abs_vs_eager_fp32": float((y32[:2] - ref).abs().max())}
+    del y32
+    be = 4
+    eager = {"sample": f"{be} x {T_} frames, scaled to {Bv}"}
+    for mode in ("tf32_default", "bf16_autocast"):
+        def run():
+            with torch.no_grad():
+                if mode == "bf16_autocast":
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        return vocoder_oracle.generator_forward(sd_d, cfg, mel_d[:be])
+                return vocoder_oracle.generator_forward(sd_d, cfg, mel_d[:be])
+        try:
+            ms_e = _event_time_ms(torch, run, 2, 1)
+            eager[mode] = {"ms_sample": ms_e, "value": be * T_ / (ms_e * 1e-3)}
+        except Exception as e:
+            eager[mode] = {"error": repr(e)[:200]}
+            torch.cuda.empty_cache()
+    best = max((eager[m].get("value", 0.0) for m in ("tf32_default", "bf16_autocast")), default=0.0)
+    eager["best_eager_value"] = best
+    out["gpu_eager_baseline"] = eager
+    out["vs_gpu_eager"] = out["bf16"]["value"] / best if best else None
+    # what the vocoder adds to the headline pipeline (decoder at 100 Euler steps + vocoder)
+    out["decoder_plus_vocoder_frames_per_s"] = 1.0 / (1.0 / decoder_fps + 1.0 / out["bf16"]["value"])
+    del gen, sd_d, mel_d
+    torch.cuda.empty_cache()
     return out
 
 

@@ -36,6 +36,12 @@ SIGNATURES = {
     "gtts_decoder_profile_step": (_i, [_vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "gtts_decoder_launches_last_call": (_l, [_vp]),
     "gtts_decoder_cache_info": (_i, [_vp, _vp, _i]),
+    "gtts_encoder_create": (_i, [_c.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i]),
+    "gtts_encoder_destroy": (None, [_vp]),
+    "gtts_encoder_set_param": (_i, [_vp, _cp, _vp, _sz]),
+    "gtts_encoder_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "gtts_encoder_check_tokens": (_i, [_vp, _vp]),
+    "gtts_encoder_launches_last_call": (_l, [_vp]),
     "gtts_vocoder_create": (_i, [_c.POINTER(_vp), _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _i]),
     "gtts_vocoder_destroy": (None, [_vp]),
     "gtts_vocoder_set_param": (_i, [_vp, _cp, _vp, _sz]),

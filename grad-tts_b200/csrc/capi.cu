@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "decoder_api.h"
 #include "ops.h"
+#include "text_encoder_api.h"
 #include "vocoder_api.h"
 #include <vector>
 
@@ -30,6 +31,10 @@ struct gtts_decoder {
     float *z = nullptr, *mask = nullptr, *mu = nullptr, *spk = nullptr, *out = nullptr;
     size_t cap_plane = 0, cap_mask = 0, cap_spk = 0;
     cudaStream_t stream = nullptr;
+};
+
+struct gtts_encoder {
+    TextEncoder* impl;
 };
 
 struct gtts_vocoder {
@@ -531,6 +536,44 @@ int gtts_test_conv(int impl, int act, int kind, int B, int H, int W, int Cin0, i
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ text encoder
+int gtts_encoder_create(gtts_encoder** out, int n_vocab, int n_feats, int n_channels, int filter_channels, int filter_channels_dp,
+                        int n_heads, int n_layers, int kernel_size, int window_size, int spk_emb_dim, int n_spks, int device) {
+    GTTS_REQUIRE(out != nullptr, "null out pointer");
+    TextEncoder* e = text_encoder_new(n_vocab, n_feats, n_channels, filter_channels, filter_channels_dp, n_heads, n_layers, kernel_size,
+                                      window_size, spk_emb_dim, n_spks, device);
+    if (!e) return 1;
+    gtts_encoder* h = new gtts_encoder();
+    h->impl = e;
+    *out = h;
+    return 0;
+}
+
+void gtts_encoder_destroy(gtts_encoder* h) {
+    if (!h) return;
+    text_encoder_delete(h->impl);
+    delete h;
+}
+
+int gtts_encoder_set_param(gtts_encoder* h, const char* name, const float* data, size_t numel) {
+    GTTS_REQUIRE(h != nullptr, "null encoder handle");
+    return text_encoder_set_param(h->impl, name, data, numel);
+}
+
+int gtts_encoder_forward(gtts_encoder* h, const int64_t* tokens, const int64_t* lengths, const float* spk, float* mu, float* logw,
+                         float* x_mask, int B, int T, void* stream) {
+    GTTS_REQUIRE(h != nullptr, "null encoder handle");
+    return text_encoder_forward(h->impl, (const long long*)tokens, (const long long*)lengths, spk, mu, logw, x_mask, B, T,
+                                (cudaStream_t)stream);
+}
+
+int gtts_encoder_check_tokens(gtts_encoder* h, void* stream) {
+    GTTS_REQUIRE(h != nullptr, "null encoder handle");
+    return text_encoder_check_tokens(h->impl, (cudaStream_t)stream);
+}
+
+long gtts_encoder_launches_last_call(const gtts_encoder* h) { return h ? text_encoder_launches_last_call(h->impl) : 0; }
 
 // ------------------------------------------------------------------------------------------------ vocoder
 int gtts_vocoder_create(gtts_vocoder** out, int resblock, int n_ups, const int* upsample_rates, const int* upsample_kernel_sizes,

@@ -106,6 +106,11 @@ int microbench_issue(int N, int n_mma, int n_commit, int iters, int wait_each, i
 int conv_tc_launch(const TcConvPlan* p, cudaStream_t stream);
 size_t conv_tc_partials_slots(const ConvGeom& g);
 
+// 1-D conv weights (vocoder.cu, text_encoder.cu): PyTorch Conv1d (Cout, Cin, k) -- or ConvTranspose1d (Cin, Cout, k) when
+// `transposed` -- to the K-major packed rows [tap][Cout_p] x [Cin_p] the implicit-GEMM kernels read (zero padding)
+int pack_conv1d_weight(ActKind act, const float* src, void* dst, int Cout, int Cin, int k, int Cout_p, int Cin_p, bool transposed,
+                       cudaStream_t s);
+
 // ------------------------------------------------------------------------------------------------
 // Point-wise / small kernels
 // ------------------------------------------------------------------------------------------------

@@ -428,16 +428,6 @@ struct Builder {
     }
 };
 
-template <typename T>
-int pack_one(const float* src, void** dst, int Cout, int Cin, int k, int Cout_p, int Cin_p, long s_co, long s_ci) {
-    const size_t n = (size_t)k * Cout_p * Cin_p;
-    if (!*dst) GTTS_CHECK_CUDA(cudaMalloc(dst, n * sizeof(T)));
-    const int blocks = (int)std::min<size_t>((n + 255) / 256, 4096);
-    pack_w1d_kernel<T><<<blocks, 256>>>(src, (T*)*dst, Cout, Cin, k, Cout_p, Cin_p, s_co, s_ci);
-    GTTS_CHECK_CUDA(cudaGetLastError());
-    return 0;
-}
-
 // (re)build the packed weights of every layer (both activation types: the strict mode and conv_pre / conv_post use fp32)
 int pack_all(Vocoder* v) {
     if (v->packed_valid) return 0;
@@ -447,10 +437,11 @@ int pack_all(Vocoder* v) {
         ConvW& w = it->second;
         GTTS_REQUIRE(w.w_numel == (size_t)Cout * Cin * k, "vocoder: weight has the wrong number of elements");
         GTTS_REQUIRE(w.b_numel == (size_t)Cout, "vocoder: bias has the wrong number of elements");
-        // Conv1d weight (Cout, Cin, k); ConvTranspose1d weight (Cin, Cout, k)
-        const long s_co = transposed ? k : (long)Cin * k, s_ci = transposed ? (long)Cout * k : k;
-        if (int rc = pack_one<float>(w.w, &w.packed[ACT_F32], Cout, Cin, k, Cout_p, Cin_p, s_co, s_ci)) return rc;
-        if (int rc = pack_one<__nv_bfloat16>(w.w, &w.packed[ACT_BF16], Cout, Cin, k, Cout_p, Cin_p, s_co, s_ci)) return rc;
+        const size_t n = (size_t)k * Cout_p * Cin_p;
+        if (!w.packed[ACT_F32]) GTTS_CHECK_CUDA(cudaMalloc(&w.packed[ACT_F32], n * 4));
+        if (!w.packed[ACT_BF16]) GTTS_CHECK_CUDA(cudaMalloc(&w.packed[ACT_BF16], n * 2));
+        if (int rc = pack_conv1d_weight(ACT_F32, w.w, w.packed[ACT_F32], Cout, Cin, k, Cout_p, Cin_p, transposed, 0)) return rc;
+        if (int rc = pack_conv1d_weight(ACT_BF16, w.w, w.packed[ACT_BF16], Cout, Cin, k, Cout_p, Cin_p, transposed, 0)) return rc;
         if (!w.bias_p) GTTS_CHECK_CUDA(cudaMalloc((void**)&w.bias_p, (size_t)std::max(Cout_p, 1) * 4));
         GTTS_CHECK_CUDA(cudaMemset(w.bias_p, 0, (size_t)std::max(Cout_p, 1) * 4));
         GTTS_CHECK_CUDA(cudaMemcpy(w.bias_p, w.b, (size_t)Cout * 4, cudaMemcpyDeviceToDevice));
@@ -578,6 +569,18 @@ size_t workspace_per_sample(const Vocoder* v, int T, ActKind kind) {
 }
 
 }  // namespace
+
+int pack_conv1d_weight(ActKind act, const float* src, void* dst, int Cout, int Cin, int k, int Cout_p, int Cin_p, bool transposed,
+                       cudaStream_t s) {
+    // Conv1d weight (Cout, Cin, k); ConvTranspose1d weight (Cin, Cout, k)
+    const long s_co = transposed ? k : (long)Cin * k, s_ci = transposed ? (long)Cout * k : k;
+    const size_t n = (size_t)k * Cout_p * Cin_p;
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 4096);
+    if (act == ACT_F32) pack_w1d_kernel<float><<<blocks, 256, 0, s>>>(src, (float*)dst, Cout, Cin, k, Cout_p, Cin_p, s_co, s_ci);
+    else pack_w1d_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(src, (__nv_bfloat16*)dst, Cout, Cin, k, Cout_p, Cin_p, s_co, s_ci);
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
 
 Vocoder* vocoder_new(int resblock, int n_ups, const int* rates, const int* up_kernels, int initial_channel, int n_rb,
                      const int* rb_kernels, const int* rb_dilations, int n_dil, int num_mels, int device) {

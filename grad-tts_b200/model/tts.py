@@ -3,9 +3,9 @@
 Only the boundary is reproduced here: speaker embedding lookup, encoder call, duration -> length -> mask ->
 `generate_path` -> `mu_y`, the single RNG draw `z = mu_y + randn_like(mu_y) / temperature` (kept in PyTorch so
 the same seed gives the same z as the reference) and the decoder call, which runs on the sm_100a
-kernels.  The text encoder is NOT part of this hot path (out of scope); it is injected:
-pass `encoder=` (any module with the reference `TextEncoder.forward(x, x_lengths, spk) -> mu_x, logw, x_mask`
-contract), or leave it None inside the reference tree and `model.text_encoder.TextEncoder` is used.
+kernels.  The text encoder defaults to the native one (model/text_encoder.py here, csrc/text_encoder.cu; inference only); for
+training pass `encoder=` (any module with the reference `TextEncoder.forward(x, x_lengths, spk) -> mu_x, logw, x_mask` contract,
+e.g. the reference's own PyTorch class).
 """
 import math
 import random
@@ -15,17 +15,8 @@ import torch
 from . import align, monotonic_align
 from .base import BaseModule
 from .diffusion import Diffusion
+from .text_encoder import TextEncoder
 from .utils import sequence_mask, generate_path, duration_loss, fix_len_compatibility  # noqa: F401
-
-
-def _reference_text_encoder(*args):
-    try:
-        from model.text_encoder import TextEncoder          # the reference's own module, if on sys.path
-    except Exception as e:                                  # pragma: no cover
-        raise RuntimeError(
-            "GradTTS needs a text encoder: pass `encoder=` or run inside the reference tree so that "
-            "`model.text_encoder.TextEncoder` is importable (the encoder is outside the B200 hot path)") from e
-    return TextEncoder(*args)
 
 
 class GradTTS(BaseModule):
@@ -55,8 +46,9 @@ class GradTTS(BaseModule):
         elif self.n_spks > 1:
             self.spk_emb = torch.nn.Embedding(n_spks, spk_emb_dim)
         if encoder is None:
-            encoder = _reference_text_encoder(n_vocab, n_feats, n_enc_channels, filter_channels, filter_channels_dp,
-                                              n_heads, n_enc_layers, enc_kernel, enc_dropout, window_size)
+            # as the reference builds it (model/tts.py:49-51): without spk_emb_dim / n_spks, i.e. the encoder ignores the speaker
+            encoder = TextEncoder(n_vocab, n_feats, n_enc_channels, filter_channels, filter_channels_dp,
+                                  n_heads, n_enc_layers, enc_kernel, enc_dropout, window_size)
         self.encoder = encoder
         self.decoder = Diffusion(n_feats, dec_dim, n_spks, spk_emb_dim, beta_min, beta_max, pe_scale)
 

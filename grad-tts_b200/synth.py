@@ -190,3 +190,79 @@ def make_mel(B, T, seed=1):
     x = torch.randn(B, N_FEATS, T + 8, generator=gen)
     x = torch.nn.functional.avg_pool1d(x, 5, stride=1, padding=2)[..., 4:4 + T]
     return (2.0 * x - 1.0).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------------------- text encoder
+TEXT_ENCODER_CONFIGS = {
+    # params.py:31-38 as GradTTS passes them (model/tts.py:49-51: without spk_emb_dim / n_spks, so the encoder ignores the speaker)
+    "ref": dict(n_vocab=149, n_feats=80, n_channels=192, filter_channels=768, filter_channels_dp=256, n_heads=2, n_layers=6,
+                kernel_size=3, p_dropout=0.1, window_size=4, spk_emb_dim=64, n_spks=1),
+    # the class's own multi-speaker mode (text_encoder.py:310,327-328): speaker embedding concatenated to the prenet output
+    "spk": dict(n_vocab=60, n_feats=80, n_channels=192, filter_channels=256, filter_channels_dp=128, n_heads=2, n_layers=2,
+                kernel_size=3, p_dropout=0.1, window_size=4, spk_emb_dim=64, n_spks=4),
+}
+
+
+def text_encoder_param_shapes(cfg):
+    """(name, shape) for every tensor of the reference `TextEncoder.state_dict()` (model/text_encoder.py:285-319)."""
+    C0, F, Fdp, k = cfg["n_channels"], cfg["filter_channels"], cfg["filter_channels_dp"], cfg["kernel_size"]
+    C = C0 + (cfg["spk_emb_dim"] if cfg["n_spks"] > 1 else 0)
+    kc, w = C // cfg["n_heads"], cfg["window_size"]
+    s = [("emb.weight", (cfg["n_vocab"], C0))]
+    for i in range(3):
+        s += [(f"prenet.conv_layers.{i}.weight", (C0, C0, 5)), (f"prenet.conv_layers.{i}.bias", (C0,))]
+    for i in range(3):
+        s += [(f"prenet.norm_layers.{i}.gamma", (C0,)), (f"prenet.norm_layers.{i}.beta", (C0,))]
+    s += [("prenet.proj.weight", (C0, C0, 1)), ("prenet.proj.bias", (C0,))]
+    for i in range(cfg["n_layers"]):
+        p = f"encoder.attn_layers.{i}"
+        if w is not None:
+            s += [(p + ".emb_rel_k", (1, 2 * w + 1, kc)), (p + ".emb_rel_v", (1, 2 * w + 1, kc))]
+        for c in ("conv_q", "conv_k", "conv_v", "conv_o"):
+            s += [(f"{p}.{c}.weight", (C, C, 1)), (f"{p}.{c}.bias", (C,))]
+    for i in range(cfg["n_layers"]):
+        s += [(f"encoder.norm_layers_1.{i}.gamma", (C,)), (f"encoder.norm_layers_1.{i}.beta", (C,))]
+    for i in range(cfg["n_layers"]):
+        s += [(f"encoder.ffn_layers.{i}.conv_1.weight", (F, C, k)), (f"encoder.ffn_layers.{i}.conv_1.bias", (F,)),
+              (f"encoder.ffn_layers.{i}.conv_2.weight", (C, F, k)), (f"encoder.ffn_layers.{i}.conv_2.bias", (C,))]
+    for i in range(cfg["n_layers"]):
+        s += [(f"encoder.norm_layers_2.{i}.gamma", (C,)), (f"encoder.norm_layers_2.{i}.beta", (C,))]
+    s += [("proj_m.weight", (cfg["n_feats"], C, 1)), ("proj_m.bias", (cfg["n_feats"],))]
+    s += [("proj_w.conv_1.weight", (Fdp, C, k)), ("proj_w.conv_1.bias", (Fdp,)), ("proj_w.norm_1.gamma", (Fdp,)), ("proj_w.norm_1.beta", (Fdp,)),
+          ("proj_w.conv_2.weight", (Fdp, Fdp, k)), ("proj_w.conv_2.bias", (Fdp,)), ("proj_w.norm_2.gamma", (Fdp,)), ("proj_w.norm_2.beta", (Fdp,)),
+          ("proj_w.proj.weight", (1, Fdp, 1)), ("proj_w.proj.bias", (1,))]
+    return s
+
+
+def make_text_encoder_state_dict(cfg, seed=0):
+    """Seeded weights at trained-model scale: fan-in scaled convs, norm gains around 1, duration head biased to a few frames."""
+    gen = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, shape in text_encoder_param_shapes(cfg):
+        if name == "emb.weight":
+            t = torch.randn(*shape, generator=gen) * cfg["n_channels"] ** -0.5
+        elif name.endswith(".gamma"):
+            t = 1.0 + 0.1 * torch.randn(*shape, generator=gen)
+        elif name.endswith(".beta") or name.endswith(".bias"):
+            t = 0.1 * torch.randn(*shape, generator=gen)
+            if name == "proj_w.proj.bias":
+                t = t + 1.0
+        elif "emb_rel" in name:
+            t = torch.randn(*shape, generator=gen) * shape[-1] ** -0.5
+        else:
+            fan_in = shape[1] * (shape[2] if len(shape) > 2 else 1)
+            t = torch.randn(*shape, generator=gen) * (1.0 / math.sqrt(fan_in))
+        sd[name] = t
+    return sd
+
+
+def make_text_inputs(cfg, B, T, seed=1, ragged=True):
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randint(0, cfg["n_vocab"], (B, T), generator=gen)
+    if ragged and B > 1:
+        lengths = torch.randint(max(1, T // 2), T + 1, (B,), generator=gen)
+        lengths[0] = T
+    else:
+        lengths = torch.full((B,), T, dtype=torch.long)
+    spk = torch.randn(B, cfg["spk_emb_dim"], generator=gen) if cfg["n_spks"] > 1 else None
+    return x, lengths, spk

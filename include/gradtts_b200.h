@@ -14,6 +14,7 @@
  *   gtts_decoder_reverse_diffusion model/diffusion.py:254-272  Diffusion.forward / reverse_diffusion(z, mask, mu, n_timesteps, stoc, spk)
  *   gtts_decoder_estimator         model/diffusion.py:174-216  GradLogPEstimator2d.forward(x, mask, mu, t, spk)
  *   gtts_decoder_create/set_param  model/diffusion.py:128-172,227-242  module construction + load_state_dict
+ *   gtts_encoder_create/set_param/forward  model/text_encoder.py:285-335  TextEncoder(...), load_state_dict, forward(x, x_lengths, spk)
  *   gtts_vocoder_create/set_param/forward  hifi-gan/models.py:77-118  Generator(h), load_state_dict + remove_weight_norm, forward(mel)
  */
 #ifndef GRADTTS_B200_H
@@ -174,6 +175,23 @@ int gtts_test_attn_xk(const void* x_bf16, const void* wkv_bf16, float* partials,
  * {n_mma tcgen05.mma M128xNx16, n_commit tcgen05.commit}, optionally waiting on the last commit every round. */
 int gtts_test_issue_microbench(int N, int n_mma, int n_commit, int iters, int wait_each, int grid, double* issue_cycles,
                                double* total_cycles);
+
+/* ---- Text encoder (the step before the decoder, model/tts.py:84) ---------------------------------------
+ * Constructor arguments as model/text_encoder.py:286-288 (window_size < 0 = None); parameters by their reference state_dict key
+ * ("emb.weight", "prenet.conv_layers.0.weight", "encoder.attn_layers.3.emb_rel_k", "proj_w.norm_1.gamma", ...), fp32, PyTorch
+ * layout, host or device pointer.  forward = TextEncoder.forward in eval mode: tokens (B, T) int64, lengths (B) int64, spk
+ * (B, spk_emb_dim) fp32 or NULL -> mu (B, n_feats, T), logw (B, 1, T), x_mask (B, 1, T), all fp32.  fp32 arithmetic throughout
+ * (the output decides integer durations).  gtts_encoder_check_tokens reports a token id outside [0, n_vocab) seen by the last
+ * forward (synchronises the stream). */
+typedef struct gtts_encoder gtts_encoder;
+int gtts_encoder_create(gtts_encoder** out, int n_vocab, int n_feats, int n_channels, int filter_channels, int filter_channels_dp,
+                        int n_heads, int n_layers, int kernel_size, int window_size, int spk_emb_dim, int n_spks, int device);
+void gtts_encoder_destroy(gtts_encoder* e);
+int gtts_encoder_set_param(gtts_encoder* e, const char* name, const float* data, size_t numel);
+int gtts_encoder_forward(gtts_encoder* e, const int64_t* tokens, const int64_t* lengths, const float* spk, float* mu, float* logw,
+                         float* x_mask, int B, int T, void* stream);
+int gtts_encoder_check_tokens(gtts_encoder* e, void* stream);
+long gtts_encoder_launches_last_call(const gtts_encoder* e);
 
 /* ---- HiFi-GAN generator (vocoder; the step after the decoder, inference.py:73-76,97) ---------------------
  * Configuration = the fields of checkpts/hifigan-config.json that hifi-gan/models.py:77-99 reads: resblock ("1" / "2"),

@@ -277,10 +277,45 @@ def make_vocoder_vectors():
         print(name, tuple(y.shape), float(y.abs().mean()), float(y.abs().max()))
 
 
+def text_encoder_cases():
+    # name, config, B, T, weight seed, input seed
+    return [("enc_ref_b2_t37", "ref", 2, 37, 41, 42), ("enc_ref_b1_t3", "ref", 1, 3, 41, 43), ("enc_spk_b3_t20", "spk", 3, 20, 44, 45)]
+
+
+def make_text_encoder_vectors():
+    """model/text_encoder.py::TextEncoder in eval mode, constructed as model/tts.py:49-51 does ("ref") and with its own
+    multi-speaker arguments ("spk")."""
+    import contextlib
+    import io
+    from model.text_encoder import TextEncoder
+    for name, cfg_name, B, T, wseed, iseed in text_encoder_cases():
+        cfg = synth.TEXT_ENCODER_CONFIGS[cfg_name]
+        sd = synth.make_text_encoder_state_dict(cfg, seed=wseed)
+        with contextlib.redirect_stdout(io.StringIO()):          # the reference constructor prints its channel counts
+            enc = TextEncoder(cfg["n_vocab"], cfg["n_feats"], cfg["n_channels"], cfg["filter_channels"], cfg["filter_channels_dp"],
+                              cfg["n_heads"], cfg["n_layers"], cfg["kernel_size"], cfg["p_dropout"], cfg["window_size"],
+                              cfg["spk_emb_dim"], cfg["n_spks"])
+        assert list(enc.state_dict().keys()) == list(sd.keys()), "synth.text_encoder_param_shapes is out of step with the reference"
+        enc.load_state_dict(sd, strict=True)
+        enc.eval()
+        x, lengths, spk = synth.make_text_inputs(cfg, B, T, seed=iseed)
+        with torch.no_grad():
+            mu, logw, x_mask = enc(x, lengths, spk)
+        out = dict(x=x.numpy(), lengths=lengths.numpy(), mu=mu.numpy(), logw=logw.numpy(), x_mask=x_mask.numpy(), cfg=cfg_name,
+                   wseed=wseed, sd_digest=sd_digest(sd))
+        if spk is not None:
+            out["spk"] = spk.numpy()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, tuple(mu.shape), float(mu.abs().mean()), float(logw.abs().mean()), float(torch.exp(logw).max()))
+
+
 def main():
     torch.set_num_threads(8)
     if sys.argv[1:] == ["voc"]:
         return make_vocoder_vectors()
+    if sys.argv[1:] == ["enc"]:
+        import_reference()
+        return make_text_encoder_vectors()
     import_reference()
     if sys.argv[1:] == ["loss"]:
         return make_loss_vectors()
@@ -293,6 +328,7 @@ def main():
     make_baseline_shape_vectors(only)
     if not only:
         make_vocoder_vectors()
+        make_text_encoder_vectors()
         make_loss_vectors()
         make_vjp_vectors()
         make_likelihood_vectors()

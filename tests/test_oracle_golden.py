@@ -220,3 +220,48 @@ def test_vocoder_module_has_the_reference_state_dict_layout(pkg, synth):
             assert torch.allclose(sd2[name + ".weight"], vocoder_oracle.effective_weight(sd, name), atol=1e-7)
     with pytest.raises(RuntimeError):
         gen.forward(torch.zeros(1, 80, 8))                       # CPU tensors: no fallback
+
+
+ENC = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "enc_*.npz")))
+
+
+def _enc_case(name, synth):
+    import hashlib
+    g = _load(name)
+    cfg = synth.TEXT_ENCODER_CONFIGS[str(g["cfg"])]
+    sd = synth.make_text_encoder_state_dict(cfg, seed=int(g["wseed"]))
+    h = hashlib.sha256()
+    for k in sd:
+        h.update(k.encode())
+        h.update(sd[k].numpy().tobytes())
+    assert h.hexdigest() == str(g["sd_digest"]), "synthetic text-encoder weights differ from the ones the fixture was made with"
+    spk = torch.from_numpy(g["spk"]) if "spk" in g else None
+    return g, cfg, sd, torch.from_numpy(g["x"]), torch.from_numpy(g["lengths"]), spk
+
+
+@pytest.mark.parametrize("name", ENC)
+def test_text_encoder_oracle_matches_reference_module(name, synth):
+    """oracle/text_encoder_oracle.py vs the reference's TextEncoder (eval mode), incl. T = 3 < window + 1 and the multi-speaker mode."""
+    from oracle import text_encoder_oracle
+    g, cfg, sd, x, lengths, spk = _enc_case(name, synth)
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        mu, logw, x_mask = text_encoder_oracle.text_encoder_forward(sd, cfg, x, lengths, spk)
+    assert torch.equal(x_mask, torch.from_numpy(g["x_mask"]))
+    assert float((mu - torch.from_numpy(g["mu"])).abs().max()) <= 2e-5          # fp32 reassociation (matmul vs gather-einsum)
+    assert float((logw - torch.from_numpy(g["logw"])).abs().max()) <= 2e-5
+
+
+def test_text_encoder_module_has_the_reference_state_dict_layout(pkg, synth):
+    import importlib
+    te = importlib.import_module("grad-tts_b200.model.text_encoder")
+    for cfg in synth.TEXT_ENCODER_CONFIGS.values():
+        enc = te.TextEncoder(**cfg)
+        want = synth.text_encoder_param_shapes(cfg)                                # checked against the reference in make_golden.py
+        got = [(k, tuple(v.shape)) for k, v in enc.state_dict().items()]
+        assert got == [(k, tuple(s)) for k, s in want]
+        enc.eval()
+        with pytest.raises(RuntimeError):
+            enc(torch.zeros(1, 5, dtype=torch.long), torch.tensor([5]))           # CPU tensors: no fallback
+    net = pkg.GradTTS(149, 1, 64, 192, 768, 256, 2, 6, 3, 0.1, 4, 80, 64, 0.05, 20.0, 1000)
+    assert isinstance(net.encoder, te.TextEncoder) and net.nparams == 14835032    # the reference's parameter count
