@@ -441,6 +441,7 @@ def main():
             varlen = varlen_record(pkg, torch, get_decoder, dev)
             line["likelihood"] = likelihood_record(pkg, torch, get_decoder, dev)
             line["vocoder"] = vocoder_record(pkg, torch, dev, line["value"])
+            line["text_encoder"] = text_encoder_record(pkg, torch, dev)
             line["configs"] = configs
             line["mas"] = mas
             line["fp32_strict"] = fp32
@@ -634,6 +635,46 @@ def likelihood_record(pkg, torch, get_decoder, dev):
     return out
 
 
+def text_encoder_record(pkg, torch, dev):
+    """The step before the decoder (model/tts.py:84): TextEncoder.forward on token batches.  Ours: csrc/text_encoder.cu (fp32).
+    Baseline: the reference's op sequence (oracle/text_encoder_oracle.py) run eagerly on this GPU with torch's defaults."""
+    from oracle import text_encoder_oracle
+    te = importlib.import_module("grad-tts_b200.model.text_encoder")
+    cfg = pkg.synth.TEXT_ENCODER_CONFIGS["ref"]
+    sd = pkg.synth.make_text_encoder_state_dict(cfg, seed=1)
+    enc = te.TextEncoder(**cfg)
+    enc.load_state_dict(sd)
+    enc = enc.to(dev).eval()
+    sd_d = {k: v.to(dev) for k, v in sd.items()}
+    out = {"unit": "tokens/s", "note": "fp32 on the CUDA cores (the output decides integer durations); eager = F.conv1d / matmul / softmax "
+                                       "as model/text_encoder.py issues them, with torch's TF32 defaults and with TF32 off (same "
+                                       "arithmetic as ours)"}
+    for name, Bt, Tt in (("batch128_x_200_tokens", 128, 200), ("single_utterance_100_tokens", 1, 100)):
+        x, lengths, _ = pkg.synth.make_text_inputs(cfg, Bt, Tt, seed=3, ragged=False)
+        xd, ld = x.to(dev), lengths.to(dev)
+        mu, logw, _ = enc(xd, ld)
+        ms = _event_time_ms(torch, lambda: enc(xd, ld), 5, 2)
+
+        def eager():
+            with torch.no_grad():
+                return text_encoder_oracle.text_encoder_forward(sd_d, cfg, xd, ld)
+        mu_e, logw_e, _ = eager()
+        ms_e = _event_time_ms(torch, eager, 5, 2)
+        tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            mu_f, _, _ = eager()
+            ms_f = _event_time_ms(torch, eager, 5, 2)
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+        out[name] = {"ms": ms, "value": Bt * Tt / (ms * 1e-3), "launches": enc.launches_last_call(), "eager_tf32_ms": ms_e,
+                     "eager_fp32_ms": ms_f, "vs_gpu_eager_tf32": ms_e / ms, "vs_gpu_eager_fp32": ms_f / ms,
+                     "max_abs_mu_vs_eager_fp32": float((mu - mu_f).abs().max()), "max_abs_mu_vs_eager_tf32": float((mu - mu_e).abs().max())}
+    del enc, sd_d
+    torch.cuda.empty_cache()
+    return out
+
+
 def vocoder_record(pkg, torch, dev, decoder_fps):
     """The step after the decoder in inference.py:97: HiFi-GAN V1 generator (hifi-gan/models.py:77-118) on mels of the headline
     shape.  Ours: csrc/vocoder.cu (tcgen05 1-D convs, bf16 activations; and the strict fp32 mode).  Baseline: the reference's op
@@ -666,14 +707,14 @@ def vocoder_record(pkg, torch, dev, decoder_fps):
     sd_d = {k: v.to(dev) for k, v in sd.items()}
     with torch.no_grad():
         ref = vocoder_oracle.generator_forward(sd_d, cfg, mel_d[:2])
-    out["bf16"]["rel_rms_vs_eager_fp32"] = float(((y[:2] - ref).pow(2).mean() / ref.pow(2).mean()).sqrt())
+    out["bf16"]["rel_rms_vs_eager_tf32_default"] = float(((y[:2] - ref).pow(2).mean() / ref.pow(2).mean()).sqrt())
     del y
     gen.precision = "fp32"
     gen.max_chunk = 4
     y32 = gen(mel_d[:4])
     ms32 = _event_time_ms(torch, lambda: gen(mel_d[:4]), 2, 1)
     out["fp32_strict"] = {"ms": ms32, "value": 4 * T_ / (ms32 * 1e-3), "sample": f"4 x {T_} frames",
-                          "max_abs_vs_eager_fp32": float((y32[:2] - ref).abs().max())}
+                          "max_abs_vs_eager_tf32_default": float((y32[:2] - ref).abs().max())}
     del y32
     be = 4
     eager = {"sample": f"{be} x {T_} frames, scaled to {Bv}"}

@@ -44,39 +44,45 @@ conv_ffma_kernel(ConvGeom g, const T* __restrict__ src0, const T* __restrict__ s
     const bool lvalid = lpix < npix;
     const int lj = lvalid ? lpix / g.Wg : 0, li = lvalid ? lpix % g.Wg : 0;
 
-    for (int tap = 0; tap < g.ntaps; ++tap) {
+    // K loop over (tap, 32-channel slice), software-pipelined: the global loads of slice it+1 are issued before the FMAs of slice
+    // it, so their latency hides behind the arithmetic (one CTA per SM at small sizes has nothing else to hide it with)
+    const int nslice = cin_tot / kTK, n_it = g.ntaps * nslice;
+    float av[8], wv[8];
+    auto fetch = [&](int it) {
+        const int tap = it / nslice, c0 = (it - tap * nslice) * kTK;
         const int ih = lj * g.stride + g.dy[ph][tap], iw = li * g.stride + g.dx[ph][tap];
         const bool inb = lvalid && ih >= 0 && ih < g.Hin && iw >= 0 && iw < g.Win;
-        const size_t ipix = ((size_t)b * g.Hin + (inb ? ih : 0)) * g.Win + (inb ? iw : 0);
+        if (inb) {
+            const size_t ipix = ((size_t)b * g.Hin + ih) * g.Win + iw;
+            if (c0 < g.Cin0) Act<T>::load8(src0 + ipix * g.Cin0 + c0 + lv, av);
+            else             Act<T>::load8(src1 + ipix * g.Cin1 + (c0 - g.Cin0) + lv, av);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) av[j] = 0.f;
+        }
         const size_t wrow = (size_t)g.wrow[ph][tap] + (size_t)b * g.w_batch_rows + co0 + lp;
-        for (int c0 = 0; c0 < cin_tot; c0 += kTK) {
-            float av[8], wv[8];
-            if (inb) {
-                if (c0 < g.Cin0) Act<T>::load8(src0 + ipix * g.Cin0 + c0 + lv, av);
-                else             Act<T>::load8(src1 + ipix * g.Cin1 + (c0 - g.Cin0) + lv, av);
-            } else {
+        Act<WT>::load8(weight + wrow * cin_tot + c0 + lv, wv);
+    };
+    if (n_it > 0) fetch(0);
+    for (int it = 0; it < n_it; ++it) {
+        __syncthreads();
 #pragma unroll
-                for (int j = 0; j < 8; ++j) av[j] = 0.f;
-            }
-            Act<WT>::load8(weight + wrow * cin_tot + c0 + lv, wv);
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                As[(lv + j) * kPitch + lp] = av[j];
-                Ws[(lv + j) * kPitch + lp] = wv[j];
-            }
-            __syncthreads();
+        for (int j = 0; j < 8; ++j) {
+            As[(lv + j) * kPitch + lp] = av[j];
+            Ws[(lv + j) * kPitch + lp] = wv[j];
+        }
+        __syncthreads();
+        if (it + 1 < n_it) fetch(it + 1);
 #pragma unroll 8
-            for (int k = 0; k < kTK; ++k) {
-                const float4 a4 = *reinterpret_cast<const float4*>(&As[k * kPitch + ty * 4]);
-                const float4 w4 = *reinterpret_cast<const float4*>(&Ws[k * kPitch + tx * 4]);
-                const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-                const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+        for (int k = 0; k < kTK; ++k) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&As[k * kPitch + ty * 4]);
+            const float4 w4 = *reinterpret_cast<const float4*>(&Ws[k * kPitch + tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
-            }
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
         }
     }
 

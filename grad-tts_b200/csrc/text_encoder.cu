@@ -14,6 +14,8 @@
 // masks the keys) and every output is masked, so results at valid positions are those of the reference.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -132,9 +134,9 @@ __global__ void rel_attention_kernel(const float* __restrict__ qkv, const float*
         } else {
             const float4* kp = reinterpret_cast<const float4*>(qkv + ((size_t)b * T + j) * 3 * C + C + h * kKC);
             float acc = 0.f;
-#pragma unroll 4
+#pragma unroll 8
             for (int c4 = 0; c4 < kKC / 4; ++c4) {
-                const float4 kv = kp[c4];
+                const float4 kv = __ldg(kp + c4);
                 acc = fmaf(s_q[c4 * 4 + 0], kv.x, acc); acc = fmaf(s_q[c4 * 4 + 1], kv.y, acc);
                 acc = fmaf(s_q[c4 * 4 + 2], kv.z, acc); acc = fmaf(s_q[c4 * 4 + 3], kv.w, acc);
             }
@@ -167,12 +169,14 @@ __global__ void rel_attention_kernel(const float* __restrict__ qkv, const float*
 #pragma unroll
     for (int k = 0; k < kPer; ++k) acc[k] = 0.f;
     const float* vbase = qkv + (size_t)b * T * 3 * C + 2 * C + h * kKC;
+    // masked keys have p = 0 exactly (exp(-1e4 - max) underflows) and v is finite, so every key can take the same path: the loop
+    // unrolls and its loads overlap
+#pragma unroll 4
     for (int j = 0; j < T; ++j) {
         const float p = s_p[j];
-        if (p == 0.f) continue;
         const float* vp = vbase + (size_t)j * 3 * C;
 #pragma unroll
-        for (int k = 0; k < kPer; ++k) acc[k] = fmaf(p, vp[lane + 32 * k], acc[k]);
+        for (int k = 0; k < kPer; ++k) acc[k] = fmaf(p, __ldg(vp + lane + 32 * k), acc[k]);
     }
     if (window >= 0) {
         for (int d = -window; d <= window; ++d) {
@@ -188,25 +192,253 @@ __global__ void rel_attention_kernel(const float* __restrict__ qkv, const float*
     for (int k = 0; k < kPer; ++k) op[lane + 32 * k] = acc[k] * inv;
 }
 
+// Latency-shaped Conv1d for short token sequences (M = B*T positions of a few hundred): a 64 x 64 implicit-GEMM tile with a serial
+// K loop leaves most SMs idle and pays one block barrier pair per 32 channels.  Here a CTA owns 16 positions x 32 output channels
+// and its 8 warps split K = k * Cin between them in chunks of 32 channels: a warp fetches a chunk with twelve independent 16-byte
+// loads per lane (its own weight row: one full 128-byte line; the 16 x 128-byte activation tile: coalesced, staged through a
+// per-warp shared-memory tile), one chunk ahead of the FMAs, and never meets a block barrier until the 8 partial tiles are summed
+// in shared memory in a fixed order (deterministic).  Same epilogue as conv_ffma: (+bias) (+residual) (*mask) (ReLU).
+// (ncu on the first version, which loaded 16 bytes per row per step: L1 hit rate 56 %, 7.9 long-scoreboard stalls per issue,
+// 70 us for the 768 -> 192 k = 3 conv at 100 tokens.)
+__global__ void __launch_bounds__(256)
+conv1d_splitk_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                     const float* __restrict__ residual, const float* __restrict__ mask, float* __restrict__ out, int M, int T, int Cin,
+                     int Cout, int k, int relu) {
+    __shared__ float part[8][16][33];
+    __shared__ float4 a_s[8][16][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p0 = blockIdx.x * 16, co = blockIdx.y * 32 + lane;
+    const int c32n = Cin / 32;                              // 32-channel chunks per tap
+    const int chunks = k * c32n;
+    const int per = (chunks + 7) / 8;
+    const int ch_begin = warp * per, ch_end = min(chunks, ch_begin + per);
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    // this lane stages rows lane/8 + 4q (q = 0..3), 16 bytes at column lane%8 of the chunk
+    const int f4 = lane & 7;
+    int row_p[4], row_t[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { row_p[q] = p0 + (lane >> 3) + 4 * q; row_t[q] = row_p[q] % T; }
+    float4 a_n[4], w_n[8], w_c[8];
+    auto prefetch = [&](int ch) {
+        const int tap = ch / c32n, cc = ch - tap * c32n;
+        const int dt = tap - k / 2;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int ti = row_t[q] + dt;
+            a_n[q] = (row_p[q] < M && ti >= 0 && ti < T)
+                         ? __ldg(reinterpret_cast<const float4*>(x + (size_t)(row_p[q] + dt) * Cin) + cc * 8 + f4)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float4* wr = reinterpret_cast<const float4*>(w + ((size_t)tap * Cout + co) * Cin) + cc * 8;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w_n[u] = __ldg(wr + u);
+    };
+    if (ch_begin < ch_end) prefetch(ch_begin);
+    for (int ch = ch_begin; ch < ch_end; ++ch) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a_s[warp][(lane >> 3) + 4 * q][f4] = a_n[q];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w_c[u] = w_n[u];
+        __syncwarp();
+        if (ch + 1 < ch_end) prefetch(ch + 1);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float4 a = a_s[warp][i][u];
+                acc[i] = fmaf(a.x, w_c[u].x, acc[i]); acc[i] = fmaf(a.y, w_c[u].y, acc[i]);
+                acc[i] = fmaf(a.z, w_c[u].z, acc[i]); acc[i] = fmaf(a.w, w_c[u].w, acc[i]);
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) part[warp][i][lane] = acc[i];
+    __syncthreads();
+    for (int o = threadIdx.x; o < 16 * 32; o += 256) {
+        const int i = o >> 5, c = o & 31;
+        const int p = p0 + i;
+        if (p >= M) continue;
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v += part[q][i][c];
+        const int cc = blockIdx.y * 32 + c;
+        if (bias) v += bias[cc];
+        if (residual) v += residual[(size_t)p * Cout + cc];
+        if (mask) v *= mask[p];
+        if (relu) v = fmaxf(v, 0.f);
+        out[(size_t)p * Cout + cc] = v;
+    }
+}
+
+// Attention for sequences whose keys and values fit in shared memory (T * kc * 8 bytes <= ~200 KB: 270 tokens at kc = 96).  A CTA
+// stages K and V of one (sample, head) once -- coalesced, rows padded to kc + 1 floats so that "lane = key" reads are conflict-free
+// -- plus the two relative-embedding tables, and its warps take queries round-robin: scores with lane = key, the relative-key
+// logits with lanes across channels and a shuffle reduction, softmax, then the value sum with lane = channel.  The query range is
+// split over gridDim.x CTAs so that a single utterance still fills a few dozen SMs.  Same arithmetic as rel_attention_kernel.
+// (ncu on rel_attention_kernel at 1 x 100 tokens: 58 us, 29 long-scoreboard stalls per issue -- every key row came from L1/L2.)
+template <int kKC>
+__global__ void __launch_bounds__(256)
+rel_attention_smem_kernel(const float* __restrict__ qkv, const float* __restrict__ mask, const float* __restrict__ emb_k,
+                          const float* __restrict__ emb_v, float* __restrict__ out, int T, int C, int window, int q_per_cta) {
+    extern __shared__ float smem[];
+    constexpr int kPitch = kKC + 1;
+    const int nrel = window >= 0 ? 2 * window + 1 : 0;
+    float* s_k = smem;                                   // [T][kPitch]
+    float* s_v = s_k + (size_t)T * kPitch;               // [T][kPitch]
+    float* s_ek = s_v + (size_t)T * kPitch;              // [nrel][kKC]
+    float* s_ev = s_ek + (size_t)nrel * kKC;
+    float* s_m = s_ev + (size_t)nrel * kKC;              // [T] key mask
+    float* s_w = s_m + T;                                // per warp: q[kKC] | p[T]
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.y, b = blockIdx.z;
+    const float* base = qkv + (size_t)b * T * 3 * C + h * kKC;
+    for (int idx = threadIdx.x; idx < T * (kKC / 4); idx += blockDim.x) {
+        const int j = idx / (kKC / 4), c4 = idx - j * (kKC / 4);
+        const float4 kv = __ldg(reinterpret_cast<const float4*>(base + (size_t)j * 3 * C + C) + c4);
+        const float4 vv = __ldg(reinterpret_cast<const float4*>(base + (size_t)j * 3 * C + 2 * C) + c4);
+        float* kd = s_k + (size_t)j * kPitch + c4 * 4;
+        float* vd = s_v + (size_t)j * kPitch + c4 * 4;
+        kd[0] = kv.x; kd[1] = kv.y; kd[2] = kv.z; kd[3] = kv.w;
+        vd[0] = vv.x; vd[1] = vv.y; vd[2] = vv.z; vd[3] = vv.w;
+    }
+    for (int idx = threadIdx.x; idx < nrel * kKC; idx += blockDim.x) { s_ek[idx] = emb_k[idx]; s_ev[idx] = emb_v[idx]; }
+    for (int j = threadIdx.x; j < T; j += blockDim.x) s_m[j] = mask[(size_t)b * T + j];
+    __syncthreads();
+    float* s_q = s_w + (size_t)warp * (kKC + T);
+    float* s_p = s_q + kKC;
+    const float scale = 1.0f / sqrtf((float)kKC);
+    constexpr int kPer = kKC / 32;
+    const int q_begin = blockIdx.x * q_per_cta, q_end = min(T, q_begin + q_per_cta);
+    for (int i = q_begin + warp; i < q_end; i += nwarps) {
+        float* op = out + ((size_t)b * T + i) * C + h * kKC;
+        if (s_m[i] == 0.f) {
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) op[lane + 32 * k] = 0.f;
+            continue;
+        }
+        float qreg[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) { qreg[k] = __ldg(base + (size_t)i * 3 * C + lane + 32 * k); s_q[lane + 32 * k] = qreg[k]; }
+        __syncwarp();
+        float mx = -3.0e38f;
+        for (int j = lane; j < T; j += 32) {
+            float sc;
+            if (s_m[j] == 0.f) {
+                sc = -1e4f;
+            } else {
+                const float* kp = s_k + (size_t)j * kPitch;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+                for (int c = 0; c < kKC; c += 4) {
+                    a0 = fmaf(s_q[c], kp[c], a0); a1 = fmaf(s_q[c + 1], kp[c + 1], a1);
+                    a2 = fmaf(s_q[c + 2], kp[c + 2], a2); a3 = fmaf(s_q[c + 3], kp[c + 3], a3);
+                }
+                sc = ((a0 + a1) + (a2 + a3)) * scale;
+            }
+            s_p[j] = sc;
+        }
+        __syncwarp();
+        // relative-key logits: lanes across channels, one shuffle reduction per offset
+        for (int d = -window; d <= window && window >= 0; ++d) {
+            const int j = i + d;
+            if (j < 0 || j >= T) continue;                  // warp-uniform
+            const float* ep = s_ek + (size_t)(d + window) * kKC;
+            float r = 0.f;
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) r = fmaf(qreg[k], ep[lane + 32 * k], r);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+            if (lane == 0 && s_m[j] != 0.f) s_p[j] += r * scale;
+        }
+        __syncwarp();
+        for (int j = lane; j < T; j += 32) mx = fmaxf(mx, s_p[j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+        for (int j = lane; j < T; j += 32) {
+            const float e = expf(s_p[j] - mx);
+            s_p[j] = e;
+            sum += e;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float inv = 1.0f / sum;
+        __syncwarp();
+        float acc[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) acc[k] = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < T; ++j) {
+            const float p = s_p[j];
+            const float* vp = s_v + (size_t)j * kPitch;
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) acc[k] = fmaf(p, vp[lane + 32 * k], acc[k]);
+        }
+        for (int d = -window; d <= window && window >= 0; ++d) {
+            const int j = i + d;
+            if (j < 0 || j >= T) continue;
+            const float p = s_p[j];
+            const float* ep = s_ev + (size_t)(d + window) * kKC;
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) acc[k] = fmaf(p, ep[lane + 32 * k], acc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) op[lane + 32 * k] = acc[k] * inv;
+        __syncwarp();
+    }
+}
+
 // 1x1 projection to the reference's (B, Cout, T) layout with the mask: out[b,co,t] = (x[b,t,:] . w[co,:] + bias[co]) * mask[b,t]
-// (proj_m :329 and the duration predictor's proj :91-92).  Block = 32 positions, warps stride over co.
-__global__ void proj_nct_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+// (proj_m :329).  Block = 8 positions; thread = output channel, 8 accumulators; wt is the weight transposed to [C][Cout] so that
+// the lanes of a warp read consecutive addresses.
+__global__ void proj_nct_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ bias,
                                 const float* __restrict__ mask, float* __restrict__ out, int T, int C, int Cout) {
-    extern __shared__ float xs[];                     // [C][33]
-    const int b = blockIdx.y, t0 = blockIdx.x * 32;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int idx = threadIdx.x; idx < 32 * C; idx += blockDim.x) {
-        const int p = idx / C, c = idx % C;
-        xs[c * 33 + p] = (t0 + p < T) ? x[((size_t)b * T + t0 + p) * C + c] : 0.f;
+    extern __shared__ float xs[];                     // [8][C]
+    const int b = blockIdx.y, t0 = blockIdx.x * 8;
+    for (int idx = threadIdx.x; idx < 8 * C; idx += blockDim.x) {
+        const int p = idx / C;
+        xs[idx] = (t0 + p < T) ? x[((size_t)b * T + t0) * C + idx] : 0.f;
     }
     __syncthreads();
-    const int t = t0 + lane;
-    const float m = t < T ? mask[(size_t)b * T + t] : 0.f;
-    for (int co = warp; co < Cout; co += nwarps) {
-        const float* wp = w + (size_t)co * C;
-        float acc = 0.f;
-        for (int c = 0; c < C; ++c) acc = fmaf(xs[c * 33 + lane], __ldg(wp + c), acc);
-        if (t < T) out[((size_t)b * Cout + co) * T + t] = (acc + bias[co]) * m;
+    const int co = threadIdx.x;
+    if (co >= Cout) return;
+    float acc[8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) acc[p] = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < C; ++c) {
+        const float wv = __ldg(wt + (size_t)c * Cout + co);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) acc[p] = fmaf(xs[p * C + c], wv, acc[p]);
+    }
+    const float bv = bias[co];
+#pragma unroll
+    for (int p = 0; p < 8; ++p)
+        if (t0 + p < T) out[((size_t)b * Cout + co) * T + t0 + p] = (acc[p] + bv) * mask[(size_t)b * T + t0 + p];
+}
+
+// the duration predictor's final projection (Cout = 1, :91-92): one warp per position
+__global__ void proj1_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                             const float* __restrict__ mask, float* __restrict__ out, long n_pos, int C) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long pos = (long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (pos >= n_pos) return;
+    const float* xp = x + pos * C;
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(xp[c], __ldg(w + c), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[pos] = (acc + bias[0]) * mask[pos];
+}
+
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int Cc) {
+    const int n = R * Cc;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int r = i / Cc, c = i % Cc;
+        dst[(size_t)c * R + r] = src[i];
     }
 }
 
@@ -215,7 +447,7 @@ struct Param { float* p = nullptr; size_t numel = 0; };
 }  // namespace
 
 struct TextEncoder {
-    int device = 0;
+    int device = 0, num_sms = 148;
     int n_vocab, n_feats, C0, F, Fdp, heads, layers, ksize, window, spk_dim, n_spks;
     int C;                                              // encoder width: C0 (+ spk_dim when n_spks > 1)
     std::map<std::string, Param> params;
@@ -225,9 +457,23 @@ struct TextEncoder {
     size_t ws_bytes = 0;
     int* status = nullptr;
     long launches_last_call = 0;
+    long small_m = 1024;                                // B*T up to which the latency-shaped conv kernel is used
+    struct Graph {
+        cudaGraphExec_t exec = nullptr;
+        void* stage = nullptr;
+        long long *tok = nullptr, *len = nullptr;
+        float *spk = nullptr, *mu = nullptr, *logw = nullptr, *mask = nullptr;
+        long launches = 0;
+        unsigned long long last_use = 0;
+    };
+    std::map<std::pair<int, int>, Graph> graphs;        // per (B, T)
+    unsigned long long use_clock = 0;
+    int use_graph = 1;
+    long graph_max_pos = 8192;                          // larger batches are not launch-bound
     ~TextEncoder() {
         cudaSetDevice(device);
         cudaDeviceSynchronize();
+        for (auto& kv : graphs) { if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec); cudaFree(kv.second.stage); }
         for (auto& kv : params) cudaFree(kv.second.p);
         for (auto& kv : packed) cudaFree(kv.second);
         cudaFree(ws); cudaFree(status);
@@ -251,6 +497,32 @@ struct Run {
     cudaStream_t s;
     long launches = 0;
     int rc = 0;
+    // GTTS_ENC_PROFILE=1: an event after every launch, per-launch times on stderr at the end of the call (measurement aid)
+    bool prof = false;
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    void mark(const std::string& name) {
+        if (!prof) return;
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, s);
+        marks.emplace_back(name, ev);
+    }
+    void report() {
+        if (!prof || marks.empty()) return;
+        cudaEventSynchronize(marks.back().second);
+        std::map<std::string, float> agg;
+        float total = 0.f;
+        for (size_t i = 1; i < marks.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+            agg[marks[i].first] += ms;
+            total += ms;
+        }
+        fprintf(stderr, "[text encoder profile] B=%d T=%d: %.1f us over %zu launches\n", B, T, total * 1e3f, marks.size() - 1);
+        for (auto& kv : agg) fprintf(stderr, "   %-28s %9.1f us\n", kv.first.c_str(), kv.second * 1e3f);
+        for (auto& m : marks) cudaEventDestroy(m.second);
+        marks.clear();
+    }
 
     const float* P(const std::string& name, size_t numel) {
         auto it = e->params.find(name);
@@ -270,12 +542,25 @@ struct Run {
         const float* w = W(name + ".weight");
         const float* b = P(name + ".bias", (size_t)Cout);
         if (rc) return;
-        ConvEpilogue ep;
-        memset(&ep, 0, sizeof(ep));
-        ep.bias = b; ep.residual = residual; ep.mask = mask; ep.out = out;
-        if (relu) { ep.act_out = 1; ep.act_slope = 0.f; }
-        rc = conv_ffma(ACT_F32, geom1d(B, T, Cin, Cout, k), x, nullptr, w, ep, s);
+        conv_raw(Cin, Cout, k, x, w, b, residual, mask, out, relu);
+    }
+    void conv_raw(int Cin, int Cout, int k, const float* x, const float* w, const float* b, const float* residual, const float* mask,
+                  float* out, bool relu) {
+        if (rc) return;
+        const long M = (long)B * T;
+        if (M <= e->small_m) {
+            dim3 grid((unsigned)((M + 15) / 16), Cout / 32);
+            conv1d_splitk_kernel<<<grid, 256, 0, s>>>(x, w, b, residual, mask, out, (int)M, T, Cin, Cout, k, relu ? 1 : 0);
+            if (cudaGetLastError() != cudaSuccess) { set_error("text encoder: conv launch failed"); rc = 1; }
+        } else {
+            ConvEpilogue ep;
+            memset(&ep, 0, sizeof(ep));
+            ep.bias = b; ep.residual = residual; ep.mask = mask; ep.out = out;
+            if (relu) { ep.act_out = 1; ep.act_slope = 0.f; }
+            rc = conv_ffma(ACT_F32, geom1d(B, T, Cin, Cout, k), x, nullptr, w, ep, s);
+        }
         ++launches;
+        mark("conv_k" + std::to_string(k) + "_" + std::to_string(Cin) + "_" + std::to_string(Cout));
     }
     void layernorm(const std::string& name, int C, const float* in, const float* mask, float* out, bool relu_after) {
         if (rc) return;
@@ -289,6 +574,7 @@ struct Run {
         else layernorm_kernel<32><<<blocks, wpb * 32, 0, s>>>(in, g, bt, mask, out, n_pos, C, 1e-4f, relu_after ? 1 : 0);
         if (cudaGetLastError() != cudaSuccess) { set_error("text encoder: layernorm launch failed"); rc = 1; }
         ++launches;
+        mark("layernorm_" + std::to_string(C));
     }
 };
 
@@ -329,6 +615,15 @@ int pack_all(TextEncoder* e) {
         if (int rc = pack(f + ".conv_1.weight", e->F, C, e->ksize)) return rc;
         if (int rc = pack(f + ".conv_2.weight", C, e->F, e->ksize)) return rc;
     }
+    {
+        auto it = e->params.find("proj_m.weight");
+        if (it == e->params.end() || !it->second.p) { set_error("text encoder: parameter proj_m.weight was not set"); return 3; }
+        GTTS_REQUIRE(it->second.numel == (size_t)e->n_feats * C, "text encoder: proj_m.weight has the wrong number of elements");
+        float*& dst = e->packed["proj_m.wt"];
+        if (!dst) GTTS_CHECK_CUDA(cudaMalloc((void**)&dst, (size_t)e->n_feats * C * 4));
+        transpose_kernel<<<64, 256>>>(it->second.p, dst, e->n_feats, C);
+        GTTS_CHECK_CUDA(cudaGetLastError());
+    }
     if (int rc = pack("proj_w.conv_1.weight", e->Fdp, C, e->ksize)) return rc;
     if (int rc = pack("proj_w.conv_2.weight", e->Fdp, e->Fdp, e->ksize)) return rc;
     GTTS_CHECK_CUDA(cudaDeviceSynchronize());
@@ -338,8 +633,29 @@ int pack_all(TextEncoder* e) {
 
 template <int kKC>
 int launch_attention(const float* qkv, const float* mask, const float* ek, const float* ev, float* out, int B, int T, int C, int heads,
-                     int window, cudaStream_t s) {
-    const int nwarps = 4;
+                     int window, int num_sms, cudaStream_t s) {
+    const int nrel = window >= 0 ? 2 * window + 1 : 0;
+    {
+        // keys and values of one (sample, head) resident in shared memory
+        const int nwarps = 8;
+        const size_t smem = ((size_t)2 * T * (kKC + 1) + (size_t)2 * nrel * kKC + T + (size_t)nwarps * (kKC + T)) * 4;
+        if (smem <= 220 * 1024 && !getenv("GTTS_ENC_ATTN_GLOBAL")) {
+            static size_t attr = 0;
+            if (smem > 48 * 1024 && smem > attr) {
+                GTTS_CHECK_CUDA(cudaFuncSetAttribute(rel_attention_smem_kernel<kKC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+                attr = 220 * 1024;
+            }
+            // split the queries of a (sample, head) over enough CTAs to fill the GPU once, at least 8 queries (one per warp) each
+            int split = std::max(1, num_sms / std::max(1, B * heads));
+            split = std::min(split, (T + nwarps - 1) / nwarps);
+            const int q_per_cta = (T + split - 1) / split;
+            dim3 grid((T + q_per_cta - 1) / q_per_cta, heads, B);
+            rel_attention_smem_kernel<kKC><<<grid, nwarps * 32, smem, s>>>(qkv, mask, ek, ev, out, T, C, window, q_per_cta);
+            GTTS_CHECK_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
+    const int nwarps = 8;
     const size_t smem = (size_t)nwarps * (T + kKC) * 4;
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
@@ -376,9 +692,12 @@ TextEncoder* text_encoder_new(int n_vocab, int n_feats, int n_channels, int filt
     }
     TextEncoder* e = new TextEncoder();
     e->device = device;
+    e->num_sms = prop.multiProcessorCount;
     e->n_vocab = n_vocab; e->n_feats = n_feats; e->C0 = n_channels; e->F = filter_channels; e->Fdp = filter_channels_dp;
     e->heads = n_heads; e->layers = n_layers; e->ksize = kernel_size; e->window = window_size; e->spk_dim = spk_emb_dim; e->n_spks = n_spks;
     e->C = C;
+    if (const char* sm = getenv("GTTS_ENC_SMALL_M")) e->small_m = atol(sm);
+    if (const char* ug = getenv("GTTS_ENC_GRAPH")) e->use_graph = atoi(ug) != 0;
     if (cudaMalloc((void**)&e->status, 4) != cudaSuccess) { set_error("text_encoder_new: out of device memory"); delete e; return nullptr; }
     cudaMemset(e->status, 0, 4);
     return e;
@@ -393,7 +712,12 @@ int text_encoder_set_param(TextEncoder* e, const char* name, const float* data, 
     GTTS_CHECK_CUDA(cudaSetDevice(e->device));
     GTTS_CHECK_CUDA(cudaDeviceSynchronize());
     Param& p = e->params[name];
-    if (p.p && p.numel != numel) { cudaFree(p.p); p.p = nullptr; }
+    if (p.p && p.numel != numel) {
+        // captured graphs hold the old pointer
+        for (auto& kv : e->graphs) { if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec); cudaFree(kv.second.stage); }
+        e->graphs.clear();
+        cudaFree(p.p); p.p = nullptr;
+    }
     if (!p.p) GTTS_CHECK_CUDA(cudaMalloc((void**)&p.p, numel * 4));
     p.numel = numel;
     GTTS_CHECK_CUDA(cudaMemcpy(p.p, data, numel * 4, cudaMemcpyDefault));
@@ -402,26 +726,120 @@ int text_encoder_set_param(TextEncoder* e, const char* name, const float* data, 
 }
 
 // tokens (B, T) int64, lengths (B) int64, spk (B, spk_emb_dim) or null -> mu (B, n_feats, T), logw (B, 1, T), x_mask (B, 1, T)
+namespace {
+
+size_t workspace_bytes(const TextEncoder* e, int B, int T) {
+    const size_t n_pos = (size_t)B * T, wide = (size_t)std::max(e->F, e->Fdp);
+    return (n_pos * (1 + 3 * (size_t)e->C0 + 3 * (size_t)e->C + 3 * (size_t)e->C + 2 * wide) + 1024) * 4;
+}
+
+void drop_graphs(TextEncoder* e) {
+    for (auto& kv : e->graphs) {
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        cudaFree(kv.second.stage);
+    }
+    e->graphs.clear();
+}
+
+int forward_body(TextEncoder* e, const long long* tokens, const long long* lengths, const float* spk, float* mu, float* logw,
+                 float* x_mask, int B, int T, cudaStream_t s);
+
+}  // namespace
+
+// One forward = ~56 small launches; for a given (B, T) they are captured once as a CUDA graph over fixed staging buffers (tokens,
+// lengths, speaker in; mu, logw, mask out -- a few KB copied on either side), so a call costs one graph launch instead of 56
+// kernel launches from the host.  At most 16 shapes are kept (least recently used goes first); growing the workspace drops them all.
 int text_encoder_forward(TextEncoder* e, const long long* tokens, const long long* lengths, const float* spk, float* mu, float* logw,
                          float* x_mask, int B, int T, cudaStream_t s) {
     GTTS_REQUIRE(e && tokens && lengths && mu && logw && x_mask, "text_encoder_forward: null pointer");
     GTTS_REQUIRE(B >= 1 && T >= 1, "text_encoder_forward: bad batch or length");
     GTTS_REQUIRE(e->n_spks <= 1 || spk != nullptr, "text_encoder_forward: this encoder was built with n_spks > 1: spk is required");
     GTTS_CHECK_CUDA(cudaSetDevice(e->device));
-    GTTS_REQUIRE((size_t)std::max(e->C, e->Fdp) * 33 * 4 <= 48 * 1024, "text_encoder_forward: channel count too large for the projection kernel");
     if (int rc = pack_all(e)) return rc;
-    const int C0 = e->C0, C = e->C, F = e->F, Fdp = e->Fdp;
-    const size_t n_pos = (size_t)B * T;
-    // workspace: mask | x0 (C0) | a (C0) | b (C0) | xe (C) | t1 (C) | t2 (C) | qkv (3C) | wide (max(F, Fdp))
-    const size_t wide = (size_t)std::max(F, Fdp);
-    const size_t need = (n_pos * (1 + 3 * (size_t)C0 + 3 * (size_t)C + 3 * (size_t)C + 2 * wide) + 1024) * 4;
+    const size_t need = workspace_bytes(e, B, T);
     if (need > e->ws_bytes) {
         GTTS_CHECK_CUDA(cudaStreamSynchronize(s));
         GTTS_CHECK_CUDA(cudaDeviceSynchronize());
+        drop_graphs(e);
         cudaFree(e->ws); e->ws = nullptr; e->ws_bytes = 0;
         GTTS_CHECK_CUDA(cudaMalloc((void**)&e->ws, need));
         e->ws_bytes = need;
     }
+    const bool want_graph = e->use_graph && (long)B * T <= e->graph_max_pos && !getenv("GTTS_ENC_PROFILE");
+    if (!want_graph) return forward_body(e, tokens, lengths, spk, mu, logw, x_mask, B, T, s);
+
+    const size_t n_pos = (size_t)B * T;
+    const size_t n_spk = e->n_spks > 1 ? (size_t)B * e->spk_dim : 0;
+    const std::pair<int, int> key(B, T);
+    auto it = e->graphs.find(key);
+    if (it == e->graphs.end()) {
+        GTTS_CHECK_CUDA(cudaStreamSynchronize(s));            // the dry run below shares the workspace with whatever was queued
+        if (e->graphs.size() >= 16) {
+            auto lru = e->graphs.begin();
+            for (auto j = e->graphs.begin(); j != e->graphs.end(); ++j)
+                if (j->second.last_use < lru->second.last_use) lru = j;
+            GTTS_CHECK_CUDA(cudaDeviceSynchronize());
+            if (lru->second.exec) cudaGraphExecDestroy(lru->second.exec);
+            cudaFree(lru->second.stage);
+            e->graphs.erase(lru);
+        }
+        TextEncoder::Graph g;
+        // staging: tokens (n_pos int64) | lengths (B int64) | spk | mu | logw | mask
+        const size_t bytes = (n_pos + B) * 8 + (n_spk + n_pos * e->n_feats + 2 * n_pos) * 4 + 256;
+        GTTS_CHECK_CUDA(cudaMalloc(&g.stage, bytes));
+        char* q = (char*)g.stage;
+        g.tok = (long long*)q; q += n_pos * 8;
+        g.len = (long long*)q; q += (size_t)B * 8;
+        g.spk = (float*)q; q += n_spk * 4;
+        g.mu = (float*)q; q += n_pos * e->n_feats * 4;
+        g.logw = (float*)q; q += n_pos * 4;
+        g.mask = (float*)q;
+        cudaStream_t cs;
+        GTTS_CHECK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        GTTS_CHECK_CUDA(cudaMemcpyAsync(g.tok, tokens, n_pos * 8, cudaMemcpyDeviceToDevice, cs));
+        GTTS_CHECK_CUDA(cudaMemcpyAsync(g.len, lengths, (size_t)B * 8, cudaMemcpyDeviceToDevice, cs));
+        if (n_spk) GTTS_CHECK_CUDA(cudaMemcpyAsync(g.spk, spk, n_spk * 4, cudaMemcpyDeviceToDevice, cs));
+        int rc = forward_body(e, g.tok, g.len, n_spk ? g.spk : nullptr, g.mu, g.logw, g.mask, B, T, cs);   // dry run (validates every launch)
+        if (!rc && cudaStreamSynchronize(cs) != cudaSuccess) { set_error("text encoder: dry run failed"); rc = 1; }
+        cudaGraph_t graph = nullptr;
+        if (!rc) {
+            cudaError_t ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+            if (ce == cudaSuccess) {
+                rc = forward_body(e, g.tok, g.len, n_spk ? g.spk : nullptr, g.mu, g.logw, g.mask, B, T, cs);
+                ce = cudaStreamEndCapture(cs, &graph);
+            }
+            if (!rc && ce != cudaSuccess) { set_error(std::string("text encoder: graph capture failed: ") + cudaGetErrorString(ce)); rc = 1; }
+            if (!rc && cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) { set_error("text encoder: cudaGraphInstantiate failed"); rc = 1; }
+            if (graph) cudaGraphDestroy(graph);
+        }
+        cudaStreamSynchronize(cs);
+        cudaStreamDestroy(cs);
+        if (rc) { cudaFree(g.stage); cudaGetLastError(); return rc; }
+        g.launches = e->launches_last_call;
+        it = e->graphs.emplace(key, g).first;
+    }
+    TextEncoder::Graph& g = it->second;
+    g.last_use = ++e->use_clock;
+    GTTS_CHECK_CUDA(cudaMemcpyAsync(g.tok, tokens, n_pos * 8, cudaMemcpyDeviceToDevice, s));
+    GTTS_CHECK_CUDA(cudaMemcpyAsync(g.len, lengths, (size_t)B * 8, cudaMemcpyDeviceToDevice, s));
+    if (n_spk) GTTS_CHECK_CUDA(cudaMemcpyAsync(g.spk, spk, n_spk * 4, cudaMemcpyDeviceToDevice, s));
+    GTTS_CHECK_CUDA(cudaGraphLaunch(g.exec, s));
+    GTTS_CHECK_CUDA(cudaMemcpyAsync(mu, g.mu, n_pos * e->n_feats * 4, cudaMemcpyDeviceToDevice, s));
+    GTTS_CHECK_CUDA(cudaMemcpyAsync(logw, g.logw, n_pos * 4, cudaMemcpyDeviceToDevice, s));
+    GTTS_CHECK_CUDA(cudaMemcpyAsync(x_mask, g.mask, n_pos * 4, cudaMemcpyDeviceToDevice, s));
+    e->launches_last_call = g.launches;
+    return 0;
+}
+
+namespace {
+
+int forward_body(TextEncoder* e, const long long* tokens, const long long* lengths, const float* spk, float* mu, float* logw,
+                 float* x_mask, int B, int T, cudaStream_t s) {
+    GTTS_REQUIRE((size_t)e->C * 8 * 4 <= 48 * 1024 && e->n_feats <= 1024, "text_encoder_forward: channel count too large for the projection kernel");
+    const int C0 = e->C0, C = e->C, F = e->F, Fdp = e->Fdp;
+    const size_t n_pos = (size_t)B * T;
+    // workspace: mask | x0 (C0) | a (C0) | b (C0) | xe (C) | t1 (C) | t2 (C) | qkv (3C) | wide (max(F, Fdp)) x 2
+    const size_t wide = (size_t)std::max(F, Fdp);
     float* p = e->ws;
     auto take = [&](size_t n) { float* r = p; p += (n + 15) / 16 * 16; return r; };
     float* mask = take(n_pos);
@@ -431,6 +849,8 @@ int text_encoder_forward(TextEncoder* e, const long long* tokens, const long lon
     float* w1 = take(n_pos * wide); float* w2 = take(n_pos * wide);
 
     Run r{e, B, T, s};
+    r.prof = getenv("GTTS_ENC_PROFILE") != nullptr;
+    r.mark("start");
     // ---- embedding (:322-324)
     {
         const float* emb = r.P("emb.weight", (size_t)e->n_vocab * C0);
@@ -469,13 +889,10 @@ int text_encoder_forward(TextEncoder* e, const long long* tokens, const long lon
         const std::string a = "encoder.attn_layers." + std::to_string(l), f = "encoder.ffn_layers." + std::to_string(l);
         // q | k | v in one 1x1 conv
         {
-            ConvEpilogue ep;
-            memset(&ep, 0, sizeof(ep));
-            ep.bias = r.W(a + ".qkv.bias"); ep.out = qkv;
+            const float* qb = r.W(a + ".qkv.bias");
             const float* w = r.W(a + ".qkv.weight");
             if (r.rc) break;
-            r.rc = conv_ffma(ACT_F32, geom1d(B, T, C, 3 * C, 1), x, nullptr, w, ep, s);
-            ++r.launches;
+            r.conv_raw(C, 3 * C, 1, x, w, qb, nullptr, nullptr, qkv, false);
             if (r.rc) break;
         }
         {
@@ -486,11 +903,12 @@ int text_encoder_forward(TextEncoder* e, const long long* tokens, const long lon
                 if (r.rc) break;
             }
             int rc = 0;
-            if (kc == 32) rc = launch_attention<32>(qkv, mask, ek, ev, t1, B, T, C, e->heads, e->window, s);
-            else if (kc == 64) rc = launch_attention<64>(qkv, mask, ek, ev, t1, B, T, C, e->heads, e->window, s);
-            else if (kc == 96) rc = launch_attention<96>(qkv, mask, ek, ev, t1, B, T, C, e->heads, e->window, s);
-            else rc = launch_attention<128>(qkv, mask, ek, ev, t1, B, T, C, e->heads, e->window, s);
+            if (kc == 32) rc = launch_attention<32>(qkv, mask, ek, ev, t1, B, T, C, e->heads, e->window, e->num_sms, s);
+            else if (kc == 64) rc = launch_attention<64>(qkv, mask, ek, ev, t1, B, T, C, e->heads, e->window, e->num_sms, s);
+            else if (kc == 96) rc = launch_attention<96>(qkv, mask, ek, ev, t1, B, T, C, e->heads, e->window, e->num_sms, s);
+            else rc = launch_attention<128>(qkv, mask, ek, ev, t1, B, T, C, e->heads, e->window, e->num_sms, s);
             ++r.launches;
+            r.mark("rel_attention");
             if (rc) return rc;
         }
         r.conv(a + ".conv_o", C, C, 1, t1, x, nullptr, xn, false);                        // x + attn(x)
@@ -502,13 +920,14 @@ int text_encoder_forward(TextEncoder* e, const long long* tokens, const long lon
     if (r.rc) return r.rc;
     // ---- mu = proj_m(x) * mask (:329), in the reference's (B, n_feats, T) layout
     {
-        const float* w = r.P("proj_m.weight", (size_t)e->n_feats * C);
+        const float* w = r.W("proj_m.wt");
         const float* b = r.P("proj_m.bias", (size_t)e->n_feats);
         if (r.rc) return r.rc;
-        dim3 grid((T + 31) / 32, B);
-        proj_nct_kernel<<<grid, 256, (size_t)C * 33 * 4, s>>>(x, w, b, mask, mu, T, C, e->n_feats);
+        dim3 grid((T + 7) / 8, B);
+        proj_nct_kernel<<<grid, (e->n_feats + 31) / 32 * 32, (size_t)C * 8 * 4, s>>>(x, w, b, mask, mu, T, C, e->n_feats);
         GTTS_CHECK_CUDA(cudaGetLastError());
         ++r.launches;
+        r.mark("proj_mu");
     }
     // ---- duration predictor (:84-93): conv -> ReLU -> LayerNorm, twice, 1x1 proj, mask
     r.conv("proj_w.conv_1", C, Fdp, e->ksize, x, nullptr, nullptr, w1, true);
@@ -520,14 +939,17 @@ int text_encoder_forward(TextEncoder* e, const long long* tokens, const long lon
         const float* w = r.P("proj_w.proj.weight", (size_t)Fdp);
         const float* b = r.P("proj_w.proj.bias", 1);
         if (r.rc) return r.rc;
-        dim3 grid((T + 31) / 32, B);
-        proj_nct_kernel<<<grid, 32, (size_t)Fdp * 33 * 4, s>>>(w2, w, b, mask, logw, T, Fdp, 1);
+        proj1_kernel<<<(unsigned)((n_pos + 7) / 8), 256, 0, s>>>(w2, w, b, mask, logw, (long)n_pos, Fdp);
         GTTS_CHECK_CUDA(cudaGetLastError());
         ++r.launches;
+        r.mark("proj_logw");
     }
+    r.report();
     e->launches_last_call = r.launches;
     return 0;
 }
+
+}  // namespace
 
 // 1 if the last forward saw a token id outside [0, n_vocab) (synchronises the stream)
 int text_encoder_check_tokens(TextEncoder* e, cudaStream_t s) {

@@ -331,11 +331,61 @@ def stage_vocoder():
         print(gen.profile(B, T), flush=True)
 
 
+def stage_encoder():
+    """text encoder: forward time at a few shapes, with the latency-shaped conv kernel on (default threshold) and off"""
+    import importlib
+    te = importlib.import_module("grad-tts_b200.model.text_encoder")
+    from oracle import text_encoder_oracle
+    synth = pkg.synth
+    cfg = synth.TEXT_ENCODER_CONFIGS["ref"]
+    sd = synth.make_text_encoder_state_dict(cfg, seed=1)
+    sd_d = {k: v.to(DEV) for k, v in sd.items()}
+    for small_m in ("1024", "0", "100000"):
+        os.environ["GTTS_ENC_SMALL_M"] = small_m
+        enc = te.TextEncoder(**cfg)
+        enc.load_state_dict(sd)
+        enc = enc.to(DEV).eval()
+        for (B, T) in [(1, 100), (4, 150), (16, 200), (128, 200)]:
+            x, lengths, _ = synth.make_text_inputs(cfg, B, T, seed=3, ragged=False)
+            xd, ld = x.to(DEV), lengths.to(DEV)
+            mu, logw, _ = enc(xd, ld)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                enc(xd, ld)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 10
+            with torch.no_grad():
+                mu_r, logw_r, _ = text_encoder_oracle.text_encoder_forward(sd, cfg, x, lengths)
+            print(f"small_m={small_m:>6s} B={B:3d} T={T:3d}: {ms:7.3f} ms  max-abs mu {float((mu.cpu() - mu_r).abs().max()):.2e} "
+                  f"logw {float((logw.cpu() - logw_r).abs().max()):.2e}", flush=True)
+        del enc
+    for (B, T) in [(1, 100), (128, 200)]:
+        x, lengths, _ = synth.make_text_inputs(cfg, B, T, seed=3, ragged=False)
+        xd, ld = x.to(DEV), lengths.to(DEV)
+        for tf32 in (True, False):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            with torch.no_grad():
+                for _ in range(2):
+                    text_encoder_oracle.text_encoder_forward(sd_d, cfg, xd, ld)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    text_encoder_oracle.text_encoder_forward(sd_d, cfg, xd, ld)
+                e1.record()
+                torch.cuda.synchronize()
+            print(f"eager tf32={tf32} B={B} T={T}: {e0.elapsed_time(e1) / 5:.3f} ms", flush=True)
+
+
 if __name__ == "__main__":
     st = sys.argv[1]
     print(f"===== stage {st} on {torch.cuda.get_device_name(0)}", flush=True)
     {"profile_vjp": stage_profile_vjp, "mas": stage_mas, "conv_ffma": lambda: (stage_conv(0, 0), stage_conv(0, 1)), "conv_tc": lambda: stage_conv(1, 1),
      "dec_fp32": lambda: stage_dec("fp32"), "dec_bf16_ffma": lambda: stage_dec("bf16", 0),
-     "dec_bf16_tc": lambda: stage_dec("bf16", 1), "perf": stage_perf, "profile": stage_profile, "halo": stage_halo, "convdbg": stage_convdbg, "mbench": stage_mbench, "align": stage_align, "vocoder": stage_vocoder}[st]()
+     "dec_bf16_tc": lambda: stage_dec("bf16", 1), "perf": stage_perf, "profile": stage_profile, "halo": stage_halo, "convdbg": stage_convdbg, "mbench": stage_mbench, "align": stage_align, "vocoder": stage_vocoder, "encoder": stage_encoder}[st]()
     torch.cuda.synchronize()
     print(f"===== stage {st} done", flush=True)
