@@ -440,8 +440,15 @@ def main():
             eager = gpu_eager_record(pkg, torch, dev, configs, line)
             varlen = varlen_record(pkg, torch, get_decoder, dev)
             line["likelihood"] = likelihood_record(pkg, torch, get_decoder, dev)
-            line["vocoder"] = vocoder_record(pkg, torch, dev, line["value"])
-            line["text_encoder"] = text_encoder_record(pkg, torch, dev)
+            def guarded(fn, *a):                         # the records around the headline path must not take the line down
+                try:
+                    return fn(*a)
+                except Exception as ex:
+                    torch.cuda.empty_cache()
+                    return {"error": repr(ex)[:300]}
+            line["vocoder"] = guarded(vocoder_record, pkg, torch, dev, line["value"])
+            line["text_encoder"] = guarded(text_encoder_record, pkg, torch, dev)
+            line["pipeline"] = guarded(pipeline_record, pkg, torch, dev)
             line["configs"] = configs
             line["mas"] = mas
             line["fp32_strict"] = fp32
@@ -632,6 +639,51 @@ def likelihood_record(pkg, torch, get_decoder, dev):
         out["fp32_vs_eager_rel_err_of_bpd"] = float(((vals["fp32"][:bs] - ref).abs() / ref.abs()).max())
     except Exception as e:
         out["gpu_eager"] = {"error": repr(e)[:200]}
+    return out
+
+
+def pipeline_record(pkg, torch, dev):
+    """Single-utterance serving latency, text to waveform (the loop body of the reference's inference.py:84-97): token ids on the
+    host -> text encoder -> durations / alignment -> 10-step decoder (BASELINE C1's step count) -> HiFi-GAN -> int16 samples on the
+    host.  Synthetic weights; the durations (hence the mel length) are whatever the random duration predictor says."""
+    ecfg = pkg.synth.TEXT_ENCODER_CONFIGS["ref"]
+    net = pkg.GradTTS(ecfg["n_vocab"], 1, 64, 192, 768, 256, 2, 6, 3, 0.1, 4, 80, 64, 0.05, 20.0, 1000)
+    net.encoder.load_state_dict(pkg.synth.make_text_encoder_state_dict(ecfg, seed=1))
+    net.decoder.load_state_dict(pkg.synth.make_decoder_state_dict(1, seed=0, g=0.05))
+    net = net.to(dev).eval()
+    vcfg = pkg.synth.VOCODER_CONFIGS["v1"]
+    voc = pkg.hifigan.Generator(pkg.hifigan.AttrDict(vcfg))
+    voc.load_state_dict(pkg.synth.make_vocoder_state_dict(vcfg, seed=1))
+    voc = voc.to(dev).eval()
+    voc.remove_weight_norm()
+    x, lengths, _ = pkg.synth.make_text_inputs(ecfg, 1, 100, seed=3, ragged=False)
+
+    def run():
+        torch.manual_seed(0)
+        return pkg.inference.synthesize(net, voc, x.to(dev), lengths.to(dev), n_timesteps=10)
+    audio, y_dec, _ = run()
+    run()
+    times = []
+    for _ in range(5):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        audio, y_dec, _ = run()
+        times.append((time.perf_counter() - t0) * 1e3)
+    frames = int(y_dec.shape[-1])
+    out = {"workload": "1 utterance, 100 tokens, 10 Euler steps, HiFi-GAN V1; host token ids -> host int16 samples (wall clock, median of 5)",
+           "ms": sorted(times)[len(times) // 2], "ms_all": times, "mel_frames": frames, "audio_seconds": frames * 256 / 22050,
+           "finite": bool(torch.isfinite(y_dec).all())}
+    out["rtf"] = out["ms"] * 1e-3 / out["audio_seconds"]
+    # where it goes (device time of each stage on its own)
+    xd, ld = x.to(dev), lengths.to(dev)
+    out["stage_ms"] = {"text_encoder": _event_time_ms(torch, lambda: net.encoder(xd, ld), 5, 2),
+                       "vocoder": _event_time_ms(torch, lambda: voc(y_dec), 5, 2)}
+    frames4 = (frames + 3) // 4 * 4                              # fix_len_compatibility (model/utils.py:13-17)
+    mask = torch.ones(1, 1, frames4, device=dev)
+    z = torch.randn(1, 80, frames4, device=dev)
+    out["stage_ms"]["decoder_10_steps"] = _event_time_ms(torch, lambda: net.decoder(z, mask, z, 10), 5, 2)
+    del net, voc
+    torch.cuda.empty_cache()
     return out
 
 

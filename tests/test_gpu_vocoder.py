@@ -125,3 +125,23 @@ def test_vocoder_rejects_bad_input(pkg, synth):
     arr = lambda xs: (ctypes.c_int * len(xs))(*xs)               # noqa: E731
     # upsample kernel smaller than its rate
     assert lib.gtts_vocoder_create(ctypes.byref(h), 1, 1, arr([8]), arr([4]), 64, 1, arr([3]), arr([1]), 1, 80, 0) != 0
+
+
+def test_synthesize_text_to_waveform(pkg, synth):
+    """inference.py:84-97 in one call: tokens -> int16 samples; equals the manual composition of its parts."""
+    ecfg = synth.TEXT_ENCODER_CONFIGS["ref"]
+    net = pkg.GradTTS(ecfg["n_vocab"], 1, 64, 192, 768, 256, 2, 6, 3, 0.1, 4, 80, 64, 0.05, 20.0, 1000)
+    net.encoder.load_state_dict(synth.make_text_encoder_state_dict(ecfg, seed=61), strict=True)
+    net.decoder.load_state_dict(synth.make_decoder_state_dict(1, seed=0, g=0.05), strict=True)
+    net = net.cuda().eval()
+    voc, _, _ = _make(pkg, synth, "v1", 62)
+    x, lengths, _ = synth.make_text_inputs(ecfg, 2, 12, seed=63)
+    torch.manual_seed(3)
+    audio, y_dec, attn = pkg.inference.synthesize(net, voc, x.cuda(), lengths.cuda(), n_timesteps=2)
+    assert audio.dtype == torch.int16 and audio.device.type == "cpu" and audio.shape == (2, y_dec.shape[-1] * 256)
+    torch.manual_seed(3)
+    _, y2, _ = net(x.cuda(), lengths.cuda(), n_timesteps=2, temperature=1.5)
+    assert torch.equal(y2, y_dec)
+    want = (voc(y2).squeeze(1).clamp(-1, 1) * 32768).to(torch.int16).cpu()
+    assert torch.equal(audio, want)
+    assert int(audio.abs().max()) > 0
