@@ -143,6 +143,7 @@ struct Decoder {
                               // wins where launches are latency-bound (B = 1, T = 400: 21 us vs 17 + 8.6 us per Block) and loses on big
                               // batches (chunk 16 x 1720: 128->128 @h40 249 vs 109 + 57 us) because every sample costs one grid barrier.
     int fuse_epi_max_b = 2;
+    int side_lanes = 1;       // small batches: time-embedding MLP and res_conv on a parallel branch of the step graph (GTTS_SIDE=0: off)
     int fuse_async = 0;       // 1: GroupNorm+Mish(+time bias / residual) by asynchronous apply warps inside the Block conv (the raw tile goes
                               // through L2, the MMA pipeline never waits).  Correct and bitwise equal to the separate pass, but OFF: with the
                               // registers the conv leaves (72 per thread at 896 threads) eight apply warps keep only ~8 KB of loads in flight
@@ -488,11 +489,25 @@ struct Plan {
     std::vector<std::function<int(cudaStream_t)>> ops;
     struct OpInfo { std::string name; int is_conv; double flops; double bytes; };
     std::vector<OpInfo> info;
+    // Small batches leave most SMs idle, so ops that are off the critical path (the time-embedding MLP, a ResnetBlock's 1x1
+    // res_conv) are captured on a side stream -- a parallel branch of the step graph -- and joined before their first consumer.
+    // lane[i] = 1: op i forks from the main branch at its position; join[i] = 1: the main branch waits for every open side op first.
+    // Eager replays (dry run, profile, no-graph mode) just run the list in order.
+    std::vector<uint8_t> lane, join;
+    int cur_lane = 0;
+    bool cur_join = false, side_open = false;
     void push(const std::string& name, int is_conv, double flops, double bytes, std::function<int(cudaStream_t)> fn) {
         ops.push_back(std::move(fn));
         info.push_back(OpInfo{name, is_conv, flops, bytes});
+        lane.push_back((uint8_t)cur_lane);
+        join.push_back(cur_join ? 1 : 0);
+        if (cur_lane) side_open = true;
+        if (cur_join) side_open = false;
+        cur_lane = 0; cur_join = false;
         kernels_per_step++;
     }
+    void on_side() { cur_lane = 1; }                       // the next push goes to the side branch
+    void join_side() { if (side_open) cur_join = true; }   // the next push waits for the side branch (no-op if nothing is open)
     // plan-owned I/O
     float *xt = nullptr, *mu = nullptr, *m0 = nullptr, *m1 = nullptr, *m2 = nullptr, *splane = nullptr, *spk = nullptr;
     float *tb = nullptr, *t_tab = nullptr, *beta_tab = nullptr, *t_per_sample = nullptr, *score = nullptr;
@@ -647,6 +662,9 @@ struct PlanBuilder {
 
     struct Apply { const float* gamma; const float* beta; const float* tbias; int tb_bstride; void* async_out; };
 
+    // small batches: off-critical-path ops go to a parallel branch of the step graph (Plan::lane)
+    bool side_lanes() const { return d->side_lanes && B <= d->fuse_epi_max_b && !vjp && !strict; }   // (fp32 convs are several launches)
+
     // true when a Block conv of this geometry can finish GroupNorm+Mish in its own epilogue (ConvEpilogue::apply)
     bool can_apply(const ConvGeom& g) const {
         if (vjp || !use_tc() || d->halo_mode != 2 || d->fuse_epi == 0 || (d->fuse_epi == 1 && B > d->fuse_epi_max_b)) return false;
@@ -736,6 +754,21 @@ struct PlanBuilder {
         void* out = act(lvl, Co);
         float* st1 = stats(); float* st2 = stats();
         if (failed) return nullptr;
+        // the residual branch first (the fused block2 epilogue adds it); at small batch it runs beside block1's conv
+        const void* resid = nullptr;
+        bool first_res = false;
+        if (r == 0) {
+            first_res = true;
+        } else if (R.wres) {
+            void* rb = act(lvl, Co);
+            if (failed) return nullptr;
+            if (side_lanes()) pl->on_side();
+            add_conv(geom_1x1(B, H[lvl], W[lvl], c0, c1, Co, 0), x0, x1, R.wres, Co, R.bres, nullptr, nullptr, rb, nullptr);
+            resid = rb;
+        } else {
+            resid = x0;                                   // Identity(x * mask): x is stored masked
+        }
+        if (failed) return nullptr;
         if (r == 0) {
             FirstConvArgs f;
             memset(&f, 0, sizeof(f));
@@ -756,25 +789,17 @@ struct PlanBuilder {
         } else {
             add_conv(g1, x0, x1, R.b1.w, 9 * Co, R.b1.bias, nullptr, nullptr, raw1, st1);
         }
-        // the residual branch first: the fused block2 epilogue adds it
-        const void* resid = nullptr;
-        bool first_res = false;
-        if (r == 0) {
-            first_res = true;
-        } else if (R.wres) {
-            void* rb = act(lvl, Co);
-            add_conv(geom_1x1(B, H[lvl], W[lvl], c0, c1, Co, 0), x0, x1, R.wres, Co, R.bres, nullptr, nullptr, rb, nullptr);
-            resid = rb;
-        } else {
-            resid = x0;                                   // Identity(x * mask): x is stored masked
-        }
-        if (failed) return nullptr;
         if (fuse2) {
             // block1's GroupNorm + Mish + time bias + mask are applied by block2's conv on its operand tiles
             InFuse fz{st1, R.b1.gamma, R.b1.beta, tb, tb_bstride, lmask[lvl]};
+            pl->join_side();
             add_conv(g2, raw1, nullptr, R.b2.w, 9 * Co, R.b2.bias, nullptr, nullptr, raw2, st2, &fz);
         } else {
-            if (!ap1 && !as1) add_gn_apply(lvl, Co, raw1, st1, R.b1, tb, nullptr, false, a1);
+            if (!ap1 && !as1) {
+                if (r == 0) pl->join_side();                 // the time-embedding biases (side branch) are first used here
+                add_gn_apply(lvl, Co, raw1, st1, R.b1, tb, nullptr, false, a1);
+            }
+            if (ap2 || as2) pl->join_side();                  // this conv's epilogue adds the res_conv output
             if (ap2) {
                 Apply ap{R.b2.gamma, R.b2.beta, nullptr, 0, nullptr};
                 add_conv(g2, a1, nullptr, R.b2.w, 9 * Co, R.b2.bias, resid, lmask[lvl], out, st2, nullptr, &ap);
@@ -785,7 +810,10 @@ struct PlanBuilder {
                 add_conv(g2, a1, nullptr, R.b2.w, 9 * Co, R.b2.bias, nullptr, nullptr, raw2, st2);
             }
         }
-        if (!ap2 && !as2) add_gn_apply(lvl, Co, raw2, st2, R.b2, nullptr, resid, first_res, out);
+        if (!ap2 && !as2) {
+            pl->join_side();
+            add_gn_apply(lvl, Co, raw2, st2, R.b2, nullptr, resid, first_res, out);
+        }
         release(raw1); release(a1); release(raw2);
         if (resid != x0) release(resid);
         if (vjp) {
@@ -1274,6 +1302,7 @@ struct PlanBuilder {
             float* tb = pl->tb;
             int nb = pl->est_mode ? B : 1;
             bool st_ = strict;
+            if (side_lanes()) pl->on_side();                  // first consumer: the gn_apply of the first block
             pl->push("temb", 0, 0.0, 0.0, [tw, tsrc, step, is_table, pes, tb, nb, st_](cudaStream_t s) {
                 return temb_bias(tw, tsrc, step, is_table, pes, tb, nb, st_, s);
             });
@@ -1422,9 +1451,35 @@ int plan_create(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde,
     GTTS_CHECK_CUDA(cudaGetLastError());
     if (d->use_graph) {
         cudaGraph_t graph = nullptr;
+        bool any_side = false;
+        for (uint8_t l : pl->lane) any_side = any_side || l;
+        cudaStream_t side = nullptr;
+        std::vector<cudaEvent_t> evs;
+        if (any_side) GTTS_CHECK_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        auto new_event = [&]() { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); evs.push_back(e); return e; };
         GTTS_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-        rc = run_ops(cs);
+        if (!any_side) {
+            rc = run_ops(cs);
+        } else {
+            std::vector<cudaEvent_t> open;                   // completion events of side ops not yet joined
+            for (size_t i = 0; i < pl->ops.size() && !rc; ++i) {
+                if (pl->lane[i]) {
+                    cudaEvent_t f = new_event(), j = new_event();
+                    cudaEventRecord(f, cs);
+                    cudaStreamWaitEvent(side, f, 0);
+                    rc = pl->ops[i](side);
+                    cudaEventRecord(j, side);
+                    open.push_back(j);
+                } else {
+                    if (pl->join[i]) { for (cudaEvent_t j : open) cudaStreamWaitEvent(cs, j, 0); open.clear(); }
+                    rc = pl->ops[i](cs);
+                }
+            }
+            for (cudaEvent_t j : open) cudaStreamWaitEvent(cs, j, 0);   // every branch rejoins before the capture ends
+        }
         cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        for (cudaEvent_t e : evs) cudaEventDestroy(e);
+        if (side) cudaStreamDestroy(side);
         if (rc || ce != cudaSuccess) {
             if (graph) cudaGraphDestroy(graph);
             cudaStreamDestroy(cs);
@@ -1457,7 +1512,8 @@ int get_plan(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, cu
     std::string key = std::to_string((int)kind) + ":" + std::to_string(B) + ":" + std::to_string(T) + ":" +
                       (est_mode ? "e" : "s") + (sde ? "n" : "o") + (vjp ? (pgrads ? "p" : "v") : "-") + (d->use_graph ? "g" : "x") +
                       std::to_string(d->conv_impl_bf16) + std::to_string(d->halo_mode) + std::to_string(d->fused_attn) + std::to_string(d->fuse_gn) +
-                      std::to_string(d->fuse_epi) + "." + std::to_string(d->fuse_epi_max_b) + "." + std::to_string(d->fp32_tc) + std::to_string(d->fuse_async);
+                      std::to_string(d->fuse_epi) + "." + std::to_string(d->fuse_epi_max_b) + "." + std::to_string(d->fp32_tc) + std::to_string(d->fuse_async) +
+                      std::to_string(d->side_lanes);
     auto it = d->plans.find(key);
     if (it != d->plans.end()) {
         it->second.last_use = ++d->use_clock;
@@ -1741,6 +1797,7 @@ Decoder* decoder_new(int n_spks, int n_feats, int dim, double beta_min, double b
     if (const char* e = getenv("GTTS_FUSE_GN")) d->fuse_gn = atoi(e);
     if (const char* e = getenv("GTTS_FP32_TC")) d->fp32_tc = atoi(e);
     if (const char* e = getenv("GTTS_FUSE_ASYNC")) d->fuse_async = atoi(e);
+    if (const char* e = getenv("GTTS_SIDE")) d->side_lanes = atoi(e);
     if (cudaEventCreateWithFlags(&d->done_ev, cudaEventDisableTiming) != cudaSuccess) {
         set_error("cudaEventCreate failed"); cudaGetLastError(); delete d; return nullptr;
     }
@@ -1791,6 +1848,7 @@ int decoder_set_option(Decoder* d, const char* key, int value) {
     else if (k == "fuse_epi_max_b") d->fuse_epi_max_b = value;
     else if (k == "fp32_tc") d->fp32_tc = value;
     else if (k == "fuse_async") d->fuse_async = value;
+    else if (k == "side_lanes") d->side_lanes = value;
     else { set_error("unknown option " + k); return 2; }
     return 0;
 }
