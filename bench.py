@@ -449,6 +449,7 @@ def main():
             line["vocoder"] = guarded(vocoder_record, pkg, torch, dev, line["value"])
             line["text_encoder"] = guarded(text_encoder_record, pkg, torch, dev)
             line["pipeline"] = guarded(pipeline_record, pkg, torch, dev)
+            line["training"] = guarded(training_record, pkg, torch, get_decoder, dev)
             line["configs"] = configs
             line["mas"] = mas
             line["fp32_strict"] = fp32
@@ -683,6 +684,56 @@ def pipeline_record(pkg, torch, dev):
     z = torch.randn(1, 80, frames4, device=dev)
     out["stage_ms"]["decoder_10_steps"] = _event_time_ms(torch, lambda: net.decoder(z, mask, z, 10), 5, 2)
     del net, voc
+    torch.cuda.empty_cache()
+    return out
+
+
+def training_record(pkg, torch, get_decoder, dev):
+    """Decoder part of one training step at the reference's training shape (params.py: batch_size 16, out_size 2 s -> 172 frames):
+    diffusion loss forward + backward to every decoder parameter (model/diffusion.py:274-287, train.py:104-118).  Ours: the
+    autograd.Function over gtts_decoder_estimator_backward.  Baseline: the reference's op sequence with torch.autograd
+    (oracle/loss_oracle.py) eager on this GPU."""
+    from oracle import loss_oracle
+    Bt, Tt = 16, 172
+    x0, mask, mu, _, _ = pkg.synth.make_inputs(Bt, Tt, 1, seed=11, ragged=True)
+    a = [v.to(dev) for v in (x0, mask, mu)]
+    tt = torch.rand(Bt, generator=torch.Generator().manual_seed(1)).clamp(1e-5, 1 - 1e-5).to(dev)
+    z = torch.randn(Bt, 80, Tt, generator=torch.Generator().manual_seed(2)).to(dev)
+    out = {"workload": f"loss_t forward + backward, {Bt} x {Tt} frames, n_spks = 1, all 172 parameter tensors", "unit": "ms per step"}
+    sd = pkg.synth.make_decoder_state_dict(1, seed=0, g=0.05)
+    for prec in ("bf16", "fp32"):
+        dec = pkg.Diffusion(80, 64, 1, 64, 0.05, 20.0, 1000)
+        dec.load_state_dict(sd)
+        dec = dec.to(dev).train()
+        dec.precision = prec
+
+        def step():
+            for p_ in dec.parameters():
+                p_.grad = None
+            loss, _ = dec.loss_t(a[0], a[1], a[2], tt, noise=z)
+            loss.backward()
+            return loss
+        loss = step()
+        ms = _event_time_ms(torch, step, 5, 2)
+        out[prec] = {"ms": ms, "loss": float(loss), "grads_finite": bool(all(torch.isfinite(p_.grad).all() for p_ in dec.parameters()))}
+        del dec
+    sd_d = {k: v.to(dev) for k, v in sd.items()}
+    eager = {}
+    for mode in ("tf32_default", "bf16_autocast"):
+        def estep():
+            if mode == "bf16_autocast":
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return loss_oracle.loss_t_grads(sd_d, a[0], a[1], a[2], tt, z, None, 1)
+            return loss_oracle.loss_t_grads(sd_d, a[0], a[1], a[2], tt, z, None, 1)
+        try:
+            l_e = estep()[0]
+            eager[mode] = {"ms": _event_time_ms(torch, estep, 5, 2), "loss": float(l_e)}
+        except Exception as ex:
+            eager[mode] = {"error": repr(ex)[:200]}
+            torch.cuda.empty_cache()
+    out["gpu_eager_baseline"] = eager
+    best = min((v["ms"] for v in eager.values() if "ms" in v), default=None)
+    out["vs_gpu_eager"] = (best / out["bf16"]["ms"]) if best else None
     torch.cuda.empty_cache()
     return out
 

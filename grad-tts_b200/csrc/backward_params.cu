@@ -7,6 +7,8 @@
 //   GroupNorm      dgamma[c], dbeta[c] = sum g_y * mask * Mish'(n) * {xhat, 1}      (gn_param_grad)
 //   final conv, first conv / first res_conv (tiny K): dedicated kernels
 // All reductions are two-stage and run in a fixed order (deterministic); accumulation in fp32, inputs in the activation type.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ops.h"
 
@@ -88,6 +90,92 @@ wgrad_kernel(ConvGeom g, const T* __restrict__ gout, const T* __restrict__ x0, c
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) o[(size_t)(co0 + ty * 4 + i) * cin_tot + ci0 + tx * 4 + j] = acc[i][j];
+}
+
+// bf16 activations: the same implicit GEMM on the tensor cores (mma.sync m16n8k16, fp32 accumulate).  Both operands are
+// [pixel][channel] rows, i.e. K-outermost, so both fragments come from ldmatrix.trans.  Same grid, pixel slicing and partial layout as
+// wgrad_kernel (the CUDA-core kernel above, which stays for fp32 activations): CTA = (tap, 64 output channels, 64 input channels,
+// pixel slice), 8 warps x (16 co x 32 ci), 32 pixels per step with the next step's global loads issued before the MMAs.
+// Measured before this kernel: wgrad was 71 % of the training step at 26 TFLOP/s (profiles/r02_profile_train_v1.txt).
+__device__ __forceinline__ void wg_ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_ptr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(smem_ptr)));
+}
+__device__ __forceinline__ void wg_mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256)
+wgrad_mma_kernel(ConvGeom g, const __nv_bfloat16* __restrict__ gout, const __nv_bfloat16* __restrict__ x0,
+                 const __nv_bfloat16* __restrict__ x1, float* __restrict__ partial, int slices, long pix_per_slice) {
+    constexpr int kPitch = 72;                                        // bf16 per pixel row: 64 + 8 pad (144 B, conflict-free ldmatrix)
+    __shared__ __align__(16) __nv_bfloat16 gs[kWgPix * kPitch];
+    __shared__ __align__(16) __nv_bfloat16 xs[kWgPix * kPitch];
+    const int pt = blockIdx.x, ph = pt / g.ntaps, tap = pt % g.ntaps;
+    const int co0 = blockIdx.y * 64;
+    const int cin_tot = g.Cin0 + g.Cin1;
+    const int nci = cin_tot / 64;
+    const int ci0 = (blockIdx.z % nci) * 64, slice = blockIdx.z / nci;
+    const long npix = (long)g.B * g.Hg * g.Wg;
+    const long p_lo = slice * pix_per_slice, p_hi = min(npix, p_lo + pix_per_slice);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = (warp & 3) * 16, n0 = (warp >> 2) * 32;
+    const int j = lane >> 3, r = lane & 7;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    const int lp = tid >> 3, lv = (tid & 7) * 8;                      // loader: pixel lp of the group, channels lv..lv+7
+    const __nv_bfloat16* xsrc = ci0 < g.Cin0 ? x0 : x1;
+    const int xc = ci0 < g.Cin0 ? g.Cin0 : g.Cin1, xoff = ci0 < g.Cin0 ? ci0 : ci0 - g.Cin0;
+    const long hw = (long)g.Hg * g.Wg;
+    uint4 gv, xv;
+    auto fetch = [&](long p0) {
+        const long q = p0 + lp;
+        gv = make_uint4(0u, 0u, 0u, 0u);
+        xv = make_uint4(0u, 0u, 0u, 0u);
+        if (q < p_hi) {
+            const int b = (int)(q / hw);
+            const int rem = (int)(q - (long)b * hw), jj = rem / g.Wg, ii = rem - jj * g.Wg;
+            const int oh = jj * g.out_step + g.oy[ph], ow = ii * g.out_step + g.ox[ph];
+            const int ih = jj * g.stride + g.dy[ph][tap], iw = ii * g.stride + g.dx[ph][tap];
+            if (ih >= 0 && ih < g.Hin && iw >= 0 && iw < g.Win) {
+                gv = __ldg(reinterpret_cast<const uint4*>(gout + (((size_t)b * g.Hout + oh) * g.Wout + ow) * g.Cout + co0 + lv));
+                xv = __ldg(reinterpret_cast<const uint4*>(xsrc + (((size_t)b * g.Hin + ih) * g.Win + iw) * xc + xoff + lv));
+            }
+        }
+    };
+    if (p_lo < p_hi) fetch(p_lo);
+    for (long p0 = p_lo; p0 < p_hi; p0 += kWgPix) {
+        __syncthreads();
+        *reinterpret_cast<uint4*>(&gs[lp * kPitch + lv]) = gv;
+        *reinterpret_cast<uint4*>(&xs[lp * kPitch + lv]) = xv;
+        __syncthreads();
+        if (p0 + kWgPix < p_hi) fetch(p0 + kWgPix);
+#pragma unroll
+        for (int ks = 0; ks < kWgPix / 16; ++ks) {
+            const int k0 = ks * 16;
+            uint32_t af[4], bf[4];
+            wg_ldmatrix_x4_trans(af, &gs[(k0 + (j >> 1) * 8 + r) * kPitch + m0 + (j & 1) * 8]);
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {
+                wg_ldmatrix_x4_trans(bf, &xs[(k0 + (j & 1) * 8 + r) * kPitch + n0 + (np * 2 + (j >> 1)) * 8]);
+                wg_mma_bf16(acc[2 * np], af, bf[0], bf[1]);
+                wg_mma_bf16(acc[2 * np + 1], af, bf[2], bf[3]);
+            }
+        }
+    }
+    float* o = partial + ((size_t)slice * (g.nphase * g.ntaps) + pt) * g.Cout * cin_tot;
+    const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+        const int n = ci0 + n0 + nb * 8 + 2 * tq;
+        *reinterpret_cast<float2*>(&o[(size_t)(co0 + m0 + gq) * cin_tot + n]) = make_float2(acc[nb][0], acc[nb][1]);
+        *reinterpret_cast<float2*>(&o[(size_t)(co0 + m0 + gq + 8) * cin_tot + n]) = make_float2(acc[nb][2], acc[nb][3]);
+    }
 }
 
 // sums the slices in order and scatters into the PyTorch layout.  kind 0: conv (Cout, Cin, kh, kw) with packed tap index = ky*kw+kx
@@ -399,7 +487,10 @@ int conv_wgrad(ActKind act, const ConvGeom& g, const void* gout, const void* x0,
     const int n_pt = g.nphase * g.ntaps, cin = g.Cin0 + g.Cin1;
     dim3 grid(n_pt, g.Cout / 64, (cin / 64) * slices);
     if (act == ACT_F32) wgrad_kernel<float><<<grid, 256, 0, s>>>(g, (const float*)gout, (const float*)x0, (const float*)x1, partial, slices, pps);
-    else wgrad_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(g, (const __nv_bfloat16*)gout, (const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, partial, slices, pps);
+    else if (getenv("GTTS_WGRAD_FFMA"))                              // CUDA-core kernel on bf16 (cross-check / measurement)
+        wgrad_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(g, (const __nv_bfloat16*)gout, (const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, partial, slices, pps);
+    else
+        wgrad_mma_kernel<<<grid, 256, 0, s>>>(g, (const __nv_bfloat16*)gout, (const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, partial, slices, pps);
     const size_t n = (size_t)n_pt * g.Cout * cin;
     wgrad_reduce_kernel<<<nblk(n, 256), 256, 0, s>>>(partial, dst, slices, n_pt, g.Cout, cin, kind, 3, scale, accumulate);
     GTTS_CHECK_CUDA(cudaGetLastError());

@@ -1739,11 +1739,12 @@ int decoder_profile_step(Decoder* d, int B, int T, int flags, int reps, char* bu
     if (int rc = common_checks(d, B, T, (const float*)1)) return rc;
     GTTS_REQUIRE(buf != nullptr && buflen > 64 && reps >= 1, "profile: bad arguments");
     const ActKind kind = (flags & 1) ? ACT_F32 : ACT_BF16;
-    const bool vjp = (flags & 4) != 0;                       // bit 2: the forward + backward (VJP) plan instead of the sampler step
+    const bool pgr = (flags & 8) != 0;                       // bit 3: ... with the parameter gradients (the training plan)
+    const bool vjp = (flags & 4) != 0 || pgr;                // bit 2: the forward + backward (VJP) plan instead of the sampler step
     const int Bc = std::min(vjp ? std::min(d->max_chunk, 16) : d->max_chunk, B);
     if (int rc = enter_call(d, stream)) return rc;
     Plan* pl = nullptr;
-    if (int rc = get_plan(d, kind, Bc, T, vjp, false, stream, &pl, vjp)) return rc;
+    if (int rc = get_plan(d, kind, Bc, T, vjp, false, stream, &pl, vjp, pgr)) return rc;
     const size_t nops = pl->ops.size();
     std::vector<cudaEvent_t> ev(2 * nops);
     for (auto& e : ev) GTTS_CHECK_CUDA(cudaEventCreate(&e));

@@ -22,7 +22,7 @@ def _module(pkg, synth, n_spks, wseed, precision):
     sd = synth.make_decoder_state_dict(n_spks, seed=wseed, g=0.05)
     dec = pkg.Diffusion(80, 64, n_spks, 64, 0.05, 20.0, 1000)
     dec.load_state_dict(sd, strict=True)
-    dec = dec.to(DEV)
+    dec = dec.to(DEV).eval()                                          # the likelihood code runs the model in eval mode (train mode: test_gpu_train.py)
     dec.precision = precision
     return dec, sd
 

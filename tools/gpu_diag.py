@@ -243,9 +243,10 @@ def stage_align():
 def stage_profile_vjp():
     """per-op times of the forward + backward (VJP) plan, both precisions"""
     import ctypes, json
-    for prec, flags in (("bf16", 4), ("fp32", 5)):
+    train = os.environ.get("GTTS_PROFILE_TRAIN") is not None      # the training plan (parameter gradients) at train.py's shape
+    for prec, flags in ((("bf16", 12),) if train else (("bf16", 4), ("fp32", 5))):
         dec, _ = _decoder(1, 0, prec)
-        B, T = 16, 400
+        B, T = (16, 172) if train else (16, 400)
         buf = ctypes.create_string_buffer(1 << 18)
         h = dec.estimator._get_handle()
         rc = pkg._lib.load().gtts_decoder_profile_step(h, B, T, flags, 3, buf, len(buf), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
