@@ -107,12 +107,14 @@ __device__ __forceinline__ void wg_mma_bf16(float (&d)[4], const uint32_t (&a)[4
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+constexpr int kWgMmaPix = 64;                                         // pixels per step of the tensor-core kernel
+
 __global__ void __launch_bounds__(256)
 wgrad_mma_kernel(ConvGeom g, const __nv_bfloat16* __restrict__ gout, const __nv_bfloat16* __restrict__ x0,
                  const __nv_bfloat16* __restrict__ x1, float* __restrict__ partial, int slices, long pix_per_slice) {
     constexpr int kPitch = 72;                                        // bf16 per pixel row: 64 + 8 pad (144 B, conflict-free ldmatrix)
-    __shared__ __align__(16) __nv_bfloat16 gs[kWgPix * kPitch];
-    __shared__ __align__(16) __nv_bfloat16 xs[kWgPix * kPitch];
+    __shared__ __align__(16) __nv_bfloat16 gs[2][kWgMmaPix * kPitch];  // double-buffered: one block barrier per step
+    __shared__ __align__(16) __nv_bfloat16 xs[2][kWgMmaPix * kPitch];
     const int pt = blockIdx.x, ph = pt / g.ntaps, tap = pt % g.ntaps;
     const int co0 = blockIdx.y * 64;
     const int cin_tot = g.Cin0 + g.Cin1;
@@ -128,45 +130,69 @@ wgrad_mma_kernel(ConvGeom g, const __nv_bfloat16* __restrict__ gout, const __nv_
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-    const int lp = tid >> 3, lv = (tid & 7) * 8;                      // loader: pixel lp of the group, channels lv..lv+7
+    const int lp = tid >> 3, lv = (tid & 7) * 8;                      // loader: pixels lp and lp + 32 of the step, channels lv..lv+7
     const __nv_bfloat16* xsrc = ci0 < g.Cin0 ? x0 : x1;
     const int xc = ci0 < g.Cin0 ? g.Cin0 : g.Cin1, xoff = ci0 < g.Cin0 ? ci0 : ci0 - g.Cin0;
     const long hw = (long)g.Hg * g.Wg;
-    uint4 gv, xv;
+    uint4 gv[2], xv[2];
+    // (sample, row, column) of this thread's two pixels, advanced by 64 pixels per step without divisions (the first version
+    // recomputed them with a 64-bit and a 32-bit division per pixel per step: more integer work than tensor work)
+    int pb[2], pj[2], pi[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const long q = p_lo + lp + 32 * u;
+        pb[u] = (int)(q / hw);
+        const int rem = (int)(q - (long)pb[u] * hw);
+        pj[u] = rem / g.Wg;
+        pi[u] = rem - pj[u] * g.Wg;
+    }
     auto fetch = [&](long p0) {
-        const long q = p0 + lp;
-        gv = make_uint4(0u, 0u, 0u, 0u);
-        xv = make_uint4(0u, 0u, 0u, 0u);
-        if (q < p_hi) {
-            const int b = (int)(q / hw);
-            const int rem = (int)(q - (long)b * hw), jj = rem / g.Wg, ii = rem - jj * g.Wg;
-            const int oh = jj * g.out_step + g.oy[ph], ow = ii * g.out_step + g.ox[ph];
-            const int ih = jj * g.stride + g.dy[ph][tap], iw = ii * g.stride + g.dx[ph][tap];
-            if (ih >= 0 && ih < g.Hin && iw >= 0 && iw < g.Win) {
-                gv = __ldg(reinterpret_cast<const uint4*>(gout + (((size_t)b * g.Hout + oh) * g.Wout + ow) * g.Cout + co0 + lv));
-                xv = __ldg(reinterpret_cast<const uint4*>(xsrc + (((size_t)b * g.Hin + ih) * g.Win + iw) * xc + xoff + lv));
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const long q = p0 + lp + 32 * u;
+            gv[u] = make_uint4(0u, 0u, 0u, 0u);
+            xv[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (q < p_hi) {
+                const int b = pb[u], jj = pj[u], ii = pi[u];
+                const int oh = jj * g.out_step + g.oy[ph], ow = ii * g.out_step + g.ox[ph];
+                const int ih = jj * g.stride + g.dy[ph][tap], iw = ii * g.stride + g.dx[ph][tap];
+                if (ih >= 0 && ih < g.Hin && iw >= 0 && iw < g.Win) {
+                    gv[u] = __ldg(reinterpret_cast<const uint4*>(gout + (((size_t)b * g.Hout + oh) * g.Wout + ow) * g.Cout + co0 + lv));
+                    xv[u] = __ldg(reinterpret_cast<const uint4*>(xsrc + (((size_t)b * g.Hin + ih) * g.Win + iw) * xc + xoff + lv));
+                }
             }
+            pi[u] += kWgMmaPix;
+            while (pi[u] >= g.Wg) { pi[u] -= g.Wg; ++pj[u]; }
+            while (pj[u] >= g.Hg) { pj[u] -= g.Hg; ++pb[u]; }
         }
     };
-    if (p_lo < p_hi) fetch(p_lo);
-    for (long p0 = p_lo; p0 < p_hi; p0 += kWgPix) {
-        __syncthreads();
-        *reinterpret_cast<uint4*>(&gs[lp * kPitch + lv]) = gv;
-        *reinterpret_cast<uint4*>(&xs[lp * kPitch + lv]) = xv;
-        __syncthreads();
-        if (p0 + kWgPix < p_hi) fetch(p0 + kWgPix);
+    auto stage = [&](int buf) {
 #pragma unroll
-        for (int ks = 0; ks < kWgPix / 16; ++ks) {
+        for (int u = 0; u < 2; ++u) {
+            *reinterpret_cast<uint4*>(&gs[buf][(lp + 32 * u) * kPitch + lv]) = gv[u];
+            *reinterpret_cast<uint4*>(&xs[buf][(lp + 32 * u) * kPitch + lv]) = xv[u];
+        }
+    };
+    if (p_lo < p_hi) { fetch(p_lo); stage(0); }
+    __syncthreads();
+    int buf = 0;
+    for (long p0 = p_lo; p0 < p_hi; p0 += kWgMmaPix, buf ^= 1) {
+        const bool more = p0 + kWgMmaPix < p_hi;
+        if (more) fetch(p0 + kWgMmaPix);                              // in flight during the MMAs
+#pragma unroll
+        for (int ks = 0; ks < kWgMmaPix / 16; ++ks) {
             const int k0 = ks * 16;
             uint32_t af[4], bf[4];
-            wg_ldmatrix_x4_trans(af, &gs[(k0 + (j >> 1) * 8 + r) * kPitch + m0 + (j & 1) * 8]);
+            wg_ldmatrix_x4_trans(af, &gs[buf][(k0 + (j >> 1) * 8 + r) * kPitch + m0 + (j & 1) * 8]);
 #pragma unroll
             for (int np = 0; np < 2; ++np) {
-                wg_ldmatrix_x4_trans(bf, &xs[(k0 + (j & 1) * 8 + r) * kPitch + n0 + (np * 2 + (j >> 1)) * 8]);
+                wg_ldmatrix_x4_trans(bf, &xs[buf][(k0 + (j & 1) * 8 + r) * kPitch + n0 + (np * 2 + (j >> 1)) * 8]);
                 wg_mma_bf16(acc[2 * np], af, bf[0], bf[1]);
                 wg_mma_bf16(acc[2 * np + 1], af, bf[2], bf[3]);
             }
         }
+        if (more) stage(buf ^ 1);                                     // nobody reads that buffer in this step
+        __syncthreads();
     }
     float* o = partial + ((size_t)slice * (g.nphase * g.ntaps) + pt) * g.Cout * cin_tot;
     const int gq = lane >> 2, tq = lane & 3;
@@ -483,7 +509,7 @@ int conv_wgrad(ActKind act, const ConvGeom& g, const void* gout, const void* x0,
     int slices;
     wgrad_partial_floats(g, &slices);
     const long npix = (long)g.B * g.Hg * g.Wg;
-    const long pps = ((npix + slices - 1) / slices + kWgPix - 1) / kWgPix * kWgPix;
+    const long pps = ((npix + slices - 1) / slices + kWgMmaPix - 1) / kWgMmaPix * kWgMmaPix;   // multiple of both kernels' step
     const int n_pt = g.nphase * g.ntaps, cin = g.Cin0 + g.Cin1;
     dim3 grid(n_pt, g.Cout / 64, (cin / 64) * slices);
     if (act == ACT_F32) wgrad_kernel<float><<<grid, 256, 0, s>>>(g, (const float*)gout, (const float*)x0, (const float*)x1, partial, slices, pps);
