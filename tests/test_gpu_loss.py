@@ -68,13 +68,17 @@ def test_forward_diffusion_and_loss_match_reference_capture(pkg, synth, name):
         assert abs(float(loss_bf) - ref_loss) <= 2e-2 * ref_loss, (float(loss_bf), ref_loss)
 
 
-def test_loss_requires_no_grad_and_draws_its_own_noise(pkg, synth):
+def test_loss_is_differentiable_and_draws_its_own_noise(pkg, synth):
     dec, sd = _module(pkg, synth, 1, 0, "fp32")
     x0, mask, mu, _, _ = synth.make_inputs(2, 64, 1, seed=5)
     x0, mask, mu = x0.to(DEV), mask.to(DEV), mu.to(DEV)
     t = torch.tensor([0.3, 0.9], device=DEV)
-    with pytest.raises(NotImplementedError):
-        dec.loss_t(x0, mask, mu, t)                       # gradients enabled: there is no backward, so refuse
+    dec.train()
+    loss, _ = dec.loss_t(x0, mask, mu, t)                 # gradients enabled, train mode: the loss carries the autograd graph
+    assert loss.requires_grad
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in dec.parameters())
+    dec.eval()
     with torch.no_grad():
         torch.manual_seed(11)
         a, xt_a = dec.loss_t(x0, mask, mu, t)
@@ -122,8 +126,12 @@ def test_gradtts_compute_loss_forward_values(pkg, synth):
     net = net.to(DEV)
     net.decoder.precision = "fp32"
     x = torch.zeros(B, tx, dtype=torch.long)
-    with pytest.raises(NotImplementedError):
-        net.compute_loss(x, x_len, y, y_len)
+    net.train()
+    _, _, diff_t = net.compute_loss(x, x_len, y, y_len)                  # train mode: differentiable down to the decoder parameters
+    assert diff_t.requires_grad
+    diff_t.backward()
+    assert all(p.grad is not None for p in net.decoder.parameters())
+    net.eval()
     with torch.no_grad():
         torch.manual_seed(21)
         dur, prior, diff = net.compute_loss(x.to(DEV), x_len.to(DEV), y.to(DEV), y_len.to(DEV))
