@@ -527,7 +527,8 @@ def mas_record(pkg, torch, dev, hbm_peak):
     return {"workload": "C2: monotonic_align.maximum_path batch 64, text 200 x mel 1000 (ragged lengths, item 0 full size)",
             "device_ms": ms, "cells_per_sec": cells / (ms * 1e-3), "algorithmic_bytes": alg,
             "achieved_gbs": alg / (ms * 1e-3) / 1e9, "hbm_peak_gbs": hbm_peak, "frac_of_hbm": alg / (ms * 1e-3) / 1e9 / hbm_peak,
-            "bound": "latency: t_y = 1000 dependent column steps per utterance, one CTA per utterance (64 CTAs)",
+            "bound": "latency: t_y = 1000 dependent column steps per utterance (one warp carries the DP column in registers, seven warps "
+                     "stage tiles), then 1000 dependent backtrack steps; one CTA per utterance (64 CTAs)",
             "host_buffers_ms": host_ms, "host_rc": int(rc), "bit_exact_vs_cpu": bool(torch.equal(got, ref)) and bool(torch.equal(path_h, ref)),
             "cpu_reference_ms": cpu_ms, "cpu_reference": "oracle/mas_oracle.c (plain-C restatement of core.pyx, 1 thread) incl. the wrapper's "
                                                          "value*mask and casts"}

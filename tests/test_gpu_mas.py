@@ -30,7 +30,8 @@ def test_mas_golden(name, pkg, synth):
 
 
 @pytest.mark.parametrize("B,tx,ty", [(1, 1, 1), (3, 1, 40), (2, 7, 7), (4, 31, 33), (2, 33, 64), (3, 100, 257),
-                                     (2, 300, 1203), (1, 1024, 1100), (1, 1500, 1600)])
+                                     (2, 300, 1203), (1, 1024, 1100), (1, 1500, 1600),
+                                     (2, 224, 300), (2, 225, 300), (2, 416, 500), (2, 417, 500), (1, 200, 4400), (1, 200, 4500)])   # edges of the warp-serial variants
 def test_mas_random_vs_oracle(B, tx, ty, pkg, synth):
     value, mask, _, _ = synth.make_mas_inputs(B, tx, ty, seed=B * 1000 + tx + ty)
     ref = mas_oracle.maximum_path(value, mask)
