@@ -51,6 +51,7 @@ SIGNATURES = {
     "gtts_vocoder_forward_host": (_i, [_vp, _vp, _vp, _i, _i, _i]),
     "gtts_vocoder_profile": (_i, [_vp, _i, _i, _i, _vp, _sz, _vp]),
     "gtts_vocoder_launches_last_call": (_l, [_vp]),
+    "gtts_vocoder_cache_info": (_i, [_vp, _vp, _i]),
     "gtts_align_log_prior": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "gtts_align_outputs": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "gtts_score_loss_workspace_bytes": (_sz, []),

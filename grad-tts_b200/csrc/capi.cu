@@ -648,6 +648,11 @@ int gtts_vocoder_profile(gtts_vocoder* h, int B, int T, int flags, char* buf, si
     return vocoder_profile(h->impl, B, T, flags, buf, buflen, (cudaStream_t)stream);
 }
 
+int gtts_vocoder_cache_info(const gtts_vocoder* h, long long* out, int n) {
+    GTTS_REQUIRE(h != nullptr, "null vocoder handle");
+    return vocoder_cache_info(h->impl, out, n);
+}
+
 long gtts_vocoder_launches_last_call(const gtts_vocoder* h) { return h ? vocoder_launches_last_call(h->impl) : 0; }
 
 }  // extern "C"

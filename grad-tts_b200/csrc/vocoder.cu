@@ -140,46 +140,73 @@ struct Vocoder {
     std::map<std::string, std::unique_ptr<VocoderPlan>> plans;
     std::vector<std::string> plan_order;
     long launches_last_call = 0;
+    // Workspace pool shared by every plan of the handle.  Calls on one handle are ordered (same stream, or through done_ev), so
+    // only one plan runs at a time and a new (B, T) reuses the blocks of earlier shapes: a server that sees a different mel length
+    // on every call rebuilds descriptors and the graph, not gigabytes of cudaMalloc.  `busy` marks liveness during ONE plan build.
+    struct Block { void* p; size_t bytes; bool busy; };
+    std::vector<Block> pool;
+    size_t pool_bytes = 0;
+    int max_plans = 8;
+    cudaEvent_t done_ev = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool has_done = false;
+    static size_t round_size(size_t bytes) {               // 1/8 of the power of two below: neighbouring lengths share size classes
+        if (bytes < 4096) return 4096;
+        size_t p2 = 1;
+        while (p2 * 2 <= bytes) p2 *= 2;
+        const size_t gran = p2 / 8;
+        return (bytes + gran - 1) / gran * gran;
+    }
+    void* pool_alloc(size_t bytes) {
+        bytes = round_size(bytes);
+        int best = -1;
+        for (int i = 0; i < (int)pool.size(); ++i)
+            if (!pool[i].busy && pool[i].bytes >= bytes && (best < 0 || pool[i].bytes < pool[best].bytes)) best = i;
+        if (best >= 0) { pool[best].busy = true; return pool[best].p; }
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        pool.push_back(Block{p, bytes, true});
+        pool_bytes += bytes;
+        return p;
+    }
+    void pool_release(const void* p) { for (auto& b : pool) if (b.p == p) b.busy = false; }
+    void pool_release_all() { for (auto& b : pool) b.busy = false; }
+    void pool_free() { for (auto& b : pool) cudaFree(b.p); pool.clear(); pool_bytes = 0; }
     int total_up() const { int u = 1; for (int r : rates) u *= r; return u; }
     ~Vocoder();
 };
 
 struct VocoderPlan {
+    Vocoder* v = nullptr;
     int B = 0, T = 0;
     ActKind kind = ACT_BF16;
-    std::vector<void*> owned;                 // cudaMalloc'ed blocks
-    struct Block { void* p; size_t bytes; bool busy; };
-    std::vector<Block> blocks;
-    size_t total_bytes = 0;
     std::vector<TcConvPlan*> tc_plans;
     std::vector<std::function<int(cudaStream_t)>> ops;
     struct OpInfo { std::string name; double flops; };
     std::vector<OpInfo> info;
-    float* mel_in = nullptr;                  // (B, num_mels, T) fp32, plan-owned staging
-    float* audio = nullptr;                   // (B, 1, T*up) fp32
+    float* mel_in = nullptr;                  // (B, num_mels, T) fp32, staging (pool)
+    float* audio = nullptr;                   // (B, 1, T*up) fp32 (pool)
     cudaGraphExec_t graph_exec = nullptr;
     bool oom = false;
+    size_t live_bytes = 0, peak_bytes = 0;
+    std::map<const void*, size_t> sizes;
     void* alloc(size_t bytes) {
         if (bytes == 0) bytes = 16;
-        bytes = (bytes + 1023) / 1024 * 1024;
-        int best = -1;
-        for (int i = 0; i < (int)blocks.size(); ++i)
-            if (!blocks[i].busy && blocks[i].bytes >= bytes && (best < 0 || blocks[i].bytes < blocks[best].bytes)) best = i;
-        if (best >= 0 && blocks[best].bytes <= bytes + bytes / 4) { blocks[best].busy = true; return blocks[best].p; }
-        void* p = nullptr;
-        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); oom = true; return nullptr; }
-        blocks.push_back(Block{p, bytes, true});
-        total_bytes += bytes;
+        void* p = v->pool_alloc(bytes);
+        if (!p) { oom = true; return nullptr; }
+        sizes[p] = bytes;
+        live_bytes += bytes;
+        peak_bytes = std::max(peak_bytes, live_bytes);
         return p;
     }
     void release(const void* p) {
-        for (auto& b : blocks) if (b.p == p) b.busy = false;
+        auto it = sizes.find(p);
+        if (it != sizes.end()) { live_bytes -= it->second; sizes.erase(it); }
+        v->pool_release(p);
     }
     ~VocoderPlan() {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         for (auto* t : tc_plans) conv_tc_plan_destroy(t);
-        for (auto& b : blocks) cudaFree(b.p);
-        for (void* p : owned) cudaFree(p);
     }
 };
 
@@ -187,6 +214,8 @@ Vocoder::~Vocoder() {
     cudaSetDevice(device);
     cudaDeviceSynchronize();
     plans.clear();
+    pool_free();
+    if (done_ev) cudaEventDestroy(done_ev);
     for (auto& kv : params) {
         cudaFree(kv.second.w); cudaFree(kv.second.b); cudaFree(kv.second.packed[0]); cudaFree(kv.second.packed[1]); cudaFree(kv.second.bias_p);
     }
@@ -476,13 +505,12 @@ int pack_all(Vocoder* v) {
 
 int plan_create(Vocoder* v, int B, int T, ActKind kind, VocoderPlan** out) {
     std::unique_ptr<VocoderPlan> pl(new VocoderPlan());
-    pl->B = B; pl->T = T; pl->kind = kind;
+    pl->v = v; pl->B = B; pl->T = T; pl->kind = kind;
     const size_t n_mel = (size_t)B * v->num_mels * T, n_audio = (size_t)B * T * v->total_up();
-    void* p = nullptr;
-    if (cudaMalloc(&p, n_mel * 4) != cudaSuccess) { cudaGetLastError(); set_error("vocoder: out of device memory"); return 4; }
-    pl->owned.push_back(p); pl->mel_in = (float*)p;
-    if (cudaMalloc(&p, n_audio * 4) != cudaSuccess) { cudaGetLastError(); set_error("vocoder: out of device memory"); return 4; }
-    pl->owned.push_back(p); pl->audio = (float*)p;
+    v->pool_release_all();                               // nothing of an earlier plan is live while this one is being laid out
+    pl->mel_in = (float*)pl->alloc(n_mel * 4);
+    pl->audio = (float*)pl->alloc(n_audio * 4);
+    if (!pl->mel_in || !pl->audio) { set_error("vocoder: out of device memory"); return 4; }
     Builder b{v, pl.get(), B, T, kind};
     int rc = b.build();
     if (rc) return pl->oom ? 4 : rc;
@@ -534,18 +562,20 @@ int get_plan(Vocoder* v, int B, int T, ActKind kind, cudaStream_t stream, Vocode
         *out = it->second.get();
         return 0;
     }
-    // a plan owns its workspace: keep at most two shapes alive (least recently used goes first)
+    // slow path: the dry run writes into pool blocks that queued work of this handle may still be using
     GTTS_CHECK_CUDA(cudaStreamSynchronize(stream));
-    while (v->plans.size() >= 2) {
-        GTTS_CHECK_CUDA(cudaDeviceSynchronize());
+    if (v->has_done) GTTS_CHECK_CUDA(cudaEventSynchronize(v->done_ev));
+    while ((int)v->plans.size() >= std::max(1, v->max_plans)) {          // descriptors + graph only; the memory is the shared pool
         v->plans.erase(v->plan_order.front());
         v->plan_order.erase(v->plan_order.begin());
     }
     VocoderPlan* pl = nullptr;
     int rc = plan_create(v, B, T, kind, &pl);
-    if (rc == 4 && !v->plans.empty()) {
+    if (rc == 4) {
+        // out of device memory: give back everything this handle caches (plans and pool) and try once more
         GTTS_CHECK_CUDA(cudaDeviceSynchronize());
         v->plans.clear(); v->plan_order.clear();
+        v->pool_free();
         rc = plan_create(v, B, T, kind, &pl);
     }
     if (rc) return rc;
@@ -651,6 +681,7 @@ int vocoder_set_option(Vocoder* v, const char* key, long long value) {
     if (k == "max_chunk") { GTTS_REQUIRE(value >= 1 && value <= 4096, "max_chunk out of range"); v->max_chunk = (int)value; }
     else if (k == "workspace_mb") { GTTS_REQUIRE(value >= 64, "workspace_mb out of range"); v->workspace_budget = (size_t)value << 20; }
     else if (k == "use_graph") v->use_graph = value != 0;
+    else if (k == "max_plans") { GTTS_REQUIRE(value >= 1 && value <= 256, "max_plans out of range"); v->max_plans = (int)value; }
     else if (k == "force_ffma") v->force_ffma = value != 0;
     else { set_error("vocoder_set_option: unknown option " + k); return 2; }
     return 0;
@@ -670,6 +701,9 @@ int vocoder_forward(Vocoder* v, const float* mel, float* audio, int B, int T, in
     chunk = std::min<long>(chunk, B);
     const size_t up = (size_t)v->total_up();
     v->launches_last_call = 0;
+    // calls on one handle are ordered even across streams (the plans share the pool)
+    if (!v->done_ev) GTTS_CHECK_CUDA(cudaEventCreateWithFlags(&v->done_ev, cudaEventDisableTiming));
+    if (v->has_done && v->last_stream != stream) GTTS_CHECK_CUDA(cudaStreamWaitEvent(stream, v->done_ev, 0));
     for (int b0 = 0; b0 < B; b0 += (int)chunk) {
         const int nb = std::min<int>((int)chunk, B - b0);
         VocoderPlan* pl = nullptr;
@@ -683,6 +717,19 @@ int vocoder_forward(Vocoder* v, const float* mel, float* audio, int B, int T, in
         GTTS_CHECK_CUDA(cudaMemcpyAsync(audio + (size_t)b0 * T * up, pl->audio, (size_t)nb * T * up * 4, cudaMemcpyDeviceToDevice, stream));
         v->launches_last_call += (long)pl->ops.size();
     }
+    GTTS_CHECK_CUDA(cudaEventRecord(v->done_ev, stream));
+    v->last_stream = stream;
+    v->has_done = true;
+    return 0;
+}
+
+// out[0] plans cached, [1] bytes of the shared workspace pool, [2] peak live bytes of the most recent plan
+int vocoder_cache_info(const Vocoder* v, long long* out, int n) {
+    GTTS_REQUIRE(v && out && n >= 3, "vocoder_cache_info: bad arguments");
+    out[0] = (long long)v->plans.size();
+    out[1] = (long long)v->pool_bytes;
+    out[2] = 0;
+    if (!v->plan_order.empty()) out[2] = (long long)v->plans.at(v->plan_order.back())->peak_bytes;
     return 0;
 }
 

@@ -15,5 +15,6 @@ long vocoder_launches_last_call(const Vocoder* v);
 int vocoder_set_param(Vocoder* v, const char* name, const float* data, size_t numel);
 int vocoder_set_option(Vocoder* v, const char* key, long long value);
 int vocoder_forward(Vocoder* v, const float* mel, float* audio, int B, int T, int flags, cudaStream_t stream);
+int vocoder_cache_info(const Vocoder* v, long long* out, int n);
 int vocoder_profile(Vocoder* v, int B, int T, int flags, char* buf, size_t buflen, cudaStream_t stream);
 }  // namespace gtts

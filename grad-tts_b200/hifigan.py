@@ -166,6 +166,14 @@ class Generator(nn.Module):
         h = self._get_handle(next(self.parameters()).device)
         _lib.check(_lib.load().gtts_vocoder_set_option(h, name.encode(), int(value)), f"vocoder_set_option({name})")
 
+    def cache_info(self):
+        """plans cached, bytes of the shared workspace pool, peak live workspace of the most recent plan"""
+        if self._handle is None:
+            return {"plans": 0, "pool_bytes": 0, "plan_peak_bytes": 0}
+        out = (ctypes.c_longlong * 3)()
+        _lib.check(_lib.load().gtts_vocoder_cache_info(self._handle, out, 3), "vocoder_cache_info")
+        return {"plans": int(out[0]), "pool_bytes": int(out[1]), "plan_peak_bytes": int(out[2])}
+
     def launches_last_call(self):
         return int(_lib.load().gtts_vocoder_launches_last_call(self._handle)) if self._handle is not None else 0
 

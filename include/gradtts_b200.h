@@ -200,7 +200,7 @@ long gtts_encoder_launches_last_call(const gtts_encoder* e);
  * remove_weight_norm ("conv_pre.weight", "ups.0.bias", "resblocks.4.convs1.2.weight", "conv_post.bias", ...), fp32, PyTorch layout,
  * host or device pointer.  forward: mel (B, num_mels, T) fp32 -> audio (B, 1, T * prod(upsample_rates)) fp32, as Generator.forward.
  * flags: GTTS_FLAG_FP32 = fp32 activations and CUDA-core FFMA convs; default bf16 activations, tcgen05 convs, fp32 accumulation.
- * Options: "max_chunk" (utterances per workspace chunk, default 32), "workspace_mb", "use_graph", "force_ffma". */
+ * Options: "max_chunk" (utterances per workspace chunk, default 32), "workspace_mb", "use_graph", "force_ffma", "max_plans". */
 typedef struct gtts_vocoder gtts_vocoder;
 int gtts_vocoder_create(gtts_vocoder** out, int resblock, int n_ups, const int* upsample_rates, const int* upsample_kernel_sizes,
                         int upsample_initial_channel, int n_rb, const int* resblock_kernel_sizes, const int* resblock_dilation_sizes,
@@ -215,6 +215,9 @@ int gtts_vocoder_forward_host(gtts_vocoder* v, const float* mel_host, float* aud
 /* per-launch CUDA-event times of one forward of (min(B, max_chunk), T) as a text table */
 int gtts_vocoder_profile(gtts_vocoder* v, int B, int T, int flags, char* buf, size_t buflen, void* stream);
 long gtts_vocoder_launches_last_call(const gtts_vocoder* v);
+/* n >= 3: out[0] plans cached (descriptors + graph per (B, T); LRU, option "max_plans", default 8), [1] bytes of the workspace pool
+ * all plans of the handle share, [2] peak live workspace of the most recent plan.  Calls on one handle are ordered across streams. */
+int gtts_vocoder_cache_info(const gtts_vocoder* v, long long* out, int n);
 
 #ifdef __cplusplus
 }

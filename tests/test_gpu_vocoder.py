@@ -145,3 +145,26 @@ def test_synthesize_text_to_waveform(pkg, synth):
     want = (voc(y2).squeeze(1).clamp(-1, 1) * 32768).to(torch.int16).cpu()
     assert torch.equal(audio, want)
     assert int(audio.abs().max()) > 0
+
+
+def test_vocoder_varying_lengths_share_one_workspace_pool(pkg, synth):
+    """A different mel length on every call (the serving pattern): plans are rebuilt, the workspace is not -- the pool stops growing
+    once the longest shape has been seen, the plan cache is LRU-bounded, and results do not depend on what ran before."""
+    gen, cfg, _ = _make(pkg, synth, "v1", 37)
+    gen.set_option("max_plans", 3)
+    mels = {T: synth.make_mel(2, T, seed=100 + T).cuda() for T in (40, 24, 33, 17, 28)}
+    first = {T: gen(m) for T, m in mels.items()}
+    info1 = gen.cache_info()
+    assert info1["plans"] <= 3 and info1["pool_bytes"] > 0
+    again = {T: gen(m) for T, m in sorted(mels.items())}
+    info2 = gen.cache_info()
+    assert info2["pool_bytes"] == info1["pool_bytes"]                # every shape fits the blocks the longest one allocated
+    assert all(torch.equal(first[T], again[T]) for T in mels)
+    # two streams on one handle are ordered by the library
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    with torch.cuda.stream(s1):
+        a = gen(mels[40])
+    with torch.cuda.stream(s2):
+        b = gen(mels[24])
+    torch.cuda.synchronize()
+    assert torch.equal(a, first[40]) and torch.equal(b, first[24])
