@@ -796,8 +796,18 @@ def vocoder_record(pkg, torch, dev, decoder_fps):
     mel_d = mel.to(dev)
     y = gen(mel_d)
     ms = _event_time_ms(torch, lambda: gen(mel_d), 3, 1)
+    # algorithmic FLOPs per mel frame of the unpadded network (conv_pre, 4 transposed convs, 12 resblocks x 6 convs, conv_post)
+    c0, flops, L, ch = cfg["upsample_initial_channel"], 2.0 * 80 * cfg["upsample_initial_channel"] * 7, 1, cfg["upsample_initial_channel"]
+    for i, (u, k) in enumerate(zip(cfg["upsample_rates"], cfg["upsample_kernel_sizes"])):
+        flops += 2.0 * L * ch * (ch // 2) * k                    # every input position meets every tap of the transposed conv
+        L, ch = L * u, ch // 2
+        flops += sum(2.0 * L * ch * ch * rk * 2 * len(rd) for rk, rd in zip(cfg["resblock_kernel_sizes"], cfg["resblock_dilation_sizes"]))
+    flops += 2.0 * L * ch * 7
+    out["gflop_per_frame"] = flops / 1e9
     out["bf16"] = {"ms": ms, "value": Bv * T_ / (ms * 1e-3), "launches": gen.launches_last_call(), "output_finite": bool(torch.isfinite(y).all()),
-                   "audio_seconds_per_second": Bv * T_ * 256 / 22050 / (ms * 1e-3)}
+                   "audio_seconds_per_second": Bv * T_ * 256 / 22050 / (ms * 1e-3),
+                   "model_tflops": flops * Bv * T_ / (ms * 1e-3) / 1e12,
+                   "frac_of_bf16_peak": flops * Bv * T_ / (ms * 1e-3) / 1e12 / peaks()[0]}
     # end to end with host buffers through the C ABI (H2D of the mels, D2H of the waveforms inside the timed region)
     mel_h = mel.pin_memory()
     wav_h = torch.empty(Bv, 1, T_ * 256).pin_memory()

@@ -469,11 +469,15 @@ struct TextEncoder {
     std::map<std::pair<int, int>, Graph> graphs;        // per (B, T)
     unsigned long long use_clock = 0;
     int use_graph = 1;
+    cudaEvent_t done_ev = nullptr;                      // calls on one handle are ordered across streams (one workspace)
+    cudaStream_t last_stream = nullptr;
+    bool has_done = false;
     long graph_max_pos = 8192;                          // larger batches are not launch-bound
     ~TextEncoder() {
         cudaSetDevice(device);
         cudaDeviceSynchronize();
         for (auto& kv : graphs) { if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec); cudaFree(kv.second.stage); }
+        if (done_ev) cudaEventDestroy(done_ev);
         for (auto& kv : params) cudaFree(kv.second.p);
         for (auto& kv : packed) cudaFree(kv.second);
         cudaFree(ws); cudaFree(status);
@@ -749,8 +753,25 @@ int forward_body(TextEncoder* e, const long long* tokens, const long long* lengt
 // One forward = ~56 small launches; for a given (B, T) they are captured once as a CUDA graph over fixed staging buffers (tokens,
 // lengths, speaker in; mu, logw, mask out -- a few KB copied on either side), so a call costs one graph launch instead of 56
 // kernel launches from the host.  At most 16 shapes are kept (least recently used goes first); growing the workspace drops them all.
+static int text_encoder_forward_impl(TextEncoder* e, const long long* tokens, const long long* lengths, const float* spk, float* mu,
+                                     float* logw, float* x_mask, int B, int T, cudaStream_t s);
+
 int text_encoder_forward(TextEncoder* e, const long long* tokens, const long long* lengths, const float* spk, float* mu, float* logw,
                          float* x_mask, int B, int T, cudaStream_t s) {
+    GTTS_REQUIRE(e != nullptr, "text_encoder_forward: null handle");
+    GTTS_CHECK_CUDA(cudaSetDevice(e->device));
+    if (!e->done_ev) GTTS_CHECK_CUDA(cudaEventCreateWithFlags(&e->done_ev, cudaEventDisableTiming));
+    if (e->has_done && e->last_stream != s) GTTS_CHECK_CUDA(cudaStreamWaitEvent(s, e->done_ev, 0));
+    const int rc = text_encoder_forward_impl(e, tokens, lengths, spk, mu, logw, x_mask, B, T, s);
+    if (rc) return rc;
+    GTTS_CHECK_CUDA(cudaEventRecord(e->done_ev, s));
+    e->last_stream = s;
+    e->has_done = true;
+    return 0;
+}
+
+static int text_encoder_forward_impl(TextEncoder* e, const long long* tokens, const long long* lengths, const float* spk, float* mu,
+                                     float* logw, float* x_mask, int B, int T, cudaStream_t s) {
     GTTS_REQUIRE(e && tokens && lengths && mu && logw && x_mask, "text_encoder_forward: null pointer");
     GTTS_REQUIRE(B >= 1 && T >= 1, "text_encoder_forward: bad batch or length");
     GTTS_REQUIRE(e->n_spks <= 1 || spk != nullptr, "text_encoder_forward: this encoder was built with n_spks > 1: spk is required");
