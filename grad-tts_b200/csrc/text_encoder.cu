@@ -284,14 +284,15 @@ __global__ void __launch_bounds__(256)
 rel_attention_smem_kernel(const float* __restrict__ qkv, const float* __restrict__ mask, const float* __restrict__ emb_k,
                           const float* __restrict__ emb_v, float* __restrict__ out, int T, int C, int window, int q_per_cta) {
     extern __shared__ float smem[];
-    constexpr int kPitch = kKC + 1;
+    constexpr int kPitch = kKC + 4;                     // 16-byte aligned rows; 8 lanes x 16 bytes of consecutive keys hit 32 distinct banks
     const int nrel = window >= 0 ? 2 * window + 1 : 0;
     float* s_k = smem;                                   // [T][kPitch]
     float* s_v = s_k + (size_t)T * kPitch;               // [T][kPitch]
     float* s_ek = s_v + (size_t)T * kPitch;              // [nrel][kKC]
     float* s_ev = s_ek + (size_t)nrel * kKC;
-    float* s_m = s_ev + (size_t)nrel * kKC;              // [T] key mask
-    float* s_w = s_m + T;                                // per warp: q[kKC] | p[T]
+    const int Tp = (T + 3) / 4 * 4;
+    float* s_m = s_ev + (size_t)nrel * kKC;              // [Tp] key mask
+    float* s_w = s_m + Tp;                               // per warp: q[kKC] | p[Tp]  (16-byte aligned)
     const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.y, b = blockIdx.z;
     const float* base = qkv + (size_t)b * T * 3 * C + h * kKC;
@@ -299,15 +300,13 @@ rel_attention_smem_kernel(const float* __restrict__ qkv, const float* __restrict
         const int j = idx / (kKC / 4), c4 = idx - j * (kKC / 4);
         const float4 kv = __ldg(reinterpret_cast<const float4*>(base + (size_t)j * 3 * C + C) + c4);
         const float4 vv = __ldg(reinterpret_cast<const float4*>(base + (size_t)j * 3 * C + 2 * C) + c4);
-        float* kd = s_k + (size_t)j * kPitch + c4 * 4;
-        float* vd = s_v + (size_t)j * kPitch + c4 * 4;
-        kd[0] = kv.x; kd[1] = kv.y; kd[2] = kv.z; kd[3] = kv.w;
-        vd[0] = vv.x; vd[1] = vv.y; vd[2] = vv.z; vd[3] = vv.w;
+        *reinterpret_cast<float4*>(s_k + (size_t)j * kPitch + c4 * 4) = kv;
+        *reinterpret_cast<float4*>(s_v + (size_t)j * kPitch + c4 * 4) = vv;
     }
     for (int idx = threadIdx.x; idx < nrel * kKC; idx += blockDim.x) { s_ek[idx] = emb_k[idx]; s_ev[idx] = emb_v[idx]; }
     for (int j = threadIdx.x; j < T; j += blockDim.x) s_m[j] = mask[(size_t)b * T + j];
     __syncthreads();
-    float* s_q = s_w + (size_t)warp * (kKC + T);
+    float* s_q = s_w + (size_t)warp * (kKC + Tp);
     float* s_p = s_q + kKC;
     const float scale = 1.0f / sqrtf((float)kKC);
     constexpr int kPer = kKC / 32;
@@ -329,12 +328,16 @@ rel_attention_smem_kernel(const float* __restrict__ qkv, const float* __restrict
             if (s_m[j] == 0.f) {
                 sc = -1e4f;
             } else {
-                const float* kp = s_k + (size_t)j * kPitch;
+                // one 16-byte read of the key row and one 16-byte broadcast of q per four FMAs (the first version read both
+                // operands word by word: two shared-memory instructions per FMA, LDS-bound)
+                const float4* kp = reinterpret_cast<const float4*>(s_k + (size_t)j * kPitch);
+                const float4* qp4 = reinterpret_cast<const float4*>(s_q);
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 8
-                for (int c = 0; c < kKC; c += 4) {
-                    a0 = fmaf(s_q[c], kp[c], a0); a1 = fmaf(s_q[c + 1], kp[c + 1], a1);
-                    a2 = fmaf(s_q[c + 2], kp[c + 2], a2); a3 = fmaf(s_q[c + 3], kp[c + 3], a3);
+                for (int c4 = 0; c4 < kKC / 4; ++c4) {
+                    const float4 kv = kp[c4], qv = qp4[c4];
+                    a0 = fmaf(qv.x, kv.x, a0); a1 = fmaf(qv.y, kv.y, a1);
+                    a2 = fmaf(qv.z, kv.z, a2); a3 = fmaf(qv.w, kv.w, a3);
                 }
                 sc = ((a0 + a1) + (a2 + a3)) * scale;
             }
@@ -642,7 +645,7 @@ int launch_attention(const float* qkv, const float* mask, const float* ek, const
     {
         // keys and values of one (sample, head) resident in shared memory
         const int nwarps = 8;
-        const size_t smem = ((size_t)2 * T * (kKC + 1) + (size_t)2 * nrel * kKC + T + (size_t)nwarps * (kKC + T)) * 4;
+        const size_t smem = ((size_t)2 * T * (kKC + 4) + (size_t)2 * nrel * kKC + (size_t)(T + 3) / 4 * 4 + (size_t)nwarps * (kKC + (T + 3) / 4 * 4)) * 4;
         if (smem <= 220 * 1024 && !getenv("GTTS_ENC_ATTN_GLOBAL")) {
             static size_t attr = 0;
             if (smem > 48 * 1024 && smem > attr) {
