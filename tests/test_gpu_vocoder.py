@@ -168,3 +168,21 @@ def test_vocoder_varying_lengths_share_one_workspace_pool(pkg, synth):
         b = gen(mels[24])
     torch.cuda.synchronize()
     assert torch.equal(a, first[40]) and torch.equal(b, first[24])
+
+
+def test_vocoder_full_length_utterance_against_oracle(pkg, synth):
+    """BASELINE-length mel (1720 frames -> 440 320 samples): every stage runs thousands of tiles per launch and the last stage is
+    3 440 position tiles per utterance; against the CPU oracle, both precisions."""
+    from oracle import vocoder_oracle
+    gen, cfg, sd = _make(pkg, synth, "v1", 38)
+    mel = synth.make_mel(1, 1720, seed=8)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    with torch.no_grad():
+        ref = vocoder_oracle.generator_forward(sd, cfg, mel)
+    gen.precision = "bf16"
+    y = gen(mel.cuda()).cpu()
+    assert y.shape == ref.shape == (1, 1, 1720 * 256) and torch.isfinite(y).all()
+    assert _rel_rms(y, ref) <= BF16_REL_RMS
+    gen.precision = "fp32"
+    y = gen(mel.cuda()).cpu()
+    assert float((y - ref).abs().max()) <= FP32_MAX_ABS
