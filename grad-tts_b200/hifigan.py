@@ -13,6 +13,7 @@ import torch
 from torch import nn
 
 from . import _lib
+from . import ops as _ops  # noqa: F401  (registers torch.ops.gradtts_b200.*)
 
 
 class AttrDict(dict):
@@ -119,15 +120,10 @@ class Generator(nn.Module):
         if mel.dtype != torch.float32 or not mel.is_contiguous():
             mel = mel.to(torch.float32).contiguous()
         B, _, T = mel.shape
-        h = self._get_handle(mel.device)
-        lib = _lib.load()
-        out = torch.empty(B, 1, T * self.hop, dtype=torch.float32, device=mel.device)
         if B == 0 or T == 0:
-            return out.to(x.dtype)
-        with torch.cuda.device(mel.device):
-            stream = ctypes.c_void_p(torch.cuda.current_stream(mel.device).cuda_stream)
-            rc = lib.gtts_vocoder_forward(h, mel.data_ptr(), out.data_ptr(), B, T, self._flags(), stream)
-        _lib.check(rc, "vocoder_forward")
+            return torch.empty(B, 1, T * self.hop, dtype=x.dtype, device=mel.device)
+        h = self._get_handle(mel.device)
+        out = torch.ops.gradtts_b200.vocoder(int(h.value), mel, self.hop, self._flags())
         return out.to(x.dtype)
 
     # ------------------------------------------------------------------------------------------------ plumbing

@@ -11,6 +11,7 @@ import torch
 from torch import nn
 
 from .. import _lib
+from .. import ops as _ops  # noqa: F401  (registers torch.ops.gradtts_b200.*)
 from .base import BaseModule
 
 
@@ -122,20 +123,11 @@ class TextEncoder(BaseModule):
             spk = spk.detach().to(device=dev, dtype=torch.float32).contiguous()
             if spk.shape != (B, self.spk_emb_dim):
                 raise ValueError("spk must be (B, spk_emb_dim)")
-        mu = torch.empty(B, self.n_feats, T, dtype=torch.float32, device=dev)
-        logw = torch.empty(B, 1, T, dtype=torch.float32, device=dev)
-        x_mask = torch.empty(B, 1, T, dtype=torch.float32, device=dev)
         if B == 0 or T == 0:
-            return mu, logw, x_mask
+            f = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)      # noqa: E731
+            return f(B, self.n_feats, T), f(B, 1, T), f(B, 1, T)
         h = self._get_handle(dev)
-        lib = _lib.load()
-        with torch.cuda.device(dev):
-            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            rc = lib.gtts_encoder_forward(h, tokens.data_ptr(), lengths.data_ptr(), spk.data_ptr() if self.n_spks > 1 else None,
-                                          mu.data_ptr(), logw.data_ptr(), x_mask.data_ptr(), B, T, stream)
-            _lib.check(rc, "encoder_forward")
-            _lib.check(lib.gtts_encoder_check_tokens(h, stream), "encoder_forward")
-        return mu, logw, x_mask
+        return torch.ops.gradtts_b200.text_encoder(int(h.value), tokens, lengths, spk if self.n_spks > 1 else None, int(self.n_feats))
 
     # ------------------------------------------------------------------------------------------------ plumbing
     def launches_last_call(self):

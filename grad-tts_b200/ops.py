@@ -15,6 +15,8 @@ with CPU tensors fails in the dispatcher -- there is no CPU implementation to fa
     torch.ops.gradtts_b200.align_outputs(attn, mu_x, x_mask)                                       -> (logw_, mu_y)
     torch.ops.gradtts_b200.forward_diffusion(x0, mask, mu, t, noise, beta_min, beta_max)           -> (xt, z_masked)
     torch.ops.gradtts_b200.score_loss(est, z_masked, mask, t, beta_min, beta_max)                  -> loss
+    torch.ops.gradtts_b200.text_encoder(handle, tokens, lengths, spk, n_feats)                     -> (mu, logw, x_mask)
+    torch.ops.gradtts_b200.vocoder(handle, mel, hop, flags)                                        -> audio
 
 `handle` is the integer value of the `gtts_decoder*` owned by the calling module (model/diffusion.py).  All tensors are fp32,
 contiguous, on the handle's sm_100 device; the Python modules do the casting and validation before they get here.
@@ -215,4 +217,47 @@ def _(est, z_masked, mask, t, beta_min, beta_max):
     return est.new_empty(())
 
 
-OPS = ("reverse_diffusion", "estimator", "estimator_vjp", "maximum_path", "log_prior", "align_outputs", "forward_diffusion", "score_loss")
+# ---------------------------------------------------------------------------------------------------------------- text encoder, vocoder
+@torch.library.custom_op(f"{NS}::text_encoder", mutates_args=(), device_types="cuda")
+def text_encoder(handle: int, tokens: Tensor, lengths: Tensor, spk: Optional[Tensor], n_feats: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """TextEncoder.forward (reference model/text_encoder.py:321-335) -> gtts_encoder_forward.  tokens (B, T) int64, lengths (B)
+    int64 -> mu (B, n_feats, T), logw (B, 1, T), x_mask (B, 1, T)."""
+    B, T = tokens.shape
+    mu = torch.empty(B, n_feats, T, dtype=torch.float32, device=tokens.device)
+    logw = torch.empty(B, 1, T, dtype=torch.float32, device=tokens.device)
+    x_mask = torch.empty(B, 1, T, dtype=torch.float32, device=tokens.device)
+    lib = _lib.load()
+    with torch.cuda.device(tokens.device):
+        rc = lib.gtts_encoder_forward(ctypes.c_void_p(handle), tokens.data_ptr(), lengths.data_ptr(), _ptr(spk), mu.data_ptr(),
+                                      logw.data_ptr(), x_mask.data_ptr(), B, T, _stream(tokens))
+        _lib.check(rc, "encoder_forward")
+        _lib.check(lib.gtts_encoder_check_tokens(ctypes.c_void_p(handle), _stream(tokens)), "encoder_forward")
+    return mu, logw, x_mask
+
+
+@text_encoder.register_fake
+def _(handle, tokens, lengths, spk, n_feats):
+    B, T = tokens.shape
+    f = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=tokens.device)   # noqa: E731
+    return f(B, n_feats, T), f(B, 1, T), f(B, 1, T)
+
+
+@torch.library.custom_op(f"{NS}::vocoder", mutates_args=(), device_types="cuda")
+def vocoder(handle: int, mel: Tensor, hop: int, flags: int) -> Tensor:
+    """HiFi-GAN Generator.forward (reference hifi-gan/models.py:101-118) -> gtts_vocoder_forward.  mel (B, 80, T) -> (B, 1, T * hop)."""
+    B, _, T = mel.shape
+    out = torch.empty(B, 1, T * hop, dtype=torch.float32, device=mel.device)
+    with torch.cuda.device(mel.device):
+        rc = _lib.load().gtts_vocoder_forward(ctypes.c_void_p(handle), mel.data_ptr(), out.data_ptr(), B, T, flags, _stream(mel))
+    _lib.check(rc, "vocoder_forward")
+    return out
+
+
+@vocoder.register_fake
+def _(handle, mel, hop, flags):
+    B, _, T = mel.shape
+    return torch.empty(B, 1, T * hop, dtype=torch.float32, device=mel.device)
+
+
+OPS = ("reverse_diffusion", "estimator", "estimator_vjp", "maximum_path", "log_prior", "align_outputs", "forward_diffusion", "score_loss",
+       "text_encoder", "vocoder")

@@ -176,5 +176,9 @@ def test_torch_library_ops_are_registered(pkg):
         xt, zm = torch.ops.gradtts_b200.forward_diffusion(z, m, z, t, z, 0.05, 20.0)
         assert xt.shape == z.shape and zm.shape == z.shape
         assert torch.ops.gradtts_b200.score_loss(z, z, m, t, 0.05, 20.0).shape == ()
+        tok = torch.empty(2, 9, dtype=torch.long, device="cuda")
+        mu, lw, xm = torch.ops.gradtts_b200.text_encoder(0, tok, torch.empty(2, dtype=torch.long, device="cuda"), None, 80)
+        assert mu.shape == (2, 80, 9) and lw.shape == (2, 1, 9) and xm.shape == (2, 1, 9)
+        assert torch.ops.gradtts_b200.vocoder(0, torch.empty(2, 80, 5, device="cuda"), 256, 0).shape == (2, 1, 1280)
     with pytest.raises(NotImplementedError):
         torch.ops.gradtts_b200.log_prior(torch.zeros(1, 80, 3), torch.zeros(1, 80, 5))
