@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgradtts_b200.so")
-SOURCES = ["capi.cu", "decoder.cu", "conv_tc.cu", "conv_tc_halo.cu", "conv_tc_halo2.cu", "conv_ffma.cu", "attention.cu", "attention_tc.cu", "pointwise.cu", "mas.cu", "align.cu", "loss.cu", "backward.cu", "backward_params.cu", "vocoder.cu", "text_encoder.cu", "microbench.cu"]
+SOURCES = ["capi.cu", "decoder.cu", "conv_tc.cu", "conv_tc_halo.cu", "conv_tc_halo2.cu", "conv_ffma.cu", "attention.cu", "attention_tc.cu", "pointwise.cu", "mas.cu", "align.cu", "loss.cu", "backward.cu", "backward_params.cu", "wgrad_tc.cu", "vocoder.cu", "text_encoder.cu", "microbench.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -523,6 +523,14 @@ int conv_wgrad(ActKind act, const ConvGeom& g, const void* gout, const void* x0,
     return 0;
 }
 
+int wgrad_reduce(const float* partial, float* dst, int slices, int n_pt, int Cout, int Cin, int kind, float scale, int accumulate,
+                 cudaStream_t s) {
+    const size_t n = (size_t)n_pt * Cout * Cin;
+    wgrad_reduce_kernel<<<nblk(n, 256), 256, 0, s>>>(partial, dst, slices, n_pt, Cout, Cin, kind, 3, scale, accumulate);
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // whole-batch column sums (bias gradients): dst[C]
 int col_sums(ActKind act, const void* gsrc, float* partial, float* dst, long npix, int C, float scale, int accumulate, cudaStream_t s) {
     GTTS_REQUIRE(C % 8 == 0 && C <= 256 && 256 % (C / 8) == 0, "col_sums: C must be 64, 128 or 256");

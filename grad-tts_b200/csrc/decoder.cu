@@ -143,6 +143,7 @@ struct Decoder {
                               // wins where launches are latency-bound (B = 1, T = 400: 21 us vs 17 + 8.6 us per Block) and loses on big
                               // batches (chunk 16 x 1720: 128->128 @h40 249 vs 109 + 57 us) because every sample costs one grid barrier.
     int fuse_epi_max_b = 2;
+    int wgrad_tc = 1;         // bf16 training plan: weight gradients of the stride-1 convs on tcgen05 (wgrad_tc.cu); 0 = mma.sync kernel
     int side_lanes = 1;       // small batches: time-embedding MLP and res_conv on a parallel branch of the step graph (GTTS_SIDE=0: off)
     int fuse_async = 0;       // 1: GroupNorm+Mish(+time bias / residual) by asynchronous apply warps inside the Block conv (the raw tile goes
                               // through L2, the MMA pipeline never waits).  Correct and bitwise equal to the separate pass, but OFF: with the
@@ -486,6 +487,7 @@ struct Plan {
     bool est_mode, sde;
     DevMem mem;
     std::vector<TcConvPlan*> tc_plans;
+    std::vector<WgradTcPlan*> wg_plans;
     std::vector<std::function<int(cudaStream_t)>> ops;
     struct OpInfo { std::string name; int is_conv; double flops; double bytes; };
     std::vector<OpInfo> info;
@@ -530,6 +532,7 @@ struct Plan {
     ~Plan() {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         for (auto* p : tc_plans) conv_tc_plan_destroy(p);
+        for (auto* p : wg_plans) wgrad_tc_plan_destroy(p);
     }
 };
 
@@ -895,7 +898,8 @@ struct PlanBuilder {
     void add_conv_param_grads(const std::string& prefix, const ConvGeom& gfwd, const void* gout, const void* x0, const void* x1, int kind_layout,
                               float* dw_override = nullptr, bool want_bias = true) {
         int slices;
-        const size_t pf = wgrad_partial_floats(gfwd, &slices);
+        const bool tcw = kind == ACT_BF16 && d->wgrad_tc && wgrad_tc_eligible(gfwd);   // tcgen05 wgrad (wgrad_tc.cu)
+        const size_t pf = tcw ? wgrad_tc_partial_floats(gfwd, d->num_sms, &slices) : wgrad_partial_floats(gfwd, &slices);
         float* part = (float*)pooled(pf * 4);
         float* bpart = (float*)pooled((size_t)256 * gfwd.Cout * 4);
         if (failed) return;
@@ -904,6 +908,23 @@ struct PlanBuilder {
         ActKind k = kind;
         ConvGeom g = gfwd;
         const long npix_out = (long)g.B * g.Hout * g.Wout;
+        if (tcw) {
+            WgradTcPlan* tp = wgrad_tc_plan_create(g, gout, x0, x1, part, d->num_sms);
+            if (!tp) { failed = true; return; }
+            pl->wg_plans.push_back(tp);
+            const int n_pt = g.ntaps, cin = g.Cin0 + g.Cin1;
+            pl->push("bwd_wgrad_" + std::to_string(cin) + "_" + std::to_string(g.Cout) + "_h" + std::to_string(g.Hin), 0,
+                     2.0 * (double)g.B * g.Hg * g.Wg * g.Cout * g.ntaps * cin, 0.0,
+                     [k, g, gout, tp, part, dw, kind_layout, db, bpart, npix_out, slices, n_pt, cin](cudaStream_t s) {
+                         if (int rc = wgrad_tc_launch(tp, s)) return rc;
+                         if (int rc = wgrad_reduce(part, dw, slices, n_pt, g.Cout, cin, kind_layout, 1.0f, 0, s)) return rc;
+                         if (db) return col_sums(k, gout, bpart, db, npix_out, g.Cout, 1.0f, 0, s);
+                         return 0;
+                     });
+            pl->kernels_per_step += db ? 3 : 1;
+            release(part, true); release(bpart, true);
+            return;
+        }
         pl->push("bwd_wgrad_" + std::to_string(g.Cin0 + g.Cin1) + "_" + std::to_string(g.Cout) + "_h" + std::to_string(g.Hin), 0,
                  2.0 * (double)g.B * g.nphase * g.Hg * g.Wg * g.Cout * g.ntaps * (g.Cin0 + g.Cin1), 0.0,
                  [k, g, gout, x0, x1, part, dw, kind_layout, db, bpart, npix_out](cudaStream_t s) {
@@ -1513,7 +1534,7 @@ int get_plan(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, cu
                       (est_mode ? "e" : "s") + (sde ? "n" : "o") + (vjp ? (pgrads ? "p" : "v") : "-") + (d->use_graph ? "g" : "x") +
                       std::to_string(d->conv_impl_bf16) + std::to_string(d->halo_mode) + std::to_string(d->fused_attn) + std::to_string(d->fuse_gn) +
                       std::to_string(d->fuse_epi) + "." + std::to_string(d->fuse_epi_max_b) + "." + std::to_string(d->fp32_tc) + std::to_string(d->fuse_async) +
-                      std::to_string(d->side_lanes);
+                      std::to_string(d->side_lanes) + std::to_string(d->wgrad_tc);
     auto it = d->plans.find(key);
     if (it != d->plans.end()) {
         it->second.last_use = ++d->use_clock;
@@ -1799,6 +1820,7 @@ Decoder* decoder_new(int n_spks, int n_feats, int dim, double beta_min, double b
     if (const char* e = getenv("GTTS_FP32_TC")) d->fp32_tc = atoi(e);
     if (const char* e = getenv("GTTS_FUSE_ASYNC")) d->fuse_async = atoi(e);
     if (const char* e = getenv("GTTS_SIDE")) d->side_lanes = atoi(e);
+    if (const char* e = getenv("GTTS_WGRAD_TC")) d->wgrad_tc = atoi(e);
     if (cudaEventCreateWithFlags(&d->done_ev, cudaEventDisableTiming) != cudaSuccess) {
         set_error("cudaEventCreate failed"); cudaGetLastError(); delete d; return nullptr;
     }
@@ -1850,6 +1872,7 @@ int decoder_set_option(Decoder* d, const char* key, int value) {
     else if (k == "fp32_tc") d->fp32_tc = value;
     else if (k == "fuse_async") d->fuse_async = value;
     else if (k == "side_lanes") d->side_lanes = value;
+    else if (k == "wgrad_tc") d->wgrad_tc = value;
     else { set_error("unknown option " + k); return 2; }
     return 0;
 }

@@ -250,6 +250,17 @@ int split_pack_weights(const float* w, void* out, size_t rows, int K, cudaStream
 
 // ---- parameter gradients (backward_params.cu): reductions of the activation gradients against the saved forward tensors
 size_t wgrad_partial_floats(const ConvGeom& g, int* slices_out);
+// the same on tcgen05 (wgrad_tc.cu): stride-1 convs, bf16 activations; operands read MN-major straight from the NHWC tensors
+struct WgradTcPlan;   // opaque, owns the tensor maps of one (geometry, buffers) binding
+bool wgrad_tc_eligible(const ConvGeom& g);
+size_t wgrad_tc_partial_floats(const ConvGeom& g, int num_sms, int* slices_out);
+WgradTcPlan* wgrad_tc_plan_create(const ConvGeom& g, const void* gout, const void* x0, const void* x1, float* partial, int num_sms);
+void wgrad_tc_plan_destroy(WgradTcPlan* p);
+int wgrad_tc_slices(const WgradTcPlan* p);
+int wgrad_tc_launch(const WgradTcPlan* p, cudaStream_t s);
+// fixed-order sum of the partial slices, scattered into the PyTorch weight layout (kind as conv_wgrad)
+int wgrad_reduce(const float* partial, float* dst, int slices, int n_pt, int Cout, int Cin, int kind, float scale, int accumulate,
+                 cudaStream_t s);
 // dW of any conv geometry; dst in the PyTorch layout: kind 0 = Conv2d (Cout, Cin, kh, kw) (also 1x1), 1 = ConvTranspose2d (Cin, Cout, 4, 4),
 // 2 = packed rows [n_pt * Cout][Cin] as is
 int conv_wgrad(ActKind act, const ConvGeom& g, const void* gout, const void* x0, const void* x1, float* partial, float* dst, int kind,
