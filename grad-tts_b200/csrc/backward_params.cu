@@ -7,6 +7,7 @@
 //   GroupNorm      dgamma[c], dbeta[c] = sum g_y * mask * Mish'(n) * {xhat, 1}      (gn_param_grad)
 //   final conv, first conv / first res_conv (tiny K): dedicated kernels
 // All reductions are two-stage and run in a fixed order (deterministic); accumulation in fp32, inputs in the activation type.
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -244,10 +245,24 @@ col_sums_kernel(const T* __restrict__ gsrc, const float* __restrict__ mask, floa
     const long p_lo = blockIdx.x * pix_per_block, p_hi = min(pix_per_sample, p_lo + pix_per_block);
     const T* base = gsrc + (size_t)b * pix_per_sample * C;
     float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (long p = p_lo + pslot; p < p_hi; p += pstep) {
+    // four pixels per round, their loads issued together (one load per round left the kernel latency-bound: 20 us for 28 MB)
+    long p = p_lo + pslot;
+    for (; p + 3 * pstep < p_hi; p += 4 * pstep) {
+        float v[4][8], m[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long q = p + u * pstep;
+            m[u] = mask ? mask[(size_t)b * W + (int)(q % W)] : 1.0f;
+            Act<T>::load8(base + (size_t)q * C + vec * 8, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] = fmaf(v[u][j], m[u], s[j]);
+    }
+    for (; p < p_hi; p += pstep) {
         float v[8];
         const float m = mask ? mask[(size_t)b * W + (int)(p % W)] : 1.0f;
-        if (m == 0.f) continue;
         Act<T>::load8(base + (size_t)p * C + vec * 8, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) s[j] = fmaf(v[j], m, s[j]);
@@ -264,16 +279,37 @@ col_sums_kernel(const T* __restrict__ gsrc, const float* __restrict__ mask, floa
     }
 }
 // dst[g * n + i] (+)= scale * sum_{k < blocks} partial[(g * blocks + k) * n + i]   (dst row stride dst_ld)
-__global__ void rows_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dst, int blocks, int n, int groups, int dst_ld,
-                                   float scale, int accumulate) {
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= n * groups) return;
-    const int gq = i / n, c = i % n;
-    float s = 0.f;
-    for (int k = 0; k < blocks; ++k) s += partial[((size_t)gq * blocks + k) * n + c];
-    s *= scale;
-    float* d = dst + (size_t)gq * dst_ld + c;
-    *d = accumulate ? *d + s : s;
+// dst[gq * dst_ld + c] = scale * sum_k partial[(gq * blocks + k) * n + c]  (c < n; columns >= split go to dst2[c - split]).
+// Block = 32 columns x 32 row slots: a thread adds every 32nd row with four independent accumulators, then the 32 slots are added
+// in slot order in shared memory (fixed order: deterministic).  The first version gave every column ONE thread that walked all rows
+// serially: 7-40 us per call for a few megabytes, more than the tensor-core weight-gradient kernels they follow.
+// grid (ceil(n / 32), groups), 1024 threads.
+__global__ void __launch_bounds__(1024)
+rows_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dst, float* __restrict__ dst2, int split, int blocks, int n,
+                   int dst_ld, float scale, int accumulate) {
+    __shared__ float sm[32][33];
+    const int cx = threadIdx.x & 31, slot = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx, gq = blockIdx.y;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (c < n) {
+        const float* base = partial + (size_t)gq * blocks * n + c;
+        int k = slot;
+        for (; k + 96 < blocks; k += 128) {
+            a0 += base[(size_t)k * n]; a1 += base[(size_t)(k + 32) * n];
+            a2 += base[(size_t)(k + 64) * n]; a3 += base[(size_t)(k + 96) * n];
+        }
+        for (; k < blocks; k += 32) a0 += base[(size_t)k * n];
+    }
+    sm[slot][cx] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (slot == 0 && c < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) t += sm[q][cx];
+        t *= scale;
+        float* d = (dst2 && c >= split) ? dst2 + (size_t)gq * dst_ld + (c - split) : dst + (size_t)gq * dst_ld + c;
+        *d = accumulate ? *d + t : t;
+    }
 }
 // ------------------------------------------------------------------------------------------------ GroupNorm affine gradients
 // dgamma[c] = sum g_y * mask * Mish'(n) * xhat,  dbeta[c] = sum g_y * mask * Mish'(n);  partial[block][2C]; grid (blocks, B)
@@ -316,14 +352,6 @@ gn_param_kernel(GnBwdArgs a, float* __restrict__ partial, int blocks) {
         for (int ps = 0; ps < pstep; ++ps) t += sm[(ps * C8 + v) * 16 + which * 8 + j];
         partial[((size_t)b * blocks + blockIdx.x) * 2 * a.C + o] = t;
     }
-}
-
-__global__ void gn_rows_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int C) {
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= 2 * C) return;
-    float s = 0.f;
-    for (int k = 0; k < rows; ++k) s += partial[(size_t)k * 2 * C + i];
-    if (i < C) dgamma[i] = s; else dbeta[i - C] = s;
 }
 
 // ------------------------------------------------------------------------------------------------ final conv (64 -> 1) gradients
@@ -540,7 +568,7 @@ int col_sums(ActKind act, const void* gsrc, float* partial, float* dst, long npi
     const long ppb = (npix + blocks - 1) / blocks;
     if (act == ACT_F32) col_sums_kernel<float><<<dim3(blocks, 1), 256, 0, s>>>((const float*)gsrc, nullptr, partial, npix, 1, C, ppb);
     else col_sums_kernel<__nv_bfloat16><<<dim3(blocks, 1), 256, 0, s>>>((const __nv_bfloat16*)gsrc, nullptr, partial, npix, 1, C, ppb);
-    rows_reduce_kernel<<<nblk(C, 256), 256, 0, s>>>(partial, dst, blocks, C, 1, C, scale, accumulate);
+    rows_reduce_kernel<<<dim3((C + 31) / 32, 1), 1024, 0, s>>>(partial, dst, nullptr, 0, blocks, C, C, scale, accumulate);
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -556,18 +584,18 @@ int col_sums_per_sample(ActKind act, const void* gsrc, const float* mask, float*
     const long ppb = (hw + blocks - 1) / blocks;
     if (act == ACT_F32) col_sums_kernel<float><<<dim3(blocks, B), 256, 0, s>>>((const float*)gsrc, mask, partial, hw, W, C, ppb);
     else col_sums_kernel<__nv_bfloat16><<<dim3(blocks, B), 256, 0, s>>>((const __nv_bfloat16*)gsrc, mask, partial, hw, W, C, ppb);
-    rows_reduce_kernel<<<nblk((size_t)C * B, 256), 256, 0, s>>>(partial, dst, blocks, C, B, dst_ld, 1.0f, 0);
+    rows_reduce_kernel<<<dim3((C + 31) / 32, B), 1024, 0, s>>>(partial, dst, nullptr, 0, blocks, C, dst_ld, 1.0f, 0);
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 int gn_param_grad(ActKind act, const GnBwdArgs& a, float* partial, float* dgamma, float* dbeta, cudaStream_t s) {
-    const int blocks = gn_bwd_blocks(a.H, a.W);
+    const int blocks = std::min(gn_bwd_blocks(a.H, a.W), 24);         // 24 x B CTAs fill the GPU; fewer partial rows to reduce
     dim3 grid(blocks, a.B);
     if (act == ACT_F32) gn_param_kernel<float><<<grid, 256, 0, s>>>(a, partial, blocks);
     else gn_param_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(a, partial, blocks);
     // partial rows are [dgamma (C) | dbeta (C)]: two reductions with a row stride of 2C
-    gn_rows_reduce_kernel<<<nblk(2 * a.C, 256), 256, 0, s>>>(partial, dgamma, dbeta, blocks * a.B, a.C);
+    rows_reduce_kernel<<<dim3((2 * a.C + 31) / 32, 1), 1024, 0, s>>>(partial, dgamma, dbeta, a.C, blocks * a.B, 2 * a.C, 2 * a.C, 1.0f, 0);
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -581,7 +609,7 @@ int final_param_grad(ActKind act, const void* rawf, const float* stats, const fl
     const long ppb = (npix + blocks - 1) / blocks;
     if (act == ACT_F32) final_param_kernel<float><<<blocks, 256, 0, s>>>((const float*)rawf, stats, gamma, beta, v, mask, partial, B, H, W, ppb);
     else final_param_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)rawf, stats, gamma, beta, v, mask, partial, B, H, W, ppb);
-    rows_reduce_kernel<<<1, 256, 0, s>>>(partial, dwf_dbf, blocks, 65, 1, 65, 1.0f, accumulate);
+    rows_reduce_kernel<<<dim3(3, 1), 1024, 0, s>>>(partial, dwf_dbf, nullptr, 0, blocks, 65, 65, 1.0f, accumulate);
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -600,7 +628,7 @@ int first_param_grad(ActKind act, const void* graw1, const void* gres, const flo
     dim3 grid(blocks, B);
     if (act == ACT_F32) first_param_kernel<float><<<grid, 256, 0, s>>>((const float*)graw1, (const float*)gres, mu, x, splane, mask, partial, B, H, W, cin, blocks);
     else first_param_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)graw1, (const __nv_bfloat16*)gres, mu, x, splane, mask, partial, B, H, W, cin, blocks);
-    rows_reduce_kernel<<<nblk(64 * nk, 256), 256, 0, s>>>(partial, dst, blocks * B, 64 * nk, 1, 64 * nk, 1.0f, accumulate);
+    rows_reduce_kernel<<<dim3((64 * nk + 31) / 32, 1), 1024, 0, s>>>(partial, dst, nullptr, 0, blocks * B, 64 * nk, 64 * nk, 1.0f, accumulate);
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
