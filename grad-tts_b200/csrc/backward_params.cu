@@ -615,7 +615,7 @@ int final_param_grad(ActKind act, const void* rawf, const float* stats, const fl
 }
 
 int first_param_blocks(int H, int W) {
-    int blocks = (H * W + 1023) / 1024;
+    int blocks = (H * W + 255) / 256;                                 // 256 pixels (four 64-pixel rounds) per CTA: the rounds are serial
     if (blocks > 64) blocks = 64;
     return blocks < 1 ? 1 : blocks;
 }
