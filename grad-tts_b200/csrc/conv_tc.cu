@@ -45,7 +45,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     // stages, are loaded once per CTA into their own region (1x1, stride-2 and transposed 64-channel convs: the kernel is
     // L2->SMEM-fill bound and a weight tile is a third to two thirds of every stage).
     const int resident = p.b_resident;
-    const int stage_bytes = resident ? kABytes : kStage;
+    const int stage_bytes = p.halo1d ? p.a_stage : (resident ? kABytes : kStage);
     uint8_t* smem_b = smem + (size_t)p.stages * stage_bytes;        // resident weights (b_slots tiles)
     const TcShared sh = tc_shared(smem_b + (size_t)(resident ? p.b_slots : 0) * kBBytes);
     uint64_t* full = sh.full;
@@ -87,6 +87,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h;
                 const int ph = (tile / tiles_per_phase) % p.nphase, b = tile / (tiles_per_phase * p.nphase);
                 const int h0 = th * p.bh, w0 = tw * p.bw;
+                if (p.halo1d) {
+                    // one box of bw + 2*halo positions per chunk; every tap reads it through a shifted descriptor
+                    for (int ck = 0; ck < p.nchunk0 + p.nchunk1; ++ck) {
+                        mbar_wait(&empty[stage], phase ^ 1u);
+                        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                        mbar_expect_tx(&full[stage], (uint32_t)(dummy ? 0 : p.a_bytes));
+                        if (!dummy) {
+                            int which, chan;
+                            tc_chunk_src(p, ck, &which, &chan);
+                            tma_load_4d(which ? &mapA1 : &mapA0, &full[stage], sa, chan, w0 - p.halo1d, h0, b);
+                        }
+                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    }
+                    continue;
+                }
                 for (int tap = 0; tap < p.ntaps; ++tap) {
                     const int dy = p.dy[ph][tap], dx = p.dx[ph][tap];
                     const int wr = p.wrow[ph][tap] + b * p.w_batch_rows;
@@ -139,6 +154,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             mbar_wait(&sh.tempty[buf], ((uint32_t)(it / acc_bufs<N>()) & 1u) ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
+            if (p.halo1d) {
+                const int nck = p.nchunk0 + p.nchunk1;
+                for (int ck = 0; ck < nck; ++ck) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t adesc0 = a_desc0 + (uint64_t)stage * stage_step;
+                        for (int tap = 0; tap < p.ntaps; ++tap) {
+                            // rows tap_row .. tap_row + 127 of the box: the swizzle is a function of the absolute shared-memory
+                            // address, so a start address shifted by whole 128-byte rows reads what TMA wrote (conv_tc_halo.cu)
+                            const uint64_t adesc = adesc0 + (uint64_t)((p.tap_row[tap] * 128) >> 4);
+                            const uint64_t bdesc = b_res0 + (uint64_t)(tap * nck + ck) * (uint64_t)(kBBytes >> 4);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
+                                           (uint32_t)((ck | tap | k) != 0));
+                        }
+                        tc_commit(&empty[stage]);
+                        if (ck == nck - 1) tc_commit(&sh.tfull[buf]);
+                    }
+                    __syncwarp();
+                    if (++stage == nstage) { stage = 0; phase ^= 1u; }
+                }
+                continue;
+            }
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
@@ -387,7 +427,30 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
     } else {
         const int btile = g.Cout * 128, nwt = g.nphase * g.ntaps * (p.nchunk0 + p.nchunk1);
         const bool want_res = getenv("GTTS_TAP_RESIDENT") ? atoi(getenv("GTTS_TAP_RESIDENT")) != 0 : true;
-        if (want_res && g.w_batch_rows == 0 && nwt * btile + 4 * kABytes <= budget && nwt * btile < (1 << 20)) {
+        // 1-D halo mode (the vocoder's dilated Conv1d stacks): H = 1, stride 1, several taps along W, weights resident
+        int halo = 0;
+        bool h1 = g.Hg == 1 && g.Hin == 1 && g.stride == 1 && g.nphase == 1 && g.ntaps > 1 && g.w_batch_rows == 0 && !g.split &&
+                  !p.mc && !(getenv("GTTS_HALO1D") && atoi(getenv("GTTS_HALO1D")) == 0);
+        for (int t = 0; t < g.ntaps && h1; ++t) {
+            if (g.dy[0][t] != 0) h1 = false;
+            const int a = g.dx[0][t] < 0 ? -g.dx[0][t] : g.dx[0][t];
+            if (a > halo) halo = a;
+        }
+        if (h1 && halo >= 1 && p.bw + 2 * halo <= 256) {
+            const int rows = p.bw + 2 * halo;
+            const int a_stage = (rows * 128 + 1023) / 1024 * 1024;
+            if (want_res && nwt * btile + 2 * a_stage <= budget && nwt * btile < (1 << 20)) {
+                p.halo1d = halo; p.a_stage = a_stage; p.a_bytes = rows * 128;
+                for (int t = 0; t < g.ntaps; ++t) p.tap_row[t] = (int16_t)(halo + g.dx[0][t]);
+                p.b_resident = 1; p.b_slots = nwt;
+                int stages = (budget - nwt * btile) / a_stage;
+                if (stages > 8) stages = 8;
+                p.stages = stages;
+                pl->smem = (size_t)stages * a_stage + (size_t)nwt * btile + kMiscBytes + 1024;
+            }
+        }
+        if (p.halo1d) {
+        } else if (want_res && g.w_batch_rows == 0 && nwt * btile + 4 * kABytes <= budget && nwt * btile < (1 << 20)) {
             p.b_resident = 1; p.b_slots = nwt;
             int stages = (budget - nwt * btile) / kABytes;
             if (stages > 8) stages = 8;
@@ -438,6 +501,7 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
             uint64_t str[3] = {(uint64_t)C * 2, W * C * 2, H * W * C * 2};
             uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, 1};
             if (halo_mode) { box[1] = halo_mode == 2 ? 10 : 16; box[2] = 18; }
+            if (p.halo1d) box[1] = (uint32_t)(p.bw + 2 * p.halo1d);
             if (p.halo_t) {                                          // dims (C, H, W, B): H is the fast box dimension
                 uint64_t dims_t[4] = {(uint64_t)C, H, W, (uint64_t)g.B};
                 uint64_t str_t[3] = {W * C * 2, (uint64_t)C * 2, H * W * C * 2};

@@ -46,6 +46,10 @@ struct TcParams {
     int split;
     int16_t a_off[48];
     int8_t a_map[48];
+    // 1-D halo mode of the per-tap kernel (conv_tc.cu; H = 1, stride 1, resident weights): ONE box of bw + 2*halo positions per
+    // 64-channel chunk, the taps are row-shifted descriptor views of it (tap_row[t] = halo + dx[t] rows of 128 bytes)
+    int halo1d, a_stage;
+    int16_t tap_row[16];
     ConvEpilogue e;
 };
 
