@@ -47,7 +47,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int resident = p.b_resident;
     const int stage_bytes = p.halo1d ? p.a_stage : (resident ? kABytes : kStage);
     uint8_t* smem_b = smem + (size_t)p.stages * stage_bytes;        // resident weights (b_slots tiles)
-    const TcShared sh = tc_shared(smem_b + (size_t)(resident ? p.b_slots : 0) * kBBytes);
+    const TcShared sh = tc_shared(smem_b + (size_t)((resident || p.halo1d) ? p.b_slots : 0) * kBBytes);   // (1-D halo mode: B ring)
     uint64_t* full = sh.full;
     uint64_t* empty = sh.empty;
 
@@ -58,7 +58,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tma_prefetch_desc(&mapW);
         tma_prefetch_desc(&mapWh);
     }
-    const uint32_t tmem_base = tc_prologue<N>(p, sh, p.stages, 1, tid, warp, lane);
+    const uint32_t tmem_base = tc_prologue<N>(p, sh, p.stages, (p.halo1d && !p.b_resident) ? p.b_slots : 1, tid, warp, lane);
     const int n_it = tc_num_iters(p);
     const int G = (int)gridDim.x;
 
@@ -68,8 +68,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (warp == 0) {
         // ================================================================ TMA producer
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = 0, sb_ring = 0;
+            uint32_t phase = 0, phb_ring = 0;
             const uint32_t rank = p.mc ? cluster_ctarank() : 0u;
             if (resident && n_it > 0) {
                 const int nck = p.nchunk0 + p.nchunk1;
@@ -88,7 +88,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 const int ph = (tile / tiles_per_phase) % p.nphase, b = tile / (tiles_per_phase * p.nphase);
                 const int h0 = th * p.bh, w0 = tw * p.bw;
                 if (p.halo1d) {
-                    // one box of bw + 2*halo positions per chunk; every tap reads it through a shifted descriptor
+                    // one box of bw + 2*halo positions per chunk; every tap reads it through a shifted descriptor.  Weights that do
+                    // not fit shared memory stream through their own ring (one slot per (tap, chunk)), so a tile costs one A box
+                    // per chunk instead of one per (tap, chunk)
                     for (int ck = 0; ck < p.nchunk0 + p.nchunk1; ++ck) {
                         mbar_wait(&empty[stage], phase ^ 1u);
                         uint8_t* sa = smem + (size_t)stage * stage_bytes;
@@ -99,6 +101,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             tma_load_4d(which ? &mapA1 : &mapA0, &full[stage], sa, chan, w0 - p.halo1d, h0, b);
                         }
                         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                        if (!resident) {
+                            for (int tap = 0; tap < p.ntaps; ++tap) {
+                                mbar_wait(&sh.emptyb[sb_ring], phb_ring ^ 1u);
+                                mbar_expect_tx(&sh.fullb[sb_ring], (uint32_t)kBBytes);
+                                tma_load_2d(&mapW, &sh.fullb[sb_ring], smem_b + (size_t)sb_ring * kBBytes, ck * 64, p.wrow[0][tap]);
+                                if (++sb_ring == p.b_slots) { sb_ring = 0; phb_ring ^= 1u; }
+                            }
+                        }
                     }
                     continue;
                 }
@@ -144,8 +154,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const uint64_t b_desc0 = make_sw128_kmajor_desc(smem_u32(smem) + kABytes);
         const uint64_t stage_step = (uint64_t)(stage_bytes >> 4);
         const uint64_t b_res0 = make_sw128_kmajor_desc(smem_u32(smem_b));
-        int stage = 0, it = 0;
-        uint32_t phase = 0;
+        int stage = 0, it = 0, sb_ring = 0;
+        uint32_t phase = 0, phb_ring = 0;
         const int mc = p.mc;
         if (resident && n_it > 0) mbar_wait(&sh.fullb[0], 0u);
         for (it = 0; it < n_it; ++it) {
@@ -154,7 +164,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             mbar_wait(&sh.tempty[buf], ((uint32_t)(it / acc_bufs<N>()) & 1u) ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * N);
-            if (p.halo1d) {
+            if (p.halo1d && resident) {
                 const int nck = p.nchunk0 + p.nchunk1;
                 for (int ck = 0; ck < nck; ++ck) {
                     mbar_wait(&full[stage], phase);
@@ -175,6 +185,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                         if (ck == nck - 1) tc_commit(&sh.tfull[buf]);
                     }
                     __syncwarp();
+                    if (++stage == nstage) { stage = 0; phase ^= 1u; }
+                }
+                continue;
+            }
+            if (p.halo1d) {                                          // streamed weights: one ring slot per (tap, chunk)
+                const int nck = p.nchunk0 + p.nchunk1;
+                for (int ck = 0; ck < nck; ++ck) {
+                    mbar_wait(&full[stage], phase);
+                    const uint64_t adesc0 = a_desc0 + (uint64_t)stage * stage_step;
+                    for (int tap = 0; tap < p.ntaps; ++tap) {
+                        mbar_wait(&sh.fullb[sb_ring], phb_ring);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t adesc = adesc0 + (uint64_t)((p.tap_row[tap] * 128) >> 4);
+                            const uint64_t bdesc = b_res0 + (uint64_t)sb_ring * (uint64_t)(kBBytes >> 4);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
+                                           (uint32_t)((ck | tap | k) != 0));
+                            tc_commit(&sh.emptyb[sb_ring]);
+                            if (tap == p.ntaps - 1) {
+                                tc_commit(&empty[stage]);
+                                if (ck == nck - 1) tc_commit(&sh.tfull[buf]);
+                            }
+                        }
+                        __syncwarp();
+                        if (++sb_ring == p.b_slots) { sb_ring = 0; phb_ring ^= 1u; }
+                    }
                     if (++stage == nstage) { stage = 0; phase ^= 1u; }
                 }
                 continue;
@@ -447,6 +485,16 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
                 if (stages > 8) stages = 8;
                 p.stages = stages;
                 pl->smem = (size_t)stages * a_stage + (size_t)nwt * btile + kMiscBytes + 1024;
+            } else if (g.Cout <= 128 && !(getenv("GTTS_HALO1D") && atoi(getenv("GTTS_HALO1D")) == 1)) {
+                // weights streamed through their own ring (GTTS_HALO1D=1: resident-weight layers only)
+                int slots = (budget - 3 * a_stage) / btile;
+                if (slots > 16) slots = 16;
+                if (slots >= 4) {
+                    p.halo1d = halo; p.a_stage = a_stage; p.a_bytes = rows * 128;
+                    for (int t = 0; t < g.ntaps; ++t) p.tap_row[t] = (int16_t)(halo + g.dx[0][t]);
+                    p.b_resident = 0; p.b_slots = slots; p.stages = 3;
+                    pl->smem = (size_t)3 * a_stage + (size_t)slots * btile + kMiscBytes + 1024;
+                }
             }
         }
         if (p.halo1d) {
