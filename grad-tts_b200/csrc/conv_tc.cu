@@ -485,7 +485,7 @@ TcConvPlan* conv_tc_plan_create(const ConvGeom& g, const void* src0, const void*
                 if (stages > 8) stages = 8;
                 p.stages = stages;
                 pl->smem = (size_t)stages * a_stage + (size_t)nwt * btile + kMiscBytes + 1024;
-            } else if (g.Cout <= 128 && !(getenv("GTTS_HALO1D") && atoi(getenv("GTTS_HALO1D")) == 1)) {
+            } else if (!(getenv("GTTS_HALO1D") && atoi(getenv("GTTS_HALO1D")) == 1)) {
                 // weights streamed through their own ring (GTTS_HALO1D=1: resident-weight layers only)
                 int slots = (budget - 3 * a_stage) / btile;
                 if (slots > 16) slots = 16;
