@@ -47,29 +47,42 @@ __global__ void mel_to_nwc_kernel(const float* __restrict__ mel, T* __restrict__
 template <typename T>
 __global__ void sum_lrelu_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c, T* __restrict__ out,
                                  long n8, float scale, float slope) {
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
-        float va[8], vb[8], vc[8];
-        Act<T>::load8(a + i * 8, va);
-        if (b) {
-            Act<T>::load8(b + i * 8, vb);
+    // four vectors of 8 per thread and round, their (up to twelve) loads issued before the first use: a streaming pass over
+    // gigabytes with one load in flight per thread ran at 40 % of the HBM rate
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n8; i0 += 4 * stride) {
+        float va[4][8], vb[4][8], vc[4][8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) va[k] += vb[k];
+        for (int u = 0; u < 4; ++u) {
+            const long i = i0 + u * stride;
+            if (i < n8) {
+                Act<T>::load8(a + i * 8, va[u]);
+                if (b) Act<T>::load8(b + i * 8, vb[u]);
+                if (c) Act<T>::load8(c + i * 8, vc[u]);
+            }
         }
-        if (c) {
-            Act<T>::load8(c + i * 8, vc);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) va[k] += vc[k];
-        }
+        for (int u = 0; u < 4; ++u) {
+            const long i = i0 + u * stride;
+            if (i < n8) {
+                float o[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const float v = va[k] * scale;
-            Act<T>::st(out + i * 8 + k, v > 0.f ? v : v * slope);
+                for (int k = 0; k < 8; ++k) {
+                    float v = va[u][k];
+                    if (b) v += vb[u][k];
+                    if (c) v += vc[u][k];
+                    v *= scale;
+                    o[k] = v > 0.f ? v : v * slope;
+                }
+                Act<T>::store8(out + i * 8, o);
+            }
         }
     }
 }
 
-// conv_post: (B, L, Cp) -> (B, 1, L) fp32, k taps, Cout = 1, + bias, tanh.  w: [k][C] fp32.
-template <typename T>
+// conv_post: (B, L, Cp) -> (B, 1, L) fp32, k taps, Cout = 1, + bias, tanh.  w: [k][C] fp32.  kC8 > 0: C = 8 * kC8 and k = 7 known at
+// compile time (the reference configuration: every load of a position's window is issued before the first FMA).
+template <typename T, int kC8>
 __global__ void conv_post_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                  float* __restrict__ out, int B, int L, int C, int Cp, int k) {
     extern __shared__ float s_w[];
@@ -82,16 +95,40 @@ __global__ void conv_post_kernel(const T* __restrict__ x, const float* __restric
         const int l = (int)(i % L);
         const long b = i / L;
         float acc = b0;
-        for (int t = 0; t < k; ++t) {
-            const int il = l + t - pad;
-            if (il < 0 || il >= L) continue;
-            const T* xp = x + ((size_t)b * L + il) * Cp;
-            const float* wp = s_w + t * C;
-            for (int c = 0; c < C; c += 8) {
-                float v[8];
-                Act<T>::load8(xp + c, v);
+        if (kC8 > 0) {
+            float v[7][kC8 > 0 ? kC8 : 1][8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) acc = fmaf(v[q], wp[c + q], acc);
+            for (int t = 0; t < 7; ++t) {
+                const int il = l + t - 3;
+                const bool ok = il >= 0 && il < L;
+                const T* xp = x + ((size_t)b * L + (ok ? il : l)) * Cp;
+#pragma unroll
+                for (int c8 = 0; c8 < kC8; ++c8) {
+                    Act<T>::load8(xp + c8 * 8, v[t][c8]);
+                    if (!ok) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) v[t][c8][q] = 0.f;
+                    }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 7; ++t)
+#pragma unroll
+                for (int c8 = 0; c8 < kC8; ++c8)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc = fmaf(v[t][c8][q], s_w[t * (kC8 * 8) + c8 * 8 + q], acc);
+        } else {
+            for (int t = 0; t < k; ++t) {
+                const int il = l + t - pad;
+                if (il < 0 || il >= L) continue;
+                const T* xp = x + ((size_t)b * L + il) * Cp;
+                const float* wp = s_w + t * C;
+                for (int c = 0; c < C; c += 8) {
+                    float v[8];
+                    Act<T>::load8(xp + c, v);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc = fmaf(v[q], wp[c + q], acc);
+                }
             }
         }
         out[i] = tanhf(acc);
@@ -445,8 +482,9 @@ struct Builder {
             const void* src = lx;
             pl->ops.push_back([=](cudaStream_t s) {
                 const size_t sm = (size_t)7 * Cc * 4;
-                if (k == ACT_F32) conv_post_kernel<float><<<blocks, 128, sm, s>>>((const float*)src, wp, bp, out, Bb, Ll, Cc, Cpp, 7);
-                else conv_post_kernel<__nv_bfloat16><<<blocks, 128, sm, s>>>((const __nv_bfloat16*)src, wp, bp, out, Bb, Ll, Cc, Cpp, 7);
+                if (k == ACT_F32) conv_post_kernel<float, 0><<<blocks, 128, sm, s>>>((const float*)src, wp, bp, out, Bb, Ll, Cc, Cpp, 7);
+                else if (Cc == 32) conv_post_kernel<__nv_bfloat16, 4><<<blocks, 128, sm, s>>>((const __nv_bfloat16*)src, wp, bp, out, Bb, Ll, Cc, Cpp, 7);
+                else conv_post_kernel<__nv_bfloat16, 0><<<blocks, 128, sm, s>>>((const __nv_bfloat16*)src, wp, bp, out, Bb, Ll, Cc, Cpp, 7);
                 GTTS_CHECK_CUDA(cudaGetLastError());
                 return 0;
             });
