@@ -39,8 +39,8 @@ struct TcParams {
     int mc;                                        // 1: 2-CTA cluster, weight tiles multicast (conv_tc.cu); 2: CTA pair, cta_group::2 MMAs (conv_tc_halo2.cu)
     unsigned long long* dbg_out;                   // optional per-CTA cycle counters (GTTS_CONV_TIMING), 16 per CTA
     int dbg;                                       // experiment switches (GTTS_CONV_DBG): 1 no MMA issue, 2 no epilogue work, 4 no A loads (halo), 8 no stats ring
-    int8_t dy[4][16], dx[4][16];
-    int wrow[4][16];
+    int8_t dy[4][kMaxTaps], dx[4][kMaxTaps];
+    int wrow[4][kMaxTaps];
     int oy[4], ox[4];
     // split (fp32-on-tensor-cores) convs: K chunk ck reads source a_map[ck] at channel a_off[ck] of its 3*Cin-channel plane tensor
     int split;
@@ -49,7 +49,7 @@ struct TcParams {
     // 1-D halo mode of the per-tap kernel (conv_tc.cu; H = 1, stride 1, resident weights): ONE box of bw + 2*halo positions per
     // 64-channel chunk, the taps are row-shifted descriptor views of it (tap_row[t] = halo + dx[t] rows of 128 bytes)
     int halo1d, a_stage;
-    int16_t tap_row[16];
+    int16_t tap_row[kMaxTaps];
     ConvEpilogue e;
 };
 

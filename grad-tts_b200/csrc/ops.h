@@ -20,14 +20,16 @@ enum ActKind { ACT_F32 = 0, ACT_BF16 = 1 };
 //   1x1    : 1 tap
 //   convT  : 4 phases x 4 taps, out_step 2                         (Upsample, diffusion.py:21-27)
 // ------------------------------------------------------------------------------------------------
+constexpr int kMaxTaps = 24;   // taps per phase: 16 for the 4x4 stride-2 conv (Upsample dgrad), up to 17 for the position-packed k = 11 Conv1d (vocoder.cu)
+
 struct ConvGeom {
     int B, Hin, Win;          // input spatial size (both sources)
     int Hg, Wg;               // output grid per phase
     int Hout, Wout;           // output tensor spatial size
     int Cin0, Cin1, Cout;
     int ntaps, nphase, stride, out_step;
-    int8_t dy[4][16], dx[4][16];   // up to 16 taps per phase (the 4x4 stride-2 conv that is the Upsample's data gradient)
-    int wrow[4][16];
+    int8_t dy[4][kMaxTaps], dx[4][kMaxTaps];   // up to kMaxTaps taps per phase
+    int wrow[4][kMaxTaps];
     int oy[4], ox[4];
     int w_batch_rows;         // 0, or Cout for per-sample weights
     // fp32 arithmetic on the tensor cores: the sources are [hi | mid | lo] bf16 planes of fp32 activations (3*Cin channels per

@@ -14,6 +14,7 @@
 // layer in strict fp32 mode run on the CUDA-core implicit GEMM (conv_ffma.cu); conv_post (32 -> 1) + tanh is a small
 // dedicated kernel.  One forward over a chunk of utterances is captured as a CUDA graph per (B, T).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -149,14 +150,96 @@ __global__ void pack_w1d_kernel(const float* __restrict__ src, T* __restrict__ d
     }
 }
 
+// ---- position packing for stages with fewer than 64 channels ---------------------------------------------------------------
+// A (B, L, C) tensor with C = 32 is, byte for byte, a (B, L/2, 64) tensor whose row j holds positions 2j and 2j+1.  Instead of
+// zero-padding the channels to 64 (twice the HBM bytes of the longest, HBM-bound stage, and 4x its MMAs) the conv is run on that
+// view: output row j, slot a (position P*j + a) reads input position P*j + a + s = row j + floor((a+s)/P), slot (a+s) mod P, so a
+// k-tap conv with shifts s_t becomes a conv over rows with taps delta in {floor((a+s_t)/P)} and 64 x 64 block weights
+//   W'[delta][(a, co)][(b, ci)] = W_t[co][ci]  where  a + s_t = delta*P + b.
+// dst rows [delta index][P*C], cols [P*C]; deltas[] lists the row offsets in ascending order.
+template <typename T>
+__global__ void pack_w1d_packed_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int k, int dil, int P, int ndelta,
+                                       const int* __restrict__ deltas) {
+    const int PC = P * C;
+    const long n = (long)ndelta * PC * PC;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const int ri = (int)(i % PC);
+        const long r = i / PC;
+        const int ro = (int)(r % PC), di = (int)(r / PC);
+        const int a = ro / C, co = ro % C, b = ri / C, ci = ri % C;
+        const int sft = deltas[di] * P + b - a;                       // shift in positions
+        float v = 0.f;
+        if (sft % dil == 0) {
+            const int t = sft / dil + (k - 1) / 2;
+            if (t >= 0 && t < k) v = src[((size_t)co * C + ci) * k + t];
+        }
+        Act<T>::st(dst + i, v);
+    }
+}
+// Transposed conv (stride u = m * P, kernel k, padding (k-u)/2) from an unpacked (B, Lin, Cin_p) input into the packed output:
+// output position o = u*i + p lies in row m*i + p/P, slot p mod P; row phase pr = p / P.  dst rows [pr][delta index][P*C], cols
+// [Cin_p]: W'[pr][delta][(a, co)][ci] = w[ci][co][r] with r = (pr*P + a) + pad - delta*u (ConvTranspose1d weight (Cin, Cout, k)).
+template <typename T>
+__global__ void pack_wT_packed_kernel(const float* __restrict__ src, T* __restrict__ dst, int Cin, int Cin_p, int C, int k, int u, int P,
+                                      int nphase, int ndelta, const int* __restrict__ deltas /* [nphase][ndelta] */) {
+    const int PC = P * C, pad = (k - u) / 2;
+    const long n = (long)nphase * ndelta * PC * Cin_p;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % Cin_p);
+        long r = i / Cin_p;
+        const int ro = (int)(r % PC); r /= PC;
+        const int di = (int)(r % ndelta), pr = (int)(r / ndelta);
+        const int a = ro / C, co = ro % C;
+        const int rr = pr * P + a + pad - deltas[pr * ndelta + di] * u;
+        float v = 0.f;
+        if (ci < Cin && rr >= 0 && rr < k) v = src[((size_t)ci * C + co) * k + rr];
+        Act<T>::st(dst + i, v);
+    }
+}
+
 int pad_ch(int c, int q) { return (c + q - 1) / q * q; }
+
+// positions per row of a stage with C channels (1 = not packed)
+int pack_factor(int C) { return (C < 64 && C >= 8 && 64 % C == 0) ? 64 / C : 1; }
+
+// row offsets of a k-tap, dilation-d conv in the packed domain (ascending)
+std::vector<int> packed_deltas(int k, int d, int P) {
+    std::vector<int> out;
+    for (int t = 0; t < k; ++t)
+        for (int a = 0; a < P; ++a) {
+            const int sft = (t - (k - 1) / 2) * d + a;
+            const int dl = sft >= 0 ? sft / P : -((-sft + P - 1) / P);
+            if (std::find(out.begin(), out.end(), dl) == out.end()) out.push_back(dl);
+        }
+    std::sort(out.begin(), out.end());
+    return out;
+}
+// row offsets of row phase pr of the transposed conv into a packed stage; every phase is padded to the same count with a
+// harmless duplicate... no: phases with fewer offsets get offsets whose weights are all zero (listed for a uniform tap count)
+std::vector<int> packed_convT_deltas(int k, int u, int P, int pr) {
+    std::vector<int> out;
+    const int pad = (k - u) / 2;
+    for (int a = 0; a < P; ++a) {
+        const int p = pr * P + a;
+        for (int r = (p + pad) % u; r < k; r += u) {
+            const int dl = (p + pad - r) / u;
+            if (std::find(out.begin(), out.end(), dl) == out.end()) out.push_back(dl);
+        }
+    }
+    std::sort(out.begin(), out.end());
+    return out;
+}
+
 
 struct ConvW {
     // effective PyTorch-layout fp32 weights as uploaded (device), and the packed forms (built lazily per activation type)
     float* w = nullptr; float* b = nullptr;
     size_t w_numel = 0, b_numel = 0;
     void* packed[2] = {nullptr, nullptr};     // [ACT_F32], [ACT_BF16]
-    float* bias_p = nullptr;                  // bias zero-padded to Cout_p
+    float* bias_p = nullptr;                  // bias zero-padded to Cout_p (position-packed stages: repeated per slot)
+    size_t packed_n = 0;                      // elements of the packed buffers (cached plans hold pointers into them)
+    std::vector<int> deltas;                  // position-packed layers: row offsets of the taps ([phase][ndelta] for the transposed conv)
+    int ndelta = 0;
 };
 
 }  // namespace
@@ -272,6 +355,17 @@ ConvGeom geom_conv1d(int B, int L, int Cin_p, int Cout_p, int k, int dil) {
     return g;
 }
 
+// conv over rows with explicit tap offsets (position-packed stages): tap t reads row j + deltas[t], weight rows t*Cout_p ..
+ConvGeom geom_rows(int B, int L, int Cin_p, int Cout_p, const std::vector<int>& deltas) {
+    ConvGeom g;
+    memset(&g, 0, sizeof(g));
+    g.B = B; g.Hin = 1; g.Win = L; g.Hg = 1; g.Wg = L; g.Hout = 1; g.Wout = L;
+    g.Cin0 = Cin_p; g.Cin1 = 0; g.Cout = Cout_p;
+    g.ntaps = (int)deltas.size(); g.nphase = 1; g.stride = 1; g.out_step = 1;
+    for (int t = 0; t < g.ntaps; ++t) { g.dx[0][t] = (int8_t)deltas[t]; g.wrow[0][t] = t * Cout_p; }
+    return g;
+}
+
 // Transposed conv, stride u, kernel k, padding (k-u)/2, output phases p0 .. p0+np-1 (np <= 4): output o = j*u + p reads input
 // j + d with weight tap r = p + pad - d*u for every r in [0, k) of that residue (hifi-gan/models.py:88-91)
 bool geom_convT1d(ConvGeom* out, int B, int Lin, int Cin_p, int Cout_p, int k, int u, int p0, int np) {
@@ -301,6 +395,15 @@ bool geom_convT1d(ConvGeom* out, int B, int Lin, int Cin_p, int Cout_p, int k, i
     g.ntaps = ntaps;
     *out = g;
     return true;
+}
+
+// Position packing is used for the last stage only (its consumers are the point-wise kernels and conv_post, which read the dense
+// (B, L, C) tensor as it is) and when the stage's upsampling rate equals the packing factor, so that input position i of the
+// transposed conv produces exactly row i.
+bool stage_packed(const Vocoder* v, int i, int Co) {
+    if (getenv("GTTS_VOC_NOPACK")) return false;
+    const int P = pack_factor(Co);
+    return P > 1 && i == (int)v->rates.size() - 1 && v->rates[i] == P;
 }
 
 struct Builder {
@@ -397,16 +500,22 @@ struct Builder {
         pl->release(x0);
         for (int i = 0; i < n_up; ++i) {
             const int u = v->rates[i], k = v->up_k[i];
-            const int Co = C / 2, Cop = std::max(64, pad_ch(Co, 64));
-            const long Lo = L * u;
+            const int Co = C / 2;
+            const bool packed = stage_packed(v, i, Co);           // < 64 channels: several positions per 64-channel row
+            const int Cop = packed ? 64 : std::max(64, pad_ch(Co, 64));
+            const long Lpos = L * u;                              // output positions
+            const long Lo = packed ? Lpos / pack_factor(Co) : Lpos;   // rows of the stage's tensors
             // ---- ups[i]: x = convT(lrelu(x)); the epilogue also writes lrelu(x) for the resblocks' first convs
             void* x = act(Lo, Cop);
             void* lxo = act(Lo, Cop);
             if (failed) return 4;
             const ConvW* wu = get("ups." + std::to_string(i));
             if (failed) return 3;
+            if (packed) {
+                add_conv("ups" + std::to_string(i), geom_rows(B, (int)L, Cp, Cop, wu->deltas), lx, wu, wu->ndelta * Cop, nullptr, x, 0, lxo, 0.1f);
+            }
             // phases grouped so that every launch has one tap count
-            for (int p0 = 0; p0 < u;) {
+            for (int p0 = packed ? u : 0; p0 < u;) {
                 int np = std::min(4, u - p0);
                 ConvGeom g;
                 while (np > 0 && !geom_convT1d(&g, B, (int)L, Cp, Cop, k, u, p0, np)) --np;
@@ -443,14 +552,20 @@ struct Builder {
                         if (failed) return 3;
                         void* t = act(Lo, Cop);
                         if (failed) return 4;
-                        add_conv(base + ".c1", geom_conv1d(B, (int)Lo, Cop, Cop, rk, dil[m]), lcur, w1, rk * Cop, nullptr, t, 1, nullptr, 0.1f);
-                        add_conv(base + ".c2", geom_conv1d(B, (int)Lo, Cop, Cop, rk, 1), t, w2, rk * Cop, cur, nx, 0, lnx, 0.1f);
+                        if (packed) {
+                            add_conv(base + ".c1", geom_rows(B, (int)Lo, Cop, Cop, w1->deltas), lcur, w1, w1->ndelta * Cop, nullptr, t, 1, nullptr, 0.1f);
+                            add_conv(base + ".c2", geom_rows(B, (int)Lo, Cop, Cop, w2->deltas), t, w2, w2->ndelta * Cop, cur, nx, 0, lnx, 0.1f);
+                        } else {
+                            add_conv(base + ".c1", geom_conv1d(B, (int)Lo, Cop, Cop, rk, dil[m]), lcur, w1, rk * Cop, nullptr, t, 1, nullptr, 0.1f);
+                            add_conv(base + ".c2", geom_conv1d(B, (int)Lo, Cop, Cop, rk, 1), t, w2, rk * Cop, cur, nx, 0, lnx, 0.1f);
+                        }
                         pl->release(t);
                     } else {
                         // xt = c(lrelu(x)); x = xt + x   (ResBlock2.forward, models.py:66-70)
                         const ConvW* w1 = get(base + ".convs." + std::to_string(m));
                         if (failed) return 3;
-                        add_conv(base + ".c", geom_conv1d(B, (int)Lo, Cop, Cop, rk, dil[m]), lcur, w1, rk * Cop, cur, nx, 0, lnx, 0.1f);
+                        if (packed) add_conv(base + ".c", geom_rows(B, (int)Lo, Cop, Cop, w1->deltas), lcur, w1, w1->ndelta * Cop, cur, nx, 0, lnx, 0.1f);
+                        else add_conv(base + ".c", geom_conv1d(B, (int)Lo, Cop, Cop, rk, dil[m]), lcur, w1, rk * Cop, cur, nx, 0, lnx, 0.1f);
                     }
                     cur = nx; lcur = lnx;
                 }
@@ -466,7 +581,8 @@ struct Builder {
             add_sum(ys[0], n_rb > 1 ? ys[1] : nullptr, n_rb > 2 ? ys[2] : nullptr, nlx, (long)B * Lo * Cop, 1.0f / (float)n_rb, slope);
             pl->release(x);
             for (void* y : ys) pl->release(y);
-            lx = nlx; C = Co; Cp = Cop; L = Lo;
+            lx = nlx; C = Co; L = Lpos;
+            Cp = packed ? Co : Cop;                               // channels per POSITION of the stage's tensors (packed = dense)
         }
         // ---- conv_post (k = 7, Cout = 1) + tanh (models.py:115-116)
         {
@@ -498,6 +614,18 @@ struct Builder {
 // (re)build the packed weights of every layer (both activation types: the strict mode and conv_pre / conv_post use fp32)
 int pack_all(Vocoder* v) {
     if (v->packed_valid) return 0;
+    // packed buffers are reused across re-packs (cached plans hold pointers into them); a size change drops the plans
+    auto ensure_packed = [&](ConvW& w, size_t n) -> int {
+        if (w.packed_n == n && w.packed[ACT_F32] && w.packed[ACT_BF16]) return 0;
+        GTTS_CHECK_CUDA(cudaDeviceSynchronize());
+        v->plans.clear(); v->plan_order.clear();
+        cudaFree(w.packed[ACT_F32]); cudaFree(w.packed[ACT_BF16]);
+        w.packed[ACT_F32] = w.packed[ACT_BF16] = nullptr;
+        GTTS_CHECK_CUDA(cudaMalloc(&w.packed[ACT_F32], n * 4));
+        GTTS_CHECK_CUDA(cudaMalloc(&w.packed[ACT_BF16], n * 2));
+        w.packed_n = n;
+        return 0;
+    };
     auto pack_conv = [&](const std::string& name, int Cout, int Cin, int k, int Cout_p, int Cin_p, bool transposed) -> int {
         auto it = v->params.find(name);
         if (it == v->params.end() || !it->second.w || !it->second.b) { set_error("vocoder: parameter " + name + " was not set"); return 3; }
@@ -505,8 +633,8 @@ int pack_all(Vocoder* v) {
         GTTS_REQUIRE(w.w_numel == (size_t)Cout * Cin * k, "vocoder: weight has the wrong number of elements");
         GTTS_REQUIRE(w.b_numel == (size_t)Cout, "vocoder: bias has the wrong number of elements");
         const size_t n = (size_t)k * Cout_p * Cin_p;
-        if (!w.packed[ACT_F32]) GTTS_CHECK_CUDA(cudaMalloc(&w.packed[ACT_F32], n * 4));
-        if (!w.packed[ACT_BF16]) GTTS_CHECK_CUDA(cudaMalloc(&w.packed[ACT_BF16], n * 2));
+        w.deltas.clear(); w.ndelta = 0;
+        if (int rc = ensure_packed(w, n)) return rc;
         if (int rc = pack_conv1d_weight(ACT_F32, w.w, w.packed[ACT_F32], Cout, Cin, k, Cout_p, Cin_p, transposed, 0)) return rc;
         if (int rc = pack_conv1d_weight(ACT_BF16, w.w, w.packed[ACT_BF16], Cout, Cin, k, Cout_p, Cin_p, transposed, 0)) return rc;
         if (!w.bias_p) GTTS_CHECK_CUDA(cudaMalloc((void**)&w.bias_p, (size_t)std::max(Cout_p, 1) * 4));
@@ -518,8 +646,58 @@ int pack_all(Vocoder* v) {
     int C = v->initial, Cp = std::max(64, pad_ch(C, 64));
     if (int rc = pack_conv("conv_pre", C, v->num_mels, 7, Cp, melp, false)) return rc;
     const int n_rb = (int)v->rb_k.size();
+    int* d_deltas = nullptr;
+    GTTS_CHECK_CUDA(cudaMalloc((void**)&d_deltas, 64 * sizeof(int)));
+    // position-packed layer: block weights over row offsets (see pack_w1d_packed_kernel)
+    auto pack_packed = [&](const std::string& name, int Cc, int k, int dil, int P, int Cin_t, int Cin_p_t, int u_t) -> int {
+        auto it = v->params.find(name);
+        if (it == v->params.end() || !it->second.w || !it->second.b) { set_error("vocoder: parameter " + name + " was not set"); return 3; }
+        ConvW& w = it->second;
+        const bool transposed = u_t > 0;
+        GTTS_REQUIRE(w.w_numel == (size_t)Cc * (transposed ? Cin_t : Cc) * k, "vocoder: weight has the wrong number of elements");
+        GTTS_REQUIRE(w.b_numel == (size_t)Cc, "vocoder: bias has the wrong number of elements");
+        w.deltas = transposed ? packed_convT_deltas(k, u_t, P, 0) : packed_deltas(k, dil, P);
+        w.ndelta = (int)w.deltas.size();
+        GTTS_REQUIRE(w.ndelta >= 1 && w.ndelta <= kMaxTaps, "vocoder: too many row offsets for a position-packed layer");
+        for (int dl : w.deltas) GTTS_REQUIRE(dl >= -127 && dl <= 127, "vocoder: row offset out of range");
+        GTTS_CHECK_CUDA(cudaMemcpy(d_deltas, w.deltas.data(), w.ndelta * sizeof(int), cudaMemcpyHostToDevice));
+        const int PC = P * Cc, cols = transposed ? Cin_p_t : PC;
+        const size_t n = (size_t)w.ndelta * PC * cols;
+        if (int rc = ensure_packed(w, n)) return rc;
+        const int blocks = (int)std::min<size_t>((n + 255) / 256, 4096);
+        if (transposed) {
+            pack_wT_packed_kernel<float><<<blocks, 256>>>(w.w, (float*)w.packed[ACT_F32], Cin_t, Cin_p_t, Cc, k, u_t, P, 1, w.ndelta, d_deltas);
+            pack_wT_packed_kernel<__nv_bfloat16><<<blocks, 256>>>(w.w, (__nv_bfloat16*)w.packed[ACT_BF16], Cin_t, Cin_p_t, Cc, k, u_t, P, 1, w.ndelta, d_deltas);
+        } else {
+            pack_w1d_packed_kernel<float><<<blocks, 256>>>(w.w, (float*)w.packed[ACT_F32], Cc, k, dil, P, w.ndelta, d_deltas);
+            pack_w1d_packed_kernel<__nv_bfloat16><<<blocks, 256>>>(w.w, (__nv_bfloat16*)w.packed[ACT_BF16], Cc, k, dil, P, w.ndelta, d_deltas);
+        }
+        GTTS_CHECK_CUDA(cudaGetLastError());
+        GTTS_CHECK_CUDA(cudaDeviceSynchronize());               // d_deltas is reused by the next layer
+        if (!w.bias_p) GTTS_CHECK_CUDA(cudaMalloc((void**)&w.bias_p, (size_t)PC * 4));
+        for (int a = 0; a < P; ++a) GTTS_CHECK_CUDA(cudaMemcpy(w.bias_p + (size_t)a * Cc, w.b, (size_t)Cc * 4, cudaMemcpyDeviceToDevice));
+        return 0;
+    };
     for (int i = 0; i < (int)v->rates.size(); ++i) {
-        const int Co = C / 2, Cop = std::max(64, pad_ch(Co, 64));
+        const int Co = C / 2;
+        if (stage_packed(v, i, Co)) {
+            const int P = pack_factor(Co);
+            if (int rc = pack_packed("ups." + std::to_string(i), Co, v->up_k[i], 1, P, C, Cp, v->rates[i])) return rc;
+            for (int j = 0; j < n_rb; ++j) {
+                const std::string base = "resblocks." + std::to_string(i * n_rb + j);
+                for (int m = 0; m < (int)v->rb_d[j].size(); ++m) {
+                    if (v->resblock == 1) {
+                        if (int rc = pack_packed(base + ".convs1." + std::to_string(m), Co, v->rb_k[j], v->rb_d[j][m], P, 0, 0, 0)) return rc;
+                        if (int rc = pack_packed(base + ".convs2." + std::to_string(m), Co, v->rb_k[j], 1, P, 0, 0, 0)) return rc;
+                    } else {
+                        if (int rc = pack_packed(base + ".convs." + std::to_string(m), Co, v->rb_k[j], v->rb_d[j][m], P, 0, 0, 0)) return rc;
+                    }
+                }
+            }
+            C = Co; Cp = Co;
+            continue;
+        }
+        const int Cop = std::max(64, pad_ch(Co, 64));
         if (int rc = pack_conv("ups." + std::to_string(i), Co, C, v->up_k[i], Cop, Cp, true)) return rc;
         for (int j = 0; j < n_rb; ++j) {
             const std::string base = "resblocks." + std::to_string(i * n_rb + j);
@@ -534,6 +712,7 @@ int pack_all(Vocoder* v) {
         }
         C = Co; Cp = Cop;
     }
+    cudaFree(d_deltas);
     // conv_post: [7][pad8(C)] fp32 rows (Cout_p = 1)
     if (int rc = pack_conv("conv_post", 1, C, 7, 1, pad_ch(C, 8), false)) return rc;
     GTTS_CHECK_CUDA(cudaDeviceSynchronize());
@@ -630,7 +809,7 @@ size_t workspace_per_sample(const Vocoder* v, int T, ActKind kind) {
     size_t peak = 0;
     for (size_t i = 0; i < v->rates.size(); ++i) {
         C /= 2; L *= v->rates[i];
-        const size_t one = (size_t)L * std::max(64, pad_ch(C, 64)) * esz(kind);
+        const size_t one = (size_t)L * (stage_packed(v, (int)i, C) ? C : std::max(64, pad_ch(C, 64))) * esz(kind);
         peak = std::max(peak, one * 11);
     }
     return peak;
