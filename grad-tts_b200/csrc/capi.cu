@@ -15,11 +15,15 @@
 namespace gtts {
 static thread_local std::string g_last_error;
 void set_error(const std::string& msg) { g_last_error = msg; }
+static thread_local int g_pdl_override = 0;
+void pdl_set_override(int on) { g_pdl_override = on; }
 bool pdl_enabled() {
     static int v = -1;
-    // measured on B200: no gain (-2 %), so off unless GTTS_PDL=1
+    // measured on B200: -2 % on the throughput workloads, so off unless GTTS_PDL=1 -- except while a small-batch plan is being
+    // captured (pdl_set_override, decoder.cu): there most SMs are idle, the successor's CTAs start on them while the predecessor
+    // still runs, and its prologue and resident-weight loads come off the critical path
     if (v < 0) { const char* e = getenv("GTTS_PDL"); v = e ? (atoi(e) != 0) : 0; }
-    return v != 0;
+    return v != 0 || g_pdl_override != 0;
 }
 }  // namespace gtts
 

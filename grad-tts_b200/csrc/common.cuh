@@ -35,7 +35,8 @@ void set_error(const std::string& msg);          // defined in capi.cu
 // memory is visible.  pdl_trigger() at kernel entry lets the successor be scheduled as soon as resources free up.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-bool pdl_enabled();                               // capi.cu (env GTTS_PDL; default off: measured no gain on B200)
+bool pdl_enabled();                               // capi.cu (env GTTS_PDL; default off except for small-batch plans)
+void pdl_set_override(int on);                    // capi.cu: programmatic dependent launch for the launches that follow (this thread)
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

@@ -58,7 +58,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tma_prefetch_desc(&mapW);
         tma_prefetch_desc(&mapWh);
     }
-    const uint32_t tmem_base = tc_prologue<N>(p, sh, p.stages, (p.halo1d && !p.b_resident) ? p.b_slots : 1, tid, warp, lane);
+    const uint32_t tmem_base = tc_prologue<N>(p, sh, p.stages, (p.halo1d && !p.b_resident) ? p.b_slots : 1, tid, warp, lane, true);
     const int n_it = tc_num_iters(p);
     const int G = (int)gridDim.x;
 
@@ -80,6 +80,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                             tma_load_2d(&mapW, &sh.fullb[0], smem_b + (size_t)((ph * p.ntaps + tap) * nck + ck) * kBBytes, ck * 64,
                                         p.wrow[ph][tap]);
             }
+            pdl_wait();                                              // (see tc_prologue) activations of the predecessors from here on
             for (int it = 0; it < n_it; ++it) {
                 if (kStats && (it == n_it - 8 || it == n_it - 1)) prefetch_l2(p.e.gn_counters);   // see conv_tc_halo.cu
                 const int tile = (int)blockIdx.x + it * G;

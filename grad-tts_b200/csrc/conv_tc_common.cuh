@@ -162,7 +162,7 @@ __device__ __forceinline__ float warp_reduce8(const float (&v)[8], int lane) {
 // Common prologue: barrier init, TMEM allocation, bias staging.  `stages` A/B ring slots, `b_slots` extra B ring slots.
 template <int N>
 __device__ __forceinline__ uint32_t tc_prologue(const TcParams& p, const TcShared& sh, int nfull, int nfullb, int tid,
-                                                int warp, int lane) {
+                                                int warp, int lane, bool producer_waits_later = false) {
     pdl_trigger();
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < nfull; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], p.mc ? 2 : 1); }
@@ -179,7 +179,9 @@ __device__ __forceinline__ uint32_t tc_prologue(const TcParams& p, const TcShare
     __syncthreads();
     if (p.mc) cluster_sync();                      // the peer's barriers are initialised before anything targets them
     tc_fence_after();
-    pdl_wait();                                    // everything above overlapped the predecessor's tail
+    // everything above overlapped the predecessor's tail; a producer warp that first requests resident weight tiles (parameters,
+    // not produced by any kernel of the step) calls pdl_wait() itself after that
+    if (!(producer_waits_later && warp == 0)) pdl_wait();
     return *sh.tmem_slot;
 }
 

@@ -659,7 +659,9 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
     __syncthreads();
     cluster_sync();                                // the peer's barriers exist before anything targets them
     tc_fence_after();
-    pdl_wait();
+    // Programmatic dependent launch: everything above overlapped the predecessor's tail.  The producer warp goes on to request the
+    // resident weight tiles (parameters, not produced by any kernel of the step) BEFORE it waits for the predecessor's results.
+    if (warp != 0) pdl_wait();
     const uint32_t tmem_base = *sh.tmem_slot;
 
     const int nck = p.nchunk0 + p.nchunk1;
@@ -689,6 +691,7 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
                             tma_load_2d_2sm(&mapWh, fb, smem_b + (size_t)(ck * 9 + tap) * kBHalf, ck * 64, p.wrow[0][tap] + wrow_off);
                 }
             }
+            pdl_wait();                                              // activations, masks, statistics of the predecessors from here on
             for (int it = 0; it < n_it; ++it, tw.advance(G)) {
                 if (kStats && (it == n_it - 8 || it == n_it - 1)) prefetch_l2(p.e.gn_counters);
                 const int b = tw.b, h0 = tw.th * p.bh, w0 = tw.tw * p.bw;

@@ -143,6 +143,7 @@ struct Decoder {
                               // wins where launches are latency-bound (B = 1, T = 400: 21 us vs 17 + 8.6 us per Block) and loses on big
                               // batches (chunk 16 x 1720: 128->128 @h40 249 vs 109 + 57 us) because every sample costs one grid barrier.
     int fuse_epi_max_b = 2;
+    int pdl_small = 1;        // small-batch sampler plans are captured with programmatic dependent launch (GTTS_PDL_SMALL=0: off)
     int wgrad_tc = 1;         // bf16 training plan: weight gradients of the stride-1 convs on tcgen05 (wgrad_tc.cu); 0 = mma.sync kernel
     int side_lanes = 1;       // small batches: time-embedding MLP and res_conv on a parallel branch of the step graph (GTTS_SIDE=0: off)
     int fuse_async = 0;       // 1: GroupNorm+Mish(+time bias / residual) by asynchronous apply warps inside the Block conv (the raw tile goes
@@ -1478,6 +1479,9 @@ int plan_create(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde,
         std::vector<cudaEvent_t> evs;
         if (any_side) GTTS_CHECK_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
         auto new_event = [&]() { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); evs.push_back(e); return e; };
+        // small-batch sampler plans: programmatic dependent launch between consecutive kernels of the step (see pdl_enabled)
+        const bool pdl_small = d->pdl_small && B <= d->fuse_epi_max_b && !vjp;
+        pdl_set_override(pdl_small ? 1 : 0);
         GTTS_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
         if (!any_side) {
             rc = run_ops(cs);
@@ -1499,6 +1503,7 @@ int plan_create(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde,
             for (cudaEvent_t j : open) cudaStreamWaitEvent(cs, j, 0);   // every branch rejoins before the capture ends
         }
         cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        pdl_set_override(0);
         for (cudaEvent_t e : evs) cudaEventDestroy(e);
         if (side) cudaStreamDestroy(side);
         if (rc || ce != cudaSuccess) {
@@ -1534,7 +1539,7 @@ int get_plan(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, cu
                       (est_mode ? "e" : "s") + (sde ? "n" : "o") + (vjp ? (pgrads ? "p" : "v") : "-") + (d->use_graph ? "g" : "x") +
                       std::to_string(d->conv_impl_bf16) + std::to_string(d->halo_mode) + std::to_string(d->fused_attn) + std::to_string(d->fuse_gn) +
                       std::to_string(d->fuse_epi) + "." + std::to_string(d->fuse_epi_max_b) + "." + std::to_string(d->fp32_tc) + std::to_string(d->fuse_async) +
-                      std::to_string(d->side_lanes) + std::to_string(d->wgrad_tc);
+                      std::to_string(d->side_lanes) + std::to_string(d->wgrad_tc) + std::to_string(d->pdl_small);
     auto it = d->plans.find(key);
     if (it != d->plans.end()) {
         it->second.last_use = ++d->use_clock;
@@ -1821,6 +1826,7 @@ Decoder* decoder_new(int n_spks, int n_feats, int dim, double beta_min, double b
     if (const char* e = getenv("GTTS_FUSE_ASYNC")) d->fuse_async = atoi(e);
     if (const char* e = getenv("GTTS_SIDE")) d->side_lanes = atoi(e);
     if (const char* e = getenv("GTTS_WGRAD_TC")) d->wgrad_tc = atoi(e);
+    if (const char* e = getenv("GTTS_PDL_SMALL")) d->pdl_small = atoi(e);
     if (cudaEventCreateWithFlags(&d->done_ev, cudaEventDisableTiming) != cudaSuccess) {
         set_error("cudaEventCreate failed"); cudaGetLastError(); delete d; return nullptr;
     }
@@ -1873,6 +1879,7 @@ int decoder_set_option(Decoder* d, const char* key, int value) {
     else if (k == "fuse_async") d->fuse_async = value;
     else if (k == "side_lanes") d->side_lanes = value;
     else if (k == "wgrad_tc") d->wgrad_tc = value;
+    else if (k == "pdl_small") d->pdl_small = value;
     else { set_error("unknown option " + k); return 2; }
     return 0;
 }
