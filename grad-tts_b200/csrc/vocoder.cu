@@ -746,9 +746,13 @@ int plan_create(Vocoder* v, int B, int T, ActKind kind, VocoderPlan** out) {
     GTTS_CHECK_CUDA(cudaGetLastError());
     if (v->use_graph) {
         cudaGraph_t graph = nullptr;
+        // short inputs leave most SMs idle: programmatic dependent launch lets a conv's prologue and resident-weight loads run
+        // under its predecessor (pdl_enabled, capi.cu); off for the throughput shapes, where it costs 2 %
+        pdl_set_override((long)B * T <= 4096 && !getenv("GTTS_VOC_NOPDL") ? 1 : 0);
         GTTS_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
         rc = run_ops(cs);
         cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        pdl_set_override(0);
         if (rc || ce != cudaSuccess) {
             if (graph) cudaGraphDestroy(graph);
             cudaStreamDestroy(cs);
