@@ -48,6 +48,10 @@ gn_bwd_stats_kernel(GnBwdArgs a, int blocks) {
     const T* raw = reinterpret_cast<const T*>(a.raw) + (size_t)b * HW * a.C;
     const T* gy = reinterpret_cast<const T*>(a.gy) + (size_t)b * HW * a.C;
     float s1 = 0.f, s2 = 0.f;
+    float t1[8], t2[8];                                             // per channel: d gamma, d beta (training plans)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { t1[j] = 0.f; t2[j] = 0.f; }
+    const bool want_params = a.param_partials != nullptr;
     const int per_block = (HW + blocks - 1) / blocks;
     const int p_lo = blockIdx.x * per_block, p_hi = min(HW, p_lo + per_block);
     for (int p = p_lo + pslot; p < p_hi; p += pstep) {
@@ -60,9 +64,24 @@ gn_bwd_stats_kernel(GnBwdArgs a, int blocks) {
         for (int j = 0; j < 8; ++j) {
             const float xh = (r[j] - mean) * rstd;
             const float n = fmaf(ga[j], xh, be[j]);
-            const float dxh = gg[j] * m * mish_grad(n) * ga[j];
+            const float gn = gg[j] * m * mish_grad(n);              // gradient w.r.t. the GroupNorm output
+            const float dxh = gn * ga[j];
             s1 += dxh;
             s2 = fmaf(dxh, xh, s2);
+            if (want_params) { t1[j] = fmaf(gn, xh, t1[j]); t2[j] += gn; }
+        }
+    }
+    if (want_params) {
+        // per-channel partial row of this CTA: [d gamma (C) | d beta (C)], position slots added in order
+        __shared__ float s_t[256 * 16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s_t[threadIdx.x * 16 + j] = t1[j]; s_t[threadIdx.x * 16 + 8 + j] = t2[j]; }
+        __syncthreads();
+        for (int o = threadIdx.x; o < 2 * a.C; o += 256) {
+            const int which = o / a.C, c = o % a.C, v = c >> 3, j = c & 7;
+            float t = 0.f;
+            for (int ps = 0; ps < pstep; ++ps) t += s_t[(ps * C8 + v) * 16 + which * 8 + j];
+            a.param_partials[((size_t)b * blocks + blockIdx.x) * 2 * a.C + o] = t;
         }
     }
     // fixed-order CTA reduction: thread values -> shared, 16 threads sum their (group, which) column

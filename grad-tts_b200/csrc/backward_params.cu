@@ -4,7 +4,7 @@
 //   conv weights   dW[tap][co][ci] = sum_pixels g_out[p][co] * x[p + tap][ci]      (wgrad: an implicit GEMM with K = pixels, generic over
 //                                                                                   ConvGeom: 3x3, 1x1, stride 2, transposed phases)
 //   biases         db[co]          = sum_pixels g_out[p][co]                        (col_sums)
-//   GroupNorm      dgamma[c], dbeta[c] = sum g_y * mask * Mish'(n) * {xhat, 1}      (gn_param_grad)
+//   GroupNorm      dgamma[c], dbeta[c] = sum g_y * mask * Mish'(n) * {xhat, 1}      (gn_bwd statistics pass + gn_param_reduce)
 //   final conv, first conv / first res_conv (tiny K): dedicated kernels
 // All reductions are two-stage and run in a fixed order (deterministic); accumulation in fp32, inputs in the activation type.
 #include <algorithm>
@@ -311,49 +311,8 @@ rows_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dst, f
         *d = accumulate ? *d + t : t;
     }
 }
-// ------------------------------------------------------------------------------------------------ GroupNorm affine gradients
-// dgamma[c] = sum g_y * mask * Mish'(n) * xhat,  dbeta[c] = sum g_y * mask * Mish'(n);  partial[block][2C]; grid (blocks, B)
-template <typename T>
-__global__ void __launch_bounds__(256)
-gn_param_kernel(GnBwdArgs a, float* __restrict__ partial, int blocks) {
-    const int C8 = a.C >> 3, b = blockIdx.y;
-    const int vec = threadIdx.x % C8, pslot = threadIdx.x / C8, pstep = 256 / C8;
-    const int c0 = vec * 8, gsz = a.C >> 3, g = c0 / gsz;
-    const float mean = a.stats[(b * 8 + g) * 2], rstd = a.stats[(b * 8 + g) * 2 + 1];
-    float ga[8], be[8], s1[8], s2[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { ga[j] = a.gamma[c0 + j]; be[j] = a.beta[c0 + j]; s1[j] = 0.f; s2[j] = 0.f; }
-    const int HW = a.H * a.W;
-    const T* raw = reinterpret_cast<const T*>(a.raw) + (size_t)b * HW * a.C;
-    const T* gy = reinterpret_cast<const T*>(a.gy) + (size_t)b * HW * a.C;
-    const int per_block = (HW + blocks - 1) / blocks;
-    const int p_lo = blockIdx.x * per_block, p_hi = min(HW, p_lo + per_block);
-    for (int p = p_lo + pslot; p < p_hi; p += pstep) {
-        const float m = a.mask[(size_t)b * a.W + p % a.W];
-        if (m == 0.f) continue;
-        float r[8], gg[8];
-        Act<T>::load8(raw + (size_t)p * a.C + c0, r);
-        Act<T>::load8(gy + (size_t)p * a.C + c0, gg);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float xh = (r[j] - mean) * rstd;
-            const float gn = gg[j] * m * mish_grad_p(fmaf(ga[j], xh, be[j]));
-            s1[j] = fmaf(gn, xh, s1[j]);
-            s2[j] += gn;
-        }
-    }
-    __shared__ float sm[256 * 16];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { sm[threadIdx.x * 16 + j] = s1[j]; sm[threadIdx.x * 16 + 8 + j] = s2[j]; }
-    __syncthreads();
-    for (int o = threadIdx.x; o < 2 * a.C; o += 256) {
-        const int which = o / a.C, c = o % a.C, v = c >> 3, j = c & 7;
-        float t = 0.f;
-        for (int ps = 0; ps < pstep; ++ps) t += sm[(ps * C8 + v) * 16 + which * 8 + j];
-        partial[((size_t)b * blocks + blockIdx.x) * 2 * a.C + o] = t;
-    }
-}
-
+// (GroupNorm affine gradients: the per-channel partial sums come out of gn_bwd's statistics pass, backward.cu; gn_param_reduce below
+// adds the rows)
 // ------------------------------------------------------------------------------------------------ final conv (64 -> 1) gradients
 // score = (sum_c wf[c] * hf[c] + bf) * mask with hf = Mish(GN(rawf)) * mask:  dwf[c] = sum v * mask * hf[c],  dbf = sum v * mask.
 // partial[block][65]
@@ -589,13 +548,9 @@ int col_sums_per_sample(ActKind act, const void* gsrc, const float* mask, float*
     return 0;
 }
 
-int gn_param_grad(ActKind act, const GnBwdArgs& a, float* partial, float* dgamma, float* dbeta, cudaStream_t s) {
-    const int blocks = std::min(gn_bwd_blocks(a.H, a.W), 24);         // 24 x B CTAs fill the GPU; fewer partial rows to reduce
-    dim3 grid(blocks, a.B);
-    if (act == ACT_F32) gn_param_kernel<float><<<grid, 256, 0, s>>>(a, partial, blocks);
-    else gn_param_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(a, partial, blocks);
-    // partial rows are [dgamma (C) | dbeta (C)]: two reductions with a row stride of 2C
-    rows_reduce_kernel<<<dim3((2 * a.C + 31) / 32, 1), 1024, 0, s>>>(partial, dgamma, dbeta, a.C, blocks * a.B, 2 * a.C, 2 * a.C, 1.0f, 0);
+int gn_param_reduce(const float* param_partials, float* dgamma, float* dbeta, int B, int H, int W, int C, cudaStream_t s) {
+    const int blocks = gn_bwd_blocks(H, W);
+    rows_reduce_kernel<<<dim3((2 * C + 31) / 32, 1), 1024, 0, s>>>(param_partials, dgamma, dbeta, C, blocks * B, 2 * C, 2 * C, 1.0f, 0);
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -869,14 +869,30 @@ struct PlanBuilder {
         int Bb = B, Hh = H[lvl], Ww = W[lvl];
         pl->push("bwd_mask", 0, 0.0, 0.0, [k, in, m, out, Bb, Hh, Ww, C](cudaStream_t s) { return mask_mul(k, in, m, out, Bb, Hh, Ww, C, s); });
     }
-    void add_gn_bwd(int lvl, int C, const void* raw, const float* st, const BlockW& bw, const void* gy, void* graw) {
+    // GroupNorm + Mish backward; with `pprefix` (training plans) the same pass over (raw, gy) also leaves the per-channel partial
+    // sums of d gamma / d beta, reduced right after
+    void add_gn_bwd(int lvl, int C, const void* raw, const float* st, const BlockW& bw, const void* gy, void* graw,
+                    const std::string* pprefix = nullptr) {
         GnBwdArgs a;
         memset(&a, 0, sizeof(a));
         a.raw = raw; a.stats = st; a.gamma = bw.gamma; a.beta = bw.beta; a.mask = lmask[lvl]; a.gy = gy; a.graw = graw;
         a.partials = gn_bwd_partials; a.B = B; a.H = H[lvl]; a.W = W[lvl]; a.C = C;
         ActKind k = kind;
+        float* ppart = nullptr;
+        if (pprefix) {
+            ppart = (float*)pooled((size_t)B * gn_bwd_blocks(H[lvl], W[lvl]) * 2 * C * 4);
+            if (failed) return;
+            a.param_partials = ppart;
+        }
         pl->push("bwd_gn_" + std::to_string(C) + "_h" + std::to_string(H[lvl]), 0, 0.0, 0.0, [k, a](cudaStream_t s) { return gn_bwd(k, a, s); });
         pl->kernels_per_step++;                               // two launches
+        if (pprefix) {
+            float* dga = pg(*pprefix + ".block.1.weight");
+            float* dbe = pg(*pprefix + ".block.1.bias");
+            int Bb = B, Hh = H[lvl], Ww = W[lvl];
+            pl->push("bwd_gn_params", 0, 0.0, 0.0, [ppart, dga, dbe, Bb, Hh, Ww, C](cudaStream_t s) { return gn_param_reduce(ppart, dga, dbe, Bb, Hh, Ww, C, s); });
+            release(ppart, true);
+        }
     }
     void add_add(int lvl, int C, const void* a, const void* b, void* out) {
         ActKind k = kind;
@@ -936,21 +952,6 @@ struct PlanBuilder {
         pl->kernels_per_step += db ? 3 : 1;
         release(part, true); release(bpart, true);
     }
-    void add_gn_param_grads(const std::string& prefix, int lvl, int C, const void* raw, const float* st, const BlockW& bw, const void* gy) {
-        GnBwdArgs a;
-        memset(&a, 0, sizeof(a));
-        a.raw = raw; a.stats = st; a.gamma = bw.gamma; a.beta = bw.beta; a.mask = lmask[lvl]; a.gy = gy;
-        a.B = B; a.H = H[lvl]; a.W = W[lvl]; a.C = C;
-        float* part = (float*)pooled((size_t)B * 256 * 2 * C * 4);
-        if (failed) return;
-        float* dga = pg(prefix + ".block.1.weight");
-        float* dbe = pg(prefix + ".block.1.bias");
-        ActKind k = kind;
-        pl->push("bwd_gn_params", 0, 0.0, 0.0, [k, a, part, dga, dbe](cudaStream_t s) { return gn_param_grad(k, a, part, dga, dbe, s); });
-        pl->kernels_per_step++;
-        release(part, true);
-    }
-
     // ResnetBlock backward: gradient of `out` -> gradients of its input source(s) (or, for the first block, of the x plane)
     void resnet_backward(int r, int lvl, const void* x0, int c0, const void* x1, int c1, void* raw1, float* st1, void* raw2, float* st2,
                          void* out, bool identity) {
@@ -966,18 +967,17 @@ struct PlanBuilder {
         const std::string rn = kResnetNames[r];
         add_mask_mul(lvl, Co, g_out, gpre);
         release(g_out);
-        add_gn_bwd(lvl, Co, raw2, st2, R.b2, gpre, g_raw2);
+        const std::string pb2 = rn + ".block2", pb1 = rn + ".block1";
+        add_gn_bwd(lvl, Co, raw2, st2, R.b2, gpre, g_raw2, pgrads ? &pb2 : nullptr);
         if (pgrads) {
-            add_gn_param_grads(rn + ".block2", lvl, Co, raw2, st2, R.b2, gpre);
             add_conv_param_grads(rn + ".block2.block.0", geom_3x3(B, H[lvl], W[lvl], Co, 0, Co, 1), g_raw2, a1_of[r], nullptr, 0);
         }
         add_bconv("dgrad3", geom_3x3(B, H[lvl], W[lvl], Co, 0, Co, 1), g_raw2, Bw.d2, nullptr, g_a1);
         release(g_raw2);
         void* g_raw1 = act(lvl, Co);                          // a1 = (Mish(GN(raw1)) + time bias) * mask
         if (failed) return;
-        add_gn_bwd(lvl, Co, raw1, st1, R.b1, g_a1, g_raw1);
+        add_gn_bwd(lvl, Co, raw1, st1, R.b1, g_a1, g_raw1, pgrads ? &pb1 : nullptr);
         if (pgrads) {
-            add_gn_param_grads(rn + ".block1", lvl, Co, raw1, st1, R.b1, g_a1);
             {   // time bias: d tb[b][c] = sum_p g_a1[b][p][c] * mask
                 float* part = (float*)pooled((size_t)B * 64 * Co * 4);
                 if (failed) return;
@@ -1399,9 +1399,9 @@ struct PlanBuilder {
                 int Bb = B, Hh = H[0], Ww = W[0];
                 pl->push("bwd_final", 0, 0.0, 0.0, [k, v, wf, m, ghf, Bb, Hh, Ww](cudaStream_t s) { return final_bwd(k, v, wf, m, ghf, Bb, Hh, Ww, s); });
             }
-            add_gn_bwd(0, 64, rawf, stf, P->final_block, ghf, g_rawf);
+            const std::string pfb = "final_block";
+            add_gn_bwd(0, 64, rawf, stf, P->final_block, ghf, g_rawf, pgrads ? &pfb : nullptr);
             if (pgrads) {
-                add_gn_param_grads("final_block", 0, 64, rawf, stf, P->final_block, ghf);
                 add_conv_param_grads("final_block.block.0", geom_3x3(B, H[0], W[0], 64, 0, 64, 1), g_rawf, x, nullptr, 0);
                 // final_conv (64 -> 1): dwf[c] = sum v * mask * hf[c], dbf = sum v * mask
                 float* part = (float*)pooled((size_t)256 * 65 * 4);

@@ -223,8 +223,12 @@ struct GnBwdArgs {
     const void* gy;                             // gradient w.r.t. the Block output (NHWC act)
     void* graw;                                 // out: gradient w.r.t. the conv output (NHWC act)
     float* partials;                            // scratch [B][gn_bwd_blocks][16]
+    float* param_partials;                      // optional scratch [B][gn_bwd_blocks][2C]: per-channel d gamma | d beta partial sums,
+                                                // produced by the same pass over (raw, gy) as the group sums (training plans)
     int B, H, W, C;
 };
+// fixed-order sum of the param_partials rows of gn_bwd into d gamma [C], d beta [C]
+int gn_param_reduce(const float* param_partials, float* dgamma, float* dbeta, int B, int H, int W, int C, cudaStream_t s);
 int gn_bwd_blocks(int H, int W);
 int gn_bwd(ActKind act, const GnBwdArgs& a, cudaStream_t s);
 int final_bwd(ActKind act, const float* v, const float* wf, const float* mask, void* ghf, int B, int H, int W, cudaStream_t s);
@@ -270,7 +274,6 @@ int conv_wgrad(ActKind act, const ConvGeom& g, const void* gout, const void* x0,
 int col_sums(ActKind act, const void* gsrc, float* partial, float* dst, long npix, int C, float scale, int accumulate, cudaStream_t s);
 int col_sums_per_sample(ActKind act, const void* gsrc, const float* mask, float* partial, float* dst, int B, int H, int W, int C, int dst_ld,
                         cudaStream_t s);
-int gn_param_grad(ActKind act, const GnBwdArgs& a, float* partial, float* dgamma, float* dbeta, cudaStream_t s);
 int attn_out_grads(const float* A, const float* sv, const float* wout, const float* bout, float g, float* dwout, float* dbout, float* dg,
                    int C, cudaStream_t s);
 int accumulate_floats(float* dst, const float* src, size_t n, int accumulate, cudaStream_t s);
