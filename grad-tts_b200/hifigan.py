@@ -103,6 +103,7 @@ class Generator(nn.Module):
         self._handle = None
         self._handle_dev = None
         self._uploaded = None
+        self._plist = None
         self._opts = {}
 
     # ------------------------------------------------------------------------------------------------ reference API
@@ -110,6 +111,7 @@ class Generator(nn.Module):
         for m in self.modules():
             if isinstance(m, _WNConv):
                 m.remove_weight_norm()
+        self._plist = None
 
     def forward(self, x):
         """mel (B, 80, T) -> waveform (B, 1, T * prod(upsample_rates)), models.py:101-118."""
@@ -145,7 +147,15 @@ class Generator(nn.Module):
                 yield name, m
 
     def _signature(self):
-        return tuple((n, p.data_ptr(), p._version) for n, p in self.named_parameters())
+        # flat list cached (the module-tree walk over 150 tensors costs more than the call at one utterance); weight norm on / off
+        # and .to() / .cuda() change the Parameter objects and reset it
+        if self._plist is None:
+            self._plist = list(self.parameters())
+        return tuple((id(p), p.data_ptr(), p._version) for p in self._plist)
+
+    def _apply(self, fn, *a, **k):
+        self._plist = None
+        return super()._apply(fn, *a, **k)
 
     def _release(self):
         if self._handle is not None:

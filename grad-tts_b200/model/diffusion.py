@@ -193,7 +193,10 @@ class GradLogPEstimator2d(BaseModule):
             self._handle = None
 
     def __del__(self):
-        self._release()
+        try:
+            self._release()
+        except Exception:                  # interpreter shutdown: torch's module machinery may already be gone
+            pass
 
     def __getstate__(self):
         d = self.__dict__.copy()          # the native handle is per-process: never pickled / deep-copied

@@ -101,6 +101,11 @@ class TextEncoder(BaseModule):
         self._handle = None
         self._handle_dev = None
         self._uploaded = None
+        self._plist = None
+
+    def _apply(self, fn, *a, **k):          # .to() / .cuda() may replace the Parameter objects
+        self._plist = None
+        return super()._apply(fn, *a, **k)
 
     @torch.no_grad()
     def forward(self, x, x_lengths, spk=None):
@@ -160,7 +165,9 @@ class TextEncoder(BaseModule):
                                          int(self.spk_emb_dim), int(self.n_spks), dev)
             _lib.check(rc, "encoder_create")
             self._handle, self._handle_dev, self._uploaded = h, dev, None
-        sig = tuple((n, p.data_ptr(), p._version) for n, p in self.named_parameters())
+        if self._plist is None:            # flat list cached: the module-tree walk costs more than the call at one utterance
+            self._plist = list(self.parameters())
+        sig = tuple((id(p), p.data_ptr(), p._version) for p in self._plist)
         if self._uploaded != sig:
             torch.cuda.current_stream(p0.device).synchronize()
             for name, p in self.named_parameters():
