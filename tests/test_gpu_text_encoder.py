@@ -116,3 +116,25 @@ def test_gradtts_forward_with_native_encoder_matches_injected_oracle_encoder(pkg
     assert float((enc_a - enc_b).abs().max()) <= MAX_ABS
     rel = float(((dec_a - dec_b).pow(2).mean() / dec_b.pow(2).mean()).sqrt())
     assert rel <= 2e-2, rel
+
+
+def test_text_encoder_c_abi_writes_only_its_outputs(pkg, synth):
+    """gtts_encoder_forward through ctypes with guard bands around the three outputs"""
+    import ctypes
+    enc, cfg, _ = _make(synth, "ref", 59)
+    B, T = 3, 19
+    x, lengths, _ = synth.make_text_inputs(cfg, B, T, seed=60)
+    xd, ld = x.cuda(), lengths.cuda()
+    mu, logw, x_mask = enc(xd, ld)
+    guard = 1024
+    sizes = (B * 80 * T, B * T, B * T)
+    bufs = [torch.full((n + 2 * guard,), -77.0, device="cuda") for n in sizes]
+    lib = pkg._lib.load()
+    rc = lib.gtts_encoder_forward(enc._handle, xd.data_ptr(), ld.data_ptr(), None, bufs[0][guard:].data_ptr(), bufs[1][guard:].data_ptr(),
+                                  bufs[2][guard:].data_ptr(), B, T, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    pkg._lib.check(rc, "encoder_forward")
+    torch.cuda.synchronize()
+    for buf, n, ref in zip(bufs, sizes, (mu, logw, x_mask)):
+        assert torch.equal(buf[guard:guard + n], ref.reshape(-1))
+        assert bool((buf[:guard] == -77.0).all()) and bool((buf[guard + n:] == -77.0).all())
+    assert torch.equal(xd.cpu(), x)

@@ -186,3 +186,22 @@ def test_vocoder_full_length_utterance_against_oracle(pkg, synth):
     gen.precision = "fp32"
     y = gen(mel.cuda()).cpu()
     assert float((y - ref).abs().max()) <= FP32_MAX_ABS
+
+
+def test_vocoder_c_abi_writes_only_its_output(pkg, synth):
+    """gtts_vocoder_forward through ctypes with guard bands around the output and an untouched-input check"""
+    gen, cfg, _ = _make(pkg, synth, "v1", 39)
+    B, T = 2, 21
+    mel = synth.make_mel(B, T, seed=9).cuda()
+    want = gen(mel)
+    mel_copy = mel.clone()
+    n, guard = B * T * gen.hop, 4096
+    buf = torch.full((n + 2 * guard,), -123.0, device="cuda")
+    lib = pkg._lib.load()
+    rc = lib.gtts_vocoder_forward(gen._handle, mel.data_ptr(), buf[guard:].data_ptr(), B, T, 0,
+                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    pkg._lib.check(rc, "vocoder_forward")
+    torch.cuda.synchronize()
+    assert torch.equal(buf[guard:guard + n].view(B, 1, -1), want)
+    assert bool((buf[:guard] == -123.0).all()) and bool((buf[guard + n:] == -123.0).all())
+    assert torch.equal(mel, mel_copy)
