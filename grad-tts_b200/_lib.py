@@ -32,6 +32,8 @@ SIGNATURES = {
     "gtts_decoder_estimator_vjp": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "gtts_decoder_estimator_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "gtts_decoder_get_param_grad": (_i, [_vp, _cp, _vp, _sz, _vp]),
+    "gtts_decoder_param_grad_slot": (_i, [_vp, _cp, _c.POINTER(_sz), _c.POINTER(_sz)]),
+    "gtts_decoder_get_param_grads_flat": (_i, [_vp, _vp, _sz, _vp]),
     "gtts_decoder_reverse_diffusion_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
     "gtts_decoder_profile_step": (_i, [_vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "gtts_decoder_launches_last_call": (_l, [_vp]),

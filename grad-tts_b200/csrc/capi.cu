@@ -187,6 +187,16 @@ int gtts_decoder_get_param_grad(gtts_decoder* h, const char* name, float* dst, s
     return decoder_get_param_grad(h->impl, name, dst, numel, (cudaStream_t)stream);
 }
 
+int gtts_decoder_get_param_grads_flat(gtts_decoder* h, float* dst, size_t numel, void* stream) {
+    GTTS_REQUIRE(h != nullptr, "null decoder handle");
+    return decoder_get_param_grads_flat(h->impl, dst, numel, (cudaStream_t)stream);
+}
+
+int gtts_decoder_param_grad_slot(const gtts_decoder* h, const char* name, size_t* offset, size_t* numel) {
+    GTTS_REQUIRE(h != nullptr, "null decoder handle");
+    return decoder_param_grad_slot(h->impl, name, offset, numel);
+}
+
 int gtts_decoder_reverse_diffusion_host(gtts_decoder* h, const float* z_host, const float* mask_host,
                                         const float* mu_host, const float* spk_host, float* out_host, int B, int T,
                                         int n_timesteps, int flags) {

@@ -1759,6 +1759,24 @@ int decoder_get_param_grad(Decoder* d, const char* name, float* dst, size_t nume
     return leave_call(d, stream);
 }
 
+// all parameter gradients in one copy: dst[offset(name) .. offset(name) + numel(name)) in the layout decoder_param_grad_slot reports
+int decoder_get_param_grads_flat(Decoder* d, float* dst, size_t numel, cudaStream_t stream) {
+    GTTS_REQUIRE(d != nullptr && dst != nullptr, "null argument");
+    GTTS_REQUIRE(d->pg_accum != nullptr && numel == d->pg_floats, "get_param_grads_flat: wrong size, or no backward call yet");
+    if (int rc = enter_call(d, stream)) return rc;
+    GTTS_CHECK_CUDA(cudaMemcpyAsync(dst, d->pg_accum, numel * 4, cudaMemcpyDeviceToDevice, stream));
+    return leave_call(d, stream);
+}
+// offset and size (floats) of one parameter's gradient in the flat buffer; total size with name == nullptr
+int decoder_param_grad_slot(const Decoder* d, const char* name, size_t* offset, size_t* numel) {
+    GTTS_REQUIRE(d != nullptr && offset != nullptr && numel != nullptr, "null argument");
+    if (name == nullptr) { *offset = 0; *numel = d->pg_floats; return 0; }
+    auto it = d->pg_layout.find(name);
+    GTTS_REQUIRE(it != d->pg_layout.end(), "param_grad_slot: this parameter has no device-side gradient");
+    *offset = it->second.first; *numel = it->second.second;
+    return 0;
+}
+
 // Runs one step of the cached sampler plan for (B<=max_chunk, T) eagerly, `reps` times, with a CUDA event pair
 // around every launch; writes a JSON report {ops:[{name,is_conv,flops,bytes,ms}...]} into buf.
 int decoder_profile_step(Decoder* d, int B, int T, int flags, int reps, char* buf, size_t buflen, cudaStream_t stream) {

@@ -20,6 +20,8 @@ int decoder_estimator_backward(Decoder* d, const float* x, const float* mask, co
                                const float* v, float* out_score, float* out_gx, float* out_gmu, float* out_gs_pix, float* out_gtb, int B,
                                int T, int flags, cudaStream_t stream);
 int decoder_get_param_grad(Decoder* d, const char* name, float* dst, size_t numel, cudaStream_t stream);
+int decoder_get_param_grads_flat(Decoder* d, float* dst, size_t numel, cudaStream_t stream);
+int decoder_param_grad_slot(const Decoder* d, const char* name, size_t* offset, size_t* numel);
 int decoder_profile_step(Decoder* d, int B, int T, int flags, int reps, char* buf, size_t buflen, cudaStream_t stream);
 long decoder_launches_last_call(const Decoder* d);
 int decoder_cache_info(const Decoder* d, long long* out, int n);

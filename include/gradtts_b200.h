@@ -131,6 +131,11 @@ int gtts_decoder_estimator_backward(gtts_decoder* d, const float* x, const float
                                     const float* v, float* out_score, float* out_gx, float* out_gmu, float* out_gs_pix, float* out_gtb,
                                     int B, int T, int flags, void* stream);
 int gtts_decoder_get_param_grad(gtts_decoder* d, const char* name, float* dst, size_t numel, void* stream);
+/* The same gradients in ONE copy: gtts_decoder_param_grad_slot gives a parameter's offset and size (floats) in the flat buffer
+ * (name == NULL: offset 0 and the total size; valid after the first estimator_backward call on the handle), and
+ * gtts_decoder_get_param_grads_flat copies the whole buffer -- an optimizer step then needs one device copy, not 172. */
+int gtts_decoder_param_grad_slot(const gtts_decoder* d, const char* name, size_t* offset, size_t* numel);
+int gtts_decoder_get_param_grads_flat(gtts_decoder* d, float* dst, size_t numel, void* stream);
 /* Host-buffer variant of reverse_diffusion: copies inputs H2D, runs, copies the mel D2H, synchronises. */
 int gtts_decoder_reverse_diffusion_host(gtts_decoder* d, const float* z_host, const float* mask_host,
                                         const float* mu_host, const float* spk_host, float* out_host, int B, int T,
