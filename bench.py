@@ -804,10 +804,27 @@ def vocoder_record(pkg, torch, dev, decoder_fps):
         flops += sum(2.0 * L * ch * ch * rk * 2 * len(rd) for rk, rd in zip(cfg["resblock_kernel_sizes"], cfg["resblock_dilation_sizes"]))
     flops += 2.0 * L * ch * 7
     out["gflop_per_frame"] = flops / 1e9
+    # algorithmic HBM bytes per mel frame of the layer-by-layer schedule (bf16 activations; weights are negligible): per stage with
+    # U = positions x channels x 2 bytes, the transposed conv reads its input and writes x and lrelu(x); a (c1, c2) pair moves
+    # 2U + 4U (3U when it is the resblock's last and lrelu(x) is not needed); the 3-way sum reads 3U and writes U
+    Lp, chp, abytes = 1, cfg["upsample_initial_channel"], 2.0 * (80 * 4 + cfg["upsample_initial_channel"] * 2)
+    for u in cfg["upsample_rates"]:
+        prev = Lp * chp * 2.0
+        Lp, chp = Lp * u, chp // 2
+        U = Lp * chp * 2.0
+        nd = len(cfg["resblock_dilation_sizes"][0])
+        abytes += prev + 2 * U + len(cfg["resblock_kernel_sizes"]) * (nd * 6 * U - U) + (len(cfg["resblock_kernel_sizes"]) + 1) * U
+    abytes += Lp * chp * 2.0 + Lp * 4.0
+    out["algorithmic_hbm_bytes_per_frame"] = abytes
     out["bf16"] = {"ms": ms, "value": Bv * T_ / (ms * 1e-3), "launches": gen.launches_last_call(), "output_finite": bool(torch.isfinite(y).all()),
                    "audio_seconds_per_second": Bv * T_ * 256 / 22050 / (ms * 1e-3),
                    "model_tflops": flops * Bv * T_ / (ms * 1e-3) / 1e12,
-                   "frac_of_bf16_peak": flops * Bv * T_ / (ms * 1e-3) / 1e12 / peaks()[0]}
+                   "frac_of_bf16_peak": flops * Bv * T_ / (ms * 1e-3) / 1e12 / peaks()[0],
+                   "roofline": {"bound": "hbm", "achieved": abytes * Bv * T_ / (ms * 1e-3) / 1e9, "peak": peaks()[1], "unit": "GB/s",
+                                "frac": abytes * Bv * T_ / (ms * 1e-3) / 1e9 / peaks()[1],
+                                "traffic_note": "profiles/r02_ncu_vocoder.csv: 81.3 GB of DRAM traffic per 16 x 1720 frames "
+                                                "(dram__bytes_read + write over the 82 conv / point-wise launches) vs the "
+                                                "algorithmic figure above"}}
     # end to end with host buffers through the C ABI (H2D of the mels, D2H of the waveforms inside the timed region)
     mel_h = mel.pin_memory()
     wav_h = torch.empty(Bv, 1, T_ * 256).pin_memory()
