@@ -61,6 +61,7 @@ SIGNATURES = {
     "gtts_score_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _i, _i, _i, _d, _d, _vp]),
     "gtts_test_conv_apply": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "gtts_test_attn_xk": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "gtts_test_attn_fold": (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _vp]),
     "gtts_test_issue_microbench": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp]),
     "gtts_test_conv": (_i, [_i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
 }

@@ -590,6 +590,152 @@ attn_fold_kernel(const float* __restrict__ ctxn, const float* __restrict__ wout,
     }
 }
 
+
+// Batched variant of attn_fold_kernel (B >= kFoldWideMinB): the 16-row tiles above re-do phase 1 for every 64-column tile and read
+// their operands through 4-way bank conflicts, which is free when one sample is in flight (latency-bound) and shared-memory-bound when
+// thousands of CTAs queue up (22 us per wave of CTAs at 16 x C = 256: attn_fold was 2.8 % of the Euler step at chunk 64).  Here one CTA
+// owns kR full rows of M: phase 1 runs once per row, the contexts are staged transposed ([h][e][d], conflict-free 16-byte reads), P is
+// kept transposed so that phase 2 reads it as warp-uniform broadcasts, the whole Wq is staged once with cp.async (requested together
+// with everything else the CTA reads) and each thread owns a kTR x kTC register tile.  Every output is the SAME chain of fmaf as in
+// attn_fold_kernel (e = 0..31 from zero, then hd = 0..127 from zero, then g * acc), so the two kernels agree bit for bit and the
+// choice by batch size does not break batch invariance (tests/test_gpu_kernels.py::test_attn_fold_variants_agree_bitwise).
+constexpr int kFoldWideMinB = 8;
+constexpr int kFoldHeadPitch = 32 * 36 + 4;     // [e][36] per head, +4 floats so that the four heads start in different banks
+
+template <int C> struct FoldWide {
+    static constexpr int kNch = C >= 256 ? C / 128 : 1;            // column chunks of 128 (one per group of warps)
+    static constexpr int kTC = C >= 128 ? 4 : C / 32;              // columns per lane
+    static constexpr int kTR = C >= 256 ? 8 : (C >= 128 ? 4 : 2);  // rows per thread: fewer where the matrix is small (more CTAs)
+    static constexpr int kRowGroups = 8 / kNch;                    // warps along the rows
+    static constexpr int kR = kRowGroups * kTR;                    // rows of M per CTA
+    static constexpr int kPPitch = kR + 4;
+    static constexpr size_t kSmem = (size_t)(4 * kFoldHeadPitch + kR * 132 + 128 * kPPitch + 128 * C) * sizeof(float);
+};
+
+template <typename WT, int C>
+__global__ void __launch_bounds__(256)
+attn_fold_wide_kernel(const float* __restrict__ ctxn, const float* __restrict__ wout, const float* __restrict__ wq,
+                      float g, WT* __restrict__ mb) {
+    typedef FoldWide<C> F;
+    constexpr int kR = F::kR, kTC = F::kTC, kTR = F::kTR, kPP = F::kPPitch;
+    pdl_trigger();
+    extern __shared__ __align__(16) float fold_smem[];
+    float* cs = fold_smem;                      // ctxn transposed: [h][e][d], pitch 36 per e, kFoldHeadPitch per head
+    float* ws = cs + 4 * kFoldHeadPitch;        // Wout rows co0.., [kR][h*33 + e], pitch 132
+    float* Pt = ws + kR * 132;                  // P transposed: [hd][kR], pitch kPP
+    float* qs = Pt + 128 * kPP;                 // Wq [128][C]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y, co0 = blockIdx.x * kR;
+    // Wq is a parameter, not a result of the step: its copy may start before the predecessor has finished
+#pragma unroll
+    for (int k = 0; k < (128 * C / 4) / 256; ++k) cp_async16(qs + (size_t)(tid + k * 256) * 4, wq + (size_t)(tid + k * 256) * 4);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    pdl_wait();
+    {
+        constexpr int kWl = (kR * 128 + 255) / 256;
+        float c_[16], w_[kWl];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) c_[k] = ctxn[(size_t)b * 4096 + tid + k * 256];
+#pragma unroll
+        for (int k = 0; k < kWl; ++k) { const int i = tid + k * 256; w_[k] = i < kR * 128 ? wout[(size_t)(co0 + (i >> 7)) * 128 + (i & 127)] : 0.f; }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {                                  // i = h*1024 + d*32 + e
+            const int i = tid + k * 256, h = i >> 10, d = (i >> 5) & 31, e = i & 31;
+            cs[h * kFoldHeadPitch + e * 36 + d] = c_[k];
+        }
+#pragma unroll
+        for (int k = 0; k < kWl; ++k) {
+            const int i = tid + k * 256, col = i & 127;
+            if (i < kR * 128) ws[(i >> 7) * 132 + (col >> 5) * 33 + (col & 31)] = w_[k];
+        }
+    }
+    __syncthreads();
+    {   // phase 1: thread = (row, kR/2 consecutive hd of one head)
+        constexpr int kHd = kR / 2, kG = 128 / kHd;
+        static_assert(kHd % 4 == 0 && kHd <= 32, "attn_fold_wide: rows per CTA must be 8..64");
+        const int r = tid / kG, hd0 = (tid % kG) * kHd, h = hd0 >> 5, d0 = hd0 & 31;
+        float acc[kHd];
+#pragma unroll
+        for (int j = 0; j < kHd; ++j) acc[j] = 0.f;
+        const float* wrow = ws + r * 132 + h * 33;
+        const float* crow = cs + h * kFoldHeadPitch + d0;
+#pragma unroll 4
+        for (int e = 0; e < 32; ++e) {
+            const float wv = wrow[e];
+#pragma unroll
+            for (int q = 0; q < kHd / 4; ++q) {
+                const float4 c4 = *reinterpret_cast<const float4*>(crow + e * 36 + 4 * q);
+                acc[4 * q + 0] = fmaf(wv, c4.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(wv, c4.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(wv, c4.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(wv, c4.w, acc[4 * q + 3]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kHd; ++j) Pt[(hd0 + j) * kPP + r] = acc[j];
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    {   // phase 2: warp = (row group of kTR, column chunk of 32 * kTC), lane = kTC consecutive columns
+        const int rg = warp % F::kRowGroups, ch = warp / F::kRowGroups;
+        const int col = ch * 128 + lane * kTC;
+        float acc[kTR][kTC];
+#pragma unroll
+        for (int i = 0; i < kTR; ++i)
+#pragma unroll
+            for (int j = 0; j < kTC; ++j) acc[i][j] = 0.f;
+        const float* prow = Pt + rg * kTR;
+        const float* qcol = qs + col;
+#pragma unroll 8
+        for (int hd = 0; hd < 128; ++hd) {
+            float qv[kTC], pv[kTR];
+            if (kTC == 4) {
+                const float4 q4 = *reinterpret_cast<const float4*>(qcol + hd * C);
+                qv[0] = q4.x; qv[1 % kTC] = q4.y; qv[2 % kTC] = q4.z; qv[3 % kTC] = q4.w;
+            } else {
+                const float2 q2 = *reinterpret_cast<const float2*>(qcol + hd * C);
+                qv[0] = q2.x; qv[1 % kTC] = q2.y;
+            }
+            if (kTR >= 4) {
+#pragma unroll
+                for (int i4 = 0; i4 < kTR / 4; ++i4) {
+                    const float4 p4 = *reinterpret_cast<const float4*>(prow + hd * kPP + 4 * i4);
+                    pv[(4 * i4 + 0) % kTR] = p4.x; pv[(4 * i4 + 1) % kTR] = p4.y; pv[(4 * i4 + 2) % kTR] = p4.z; pv[(4 * i4 + 3) % kTR] = p4.w;
+                }
+            } else {
+                const float2 p2 = *reinterpret_cast<const float2*>(prow + hd * kPP);
+                pv[0] = p2.x; pv[1 % kTR] = p2.y;
+            }
+#pragma unroll
+            for (int i = 0; i < kTR; ++i)
+#pragma unroll
+                for (int j = 0; j < kTC; ++j) acc[i][j] = fmaf(pv[i], qv[j], acc[i][j]);
+        }
+#pragma unroll
+        for (int i = 0; i < kTR; ++i) {
+            WT* o = mb + ((size_t)b * C + co0 + rg * kTR + i) * C + col;
+#pragma unroll
+            for (int j = 0; j < kTC; ++j) Act<WT>::st(o + j, g * acc[i][j]);
+        }
+    }
+}
+
+template <typename WT, int C>
+int attn_fold_wide_launch(const float* ctxn, const float* wout, const float* wq, float g, WT* mb, int B, cudaStream_t s) {
+    typedef FoldWide<C> F;
+    static bool set = false;
+    auto k = attn_fold_wide_kernel<WT, C>;
+    if (!set) { GTTS_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F::kSmem)); set = true; }
+    GTTS_CHECK_CUDA(launch_pdl(k, dim3(C / F::kR, B), dim3(256), F::kSmem, s, 1, ctxn, wout, wq, g, mb));
+    GTTS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename WT>
+int attn_fold_wide(const float* ctxn, const float* wout, const float* wq, float g, WT* mb, int B, int C, cudaStream_t s) {
+    if (C == 64) return attn_fold_wide_launch<WT, 64>(ctxn, wout, wq, g, mb, B, s);
+    if (C == 128) return attn_fold_wide_launch<WT, 128>(ctxn, wout, wq, g, mb, B, s);
+    return attn_fold_wide_launch<WT, 256>(ctxn, wout, wq, g, mb, B, s);
+}
+
 }  // namespace
 
 void attn_ctx_plan(int n, int* chunks, int* chunk_len) {
@@ -674,9 +820,16 @@ int attn_merge(const AttnCtxArgs& a, bool strict, cudaStream_t s) {
     return 0;
 }
 
+// variant: -1 = by batch size (the product path), 0 = 16-row tiles (latency), 1 = full-row tiles (throughput); bitwise equal results
 int attn_fold(ActKind wkind, const float* ctxn, const float* wout, const float* wq, float g, void* mb_out, int B,
-              int C, cudaStream_t s) {
+              int C, cudaStream_t s, int variant) {
     GTTS_REQUIRE(C % 64 == 0 && C <= 256, "attn_fold: C must be a multiple of 64 and <= 256");
+    const bool wide = variant < 0 ? (B >= kFoldWideMinB && (C == 64 || C == 128 || C == 256)) : variant == 1;
+    if (wide) {
+        GTTS_REQUIRE(C == 64 || C == 128 || C == 256, "attn_fold: the full-row variant needs C = 64, 128 or 256");
+        return wkind == ACT_F32 ? attn_fold_wide<float>(ctxn, wout, wq, g, (float*)mb_out, B, C, s)
+                                : attn_fold_wide<__nv_bfloat16>(ctxn, wout, wq, g, (__nv_bfloat16*)mb_out, B, C, s);
+    }
     dim3 grid(C / 16, C / 64, B);
     const size_t smem = (size_t)(128 * 33 + 2 * 16 * 129 + 128 * 64) * sizeof(float);       // ctx, Wout rows, P, Wq slice
     static bool set_f = false, set_h = false;

@@ -289,6 +289,13 @@ int gtts_test_attn_xk(const void* x_bf16, const void* wkv_bf16, float* partials,
     return rc;
 }
 
+int gtts_test_attn_fold(const float* ctxn, const float* wout, const float* wq, float g, void* m_out, int B, int C, int out_bf16,
+                        int variant, void* stream) {
+    GTTS_REQUIRE(ctxn && wout && wq && m_out && B >= 1, "null argument");
+    GTTS_REQUIRE(variant >= -1 && variant <= 1, "gtts_test_attn_fold: variant must be -1, 0 or 1");
+    return attn_fold(out_bf16 ? ACT_BF16 : ACT_F32, ctxn, wout, wq, g, m_out, B, C, (cudaStream_t)stream, variant);
+}
+
 int gtts_test_issue_microbench(int N, int n_mma, int n_commit, int iters, int wait_each, int grid, double* issue_cycles,
                                double* total_cycles) {
     GTTS_REQUIRE((N == 64 || N == 128 || N == 256) && grid >= 1 && grid <= 1024 && iters >= 1,

@@ -143,6 +143,8 @@ struct Decoder {
                               // wins where launches are latency-bound (B = 1, T = 400: 21 us vs 17 + 8.6 us per Block) and loses on big
                               // batches (chunk 16 x 1720: 128->128 @h40 249 vs 109 + 57 us) because every sample costs one grid barrier.
     int fuse_epi_max_b = 2;
+    int first_conv_mma = 1;   // bf16 mode: the first conv (2 | 3 fp32 planes -> 64 channels) on mma.sync with hi + lo split inputs and bf16
+                              // weights (pointwise.cu: first_conv_mma_kernel); 0 = the FFMA kernel with fp32 weights (GTTS_FIRST_CONV_MMA=0)
     int pdl_small = 1;        // small-batch sampler plans are captured with programmatic dependent launch (GTTS_PDL_SMALL=0: off)
     int wgrad_tc = 1;         // bf16 training plan: weight gradients of the stride-1 convs on tcgen05 (wgrad_tc.cu); 0 = mma.sync kernel
     int side_lanes = 1;       // small batches: time-embedding MLP and res_conv on a parallel branch of the step graph (GTTS_SIDE=0: off)
@@ -778,6 +780,7 @@ struct PlanBuilder {
             memset(&f, 0, sizeof(f));
             f.mu = pl->mu; f.x = pl->xt; f.splane = pl->splane; f.mask = lmask[0];
             f.w = P->first_wT; f.bias = P->first_b; f.B = B; f.H = H[0]; f.W = W[0]; f.cin = d->cin_first;
+            f.use_mma = d->first_conv_mma;
             f.raw = raw1; f.gn_partials = pl->partials; f.gn_stats = st1; f.gn_counters = pl->counters; f.gn_eps = 1e-5f;
             if (first_conv_partials_slots(H[0], W[0]) > pl->partial_slots) { set_error("internal: GN partial buffer too small"); failed = true; return nullptr; }
             ActKind k = kind;
@@ -1539,7 +1542,7 @@ int get_plan(Decoder* d, ActKind kind, int B, int T, bool est_mode, bool sde, cu
                       (est_mode ? "e" : "s") + (sde ? "n" : "o") + (vjp ? (pgrads ? "p" : "v") : "-") + (d->use_graph ? "g" : "x") +
                       std::to_string(d->conv_impl_bf16) + std::to_string(d->halo_mode) + std::to_string(d->fused_attn) + std::to_string(d->fuse_gn) +
                       std::to_string(d->fuse_epi) + "." + std::to_string(d->fuse_epi_max_b) + "." + std::to_string(d->fp32_tc) + std::to_string(d->fuse_async) +
-                      std::to_string(d->side_lanes) + std::to_string(d->wgrad_tc) + std::to_string(d->pdl_small);
+                      std::to_string(d->side_lanes) + std::to_string(d->wgrad_tc) + std::to_string(d->pdl_small) + std::to_string(d->first_conv_mma);
     auto it = d->plans.find(key);
     if (it != d->plans.end()) {
         it->second.last_use = ++d->use_clock;
@@ -1845,6 +1848,7 @@ Decoder* decoder_new(int n_spks, int n_feats, int dim, double beta_min, double b
     if (const char* e = getenv("GTTS_SIDE")) d->side_lanes = atoi(e);
     if (const char* e = getenv("GTTS_WGRAD_TC")) d->wgrad_tc = atoi(e);
     if (const char* e = getenv("GTTS_PDL_SMALL")) d->pdl_small = atoi(e);
+    if (const char* e = getenv("GTTS_FIRST_CONV_MMA")) d->first_conv_mma = atoi(e);
     if (cudaEventCreateWithFlags(&d->done_ev, cudaEventDisableTiming) != cudaSuccess) {
         set_error("cudaEventCreate failed"); cudaGetLastError(); delete d; return nullptr;
     }
@@ -1898,6 +1902,7 @@ int decoder_set_option(Decoder* d, const char* key, int value) {
     else if (k == "side_lanes") d->side_lanes = value;
     else if (k == "wgrad_tc") d->wgrad_tc = value;
     else if (k == "pdl_small") d->pdl_small = value;
+    else if (k == "first_conv_mma") d->first_conv_mma = value;
     else { set_error("unknown option " + k); return 2; }
     return 0;
 }

@@ -140,6 +140,7 @@ struct FirstConvArgs {
     const float* w;                                         // [27|18][64]  (k = (ci*3+ky)*3+kx, transposed)
     const float* bias;                                      // [64]
     int B, H, W, cin;
+    int use_mma;                                            // bf16 activations: 1 = tensor-core kernel (bf16 weights, split inputs)
     void* raw;                                              // NHWC act
     float* gn_partials; float* gn_stats; unsigned int* gn_counters; float gn_eps;
 };
@@ -199,7 +200,7 @@ int attn_xk(const void* x, const void* wkv_bf16 /*[256][C]*/, float* partials, i
 int attn_xk_tc(const void* x, const void* wkv_bf16, float* partials, int B, int n, int C, int chunks, int chunk_len, cudaStream_t s);
 // per-sample folded weights M_b = g * Wout * blockdiag(ctxn^T) * Wq  -> [B*C][C] in weight type
 int attn_fold(ActKind wkind, const float* ctxn, const float* wout /*[C][128]*/, const float* wq /*[128][C]*/,
-              float g, void* mb_out, int B, int C, cudaStream_t s);
+              float g, void* mb_out, int B, int C, cudaStream_t s, int variant = -1 /* test hook: 0 / 1 force a kernel */);
 
 // alignment stage around MAS (align.cu): log-prior (tts.py:143-149), durations and aligned means (tts.py:155,184-185)
 int align_log_prior(const float* mu_x, const float* y, float* log_prior, int B, int C, int tx, int ty, cudaStream_t s);

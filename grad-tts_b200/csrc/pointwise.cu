@@ -278,6 +278,161 @@ first_conv_kernel(FirstConvArgs a) {
     gn_stats_publish(go, b, blockIdx.x, tid, 128, s_tile, s_red, &s_flag, [] { __syncthreads(); });
 }
 
+// ------------------------------------------------------------------------------------------------ first conv, bf16 mode
+// The FFMA kernel above is bound by its shared-memory weight reads (168 us at 16 x 80 x 1720 against a 47 us store floor).  In bf16
+// mode the weights are bf16 like those of every other conv, so the K = 18 | 27 contraction goes to the tensor cores as
+// mma.sync.m16n8k16 (too thin for a tcgen05 tile pipeline: 2-4 k-steps per pixel group).  The fp32 inputs stay fp32-accurate: every
+// staged value is split into bf16 hi + lo halves packed in ONE 32-bit shared-memory word, and K runs over (tap, half) pairs with
+// the tap's weight in both B rows, so a single LDS.32 is a whole A register and x = hi + lo enters with ~16 mantissa bits.
+// The B columns are permuted (column c of n-tile n <-> channel 16 (c >> 1) + 2n + (c & 1)) so that the accumulators of lane t
+// are the 16 CONSECUTIVE channels 16t..16t+15 of its two pixels: one 32-byte store per pixel, and GroupNorm groups 2t, 2t+1.
+// The weights live in registers for the whole CTA (48 | 64 per thread).  Grid, window staging and the statistics hand-off are those
+// of first_conv_kernel.
+__device__ __forceinline__ void fc_mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t fc_split(float v) {        // low half = bf16(v), high half = bf16(v - bf16(v))
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    return (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(128)
+first_conv_mma_kernel(FirstConvArgs a) {
+    constexpr int kTaps = CIN * 9, kSteps = (kTaps * 2 + 15) / 16;      // k = 2 * tap + half
+    constexpr int kPitch = kFcSpan + 6;
+    pdl_trigger();
+    pdl_wait();
+    __shared__ __align__(16) uint32_t s_in[CIN * 3 * kPitch + 16];      // [plane][row][i]: element i + 3 <-> pixel P0 - 1 + i
+    __shared__ __align__(16) float sb[64];
+    __shared__ float s_tile[16];
+    __shared__ float s_part[4][16];
+    __shared__ double s_red[8 * 16];
+    __shared__ int s_flag;
+    const int tid = threadIdx.x, b = blockIdx.y, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int H = a.H, W = a.W, HW = H * W;
+    const int P0 = blockIdx.x * (kFcTiles * 128);
+
+    // weights: B fragments of all n-tiles and k-steps; rows (2t, 2t+1) <-> tap 8s + t, rows (2t+8, 2t+9) <-> tap 8s + t + 4
+    uint32_t bfrag[kSteps][8][2];
+#pragma unroll
+    for (int s = 0; s < kSteps; ++s)
+#pragma unroll
+        for (int n = 0; n < 8; ++n)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int j = 8 * s + t + 4 * hh, ch = 16 * (g >> 1) + 2 * n + (g & 1);
+                const float wv = j < kTaps ? __ldg(a.w + j * 64 + ch) : 0.f;
+                const uint32_t wb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(wv));
+                bfrag[s][n][hh] = wb | (wb << 16);
+            }
+    if (tid < 64) sb[tid] = a.bias[tid];
+    {   // input window, masked, split and packed (see first_conv_kernel for the staging scheme)
+        const float* mrow = a.mask + (size_t)b * W;
+        const float* mup = a.mu + (size_t)b * HW;
+        const float* xp = a.x + (size_t)b * HW;
+        constexpr int kIt = (kFcSpan + 127) / 128;
+        float mv[kIt], v[kIt][CIN * 3];
+#pragma unroll
+        for (int k = 0; k < kIt; ++k) {
+            const int i = tid + k * 128, p = P0 - 1 + i;
+            const bool okp = i < kFcSpan && p >= 0 && p < HW;
+            mv[k] = okp ? mrow[p % W] : 0.f;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int qq = p + (r - 1) * W;
+                const bool ok = okp && qq >= 0 && qq < HW;
+                v[k][r] = ok ? mup[qq] : 0.f;
+                v[k][3 + r] = ok ? xp[qq] : 0.f;
+                if (CIN == 3) v[k][CIN * 3 - 3 + r] = ok ? a.splane[b * H + qq / W] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kIt; ++k) {
+            const int i = tid + k * 128;
+            if (i < kFcSpan) {
+#pragma unroll
+                for (int c = 0; c < CIN * 3; ++c) s_in[c * kPitch + i + 3] = fc_split(v[k][c] * mv[k]);
+            }
+        }
+    }
+    // my taps: shared-memory offset of (plane, row, kx) relative to the pixel's slot, and kx for the column-border test
+    int toff[kSteps][2], tkx[kSteps][2];
+#pragma unroll
+    for (int s = 0; s < kSteps; ++s)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int j = 8 * s + t + 4 * hh;
+            const bool okj = j < kTaps;
+            const int ci = j / 9, ky = (j - ci * 9) / 3, kx = j - ci * 9 - ky * 3;
+            toff[s][hh] = okj ? (ci * 3 + ky) * kPitch + 3 + kx : -1;
+            tkx[s][hh] = okj ? kx : 1;
+        }
+    __syncthreads();
+
+    float st[4] = {0.f, 0.f, 0.f, 0.f};                   // sums of groups 2t, 2t+1, then their sums of squares
+    const int wbase = P0 % W;
+    for (int grp = warp; grp < kFcTiles * 8; grp += 4) {
+        const int local = grp * 16;
+        if (P0 + local >= HW) break;                       // H * W is a multiple of 16: groups are whole
+        const int pl0 = local + g, pl1 = pl0 + 8;
+        const int w0 = (wbase + pl0) % W, w1 = (wbase + pl1) % W;
+        float acc[8][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const float2 bb = *reinterpret_cast<const float2*>(&sb[16 * t + 2 * n]);
+            acc[n][0] = bb.x; acc[n][1] = bb.y; acc[n][2] = bb.x; acc[n][3] = bb.y;
+        }
+#pragma unroll
+        for (int s = 0; s < kSteps; ++s) {
+            uint32_t af[4];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int off = toff[s][hh], kx = tkx[s][hh];
+                const bool in0 = off >= 0 && !(kx == 0 && w0 == 0) && !(kx == 2 && w0 == W - 1);
+                const bool in1 = off >= 0 && !(kx == 0 && w1 == 0) && !(kx == 2 && w1 == W - 1);
+                af[2 * hh + 0] = in0 ? s_in[off + pl0] : 0u;
+                af[2 * hh + 1] = in1 ? s_in[off + pl1] : 0u;
+            }
+#pragma unroll
+            for (int n = 0; n < 8; ++n) fc_mma_16816(acc[n], af, bfrag[s][n][0], bfrag[s][n][1]);
+        }
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.raw) + ((size_t)b * HW + P0) * 64 + 16 * t;
+        uint32_t w0w[8], w1w[8];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[n][0], acc[n][1]);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(acc[n][2], acc[n][3]);
+            w0w[n] = *reinterpret_cast<uint32_t*>(&h0);
+            w1w[n] = *reinterpret_cast<uint32_t*>(&h1);
+            const int k = n >> 2;                          // channels 16t + 2n, +1: group 2t + (n >> 2)
+            st[k] += (acc[n][0] + acc[n][1]) + (acc[n][2] + acc[n][3]);
+            st[2 + k] = fmaf(acc[n][0], acc[n][0], st[2 + k]); st[2 + k] = fmaf(acc[n][1], acc[n][1], st[2 + k]);
+            st[2 + k] = fmaf(acc[n][2], acc[n][2], st[2 + k]); st[2 + k] = fmaf(acc[n][3], acc[n][3], st[2 + k]);
+        }
+        st_global_256(o + (size_t)pl0 * 64, w0w);
+        st_global_256(o + (size_t)pl1 * 64, w1w);
+    }
+    // GroupNorm statistics over the unmasked conv output: fixed butterfly over the 8 pixel lanes, then the 4 warps in order
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int o = 16; o >= 4; o >>= 1) st[k] += __shfl_xor_sync(0xffffffffu, st[k], o);
+    }
+    if (g == 0) {
+        s_part[warp][2 * t] = st[0];     s_part[warp][2 * t + 1] = st[1];
+        s_part[warp][8 + 2 * t] = st[2]; s_part[warp][8 + 2 * t + 1] = st[3];
+    }
+    __syncthreads();
+    if (tid < 16) s_tile[tid] = (s_part[0][tid] + s_part[1][tid]) + (s_part[2][tid] + s_part[3][tid]);
+    __syncthreads();
+    GnStatsOut go{a.gn_partials, a.gn_stats, a.gn_counters, (int)gridDim.x, 1.0f / (8.0f * H * W), a.gn_eps};
+    gn_stats_publish(go, b, blockIdx.x, tid, 128, s_tile, s_red, &s_flag, [] { __syncthreads(); });
+}
+
 // ------------------------------------------------------------------------------------------------ GN apply
 // grid (blocks per sample, B).  Each thread owns one 8-channel vector position (fixed channels, so the affine
 // constants stay in registers) and walks kGnIter groups of kGnVec vectors; the loads of group i+1 are issued before
@@ -745,8 +900,13 @@ int first_conv(ActKind act, const FirstConvArgs& a, cudaStream_t s) {
         if (a.cin == 2) GTTS_CHECK_CUDA(launch_pdl(first_conv_kernel<float, 2>, grid, dim3(128), 0, s, 1, a));
         else            GTTS_CHECK_CUDA(launch_pdl(first_conv_kernel<float, 3>, grid, dim3(128), 0, s, 1, a));
     } else {
-        if (a.cin == 2) GTTS_CHECK_CUDA(launch_pdl(first_conv_kernel<__nv_bfloat16, 2>, grid, dim3(128), 0, s, 1, a));
-        else            GTTS_CHECK_CUDA(launch_pdl(first_conv_kernel<__nv_bfloat16, 3>, grid, dim3(128), 0, s, 1, a));
+        if (a.use_mma && (a.H * a.W) % 16 == 0) {
+            if (a.cin == 2) GTTS_CHECK_CUDA(launch_pdl(first_conv_mma_kernel<2>, grid, dim3(128), 0, s, 1, a));
+            else            GTTS_CHECK_CUDA(launch_pdl(first_conv_mma_kernel<3>, grid, dim3(128), 0, s, 1, a));
+        } else {
+            if (a.cin == 2) GTTS_CHECK_CUDA(launch_pdl(first_conv_kernel<__nv_bfloat16, 2>, grid, dim3(128), 0, s, 1, a));
+            else            GTTS_CHECK_CUDA(launch_pdl(first_conv_kernel<__nv_bfloat16, 3>, grid, dim3(128), 0, s, 1, a));
+        }
     }
     GTTS_CHECK_CUDA(cudaGetLastError());
     return 0;

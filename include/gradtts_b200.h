@@ -176,6 +176,13 @@ int gtts_test_conv_apply(int B, int H, int W, int Cin0, int Cin1, int Cout, cons
 int gtts_test_attn_xk(const void* x_bf16, const void* wkv_bf16, float* partials, int B, int n, int C, int chunks, int chunk_len,
                       int use_tc, void* stream);
 
+/* Test hook: per-sample folded attention weights M_b = g * Wout . blockdiag(ctxn_b^T) . Wq (to_out after the context einsum and
+ * to_qkv's q rows, model/diffusion.py:95-104, as one C x C matrix per sample).  ctxn: [B][4][32][32] floats (normalised contexts),
+ * wout: [C][128], wq: [128][C] floats, m_out: [B][C][C] floats (out_bf16 = 0) or bf16 (1).  variant: 0 = 16-row tiles (small
+ * batches), 1 = full-row tiles (large batches), -1 = the product path's choice by batch size; the variants agree bit for bit. */
+int gtts_test_attn_fold(const float* ctxn, const float* wout, const float* wq, float g, void* m_out, int B, int C, int out_bf16,
+                        int variant, void* stream);
+
 /* Test hook: tcgen05 issue-path micro-benchmark (cycles per CTA, averaged over `grid` CTAs): `iters` rounds of
  * {n_mma tcgen05.mma M128xNx16, n_commit tcgen05.commit}, optionally waiting on the last commit every round. */
 int gtts_test_issue_microbench(int N, int n_mma, int n_commit, int iters, int wait_each, int grid, double* issue_cycles,

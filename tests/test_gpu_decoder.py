@@ -107,6 +107,34 @@ def test_fused_gn_input_is_bitwise_equal_to_separate_pass(pkg, synth):
     assert torch.equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("n_spks,B,T", [(1, 2, 88), (247, 3, 88), (1, 1, 4), (247, 2, 1032)])
+def test_first_conv_on_tensor_cores_matches_ffma_kernel(pkg, synth, n_spks, B, T):
+    """bf16 mode, first conv of the U-Net (2 | 3 fp32 planes -> 64 channels, model/diffusion.py:181-184, 52): the mma.sync kernel
+    (bf16 weights, inputs split into bf16 hi + lo so they stay fp32-accurate; option first_conv_mma=1, the default) against the
+    FFMA kernel with fp32 weights (first_conv_mma=0).  Two bf16 runs that round differently anywhere differ by about sqrt(2) x the
+    bf16 error of either (measured 1.4e-2 rel-rms between them), so the yardstick is the fp32 mode of the same weights (within 1e-4
+    of the reference): the tensor-core variant must be as close to it as the FFMA variant is (<= 1.5x its rel-rms error, both
+    <= 2.5e-2), and close to the FFMA variant (<= 3e-2).  T = 88 / 1032 put 16-pixel groups across row ends (a wrong border
+    tap would show as an error of order 1), T = 4 is the smallest legal width."""
+    z, mask, mu, spk, _ = synth.make_inputs(B, T, n_spks, seed=33)
+    t = torch.linspace(0.2, 0.9, B)
+    args = ((z * mask).to(DEV), mask.to(DEV), mu.to(DEV), t.to(DEV), spk.to(DEV) if spk is not None else None)
+    dec32, _ = _module(pkg, synth, n_spks, 5, "fp32")
+    ref = dec32.estimator(*args).cpu()
+    outs = []
+    for mma in (1, 0):
+        dec, _ = _module(pkg, synth, n_spks, 5, "bf16")
+        dec.estimator.set_option("first_conv_mma", mma)
+        outs.append(dec.estimator(*args).cpu())
+    assert torch.isfinite(outs[0]).all()
+    rms = lambda a: float(a.pow(2).mean().sqrt())
+    e_mma, e_ffma, diff = rms(outs[0] - ref) / rms(ref), rms(outs[1] - ref) / rms(ref), rms(outs[0] - outs[1]) / rms(ref)
+    msg = f"rel-rms vs fp32 mode: mma {e_mma:.3e}, ffma {e_ffma:.3e}; between them {diff:.3e}"
+    print(msg)
+    assert e_mma <= 2.5e-2 and e_ffma <= 2.5e-2 and e_mma <= 1.5 * e_ffma + 1e-3 and diff <= 3e-2, msg
+    assert float((outs[0] - ref).abs().max()) <= 6e-2 * max(1.0, float(ref.abs().max())), msg
+
+
 def test_apply_epilogue_is_bitwise_equal_to_separate_gn_pass(pkg, synth):
     """Plan whose Block convs finish GroupNorm+Mish(+time bias / residual) in their own epilogue (fuse_epi=2: always; the default
     uses it for small batches) against the plan with the separate gn_apply pass (fuse_epi=0): the same bits -- the fused epilogue

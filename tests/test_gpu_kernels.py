@@ -145,6 +145,40 @@ def test_attn_xk_matches_reference(use_tc, C, B, n, chunks, chunk_len, scale, mo
     assert err <= 2e-2, f"use_tc={use_tc}: relative max error {err}"          # bf16 P and bf16 S
 
 
+@pytest.mark.parametrize("C", [64, 128, 256])
+@pytest.mark.parametrize("B", [1, 3, 19])
+@pytest.mark.parametrize("out_bf16", [0, 1])
+def test_attn_fold_variants_agree_bitwise(C, B, out_bf16):
+    """Folded attention weights M_b = g * Wout . blockdiag(ctx_b^T) . Wq (model/diffusion.py:95-104 applied to a per-sample matrix):
+    both kernels (16-row tiles for small batches, full-row tiles for large ones) against the fp64 formula (fp32 tolerance 1e-5
+    relative to the largest entry), and against each other BIT FOR BIT -- the product path picks one by batch size, so a sample's
+    result must not depend on which."""
+    import ctypes
+    import importlib
+    pkg = importlib.import_module("grad-tts_b200")
+    lib = pkg._lib.load()
+    g = torch.Generator().manual_seed(1000 * C + 10 * B + out_bf16)
+    ctx = torch.randn(B, 4, 32, 32, generator=g) / 6.0                 # [b][h][d][e]
+    wout = torch.randn(C, 128, generator=g) / 128 ** 0.5               # [co][h*32 + e]
+    wq = torch.randn(128, C, generator=g) / C ** 0.5                   # [h*32 + d][ci]
+    gain = 0.37
+    P = torch.einsum("che,bhde->bchd", wout.double().view(C, 4, 32), ctx.double()).reshape(B, C, 128)
+    ref = gain * P @ wq.double()
+    outs = []
+    for variant in (0, 1, -1):
+        out = torch.full((B, C, C), float("nan"), device="cuda", dtype=torch.bfloat16 if out_bf16 else torch.float32)
+        a = [t.cuda().contiguous() for t in (ctx, wout, wq)]
+        rc = lib.gtts_test_attn_fold(ctypes.c_void_p(a[0].data_ptr()), ctypes.c_void_p(a[1].data_ptr()), ctypes.c_void_p(a[2].data_ptr()),
+                                     ctypes.c_float(gain), ctypes.c_void_p(out.data_ptr()), B, C, out_bf16, variant,
+                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        pkg._lib.check(rc, "gtts_test_attn_fold")
+        torch.cuda.synchronize()
+        outs.append(out.cpu())
+    tol = (8e-3 if out_bf16 else 1e-5) * float(ref.abs().max())
+    assert float((outs[0].double() - ref).abs().max()) <= tol
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
 APPLY_CASES = [
     # name, B, H, W, Cin0, Cin1, Cout, residual (else time bias), per-sample time bias
     ("l1_128_128_tb", 3, 40, 52, 128, 0, 128, False, False),        # 3 x 21 tiles (odd count per sample): runs straddle CTA pairs
