@@ -273,6 +273,12 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
         const bool all_valid = __all_sync(0xffffffffu, valid);
         const int oh = j * p.out_step + p.oy[ph], ow = i * p.out_step + p.ox[ph];
         const size_t opix = valid ? ((size_t)b * p.Hout + oh) * p.Wout + ow : 0;
+        // Paired stores (bf16 outputs): lanes 2k and 2k+1 first write the two 32-byte sectors of lane 2k's pixel, then those of
+        // lane 2k+1's, so one store instruction touches 16 lines instead of 32.  The row-per-thread pattern made the 1x1 / N = 64
+        // kernels L1TEX-bound (ncu: l1tex throughput 77-90 % at 52-66 % of DRAM bandwidth, profiles/r02_ncu_thin_convs.md).
+        constexpr bool kPairSt = !kOutF32 && !kAct && !kStats;   // (the statistics variants have no registers to spare: ptxas spills)
+        const size_t opix_p = kPairSt ? __shfl_xor_sync(0xffffffffu, (unsigned long long)opix, 1) : 0;
+        const bool valid_p = kPairSt ? __shfl_xor_sync(0xffffffffu, (int)valid, 1) != 0 : false;
         float m = 1.0f;
         if (kMask) m = valid ? e.mask[(size_t)b * p.Wout + ow] : 0.f;
         const float2 m2 = make_float2(m, m);
@@ -356,6 +362,46 @@ __device__ __forceinline__ void tc_epilogue_loop(const TcParams& p, const TcShar
                         w[2 * k] = __float_as_uint(o.x); w[2 * k + 1] = __float_as_uint(o.y);
                     }
                     st_global_256(op + v8 * 8, w);
+                }
+            } else if (kPairSt) {
+                uint32_t wv[2][8];
+                if (valid) {
+                    if (kRes) {
+                        const __nv_bfloat16* rp = res + opix * N + cbase + c0;
+#pragma unroll
+                        for (int v8 = 0; v8 < 2; ++v8) {             // 2 x 32 bytes = 32 bf16 residual values
+                            uint32_t w[8];
+                            ld_global_nc_256(rp + v8 * 16, w);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                f[v8 * 8 + k] = fadd2(f[v8 * 8 + k], make_float2(__uint_as_float(w[k] << 16),
+                                                                                 __uint_as_float(w[k] & 0xffff0000u)));
+                        }
+                    }
+                    if (kMask) {
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) f[q] = fmul2(f[q], m2);
+                    }
+#pragma unroll
+                    for (int v8 = 0; v8 < 2; ++v8)
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[v8 * 8 + k].x, f[v8 * 8 + k].y);
+                            wv[v8][k] = *reinterpret_cast<uint32_t*>(&h2);
+                        }
+                }
+                const bool odd = (lane & 1) != 0;
+                uint32_t rx[8];                                      // the partner's half of the pixel I store
+#pragma unroll
+                for (int k = 0; k < 8; ++k) rx[k] = __shfl_xor_sync(0xffffffffu, odd ? wv[0][k] : wv[1][k], 1);
+                __nv_bfloat16* op = out + opix * N + cbase + c0;
+                __nv_bfloat16* opp = out + opix_p * N + cbase + c0;
+                if (!(p.dbg & 64)) {
+                    uint32_t w1[8], w2[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { w1[k] = odd ? rx[k] : wv[0][k]; w2[k] = odd ? wv[1][k] : rx[k]; }
+                    if (odd ? valid_p : valid) st_global_256(odd ? opp + 16 : op, w1);        // the even lane's pixel
+                    if (odd ? valid : valid_p) st_global_256(odd ? op + 16 : opp, w2);        // the odd lane's pixel
                 }
             } else if (valid) {
                 if (kRes) {
