@@ -59,5 +59,16 @@ allk = collections.Counter()
 for c in counts.values():
     allk.update(c)
 out += ["", f"Whole library ({len(counts)} kernels): " + ", ".join(f"{k} {allk[k]}" for k in keys) + "."]
+# the legacy mma.sync path, by kernel: only where a tcgen05 tile pipeline does not pay (K of 18 / 27, 32 x 32 head matrices) or as a
+# selectable fallback next to the tcgen05 kernel
+hm = collections.OrderedDict()
+for fn, d in zip(counts, names):
+    if counts[fn]["HMMA (mma.sync)"]:
+        key = re.sub(r"<.*", "", short(d))
+        a = hm.setdefault(key, [0, 0]); a[0] += 1; a[1] += counts[fn]["HMMA (mma.sync)"]
+out += ["", "`HMMA` (mma.sync) by kernel: " + ", ".join(f"`{k}` ({n}): {c}" for k, (n, c) in hm.items()) + ".",
+        "`first_conv_mma_kernel` is the default first conv of the bf16 mode (K = 18 | 27: 2-4 k-steps per pixel group, too thin for a tcgen05",
+        "tile pipeline); the others are the mma.sync attention / weight-gradient kernels that the tcgen05 versions replaced on the default path",
+        "(`attn_xk_tc_kernel`, `wgrad_tc_kernel`) and that remain for C = 256 contexts, stride-2 / transposed weight gradients and as fallbacks."]
 open(OUT, "w").write("\n".join(out) + "\n")
 sys.stdout.write("\n".join(out) + "\n")
