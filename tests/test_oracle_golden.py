@@ -265,3 +265,57 @@ def test_text_encoder_module_has_the_reference_state_dict_layout(pkg, synth):
             enc(torch.zeros(1, 5, dtype=torch.long), torch.tensor([5]))           # CPU tensors: no fallback
     net = pkg.GradTTS(149, 1, 64, 192, 768, 256, 2, 6, 3, 0.1, 4, 80, 64, 0.05, 20.0, 1000)
     assert isinstance(net.encoder, te.TextEncoder) and net.nparams == 14835032    # the reference's parameter count
+
+
+@pytest.mark.parametrize("C", [64, 256])
+def test_attention_fold_identity_against_the_oracle(C):
+    """What `attn_fold` + the per-sample 1x1 conv compute (csrc/attention.cu, include/gradtts_b200.h: gtts_test_attn_fold):
+    Residual(Rezero(LinearAttention))(x) = (g * Wout . blockdiag(ctx_b^T) . Wq) x + g * bias + x, with ctx_b the softmax-over-positions
+    context of sample b (model/diffusion.py:90-104, 39-46).  Checked in fp64 against the oracle's restatement of the reference module,
+    with the layouts the C ABI documents (ctx [b][h][d][e], Wout [co][h*32 + e], Wq [h*32 + d][ci])."""
+    g0 = torch.Generator().manual_seed(C)
+    b, h, w, heads, dh = 2, 5, 7, 4, 32
+    p = "attn"
+    sd = {p + ".fn.fn.to_qkv.weight": torch.randn(3 * heads * dh, C, 1, 1, generator=g0, dtype=torch.float64) / C ** 0.5,
+          p + ".fn.fn.to_out.weight": torch.randn(C, heads * dh, 1, 1, generator=g0, dtype=torch.float64) / 128 ** 0.5,
+          p + ".fn.fn.to_out.bias": torch.randn(C, generator=g0, dtype=torch.float64),
+          p + ".fn.g": torch.tensor([0.37], dtype=torch.float64)}
+    x = torch.randn(b, C, h, w, generator=g0, dtype=torch.float64)
+    ref = decoder_oracle._attn_residual(sd, p, x)
+
+    wqkv = sd[p + ".fn.fn.to_qkv.weight"].view(3, heads * dh, C)
+    wq, wk, wv = wqkv[0], wqkv[1], wqkv[2]                              # rows h*32 + d
+    xf = x.view(b, C, h * w)
+    k = torch.einsum("kc,bcn->bkn", wk, xf).view(b, heads, dh, -1).softmax(dim=-1)
+    v = torch.einsum("kc,bcn->bkn", wv, xf).view(b, heads, dh, -1)
+    ctx = torch.einsum("bhdn,bhen->bhde", k, v)                         # [b][h][d][e]
+    wout = sd[p + ".fn.fn.to_out.weight"].view(C, heads, dh)            # [co][h][e]
+    gain = sd[p + ".fn.g"]
+    P = torch.einsum("che,bhde->bchd", wout, ctx).reshape(b, C, heads * dh)
+    M = gain * P @ wq                                                   # [b][co][ci]
+    got = torch.einsum("boc,bcn->bon", M, xf) + (gain * sd[p + ".fn.fn.to_out.bias"]).view(1, C, 1) + xf
+    assert float((got.view_as(ref) - ref).abs().max()) <= 1e-10 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("cin", [2, 3])
+def test_first_conv_split_arithmetic(cin):
+    """The arithmetic of the bf16-mode first conv (csrc/pointwise.cu: first_conv_mma_kernel; reference op model/diffusion.py:52 on
+    stack([mu, x, (s)]) * mask, :181-184): every fp32 input is split into bf16 hi + lo (x = hi + lo to ~2^-17 relative), the weights
+    are rounded to bf16 like those of every other conv of the bf16 mode, products are exact and summed in fp32.  Emulated on the CPU:
+    the split alone is fp32-accurate (<= 1e-4 of the output scale); with bf16 weights the error against the fp32 conv is the
+    weight rounding (<= 2^-8 relative to sum |w| |x| per output), far below the bf16 activations that follow."""
+    import torch.nn.functional as F
+    g0 = torch.Generator().manual_seed(7 + cin)
+    x = torch.randn(2, cin, 80, 24, generator=g0) * 3.0
+    w = torch.randn(64, cin, 3, 3, generator=g0) / (9 * cin) ** 0.5
+    bias = torch.randn(64, generator=g0)
+    ref = F.conv2d(x.double(), w.double(), bias.double(), padding=1)
+    hi = x.bfloat16().float()
+    lo = (x - hi).bfloat16().float()
+    assert float((hi + lo - x).abs().max()) <= 2.0 ** -16 * float(x.abs().max())
+    split_only = F.conv2d(hi.double(), w.double(), bias.double(), padding=1) + F.conv2d(lo.double(), w.double(), None, padding=1)
+    assert float((split_only - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+    wb = w.bfloat16().double()
+    got = F.conv2d(hi.double(), wb, bias.double(), padding=1) + F.conv2d(lo.double(), wb, None, padding=1)
+    bound = 2.0 ** -8 * F.conv2d(x.abs().double(), w.abs().double(), None, padding=1) + 1e-4 * float(ref.abs().max())
+    assert bool(((got - ref).abs() <= bound).all())
